@@ -1,0 +1,57 @@
+"""End-to-end: the GTV segmentation spec of Greta.pdf p.48 run by the ImgQL driver on the
+GPU, against the oracle composition of the same spec, on small BraTS-like volumes."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+NAMES_BOOL = ("background", "brain", "hyperIntense", "veryIntense", "growTum", "tumStatCC", "gtv")
+
+
+@pytest.mark.parametrize("shape,seeds", [((24, 40, 48), (1234, 7)), ((31, 50, 64), (3,))])
+def test_gtv_spec_matches_oracle(ctx, oracle, shape, seeds):
+    from gtv_ref import gtv_oracle
+    from voxlogica_b200.imgql import run_gtv
+    from voxlogica_b200.synth import brats_batch
+    vols = brats_batch(seeds, shape)
+    got = run_gtv(ctx, ctx.upload(vols))
+    for i in range(len(seeds)):
+        want = gtv_oracle(oracle, vols[i])
+        for name in NAMES_BOOL:
+            assert np.array_equal(got[name].numpy()[i], want[name]), (name, seeds[i])
+        for name in ("normFlair", "tumSim"):
+            assert np.array_equal(got[name].numpy()[i].view(np.uint32), want[name].view(np.uint32)), name
+        assert got["_printed"]["gtvVolume"][i] == want["gtv"].sum()
+    # the spec must find the lesion: a non-trivial GTV strictly inside the brain
+    g = got["gtv"].numpy()
+    assert g.sum() > 0 and np.all(g <= got["brain"].numpy())
+    assert got["_tasks"] < 60     # hash-consing: shared sub-terms evaluated once
+
+
+def test_maze_reachability_2d(ctx, oracle):
+    """BASELINE configs[0]: 2D maze, colour thresholds -> near -> through (reach)."""
+    from voxlogica_b200.imgql import run_spec
+    from voxlogica_b200.synth import maze
+    img = maze(40, seed=0)
+    r, g, b = (img[..., k].astype(np.float32) for k in range(3))
+    spec = '''
+    import "stdlib.imgql"
+    load r = "r"
+    load g = "g"
+    load b = "b"
+    let corridor = (r >. 127) & (g >. 127) & (b >. 127)
+    let start = (b >. 127) & (r <. 127)
+    let exit = (g >. 127) & (r <. 127)
+    let path = corridor | start | exit
+    let fromStart = through(start, path)
+    let reachesExit = volume(fromStart & exit)
+    let dead = corridor & !through(near(exit), corridor)
+    '''
+    for conn in (6, 26):
+        it = run_spec(ctx, spec, {k: ctx.upload(v) for k, v in (("r", r), ("g", g), ("b", b))}, conn=conn)
+        path = ((img.sum(axis=2) > 0)).astype(np.uint8)
+        start = np.zeros_like(path); start[1, 1] = 1
+        want = oracle.through(start, path, conn)
+        assert np.array_equal(it.globals["fromStart"].numpy()[0, 0], want)
+        assert it.globals["reachesExit"].v[0] == 1.0     # a perfect maze connects start and exit
+        assert it.globals["dead"].numpy().sum() == 0

@@ -1,0 +1,354 @@
+"""Parity of the CUDA operators (through the C ABI) against the CPU oracle.
+
+Bar (task section 3): bit-exact for boolean, label and index outputs; distances and
+correlations are ALSO compared bit-for-bit here because oracle and kernels share one
+arithmetic contract (see vx_edt.cu / vx_xcorr.cu headers); the 1e-5 relative tolerance
+of north_star is checked against scipy as an independent witness.
+
+Every test runs through libvoxcuda.so; the `ctx` fixture fails (never skips) when the
+extension or the device is missing.
+"""
+import numpy as np
+import pytest
+from scipy import ndimage as ndi
+
+pytestmark = pytest.mark.gpu
+
+# (nb, nz, ny, nx): aligned rows, ragged rows, 2D, single row/column, BraTS-like x extent
+SHAPES = [(2, 9, 20, 48), (1, 7, 13, 37), (3, 1, 33, 70), (1, 5, 1, 19), (1, 1, 1, 1), (2, 6, 10, 240),
+          (1, 20, 18, 32)]
+
+
+def rnd_mask(shape, p, seed):
+    return (np.random.default_rng(seed).random(shape) < p).astype(np.uint8)
+
+
+def blobs(shape, seed, sigma=2.0, q=0.55):
+    r = np.random.default_rng(seed).random(shape).astype(np.float32)
+    g = np.stack([ndi.gaussian_filter(v, sigma) for v in r])
+    return (g > np.quantile(g, q)).astype(np.uint8)
+
+
+def per_volume(fn, *arrs, **kw):
+    return np.stack([fn(*[a[i] for a in arrs], **kw) for i in range(arrs[0].shape[0])])
+
+
+# ------------------------------------------------------------------ pointwise / fused
+@pytest.mark.parametrize("shape", SHAPES)
+def test_boolean_ops(ctx, oracle, shape):
+    a, b = rnd_mask(shape, 0.4, 1), rnd_mask(shape, 0.6, 2)
+    A, B = ctx.upload(a), ctx.upload(b)
+    assert np.array_equal(ctx.not_(A).numpy(), oracle.not_(a))
+    assert np.array_equal(ctx.and_(A, B).numpy(), oracle.and_(a, b))
+    assert np.array_equal(ctx.or_(A, B).numpy(), oracle.or_(a, b))
+    assert np.array_equal(ctx.xor(A, B).numpy(), oracle.xor(a, b))
+    assert np.all(ctx.tt(A).numpy() == 1) and np.all(ctx.ff(A).numpy() == 0)
+    assert ctx.tt(A).numpy().shape == shape
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_numeric_ops(ctx, oracle, shape):
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal(shape).astype(np.float32)
+    b = rng.standard_normal(shape).astype(np.float32)
+    a.ravel()[0] = 0.5  # an exact tie with the threshold
+    A, B = ctx.upload(a), ctx.upload(b)
+    for op in ("<", "<=", ">", ">=", "==", "!="):
+        assert np.array_equal(ctx.cmp_scalar(A, op, 0.5).numpy(), oracle.cmp_scalar(a, op, 0.5)), op
+        assert np.array_equal(ctx.cmp(A, op, B).numpy(), oracle.cmp(a, op, b)), op
+    for op in ("+", "-", "*", "/", "r-", "r/", "min", "max"):
+        got, want = ctx.arith_scalar(A, op, 1.7).numpy(), oracle.arith_scalar(a, op, 1.7)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), op
+        got, want = ctx.arith(A, op, B).numpy(), oracle.arith(a, op, b)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), op
+    m = rnd_mask(shape, 0.5, 4)
+    assert np.array_equal(ctx.mask(A, ctx.upload(m), -1.0).numpy(), oracle.mask(a, m, -1.0))
+    assert np.array_equal(ctx.to_f32(ctx.upload(m)).numpy(), oracle.to_f32(m))
+    assert np.array_equal(ctx.to_bool(A).numpy(), oracle.to_bool(a))
+    assert np.all(ctx.constant(A, 2.5).numpy() == np.float32(2.5))
+
+
+def test_per_volume_scalars(ctx, oracle):
+    shape = (3, 5, 7, 11)  # 385 voxels per volume: 16-voxel groups straddle volumes
+    a = np.random.default_rng(5).random(shape).astype(np.float32)
+    s = np.array([0.2, 0.5, 0.8])
+    A = ctx.upload(a)
+    want = np.stack([oracle.cmp_scalar(a[i], ">", s[i]) for i in range(3)])
+    assert np.array_equal(ctx.cmp_scalar(A, ">", s).numpy(), want)
+    want = np.stack([oracle.arith_scalar(a[i], "/", s[i]) for i in range(3)])
+    assert np.array_equal(ctx.arith_scalar(A, "/", s).numpy(), want)
+
+
+def test_fused_program(ctx, oracle):
+    from voxlogica_b200 import _abi as A
+    shape = (2, 6, 9, 40)
+    rng = np.random.default_rng(6)
+    f = rng.random(shape).astype(np.float32)
+    g = rng.random(shape).astype(np.float32)
+    m = rnd_mask(shape, 0.5, 7)
+    # out = ((f > 0.3) & !(g <= f)) | (m ^ (f*2 - g >= 0.4))
+    prog = [
+        (A.VXP_LOAD, 0, 0, 0, 0, 0.0), (A.VXP_LOAD, 1, 1, 0, 0, 0.0), (A.VXP_LOAD, 2, 2, 0, 0, 0.0),
+        (A.VXP_CMPS, 3, 0, 0, A.VX_GT, 0.3),
+        (A.VXP_CMP, 4, 1, 0, A.VX_LE, 0.0),
+        (A.VXP_NOT, 4, 4, 0, 0, 0.0),
+        (A.VXP_AND, 3, 3, 4, 0, 0.0),
+        (A.VXP_ARITHS, 5, 0, 0, A.VX_MUL, 2.0),
+        (A.VXP_ARITH, 5, 5, 1, A.VX_SUB, 0.0),
+        (A.VXP_CMPS, 6, 5, 0, A.VX_GE, 0.4),
+        (A.VXP_XOR, 6, 2, 6, 0, 0.0),
+        (A.VXP_OR, 7, 3, 6, 0, 0.0),
+    ]
+    got = ctx.fused(prog, [ctx.upload(f), ctx.upload(g), ctx.upload(m)]).numpy()
+    t = oracle.arith(oracle.arith_scalar(f, "*", 2.0), "-", g)
+    want = oracle.or_(oracle.and_(oracle.cmp_scalar(f, ">", 0.3), oracle.not_(oracle.cmp(g, "<=", f))),
+                      oracle.xor(m, oracle.cmp_scalar(t, ">=", 0.4)))
+    assert np.array_equal(got, want)
+    # numeric root + select
+    prog2 = [(A.VXP_LOAD, 0, 0, 0, 0, 0.0), (A.VXP_LOAD, 1, 2, 0, 0, 0.0),
+             (A.VXP_ARITHS, 2, 0, 0, A.VX_ADD, 1.0), (A.VXP_SELECT, 3, 1, 2, 0, -7.0)]
+    got2 = ctx.fused(prog2, [ctx.upload(f), ctx.upload(g), ctx.upload(m)]).numpy()
+    assert np.array_equal(got2, oracle.mask(oracle.arith_scalar(f, "+", 1.0), m, -7.0))
+
+
+def test_error_convention(ctx):
+    from voxlogica_b200.ops import VoxError
+    a = ctx.upload(np.zeros((2, 3, 4), np.uint8))
+    b = ctx.upload(np.zeros((2, 3, 5), np.uint8))
+    f = ctx.upload(np.zeros((2, 3, 4), np.float32))
+    with pytest.raises(VoxError, match="SHAPE"):
+        ctx.and_(a, b)
+    with pytest.raises(VoxError, match="DTYPE"):
+        ctx.near(f)
+    with pytest.raises(VoxError, match="DTYPE"):
+        ctx.and_(a, f)
+    with pytest.raises(VoxError, match="INVALID_ARG"):
+        ctx.near(a, conn=5)
+    a.release()
+    with pytest.raises(VoxError, match="INVALID_ARG"):
+        ctx.not_(a)
+
+
+# ------------------------------------------------------------------ border / near / interior
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("conn", [6, 26])
+def test_near_interior(ctx, oracle, shape, conn):
+    for p, seed in ((0.03, 8), (0.5, 9), (0.97, 10)):
+        a = rnd_mask(shape, p, seed)
+        A = ctx.upload(a)
+        assert np.array_equal(ctx.near(A, conn).numpy(), per_volume(oracle.near, a, conn=conn)), (p, "near")
+        assert np.array_equal(ctx.interior(A, conn).numpy(), per_volume(oracle.interior, a, conn=conn)), (p, "int")
+
+
+def test_near_wide_rows(ctx, oracle):
+    """rows wider than one 16-chunk strip (256 voxels) exercise the cross-strip edge bytes"""
+    a = rnd_mask((1, 3, 5, 1040), 0.01, 11)
+    a[0, 1, 2, 255] = 1; a[0, 1, 2, 256] = 0; a[0, 2, 3, 512] = 1; a[0, 0, 0, 1039] = 1
+    A = ctx.upload(a)
+    for conn in (6, 26):
+        assert np.array_equal(ctx.near(A, conn).numpy(), per_volume(oracle.near, a, conn=conn))
+        assert np.array_equal(ctx.interior(ctx.not_(A), conn).numpy(), per_volume(oracle.interior, 1 - a, conn=conn))
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_border(ctx, oracle, shape):
+    A = ctx.upload(np.zeros(shape, np.uint8))
+    assert np.array_equal(ctx.border(A).numpy(), per_volume(oracle.border, np.zeros(shape, np.uint8)))
+
+
+# ------------------------------------------------------------------ connected components
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("conn", [6, 26])
+def test_components_and_through(ctx, oracle, shape, conn):
+    for p, seed in ((0.05, 12), (0.25, 13), (0.45, 14), (0.8, 15)):
+        b = rnd_mask(shape, p, seed)
+        a = rnd_mask(shape, 0.02, seed + 100)
+        B, Aimg = ctx.upload(b), ctx.upload(a)
+        assert np.array_equal(ctx.components(B, conn).numpy(), per_volume(oracle.components, b, conn=conn)), p
+        assert np.array_equal(ctx.through(Aimg, B, conn).numpy(), per_volume(oracle.through, a, b, conn=conn)), p
+        assert np.array_equal(ctx.maxvol(B, conn).numpy(), per_volume(oracle.maxvol, b, conn=conn)), p
+
+
+@pytest.mark.parametrize("conn", [6, 26])
+def test_components_structured(ctx, oracle, conn):
+    """blobs, long snakes and diagonal staircases: many cross-row merges per component"""
+    shape = (2, 12, 40, 96)
+    b = blobs(shape, 16)
+    z, y, x = np.indices(shape[1:])
+    b[1] = (((x + y + z) % 7 == 0) | ((x - y) % 11 == 0)).astype(np.uint8)
+    a = rnd_mask(shape, 0.001, 17)
+    B, Aimg = ctx.upload(b), ctx.upload(a)
+    assert np.array_equal(ctx.components(B, conn).numpy(), per_volume(oracle.components, b, conn=conn))
+    assert np.array_equal(ctx.through(Aimg, B, conn).numpy(), per_volume(oracle.through, a, b, conn=conn))
+    assert np.array_equal(ctx.maxvol(B, conn).numpy(), per_volume(oracle.maxvol, b, conn=conn))
+
+
+def test_components_spiral_2d(ctx, oracle):
+    """one long spiral corridor: worst case for label propagation (Greta.pdf p.78 needed
+    ~29 sweeps on a small scene); union-find must resolve it in one pass"""
+    n = 129
+    b = np.zeros((n, n), np.uint8)
+    x0, y0, x1, y1 = 0, 0, n - 1, n - 1
+    while x0 <= x1 and y0 <= y1:
+        b[y0, x0:x1 + 1] = 1; b[y0:y1 + 1, x1] = 1; b[y1, x0 + 2:x1 + 1] = 1; b[y0 + 2:y1 + 1, x0 + 2] = 1
+        x0 += 4; y0 += 4; x1 -= 4; y1 -= 4
+    for conn in (6, 26):
+        got = ctx.components(ctx.upload(b), conn).numpy()[0, 0]
+        assert np.array_equal(got, oracle.components(b, conn))
+
+
+# ------------------------------------------------------------------ distances
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("spacing", [(1.0, 1.0, 1.0), (0.5, 1.25, 3.0)])
+def test_edt(ctx, oracle, shape, spacing):
+    for p, seed in ((0.002, 18), (0.05, 19), (0.6, 20)):
+        a = rnd_mask(shape, p, seed)
+        a[0].ravel()[a[0].size // 2] = 1
+        got = ctx.edt(ctx.upload(a, spacing=spacing)).numpy()
+        want = per_volume(oracle.edt, a, spacing=spacing)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), p
+        sci = per_volume(lambda v: ndi.distance_transform_edt(1 - v, sampling=spacing[::-1]) if v.any()
+                         else np.full(v.shape, np.inf), a)
+        np.testing.assert_allclose(got, sci, rtol=1e-5)
+
+
+def test_edt_empty_volume_in_batch(ctx, oracle):
+    a = rnd_mask((3, 4, 9, 21), 0.05, 21)
+    a[1] = 0
+    got = ctx.edt(ctx.upload(a)).numpy()
+    assert np.all(np.isinf(got[1]))
+    assert np.array_equal(got, per_volume(oracle.edt, a))
+    assert np.all(ctx.distlt(2.0, ctx.upload(a)).numpy()[1] == 0)
+    assert np.all(ctx.distgeq(2.0, ctx.upload(a)).numpy()[1] == 1)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("spacing", [(1.0, 1.0, 1.0), (0.7, 1.0, 2.5)])
+def test_dist_thresholds(ctx, oracle, shape, spacing):
+    a = rnd_mask(shape, 0.01, 22)
+    A = ctx.upload(a, spacing=spacing)
+    # 5.0 and 2.0 are the GTV radii; sqrt(5), 3.0 hit exact ties; 40 forces the wide-radius path
+    for r in (2.0, 5.0, float(np.sqrt(np.float32(5.0))), 3.0, 0.0, -1.0, 40.0):
+        for name, op in (("distlt", "<"), ("distleq", "<="), ("distgeq", ">="), ("distgt", ">")):
+            got = getattr(ctx, name)(r, A).numpy()
+            want = per_volume(oracle.dist_cmp, a, op=op, r=r, spacing=spacing)
+            assert np.array_equal(got, want), (name, r)
+
+
+def test_filter_is_opening(ctx, oracle):
+    a = blobs((2, 10, 30, 48), 23)
+    A = ctx.upload(a)
+    f = ctx.distlt(2.0, ctx.distgeq(2.0, ctx.not_(A)))
+    want = np.stack([oracle.flt(2.0, v) for v in a])
+    assert np.array_equal(f.numpy(), want)
+    again = ctx.distlt(2.0, ctx.distgeq(2.0, ctx.not_(f)))
+    assert np.array_equal(again.numpy(), f.numpy())
+
+
+def test_edt_signed(ctx, oracle):
+    a = blobs((2, 8, 20, 32), 24)
+    got = ctx.edt_signed(ctx.upload(a)).numpy()
+    want = per_volume(oracle.edt_signed, a)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+# ------------------------------------------------------------------ reductions / percentiles
+@pytest.mark.parametrize("shape", SHAPES)
+def test_reductions(ctx, oracle, shape):
+    rng = np.random.default_rng(25)
+    a = rng.standard_normal(shape).astype(np.float32)
+    m = rnd_mask(shape, 0.3, 26)
+    A, M = ctx.upload(a), ctx.upload(m)
+    nb = shape[0]
+    assert np.array_equal(ctx.volume(M), [oracle.volume(m[i]) for i in range(nb)])
+    assert np.array_equal(ctx.min(A), [oracle.min_(a[i]) for i in range(nb)])
+    assert np.array_equal(ctx.max(A), [oracle.max_(a[i]) for i in range(nb)])
+    assert np.array_equal(ctx.min(A, M), [oracle.min_(a[i], m[i]) for i in range(nb)])
+    assert np.array_equal(ctx.max(A, M), [oracle.max_(a[i], m[i]) for i in range(nb)])
+    np.testing.assert_allclose(ctx.sum(A), [oracle.sum_(a[i]) for i in range(nb)], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("shape", SHAPES + [(2, 12, 40, 50)])
+def test_percentiles(ctx, oracle, shape):
+    rng = np.random.default_rng(27)
+    a = rng.random(shape).astype(np.float32)
+    a[rng.random(shape) < 0.3] = 0.25        # long runs of equal keys
+    a[rng.random(shape) < 0.05] *= -1.0      # negative keys
+    a.ravel()[:2] = [0.0, -0.0] if a.size > 1 else [0.0]
+    m = rnd_mask(shape, 0.7, 28)
+    A, M = ctx.upload(a), ctx.upload(m)
+    for corr in (0.0, 0.5):
+        got = ctx.percentiles(A, M, corr).numpy()
+        want = per_volume(oracle.percentiles, a, m, correction=corr)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), corr
+    empty = ctx.percentiles(A, ctx.ff(M)).numpy()
+    assert np.all(empty == 0)
+
+
+# ------------------------------------------------------------------ cross correlation
+@pytest.mark.parametrize("shape,rho,k", [((2, 9, 20, 48), 2.0, 10), ((1, 7, 13, 37), 3.0, 100),
+                                         ((1, 1, 33, 70), 5.0, 16), ((1, 12, 70, 40), 5.0, 100)])
+def test_cross_correlation(ctx, oracle, shape, rho, k):
+    rng = np.random.default_rng(29)
+    a = ndi.gaussian_filter(rng.random(shape).astype(np.float32), (0, 1, 1, 1))
+    b = rng.random(shape).astype(np.float32)
+    reg = rnd_mask(shape, 0.3, 30)
+    A, B, R = ctx.upload(a), ctx.upload(b), ctx.upload(reg)
+    m, M = ctx.min(A), ctx.max(A)
+    got = ctx.cross_correlation(rho, A, B, R, m, M, k).numpy()
+    want = np.stack([oracle.cross_correlation(rho, a[i], b[i], reg[i], m[i], M[i], k) for i in range(shape[0])])
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    text = np.stack([oracle.cross_correlation(rho, a[i], b[i], reg[i], m[i], M[i], k, textbook=True)
+                     for i in range(shape[0])])
+    np.testing.assert_allclose(got, text, rtol=1e-5, atol=1e-6)
+
+
+def test_cross_correlation_spacing_and_empty_region(ctx, oracle):
+    shape = (1, 8, 16, 32)
+    rng = np.random.default_rng(31)
+    a = rng.random(shape).astype(np.float32)
+    sp = (1.0, 2.0, 1.5)
+    A = ctx.upload(a, spacing=sp)
+    reg = rnd_mask(shape, 0.5, 32)
+    got = ctx.cross_correlation(3.0, A, A, ctx.upload(reg, spacing=sp), 0.0, 1.0, 20).numpy()
+    want = oracle.cross_correlation(3.0, a[0], a[0], reg[0], 0.0, 1.0, 20, spacing=sp)
+    assert np.array_equal(got[0].view(np.uint32), want.view(np.uint32))
+    none = ctx.cross_correlation(3.0, A, A, ctx.ff(A), 0.0, 1.0, 20).numpy()
+    assert np.all(none == 0)
+
+
+# ------------------------------------------------------------------ runtime
+def test_handles_and_memory(ctx):
+    before = ctx.mem_info()
+    a = ctx.upload(np.ones((4, 8, 16), np.uint8))
+    imgs = [ctx.near(a) for _ in range(50)]
+    mid = ctx.mem_info()
+    assert mid["live_handles"] == before["live_handles"] + 51
+    del imgs
+    a.release()
+    assert ctx.mem_info()["live_handles"] == before["live_handles"]
+    assert ctx.launch_count() > 0
+
+
+def test_concurrent_callers(ctx, oracle):
+    """The F# scheduler calls from many threads: each thread gets its own stream and
+    results produced on one stream are consumed on another."""
+    import threading
+    shape = (1, 8, 24, 48)
+    base = rnd_mask(shape, 0.2, 33)
+    A = ctx.upload(base)
+    want = per_volume(oracle.near, per_volume(oracle.near, base))
+    results, errors = {}, []
+
+    def work(i):
+        try:
+            x = ctx.near(ctx.near(A))        # consumes an image produced on the main thread's stream
+            results[i] = x.numpy()
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors
+    assert all(np.array_equal(r, want) for r in results.values())

@@ -1,0 +1,442 @@
+// A5 distance operators (Greta.pdf p.37 "distance modality",
+// p.43 D^I): exact Euclidean distance transform in physical units and the fused
+// distance-interval tests behind distlt / distleq / distgeq / distgt.
+//
+// Arithmetic contract (identical in oracle/vx_oracle.c, so results are bit-exact):
+// the squared distance is built separably in IEEE binary32, one rounding per step,
+//      g1 = fl(fl(dx*sx)^2),  g2 = min_j fl(g1[j] + fl(fl(dy*sy)^2)),
+//      g3 = min_j fl(g2[j] + fl(fl(dz*sz)^2)),  d = sqrt_rn(g3)
+// (exact integers for unit spacing below 2^24).  fl(. + t) is monotone, so g3 equals
+// the minimum over all feature voxels of the same expression evaluated per offset.
+//
+// Two device paths:
+//  * vx_edt: three axis passes.  The x pass works on ballot bit masks; the y and z
+//    passes scan outwards from each voxel with exact early termination and visit only
+//    rows/planes that contain a feature at all (tracked as bit sets), so sparse masks
+//    cost O(#non-empty rows) and dense masks O(sqrt(result)).
+//  * vx_dist_*: "sqrt(g3) OP r" is a monotone step function of g3, hence equivalent to
+//    "g3 < T" for a threshold T found on the host; that in turn is a binary dilation
+//    by the exact discrete ball {offset : g3(offset) < T}, which is evaluated in the
+//    bit domain: pack 32 voxels per word, pre-dilate rows in x for every extent that
+//    occurs, then OR the <= 441 (dy,dz) rows per output word.  1 byte read + 1 byte
+//    written per voxel; the f32 map is never materialised.
+#include <math.h>
+
+#include "vx_internal.h"
+
+namespace vx {
+
+constexpr int kEdtThreads = 256;
+constexpr int kMaxRowWords = 128;  // x pass supports nx <= 4096
+constexpr int kMaxBallEntries = 441;
+
+// ------------------------------------------------------------------ bit helpers
+__device__ __forceinline__ int prev_set(const unsigned* __restrict__ fl, int pos) {
+    if (pos < 0) return -1;
+    int w = pos >> 5;
+    unsigned m = __ldg(fl + w) & (0xffffffffu >> (31 - (pos & 31)));
+    while (!m) {
+        if (--w < 0) return -1;
+        m = __ldg(fl + w);
+    }
+    return w * 32 + 31 - __clz(m);
+}
+__device__ __forceinline__ int next_set(const unsigned* __restrict__ fl, int pos, int n, int nw) {
+    if (pos >= n) return n;
+    int w = pos >> 5;
+    unsigned m = __ldg(fl + w) & (0xffffffffu << (pos & 31));
+    while (!m) {
+        if (++w >= nw) return n;
+        m = __ldg(fl + w);
+    }
+    return w * 32 + __ffs(m) - 1;
+}
+
+// ------------------------------------------------------------------ x pass
+// one warp per row.  g1 = (dx*sx)^2 to the nearest feature in the row, +inf if none.
+__global__ void __launch_bounds__(kEdtThreads)
+edt_x_kernel(const uint8_t* __restrict__ img, float* __restrict__ g1, unsigned* __restrict__ rowflag,
+             unsigned* __restrict__ planeflag, int nx, int ny, int nz, unsigned long long rows,
+             float sx) {
+    __shared__ unsigned sm[kEdtThreads / 32][kMaxRowWords];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned long long row = (unsigned long long)blockIdx.x * (kEdtThreads / 32) + warp;
+    if (row >= rows) return;
+    const int nwx = (nx + 31) >> 5;
+    const uint8_t* src = img + row * nx;
+    unsigned any = 0;
+    for (int c = 0; c < nwx; c++) {
+        int x = c * 32 + lane;
+        unsigned m = __ballot_sync(0xffffffffu, x < nx && src[x] != 0);
+        if (lane == 0) sm[warp][c] = m;
+        any |= m;
+    }
+    __syncwarp();
+    if (lane == 0 && any) {
+        const int y = (int)(row % ny);
+        const unsigned long long pz = row / ny;  // vol*nz + z
+        const int z = (int)(pz % nz);
+        const unsigned long long vol = pz / nz;
+        atomicOr(rowflag + pz * ((ny + 31) >> 5) + (y >> 5), 1u << (y & 31));
+        atomicOr(planeflag + vol * ((nz + 31) >> 5) + (z >> 5), 1u << (z & 31));
+    }
+    float* dst = g1 + row * nx;
+    const unsigned* bw = sm[warp];
+    for (int c = 0; c < nwx; c++) {
+        int x = c * 32 + lane;
+        if (x >= nx) break;
+        float v = INFINITY;
+        if (any) {
+            int b = x & 31;
+            int lw = c;
+            unsigned m = bw[lw] & (0xffffffffu >> (31 - b));
+            while (!m && lw > 0) m = bw[--lw];
+            int lpos = m ? lw * 32 + 31 - __clz(m) : -1;
+            int rw = c;
+            m = bw[rw] & (0xffffffffu << b);
+            while (!m && rw < nwx - 1) m = bw[++rw];
+            int rpos = m ? rw * 32 + __ffs(m) - 1 : -1;
+            int d = 0x7fffffff;
+            if (lpos >= 0) d = x - lpos;
+            if (rpos >= 0 && rpos - x < d) d = rpos - x;
+            float t = __fmul_rn((float)d, sx);
+            v = __fmul_rn(t, t);
+        }
+        dst[x] = v;
+    }
+}
+
+// ------------------------------------------------------------------ y / z passes
+enum { EDT_MID = 0, EDT_SQRT = 1, EDT_THRESH = 2 };
+
+// AXIS 1: along y, flags = rows of plane (vol,z).  AXIS 2: along z, flags = planes of vol.
+template <int AXIS, int MODE>
+__global__ void __launch_bounds__(kEdtThreads)
+edt_axis_kernel(const float* __restrict__ gin, void* __restrict__ gout_,
+                const unsigned* __restrict__ flags, int nx, int ny, int nz, size_t total, float s,
+                float T, int invert) {
+    const size_t idx = (size_t)blockIdx.x * kEdtThreads + threadIdx.x;
+    if (idx >= total) return;
+    const int x = (int)(idx % nx);
+    size_t t0 = idx / nx;
+    const int y = (int)(t0 % ny);
+    t0 /= ny;
+    const int z = (int)(t0 % nz);
+    const size_t vol = t0 / nz;
+    int i, n;
+    size_t stride;
+    const float* col;
+    const unsigned* fl;
+    if (AXIS == 1) {
+        i = y; n = ny; stride = nx;
+        col = gin + ((vol * nz + z) * ny) * (size_t)nx + x;
+        fl = flags + (vol * nz + z) * ((ny + 31) >> 5);
+    } else {
+        i = z; n = nz; stride = (size_t)nx * ny;
+        col = gin + (vol * nz) * stride + (size_t)y * nx + x;
+        fl = flags + vol * ((nz + 31) >> 5);
+    }
+    const int nw = (n + 31) >> 5;
+    float best = __ldg(col + (size_t)i * stride);
+    int jl = prev_set(fl, i - 1), jh = next_set(fl, i + 1, n, nw);
+    while (true) {
+        const int dl = jl >= 0 ? i - jl : 0x7fffffff;
+        const int dh = jh < n ? jh - i : 0x7fffffff;
+        const bool low = dl <= dh;
+        const int k = low ? dl : dh;
+        if (k == 0x7fffffff) break;
+        float t = __fmul_rn((float)k, s);
+        t = __fmul_rn(t, t);
+        if (!(t < best)) break;
+        const int j = low ? jl : jh;
+        best = fminf(best, __fadd_rn(__ldg(col + (size_t)j * stride), t));
+        if (low) jl = prev_set(fl, jl - 1);
+        else jh = next_set(fl, jh + 1, n, nw);
+    }
+    if (MODE == EDT_MID) reinterpret_cast<float*>(gout_)[idx] = best;
+    else if (MODE == EDT_SQRT) reinterpret_cast<float*>(gout_)[idx] = __fsqrt_rn(best);
+    else reinterpret_cast<uint8_t*>(gout_)[idx] = (uint8_t)((best < T ? 1 : 0) ^ invert);
+}
+
+// ------------------------------------------------------------------ bit-domain ball dilation
+// pack: one thread per 32-voxel word of a row
+__device__ __forceinline__ unsigned nib_of(unsigned w) {
+    w = __vcmpne4(w, 0u) & 0x01010101u;
+    return ((w * 0x01020408u) >> 24) & 0xfu;
+}
+__device__ __forceinline__ unsigned bits16(uint4 v) {
+    return nib_of(v.x) | (nib_of(v.y) << 4) | (nib_of(v.z) << 8) | (nib_of(v.w) << 12);
+}
+__global__ void __launch_bounds__(kEdtThreads)
+pack_bits_kernel(const uint8_t* __restrict__ img, unsigned* __restrict__ bits, int nx, int nwx,
+                 unsigned long long nwords) {
+    const unsigned long long wid = (unsigned long long)blockIdx.x * kEdtThreads + threadIdx.x;
+    if (wid >= nwords) return;
+    const unsigned long long row = wid / nwx;
+    const int w = (int)(wid % nwx);
+    const int x0 = w * 32;
+    const uint8_t* src = img + row * nx + x0;
+    unsigned m = 0;
+    if ((nx & 15) == 0) {
+        m = bits16(__ldg(reinterpret_cast<const uint4*>(src)));
+        if (x0 + 16 < nx) m |= bits16(__ldg(reinterpret_cast<const uint4*>(src + 16))) << 16;
+    } else {
+        const int lim = min(32, nx - x0);
+        for (int b = 0; b < lim; b++) m |= (unsigned)(src[b] != 0) << b;
+    }
+    bits[wid] = m;
+}
+
+// D[e][word] = row dilated by +-e voxels in x, for e = 1..emax (D[0] = the packed bits)
+__global__ void __launch_bounds__(kEdtThreads)
+xdilate_bits_kernel(unsigned* __restrict__ D, int nwx, unsigned long long nwords, int emax) {
+    const unsigned long long wid = (unsigned long long)blockIdx.x * kEdtThreads + threadIdx.x;
+    if (wid >= nwords) return;
+    const int w = (int)(wid % nwx);
+    const unsigned cur = D[wid];
+    const unsigned prev = w > 0 ? D[wid - 1] : 0u;
+    const unsigned next = w + 1 < nwx ? D[wid + 1] : 0u;
+    unsigned acc = cur;
+    for (int e = 1; e <= emax; e++) {
+        acc |= (cur << e) | (prev >> (32 - e)) | (cur >> e) | (next << (32 - e));
+        D[(size_t)e * nwords + wid] = acc;
+    }
+}
+
+struct Ball {
+    int n;
+    int8_t dy[kMaxBallEntries], dz[kMaxBallEntries], e[kMaxBallEntries];
+};
+
+__device__ __forceinline__ unsigned bytes_of(unsigned nib) {
+    return (nib * 0x00204081u) & 0x01010101u;
+}
+
+// one thread per output word: OR the pre-dilated neighbour rows, unpack to 0/1 bytes
+__global__ void __launch_bounds__(kEdtThreads)
+ball_or_kernel(const unsigned* __restrict__ D, uint8_t* __restrict__ out, int nx, int ny, int nz,
+               int nwx, unsigned long long nwords, const __grid_constant__ Ball ball, int invert) {
+    const unsigned long long wid = (unsigned long long)blockIdx.x * kEdtThreads + threadIdx.x;
+    if (wid >= nwords) return;
+    const unsigned long long row = wid / nwx;
+    const int w = (int)(wid % nwx);
+    const int y = (int)(row % ny);
+    const int z = (int)((row / ny) % nz);
+    unsigned acc = 0;
+    for (int t = 0; t < ball.n; t++) {
+        const int yy = y + ball.dy[t], zz = z + ball.dz[t];
+        if (yy < 0 || yy >= ny || zz < 0 || zz >= nz) continue;
+        const long long drow = (long long)ball.dz[t] * ny + ball.dy[t];
+        acc |= __ldg(D + (size_t)ball.e[t] * nwords + (size_t)((long long)wid + drow * nwx));
+    }
+    if (invert) acc = ~acc;
+    const int x0 = w * 32;
+    uint8_t* dst = out + row * nx + x0;
+    if ((nx & 15) == 0) {
+        uint4 v;
+        v.x = bytes_of(acc & 0xfu); v.y = bytes_of((acc >> 4) & 0xfu);
+        v.z = bytes_of((acc >> 8) & 0xfu); v.w = bytes_of((acc >> 12) & 0xfu);
+        *reinterpret_cast<uint4*>(dst) = v;
+        if (x0 + 16 < nx) {
+            v.x = bytes_of((acc >> 16) & 0xfu); v.y = bytes_of((acc >> 20) & 0xfu);
+            v.z = bytes_of((acc >> 24) & 0xfu); v.w = bytes_of((acc >> 28) & 0xfu);
+            *reinterpret_cast<uint4*>(dst + 16) = v;
+        }
+    } else {
+        const int lim = min(32, nx - x0);
+        for (int b = 0; b < lim; b++) dst[b] = (uint8_t)((acc >> b) & 1u);
+    }
+}
+
+// ------------------------------------------------------------------ host: thresholds and the ball
+// smallest binary32 T such that sqrtf(T) >= r  (strict = false)  or  sqrtf(T) > r  (strict = true):
+//   d <  r  <=>  g3 < T(strict=false);     d <= r  <=>  g3 < T(strict=true)
+static float threshold_for(float r, bool strict) {
+    auto ok = [&](float t) { float s = sqrtf(t); return strict ? s > r : s >= r; };
+    if (ok(0.0f)) return 0.0f;                 // r <= 0 (or r < 0 when strict)
+    // beyond sqrt(FLT_MAX) every finite squared distance passes (an empty feature set,
+    // d = +inf, is reported as "not within r" even for r = +inf)
+    if (!ok(INFINITY) || r > 1.8e19f) return INFINITY;
+    double rr = (double)r * (double)r;
+    float t = (float)rr;
+    if (!(t > 0.0f)) t = nextafterf(0.0f, 1.0f);
+    while (!ok(t)) t = nextafterf(t, INFINITY);
+    while (t > 0.0f && ok(nextafterf(t, 0.0f))) t = nextafterf(t, 0.0f);
+    return t;
+}
+
+static inline float sq_step(int d, float s) {
+    volatile float t = (float)d * s;  // volatile: one rounding per operation, no contraction
+    volatile float q = t * t;
+    return q;
+}
+static inline float add_step(float a, float b) {
+    volatile float r = a + b;
+    return r;
+}
+
+// exact discrete ball {(dx,dy,dz) : g3(offset) < T} as per-(dy,dz) x extents
+static bool build_ball(const float sp[3], float T, int nx, int ny, int nz, Ball* ball, int* emax) {
+    ball->n = 0;
+    *emax = 0;
+    if (!(T > 0.0f)) return true;  // empty ball: nothing is closer than 0
+    auto val = [&](int dx, int dy, int dz) {
+        return add_step(add_step(sq_step(dx, sp[0]), sq_step(dy, sp[1])), sq_step(dz, sp[2]));
+    };
+    int wy = 0, wz = 0;
+    while (wy + 1 < ny && val(0, wy + 1, 0) < T) { if (++wy > 120) return false; }
+    while (wz + 1 < nz && val(0, 0, wz + 1) < T) { if (++wz > 120) return false; }
+    for (int dz = -wz; dz <= wz; dz++)
+        for (int dy = -wy; dy <= wy; dy++) {
+            if (!(val(0, dy, dz) < T)) continue;
+            int e = 0;
+            while (e + 1 < nx && val(e + 1, dy, dz) < T) {
+                if (++e > 31) return false;
+            }
+            if (ball->n >= kMaxBallEntries) return false;
+            ball->dy[ball->n] = (int8_t)dy; ball->dz[ball->n] = (int8_t)dz; ball->e[ball->n] = (int8_t)e;
+            ball->n++;
+            if (e > *emax) *emax = e;
+        }
+    return true;
+}
+
+// squared-distance passes shared by vx_edt and the large-radius fallback of vx_dist_*
+static int edt_passes(OpGuard& og, const Image* A, void* out, int final_mode, float T, int invert) {
+    const size_t total = A->count();
+    const unsigned long long rows = (unsigned long long)A->nb * A->nz * A->ny;
+    VX_REQUIRE(A->nx <= kMaxRowWords * 32, VX_E_UNSUPPORTED, "vx_edt supports nx <= %d",
+               kMaxRowWords * 32);
+    const size_t n_rowflag = (size_t)A->nb * A->nz * ((A->ny + 31) / 32);
+    const size_t n_planeflag = (size_t)A->nb * ((A->nz + 31) / 32);
+    unsigned* flags = nullptr;
+    float *g1 = nullptr, *g2 = nullptr;
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (n_rowflag + n_planeflag), (void**)&flags));
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(float) * total, (void**)&g1));
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(float) * total, (void**)&g2));
+    VX_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (n_rowflag + n_planeflag), og.st));
+    unsigned* rowflag = flags;
+    unsigned* planeflag = flags + n_rowflag;
+    {
+        VX_LAUNCH(og.c, og.s, "edt_x_kernel");
+        unsigned grid = (unsigned)((rows + kEdtThreads / 32 - 1) / (kEdtThreads / 32));
+        edt_x_kernel<<<grid, kEdtThreads, 0, og.st>>>((const uint8_t*)A->d, g1, rowflag, planeflag,
+                                                     A->nx, A->ny, A->nz, rows, A->sp[0]);
+    }
+    VX_TRY(check_launch("edt_x_kernel"));
+    const unsigned grid = (unsigned)((total + kEdtThreads - 1) / kEdtThreads);
+    {
+        VX_LAUNCH(og.c, og.s, "edt_axis_kernel_y");
+        edt_axis_kernel<1, EDT_MID><<<grid, kEdtThreads, 0, og.st>>>(g1, g2, rowflag, A->nx, A->ny, A->nz,
+                                                                    total, A->sp[1], 0.f, 0);
+    }
+    VX_TRY(check_launch("edt_axis_kernel_y"));
+    {
+        VX_LAUNCH(og.c, og.s, "edt_axis_kernel_z");
+        if (final_mode == EDT_SQRT)
+            edt_axis_kernel<2, EDT_SQRT><<<grid, kEdtThreads, 0, og.st>>>(g2, out, planeflag, A->nx, A->ny,
+                                                                         A->nz, total, A->sp[2], 0.f, 0);
+        else
+            edt_axis_kernel<2, EDT_THRESH><<<grid, kEdtThreads, 0, og.st>>>(g2, out, planeflag, A->nx, A->ny,
+                                                                           A->nz, total, A->sp[2], T, invert);
+    }
+    VX_TRY(check_launch("edt_axis_kernel_z"));
+    VX_TRY(scratch_free(og.c, og.s, g1));
+    VX_TRY(scratch_free(og.c, og.s, g2));
+    return scratch_free(og.c, og.s, flags);
+}
+
+static int dist_threshold(vx_ctx ctx, vx_img a, float r, bool strict, int invert, vx_img* out) {
+    VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");
+    VX_REQUIRE(r == r, VX_E_INVALID_ARG, "radius is NaN");
+    OpGuard og;
+    VX_TRY(og.begin(ctx));
+    Image* A = nullptr;
+    VX_TRY(og.input(a, &A, VX_U8));
+    const float T = threshold_for(r, strict);
+    Image* O = nullptr;
+    VX_TRY(new_image(og.c, VX_U8, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
+    Ball ball;
+    int emax = 0;
+    int rc = VX_OK;
+    if (build_ball(A->sp, T, A->nx, A->ny, A->nz, &ball, &emax)) {
+        const int nwx = (A->nx + 31) / 32;
+        const unsigned long long nwords = (unsigned long long)A->nb * A->nz * A->ny * nwx;
+        unsigned* D = nullptr;
+        rc = scratch_alloc(og.c, og.s, sizeof(unsigned) * nwords * (emax + 1), (void**)&D);
+        const unsigned grid = (unsigned)((nwords + kEdtThreads - 1) / kEdtThreads);
+        if (rc == VX_OK) {
+            { VX_LAUNCH(og.c, og.s, "pack_bits_kernel");
+              pack_bits_kernel<<<grid, kEdtThreads, 0, og.st>>>((const uint8_t*)A->d, D, A->nx, nwx, nwords); }
+            rc = check_launch("pack_bits_kernel");
+        }
+        if (rc == VX_OK && emax > 0) {
+            { VX_LAUNCH(og.c, og.s, "xdilate_bits_kernel");
+              xdilate_bits_kernel<<<grid, kEdtThreads, 0, og.st>>>(D, nwx, nwords, emax); }
+            rc = check_launch("xdilate_bits_kernel");
+        }
+        if (rc == VX_OK) {
+            { VX_LAUNCH(og.c, og.s, "ball_or_kernel");
+              ball_or_kernel<<<grid, kEdtThreads, 0, og.st>>>(D, (uint8_t*)O->d, A->nx, A->ny, A->nz, nwx,
+                                                             nwords, ball, invert); }
+            rc = check_launch("ball_or_kernel");
+        }
+        if (rc == VX_OK) rc = scratch_free(og.c, og.s, D);
+    } else {
+        rc = edt_passes(og, A, O->d, EDT_THRESH, T, invert);
+    }
+    if (rc != VX_OK) { drop(O); return rc; }
+    return og.finish(O, out);
+}
+
+}  // namespace vx
+
+using namespace vx;
+
+extern "C" {
+
+int32_t vx_edt(vx_ctx ctx, vx_img a, vx_img* out) {
+    VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");
+    OpGuard og;
+    VX_TRY(og.begin(ctx));
+    Image* A = nullptr;
+    VX_TRY(og.input(a, &A, VX_U8));
+    Image* O = nullptr;
+    VX_TRY(new_image(og.c, VX_F32, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
+    int rc = edt_passes(og, A, O->d, EDT_SQRT, 0.f, 0);
+    if (rc != VX_OK) { drop(O); return rc; }
+    return og.finish(O, out);
+}
+
+int32_t vx_edt_signed(vx_ctx ctx, vx_img a, int32_t conn, vx_img* out) {
+    VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");
+    // boundary = a & near(!a);  signed = a ? -edt(boundary) : edt(a)
+    vx_img na = 0, nna = 0, bnd = 0, dout = 0, din = 0, neg = 0, res = 0;
+    int rc = vx_not(ctx, a, &na);
+    if (rc == VX_OK) rc = vx_near(ctx, na, conn, &nna);
+    if (rc == VX_OK) rc = vx_and(ctx, a, nna, &bnd);
+    if (rc == VX_OK) rc = vx_edt(ctx, a, &dout);
+    if (rc == VX_OK) rc = vx_edt(ctx, bnd, &din);
+    if (rc == VX_OK) rc = vx_arith_scalar(ctx, din, VX_RSUB, 0.0f, &neg);
+    if (rc == VX_OK) {
+        // res = a ? neg : dout   ==  select(a, neg, 0) + select(!a, dout, 0)
+        vx_op p[7] = {{VXP_LOAD, 0, 0, 0, 0, 0.f}, {VXP_LOAD, 1, 1, 0, 0, 0.f}, {VXP_LOAD, 2, 2, 0, 0, 0.f},
+                      {VXP_SELECT, 3, 0, 1, 0, 0.f}, {VXP_NOT, 4, 0, 0, 0, 0.f},
+                      {VXP_SELECT, 5, 4, 2, 0, 0.f}, {VXP_ARITH, 6, 3, 5, VX_ADD, 0.f}};
+        vx_img leaves[3] = {a, neg, dout};
+        rc = vx_fused_pointwise(ctx, p, 7, leaves, 3, nullptr, 0, &res);
+    }
+    vx_img tmp[6] = {na, nna, bnd, dout, din, neg};
+    for (vx_img t : tmp)
+        if (t) vx_release(t);
+    if (rc != VX_OK) return rc;
+    *out = res;
+    return VX_OK;
+}
+
+int32_t vx_dist_lt(vx_ctx ctx, vx_img a, float r, vx_img* out) { return dist_threshold(ctx, a, r, false, 0, out); }
+int32_t vx_dist_leq(vx_ctx ctx, vx_img a, float r, vx_img* out) { return dist_threshold(ctx, a, r, true, 0, out); }
+int32_t vx_dist_geq(vx_ctx ctx, vx_img a, float r, vx_img* out) { return dist_threshold(ctx, a, r, false, 1, out); }
+int32_t vx_dist_gt(vx_ctx ctx, vx_img a, float r, vx_img* out) { return dist_threshold(ctx, a, r, true, 1, out); }
+
+}  // extern "C"

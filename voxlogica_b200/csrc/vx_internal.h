@@ -1,0 +1,141 @@
+// Internal runtime of libvoxcuda.so: contexts, HBM-resident image handles, the
+// stream-ordered memory pool, per-thread streams and the error convention.
+// Nothing in this header crosses the C ABI (include/voxcuda.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/voxcuda.h"
+
+namespace vx {
+
+constexpr int kMaxStreams = 32;
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+struct Ctx;
+
+// T1: a device-resident batch of volumes.
+struct Image {
+    void* d = nullptr;
+    size_t bytes = 0;
+    int dtype = 0;
+    int nx = 0, ny = 0, nz = 0, nb = 0;
+    float sp[3] = {1.f, 1.f, 1.f};
+    std::atomic<int> rc{1};
+    Ctx* ctx = nullptr;
+    int home = 0;                 // stream index the image was produced on
+    cudaEvent_t ready = nullptr;  // recorded on `home` after the producer
+    std::mutex mu;                // guards `foreign`
+    std::vector<std::pair<int, cudaEvent_t>> foreign;  // last use on other streams
+    uint64_t handle = 0;
+    size_t nvox() const { return (size_t)nx * ny * nz; }       // per volume
+    size_t count() const { return (size_t)nx * ny * nz * nb; }  // whole batch
+};
+
+struct ProfRec {
+    const char* name;
+    cudaEvent_t e0, e1;
+};
+
+struct Ctx {
+    int device = 0;
+    uint64_t id = 0;
+    cudaStream_t streams[kMaxStreams] = {};
+    std::atomic<int> next_stream{0};
+    std::mutex mu;  // guards pools and accounting below
+    std::vector<cudaEvent_t> event_pool;
+    std::atomic<uint64_t> launches{0};
+    std::atomic<uint64_t> live_bytes{0};
+    std::atomic<uint64_t> live_handles{0};
+    std::atomic<int> prof_on{0};
+    std::vector<ProfRec> prof;
+    std::map<std::string, std::pair<uint64_t, double>> prof_acc;
+    void* flush_buf = nullptr;
+    size_t flush_bytes = 0;
+    cudaMemPool_t pool = nullptr;
+};
+
+// ---- error convention ------------------------------------------------------
+int fail(int code, const char* fmt, ...);
+#define VX_CUDA(call)                                                                   \
+    do {                                                                                \
+        cudaError_t _e = (call);                                                        \
+        if (_e != cudaSuccess)                                                          \
+            return vx::fail(_e == cudaErrorMemoryAllocation ? VX_E_OOM : VX_E_CUDA,     \
+                            "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e),     \
+                            __FILE__, __LINE__);                                        \
+    } while (0)
+#define VX_TRY(expr)               \
+    do {                           \
+        int _r = (expr);           \
+        if (_r != VX_OK) return _r; \
+    } while (0)
+#define VX_REQUIRE(cond, code, ...)                    \
+    do {                                               \
+        if (!(cond)) return vx::fail(code, __VA_ARGS__); \
+    } while (0)
+
+// ---- handles ---------------------------------------------------------------
+Ctx* get_ctx(vx_ctx h);
+Image* get_img(vx_img h);  // nullptr when invalid
+// Stream of the calling thread in this context (created lazily, round-robin).
+int my_stream_index(Ctx* c);
+inline cudaStream_t stream_of(Ctx* c, int idx) { return c->streams[idx]; }
+
+// Allocate a new image on the calling thread's stream.  On success *out holds a
+// handle with one reference owned by the caller.
+int new_image(Ctx* c, int dtype, int nx, int ny, int nz, int nb, const float* sp, Image** out);
+// Make `img` safe to read on stream index `s` (waits for its producer if needed).
+int use_input(Ctx* c, Image* img, int s);
+// Called after the consuming kernels were enqueued on stream `s`.
+int done_input(Ctx* c, Image* img, int s);
+// Called after the producing kernels were enqueued: records the ready event.
+int publish(Ctx* c, Image* img, int s);
+void drop(Image* img);  // release one reference
+
+// Scratch memory from the stream-ordered pool.
+int scratch_alloc(Ctx* c, int s, size_t bytes, void** out);
+int scratch_free(Ctx* c, int s, void* p);
+
+// ---- launch accounting / profiling ----------------------------------------
+struct LaunchScope {
+    Ctx* c;
+    int s;
+    const char* name;
+    cudaEvent_t e0 = nullptr;
+    LaunchScope(Ctx* c, int s, const char* name);
+    ~LaunchScope();
+};
+// Use as: { VX_LAUNCH(c, s, "kernel_name"); kernel<<<...>>>(...); }
+#define VX_LAUNCH(c, s, name) vx::LaunchScope _ls_##__LINE__(c, s, name)
+int check_launch(const char* name);
+
+// Grid sizing helper: a multiple of the SM count, capped by the work available.
+inline int grid_for(size_t work_items, int per_block, int ctas_per_sm) {
+    size_t need = (work_items + per_block - 1) / per_block;
+    size_t cap = (size_t)kNumSMs * ctas_per_sm;
+    if (need == 0) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+// RAII guard that validates common arguments and pins the inputs for one op.
+struct OpGuard {
+    Ctx* c = nullptr;
+    int s = 0;
+    cudaStream_t st = nullptr;
+    std::vector<Image*> ins;
+    int begin(vx_ctx ctx);
+    int input(vx_img h, Image** out, int want_dtype /*0 = any*/);
+    int finish(Image* out_img, vx_img* out);  // publish output + mark inputs used
+    int finish_scalar();                       // ops without an image result
+};
+
+int same_shape(const Image* a, const Image* b);
+
+}  // namespace vx

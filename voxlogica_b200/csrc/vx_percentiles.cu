@@ -1,0 +1,296 @@
+// A9 percentiles(img, mask, correction) (Greta.pdf p.43
+// "Normalization", p.52 percentiles(intensity(flair), brain)).
+//
+//   for x in mask:  ( #{y in mask : img(y) < img(x)} + correction * #{y in mask : img(y) = img(x)} ) / |mask|
+//   outside mask :  0
+// The rank is an exact integer; only the final division rounds (binary64, then to f32).
+//
+// Device algorithm, per volume of the batch and with no host round trip:
+//   1. compact the masked voxels into (sortable key, voxel index) pairs
+//      (block-aggregated: one atomicAdd per 4096 voxels);
+//   2. stable LSD radix sort of the pairs, 4 passes of 8 bits.  The unit of work is a
+//      warp-owned chunk of 2048 keys: digits are ranked inside the warp with
+//      match.any, running offsets live in warp-private shared memory, so no block
+//      barrier and no atomics are needed inside a pass;
+//   3. every sorted position finds the start of its run of equal keys (its rank) and
+//      scatters the normalised rank back to its voxel.
+#include "vx_internal.h"
+
+namespace vx {
+
+constexpr int kPcThreads = 256;
+constexpr int kWarpChunk = 2048;                 // keys owned by one warp in a sort pass
+constexpr int kRounds = kWarpChunk / 32;
+
+__device__ __forceinline__ unsigned sortable_key(float v) {
+    v = v + 0.0f;  // -0.0 -> +0.0 so that both zeros get the same rank
+    unsigned u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// ---- 1. compaction -------------------------------------------------------------------
+// grid (blocks, nb).  Each block walks tiles of 256*16 voxels of its volume.
+__global__ void __launch_bounds__(kPcThreads)
+pc_compact_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mask, size_t nvox,
+                  unsigned* __restrict__ keys, unsigned* __restrict__ idx,
+                  unsigned* __restrict__ count) {
+    __shared__ unsigned warp_tot[kPcThreads / 32];
+    __shared__ unsigned tile_base;
+    const size_t vol = blockIdx.y;
+    const float* a = img + vol * nvox;
+    const uint8_t* m = mask + vol * nvox;
+    unsigned* ko = keys + vol * nvox;
+    unsigned* io = idx + vol * nvox;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t tile = (size_t)kPcThreads * 16;
+    for (size_t t0 = (size_t)blockIdx.x * tile; t0 < nvox; t0 += (size_t)gridDim.x * tile) {
+        const size_t first = t0 + (size_t)threadIdx.x * 16;
+        unsigned bits = 0;
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            size_t i = first + e;
+            if (i < nvox && m[i] != 0) bits |= 1u << e;
+        }
+        unsigned c = __popc(bits);
+        // exclusive scan over the block
+        unsigned incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        unsigned wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kPcThreads / 32; w++) {
+            unsigned v = warp_tot[w];
+            if (w < warp) wbase += v;
+            total += v;
+        }
+        if (threadIdx.x == 0) tile_base = total ? atomicAdd(count + vol, total) : 0u;
+        __syncthreads();
+        unsigned pos = tile_base + wbase + incl - c;
+        while (bits) {
+            int e = __ffs(bits) - 1;
+            bits &= bits - 1;
+            size_t i = first + e;
+            ko[pos] = sortable_key(a[i]);
+            io[pos] = (unsigned)i;
+            pos++;
+        }
+        __syncthreads();  // tile_base / warp_tot reuse
+    }
+}
+
+// ---- 2. radix sort passes --------------------------------------------------------------
+// table layout: [vol][digit][chunk]  (chunk-major inside a digit so the scan is one sweep)
+__global__ void __launch_bounds__(kPcThreads)
+rs_hist_kernel(const unsigned* __restrict__ keys, const unsigned* __restrict__ count, size_t nvox,
+               unsigned* __restrict__ table, int nchunks_max, int shift) {
+    __shared__ unsigned cnt[kPcThreads / 32][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t vol = blockIdx.y;
+    const unsigned n = count[vol];
+    const unsigned chunk = blockIdx.x * (kPcThreads / 32) + warp;
+    const unsigned nchunks = (n + kWarpChunk - 1) / kWarpChunk;
+    if (chunk >= nchunks) return;
+    for (int d = lane; d < 256; d += 32) cnt[warp][d] = 0;
+    __syncwarp();
+    const unsigned* k = keys + vol * nvox;
+    const unsigned base = chunk * kWarpChunk;
+    for (int r = 0; r < kRounds; r++) {
+        unsigned p = base + r * 32 + lane;
+        bool ok = p < n;
+        unsigned active = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            unsigned d = (k[p] >> shift) & 0xffu;
+            unsigned peers = __match_any_sync(active, d);
+            if ((peers & ((1u << lane) - 1u)) == 0) cnt[warp][d] += __popc(peers);
+        }
+        __syncwarp();
+    }
+    unsigned* tab = table + (vol * 256) * (size_t)nchunks_max;
+    for (int d = lane; d < 256; d += 32) tab[(size_t)d * nchunks_max + chunk] = cnt[warp][d];
+}
+
+// one block per volume: exclusive scan of the used part of the table, in (digit, chunk) order
+__global__ void __launch_bounds__(1024)
+rs_scan_kernel(const unsigned* __restrict__ count, unsigned* __restrict__ table, int nchunks_max) {
+    __shared__ unsigned part[1024];
+    const size_t vol = blockIdx.x;
+    const unsigned n = count[vol];
+    const unsigned nchunks = (n + kWarpChunk - 1) / kWarpChunk;
+    if (nchunks == 0) return;
+    unsigned* tab = table + (vol * 256) * (size_t)nchunks_max;
+    const unsigned total = 256u * nchunks;
+    const unsigned per = (total + 1023u) / 1024u;
+    const unsigned lo = threadIdx.x * per;
+    const unsigned hi = min(lo + per, total);
+    unsigned sum = 0;
+    for (unsigned e = lo; e < hi; e++) sum += tab[(size_t)(e / nchunks) * nchunks_max + (e % nchunks)];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over 1024 partial sums
+    for (int o = 1; o < 1024; o <<= 1) {
+        unsigned v = threadIdx.x >= o ? part[threadIdx.x - o] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned run = part[threadIdx.x] - sum;
+    for (unsigned e = lo; e < hi; e++) {
+        size_t a = (size_t)(e / nchunks) * nchunks_max + (e % nchunks);
+        unsigned v = tab[a];
+        tab[a] = run;
+        run += v;
+    }
+}
+
+__global__ void __launch_bounds__(kPcThreads)
+rs_scatter_kernel(const unsigned* __restrict__ keys_in, const unsigned* __restrict__ idx_in,
+                  unsigned* __restrict__ keys_out, unsigned* __restrict__ idx_out,
+                  const unsigned* __restrict__ count, size_t nvox, const unsigned* __restrict__ table,
+                  int nchunks_max, int shift) {
+    __shared__ unsigned off[kPcThreads / 32][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t vol = blockIdx.y;
+    const unsigned n = count[vol];
+    const unsigned chunk = blockIdx.x * (kPcThreads / 32) + warp;
+    const unsigned nchunks = (n + kWarpChunk - 1) / kWarpChunk;
+    if (chunk >= nchunks) return;
+    const unsigned* tab = table + (vol * 256) * (size_t)nchunks_max;
+    for (int d = lane; d < 256; d += 32) off[warp][d] = tab[(size_t)d * nchunks_max + chunk];
+    __syncwarp();
+    const unsigned* ki = keys_in + vol * nvox;
+    const unsigned* ii = idx_in + vol * nvox;
+    unsigned* ko = keys_out + vol * nvox;
+    unsigned* io = idx_out + vol * nvox;
+    const unsigned base = chunk * kWarpChunk;
+    for (int r = 0; r < kRounds; r++) {
+        unsigned p = base + r * 32 + lane;
+        bool ok = p < n;
+        unsigned active = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            unsigned key = ki[p], id = ii[p];
+            unsigned d = (key >> shift) & 0xffu;
+            unsigned peers = __match_any_sync(active, d);
+            unsigned rank = __popc(peers & ((1u << lane) - 1u));
+            int leader = __ffs(peers) - 1;
+            unsigned start = 0;
+            if (lane == leader) {
+                start = off[warp][d];
+                off[warp][d] = start + __popc(peers);
+            }
+            start = __shfl_sync(peers, start, leader);
+            ko[start + rank] = key;
+            io[start + rank] = id;
+        }
+        __syncwarp();
+    }
+}
+
+// ---- 3. ranks ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPcThreads)
+pc_rank_kernel(const unsigned* __restrict__ keys, const unsigned* __restrict__ idx,
+               const unsigned* __restrict__ count, size_t nvox, float* __restrict__ out,
+               double correction) {
+    const size_t vol = blockIdx.y;
+    const unsigned n = count[vol];
+    const unsigned* k = keys + vol * nvox;
+    const unsigned* id = idx + vol * nvox;
+    float* o = out + vol * nvox;
+    for (unsigned p = blockIdx.x * kPcThreads + threadIdx.x; p < n; p += gridDim.x * kPcThreads) {
+        const unsigned key = k[p];
+        unsigned less = p;
+        if (p > 0 && k[p - 1] == key) {  // inside a run of equal keys: lower bound
+            unsigned lo = 0, hi = p;
+            while (lo < hi) {
+                unsigned mid = (lo + hi) >> 1;
+                if (k[mid] < key) lo = mid + 1; else hi = mid;
+            }
+            less = lo;
+        }
+        double num = (double)less;
+        if (correction != 0.0) {
+            unsigned up = p + 1;
+            if (up < n && k[up] == key) {  // upper bound
+                unsigned lo = up, hi = n;
+                while (lo < hi) {
+                    unsigned mid = (lo + hi) >> 1;
+                    if (k[mid] <= key) lo = mid + 1; else hi = mid;
+                }
+                up = lo;
+            }
+            num = __dadd_rn(num, __dmul_rn(correction, (double)(up - less)));
+        }
+        o[id[p]] = (float)__ddiv_rn(num, (double)n);
+    }
+}
+
+}  // namespace vx
+
+using namespace vx;
+
+extern "C" int32_t vx_percentiles(vx_ctx ctx, vx_img a, vx_img mask, double correction, vx_img* out) {
+    VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");
+    OpGuard og;
+    VX_TRY(og.begin(ctx));
+    Image *A = nullptr, *M = nullptr;
+    VX_TRY(og.input(a, &A, VX_F32));
+    VX_TRY(og.input(mask, &M, VX_U8));
+    VX_TRY(same_shape(A, M));
+    const size_t nvox = A->nvox(), total = A->count();
+    const int nb = A->nb;
+    const int nchunks_max = (int)((nvox + kWarpChunk - 1) / kWarpChunk);
+    unsigned *buf = nullptr, *count = nullptr, *table = nullptr;
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * total * 4, (void**)&buf));
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * nb, (void**)&count));
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (size_t)nb * 256 * nchunks_max, (void**)&table));
+    unsigned *k0 = buf, *i0 = buf + total, *k1 = buf + 2 * total, *i1 = buf + 3 * total;
+    VX_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned) * nb, og.st));
+    Image* O = nullptr;
+    VX_TRY(new_image(og.c, VX_F32, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
+    int rc = VX_OK;
+    cudaError_t ce = cudaMemsetAsync(O->d, 0, O->bytes, og.st);
+    if (ce != cudaSuccess) rc = fail(VX_E_CUDA, "memset: %s", cudaGetErrorString(ce));
+    if (rc == VX_OK) {
+        int per_vol = (int)((nvox + (size_t)kPcThreads * 16 - 1) / ((size_t)kPcThreads * 16));
+        int cap = (kNumSMs * 8 + nb - 1) / nb;
+        dim3 grid(per_vol < cap ? per_vol : cap, nb);
+        { VX_LAUNCH(og.c, og.s, "pc_compact_kernel");
+          pc_compact_kernel<<<grid, kPcThreads, 0, og.st>>>((const float*)A->d, (const uint8_t*)M->d, nvox, k0, i0, count); }
+        rc = check_launch("pc_compact_kernel");
+    }
+    dim3 sgrid((nchunks_max + kPcThreads / 32 - 1) / (kPcThreads / 32), nb);
+    for (int pass = 0; pass < 4 && rc == VX_OK; pass++) {
+        const int shift = pass * 8;
+        { VX_LAUNCH(og.c, og.s, "rs_hist_kernel");
+          rs_hist_kernel<<<sgrid, kPcThreads, 0, og.st>>>(k0, count, nvox, table, nchunks_max, shift); }
+        rc = check_launch("rs_hist_kernel");
+        if (rc != VX_OK) break;
+        { VX_LAUNCH(og.c, og.s, "rs_scan_kernel");
+          rs_scan_kernel<<<nb, 1024, 0, og.st>>>(count, table, nchunks_max); }
+        rc = check_launch("rs_scan_kernel");
+        if (rc != VX_OK) break;
+        { VX_LAUNCH(og.c, og.s, "rs_scatter_kernel");
+          rs_scatter_kernel<<<sgrid, kPcThreads, 0, og.st>>>(k0, i0, k1, i1, count, nvox, table, nchunks_max, shift); }
+        rc = check_launch("rs_scatter_kernel");
+        unsigned* t;
+        t = k0; k0 = k1; k1 = t;
+        t = i0; i0 = i1; i1 = t;
+    }
+    if (rc == VX_OK) {
+        int per_vol = (int)((nvox + kPcThreads - 1) / kPcThreads);
+        int cap = (kNumSMs * 8 + nb - 1) / nb;
+        dim3 grid(per_vol < cap ? per_vol : cap, nb);
+        { VX_LAUNCH(og.c, og.s, "pc_rank_kernel");
+          pc_rank_kernel<<<grid, kPcThreads, 0, og.st>>>(k0, i0, count, nvox, (float*)O->d, correction); }
+        rc = check_launch("pc_rank_kernel");
+    }
+    if (rc == VX_OK) rc = scratch_free(og.c, og.s, buf);
+    if (rc == VX_OK) rc = scratch_free(og.c, og.s, count);
+    if (rc == VX_OK) rc = scratch_free(og.c, og.s, table);
+    if (rc != VX_OK) { drop(O); return rc; }
+    return og.finish(O, out);
+}

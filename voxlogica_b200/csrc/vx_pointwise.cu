@@ -1,0 +1,534 @@
+// A1/A2: boolean and intensity pointwise operators, fused along
+// the DAG.  One kernel executes a whole straight-line program per 16-voxel group:
+// leaves are read once with 128-bit loads, intermediates live in a shared-memory
+// register file sized by the program (zero bytes for a single operator), and only
+// the root is written back.  HBM traffic of a chain = leaf bytes + root bytes.
+//
+// Semantics: Greta.pdf p.30 (not, and, true), p.35 (or, false), p.43 (thresholds);
+// comparisons and arithmetic are IEEE-754 binary32, one rounding per operator
+// (no FMA contraction can occur across the interpreter's dispatch).
+#include "vx_internal.h"
+
+namespace vx {
+
+constexpr int kPwThreads = 256;
+constexpr int kGroup = 16;  // voxels per thread per iteration
+
+enum : uint8_t { K_REG = 0, K_LEAF = 1 };
+enum : uint8_t { OPC_COPYB = 32, OPC_COPYF = 33 };
+
+struct DevOp {
+    uint8_t opcode, aux;
+    int8_t dst;  // physical register, -1 = program output
+    uint8_t a_kind, a_idx, b_kind, b_idx, pad;
+    float imm;
+};
+
+struct DevProg {
+    int n_ops;
+    int n_breg, n_freg;
+    int nb;
+    unsigned long long nvox;     // voxels per volume
+    unsigned long long ngroups;  // 16-voxel groups over the whole batch
+    const void* leaf[VXP_MAX_LEAVES];
+    void* out;
+    const float* bscal;  // [n_scalars][nb]
+    DevOp ops[VXP_MAX_OPS];
+};
+
+struct F16 {
+    float4 v[4];
+};
+
+__device__ __forceinline__ uint4 ld_b(const DevProg& P, uint8_t kind, uint8_t idx, size_t g,
+                                      const uint4* sb) {
+    if (kind == K_LEAF) return __ldg(reinterpret_cast<const uint4*>(P.leaf[idx]) + g);
+    return sb[idx * kPwThreads + threadIdx.x];
+}
+__device__ __forceinline__ F16 ld_f(const DevProg& P, uint8_t kind, uint8_t idx, size_t g,
+                                    const float4* sf) {
+    F16 r;
+    if (kind == K_LEAF) {
+        const float4* p = reinterpret_cast<const float4*>(P.leaf[idx]) + g * 4;
+#pragma unroll
+        for (int q = 0; q < 4; q++) r.v[q] = __ldg(p + q);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; q++) r.v[q] = sf[(idx * 4 + q) * kPwThreads + threadIdx.x];
+    }
+    return r;
+}
+__device__ __forceinline__ void st_b(const DevProg& P, int8_t dst, size_t g, uint4* sb, uint4 v) {
+    if (dst < 0) reinterpret_cast<uint4*>(P.out)[g] = v;
+    else sb[dst * kPwThreads + threadIdx.x] = v;
+}
+__device__ __forceinline__ void st_f(const DevProg& P, int8_t dst, size_t g, float4* sf,
+                                     const F16& v) {
+    if (dst < 0) {
+        float4* p = reinterpret_cast<float4*>(P.out) + g * 4;
+#pragma unroll
+        for (int q = 0; q < 4; q++) p[q] = v.v[q];
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; q++) sf[(dst * 4 + q) * kPwThreads + threadIdx.x] = v.v[q];
+    }
+}
+
+__device__ __forceinline__ unsigned cmp1(float x, float y, int op) {
+    switch (op) {
+        case VX_LT: return x < y;
+        case VX_LE: return x <= y;
+        case VX_GT: return x > y;
+        case VX_GE: return x >= y;
+        case VX_EQ: return x == y;
+        default: return x != y;
+    }
+}
+__device__ __forceinline__ float arith1(float x, float y, int op) {
+    switch (op) {
+        case VX_ADD: return __fadd_rn(x, y);
+        case VX_SUB: return __fsub_rn(x, y);
+        case VX_MUL: return __fmul_rn(x, y);
+        case VX_DIV: return __fdiv_rn(x, y);
+        case VX_RSUB: return __fsub_rn(y, x);
+        case VX_RDIV: return __fdiv_rn(y, x);
+        case VX_MIN: return fminf(x, y);
+        default: return fmaxf(x, y);
+    }
+}
+__device__ __forceinline__ unsigned pack4(unsigned a, unsigned b, unsigned c, unsigned d) {
+    return a | (b << 8) | (c << 16) | (d << 24);
+}
+__device__ __forceinline__ uint4 cmp16(const F16& x, const F16& y, int op) {
+    uint4 r;
+    r.x = pack4(cmp1(x.v[0].x, y.v[0].x, op), cmp1(x.v[0].y, y.v[0].y, op),
+                cmp1(x.v[0].z, y.v[0].z, op), cmp1(x.v[0].w, y.v[0].w, op));
+    r.y = pack4(cmp1(x.v[1].x, y.v[1].x, op), cmp1(x.v[1].y, y.v[1].y, op),
+                cmp1(x.v[1].z, y.v[1].z, op), cmp1(x.v[1].w, y.v[1].w, op));
+    r.z = pack4(cmp1(x.v[2].x, y.v[2].x, op), cmp1(x.v[2].y, y.v[2].y, op),
+                cmp1(x.v[2].z, y.v[2].z, op), cmp1(x.v[2].w, y.v[2].w, op));
+    r.w = pack4(cmp1(x.v[3].x, y.v[3].x, op), cmp1(x.v[3].y, y.v[3].y, op),
+                cmp1(x.v[3].z, y.v[3].z, op), cmp1(x.v[3].w, y.v[3].w, op));
+    return r;
+}
+__device__ __forceinline__ F16 arith16(const F16& x, const F16& y, int op) {
+    F16 r;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        r.v[q].x = arith1(x.v[q].x, y.v[q].x, op);
+        r.v[q].y = arith1(x.v[q].y, y.v[q].y, op);
+        r.v[q].z = arith1(x.v[q].z, y.v[q].z, op);
+        r.v[q].w = arith1(x.v[q].w, y.v[q].w, op);
+    }
+    return r;
+}
+__device__ __forceinline__ F16 splat(float s) {
+    F16 r;
+#pragma unroll
+    for (int q = 0; q < 4; q++) r.v[q] = make_float4(s, s, s, s);
+    return r;
+}
+// per-volume scalar number `which` for the 16 voxels of group g
+__device__ __forceinline__ F16 batch_scalar(const DevProg& P, int which, size_t g) {
+    size_t first = g * kGroup;
+    unsigned v0 = (unsigned)(first / P.nvox);
+    unsigned v1 = (unsigned)((first + kGroup - 1) / P.nvox);
+    const float* tab = P.bscal + (size_t)which * P.nb;
+    if (v1 >= (unsigned)P.nb) v1 = P.nb - 1;
+    if (v0 >= (unsigned)P.nb) v0 = P.nb - 1;
+    if (v0 == v1) return splat(__ldg(tab + v0));
+    F16 r;
+    float tmp[kGroup];
+#pragma unroll
+    for (int e = 0; e < kGroup; e++) {
+        unsigned v = (unsigned)((first + e) / P.nvox);
+        if (v >= (unsigned)P.nb) v = P.nb - 1;
+        tmp[e] = __ldg(tab + v);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) r.v[q] = make_float4(tmp[4 * q], tmp[4 * q + 1], tmp[4 * q + 2], tmp[4 * q + 3]);
+    return r;
+}
+__device__ __forceinline__ float sel1(unsigned m, int sh, float a, float fill) {
+    return ((m >> sh) & 0xffu) ? a : fill;
+}
+
+__global__ void __launch_bounds__(kPwThreads)
+pointwise_program_kernel(const __grid_constant__ DevProg P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4* sb = reinterpret_cast<uint4*>(smem_raw);
+    float4* sf = reinterpret_cast<float4*>(smem_raw + (size_t)P.n_breg * kPwThreads * sizeof(uint4));
+    const size_t stride = (size_t)gridDim.x * kPwThreads;
+    for (size_t g = (size_t)blockIdx.x * kPwThreads + threadIdx.x; g < P.ngroups; g += stride) {
+        for (int i = 0; i < P.n_ops; i++) {
+            const DevOp op = P.ops[i];
+            switch (op.opcode) {
+                case VXP_NOT: {
+                    uint4 x = ld_b(P, op.a_kind, op.a_idx, g, sb);
+                    x.x ^= 0x01010101u; x.y ^= 0x01010101u; x.z ^= 0x01010101u; x.w ^= 0x01010101u;
+                    st_b(P, op.dst, g, sb, x);
+                } break;
+                case VXP_AND: {
+                    uint4 x = ld_b(P, op.a_kind, op.a_idx, g, sb), y = ld_b(P, op.b_kind, op.b_idx, g, sb);
+                    x.x &= y.x; x.y &= y.y; x.z &= y.z; x.w &= y.w;
+                    st_b(P, op.dst, g, sb, x);
+                } break;
+                case VXP_OR: {
+                    uint4 x = ld_b(P, op.a_kind, op.a_idx, g, sb), y = ld_b(P, op.b_kind, op.b_idx, g, sb);
+                    x.x |= y.x; x.y |= y.y; x.z |= y.z; x.w |= y.w;
+                    st_b(P, op.dst, g, sb, x);
+                } break;
+                case VXP_XOR: {
+                    uint4 x = ld_b(P, op.a_kind, op.a_idx, g, sb), y = ld_b(P, op.b_kind, op.b_idx, g, sb);
+                    x.x ^= y.x; x.y ^= y.y; x.z ^= y.z; x.w ^= y.w;
+                    st_b(P, op.dst, g, sb, x);
+                } break;
+                case OPC_COPYB: {
+                    st_b(P, op.dst, g, sb, ld_b(P, op.a_kind, op.a_idx, g, sb));
+                } break;
+                case OPC_COPYF: {
+                    st_f(P, op.dst, g, sf, ld_f(P, op.a_kind, op.a_idx, g, sf));
+                } break;
+                case VXP_CMPS: {
+                    F16 x = ld_f(P, op.a_kind, op.a_idx, g, sf);
+                    st_b(P, op.dst, g, sb, cmp16(x, splat(op.imm), op.aux));
+                } break;
+                case VXP_CMPSB: {
+                    F16 x = ld_f(P, op.a_kind, op.a_idx, g, sf);
+                    st_b(P, op.dst, g, sb, cmp16(x, batch_scalar(P, op.b_idx, g), op.aux));
+                } break;
+                case VXP_CMP: {
+                    F16 x = ld_f(P, op.a_kind, op.a_idx, g, sf), y = ld_f(P, op.b_kind, op.b_idx, g, sf);
+                    st_b(P, op.dst, g, sb, cmp16(x, y, op.aux));
+                } break;
+                case VXP_ARITHS: {
+                    F16 x = ld_f(P, op.a_kind, op.a_idx, g, sf);
+                    st_f(P, op.dst, g, sf, arith16(x, splat(op.imm), op.aux));
+                } break;
+                case VXP_ARITHSB: {
+                    F16 x = ld_f(P, op.a_kind, op.a_idx, g, sf);
+                    st_f(P, op.dst, g, sf, arith16(x, batch_scalar(P, op.b_idx, g), op.aux));
+                } break;
+                case VXP_ARITH: {
+                    F16 x = ld_f(P, op.a_kind, op.a_idx, g, sf), y = ld_f(P, op.b_kind, op.b_idx, g, sf);
+                    st_f(P, op.dst, g, sf, arith16(x, y, op.aux));
+                } break;
+                case VXP_TOF32: {
+                    uint4 x = ld_b(P, op.a_kind, op.a_idx, g, sb);
+                    unsigned w[4] = {x.x, x.y, x.z, x.w};
+                    F16 r;
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        r.v[q] = make_float4((float)(w[q] & 0xffu), (float)((w[q] >> 8) & 0xffu),
+                                             (float)((w[q] >> 16) & 0xffu), (float)(w[q] >> 24));
+                    st_f(P, op.dst, g, sf, r);
+                } break;
+                case VXP_TOBOOL: {
+                    F16 x = ld_f(P, op.a_kind, op.a_idx, g, sf);
+                    st_b(P, op.dst, g, sb, cmp16(x, splat(0.f), VX_NE));
+                } break;
+                case VXP_CONSTB: {
+                    unsigned w = op.aux ? 0x01010101u : 0u;
+                    st_b(P, op.dst, g, sb, make_uint4(w, w, w, w));
+                } break;
+                case VXP_CONSTF: {
+                    st_f(P, op.dst, g, sf, splat(op.imm));
+                } break;
+                case VXP_SELECT: {
+                    uint4 m = ld_b(P, op.a_kind, op.a_idx, g, sb);
+                    F16 x = ld_f(P, op.b_kind, op.b_idx, g, sf);
+                    unsigned w[4] = {m.x, m.y, m.z, m.w};
+                    F16 r;
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        r.v[q] = make_float4(sel1(w[q], 0, x.v[q].x, op.imm), sel1(w[q], 8, x.v[q].y, op.imm),
+                                             sel1(w[q], 16, x.v[q].z, op.imm), sel1(w[q], 24, x.v[q].w, op.imm));
+                    st_f(P, op.dst, g, sf, r);
+                } break;
+                default: break;
+            }
+        }
+    }
+}
+
+// ---- host side: validate, allocate registers, launch ---------------------------
+enum { T_NONE = 0, T_B = 1, T_F = 2 };
+
+struct PubReg {
+    int type = T_NONE;
+    int leaf = -1;  // alias of a leaf (written by VXP_LOAD)
+    int phys = -1;  // physical register of its type
+    int def = -1;   // defining instruction
+};
+
+static int result_type(int opcode) {
+    switch (opcode) {
+        case VXP_NOT: case VXP_AND: case VXP_OR: case VXP_XOR: case VXP_CMPS: case VXP_CMP:
+        case VXP_TOBOOL: case VXP_CONSTB: case VXP_CMPSB:
+            return T_B;
+        case VXP_ARITHS: case VXP_ARITH: case VXP_TOF32: case VXP_CONSTF: case VXP_SELECT:
+        case VXP_ARITHSB:
+            return T_F;
+    }
+    return T_NONE;
+}
+// operand types: returns number of register operands and their required types
+static int operand_types(int opcode, int* ta, int* tb) {
+    *ta = *tb = T_NONE;
+    switch (opcode) {
+        case VXP_NOT: *ta = T_B; return 1;
+        case VXP_AND: case VXP_OR: case VXP_XOR: *ta = *tb = T_B; return 2;
+        case VXP_CMPS: case VXP_ARITHS: case VXP_TOBOOL: case VXP_CMPSB: case VXP_ARITHSB:
+            *ta = T_F; return 1;
+        case VXP_CMP: case VXP_ARITH: *ta = *tb = T_F; return 2;
+        case VXP_TOF32: *ta = T_B; return 1;
+        case VXP_SELECT: *ta = T_B; *tb = T_F; return 2;
+        case VXP_CONSTB: case VXP_CONSTF: return 0;
+    }
+    return -1;
+}
+
+int run_pointwise(vx_ctx ctx, const vx_op* prog, int n_ops, const vx_img* leaves, int n_leaves,
+                  const float* batch_scalars, int n_scalars, vx_img like, vx_img* out) {
+    VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");
+    VX_REQUIRE(prog != nullptr && n_ops > 0 && n_ops <= VXP_MAX_OPS, VX_E_INVALID_ARG,
+               "program length %d outside [1,%d]", n_ops, VXP_MAX_OPS);
+    VX_REQUIRE(n_leaves >= 0 && n_leaves <= VXP_MAX_LEAVES, VX_E_INVALID_ARG,
+               "%d leaves, at most %d supported", n_leaves, VXP_MAX_LEAVES);
+    OpGuard g;
+    VX_TRY(g.begin(ctx));
+    Image* L[VXP_MAX_LEAVES] = {};
+    for (int i = 0; i < n_leaves; i++) {
+        VX_TRY(g.input(leaves[i], &L[i], 0));
+        VX_REQUIRE(L[i]->dtype == VX_U8 || L[i]->dtype == VX_F32, VX_E_DTYPE,
+                   "leaf %d has dtype %d; pointwise programs take u8 or f32", i, L[i]->dtype);
+        if (i > 0) VX_TRY(same_shape(L[0], L[i]));
+    }
+    Image* shape = nullptr;
+    if (n_leaves > 0) shape = L[0];
+    else {
+        VX_TRY(g.input(like, &shape, 0));
+    }
+
+    DevProg P;
+    memset(&P, 0, sizeof(P));
+    PubReg regs[VXP_MAX_REGS];
+    // last use of the value defined at instruction i
+    int last_use[VXP_MAX_OPS];
+    int cur_def[VXP_MAX_REGS];
+    for (int r = 0; r < VXP_MAX_REGS; r++) cur_def[r] = -1;
+    for (int i = 0; i < n_ops; i++) last_use[i] = -1;
+    for (int i = 0; i < n_ops; i++) {
+        const vx_op& o = prog[i];
+        VX_REQUIRE(o.dst >= 0 && o.dst < VXP_MAX_REGS, VX_E_INVALID_ARG,
+                   "instruction %d: dst register %d out of range", i, o.dst);
+        int ta, tb;
+        int nopnd = (o.opcode == VXP_LOAD) ? 0 : operand_types(o.opcode, &ta, &tb);
+        VX_REQUIRE(nopnd >= 0, VX_E_INVALID_ARG, "instruction %d: unknown opcode %d", i, o.opcode);
+        if (nopnd >= 1) {
+            VX_REQUIRE(o.a >= 0 && o.a < VXP_MAX_REGS && cur_def[o.a] >= 0, VX_E_INVALID_ARG,
+                       "instruction %d: operand a reads undefined register %d", i, o.a);
+            last_use[cur_def[o.a]] = i;
+        }
+        if (nopnd >= 2) {
+            VX_REQUIRE(o.b >= 0 && o.b < VXP_MAX_REGS && cur_def[o.b] >= 0, VX_E_INVALID_ARG,
+                       "instruction %d: operand b reads undefined register %d", i, o.b);
+            last_use[cur_def[o.b]] = i;
+        }
+        cur_def[o.dst] = i;
+    }
+
+    std::vector<int> free_b, free_f;
+    int n_b = 0, n_f = 0;
+    int phys_of_def[VXP_MAX_OPS], type_of_def[VXP_MAX_OPS];
+    for (int i = 0; i < n_ops; i++) { phys_of_def[i] = -1; type_of_def[i] = T_NONE; }
+    int out_type = T_NONE;
+    int nd = 0;
+    for (int i = 0; i < n_ops; i++) {
+        const vx_op& o = prog[i];
+        const bool last = (i == n_ops - 1);
+        if (o.opcode == VXP_LOAD) {
+            VX_REQUIRE(o.a >= 0 && o.a < n_leaves, VX_E_INVALID_ARG,
+                       "instruction %d: leaf %d out of range", i, o.a);
+            PubReg& d = regs[o.dst];
+            d.type = (L[o.a]->dtype == VX_U8) ? T_B : T_F;
+            d.leaf = o.a; d.phys = -1; d.def = i;
+            if (last) {
+                DevOp& D = P.ops[nd++];
+                D.opcode = d.type == T_B ? OPC_COPYB : OPC_COPYF;
+                D.dst = -1; D.a_kind = K_LEAF; D.a_idx = (uint8_t)o.a;
+                out_type = d.type;
+            }
+            continue;
+        }
+        int ta, tb;
+        int nopnd = operand_types(o.opcode, &ta, &tb);
+        DevOp& D = P.ops[nd++];
+        D.opcode = (uint8_t)o.opcode;
+        D.aux = (uint8_t)o.aux;
+        D.imm = o.imm;
+        if (o.opcode == VXP_CMPS || o.opcode == VXP_CMP || o.opcode == VXP_CMPSB)
+            VX_REQUIRE(o.aux >= VX_LT && o.aux <= VX_NE, VX_E_INVALID_ARG,
+                       "instruction %d: comparison %d unknown", i, o.aux);
+        if (o.opcode == VXP_ARITHS || o.opcode == VXP_ARITH || o.opcode == VXP_ARITHSB)
+            VX_REQUIRE(o.aux >= VX_ADD && o.aux <= VX_MAX, VX_E_INVALID_ARG,
+                       "instruction %d: arithmetic operator %d unknown", i, o.aux);
+        if (o.opcode == VXP_CMPSB || o.opcode == VXP_ARITHSB) {
+            VX_REQUIRE(batch_scalars != nullptr && o.b >= 0 && o.b < n_scalars, VX_E_INVALID_ARG,
+                       "instruction %d: per-volume scalar %d not supplied", i, o.b);
+            D.b_idx = (uint8_t)o.b;
+        }
+        int deferred_free[2] = {-1, -1};
+        for (int k = 0; k < nopnd; k++) {
+            int r = k == 0 ? o.a : o.b;
+            int want = k == 0 ? ta : tb;
+            PubReg& pr = regs[r];
+            VX_REQUIRE(pr.type == want, VX_E_DTYPE,
+                       "instruction %d: operand %c is %s but the operator needs %s", i, 'a' + k,
+                       pr.type == T_B ? "boolean" : "numeric", want == T_B ? "boolean" : "numeric");
+            uint8_t kind = pr.leaf >= 0 ? K_LEAF : K_REG;
+            uint8_t idx = (uint8_t)(pr.leaf >= 0 ? pr.leaf : pr.phys);
+            if (k == 0) { D.a_kind = kind; D.a_idx = idx; }
+            else { D.b_kind = kind; D.b_idx = idx; }
+            if (pr.leaf < 0 && last_use[pr.def] == i) deferred_free[k] = pr.def;
+        }
+        // operands are read into registers before dst is written, so a register whose
+        // last use is this instruction can be reused as its destination
+        for (int k = 0; k < 2; k++) {
+            int d = deferred_free[k];
+            if (d < 0 || (k == 1 && d == deferred_free[0])) continue;
+            if (type_of_def[d] == T_B) free_b.push_back(phys_of_def[d]);
+            else free_f.push_back(phys_of_def[d]);
+        }
+        int rt = result_type(o.opcode);
+        PubReg& d = regs[o.dst];
+        // (a value that is never read keeps its physical register: dead code is the
+        // caller's business, it only costs shared memory)
+        d.type = rt; d.leaf = -1; d.def = i;
+        if (last) {
+            D.dst = -1;
+            d.phys = -1;
+            out_type = rt;
+        } else {
+            int p;
+            if (rt == T_B) {
+                if (!free_b.empty()) { p = free_b.back(); free_b.pop_back(); } else p = n_b++;
+            } else {
+                if (!free_f.empty()) { p = free_f.back(); free_f.pop_back(); } else p = n_f++;
+            }
+            d.phys = p;
+            phys_of_def[i] = p; type_of_def[i] = rt;
+            D.dst = (int8_t)p;
+        }
+    }
+    size_t smem = (size_t)kPwThreads * (16 * (size_t)n_b + 64 * (size_t)n_f);
+    VX_REQUIRE(smem <= 200 * 1024, VX_E_UNSUPPORTED,
+               "program needs %d boolean + %d numeric live registers (%zu B shared memory); split it",
+               n_b, n_f, smem);
+
+    Image* o = nullptr;
+    VX_TRY(new_image(g.c, out_type == T_B ? VX_U8 : VX_F32, shape->nx, shape->ny, shape->nz,
+                     shape->nb, shape->sp, &o));
+    P.n_ops = nd;
+    P.n_breg = n_b; P.n_freg = n_f;
+    P.nb = shape->nb;
+    P.nvox = shape->nvox();
+    P.ngroups = (shape->count() + kGroup - 1) / kGroup;
+    for (int i = 0; i < n_leaves; i++) P.leaf[i] = L[i]->d;
+    P.out = o->d;
+    float* d_scal = nullptr;
+    if (n_scalars > 0 && batch_scalars) {
+        size_t bytes = sizeof(float) * (size_t)n_scalars * shape->nb;
+        int r = scratch_alloc(g.c, g.s, bytes, (void**)&d_scal);
+        if (r != VX_OK) { drop(o); return r; }
+        // pageable source: the runtime stages it before returning
+        cudaError_t e = cudaMemcpyAsync(d_scal, batch_scalars, bytes, cudaMemcpyHostToDevice, g.st);
+        if (e != cudaSuccess) { drop(o); return fail(VX_E_CUDA, "scalar upload: %s", cudaGetErrorString(e)); }
+        P.bscal = d_scal;
+    }
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(pointwise_program_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { drop(o); return fail(VX_E_CUDA, "smem attribute: %s", cudaGetErrorString(e)); }
+    }
+    int ctas = smem == 0 ? 8 : (int)((220 * 1024) / smem);
+    if (ctas < 1) ctas = 1;
+    if (ctas > 8) ctas = 8;
+    int grid = grid_for(P.ngroups, kPwThreads, ctas);
+    {
+        VX_LAUNCH(g.c, g.s, "pointwise_program_kernel");
+        pointwise_program_kernel<<<grid, kPwThreads, smem, g.st>>>(P);
+    }
+    int r = check_launch("pointwise_program_kernel");
+    if (r == VX_OK && d_scal) r = scratch_free(g.c, g.s, d_scal);
+    if (r != VX_OK) { drop(o); return r; }
+    return g.finish(o, out);
+}
+
+}  // namespace vx
+
+using namespace vx;
+
+static int32_t unary(vx_ctx ctx, vx_img a, int opcode, int aux, float imm, vx_img* out) {
+    vx_op p[2] = {{VXP_LOAD, 0, 0, 0, 0, 0.f}, {opcode, 1, 0, 0, aux, imm}};
+    return run_pointwise(ctx, p, 2, &a, 1, nullptr, 0, 0, out);
+}
+static int32_t binary(vx_ctx ctx, vx_img a, vx_img b, int opcode, int aux, float imm, vx_img* out) {
+    vx_op p[3] = {{VXP_LOAD, 0, 0, 0, 0, 0.f}, {VXP_LOAD, 1, 1, 0, 0, 0.f}, {opcode, 2, 0, 1, aux, imm}};
+    vx_img l[2] = {a, b};
+    return run_pointwise(ctx, p, 3, l, 2, nullptr, 0, 0, out);
+}
+
+extern "C" {
+
+int32_t vx_fused_pointwise(vx_ctx ctx, const vx_op* program, int32_t n_ops, const vx_img* leaves,
+                           int32_t n_leaves, const float* batch_scalars, int32_t n_scalars,
+                           vx_img* out) {
+    VX_REQUIRE(n_leaves > 0 && leaves != nullptr, VX_E_INVALID_ARG,
+               "a fused program needs at least one leaf image");
+    return run_pointwise(ctx, program, n_ops, leaves, n_leaves, batch_scalars, n_scalars, 0, out);
+}
+
+int32_t vx_const_bool(vx_ctx ctx, vx_img like, int32_t value, vx_img* out) {
+    vx_op p = {VXP_CONSTB, 0, 0, 0, value ? 1 : 0, 0.f};
+    return run_pointwise(ctx, &p, 1, nullptr, 0, nullptr, 0, like, out);
+}
+int32_t vx_const_f32(vx_ctx ctx, vx_img like, float value, vx_img* out) {
+    vx_op p = {VXP_CONSTF, 0, 0, 0, 0, value};
+    return run_pointwise(ctx, &p, 1, nullptr, 0, nullptr, 0, like, out);
+}
+int32_t vx_not(vx_ctx ctx, vx_img a, vx_img* out) { return unary(ctx, a, VXP_NOT, 0, 0.f, out); }
+int32_t vx_and(vx_ctx ctx, vx_img a, vx_img b, vx_img* out) { return binary(ctx, a, b, VXP_AND, 0, 0.f, out); }
+int32_t vx_or(vx_ctx ctx, vx_img a, vx_img b, vx_img* out) { return binary(ctx, a, b, VXP_OR, 0, 0.f, out); }
+int32_t vx_xor(vx_ctx ctx, vx_img a, vx_img b, vx_img* out) { return binary(ctx, a, b, VXP_XOR, 0, 0.f, out); }
+int32_t vx_cmp_scalar(vx_ctx ctx, vx_img a, int32_t op, float scalar, vx_img* out) {
+    return unary(ctx, a, VXP_CMPS, op, scalar, out);
+}
+int32_t vx_cmp(vx_ctx ctx, vx_img a, vx_img b, int32_t op, vx_img* out) {
+    return binary(ctx, a, b, VXP_CMP, op, 0.f, out);
+}
+int32_t vx_arith_scalar(vx_ctx ctx, vx_img a, int32_t op, float scalar, vx_img* out) {
+    return unary(ctx, a, VXP_ARITHS, op, scalar, out);
+}
+int32_t vx_arith(vx_ctx ctx, vx_img a, vx_img b, int32_t op, vx_img* out) {
+    return binary(ctx, a, b, VXP_ARITH, op, 0.f, out);
+}
+int32_t vx_cmp_scalar_batch(vx_ctx ctx, vx_img a, int32_t op, const float* scalars, vx_img* out) {
+    VX_REQUIRE(scalars != nullptr, VX_E_INVALID_ARG, "scalars is NULL");
+    vx_op p[2] = {{VXP_LOAD, 0, 0, 0, 0, 0.f}, {VXP_CMPSB, 1, 0, 0, op, 0.f}};
+    return run_pointwise(ctx, p, 2, &a, 1, scalars, 1, 0, out);
+}
+int32_t vx_arith_scalar_batch(vx_ctx ctx, vx_img a, int32_t op, const float* scalars, vx_img* out) {
+    VX_REQUIRE(scalars != nullptr, VX_E_INVALID_ARG, "scalars is NULL");
+    vx_op p[2] = {{VXP_LOAD, 0, 0, 0, 0, 0.f}, {VXP_ARITHSB, 1, 0, 0, op, 0.f}};
+    return run_pointwise(ctx, p, 2, &a, 1, scalars, 1, 0, out);
+}
+int32_t vx_to_f32(vx_ctx ctx, vx_img a, vx_img* out) { return unary(ctx, a, VXP_TOF32, 0, 0.f, out); }
+int32_t vx_to_bool(vx_ctx ctx, vx_img a, vx_img* out) { return unary(ctx, a, VXP_TOBOOL, 0, 0.f, out); }
+int32_t vx_mask(vx_ctx ctx, vx_img a, vx_img m, float fill, vx_img* out) {
+    vx_op p[3] = {{VXP_LOAD, 0, 0, 0, 0, 0.f}, {VXP_LOAD, 1, 1, 0, 0, 0.f}, {VXP_SELECT, 2, 1, 0, 0, fill}};
+    vx_img l[2] = {a, m};
+    return run_pointwise(ctx, p, 3, l, 2, nullptr, 0, 0, out);
+}
+
+}  // extern "C"

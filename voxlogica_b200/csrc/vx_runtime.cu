@@ -1,0 +1,560 @@
+// Runtime of libvoxcuda.so: contexts, image handles (T1 in SURVEY.md section 8a),
+// stream-ordered device memory, per-thread streams, events, profiling.
+//
+// Design notes (B200-first, not a port of anything):
+//  * images never leave HBM between operators; the only host traffic is
+//    vx_upload / vx_download and the nb doubles of a scalar reduction;
+//  * allocation is cudaMallocAsync on the device's default pool with the release
+//    threshold raised to "never", so steady-state alloc/free of intermediates is a
+//    pointer bump ("garbage collection", Greta.pdf p.78-79: the OpenCL backend
+//    either ran out of memory or paid up to 64% for its GC);
+//  * each host thread gets its own CUDA stream per context; handles carry a
+//    `ready` event so a consumer on another stream waits on the device, never on
+//    the host (the F# scheduler calls concurrently from thread-pool threads).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "vx_internal.h"
+
+namespace vx {
+
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+// ---- handle tables ----------------------------------------------------------
+static std::mutex g_tab_mu;
+static std::vector<Image*> g_imgs(1, nullptr);   // slot 0 unused
+static std::vector<uint32_t> g_gen(1, 0);
+static std::vector<uint32_t> g_free_slots;
+static std::vector<Ctx*> g_ctxs(1, nullptr);
+static std::atomic<uint64_t> g_ctx_serial{1};
+
+static uint64_t register_image(Image* im) {
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    uint32_t slot;
+    if (!g_free_slots.empty()) {
+        slot = g_free_slots.back();
+        g_free_slots.pop_back();
+    } else {
+        slot = (uint32_t)g_imgs.size();
+        g_imgs.push_back(nullptr);
+        g_gen.push_back(0);
+    }
+    g_gen[slot]++;
+    g_imgs[slot] = im;
+    im->handle = ((uint64_t)g_gen[slot] << 32) | slot;
+    return im->handle;
+}
+
+Image* get_img(vx_img h) {
+    uint32_t slot = (uint32_t)(h & 0xffffffffu), gen = (uint32_t)(h >> 32);
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    if (slot == 0 || slot >= g_imgs.size() || g_gen[slot] != gen) return nullptr;
+    return g_imgs[slot];
+}
+
+static void unregister_image(Image* im) {
+    uint32_t slot = (uint32_t)(im->handle & 0xffffffffu);
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    g_imgs[slot] = nullptr;
+    g_free_slots.push_back(slot);
+}
+
+Ctx* get_ctx(vx_ctx h) {
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    if (h == 0 || h >= g_ctxs.size()) return nullptr;
+    return g_ctxs[h];
+}
+
+// ---- streams ------------------------------------------------------------------
+int my_stream_index(Ctx* c) {
+    static thread_local std::vector<std::pair<uint64_t, int>> mine;
+    for (auto& p : mine)
+        if (p.first == c->id) return p.second;
+    int idx = c->next_stream.fetch_add(1) % kMaxStreams;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (!c->streams[idx]) {
+            cudaStream_t st = nullptr;
+            if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return 0;
+            c->streams[idx] = st;
+        }
+    }
+    mine.emplace_back(c->id, idx);
+    return idx;
+}
+
+static cudaEvent_t get_event(Ctx* c) {
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (!c->event_pool.empty()) {
+            cudaEvent_t e = c->event_pool.back();
+            c->event_pool.pop_back();
+            return e;
+        }
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    return e;
+}
+static void put_event(Ctx* c, cudaEvent_t e) {
+    if (!e) return;
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->event_pool.push_back(e);
+}
+
+// ---- images -------------------------------------------------------------------
+static size_t dtype_size(int dtype) {
+    switch (dtype) {
+        case VX_U8: return 1;
+        case VX_F32: return 4;
+        case VX_U32: return 4;
+    }
+    return 0;
+}
+
+int new_image(Ctx* c, int dtype, int nx, int ny, int nz, int nb, const float* sp, Image** out) {
+    size_t es = dtype_size(dtype);
+    VX_REQUIRE(es != 0, VX_E_DTYPE, "unknown dtype %d", dtype);
+    VX_REQUIRE(nx > 0 && ny > 0 && nz > 0 && nb > 0, VX_E_INVALID_ARG,
+               "bad shape nx=%d ny=%d nz=%d nb=%d", nx, ny, nz, nb);
+    VX_REQUIRE((size_t)nx * ny * nz < ((size_t)1 << 31), VX_E_UNSUPPORTED,
+               "a single volume must have fewer than 2^31 voxels (slab-decompose it)");
+    int s = my_stream_index(c);
+    Image* im = new Image();
+    im->dtype = dtype;
+    im->nx = nx; im->ny = ny; im->nz = nz; im->nb = nb;
+    if (sp) { im->sp[0] = sp[0]; im->sp[1] = sp[1]; im->sp[2] = sp[2]; }
+    im->bytes = es * im->count();
+    im->ctx = c;
+    im->home = s;
+    // kernels read and write whole 16-element groups: pad the allocation so that the
+    // last group of the batch stays inside it (the padding is never data)
+    size_t alloc = ((im->count() + 15) / 16 * 16) * es + 64;
+    cudaError_t e = cudaMallocAsync(&im->d, alloc, c->streams[s]);
+    if (e != cudaSuccess) {
+        delete im;
+        (void)cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? VX_E_OOM : VX_E_CUDA,
+                    "cudaMallocAsync(%zu bytes) failed: %s", es * (size_t)nx * ny * nz * nb,
+                    cudaGetErrorString(e));
+    }
+    im->ready = get_event(c);
+    c->live_bytes += im->bytes;
+    c->live_handles += 1;
+    register_image(im);
+    *out = im;
+    return VX_OK;
+}
+
+int use_input(Ctx* c, Image* img, int s) {
+    if (img->home != s) VX_CUDA(cudaStreamWaitEvent(c->streams[s], img->ready, 0));
+    return VX_OK;
+}
+
+int done_input(Ctx* c, Image* img, int s) {
+    if (img->home == s) return VX_OK;
+    // a foreign stream read the image: remember when it finishes so that the free
+    // (ordered on the home stream) cannot overtake it
+    std::lock_guard<std::mutex> lk(img->mu);
+    for (auto& p : img->foreign)
+        if (p.first == s) {
+            VX_CUDA(cudaEventRecord(p.second, c->streams[s]));
+            return VX_OK;
+        }
+    cudaEvent_t e = get_event(c);
+    VX_CUDA(cudaEventRecord(e, c->streams[s]));
+    img->foreign.emplace_back(s, e);
+    return VX_OK;
+}
+
+int publish(Ctx* c, Image* img, int s) {
+    VX_CUDA(cudaEventRecord(img->ready, c->streams[s]));
+    return VX_OK;
+}
+
+void drop(Image* im) {
+    if (im->rc.fetch_sub(1) != 1) return;
+    Ctx* c = im->ctx;
+    unregister_image(im);
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != c->device) cudaSetDevice(c->device);
+    cudaStream_t st = c->streams[im->home];
+    for (auto& p : im->foreign) {
+        cudaStreamWaitEvent(st, p.second, 0);
+        put_event(c, p.second);
+    }
+    cudaFreeAsync(im->d, st);
+    put_event(c, im->ready);
+    c->live_bytes -= im->bytes;
+    c->live_handles -= 1;
+    if (prev != c->device && prev >= 0) cudaSetDevice(prev);
+    delete im;
+}
+
+int scratch_alloc(Ctx* c, int s, size_t bytes, void** out) {
+    cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 16, c->streams[s]);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? VX_E_OOM : VX_E_CUDA,
+                    "scratch cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return VX_OK;
+}
+int scratch_free(Ctx* c, int s, void* p) {
+    if (p) VX_CUDA(cudaFreeAsync(p, c->streams[s]));
+    return VX_OK;
+}
+
+int same_shape(const Image* a, const Image* b) {
+    if (a->nx != b->nx || a->ny != b->ny || a->nz != b->nz || a->nb != b->nb)
+        return fail(VX_E_SHAPE_MISMATCH, "shape mismatch: %dx%dx%dx%d vs %dx%dx%dx%d", a->nx,
+                    a->ny, a->nz, a->nb, b->nx, b->ny, b->nz, b->nb);
+    return VX_OK;
+}
+
+// ---- launch accounting ---------------------------------------------------------
+LaunchScope::LaunchScope(Ctx* c_, int s_, const char* name_) : c(c_), s(s_), name(name_) {
+    c->launches.fetch_add(1, std::memory_order_relaxed);
+    if (c->prof_on.load(std::memory_order_relaxed)) {
+        cudaEventCreate(&e0);
+        cudaEventRecord(e0, c->streams[s]);
+    }
+}
+LaunchScope::~LaunchScope() {
+    if (e0) {
+        cudaEvent_t e1 = nullptr;
+        cudaEventCreate(&e1);
+        cudaEventRecord(e1, c->streams[s]);
+        std::lock_guard<std::mutex> lk(c->mu);
+        c->prof.push_back({name, e0, e1});
+    }
+}
+
+int check_launch(const char* name) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return fail(VX_E_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e));
+    return VX_OK;
+}
+
+// ---- OpGuard ----------------------------------------------------------------
+int OpGuard::begin(vx_ctx ctx) {
+    c = get_ctx(ctx);
+    VX_REQUIRE(c != nullptr, VX_E_INVALID_ARG, "invalid context handle");
+    VX_CUDA(cudaSetDevice(c->device));
+    s = my_stream_index(c);
+    st = c->streams[s];
+    return VX_OK;
+}
+int OpGuard::input(vx_img h, Image** out, int want_dtype) {
+    Image* im = get_img(h);
+    VX_REQUIRE(im != nullptr, VX_E_INVALID_ARG, "invalid image handle %llu",
+               (unsigned long long)h);
+    VX_REQUIRE(im->ctx == c, VX_E_INVALID_ARG, "image belongs to another context");
+    VX_REQUIRE(want_dtype == 0 || im->dtype == want_dtype, VX_E_DTYPE,
+               "operand has dtype %d, expected %d", im->dtype, want_dtype);
+    VX_TRY(use_input(c, im, s));
+    ins.push_back(im);
+    *out = im;
+    return VX_OK;
+}
+int OpGuard::finish(Image* out_img, vx_img* out) {
+    for (Image* im : ins) VX_TRY(done_input(c, im, s));
+    VX_TRY(publish(c, out_img, s));
+    *out = out_img->handle;
+    return VX_OK;
+}
+int OpGuard::finish_scalar() {
+    for (Image* im : ins) VX_TRY(done_input(c, im, s));
+    return VX_OK;
+}
+
+}  // namespace vx
+
+using namespace vx;
+
+// =============================================================== C ABI: lifecycle
+extern "C" {
+
+int32_t vx_version(void) { return 100; }
+const char* vx_last_error(void) { return g_err; }
+
+int32_t vx_init(int32_t device, vx_ctx* out) {
+    VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        return fail(VX_E_CUDA, "no CUDA device available (%s); libvoxcuda has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    VX_REQUIRE(device >= 0 && device < n, VX_E_INVALID_ARG, "device %d out of range [0,%d)",
+               device, n);
+    VX_CUDA(cudaSetDevice(device));
+    Ctx* c = new Ctx();
+    c->device = device;
+    VX_CUDA(cudaDeviceGetDefaultMemPool(&c->pool, device));
+    uint64_t never = UINT64_MAX;
+    VX_CUDA(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &never));
+    {
+        std::lock_guard<std::mutex> lk(g_tab_mu);
+        c->id = g_ctxs.size();
+        g_ctxs.push_back(c);
+    }
+    *out = c->id;
+    return VX_OK;
+}
+
+int32_t vx_shutdown(vx_ctx ctx) {
+    Ctx* c = get_ctx(ctx);
+    VX_REQUIRE(c != nullptr, VX_E_INVALID_ARG, "invalid context handle");
+    VX_CUDA(cudaSetDevice(c->device));
+    for (int i = 0; i < kMaxStreams; i++)
+        if (c->streams[i]) cudaStreamSynchronize(c->streams[i]);
+    // images still alive keep pointing at the context; the context object itself is
+    // retained (leaked) so late vx_release calls from finalisers stay safe.
+    if (c->flush_buf) { cudaFree(c->flush_buf); c->flush_buf = nullptr; }
+    return VX_OK;
+}
+
+int32_t vx_sync(vx_ctx ctx) {
+    Ctx* c = get_ctx(ctx);
+    VX_REQUIRE(c != nullptr, VX_E_INVALID_ARG, "invalid context handle");
+    VX_CUDA(cudaSetDevice(c->device));
+    for (int i = 0; i < kMaxStreams; i++)
+        if (c->streams[i]) VX_CUDA(cudaStreamSynchronize(c->streams[i]));
+    return VX_OK;
+}
+
+int32_t vx_upload_batch(vx_ctx ctx, const void* host, int32_t dtype, int32_t nx, int32_t ny,
+                        int32_t nz, int32_t nb, const float* spacing, vx_img* out) {
+    VX_REQUIRE(host != nullptr && out != nullptr, VX_E_INVALID_ARG, "NULL argument");
+    OpGuard g;
+    VX_TRY(g.begin(ctx));
+    Image* im = nullptr;
+    VX_TRY(new_image(g.c, dtype, nx, ny, nz, nb, spacing, &im));
+    cudaError_t e = cudaMemcpyAsync(im->d, host, im->bytes, cudaMemcpyHostToDevice, g.st);
+    if (e != cudaSuccess) {
+        drop(im);
+        return fail(VX_E_CUDA, "upload failed: %s", cudaGetErrorString(e));
+    }
+    return g.finish(im, out);
+}
+
+int32_t vx_upload(vx_ctx ctx, const void* host, int32_t dtype, int32_t nx, int32_t ny, int32_t nz,
+                  const float* spacing, vx_img* out) {
+    return vx_upload_batch(ctx, host, dtype, nx, ny, nz, 1, spacing, out);
+}
+
+int32_t vx_download(vx_ctx ctx, vx_img img, void* host, size_t bytes) {
+    VX_REQUIRE(host != nullptr, VX_E_INVALID_ARG, "host is NULL");
+    OpGuard g;
+    VX_TRY(g.begin(ctx));
+    Image* im = nullptr;
+    VX_TRY(g.input(img, &im, 0));
+    VX_REQUIRE(bytes == im->bytes, VX_E_INVALID_ARG, "download size %zu != image size %zu", bytes,
+               im->bytes);
+    VX_CUDA(cudaMemcpyAsync(host, im->d, bytes, cudaMemcpyDeviceToHost, g.st));
+    VX_CUDA(cudaStreamSynchronize(g.st));
+    return g.finish_scalar();
+}
+
+int32_t vx_info(vx_img img, int32_t* dtype, int32_t* nx, int32_t* ny, int32_t* nz, int32_t* nb,
+                float* spacing3) {
+    Image* im = get_img(img);
+    VX_REQUIRE(im != nullptr, VX_E_INVALID_ARG, "invalid image handle");
+    if (dtype) *dtype = im->dtype;
+    if (nx) *nx = im->nx;
+    if (ny) *ny = im->ny;
+    if (nz) *nz = im->nz;
+    if (nb) *nb = im->nb;
+    if (spacing3) { spacing3[0] = im->sp[0]; spacing3[1] = im->sp[1]; spacing3[2] = im->sp[2]; }
+    return VX_OK;
+}
+
+int32_t vx_retain(vx_img img) {
+    Image* im = get_img(img);
+    VX_REQUIRE(im != nullptr, VX_E_INVALID_ARG, "invalid image handle");
+    im->rc.fetch_add(1);
+    return VX_OK;
+}
+
+int32_t vx_release(vx_img img) {
+    Image* im = get_img(img);
+    VX_REQUIRE(im != nullptr, VX_E_INVALID_ARG, "invalid image handle");
+    drop(im);
+    return VX_OK;
+}
+
+int32_t vx_batch_slice(vx_ctx ctx, vx_img img, int32_t first, int32_t count, vx_img* out) {
+    VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");
+    OpGuard g;
+    VX_TRY(g.begin(ctx));
+    Image* im = nullptr;
+    VX_TRY(g.input(img, &im, 0));
+    VX_REQUIRE(first >= 0 && count > 0 && first + count <= im->nb, VX_E_INVALID_ARG,
+               "slice [%d,%d) outside batch of %d", first, first + count, im->nb);
+    Image* o = nullptr;
+    VX_TRY(new_image(g.c, im->dtype, im->nx, im->ny, im->nz, count, im->sp, &o));
+    size_t per = im->bytes / im->nb;
+    cudaError_t e = cudaMemcpyAsync(o->d, (const char*)im->d + per * first, per * count,
+                                    cudaMemcpyDeviceToDevice, g.st);
+    if (e != cudaSuccess) {
+        drop(o);
+        return fail(VX_E_CUDA, "slice copy failed: %s", cudaGetErrorString(e));
+    }
+    return g.finish(o, out);
+}
+
+int32_t vx_host_alloc(size_t bytes, void** out) {
+    VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");
+    VX_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+    return VX_OK;
+}
+int32_t vx_host_free(void* p) {
+    if (p) VX_CUDA(cudaFreeHost(p));
+    return VX_OK;
+}
+
+int32_t vx_mem_info(vx_ctx ctx, uint64_t* live_bytes, uint64_t* live_handles,
+                    uint64_t* pool_reserved) {
+    Ctx* c = get_ctx(ctx);
+    VX_REQUIRE(c != nullptr, VX_E_INVALID_ARG, "invalid context handle");
+    if (live_bytes) *live_bytes = c->live_bytes.load();
+    if (live_handles) *live_handles = c->live_handles.load();
+    if (pool_reserved) {
+        uint64_t v = 0;
+        VX_CUDA(cudaMemPoolGetAttribute(c->pool, cudaMemPoolAttrReservedMemCurrent, &v));
+        *pool_reserved = v;
+    }
+    return VX_OK;
+}
+
+int32_t vx_mem_trim(vx_ctx ctx, uint64_t keep_bytes) {
+    Ctx* c = get_ctx(ctx);
+    VX_REQUIRE(c != nullptr, VX_E_INVALID_ARG, "invalid context handle");
+    VX_CUDA(cudaSetDevice(c->device));
+    VX_TRY(vx_sync(ctx));
+    VX_CUDA(cudaMemPoolTrimTo(c->pool, (size_t)keep_bytes));
+    return VX_OK;
+}
+
+// ------------------------------------------------------------------ measurement
+int32_t vx_event_create(vx_ctx ctx, vx_evt* out) {
+    Ctx* c = get_ctx(ctx);
+    VX_REQUIRE(c != nullptr && out != nullptr, VX_E_INVALID_ARG, "invalid argument");
+    VX_CUDA(cudaSetDevice(c->device));
+    cudaEvent_t e;
+    VX_CUDA(cudaEventCreate(&e));
+    *out = (vx_evt)(uintptr_t)e;
+    return VX_OK;
+}
+int32_t vx_event_record(vx_ctx ctx, vx_evt ev) {
+    Ctx* c = get_ctx(ctx);
+    VX_REQUIRE(c != nullptr && ev != 0, VX_E_INVALID_ARG, "invalid argument");
+    VX_CUDA(cudaSetDevice(c->device));
+    int s = my_stream_index(c);
+    VX_CUDA(cudaEventRecord((cudaEvent_t)(uintptr_t)ev, c->streams[s]));
+    return VX_OK;
+}
+int32_t vx_event_sync(vx_evt ev) {
+    VX_REQUIRE(ev != 0, VX_E_INVALID_ARG, "invalid event");
+    VX_CUDA(cudaEventSynchronize((cudaEvent_t)(uintptr_t)ev));
+    return VX_OK;
+}
+int32_t vx_event_elapsed_ms(vx_evt start, vx_evt stop, float* ms) {
+    VX_REQUIRE(start != 0 && stop != 0 && ms != nullptr, VX_E_INVALID_ARG, "invalid argument");
+    VX_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)(uintptr_t)start, (cudaEvent_t)(uintptr_t)stop));
+    return VX_OK;
+}
+int32_t vx_event_destroy(vx_evt ev) {
+    if (ev) VX_CUDA(cudaEventDestroy((cudaEvent_t)(uintptr_t)ev));
+    return VX_OK;
+}
+
+int32_t vx_launch_count(vx_ctx ctx, uint64_t* out) {
+    Ctx* c = get_ctx(ctx);
+    VX_REQUIRE(c != nullptr && out != nullptr, VX_E_INVALID_ARG, "invalid argument");
+    *out = c->launches.load();
+    return VX_OK;
+}
+
+int32_t vx_prof_enable(vx_ctx ctx, int32_t on) {
+    Ctx* c = get_ctx(ctx);
+    VX_REQUIRE(c != nullptr, VX_E_INVALID_ARG, "invalid context handle");
+    c->prof_on.store(on ? 1 : 0);
+    return VX_OK;
+}
+
+static int prof_drain(Ctx* c) {
+    std::vector<ProfRec> recs;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        recs.swap(c->prof);
+    }
+    for (auto& r : recs) {
+        float ms = 0.f;
+        cudaEventSynchronize(r.e1);
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+            std::lock_guard<std::mutex> lk(c->mu);
+            auto& acc = c->prof_acc[r.name];
+            acc.first += 1;
+            acc.second += ms;
+        }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    return VX_OK;
+}
+
+int32_t vx_prof_reset(vx_ctx ctx) {
+    Ctx* c = get_ctx(ctx);
+    VX_REQUIRE(c != nullptr, VX_E_INVALID_ARG, "invalid context handle");
+    VX_CUDA(cudaSetDevice(c->device));
+    prof_drain(c);
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->prof_acc.clear();
+    return VX_OK;
+}
+
+int32_t vx_prof_report(vx_ctx ctx, char* buf, size_t buf_bytes) {
+    Ctx* c = get_ctx(ctx);
+    VX_REQUIRE(c != nullptr && buf != nullptr && buf_bytes > 0, VX_E_INVALID_ARG,
+               "invalid argument");
+    VX_CUDA(cudaSetDevice(c->device));
+    prof_drain(c);
+    std::lock_guard<std::mutex> lk(c->mu);
+    size_t off = 0;
+    buf[0] = 0;
+    for (auto& kv : c->prof_acc) {
+        int n = snprintf(buf + off, buf_bytes - off, "%s %llu %.6f\n", kv.first.c_str(),
+                         (unsigned long long)kv.second.first, kv.second.second);
+        if (n < 0 || (size_t)n >= buf_bytes - off) break;
+        off += n;
+    }
+    return VX_OK;
+}
+
+int32_t vx_flush_l2(vx_ctx ctx) {
+    OpGuard g;
+    VX_TRY(g.begin(ctx));
+    Ctx* c = g.c;
+    if (!c->flush_buf) {
+        c->flush_bytes = (size_t)256 << 20;  // 2x the 126 MB L2
+        VX_CUDA(cudaMalloc(&c->flush_buf, c->flush_bytes));
+    }
+    VX_CUDA(cudaMemsetAsync(c->flush_buf, 0, c->flush_bytes, g.st));
+    return VX_OK;
+}
+
+}  // extern "C"

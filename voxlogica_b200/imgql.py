@@ -1,0 +1,400 @@
+"""Minimal ImgQL driver: tokenizer, parser, memoising evaluator over the C-ABI operators.
+
+SURVEY.md section 8(f) rank 1.  VoxLogicA's real front end (F# parser + reducer, Greta.pdf
+p.7 "syntactic manipulation, memoization") is neither mounted nor runnable here, so this
+small driver exists to run specs such as the GTV one on Greta.pdf p.48 *unchanged* on top
+of libvoxcuda.  It is a harness, not a re-implementation of VoxLogicA: it supports
+
+    import "stdlib.imgql"          load x = "file"         let x = e
+    let f(a, b) = e                save "file" e           print "label" e
+
+with function application, numbers, prefix ``!`` and the dotted infix operators
+(``<. >. <=. >=. =.`` image-vs-number, ``.< .> ...`` number-vs-image, ``+ - * /`` on
+images, ``+. .+ .+.`` mixed / numeric, ``& |`` boolean).  Every operator evaluates to a
+call into ``ops.Context``; identical sub-terms are evaluated once (hash-consing), which is
+the memoisation the reference's evaluator performs.
+
+The derived operators are restated from the slide semantics in
+STDLIB below; the real stdlib.imgql is not in the mount.
+"""
+from __future__ import annotations
+
+import re
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .ops import Context, Image
+
+STDLIB = """
+// derived operators, restated (Greta.pdf p.35-38, p.48, p.51-53)
+let complement(a) = !a
+let not(a) = !a
+let and(a,b) = a & b
+let or(a,b) = a | b
+let N(a) = near(a)
+let I(a) = interior(a)
+let touch(a,b) = a & through(near(b), a)
+let grow(a,b) = a | touch(b,a)
+let flt(r,a) = distlt(r, distgeq(r, !a))
+let filter(r,a) = flt(r,a)
+let reach(t,p) = near(t) | near(through(near(t), p))
+let surrounded(a,b) = a & !reach(!(a | b), !b)
+"""
+
+GTV_SPEC = """
+import "stdlib.imgql"
+load flair = "flair"
+let similarTo(a) = crossCorrelation(5, intensity(flair), intensity(flair), a, min(intensity(flair)), max(intensity(flair)), 100)
+// Greta.pdf p.48 (Image290), constants per SURVEY.md Q5
+let background   = touch(intensity(flair) <. 0.1, border)
+let brain        = complement(background)
+let normFlair    = percentiles(intensity(flair), brain)
+let hyperIntense = filter(5.0, normFlair >. 0.95)
+let veryIntense  = filter(2.0, normFlair >. 0.86)
+let growTum      = grow(hyperIntense, veryIntense)
+let tumSim       = similarTo(growTum)
+let tumStatCC    = filter(2.0, tumSim >. 0.6)
+let gtv          = grow(growTum, tumStatCC)
+save "gtv" gtv
+print "gtvVolume" volume(gtv)
+"""
+
+# ---------------------------------------------------------------------------- lexer
+_TOKEN = re.compile(r"""
+    (?P<ws>\s+|//[^\n]*)
+  | (?P<num>\d+\.\d*(?:[eE][-+]?\d+)?|\.\d+(?:[eE][-+]?\d+)?|\d+(?:[eE][-+]?\d+)?)
+  | (?P<id>[A-Za-z_][A-Za-z0-9_]*)
+  | (?P<str>"[^"]*")
+  | (?P<punct>[(),])
+  | (?P<op>[!<>=.&|+\-*/^~%#@$]+)
+""", re.X)
+
+
+def tokenize(src: str) -> List[Tuple[str, str]]:
+    out, pos = [], 0
+    while pos < len(src):
+        m = _TOKEN.match(src, pos)
+        if not m:
+            raise SyntaxError(f"ImgQL: unexpected character {src[pos]!r} at offset {pos}")
+        pos = m.end()
+        kind = m.lastgroup
+        if kind == "ws":
+            continue
+        text = m.group()
+        if kind == "op" and text == "=":
+            kind = "eq"
+        out.append((kind, text))
+    out.append(("eof", ""))
+    return out
+
+
+# ---------------------------------------------------------------------------- AST
+@dataclass(frozen=True)
+class Num:
+    v: float
+
+
+@dataclass(frozen=True)
+class Var:
+    name: str
+
+
+@dataclass(frozen=True)
+class Call:
+    fn: str
+    args: tuple
+
+
+_PREC = {"|": 1, "&": 2, "<": 3, "<=": 3, ">": 3, ">=": 3, "=": 3, "==": 3, "!=": 3,
+         "+": 4, "-": 4, "*": 5, "/": 5}
+
+
+class Parser:
+    def __init__(self, src: str):
+        self.t = tokenize(src)
+        self.i = 0
+
+    def peek(self):
+        return self.t[self.i]
+
+    def next(self):
+        tok = self.t[self.i]
+        self.i += 1
+        return tok
+
+    def expect(self, kind, text=None):
+        k, s = self.next()
+        if k != kind or (text is not None and s != text):
+            raise SyntaxError(f"ImgQL: expected {text or kind}, found {s!r}")
+        return s
+
+    def program(self):
+        stmts = []
+        while self.peek()[0] != "eof":
+            k, s = self.next()
+            if k != "id":
+                raise SyntaxError(f"ImgQL: expected a statement, found {s!r}")
+            if s == "import":
+                stmts.append(("import", self.expect("str").strip('"')))
+            elif s == "load":
+                name = self.expect("id")
+                self.expect("eq")
+                stmts.append(("load", name, self.expect("str").strip('"')))
+            elif s == "let":
+                k2, name = self.next()
+                if k2 not in ("id", "op"):
+                    raise SyntaxError(f"ImgQL: bad name {name!r} in let")
+                params = None
+                if self.peek() == ("punct", "("):
+                    self.next()
+                    params = []
+                    while self.peek() != ("punct", ")"):
+                        params.append(self.expect("id"))
+                        if self.peek() == ("punct", ","):
+                            self.next()
+                    self.next()
+                self.expect("eq")
+                stmts.append(("let", name, params, self.expr(0)))
+            elif s == "save":
+                path = self.expect("str").strip('"')
+                stmts.append(("save", path, self.expr(0)))
+            elif s == "print":
+                label = self.expect("str").strip('"')
+                stmts.append(("print", label, self.expr(0)))
+            else:
+                raise SyntaxError(f"ImgQL: unknown statement {s!r}")
+        return stmts
+
+    def expr(self, minprec):
+        lhs = self.unary()
+        while True:
+            k, s = self.peek()
+            if k == "eq":
+                k, s = "op", "="
+            if k != "op":
+                break
+            core = s.strip(".")
+            if core not in _PREC or _PREC[core] < minprec:
+                break
+            self.next()
+            rhs = self.expr(_PREC[core] + 1)
+            lhs = Call("infix:" + s, (lhs, rhs))
+        return lhs
+
+    def unary(self):
+        k, s = self.peek()
+        if k == "op" and s == "!":
+            self.next()
+            return Call("prefix:!", (self.unary(),))
+        if k == "op" and s == "-":
+            self.next()
+            return Call("neg", (self.unary(),))
+        return self.atom()
+
+    def atom(self):
+        k, s = self.next()
+        if k == "num":
+            return Num(float(s))
+        if k == "punct" and s == "(":
+            e = self.expr(0)
+            self.expect("punct", ")")
+            return e
+        if k == "id":
+            if self.peek() == ("punct", "("):
+                self.next()
+                args = []
+                while self.peek() != ("punct", ")"):
+                    args.append(self.expr(0))
+                    if self.peek() == ("punct", ","):
+                        self.next()
+                self.next()
+                return Call(s, tuple(args))
+            return Var(s)
+        raise SyntaxError(f"ImgQL: unexpected token {s!r}")
+
+
+# ---------------------------------------------------------------------------- evaluator
+class Number:
+    """An ImgQL number: one value per volume of the batch."""
+
+    def __init__(self, v):
+        self.v = np.atleast_1d(np.asarray(v, dtype=np.float64))
+
+    def __repr__(self):
+        return f"Number({self.v.tolist()})"
+
+
+def _is_img(v):
+    return isinstance(v, Image)
+
+
+class Interpreter:
+    def __init__(self, ctx: Context, loader: Optional[Callable[[str], Image]] = None, conn: int = 26):
+        self.ctx = ctx
+        self.loader = loader
+        self.conn = conn                     # adjacency of near/through
+        self.globals: Dict[str, object] = {}
+        self.functions: Dict[str, Tuple[List[str], object]] = {}
+        self.base: Optional[Image] = None    # shape provider for border / tt / ff
+        self.memo: Dict[tuple, object] = {}
+        self.saved: Dict[str, Image] = {}
+        self.printed: Dict[str, object] = {}
+        self.n_tasks = 0                     # operator calls actually executed
+
+    # -- program level
+    def run(self, src: str):
+        for st in Parser(src).program():
+            kind = st[0]
+            if kind == "import":
+                if st[1].endswith("stdlib.imgql"):
+                    self.run(STDLIB)
+                else:
+                    with open(st[1]) as f:
+                        self.run(f.read())
+            elif kind == "load":
+                if self.loader is None:
+                    raise RuntimeError("ImgQL: no loader configured for `load`")
+                img = self.loader(st[2])
+                self.globals[st[1]] = img
+                if self.base is None:
+                    self.base = img
+            elif kind == "let":
+                _, name, params, body = st
+                if params is None:
+                    self.globals[name] = self.eval(body, {})
+                else:
+                    self.functions[name] = (params, body)
+            elif kind == "save":
+                self.saved[st[1]] = self.eval(st[2], {})
+            elif kind == "print":
+                v = self.eval(st[2], {})
+                self.printed[st[1]] = v.v.copy() if isinstance(v, Number) else v
+        return self
+
+    # -- expression level.  Values are identified by id() for hash-consing.
+    def eval(self, e, env):
+        if isinstance(e, Num):
+            return Number(e.v)
+        if isinstance(e, Var):
+            if e.name in env:
+                return env[e.name]
+            if e.name in self.globals:
+                return self.globals[e.name]
+            if e.name in ("border", "tt", "ff"):
+                return self.apply(e.name, [])
+            raise NameError(f"ImgQL: unbound identifier {e.name!r}")
+        if isinstance(e, Call):
+            args = [self.eval(a, env) for a in e.args]
+            if e.fn in self.functions:
+                params, body = self.functions[e.fn]
+                if len(params) != len(args):
+                    raise TypeError(f"ImgQL: {e.fn} takes {len(params)} arguments")
+                return self.eval(body, dict(zip(params, args)))
+            return self.apply(e.fn, args)
+        raise TypeError(e)
+
+    def _key(self, fn, args):
+        ks = []
+        for a in args:
+            if isinstance(a, Number):
+                ks.append(("n", a.v.tobytes()))
+            else:
+                ks.append(("i", id(a)))
+        return (fn, tuple(ks))
+
+    def apply(self, fn, args):
+        key = self._key(fn, args)
+        if key in self.memo:
+            return self.memo[key][0]
+        val = self._apply(fn, args)
+        self.memo[key] = (val, args)   # keep args alive so id() stays unique
+        self.n_tasks += 1
+        return val
+
+    def _like(self) -> Image:
+        if self.base is None:
+            raise RuntimeError("ImgQL: border/tt/ff need a loaded image for their shape")
+        return self.base
+
+    def _apply(self, fn, a):
+        c = self.ctx
+        if fn.startswith("infix:"):
+            return self._infix(fn[6:], a[0], a[1])
+        if fn == "prefix:!":
+            return c.not_(a[0])
+        if fn == "neg":
+            return Number(-a[0].v) if isinstance(a[0], Number) else c.arith_scalar(a[0], "r-", 0.0)
+        table = {
+            "intensity": lambda x: x,     # single-channel images: the identity
+            "border": lambda: c.border(self._like()),
+            "tt": lambda: c.tt(self._like()),
+            "ff": lambda: c.ff(self._like()),
+            "near": lambda x: c.near(x, self.conn),
+            "interior": lambda x: c.interior(x, self.conn),
+            "through": lambda x, y: c.through(x, y, self.conn),
+            "maxvol": lambda x: c.maxvol(x, self.conn),
+            "distlt": lambda r, x: c.distlt(r.v[0], x),
+            "distleq": lambda r, x: c.distleq(r.v[0], x),
+            "distgeq": lambda r, x: c.distgeq(r.v[0], x),
+            "distgt": lambda r, x: c.distgt(r.v[0], x),
+            "dt": lambda x: c.edt_signed(x, self.conn),
+            "edt": lambda x: c.edt(x),
+            "volume": lambda x: Number(c.volume(x)),
+            "min": lambda x: Number(c.min(x)),
+            "max": lambda x: Number(c.max(x)),
+            "constant": lambda v: c.constant(self._like(), v.v[0]),
+            "mask": lambda x, m: c.mask(x, m, 0.0),
+            "percentiles": lambda x, m, corr=None: c.percentiles(x, m, 0.0 if corr is None else corr.v[0]),
+            "crossCorrelation": lambda rho, x, y, reg, m, M, k: c.cross_correlation(
+                rho.v[0], x, y, reg, m.v, M.v, int(k.v[0])),
+        }
+        if fn not in table:
+            raise NameError(f"ImgQL: unknown operator {fn!r}")
+        return table[fn](*a)
+
+    def _infix(self, op, l, r):
+        c = self.ctx
+        core = op.strip(".")
+        cmp_map = {"<": "<", "<=": "<=", ">": ">", ">=": ">=", "=": "==", "==": "==", "!=": "!="}
+        swap = {"<": ">", "<=": ">=", ">": "<", ">=": "<=", "==": "==", "!=": "!="}
+        if core in ("&", "|"):
+            return c.and_(l, r) if core == "&" else c.or_(l, r)
+        li, ri = _is_img(l), _is_img(r)
+        scal = lambda n: n.v[0] if n.v.size == 1 else n.v
+        if core in cmp_map:
+            k = cmp_map[core]
+            if li and ri:
+                return c.cmp(l, k, r)
+            if li:
+                return c.cmp_scalar(l, k, scal(r))
+            if ri:
+                return c.cmp_scalar(r, swap[k], scal(l))
+            return Number({"<": np.less, "<=": np.less_equal, ">": np.greater, ">=": np.greater_equal,
+                           "==": np.equal, "!=": np.not_equal}[k](l.v, r.v).astype(np.float64))
+        if core in ("+", "-", "*", "/"):
+            if li and ri:
+                return c.arith(l, core, r)
+            if li:
+                return c.arith_scalar(l, core, scal(r))
+            if ri:
+                rop = {"+": "+", "*": "*", "-": "r-", "/": "r/"}[core]
+                return c.arith_scalar(r, rop, scal(l))
+            return Number({"+": np.add, "-": np.subtract, "*": np.multiply, "/": np.divide}[core](l.v, r.v))
+        raise NameError(f"ImgQL: unknown infix operator {op!r}")
+
+
+def run_spec(ctx: Context, src: str, images: Dict[str, Image], conn: int = 26) -> Interpreter:
+    """Run an ImgQL spec whose `load` statements name entries of ``images``."""
+    it = Interpreter(ctx, loader=lambda name: images[name], conn=conn)
+    return it.run(src)
+
+
+def run_gtv(ctx: Context, flair: Image, conn: int = 26) -> Dict[str, object]:
+    """The BraTS GTV segmentation spec of Greta.pdf p.48 on a (batched) FLAIR image."""
+    it = run_spec(ctx, GTV_SPEC, {"flair": flair}, conn)
+    out = dict(it.globals)
+    out["_tasks"] = it.n_tasks
+    out["_printed"] = it.printed
+    return out

@@ -1,0 +1,101 @@
+"""Synthetic inputs of SURVEY.md section 8(d): BraTS-shaped FLAIR-like volumes, a DFS maze
+PNG-like image and the 512^3-style binary microbenchmark volumes.  Host-side numpy only;
+used by bench.py, the tests and smoke().  (BraTS data itself is not available here.)"""
+from __future__ import annotations
+
+import numpy as np
+from scipy import ndimage as ndi
+
+BRATS_SHAPE = (155, 240, 240)  # [nz][ny][nx]  = 8,928,000 voxels (Greta.pdf p.48 "9 M voxels")
+
+
+def _smooth_noise(rng, shape, coarse=12):
+    """band-limited noise in [0,1]: coarse grid, trilinear zoom (fast at full BraTS size)"""
+    cs = tuple(max(2, int(np.ceil(s / coarse)) + 1) for s in shape)
+    c = rng.random(cs).astype(np.float32)
+    z = ndi.zoom(c, [s / k for s, k in zip(shape, cs)], order=1, mode="nearest", grid_mode=True)
+    z = z[: shape[0], : shape[1], : shape[2]]
+    pad = [(0, s - t) for s, t in zip(shape, z.shape)]
+    if any(p[1] for p in pad):
+        z = np.pad(z, pad, mode="edge")
+    return z
+
+
+def brats_like(seed: int = 1234, shape=BRATS_SHAPE) -> np.ndarray:
+    """f32 [nz][ny][nx] in [0,1]: ellipsoidal head of smooth low-frequency tissue noise in
+    [0.15,0.6], background exactly 0 with a thin dim rim (< 0.1) around the head, 1-3
+    ellipsoidal hyper-intense lesions (0.8-1.0) each with a 0.65-0.8 halo, Gaussian noise
+    sigma 0.02 inside the head, clipped to [0,1]  (SURVEY.md section 8d, config 2)."""
+    rng = np.random.default_rng(seed)
+    nz, ny, nx = shape
+    z, y, x = np.meshgrid(np.arange(nz, dtype=np.float32), np.arange(ny, dtype=np.float32),
+                          np.arange(nx, dtype=np.float32), indexing="ij", sparse=True)
+    cz, cy, cx = (nz - 1) / 2, (ny - 1) / 2, (nx - 1) / 2
+    az, ay, ax = 65 / 155 * nz, 100 / 240 * ny, 85 / 240 * nx        # semi-axes
+    rr = ((z - cz) / az) ** 2 + ((y - cy) / ay) ** 2 + ((x - cx) / ax) ** 2
+    head = rr <= 1.0
+    rim = (rr > 1.0) & (rr <= 1.06)
+    vol = np.zeros(shape, np.float32)
+    tissue = 0.15 + 0.45 * _smooth_noise(rng, shape)
+    vol[head] = tissue[head]
+    scale = min(nz / 155, ny / 240, nx / 240)
+    for _ in range(int(rng.integers(1, 4))):
+        r = rng.uniform(8, 25) * scale
+        # keep lesions inside the head
+        lz = cz + rng.uniform(-0.45, 0.45) * az
+        ly = cy + rng.uniform(-0.45, 0.45) * ay
+        lx = cx + rng.uniform(-0.45, 0.45) * ax
+        ez, ey, ex = r * rng.uniform(0.7, 1.0), r * rng.uniform(0.7, 1.0), r * rng.uniform(0.7, 1.0)
+        d = ((z - lz) / ez) ** 2 + ((y - ly) / ey) ** 2 + ((x - lx) / ex) ** 2
+        core = d <= 1.0
+        halo = (d > 1.0) & (d <= 1.7) & head
+        vol[halo] = np.maximum(vol[halo], rng.uniform(0.65, 0.8))
+        vol[core & head] = rng.uniform(0.8, 1.0)
+    noise = rng.normal(0.0, 0.02, size=shape).astype(np.float32)
+    vol = np.where(head, vol + noise, vol)
+    vol[rim] = rng.uniform(0.0, 0.09, size=int(rim.sum())).astype(np.float32)
+    return np.clip(vol, 0.0, 1.0).astype(np.float32)
+
+
+def brats_batch(seeds, shape=BRATS_SHAPE) -> np.ndarray:
+    return np.stack([brats_like(int(s), shape) for s in seeds])
+
+
+def maze(n_cells: int = 512, seed: int = 0):
+    """Perfect maze by randomised DFS on n_cells x n_cells cells -> RGB uint8 image of
+    (2n+1)^2 pixels: walls black, corridors white, start cell blue, exit cell green
+    (the reference's maze PNG is not in the mount)."""
+    rng = np.random.default_rng(seed)
+    n = n_cells
+    img = np.zeros((2 * n + 1, 2 * n + 1, 3), np.uint8)
+    seen = np.zeros((n, n), bool)
+    stack = [(0, 0)]
+    seen[0, 0] = True
+    img[1, 1] = 255
+    dirs = [(0, 1), (1, 0), (0, -1), (-1, 0)]
+    while stack:
+        cy, cx = stack[-1]
+        order = rng.permutation(4)
+        for k in order:
+            dy, dx = dirs[k]
+            yy, xx = cy + dy, cx + dx
+            if 0 <= yy < n and 0 <= xx < n and not seen[yy, xx]:
+                seen[yy, xx] = True
+                img[2 * cy + 1 + dy, 2 * cx + 1 + dx] = 255
+                img[2 * yy + 1, 2 * xx + 1] = 255
+                stack.append((yy, xx))
+                break
+        else:
+            stack.pop()
+    img[1, 1] = (0, 0, 255)
+    img[2 * n - 1, 2 * n - 1] = (0, 255, 0)
+    return img
+
+
+def bernoulli_volume(shape, p: float, seed: int = 7) -> np.ndarray:
+    return (np.random.default_rng(seed).random(shape, dtype=np.float32) < p).astype(np.uint8)
+
+
+def blob_volume(shape, seed: int = 7, coarse: int = 24, q: float = 0.6) -> np.ndarray:
+    s = _smooth_noise(np.random.default_rng(seed), shape, coarse)
+    return (s > np.quantile(s[::4, ::4, ::4], q)).astype(np.uint8)
