@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- BraTS-shape GTV-spec throughput (volumes/s), the metric of BASELINE.json.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm on the host cores
+
+A "step" is one pass of the whole GTV segmentation spec (Greta.pdf p.48) over one batch
+of synthetic BraTS-shaped volumes (240x240x155 f32) per
+GPU, driven through the ImgQL driver -> ctypes -> libvoxcuda.so (the C ABI).
+  value : volumes/s with the batch already resident in HBM (weak scaling: every rank
+          owns its own batch; the path shards by volume, no data-path collective).
+  e2e   : the same with the batch in pinned HOST memory: H2D of the f32 volumes and D2H
+          of the u8 GTV masks inside the timed region.
+  roofline     : dominant kernel by device time, algorithmic bytes / CUDA-event time
+                 against the measured HBM copy peak (MEASURED_PEAKS.json).
+  cpu_baseline : the CPU oracle (a port: the reference implementation is not mounted)
+                 timed on this box's host cores on a bounded sample.
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "brats_gtv_spec_throughput"
+UNIT = "volumes/s"
+BRATS = (155, 240, 240)
+NVOX = BRATS[0] * BRATS[1] * BRATS[2]
+# algorithmic HBM bytes per voxel per launch (SURVEY.md section 8d / DESIGN.md kernel table)
+ALG_BYTES = {
+    "xcorr_kernel": 5.0,             # u8 bins in, f32 coefficient out (13 B/voxel for the whole operator)
+    "pointwise_program_kernel": None,  # depends on the program; reported per launch mix
+    "morph16_kernel": 2.0, "ball_or_kernel": 1.0 + 1.0 / 8, "pack_bits_kernel": 1.0 + 1.0 / 8,
+    "ccl_init_kernel": 5.0, "ccl_merge_kernel": 4.0, "ccl_select_kernel": 5.0, "ccl_seed_kernel": 1.0,
+    "xc_bin_kernel": 5.0, "xc_region_hist_kernel": 5.0, "pc_compact_kernel": 5.0, "pc_rank_kernel": 12.0,
+    "rs_hist_kernel": 4.0, "rs_scatter_kernel": 16.0, "reduce_f32_kernel": 4.0, "reduce_volume_kernel": 1.0,
+    "border_kernel": 1.0, "edt_x_kernel": 5.0, "edt_axis_kernel_y": 8.0, "edt_axis_kernel_z": 8.0,
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (profiling guide)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_batch(batch: int, rank: int, shape=BRATS) -> np.ndarray:
+    """`batch` distinct BraTS-like volumes: up to 4 generated (seeds per SURVEY 8d config 5),
+    the rest are axis flips of them (distinct data, identical statistics; generation of
+    a full-size volume costs ~1 s of host time)."""
+    from voxlogica_b200.synth import brats_like
+    uniq = min(batch, 4)
+    base = [brats_like(seed=rank * 64 + i, shape=shape) for i in range(uniq)]
+    vols = []
+    for i in range(batch):
+        v = base[i % uniq]
+        f = i // uniq
+        if f & 1:
+            v = v[:, :, ::-1]
+        if f & 2:
+            v = v[:, ::-1, :]
+        if f & 4:
+            v = v[::-1, :, :]
+        vols.append(np.ascontiguousarray(v))
+    return np.stack(vols)
+
+
+# --------------------------------------------------------------------------------- CPU arm
+def cpu_gtv_sample(n_threads: int, shape, seed=1234):
+    """One GTV spec pass of the CPU oracle on one volume of `shape`.  Returns seconds."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ["OMP_NUM_THREADS"] = str(n_threads)
+    import oracle as orc
+    from gtv_ref import gtv_oracle
+    from voxlogica_b200.synth import brats_like
+    vol = brats_like(seed=seed, shape=shape)
+    orc.lib()
+    t0 = time.perf_counter()
+    gtv_oracle(orc, vol)
+    return time.perf_counter() - t0
+
+
+CPU_SAMPLE_SHAPE = (78, 120, 120)   # 1/8 of the BraTS voxel count (each axis halved)
+
+
+def cpu_baseline(n_threads: int):
+    sec = cpu_gtv_sample(n_threads, CPU_SAMPLE_SHAPE)
+    frac = (CPU_SAMPLE_SHAPE[0] * CPU_SAMPLE_SHAPE[1] * CPU_SAMPLE_SHAPE[2]) / NVOX
+    return {"value": frac / sec, "unit": UNIT, "cores": n_threads, "kind": "port",
+            "seconds": sec,
+            "sample": f"one synthetic volume of {CPU_SAMPLE_SHAPE[2]}x{CPU_SAMPLE_SHAPE[1]}x{CPU_SAMPLE_SHAPE[0]} "
+                      f"voxels ({frac:.4f} of a BraTS volume, value scaled by voxel count) through the whole "
+                      "GTV spec with the OpenMP CPU oracle (a restatement; SimpleITK/F# reference not available)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_threads = os.cpu_count() or 1
+    cpu_gtv_sample(n_threads, (20, 32, 32))  # build/load the oracle, warm caches
+    times = []
+    for i in range(args.warmup + args.steps):
+        sec = cpu_gtv_sample(n_threads, CPU_SAMPLE_SHAPE, seed=1234 + i)
+        if i >= args.warmup:
+            times.append(sec)
+    frac = (CPU_SAMPLE_SHAPE[0] * CPU_SAMPLE_SHAPE[1] * CPU_SAMPLE_SHAPE[2]) / NVOX
+    total = sum(times)
+    val = frac * len(times) / total
+    cb = {"value": val, "unit": UNIT, "cores": n_threads, "kind": "port",
+          "sample": f"{len(times)} steps, each one {CPU_SAMPLE_SHAPE[2]}x{CPU_SAMPLE_SHAPE[1]}x{CPU_SAMPLE_SHAPE[0]} "
+                    f"synthetic volume ({frac:.4f} BraTS volumes) through the whole GTV spec, OpenMP CPU oracle"}
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32/int64",
+        "data": "synthetic", "gpu_launches": 0,
+        "config": {"workload": "BraTS-shape 240x240x155 GTV segmentation spec (threshold, near, through, "
+                               "distlt/distgeq, percentiles, crossCorrelation), CPU restatement on host cores",
+                   "note": "the SimpleITK/F# reference is not mounted and not runnable; this arm is the "
+                           "repo's CPU oracle with all host threads"},
+        "cpu_baseline": cb,
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# --------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from voxlogica_b200 import Context
+    from voxlogica_b200.imgql import run_gtv
+
+    ctx = Context(local)
+    B = args.batch
+    shape4 = (B,) + BRATS
+    host = make_batch(B, rank)
+    in_bytes, out_bytes = host.nbytes, B * NVOX
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+        ctx.sync()
+
+    def step_resident(flair):
+        out = run_gtv(ctx, flair)
+        return out["gtv"], out["_printed"]["gtvVolume"]   # volume(gtv) syncs: the step's result
+
+    # ---- device-resident throughput
+    flair = ctx.upload(host)
+    ctx.sync()
+    for _ in range(args.warmup):
+        step_resident(flair)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ctx.prof_reset()
+    ctx.prof_enable(True)
+    l0 = ctx.launch_count()
+    e0, e1 = ctx.event(), ctx.event()
+    ctx.record(e0)
+    vols = None
+    for _ in range(args.steps):
+        _, vols = step_resident(flair)
+    ctx.record(e1)
+    ms = ctx.elapsed_ms(e0, e1)
+    barrier()
+    ctx.prof_enable(False)
+    launches = ctx.launch_count() - l0
+    prof = ctx.prof_report()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end: pinned host -> HBM -> spec -> pinned host
+    pin_in = ctx.host_alloc(in_bytes)
+    pin_out = ctx.host_alloc(out_bytes)
+    import ctypes as C
+    C.memmove(pin_in, host.ctypes.data, in_bytes)
+    del flair
+
+    def step_e2e():
+        f = ctx.upload_ptr(pin_in, np.float32, shape4)
+        out = run_gtv(ctx, f)
+        ctx.download_ptr(out["gtv"], pin_out, out_bytes)
+
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    g0, g1 = ctx.event(), ctx.event()
+    ctx.record(g0)
+    for _ in range(args.steps):
+        step_e2e()
+    ctx.record(g1)
+    ms_e2e = ctx.elapsed_ms(g0, g1)
+    barrier()
+
+    if dist is not None:
+        t = torch.tensor([ms, ms_e2e], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+        n = torch.tensor([launches], device=f"cuda:{local}", dtype=torch.int64)
+        dist.all_reduce(n)
+        launches = int(n[0])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    total_vol = world * B * args.steps
+    value = total_vol / (ms / 1e3)
+    e2e = total_vol / (ms_e2e / 1e3)
+    peak, how = peaks()
+    # dominant kernel by device time
+    tot_ms = sum(v[1] for v in prof.values()) or 1.0
+    top = max(prof.items(), key=lambda kv: kv[1][1])
+    name, (cnt, kms) = top
+    per_launch_vox = B * NVOX
+    alg = ALG_BYTES.get(name) or 5.0
+    achieved = alg * per_launch_vox / ((kms / cnt) * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(name)
+        except Exception:
+            traffic = None
+    kernels = {k: {"launches": c, "ms_total": round(m, 4), "share": round(m / tot_ms, 4),
+                   "gvox_per_s": round(B * NVOX / ((m / c) * 1e-3) / 1e9, 2)}
+               for k, (c, m) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    cb = cpu_baseline(os.cpu_count() or 1) if world == 1 and not args.no_cpu_baseline else None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32/int64", "data": "synthetic",
+        "config": {"workload": "BraTS-shape 240x240x155 GTV segmentation spec (Greta.pdf p.48: threshold, "
+                               "touch/grow via through, filter via distlt/distgeq, percentiles, crossCorrelation "
+                               "rho=5 k=100)",
+                   "volumes_per_step_per_gpu": B, "voxels_per_volume": NVOX, "adjacency": 26,
+                   "sharding": "independent volumes per GPU, no collective",
+                   "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB f32 batch per step)",
+                   "data_note": "min(batch,4) generated volumes per rank + axis flips"},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "peak_source": how, "traffic": traffic,
+                     "alg_bytes_per_voxel": alg, "avg_launch_ms": kms / cnt, "share_of_step": kms / tot_ms,
+                     "note": "xcorr_kernel is shared-memory/issue bound, not HBM bound (SURVEY.md 8d); "
+                             "fraction reported against HBM as required" if name == "xcorr_kernel" else ""},
+        "kernels": kernels,
+        "clocks": clocks,
+        "cpu_baseline": cb,
+        "gtv_voxels_last_step": [float(v) for v in (vols if vols is not None else [])][:4],
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="BraTS volumes per step per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

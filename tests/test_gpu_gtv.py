@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 NAMES_BOOL = ("background", "brain", "hyperIntense", "veryIntense", "growTum", "tumStatCC", "gtv")
 
 
-@pytest.mark.parametrize("shape,seeds", [((24, 40, 48), (1234, 7)), ((31, 50, 64), (3,))])
+@pytest.mark.parametrize("shape,seeds", [((48, 80, 96), (1234, 7)), ((40, 70, 90), (3,))])
 def test_gtv_spec_matches_oracle(ctx, oracle, shape, seeds):
     from gtv_ref import gtv_oracle
     from voxlogica_b200.imgql import run_gtv

@@ -40,7 +40,7 @@ def brats_like(seed: int = 1234, shape=BRATS_SHAPE) -> np.ndarray:
     vol[head] = tissue[head]
     scale = min(nz / 155, ny / 240, nx / 240)
     for _ in range(int(rng.integers(1, 4))):
-        r = rng.uniform(8, 25) * scale
+        r = max(rng.uniform(8, 25) * scale, 6.5)   # filter(5.0, .) keeps only blobs of radius > 5
         # keep lesions inside the head
         lz = cz + rng.uniform(-0.45, 0.45) * az
         ly = cy + rng.uniform(-0.45, 0.45) * ay
