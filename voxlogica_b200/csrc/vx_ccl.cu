@@ -4,19 +4,25 @@
 //
 //   through(a, b) = union of the connected components of b that contain a voxel of a.
 //
-// Algorithm (B200-first; not the OpenCL branch's ~29 relabelling sweeps, p.78):
-//   1. init    one warp per 32-voxel row segment: ballot the foreground into a bit
-//              mask and label every voxel with the start of its x-run inside the
-//              segment, so whole runs are already merged before any atomic is issued;
-//   2. merge   per voxel, link to the backward neighbour rows ((y-1,z),(y-1,z-1),
-//              (y,z-1),(y+1,z-1) for 26-adjacency; (y-1,z),(y,z-1) for 6) using the bit
-//              masks; a voxel only issues a union where a NEW neighbour run begins,
-//              i.e. O(#run contacts) atomicMin unions, not O(#voxels x 13);
-//   3. select  roots are the minimum linear index of their component (unions always
-//              hang the larger root under the smaller), so labels are canonical.
-//              through: seeds OR a flag bit into their root, then every voxel of b
-//              looks its root up.  maxvol: run lengths are accumulated on roots.
-// Labels are u32 linear indices inside their own volume (< 2^31), bit 31 is the flag.
+// Algorithm (B200-first; not the OpenCL branch's ~29 relabelling sweeps, p.78).
+// Everything after the first pass works on 32-voxel bit words, one THREAD per word:
+//   1. init     one warp per row: ballot the foreground into bit words and create the
+//               "anchors" of every x-run: the run start (parent = itself) and, where a
+//               run crosses a word boundary, the first voxel of the next word (parent =
+//               run start).  Only anchors ever get a parent entry, so the label array is
+//               written sparsely (a few entries per word instead of 32);
+//   2. merge    per word, contacts with the backward neighbour rows ((y-1,z), (y-1,z-1),
+//               (y,z-1), (y+1,z-1) for 26-adjacency; (y-1,z), (y,z-1) for 6) are found
+//               with bit operations on the neighbour words; one union per place where a
+//               NEW neighbour run begins next to a run of this word.  Unions hang the
+//               larger root under the smaller (atomicMin), finds compress paths with
+//               atomicMin (this can only replace a parent by an ancestor, never lose a
+//               link);
+//   3. flatten  every anchor is pointed straight at its root;
+//   4. select   per word and per run segment: anchor -> root -> test (seed flag /
+//               component size) and write 32 output voxels with two 128-bit stores.
+// Roots are the minimum linear index of their component, so labels are canonical.
+// Labels are u32 linear indices inside their own volume (< 2^31); bit 31 is the flag.
 #include "vx_internal.h"
 
 namespace vx {
@@ -26,9 +32,10 @@ constexpr unsigned kIdx = 0x7fffffffu;
 constexpr int kCclThreads = 256;
 
 struct Geo {
-    int nx, ny, nz, nb, nwx;  // nwx = 32-voxel words per row
-    unsigned long long rows;  // nb*nz*ny
-    unsigned long long nvox;
+    int nx, ny, nz, nb, nwx;    // nwx = 32-voxel words per row
+    unsigned long long rows;    // nb*nz*ny
+    unsigned long long nwords;  // rows*nwx
+    unsigned long long nvox;    // voxels per volume
 };
 
 __device__ __forceinline__ unsigned find_root(const unsigned* L, unsigned x) {
@@ -40,11 +47,25 @@ __device__ __forceinline__ unsigned find_root(const unsigned* L, unsigned x) {
     return x;
 }
 
+__device__ __forceinline__ unsigned find_compress(unsigned* L, unsigned x) {
+    unsigned p = __ldcg(L + x) & kIdx;
+    if (p == x) return x;
+    unsigned r = p, q = __ldcg(L + r) & kIdx;
+    if (q == r) return r;  // depth 1: nothing to compress
+    while (q != r) {
+        r = q;
+        q = __ldcg(L + r) & kIdx;
+    }
+    atomicMin(L + x, r);
+    atomicMin(L + p, r);
+    return r;
+}
+
 __device__ __forceinline__ void unite(unsigned* L, unsigned a, unsigned b) {
     bool done = false;
     do {
-        a = find_root(L, a);
-        b = find_root(L, b);
+        a = find_compress(L, a);
+        b = find_compress(L, b);
         if (a < b) {
             unsigned old = atomicMin(L + b, a);
             done = (old == b);
@@ -59,177 +80,319 @@ __device__ __forceinline__ void unite(unsigned* L, unsigned a, unsigned b) {
     } while (!done);
 }
 
-// decode the (row, word) handled by this warp
-struct WarpPos {
+// ---- bit helpers on one 32-voxel word -----------------------------------------------------
+// first bit of the run segment (inside the word) that contains set bit j
+__device__ __forceinline__ int seg_start(unsigned m, int j) {
+    const unsigned zeros_below = ~m & ((1u << j) - 1u);
+    return zeros_below ? 32 - __clz(zeros_below) : 0;
+}
+// mask of the segment that starts at set bit p
+__device__ __forceinline__ unsigned seg_mask(unsigned m, int p) {
+    const unsigned above = ~(m >> p);
+    int len = above ? __ffs(above) - 1 : 32;
+    if (len > 32 - p) len = 32 - p;
+    return (len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << p;
+}
+
+// the word handled by this thread
+struct WordPos {
     bool ok;
-    int x, y, z, w;
-    unsigned long long row;  // global row index (over the batch)
-    unsigned vol;            // volume index
-    unsigned lin;            // linear index of voxel x inside its volume
-    int lane;
+    int w, y, z;
+    unsigned long long wid, row;
+    unsigned vol;
+    unsigned lin0;  // linear index (inside the volume) of the word's first voxel
 };
-__device__ __forceinline__ WarpPos warp_pos(const Geo& g) {
-    WarpPos p;
-    unsigned long long wid = ((unsigned long long)blockIdx.x * kCclThreads + threadIdx.x) >> 5;
-    p.lane = threadIdx.x & 31;
-    p.ok = wid < g.rows * g.nwx;
-    if (!p.ok) wid = 0;
+__device__ __forceinline__ WordPos word_pos(const Geo& g) {
+    WordPos p;
+    p.wid = (unsigned long long)blockIdx.x * kCclThreads + threadIdx.x;
+    p.ok = p.wid < g.nwords;
+    const unsigned long long wid = p.ok ? p.wid : 0;
     p.row = wid / g.nwx;
     p.w = (int)(wid % g.nwx);
     p.y = (int)(p.row % g.ny);
-    unsigned long long t = p.row / g.ny;
+    const unsigned long long t = p.row / g.ny;
     p.z = (int)(t % g.nz);
     p.vol = (unsigned)(t / g.nz);
-    p.x = p.w * 32 + p.lane;
-    p.lin = (unsigned)(((unsigned long long)p.z * g.ny + p.y) * g.nx + p.x);
+    p.lin0 = (unsigned)(((unsigned long long)p.z * g.ny + p.y) * g.nx + (unsigned)p.w * 32u);
     return p;
 }
 
+// ---- 1. init: one warp per row ------------------------------------------------------------
 __global__ void __launch_bounds__(kCclThreads)
 ccl_init_kernel(const uint8_t* __restrict__ img, unsigned* __restrict__ L,
                 unsigned* __restrict__ bits, Geo g) {
-    WarpPos p = warp_pos(g);
-    if (!p.ok) return;  // whole warp
-    const size_t gi = (size_t)p.vol * g.nvox + p.lin;
-    bool fg = p.x < g.nx && img[gi] != 0;
-    unsigned m = __ballot_sync(0xffffffffu, fg);
-    if (p.lane == 0) bits[p.row * g.nwx + p.w] = m;
-    if (fg) {
-        unsigned zeros_below = ~m & ((1u << p.lane) - 1u);
-        int start = zeros_below ? 32 - __clz(zeros_below) : 0;
-        L[gi] = p.lin - (unsigned)(p.lane - start);
+    const unsigned long long row = ((unsigned long long)blockIdx.x * kCclThreads + threadIdx.x) >> 5;
+    if (row >= g.rows) return;  // whole warp
+    const int lane = threadIdx.x & 31;
+    const unsigned long long rv = row % ((unsigned long long)g.nz * g.ny);  // row inside its volume
+    const size_t gbase = (size_t)row * g.nx;       // global offset of the row
+    const unsigned lbase = (unsigned)(rv * g.nx);  // linear index of x = 0 inside the volume
+    int carry = -1;  // x where the run reaching into this word started, -1 if none
+    for (int w = 0; w < g.nwx; w++) {
+        const int x = w * 32 + lane;
+        const bool fg = x < g.nx && img[gbase + x] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, fg);
+        if (lane == 0) bits[row * g.nwx + w] = m;
+        if (fg) {
+            const bool left = lane > 0 ? ((m >> (lane - 1)) & 1u) : (carry >= 0);
+            if (!left) L[gbase + x] = lbase + (unsigned)x;               // run start
+            else if (lane == 0) L[gbase + x] = lbase + (unsigned)carry;  // word-boundary anchor
+        }
+        if (m >> 31) {
+            const int ones = __clz(~m);  // leading ones (32 when the word is full)
+            if (ones < 32) carry = w * 32 + 32 - ones;
+            else if (carry < 0) carry = w * 32;
+        } else {
+            carry = -1;
+        }
     }
 }
 
+// ---- 2. merge: one thread per word ----------------------------------------------------------
 template <bool FULL>
 __global__ void __launch_bounds__(kCclThreads)
 ccl_merge_kernel(unsigned* __restrict__ Lall, const unsigned* __restrict__ bits, Geo g) {
-    WarpPos p = warp_pos(g);
+    const WordPos p = word_pos(g);
     if (!p.ok) return;
     const unsigned* brow = bits + p.row * g.nwx;
     const unsigned m = __ldg(brow + p.w);
-    if (m == 0) return;  // warp-uniform
-    const bool fg = (m >> p.lane) & 1u;
+    if (m == 0) return;
+    const unsigned prev_m = p.w > 0 ? __ldg(brow + p.w - 1) : 0u;
+    const unsigned left = (m << 1) | (prev_m >> 31);  // bit j: voxel j-1 of the same row is set
     unsigned* L = Lall + (size_t)p.vol * g.nvox;
-    const bool left_in_word = p.lane > 0 && ((m >> (p.lane - 1)) & 1u);
-    // run continues from the previous 32-voxel segment
-    if (p.lane == 0 && fg && p.w > 0 && (__ldg(brow + p.w - 1) >> 31)) unite(L, p.lin, p.lin - 1);
 
-    // backward neighbour rows
     const int ndir = FULL ? 4 : 2;
     const int dys[4] = {-1, 0, -1, 1};
     const int dzs[4] = {0, -1, -1, -1};
 #pragma unroll
     for (int d = 0; d < ndir; d++) {
         const int yy = p.y + dys[d], zz = p.z + dzs[d];
-        if (yy < 0 || yy >= g.ny || zz < 0) continue;  // warp-uniform
+        if (yy < 0 || yy >= g.ny || zz < 0) continue;
         const long long drow = (long long)dzs[d] * g.ny + dys[d];
         const unsigned* nrow = brow + drow * g.nwx;
-        const unsigned c = __ldg(nrow + p.w);
-        unsigned long long W = (unsigned long long)c << 1;
+        const unsigned nc = __ldg(nrow + p.w);
+        const unsigned np = p.w > 0 ? __ldg(nrow + p.w - 1) : 0u;
+        const unsigned nn = (FULL && p.w + 1 < g.nwx) ? __ldg(nrow + p.w + 1) : 0u;
+        // neighbour bits relative to voxel j:  N0 = same x, Nm = x-1, Np = x+1
+        const unsigned N0 = nc;
+        const unsigned Nm = (nc << 1) | (np >> 31);
+        const unsigned Np = (nc >> 1) | (nn << 31);
+        const unsigned nlin0 = (unsigned)((long long)p.lin0 + drow * g.nx);  // neighbour word, bit 0
+        unsigned first, second;
         if (FULL) {
-            if (p.w > 0) W |= (unsigned long long)(__ldg(nrow + p.w - 1) >> 31);
-            if (p.w + 1 < g.nwx) W |= (unsigned long long)(__ldg(nrow + p.w + 1) & 1u) << 33;
-        }
-        if (W == 0 || !fg) continue;
-        const unsigned t = (unsigned)(W >> p.lane) & 7u;  // bit0 n(x-1), bit1 n(x), bit2 n(x+1)
-        const unsigned nlin = (unsigned)((long long)p.lin + drow * g.nx);  // neighbour at same x
-        if (FULL) {
-            if ((t & 4u) && !(t & 2u)) unite(L, p.lin, nlin + 1);  // a new neighbour run starts at x+1
-            if (!left_in_word) {
-                if (t & 2u) unite(L, p.lin, nlin);
-                else if (t & 1u) unite(L, p.lin, nlin - 1);
-            }
+            first = m & Np & ~N0;             // a neighbour run begins at x+1 next to voxel x
+            second = m & ~left & (N0 | Nm);   // this run begins at x and touches x or x-1 below
         } else {
-            if ((t & 2u) && !(left_in_word && (t & 1u))) unite(L, p.lin, nlin);
+            first = 0;
+            second = m & N0 & ~(left & Nm);   // face contact that the voxel to the left did not see
+        }
+        while (first) {
+            const int j = __ffs(first) - 1;
+            first &= first - 1;
+            // the neighbour voxel x+1 starts its run, so it is an anchor itself (bit 0 of the
+            // next word when j == 31)
+            unite(L, p.lin0 + seg_start(m, j), nlin0 + j + 1);
+        }
+        while (second) {
+            const int j = __ffs(second) - 1;
+            second &= second - 1;
+            unsigned b;
+            if ((N0 >> j) & 1u) b = nlin0 + seg_start(nc, j);
+            else if (j > 0) b = nlin0 + seg_start(nc, j - 1);
+            else b = nlin0 - 32 + seg_start(np, 31);
+            unite(L, p.lin0 + seg_start(m, j), b);
         }
     }
 }
 
-// seeds: voxels of a & b flag the root of their component
+// anchors of a word: run starts plus bit 0 when the run continues from the previous word
+__device__ __forceinline__ unsigned anchor_mask(unsigned m, unsigned prev_m) {
+    return (m & ~((m << 1) | (prev_m >> 31))) | (m & 1u & (prev_m >> 31));
+}
+
+// ---- 3. flatten ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCclThreads)
+ccl_flatten_kernel(unsigned* __restrict__ Lall, const unsigned* __restrict__ bits, Geo g) {
+    const WordPos p = word_pos(g);
+    if (!p.ok) return;
+    const unsigned* brow = bits + p.row * g.nwx;
+    const unsigned m = __ldg(brow + p.w);
+    if (m == 0) return;
+    const unsigned prev_m = p.w > 0 ? __ldg(brow + p.w - 1) : 0u;
+    unsigned* L = Lall + (size_t)p.vol * g.nvox;
+    unsigned anchors = anchor_mask(m, prev_m);
+    while (anchors) {
+        const int j = __ffs(anchors) - 1;
+        anchors &= anchors - 1;
+        const unsigned a = p.lin0 + j;
+        const unsigned r = find_root(L, a);
+        if (r != a) L[a] = r;
+    }
+}
+
+// 32 boolean voxels of `img` at this word as a bit mask
+__device__ __forceinline__ unsigned nib4(unsigned w) {
+    w = __vcmpne4(w, 0u) & 0x01010101u;
+    return ((w * 0x01020408u) >> 24) & 0xfu;
+}
+__device__ __forceinline__ unsigned load_bits32(const uint8_t* __restrict__ src, int nx, int x0) {
+    unsigned v = 0;
+    if ((nx & 15) == 0) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
+        v = nib4(a.x) | (nib4(a.y) << 4) | (nib4(a.z) << 8) | (nib4(a.w) << 12);
+        if (x0 + 16 < nx) {
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(src + 16));
+            v |= (nib4(b.x) | (nib4(b.y) << 4) | (nib4(b.z) << 8) | (nib4(b.w) << 12)) << 16;
+        }
+    } else {
+        const int lim = min(32, nx - x0);
+        for (int b = 0; b < lim; b++) v |= (unsigned)(src[b] != 0) << b;
+    }
+    return v;
+}
+__device__ __forceinline__ unsigned bytes4(unsigned nib) { return (nib * 0x00204081u) & 0x01010101u; }
+__device__ __forceinline__ void store_bits32(uint8_t* __restrict__ dst, int nx, int x0, unsigned v) {
+    if ((nx & 15) == 0) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(bytes4(v & 0xfu), bytes4((v >> 4) & 0xfu),
+                                                    bytes4((v >> 8) & 0xfu), bytes4((v >> 12) & 0xfu));
+        if (x0 + 16 < nx)
+            *reinterpret_cast<uint4*>(dst + 16) = make_uint4(bytes4((v >> 16) & 0xfu), bytes4((v >> 20) & 0xfu),
+                                                             bytes4((v >> 24) & 0xfu), bytes4(v >> 28));
+    } else {
+        const int lim = min(32, nx - x0);
+        for (int b = 0; b < lim; b++) dst[b] = (uint8_t)((v >> b) & 1u);
+    }
+}
+
+// ---- seeds: every run segment of b that contains a voxel of a flags its root ----------------
 __global__ void __launch_bounds__(kCclThreads)
 ccl_seed_kernel(const uint8_t* __restrict__ seed, unsigned* __restrict__ Lall,
                 const unsigned* __restrict__ bits, Geo g) {
-    WarpPos p = warp_pos(g);
+    const WordPos p = word_pos(g);
     if (!p.ok) return;
-    const unsigned m = __ldg(bits + p.row * g.nwx + p.w);
+    const unsigned m = __ldg(bits + p.wid);
     if (m == 0) return;
-    if (!((m >> p.lane) & 1u)) return;
-    const size_t gi = (size_t)p.vol * g.nvox + p.lin;
-    if (seed[gi] == 0) return;
+    unsigned s = load_bits32(seed + p.row * g.nx + (size_t)p.w * 32, g.nx, p.w * 32) & m;
     unsigned* L = Lall + (size_t)p.vol * g.nvox;
-    unsigned r = find_root(L, p.lin);
-    if (!(__ldcg(L + r) & kFlag)) atomicOr(L + r, kFlag);
+    while (s) {
+        const int j = __ffs(s) - 1;
+        const int st = seg_start(m, j);
+        s &= ~seg_mask(m, st);
+        const unsigned r = find_root(L, p.lin0 + st);
+        if (!(__ldcg(L + r) & kFlag)) atomicOr(L + r, kFlag);
+    }
 }
 
 enum SelMode { SEL_THROUGH = 0, SEL_LABELS = 1, SEL_MAXVOL = 2 };
 
-// final pass: resolve every voxel's root and emit the requested image
+// ---- 4. select -----------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(kCclThreads)
 ccl_select_kernel(const unsigned* __restrict__ Lall, const unsigned* __restrict__ bits, void* out_,
                   const unsigned* __restrict__ cnt, const unsigned* __restrict__ vmax, Geo g) {
-    WarpPos p = warp_pos(g);
-    if (!p.ok || p.x >= g.nx) return;
-    const unsigned m = __ldg(bits + p.row * g.nwx + p.w);
-    const bool fg = (m >> p.lane) & 1u;
-    const size_t gi = (size_t)p.vol * g.nvox + p.lin;
+    const WordPos p = word_pos(g);
+    if (!p.ok) return;
+    const unsigned m = __ldg(bits + p.wid);
     const unsigned* L = Lall + (size_t)p.vol * g.nvox;
-    unsigned r = 0;
-    if (fg) r = find_root(L, p.lin);
-    if (MODE == SEL_THROUGH) {
-        reinterpret_cast<uint8_t*>(out_)[gi] = (fg && (L[r] & kFlag)) ? 1 : 0;
-    } else if (MODE == SEL_LABELS) {
-        reinterpret_cast<unsigned*>(out_)[gi] = fg ? r + 1u : 0u;
-    } else {
-        reinterpret_cast<uint8_t*>(out_)[gi] =
-            (fg && cnt[(size_t)p.vol * g.nvox + r] == vmax[p.vol]) ? 1 : 0;
+    const int x0 = p.w * 32;
+    const size_t goff = p.row * g.nx + (size_t)x0;
+    unsigned rest = m, outbits = 0;
+    if (MODE == SEL_LABELS) {
+        unsigned* dst = reinterpret_cast<unsigned*>(out_) + goff;
+        const int lim = min(32, g.nx - x0);
+        unsigned lab[32];
+#pragma unroll
+        for (int b = 0; b < 32; b++) lab[b] = 0;
+        while (rest) {
+            const int st = __ffs(rest) - 1;
+            const unsigned sm = seg_mask(m, st);
+            rest &= ~sm;
+            const unsigned r = find_root(L, p.lin0 + st) + 1u;
+#pragma unroll
+            for (int b = 0; b < 32; b++)
+                if ((sm >> b) & 1u) lab[b] = r;
+        }
+        if ((g.nx & 3) == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if (4 * q < lim)
+                    reinterpret_cast<uint4*>(dst)[q] =
+                        make_uint4(lab[4 * q], lab[4 * q + 1], lab[4 * q + 2], lab[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int b = 0; b < 32; b++)
+                if (b < lim) dst[b] = lab[b];
+        }
+        return;
     }
+    while (rest) {
+        const int st = __ffs(rest) - 1;
+        const unsigned sm = seg_mask(m, st);
+        rest &= ~sm;
+        const unsigned r = find_root(L, p.lin0 + st);
+        bool keep;
+        if (MODE == SEL_THROUGH) keep = (__ldcg(L + r) & kFlag) != 0;
+        else keep = cnt[(size_t)p.vol * g.nvox + r] == vmax[p.vol];
+        if (keep) outbits |= sm;
+    }
+    store_bits32(reinterpret_cast<uint8_t*>(out_) + goff, g.nx, x0, outbits);
 }
 
-// maxvol step 1: zero the counters of the roots
+// ---- maxvol --------------------------------------------------------------------------------
+// step 1: zero the counters of the roots (run starts whose parent is themselves)
 __global__ void __launch_bounds__(kCclThreads)
 ccl_zero_roots_kernel(const unsigned* __restrict__ Lall, const unsigned* __restrict__ bits,
                       unsigned* __restrict__ cnt, Geo g) {
-    WarpPos p = warp_pos(g);
+    const WordPos p = word_pos(g);
     if (!p.ok) return;
-    const unsigned m = __ldg(bits + p.row * g.nwx + p.w);
-    if (!((m >> p.lane) & 1u)) return;
-    const size_t gi = (size_t)p.vol * g.nvox + p.lin;
-    if ((Lall[gi] & kIdx) == p.lin) cnt[gi] = 0;
+    const unsigned* brow = bits + p.row * g.nwx;
+    const unsigned m = __ldg(brow + p.w);
+    if (m == 0) return;
+    const unsigned prev_m = p.w > 0 ? __ldg(brow + p.w - 1) : 0u;
+    unsigned starts = m & ~((m << 1) | (prev_m >> 31));
+    const size_t vbase = (size_t)p.vol * g.nvox;
+    while (starts) {
+        const int j = __ffs(starts) - 1;
+        starts &= starts - 1;
+        if ((Lall[vbase + p.lin0 + j] & kIdx) == p.lin0 + j) cnt[vbase + p.lin0 + j] = 0;
+    }
 }
-// maxvol step 2: one atomicAdd per x-run segment (all its voxels share a root)
+// step 2: one atomicAdd per run segment (all its voxels share a root)
 __global__ void __launch_bounds__(kCclThreads)
 ccl_count_kernel(const unsigned* __restrict__ Lall, const unsigned* __restrict__ bits,
                  unsigned* __restrict__ cnt, Geo g) {
-    WarpPos p = warp_pos(g);
+    const WordPos p = word_pos(g);
     if (!p.ok) return;
-    const unsigned m = __ldg(bits + p.row * g.nwx + p.w);
-    if (!((m >> p.lane) & 1u)) return;
-    const bool run_start = p.lane == 0 || !((m >> (p.lane - 1)) & 1u);
-    if (!run_start) return;
-    // length of the run starting at this lane, inside the 32-voxel segment
-    unsigned above = ~(m >> p.lane);  // first zero above
-    int len = above ? __ffs(above) - 1 : 32 - p.lane;
-    if (len > 32 - p.lane) len = 32 - p.lane;
+    const unsigned m = __ldg(bits + p.wid);
     const unsigned* L = Lall + (size_t)p.vol * g.nvox;
-    unsigned r = find_root(L, p.lin);
-    atomicAdd(cnt + (size_t)p.vol * g.nvox + r, (unsigned)len);
+    unsigned rest = m;
+    while (rest) {
+        const int st = __ffs(rest) - 1;
+        const unsigned sm = seg_mask(m, st);
+        rest &= ~sm;
+        const unsigned r = find_root(L, p.lin0 + st);
+        atomicAdd(cnt + (size_t)p.vol * g.nvox + r, (unsigned)__popc(sm));
+    }
 }
-// maxvol step 3: per-volume maximum over roots
+// step 3: per-volume maximum over roots
 __global__ void __launch_bounds__(kCclThreads)
 ccl_max_kernel(const unsigned* __restrict__ Lall, const unsigned* __restrict__ bits,
                const unsigned* __restrict__ cnt, unsigned* __restrict__ vmax, Geo g) {
-    WarpPos p = warp_pos(g);
+    const WordPos p = word_pos(g);
     if (!p.ok) return;
-    const unsigned m = __ldg(bits + p.row * g.nwx + p.w);
+    const unsigned* brow = bits + p.row * g.nwx;
+    const unsigned m = __ldg(brow + p.w);
+    if (m == 0) return;
+    const unsigned prev_m = p.w > 0 ? __ldg(brow + p.w - 1) : 0u;
+    unsigned starts = m & ~((m << 1) | (prev_m >> 31));
+    const size_t vbase = (size_t)p.vol * g.nvox;
     unsigned v = 0;
-    if ((m >> p.lane) & 1u) {
-        const size_t gi = (size_t)p.vol * g.nvox + p.lin;
-        if ((Lall[gi] & kIdx) == p.lin) v = cnt[gi];
+    while (starts) {
+        const int j = __ffs(starts) - 1;
+        starts &= starts - 1;
+        if ((Lall[vbase + p.lin0 + j] & kIdx) == p.lin0 + j) v = max(v, cnt[vbase + p.lin0 + j]);
     }
-    v = __reduce_max_sync(0xffffffffu, v);
-    if (p.lane == 0 && v) atomicMax(vmax + p.vol, v);
+    if (v) atomicMax(vmax + p.vol, v);
 }
 
 static Geo make_geo(const Image* b) {
@@ -237,24 +400,25 @@ static Geo make_geo(const Image* b) {
     g.nx = b->nx; g.ny = b->ny; g.nz = b->nz; g.nb = b->nb;
     g.nwx = (b->nx + 31) / 32;
     g.rows = (unsigned long long)b->nb * b->nz * b->ny;
+    g.nwords = g.rows * g.nwx;
     g.nvox = b->nvox();
     return g;
 }
 
-// shared front end: labels + bit masks of image B on the op's stream
+// shared front end: parents + bit words of image B on the op's stream
 static int ccl_label(OpGuard& og, const Image* B, bool full, unsigned** L_out, unsigned** bits_out,
                      Geo* geo, unsigned* grid_out) {
     Geo g = make_geo(B);
-    unsigned long long warps = g.rows * g.nwx;
-    unsigned long long blocks = (warps * 32 + kCclThreads - 1) / kCclThreads;
-    VX_REQUIRE(blocks < 0x7fffffffull, VX_E_UNSUPPORTED, "batch too large for one launch");
+    unsigned long long blocks = (g.nwords + kCclThreads - 1) / kCclThreads;
+    unsigned long long iblocks = (g.rows * 32 + kCclThreads - 1) / kCclThreads;
+    VX_REQUIRE(iblocks < 0x7fffffffull, VX_E_UNSUPPORTED, "batch too large for one launch");
     unsigned grid = (unsigned)blocks;
     unsigned *L = nullptr, *bits = nullptr;
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * B->count(), (void**)&L));
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * warps, (void**)&bits));
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * g.nwords, (void**)&bits));
     {
         VX_LAUNCH(og.c, og.s, "ccl_init_kernel");
-        ccl_init_kernel<<<grid, kCclThreads, 0, og.st>>>((const uint8_t*)B->d, L, bits, g);
+        ccl_init_kernel<<<(unsigned)iblocks, kCclThreads, 0, og.st>>>((const uint8_t*)B->d, L, bits, g);
     }
     VX_TRY(check_launch("ccl_init_kernel"));
     {
@@ -263,6 +427,11 @@ static int ccl_label(OpGuard& og, const Image* B, bool full, unsigned** L_out, u
         else ccl_merge_kernel<false><<<grid, kCclThreads, 0, og.st>>>(L, bits, g);
     }
     VX_TRY(check_launch("ccl_merge_kernel"));
+    {
+        VX_LAUNCH(og.c, og.s, "ccl_flatten_kernel");
+        ccl_flatten_kernel<<<grid, kCclThreads, 0, og.st>>>(L, bits, g);
+    }
+    VX_TRY(check_launch("ccl_flatten_kernel"));
     *L_out = L; *bits_out = bits; *geo = g; *grid_out = grid;
     return VX_OK;
 }

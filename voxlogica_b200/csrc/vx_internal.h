@@ -9,6 +9,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/voxcuda.h"
@@ -50,6 +51,7 @@ struct Ctx {
     std::atomic<int> next_stream{0};
     std::mutex mu;  // guards pools and accounting below
     std::vector<cudaEvent_t> event_pool;
+    std::vector<cudaEvent_t> timing_pool;  // timing-enabled events for the profiler
     std::atomic<uint64_t> launches{0};
     std::atomic<uint64_t> live_bytes{0};
     std::atomic<uint64_t> live_handles{0};
@@ -59,7 +61,18 @@ struct Ctx {
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
     cudaMemPool_t pool = nullptr;
+    // caching sub-allocator: freed blocks are kept per (stream, rounded size) and handed
+    // out again without touching the driver (the operator DAG of a spec repeats sizes)
+    std::map<size_t, std::vector<void*>> cache[kMaxStreams];
+    std::unordered_map<void*, size_t> block_size;  // every block handed out by dev_alloc
+    uint64_t cached_bytes = 0;
+    uint64_t cache_limit = 0;  // bytes kept in the free lists before blocks go back to the pool
 };
+
+// Device memory for images and scratch, ordered on stream index s.
+int dev_alloc(Ctx* c, int s, size_t bytes, void** out);
+void dev_free(Ctx* c, int s, void* p);
+void dev_cache_release(Ctx* c, uint64_t keep_bytes);
 
 // ---- error convention ------------------------------------------------------
 int fail(int code, const char* fmt, ...);

@@ -158,6 +158,23 @@ border_kernel(uint8_t* __restrict__ out, int nx, int ny, int nz, size_t total) {
     out[i] = b ? 1 : 0;
 }
 
+// nx % 16 == 0: one thread per 16 voxels, one 128-bit store
+__global__ void __launch_bounds__(256)
+border16_kernel(uint4* __restrict__ out, int ncx, int nx, int ny, int nz, size_t nchunks) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nchunks) return;
+    const int xc = (int)(i % ncx);
+    size_t t = i / ncx;
+    const int y = (int)(t % ny);
+    const int z = (int)((t / ny) % nz);
+    const bool face = (ny > 1 && (y == 0 || y == ny - 1)) || (nz > 1 && (z == 0 || z == nz - 1));
+    unsigned w = face ? 0x01010101u : 0u;
+    uint4 v = make_uint4(w, w, w, w);
+    if (nx > 1 && xc == 0) v.x |= 1u;
+    if (nx > 1 && xc == ncx - 1) v.w |= 0x01000000u;
+    out[i] = v;
+}
+
 static int morph(vx_ctx ctx, vx_img a, int conn, bool erode, vx_img* out) {
     VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");
     VX_REQUIRE(conn == VX_CONN_FACE || conn == VX_CONN_FULL, VX_E_INVALID_ARG,
@@ -215,7 +232,11 @@ int32_t vx_border(vx_ctx ctx, vx_img like, vx_img* out) {
     Image* O = nullptr;
     VX_TRY(new_image(g.c, VX_U8, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
     size_t total = A->count();
-    {
+    if ((A->nx & 15) == 0) {
+        size_t nchunks = total / 16;
+        VX_LAUNCH(g.c, g.s, "border_kernel");
+        border16_kernel<<<(unsigned)((nchunks + 255) / 256), 256, 0, g.st>>>((uint4*)O->d, A->nx / 16, A->nx, A->ny, A->nz, nchunks);
+    } else {
         VX_LAUNCH(g.c, g.s, "border_kernel");
         border_kernel<<<(unsigned)((total + 255) / 256), 256, 0, g.st>>>((uint8_t*)O->d, A->nx, A->ny, A->nz, total);
     }

@@ -114,44 +114,54 @@ rs_hist_kernel(const unsigned* __restrict__ keys, const unsigned* __restrict__ c
     for (int d = lane; d < 256; d += 32) tab[(size_t)d * nchunks_max + chunk] = cnt[warp][d];
 }
 
-// one block per volume: exclusive scan of the used part of the table, in (digit, chunk) order
-__global__ void __launch_bounds__(1024)
-rs_scan_kernel(const unsigned* __restrict__ count, unsigned* __restrict__ table, int nchunks_max) {
-    __shared__ unsigned part[1024];
-    const size_t vol = blockIdx.x;
+// grid (256, nb): block (d, vol) turns row d of the table (one count per chunk) into an
+// exclusive prefix over chunks and records the row total; the digit bases are then a
+// 256-entry scan that every scatter warp does for itself.
+__global__ void __launch_bounds__(256)
+rs_rowscan_kernel(const unsigned* __restrict__ count, unsigned* __restrict__ table,
+                  unsigned* __restrict__ totals, int nchunks_max) {
+    __shared__ unsigned wsum[8];
+    __shared__ unsigned carry_s;
+    const size_t vol = blockIdx.y;
+    const unsigned d = blockIdx.x;
     const unsigned n = count[vol];
     const unsigned nchunks = (n + kWarpChunk - 1) / kWarpChunk;
-    if (nchunks == 0) return;
-    unsigned* tab = table + (vol * 256) * (size_t)nchunks_max;
-    const unsigned total = 256u * nchunks;
-    const unsigned per = (total + 1023u) / 1024u;
-    const unsigned lo = threadIdx.x * per;
-    const unsigned hi = min(lo + per, total);
-    unsigned sum = 0;
-    for (unsigned e = lo; e < hi; e++) sum += tab[(size_t)(e / nchunks) * nchunks_max + (e % nchunks)];
-    part[threadIdx.x] = sum;
+    unsigned* row = table + (vol * 256 + d) * (size_t)nchunks_max;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    // Hillis-Steele inclusive scan over 1024 partial sums
-    for (int o = 1; o < 1024; o <<= 1) {
-        unsigned v = threadIdx.x >= o ? part[threadIdx.x - o] : 0u;
+    for (unsigned base = 0; base < nchunks; base += 256) {
+        const unsigned i = base + threadIdx.x;
+        const unsigned v = i < nchunks ? row[i] : 0u;
+        unsigned incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
         __syncthreads();
-        part[threadIdx.x] += v;
+        unsigned wbase = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            unsigned t = wsum[w];
+            if (w < warp) wbase += t;
+            tot += t;
+        }
+        const unsigned carry = carry_s;
+        if (i < nchunks) row[i] = carry + wbase + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + tot;
         __syncthreads();
     }
-    unsigned run = part[threadIdx.x] - sum;
-    for (unsigned e = lo; e < hi; e++) {
-        size_t a = (size_t)(e / nchunks) * nchunks_max + (e % nchunks);
-        unsigned v = tab[a];
-        tab[a] = run;
-        run += v;
-    }
+    if (threadIdx.x == 0) totals[vol * 256 + d] = carry_s;
 }
 
 __global__ void __launch_bounds__(kPcThreads)
 rs_scatter_kernel(const unsigned* __restrict__ keys_in, const unsigned* __restrict__ idx_in,
                   unsigned* __restrict__ keys_out, unsigned* __restrict__ idx_out,
                   const unsigned* __restrict__ count, size_t nvox, const unsigned* __restrict__ table,
-                  int nchunks_max, int shift) {
+                  const unsigned* __restrict__ totals, int nchunks_max, int shift) {
     __shared__ unsigned off[kPcThreads / 32][256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t vol = blockIdx.y;
@@ -160,7 +170,25 @@ rs_scatter_kernel(const unsigned* __restrict__ keys_in, const unsigned* __restri
     const unsigned nchunks = (n + kWarpChunk - 1) / kWarpChunk;
     if (chunk >= nchunks) return;
     const unsigned* tab = table + (vol * 256) * (size_t)nchunks_max;
-    for (int d = lane; d < 256; d += 32) off[warp][d] = tab[(size_t)d * nchunks_max + chunk];
+    {   // digit bases: exclusive scan of the 256 row totals, 8 digits per lane
+        const unsigned* tot = totals + vol * 256;
+        unsigned t[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { t[j] = tot[lane * 8 + j]; sum += t[j]; }
+        unsigned incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        unsigned base = incl - sum;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int d = lane * 8 + j;
+            off[warp][d] = base + tab[(size_t)d * nchunks_max + chunk];
+            base += t[j];
+        }
+    }
     __syncwarp();
     const unsigned* ki = keys_in + vol * nvox;
     const unsigned* ii = idx_in + vol * nvox;
@@ -243,10 +271,11 @@ extern "C" int32_t vx_percentiles(vx_ctx ctx, vx_img a, vx_img mask, double corr
     const size_t nvox = A->nvox(), total = A->count();
     const int nb = A->nb;
     const int nchunks_max = (int)((nvox + kWarpChunk - 1) / kWarpChunk);
-    unsigned *buf = nullptr, *count = nullptr, *table = nullptr;
+    unsigned *buf = nullptr, *count = nullptr, *table = nullptr, *totals = nullptr;
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * total * 4, (void**)&buf));
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * nb, (void**)&count));
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (size_t)nb * 256 * nchunks_max, (void**)&table));
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (size_t)nb * 256, (void**)&totals));
     unsigned *k0 = buf, *i0 = buf + total, *k1 = buf + 2 * total, *i1 = buf + 3 * total;
     VX_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned) * nb, og.st));
     Image* O = nullptr;
@@ -269,12 +298,12 @@ extern "C" int32_t vx_percentiles(vx_ctx ctx, vx_img a, vx_img mask, double corr
           rs_hist_kernel<<<sgrid, kPcThreads, 0, og.st>>>(k0, count, nvox, table, nchunks_max, shift); }
         rc = check_launch("rs_hist_kernel");
         if (rc != VX_OK) break;
-        { VX_LAUNCH(og.c, og.s, "rs_scan_kernel");
-          rs_scan_kernel<<<nb, 1024, 0, og.st>>>(count, table, nchunks_max); }
-        rc = check_launch("rs_scan_kernel");
+        { VX_LAUNCH(og.c, og.s, "rs_rowscan_kernel");
+          rs_rowscan_kernel<<<dim3(256, nb), 256, 0, og.st>>>(count, table, totals, nchunks_max); }
+        rc = check_launch("rs_rowscan_kernel");
         if (rc != VX_OK) break;
         { VX_LAUNCH(og.c, og.s, "rs_scatter_kernel");
-          rs_scatter_kernel<<<sgrid, kPcThreads, 0, og.st>>>(k0, i0, k1, i1, count, nvox, table, nchunks_max, shift); }
+          rs_scatter_kernel<<<sgrid, kPcThreads, 0, og.st>>>(k0, i0, k1, i1, count, nvox, table, totals, nchunks_max, shift); }
         rc = check_launch("rs_scatter_kernel");
         unsigned* t;
         t = k0; k0 = k1; k1 = t;
@@ -291,6 +320,7 @@ extern "C" int32_t vx_percentiles(vx_ctx ctx, vx_img a, vx_img mask, double corr
     if (rc == VX_OK) rc = scratch_free(og.c, og.s, buf);
     if (rc == VX_OK) rc = scratch_free(og.c, og.s, count);
     if (rc == VX_OK) rc = scratch_free(og.c, og.s, table);
+    if (rc == VX_OK) rc = scratch_free(og.c, og.s, totals);
     if (rc != VX_OK) { drop(O); return rc; }
     return og.finish(O, out);
 }

@@ -111,6 +111,68 @@ static void put_event(Ctx* c, cudaEvent_t e) {
     c->event_pool.push_back(e);
 }
 
+// ---- device memory: caching sub-allocator over the stream-ordered pool ---------------
+static size_t round_block(size_t bytes) {
+    const size_t g = bytes < (1u << 20) ? 512 : (64u << 10);
+    return (bytes + g - 1) / g * g;
+}
+
+int dev_alloc(Ctx* c, int s, size_t bytes, void** out) {
+    const size_t sz = round_block(bytes ? bytes : 1);
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        auto it = c->cache[s].find(sz);
+        if (it != c->cache[s].end() && !it->second.empty()) {
+            *out = it->second.back();
+            it->second.pop_back();
+            c->cached_bytes -= sz;
+            return VX_OK;
+        }
+    }
+    cudaError_t e = cudaMallocAsync(out, sz, c->streams[s]);
+    if (e == cudaErrorMemoryAllocation) {  // give the cached blocks back and retry once
+        (void)cudaGetLastError();
+        dev_cache_release(c, 0);
+        e = cudaMallocAsync(out, sz, c->streams[s]);
+    }
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? VX_E_OOM : VX_E_CUDA,
+                    "cudaMallocAsync(%zu bytes) failed: %s", sz, cudaGetErrorString(e));
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->block_size[*out] = sz;
+    return VX_OK;
+}
+
+void dev_free(Ctx* c, int s, void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(c->mu);
+    auto it = c->block_size.find(p);
+    if (it == c->block_size.end()) return;
+    const size_t sz = it->second;
+    if (c->cached_bytes + sz > c->cache_limit) {  // over budget: hand it back to the pool
+        c->block_size.erase(it);
+        cudaFreeAsync(p, c->streams[s]);
+        return;
+    }
+    c->cache[s][sz].push_back(p);
+    c->cached_bytes += sz;
+}
+
+void dev_cache_release(Ctx* c, uint64_t keep_bytes) {
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int s = 0; s < kMaxStreams; s++)
+        for (auto& kv : c->cache[s])
+            while (!kv.second.empty() && c->cached_bytes > keep_bytes) {
+                void* p = kv.second.back();
+                kv.second.pop_back();
+                c->cached_bytes -= kv.first;
+                c->block_size.erase(p);
+                cudaFreeAsync(p, c->streams[s]);
+            }
+}
+
 // ---- images -------------------------------------------------------------------
 static size_t dtype_size(int dtype) {
     switch (dtype) {
@@ -139,13 +201,10 @@ int new_image(Ctx* c, int dtype, int nx, int ny, int nz, int nb, const float* sp
     // kernels read and write whole 16-element groups: pad the allocation so that the
     // last group of the batch stays inside it (the padding is never data)
     size_t alloc = ((im->count() + 15) / 16 * 16) * es + 64;
-    cudaError_t e = cudaMallocAsync(&im->d, alloc, c->streams[s]);
-    if (e != cudaSuccess) {
+    int arc = dev_alloc(c, s, alloc, &im->d);
+    if (arc != VX_OK) {
         delete im;
-        (void)cudaGetLastError();
-        return fail(e == cudaErrorMemoryAllocation ? VX_E_OOM : VX_E_CUDA,
-                    "cudaMallocAsync(%zu bytes) failed: %s", es * (size_t)nx * ny * nz * nb,
-                    cudaGetErrorString(e));
+        return arc;
     }
     im->ready = get_event(c);
     c->live_bytes += im->bytes;
@@ -193,7 +252,7 @@ void drop(Image* im) {
         cudaStreamWaitEvent(st, p.second, 0);
         put_event(c, p.second);
     }
-    cudaFreeAsync(im->d, st);
+    dev_free(c, im->home, im->d);
     put_event(c, im->ready);
     c->live_bytes -= im->bytes;
     c->live_handles -= 1;
@@ -201,17 +260,9 @@ void drop(Image* im) {
     delete im;
 }
 
-int scratch_alloc(Ctx* c, int s, size_t bytes, void** out) {
-    cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 16, c->streams[s]);
-    if (e != cudaSuccess) {
-        (void)cudaGetLastError();
-        return fail(e == cudaErrorMemoryAllocation ? VX_E_OOM : VX_E_CUDA,
-                    "scratch cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
-    }
-    return VX_OK;
-}
+int scratch_alloc(Ctx* c, int s, size_t bytes, void** out) { return dev_alloc(c, s, bytes, out); }
 int scratch_free(Ctx* c, int s, void* p) {
-    if (p) VX_CUDA(cudaFreeAsync(p, c->streams[s]));
+    dev_free(c, s, p);
     return VX_OK;
 }
 
@@ -223,17 +274,30 @@ int same_shape(const Image* a, const Image* b) {
 }
 
 // ---- launch accounting ---------------------------------------------------------
+static cudaEvent_t get_timing_event(Ctx* c) {
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (!c->timing_pool.empty()) {
+            cudaEvent_t e = c->timing_pool.back();
+            c->timing_pool.pop_back();
+            return e;
+        }
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
 LaunchScope::LaunchScope(Ctx* c_, int s_, const char* name_) : c(c_), s(s_), name(name_) {
     c->launches.fetch_add(1, std::memory_order_relaxed);
     if (c->prof_on.load(std::memory_order_relaxed)) {
-        cudaEventCreate(&e0);
+        e0 = get_timing_event(c);
         cudaEventRecord(e0, c->streams[s]);
     }
 }
 LaunchScope::~LaunchScope() {
     if (e0) {
-        cudaEvent_t e1 = nullptr;
-        cudaEventCreate(&e1);
+        cudaEvent_t e1 = get_timing_event(c);
         cudaEventRecord(e1, c->streams[s]);
         std::lock_guard<std::mutex> lk(c->mu);
         c->prof.push_back({name, e0, e1});
@@ -306,6 +370,9 @@ int32_t vx_init(int32_t device, vx_ctx* out) {
     VX_CUDA(cudaDeviceGetDefaultMemPool(&c->pool, device));
     uint64_t never = UINT64_MAX;
     VX_CUDA(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &never));
+    size_t free_b = 0, total_b = 0;
+    VX_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    c->cache_limit = total_b / 2;
     {
         std::lock_guard<std::mutex> lk(g_tab_mu);
         c->id = g_ctxs.size();
@@ -444,6 +511,7 @@ int32_t vx_mem_trim(vx_ctx ctx, uint64_t keep_bytes) {
     Ctx* c = get_ctx(ctx);
     VX_REQUIRE(c != nullptr, VX_E_INVALID_ARG, "invalid context handle");
     VX_CUDA(cudaSetDevice(c->device));
+    dev_cache_release(c, keep_bytes);
     VX_TRY(vx_sync(ctx));
     VX_CUDA(cudaMemPoolTrimTo(c->pool, (size_t)keep_bytes));
     return VX_OK;
@@ -511,8 +579,9 @@ static int prof_drain(Ctx* c) {
             acc.first += 1;
             acc.second += ms;
         }
-        cudaEventDestroy(r.e0);
-        cudaEventDestroy(r.e1);
+        std::lock_guard<std::mutex> lk(c->mu);
+        c->timing_pool.push_back(r.e0);
+        c->timing_pool.push_back(r.e1);
     }
     return VX_OK;
 }

@@ -19,6 +19,8 @@
 // (+-(2h+1)).  P is a k-term dot product against h2 (broadcast reads).
 #include <math.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "vx_internal.h"
@@ -27,11 +29,11 @@ namespace vx {
 
 constexpr int kXcThreads = 128;
 constexpr int kXcWarps = kXcThreads / 32;
-constexpr int kXcMaxBins = 254;  // bins are stored as u8, 255 = not counted
+constexpr int kXcMaxBins = 254;  // bins are stored as u8; value k = not counted
 
 __host__ __device__ __forceinline__ int xc_bin_of(float v, double m, double M, int k) {
     double dv = (double)v;
-    if (!(dv >= m) || !(dv < M)) return 255;
+    if (!(dv >= m) || !(dv < M)) return k;  // the dummy bin: not counted
 #ifdef __CUDA_ARCH__
     double t = __ddiv_rn(__dmul_rn(__dsub_rn(dv, m), (double)k), __dsub_rn(M, m));
 #else
@@ -113,7 +115,7 @@ __device__ __forceinline__ void hist_sub(unsigned char* hb, unsigned bin, unsign
 //   h2s   [2*nw]    u32   region histogram of this volume (zero padded)
 //   cols  [ncols]   u32   ball columns: dx | dz<<8 | ey<<16 (dx,dz as signed bytes)
 __global__ void __launch_bounds__(kXcThreads)
-xcorr_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
+xcorr_direct_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
              const unsigned* __restrict__ cols_g, const unsigned* __restrict__ h2,
              const long long* __restrict__ vstat, XcGeo g) {
     extern __shared__ __align__(16) unsigned smem[];
@@ -192,6 +194,223 @@ xcorr_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Ring-buffered variant (the default).  A block = 4 warps = 4 consecutive z planes of one
+// 32-voxel x chunk, marching together along a y segment.  The u8 bins the block needs
+// (x0-8..x0+39, 4+2*wz planes) are staged in a shared-memory ring of R >= 2*wy+3 rows:
+// every step the block fetches ONE new row per plane with coalesced 32-bit loads (168
+// words for rho = 5) instead of 162 scattered global byte loads per thread, and every
+// bin read of the inner loop is a conflict-free LDS (32 lanes = 32 consecutive bytes).
+//
+// The inner loop is branch-free: voxels that are not counted (outside [m,M) or outside
+// the image) carry the dummy bin k, which has its own histogram slot; its count is
+// subtracted when the coefficient is emitted (n1 = |ball| - h[k], S11 excludes h[k]^2,
+// h2[k] = 0).  Columns are sorted by their y half-extent so that the ring-row offsets of
+// the entering / leaving voxels are loop invariants of each group, and all histogram
+// traffic uses explicit shared-space addresses.
+struct XrGeo {
+    int nx, ny, nz, k, ncols, seg, nseg, nw, ball;
+    int wy, wz, R, P;      // ring rows (power of two) and planes (4 + 2*wz)
+    int gstart[17], gend[17];  // columns with y half-extent e are [gstart[e], gend[e]), gstart 4-aligned
+};
+constexpr int kRingXW = 48;  // bytes per ring row: 8 + 32 + 8
+
+__device__ __forceinline__ unsigned lds_u8(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// h[bin] += delta on the calling thread's private histogram column (hbase = shared address
+// of its word 0).  Word pair index = bin >> 1, stride kXcThreads*4 = 512 bytes.
+__device__ __forceinline__ void hist_bump(unsigned hbase, unsigned bin, int delta) {
+    const unsigned a = hbase + ((bin & 0xfeu) << 8) + ((bin & 1u) << 1);
+    unsigned short h;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(a));
+    h = (unsigned short)(h + delta);
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(h));
+}
+
+// one voxel enters with bin bi, one leaves with bin bo: nothing to do when they are equal
+// (the common case in flat regions), otherwise two predicated read-modify-writes
+__device__ __forceinline__ void hist_move(unsigned hbase, unsigned bi, unsigned bo) {
+    const unsigned ai = hbase + ((bi & 0xfeu) << 8) + ((bi & 1u) << 1);
+    const unsigned ao = hbase + ((bo & 0xfeu) << 8) + ((bo & 1u) << 1);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .u16 h;\n\t"
+        "setp.ne.u32 p, %0, %1;\n\t"
+        "@p ld.shared.u16 h, [%0];\n\t"
+        "@p add.u16 h, h, 1;\n\t"
+        "@p st.shared.u16 [%0], h;\n\t"
+        "@p ld.shared.u16 h, [%1];\n\t"
+        "@p sub.u16 h, h, 1;\n\t"
+        "@p st.shared.u16 [%1], h;\n\t"
+        "}" ::"r"(ai), "r"(ao) : "memory");
+}
+
+// Loads ring row yr (all planes).  Returns true when every word this thread loaded is
+// `ref` repeated (ref_word) -- used to detect rows that are one flat value.
+__device__ __forceinline__ bool ring_load_row(unsigned* ring32, const uint8_t* __restrict__ bv,
+                                              const XrGeo& g, int x0, int z0, int yr, unsigned ref_word) {
+    const int nwords = g.P * (kRingXW / 4);
+    const bool row_ok = yr >= 0 && yr < g.ny;
+    // a row outside the image is all dummy: it changes the histograms when it enters or
+    // leaves, so it is never "flat"; columns/planes outside the image are dummy in every
+    // row and are ignored by the test
+    bool flat = row_ok;
+    const int slot = yr & (g.R - 1);
+    const unsigned dummy = (unsigned)g.k * 0x01010101u;
+    for (int i = threadIdx.x; i < nwords; i += kXcThreads) {
+        const int p = i / (kRingXW / 4), w = i % (kRingXW / 4);
+        const int zz = z0 - g.wz + p;
+        const int xg = x0 - 8 + 4 * w;
+        unsigned v = dummy;
+        if (row_ok && zz >= 0 && zz < g.nz) {
+            const uint8_t* src = bv + ((size_t)zz * g.ny + yr) * g.nx;
+            if ((g.nx & 3) == 0) {
+                if (xg >= 0 && xg < g.nx) {
+                    v = __ldg(reinterpret_cast<const unsigned*>(src + xg));
+                    flat = flat && (v == ref_word);
+                }
+            } else {
+                v = 0;
+                int inside = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int xx = xg + b;
+                    const bool in = xx >= 0 && xx < g.nx;
+                    unsigned byte = in ? (unsigned)__ldg(src + xx) : (unsigned)g.k;
+                    inside += in;
+                    v |= byte << (8 * b);
+                }
+                if (inside == 4) flat = flat && (v == ref_word);
+                else if (inside != 0) flat = false;
+            }
+        }
+        ring32[(p * g.R + slot) * (kRingXW / 4) + w] = v;
+    }
+    return flat;
+}
+
+// grid (ceil(nx/32), ceil(nz/4)*nseg, nb), block 128.  Dynamic shared memory:
+//   hist [nw][128] u32 | h2s [2*nw] u32 | cols [ncols] u32 | ring [P][R][48] u8
+// cols[c] = byte offset of column c inside the ring relative to (plane = warp, row slot 0,
+// x = lane): ((wz+dz)*R)*48 + 8 + dx.
+__global__ void __launch_bounds__(kXcThreads)
+xcorr_ring_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
+                  const unsigned* __restrict__ cols_g, const unsigned* __restrict__ h2,
+                  const long long* __restrict__ vstat, const __grid_constant__ XrGeo g) {
+    extern __shared__ __align__(16) unsigned smem[];
+    unsigned* hist = smem;
+    unsigned* h2s = smem + (size_t)g.nw * kXcThreads;
+    unsigned* cols = h2s + ((2 * g.nw + 3) & ~3);
+    unsigned* ring32 = cols + ((g.ncols + 3) & ~3);
+    const int vol = blockIdx.z;
+    for (int i = threadIdx.x; i < 2 * g.nw; i += kXcThreads) h2s[i] = i < g.k ? h2[(size_t)vol * 256 + i] : 0u;
+    for (int i = threadIdx.x; i < g.ncols; i += kXcThreads) cols[i] = cols_g[i];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * 32;
+    const int zb = blockIdx.y / g.nseg, sg = blockIdx.y % g.nseg;
+    const int z0 = zb * kXcWarps;
+    const int x = x0 + lane, z = z0 + warp;
+    const int y0 = sg * g.seg;
+    const int y1 = min(g.ny, y0 + g.seg);
+    const bool active = x < g.nx && z < g.nz;
+    const size_t nvox = (size_t)g.nx * g.ny * g.nz;
+    const uint8_t* bv = bins + (size_t)vol * nvox;
+    float* ov = out + (size_t)vol * nvox;
+    const long long n2 = vstat[2 * vol], d2 = vstat[2 * vol + 1];
+    const unsigned K = (unsigned)g.k;
+    const int Rm = g.R - 1;
+    const unsigned hbase = (unsigned)__cvta_generic_to_shared(hist) + threadIdx.x * 4;
+    const unsigned tbase = (unsigned)__cvta_generic_to_shared(ring32) + warp * g.R * kRingXW + lane;
+
+    // Flat-region shortcut: when all 2*wy+2 ring rows a step touches hold one single value
+    // (background, saturated tissue) the histogram cannot change, so the step is skipped and
+    // the previous coefficient is stored again.  ref = bin of the first voxel of the block.
+    unsigned ref_word;
+    {
+        const int zz = min(max(z0 - g.wz, 0), g.nz - 1), xx = min(max(x0 - 8, 0), g.nx - 1);
+        const int yy = min(max(y0 - g.wy, 0), g.ny - 1);
+        ref_word = (unsigned)__ldg(bv + ((size_t)zz * g.ny + yy) * g.nx + xx) * 0x01010101u;
+    }
+    int flat_rows = 0;   // block-uniform: number of most recent consecutive flat rows
+    for (int yr = y0 - g.wy; yr <= y0 + g.wy; yr++) {
+        const bool f = ring_load_row(ring32, bv, g, x0, z0, yr, ref_word);
+        flat_rows = __syncthreads_and(f) ? flat_rows + 1 : 0;
+    }
+    for (int w = 0; w < g.nw; w++) hist[w * kXcThreads + threadIdx.x] = 0u;
+    __syncthreads();
+
+    if (active) {  // full ball around (x, y0, z)
+        for (int e = 0; e <= g.wy; e++)
+            for (int c = g.gstart[e]; c < g.gend[e]; c++) {
+                const unsigned co = cols[c];
+                for (int dy = -e; dy <= e; dy++)
+                    hist_bump(hbase, lds_u8(tbase + ((y0 + dy) & Rm) * kRingXW + co), 1);
+            }
+    }
+    float res = 0.0f;
+    bool changed = true;   // block-uniform: did the last slide touch the histograms?
+    for (int y = y0; y < y1; y++) {
+        if (active && changed) {
+            unsigned long long P = 0;
+            unsigned S2 = 0;
+            for (int w = 0; w < g.nw; w++) {
+                const unsigned v = hist[w * kXcThreads + threadIdx.x];
+                const uint2 hh = *reinterpret_cast<const uint2*>(h2s + 2 * w);
+                const unsigned lo = v & 0xffffu, hi = v >> 16;
+                P += (unsigned long long)lo * hh.x;
+                P += (unsigned long long)hi * hh.y;
+                S2 += lo * lo + hi * hi;
+            }
+            // remove the dummy bin K (not-counted voxels) from the statistics
+            const unsigned vd = hist[(K >> 1) * kXcThreads + threadIdx.x];
+            const unsigned hd = (K & 1u) ? (vd >> 16) : (vd & 0xffffu);
+            S2 -= hd * hd;
+            const long long n1 = (long long)g.ball - (long long)hd;
+            const long long num = (long long)K * (long long)P - n1 * n2;
+            const long long d1 = (long long)K * (long long)S2 - n1 * n1;
+            res = 0.0f;
+            if (d1 > 0 && d2 > 0)
+                res = (float)__ddiv_rn((double)num, __dsqrt_rn(__dmul_rn((double)d1, (double)d2)));
+        }
+        if (active) ov[((size_t)z * g.ny + y) * g.nx + x] = res;
+        if (y + 1 >= y1) break;
+        // the slot of row y+1+wy last held row y+1+wy-R < y-1-wy: nobody reads it any more
+        const bool f = ring_load_row(ring32, bv, g, x0, z0, y + 1 + g.wy, ref_word);
+        flat_rows = __syncthreads_and(f) ? flat_rows + 1 : 0;
+        changed = flat_rows < 2 * g.wy + 2;   // rows y-wy .. y+1+wy
+        if (active && changed) {
+            for (int e = 0; e <= g.wy; e++) {
+                const unsigned pin = tbase + ((y + 1 + e) & Rm) * kRingXW;
+                const unsigned pout = tbase + ((y - e) & Rm) * kRingXW;
+                int c = g.gstart[e];
+                const int cend = g.gend[e];
+                for (; c + 4 <= cend; c += 4) {
+                    const uint4 co = *reinterpret_cast<const uint4*>(cols + c);   // gstart is 4-aligned
+                    const unsigned i0 = lds_u8(pin + co.x), o0 = lds_u8(pout + co.x);
+                    const unsigned i1 = lds_u8(pin + co.y), o1 = lds_u8(pout + co.y);
+                    const unsigned i2 = lds_u8(pin + co.z), o2 = lds_u8(pout + co.z);
+                    const unsigned i3 = lds_u8(pin + co.w), o3 = lds_u8(pout + co.w);
+                    hist_move(hbase, i0, o0);
+                    hist_move(hbase, i1, o1);
+                    hist_move(hbase, i2, o2);
+                    hist_move(hbase, i3, o3);
+                }
+                for (; c < cend; c++) {
+                    const unsigned co = cols[c];
+                    const unsigned i0 = lds_u8(pin + co), o0 = lds_u8(pout + co);
+                    hist_move(hbase, i0, o0);
+                }
+            }
+        }
+    }
+}
+
 // ball columns (dx, dz, ey): offsets with (dx*sx)^2 + (dy*sy)^2 + (dz*sz)^2 <= rho^2, binary64
 static bool build_columns(const float sp[3], float rho, std::vector<unsigned>* cols, long long* ball) {
     cols->clear();
@@ -252,7 +471,7 @@ extern "C" int32_t vx_cross_correlation(vx_ctx ctx, vx_img a, vx_img b, vx_img r
     VX_TRY(scratch_alloc(og.c, og.s, total, (void**)&d_bins));
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * 256 * nb, (void**)&d_h2));
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(long long) * 2 * nb, (void**)&d_vstat));
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (cols.size() + 1), (void**)&d_cols));
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (cols.size() + 128), (void**)&d_cols));
     VX_CUDA(cudaMemcpyAsync(d_mM, m, sizeof(double) * nb, cudaMemcpyHostToDevice, og.st));
     VX_CUDA(cudaMemcpyAsync(d_mM + nb, M, sizeof(double) * nb, cudaMemcpyHostToDevice, og.st));
     if (!cols.empty())
@@ -278,27 +497,77 @@ extern "C" int32_t vx_cross_correlation(vx_ctx ctx, vx_img a, vx_img b, vx_img r
     VX_TRY(check_launch("xc_stat_kernel"));
     Image* O = nullptr;
     VX_TRY(new_image(og.c, VX_F32, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
-    XcGeo g;
-    g.nx = A->nx; g.ny = A->ny; g.nz = A->nz; g.k = k;
-    g.ncols = (int)cols.size();
-    g.nw = (k + 1) / 2;
+    // geometry of the ball
+    int wx = 0, wy = 0, wz = 0;
+    for (unsigned cw : cols) {
+        int dx = (int)(signed char)(cw & 0xffu), dz = (int)(signed char)((cw >> 8) & 0xffu), ey = (int)(cw >> 16);
+        wx = std::max(wx, std::abs(dx)); wz = std::max(wz, std::abs(dz)); wy = std::max(wy, ey);
+    }
+    const int nw = (k + 2) / 2;   // k bins + the dummy bin k
     // y segments: long enough to amortise the initial full-ball build, short enough to
     // give the batch at least a few waves of CTAs
-    g.seg = A->ny <= 64 ? A->ny : 64;
-    g.nseg = (A->ny + g.seg - 1) / g.seg;
-    size_t smem = sizeof(unsigned) * ((size_t)g.nw * kXcThreads + 2 * g.nw + g.ncols);
+    const int seg = A->ny <= 64 ? A->ny : 64;
+    const int nseg = (A->ny + seg - 1) / seg;
+    int ringR = 4;
+    while (ringR < 2 * wy + 3) ringR <<= 1;
+    const int P = kXcWarps + 2 * wz;
     int rc = VX_OK;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(xcorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) rc = fail(VX_E_CUDA, "smem attribute: %s", cudaGetErrorString(e));
-    }
-    if (rc == VX_OK) {
-        dim3 grid((A->nx + 31) / 32, (A->nz * g.nseg + kXcWarps - 1) / kXcWarps, nb);
-        {
-            VX_LAUNCH(og.c, og.s, "xcorr_kernel");
-            xcorr_kernel<<<grid, kXcThreads, smem, og.st>>>(d_bins, (float*)O->d, d_cols, d_h2, d_vstat, g);
+    // ring offsets, sorted by y half-extent, every group padded to start 4-aligned
+    std::vector<unsigned> ring_cols;
+    XrGeo g;
+    bool ring_ok = wx <= 8 && wy <= 16;
+    if (ring_ok) {
+        for (int e = 0; e <= wy; e++) {
+            while (ring_cols.size() & 3) ring_cols.push_back(0);   // alignment filler, never read
+            g.gstart[e] = (int)ring_cols.size();
+            int cnt = 0;
+            for (unsigned cw : cols) {
+                int dx = (int)(signed char)(cw & 0xffu), dz = (int)(signed char)((cw >> 8) & 0xffu), ey = (int)(cw >> 16);
+                if (ey != e) continue;
+                ring_cols.push_back((unsigned)(((wz + dz) * ringR) * kRingXW + 8 + dx));
+                cnt++;
+            }
+            g.gend[e] = g.gstart[e] + cnt;
         }
-        rc = check_launch("xcorr_kernel");
+    }
+    const size_t smem_ring = sizeof(unsigned) * ((size_t)nw * kXcThreads + ((2 * nw + 3) & ~3) + ((ring_cols.size() + 3) & ~(size_t)3)) +
+                             (size_t)P * ringR * kRingXW;
+    if (ring_ok && smem_ring <= 160 * 1024) {
+        g.nx = A->nx; g.ny = A->ny; g.nz = A->nz; g.k = k;
+        g.ncols = (int)ring_cols.size();
+        g.seg = seg; g.nseg = nseg; g.nw = nw; g.wy = wy; g.wz = wz; g.R = ringR; g.P = P;
+        g.ball = (int)ball;
+        VX_CUDA(cudaMemcpyAsync(d_cols, ring_cols.data(), sizeof(unsigned) * ring_cols.size(), cudaMemcpyHostToDevice, og.st));
+        if (smem_ring > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(xcorr_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ring);
+            if (e != cudaSuccess) rc = fail(VX_E_CUDA, "smem attribute: %s", cudaGetErrorString(e));
+        }
+        if (rc == VX_OK) {
+            dim3 grid((A->nx + 31) / 32, ((A->nz + kXcWarps - 1) / kXcWarps) * nseg, nb);
+            {
+                VX_LAUNCH(og.c, og.s, "xcorr_kernel");
+                xcorr_ring_kernel<<<grid, kXcThreads, smem_ring, og.st>>>(d_bins, (float*)O->d, d_cols, d_h2, d_vstat, g);
+            }
+            rc = check_launch("xcorr_kernel");
+        }
+    } else {
+        XcGeo g;
+        g.nx = A->nx; g.ny = A->ny; g.nz = A->nz; g.k = k;
+        g.ncols = (int)cols.size();
+        g.nw = nw; g.seg = seg; g.nseg = nseg;
+        size_t smem = sizeof(unsigned) * ((size_t)g.nw * kXcThreads + 2 * g.nw + g.ncols);
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(xcorr_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) rc = fail(VX_E_CUDA, "smem attribute: %s", cudaGetErrorString(e));
+        }
+        if (rc == VX_OK) {
+            dim3 grid((A->nx + 31) / 32, (A->nz * g.nseg + kXcWarps - 1) / kXcWarps, nb);
+            {
+                VX_LAUNCH(og.c, og.s, "xcorr_direct_kernel");
+                xcorr_direct_kernel<<<grid, kXcThreads, smem, og.st>>>(d_bins, (float*)O->d, d_cols, d_h2, d_vstat, g);
+            }
+            rc = check_launch("xcorr_direct_kernel");
+        }
     }
     if (rc == VX_OK) rc = scratch_free(og.c, og.s, d_mM);
     if (rc == VX_OK) rc = scratch_free(og.c, og.s, d_bins);
