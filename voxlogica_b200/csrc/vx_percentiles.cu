@@ -6,7 +6,7 @@
 // The rank is an exact integer; only the final division rounds (binary64, then to f32).
 //
 // Device algorithm, per volume of the batch and with no host round trip:
-//   1. compact the masked voxels into (sortable key, voxel index) pairs
+//   1. compact the masked voxels into packed (sortable key << 32 | voxel index) pairs
 //      (block-aggregated: one atomicAdd per 4096 voxels);
 //   2. stable LSD radix sort of the pairs, 4 passes of 8 bits.  The unit of work is a
 //      warp-owned chunk of 2048 keys: digits are ranked inside the warp with
@@ -29,29 +29,45 @@ __device__ __forceinline__ unsigned sortable_key(float v) {
 }
 
 // ---- 1. compaction -------------------------------------------------------------------
+// Pairs are packed as (key << 32) | voxel index so that every pass moves ONE 8-byte word per
+// element (a scattered 8-byte store costs one L2 transaction, two 4-byte stores cost two).
 // grid (blocks, nb).  Each block walks tiles of 256*16 voxels of its volume.
 __global__ void __launch_bounds__(kPcThreads)
 pc_compact_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mask, size_t nvox,
-                  unsigned* __restrict__ keys, unsigned* __restrict__ idx,
-                  unsigned* __restrict__ count) {
+                  unsigned long long* __restrict__ pairs, unsigned* __restrict__ count) {
     __shared__ unsigned warp_tot[kPcThreads / 32];
     __shared__ unsigned tile_base;
     const size_t vol = blockIdx.y;
     const float* a = img + vol * nvox;
     const uint8_t* m = mask + vol * nvox;
-    unsigned* ko = keys + vol * nvox;
-    unsigned* io = idx + vol * nvox;
+    unsigned long long* po = pairs + vol * nvox;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t tile = (size_t)kPcThreads * 16;
+    const bool aligned = (nvox & 15) == 0;  // every volume of the batch starts 16-aligned
     for (size_t t0 = (size_t)blockIdx.x * tile; t0 < nvox; t0 += (size_t)gridDim.x * tile) {
         const size_t first = t0 + (size_t)threadIdx.x * 16;
         unsigned bits = 0;
+        float v[16];
+        if (aligned && first + 16 <= nvox) {
+            const uint4 mw = __ldg(reinterpret_cast<const uint4*>(m + first));
+            const unsigned w[4] = {mw.x, mw.y, mw.z, mw.w};
 #pragma unroll
-        for (int e = 0; e < 16; e++) {
-            size_t i = first + e;
-            if (i < nvox && m[i] != 0) bits |= 1u << e;
+            for (int q = 0; q < 4; q++) {
+                const unsigned t = __vcmpne4(w[q], 0u) & 0x01010101u;
+                bits |= (((t * 0x01020408u) >> 24) & 0xfu) << (4 * q);
+                const float4 f = __ldg(reinterpret_cast<const float4*>(a + first) + q);
+                v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                const size_t i = first + e;
+                const bool in = i < nvox;
+                v[e] = in ? a[i] : 0.f;
+                if (in && m[i] != 0) bits |= 1u << e;
+            }
         }
-        unsigned c = __popc(bits);
+        const unsigned c = __popc(bits);
         // exclusive scan over the block
         unsigned incl = c;
 #pragma unroll
@@ -64,20 +80,19 @@ pc_compact_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mas
         unsigned wbase = 0, total = 0;
 #pragma unroll
         for (int w = 0; w < kPcThreads / 32; w++) {
-            unsigned v = warp_tot[w];
-            if (w < warp) wbase += v;
-            total += v;
+            unsigned t = warp_tot[w];
+            if (w < warp) wbase += t;
+            total += t;
         }
         if (threadIdx.x == 0) tile_base = total ? atomicAdd(count + vol, total) : 0u;
         __syncthreads();
         unsigned pos = tile_base + wbase + incl - c;
-        while (bits) {
-            int e = __ffs(bits) - 1;
-            bits &= bits - 1;
-            size_t i = first + e;
-            ko[pos] = sortable_key(a[i]);
-            io[pos] = (unsigned)i;
-            pos++;
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            if ((bits >> e) & 1u) {
+                po[pos] = ((unsigned long long)sortable_key(v[e]) << 32) | (unsigned)(first + e);
+                pos++;
+            }
         }
         __syncthreads();  // tile_base / warp_tot reuse
     }
@@ -86,7 +101,7 @@ pc_compact_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mas
 // ---- 2. radix sort passes --------------------------------------------------------------
 // table layout: [vol][digit][chunk]  (chunk-major inside a digit so the scan is one sweep)
 __global__ void __launch_bounds__(kPcThreads)
-rs_hist_kernel(const unsigned* __restrict__ keys, const unsigned* __restrict__ count, size_t nvox,
+rs_hist_kernel(const unsigned long long* __restrict__ pairs, const unsigned* __restrict__ count, size_t nvox,
                unsigned* __restrict__ table, int nchunks_max, int shift) {
     __shared__ unsigned cnt[kPcThreads / 32][256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -97,14 +112,14 @@ rs_hist_kernel(const unsigned* __restrict__ keys, const unsigned* __restrict__ c
     if (chunk >= nchunks) return;
     for (int d = lane; d < 256; d += 32) cnt[warp][d] = 0;
     __syncwarp();
-    const unsigned* k = keys + vol * nvox;
+    const unsigned long long* k = pairs + vol * nvox;
     const unsigned base = chunk * kWarpChunk;
     for (int r = 0; r < kRounds; r++) {
         unsigned p = base + r * 32 + lane;
         bool ok = p < n;
         unsigned active = __ballot_sync(0xffffffffu, ok);
         if (ok) {
-            unsigned d = (k[p] >> shift) & 0xffu;
+            unsigned d = (unsigned)(k[p] >> (32 + shift)) & 0xffu;
             unsigned peers = __match_any_sync(active, d);
             if ((peers & ((1u << lane) - 1u)) == 0) cnt[warp][d] += __popc(peers);
         }
@@ -158,8 +173,7 @@ rs_rowscan_kernel(const unsigned* __restrict__ count, unsigned* __restrict__ tab
 }
 
 __global__ void __launch_bounds__(kPcThreads)
-rs_scatter_kernel(const unsigned* __restrict__ keys_in, const unsigned* __restrict__ idx_in,
-                  unsigned* __restrict__ keys_out, unsigned* __restrict__ idx_out,
+rs_scatter_kernel(const unsigned long long* __restrict__ pairs_in, unsigned long long* __restrict__ pairs_out,
                   const unsigned* __restrict__ count, size_t nvox, const unsigned* __restrict__ table,
                   const unsigned* __restrict__ totals, int nchunks_max, int shift) {
     __shared__ unsigned off[kPcThreads / 32][256];
@@ -190,18 +204,16 @@ rs_scatter_kernel(const unsigned* __restrict__ keys_in, const unsigned* __restri
         }
     }
     __syncwarp();
-    const unsigned* ki = keys_in + vol * nvox;
-    const unsigned* ii = idx_in + vol * nvox;
-    unsigned* ko = keys_out + vol * nvox;
-    unsigned* io = idx_out + vol * nvox;
+    const unsigned long long* pi = pairs_in + vol * nvox;
+    unsigned long long* po = pairs_out + vol * nvox;
     const unsigned base = chunk * kWarpChunk;
     for (int r = 0; r < kRounds; r++) {
         unsigned p = base + r * 32 + lane;
         bool ok = p < n;
         unsigned active = __ballot_sync(0xffffffffu, ok);
         if (ok) {
-            unsigned key = ki[p], id = ii[p];
-            unsigned d = (key >> shift) & 0xffu;
+            const unsigned long long kv = pi[p];
+            unsigned d = (unsigned)(kv >> (32 + shift)) & 0xffu;
             unsigned peers = __match_any_sync(active, d);
             unsigned rank = __popc(peers & ((1u << lane) - 1u));
             int leader = __ffs(peers) - 1;
@@ -211,8 +223,7 @@ rs_scatter_kernel(const unsigned* __restrict__ keys_in, const unsigned* __restri
                 off[warp][d] = start + __popc(peers);
             }
             start = __shfl_sync(peers, start, leader);
-            ko[start + rank] = key;
-            io[start + rank] = id;
+            po[start + rank] = kv;
         }
         __syncwarp();
     }
@@ -220,39 +231,39 @@ rs_scatter_kernel(const unsigned* __restrict__ keys_in, const unsigned* __restri
 
 // ---- 3. ranks ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(kPcThreads)
-pc_rank_kernel(const unsigned* __restrict__ keys, const unsigned* __restrict__ idx,
-               const unsigned* __restrict__ count, size_t nvox, float* __restrict__ out,
-               double correction) {
+pc_rank_kernel(const unsigned long long* __restrict__ pairs, const unsigned* __restrict__ count,
+               size_t nvox, float* __restrict__ out, double correction) {
     const size_t vol = blockIdx.y;
     const unsigned n = count[vol];
-    const unsigned* k = keys + vol * nvox;
-    const unsigned* id = idx + vol * nvox;
+    const unsigned long long* k = pairs + vol * nvox;
     float* o = out + vol * nvox;
+    auto key_at = [&](unsigned i) { return (unsigned)(k[i] >> 32); };
     for (unsigned p = blockIdx.x * kPcThreads + threadIdx.x; p < n; p += gridDim.x * kPcThreads) {
-        const unsigned key = k[p];
+        const unsigned long long kv = k[p];
+        const unsigned key = (unsigned)(kv >> 32);
         unsigned less = p;
-        if (p > 0 && k[p - 1] == key) {  // inside a run of equal keys: lower bound
+        if (p > 0 && key_at(p - 1) == key) {  // inside a run of equal keys: lower bound
             unsigned lo = 0, hi = p;
             while (lo < hi) {
                 unsigned mid = (lo + hi) >> 1;
-                if (k[mid] < key) lo = mid + 1; else hi = mid;
+                if (key_at(mid) < key) lo = mid + 1; else hi = mid;
             }
             less = lo;
         }
         double num = (double)less;
         if (correction != 0.0) {
             unsigned up = p + 1;
-            if (up < n && k[up] == key) {  // upper bound
+            if (up < n && key_at(up) == key) {  // upper bound
                 unsigned lo = up, hi = n;
                 while (lo < hi) {
                     unsigned mid = (lo + hi) >> 1;
-                    if (k[mid] <= key) lo = mid + 1; else hi = mid;
+                    if (key_at(mid) <= key) lo = mid + 1; else hi = mid;
                 }
                 up = lo;
             }
             num = __dadd_rn(num, __dmul_rn(correction, (double)(up - less)));
         }
-        o[id[p]] = (float)__ddiv_rn(num, (double)n);
+        o[(unsigned)kv] = (float)__ddiv_rn(num, (double)n);
     }
 }
 
@@ -271,12 +282,13 @@ extern "C" int32_t vx_percentiles(vx_ctx ctx, vx_img a, vx_img mask, double corr
     const size_t nvox = A->nvox(), total = A->count();
     const int nb = A->nb;
     const int nchunks_max = (int)((nvox + kWarpChunk - 1) / kWarpChunk);
-    unsigned *buf = nullptr, *count = nullptr, *table = nullptr, *totals = nullptr;
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * total * 4, (void**)&buf));
+    unsigned long long* buf = nullptr;
+    unsigned *count = nullptr, *table = nullptr, *totals = nullptr;
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned long long) * total * 2, (void**)&buf));
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * nb, (void**)&count));
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (size_t)nb * 256 * nchunks_max, (void**)&table));
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (size_t)nb * 256, (void**)&totals));
-    unsigned *k0 = buf, *i0 = buf + total, *k1 = buf + 2 * total, *i1 = buf + 3 * total;
+    unsigned long long *k0 = buf, *k1 = buf + total;
     VX_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned) * nb, og.st));
     Image* O = nullptr;
     VX_TRY(new_image(og.c, VX_F32, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
@@ -288,7 +300,7 @@ extern "C" int32_t vx_percentiles(vx_ctx ctx, vx_img a, vx_img mask, double corr
         int cap = (kNumSMs * 8 + nb - 1) / nb;
         dim3 grid(per_vol < cap ? per_vol : cap, nb);
         { VX_LAUNCH(og.c, og.s, "pc_compact_kernel");
-          pc_compact_kernel<<<grid, kPcThreads, 0, og.st>>>((const float*)A->d, (const uint8_t*)M->d, nvox, k0, i0, count); }
+          pc_compact_kernel<<<grid, kPcThreads, 0, og.st>>>((const float*)A->d, (const uint8_t*)M->d, nvox, k0, count); }
         rc = check_launch("pc_compact_kernel");
     }
     dim3 sgrid((nchunks_max + kPcThreads / 32 - 1) / (kPcThreads / 32), nb);
@@ -303,18 +315,16 @@ extern "C" int32_t vx_percentiles(vx_ctx ctx, vx_img a, vx_img mask, double corr
         rc = check_launch("rs_rowscan_kernel");
         if (rc != VX_OK) break;
         { VX_LAUNCH(og.c, og.s, "rs_scatter_kernel");
-          rs_scatter_kernel<<<sgrid, kPcThreads, 0, og.st>>>(k0, i0, k1, i1, count, nvox, table, totals, nchunks_max, shift); }
+          rs_scatter_kernel<<<sgrid, kPcThreads, 0, og.st>>>(k0, k1, count, nvox, table, totals, nchunks_max, shift); }
         rc = check_launch("rs_scatter_kernel");
-        unsigned* t;
-        t = k0; k0 = k1; k1 = t;
-        t = i0; i0 = i1; i1 = t;
+        unsigned long long* t = k0; k0 = k1; k1 = t;
     }
     if (rc == VX_OK) {
         int per_vol = (int)((nvox + kPcThreads - 1) / kPcThreads);
         int cap = (kNumSMs * 8 + nb - 1) / nb;
         dim3 grid(per_vol < cap ? per_vol : cap, nb);
         { VX_LAUNCH(og.c, og.s, "pc_rank_kernel");
-          pc_rank_kernel<<<grid, kPcThreads, 0, og.st>>>(k0, i0, count, nvox, (float*)O->d, correction); }
+          pc_rank_kernel<<<grid, kPcThreads, 0, og.st>>>(k0, count, nvox, (float*)O->d, correction); }
         rc = check_launch("pc_rank_kernel");
     }
     if (rc == VX_OK) rc = scratch_free(og.c, og.s, buf);

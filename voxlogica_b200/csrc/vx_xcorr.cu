@@ -211,94 +211,148 @@ xcorr_direct_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
 // traffic uses explicit shared-space addresses.
 struct XrGeo {
     int nx, ny, nz, k, ncols, seg, nseg, nw, ball;
-    int wy, wz, R, P;      // ring rows (power of two) and planes (4 + 2*wz)
+    int wy, wz, R, P;      // ring rows (2*wy+3) and planes (4 + 2*wz)
     int gstart[17], gend[17];  // columns with y half-extent e are [gstart[e], gend[e]), gstart 4-aligned
 };
-constexpr int kRingXW = 48;  // bytes per ring row: 8 + 32 + 8
+constexpr int kRingXW = 48;  // voxels per ring row: 8 + 32 + 8
+constexpr int kRingXB = 96;  // bytes per ring row (one u16 per voxel)
 
-__device__ __forceinline__ unsigned lds_u8(unsigned addr) {
-    unsigned v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+// The ring does not hold bins but the byte offset of the bin's counter inside a thread's
+// histogram column: word pair index = bin >> 1 (stride kXcThreads*4 = 512 bytes), half =
+// bin & 1.  Converting once per loaded voxel saves five ALU instructions on each of the
+// 162 counter accesses per step.
+__device__ __forceinline__ unsigned bin_offset(unsigned bin) { return ((bin & 0xfeu) << 8) + ((bin & 1u) << 1); }
+__device__ __forceinline__ unsigned offsets2(unsigned two_bins) {  // bins in bits 0-7 and 8-15
+    return bin_offset(two_bins & 0xffu) | (bin_offset((two_bins >> 8) & 0xffu) << 16);
+}
+__device__ __forceinline__ unsigned lds_u16(unsigned addr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
     return v;
 }
-// h[bin] += delta on the calling thread's private histogram column (hbase = shared address
-// of its word 0).  Word pair index = bin >> 1, stride kXcThreads*4 = 512 bytes.
-__device__ __forceinline__ void hist_bump(unsigned hbase, unsigned bin, int delta) {
-    const unsigned a = hbase + ((bin & 0xfeu) << 8) + ((bin & 1u) << 1);
-    unsigned short h;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(a));
-    h = (unsigned short)(h + delta);
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(h));
+__device__ __forceinline__ int ring_slot(int yr, int R) {
+    int s = yr % R;
+    return s < 0 ? s + R : s;
+}
+// slot of (row with slot s) + d, for -R < d < R, without a division
+__device__ __forceinline__ int slot_add(int s, int d, int R) {
+    int t = s + d;
+    if (t >= R) t -= R;
+    if (t < 0) t += R;
+    return t;
+}
+// h[counter at offset] += delta on the calling thread's private histogram column (hbase =
+// shared address of its word 0)
+__device__ __forceinline__ void hist_bump(unsigned hbase, unsigned off, int delta) {
+    const unsigned a = hbase + off;
+    unsigned h;   // 32-bit registers: no PRMT juggling of 16-bit halves
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(h) : "r"(a));
+    h += delta;
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(h));
 }
 
-// one voxel enters with bin bi, one leaves with bin bo: nothing to do when they are equal
+// one voxel enters (counter offset oi), one leaves (oo): nothing to do when they are equal
 // (the common case in flat regions), otherwise two predicated read-modify-writes
-__device__ __forceinline__ void hist_move(unsigned hbase, unsigned bi, unsigned bo) {
-    const unsigned ai = hbase + ((bi & 0xfeu) << 8) + ((bi & 1u) << 1);
-    const unsigned ao = hbase + ((bo & 0xfeu) << 8) + ((bo & 1u) << 1);
+__device__ __forceinline__ void hist_move(unsigned hbase, unsigned oi, unsigned oo) {
+    const unsigned ai = hbase + oi;
+    const unsigned ao = hbase + oo;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        ".reg .u16 h;\n\t"
+        ".reg .u32 h, g;\n\t"
         "setp.ne.u32 p, %0, %1;\n\t"
         "@p ld.shared.u16 h, [%0];\n\t"
-        "@p add.u16 h, h, 1;\n\t"
+        "@p ld.shared.u16 g, [%1];\n\t"
+        "@p add.u32 h, h, 1;\n\t"
+        "@p sub.u32 g, g, 1;\n\t"
         "@p st.shared.u16 [%0], h;\n\t"
-        "@p ld.shared.u16 h, [%1];\n\t"
-        "@p sub.u16 h, h, 1;\n\t"
-        "@p st.shared.u16 [%1], h;\n\t"
+        "@p st.shared.u16 [%1], g;\n\t"
         "}" ::"r"(ai), "r"(ao) : "memory");
 }
 
-// Loads ring row yr (all planes).  Returns true when every word this thread loaded is
-// `ref` repeated (ref_word) -- used to detect rows that are one flat value.
-__device__ __forceinline__ bool ring_load_row(unsigned* ring32, const uint8_t* __restrict__ bv,
-                                              const XrGeo& g, int x0, int z0, int yr, unsigned ref_word) {
-    const int nwords = g.P * (kRingXW / 4);
-    const bool row_ok = yr >= 0 && yr < g.ny;
-    // a row outside the image is all dummy: it changes the histograms when it enters or
-    // leaves, so it is never "flat"; columns/planes outside the image are dummy in every
-    // row and are ignored by the test
-    bool flat = row_ok;
-    const int slot = yr & (g.R - 1);
-    const unsigned dummy = (unsigned)g.k * 0x01010101u;
-    for (int i = threadIdx.x; i < nwords; i += kXcThreads) {
-        const int p = i / (kRingXW / 4), w = i % (kRingXW / 4);
-        const int zz = z0 - g.wz + p;
-        const int xg = x0 - 8 + 4 * w;
-        unsigned v = dummy;
-        if (row_ok && zz >= 0 && zz < g.nz) {
-            const uint8_t* src = bv + ((size_t)zz * g.ny + yr) * g.nx;
-            if ((g.nx & 3) == 0) {
-                if (xg >= 0 && xg < g.nx) {
-                    v = __ldg(reinterpret_cast<const unsigned*>(src + xg));
-                    flat = flat && (v == ref_word);
-                }
-            } else {
-                v = 0;
-                int inside = 0;
+// Per-thread view of the ring rows: thread t owns ring words t and t+128 of every row
+// (a row is P planes x 12 words).  fetch() issues the global loads of one row into
+// registers, commit() stores them into the ring two steps later (software prefetch, so
+// the load latency hides behind the histogram work of the steps in between) and reports
+// whether every in-image word equals ref_word (the row is "flat").
+struct RingLoader {
+    const uint8_t* src[2];  // address of x = xg in row y = 0 of the word's plane (nullptr: plane outside)
+    int xg[2];              // x of the word's first byte (may be < 0 or >= nx)
+    int ring_off[2];        // word index inside ring row slot 0, -1: thread owns no such word
+    int nx, ny;
+    unsigned dummy, ref_word, kbin;
+    bool bytewise;
+
+    __device__ __forceinline__ void init(const uint8_t* bv, const XrGeo& g, int x0, int z0, unsigned ref) {
+        nx = g.nx; ny = g.ny;
+        kbin = (unsigned)g.k;
+        dummy = kbin * 0x01010101u;
+        ref_word = ref;
+        bytewise = (g.nx & 3) != 0;
+        const int nwords = g.P * (kRingXW / 4);
 #pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const int xx = xg + b;
-                    const bool in = xx >= 0 && xx < g.nx;
-                    unsigned byte = in ? (unsigned)__ldg(src + xx) : (unsigned)g.k;
-                    inside += in;
-                    v |= byte << (8 * b);
-                }
-                if (inside == 4) flat = flat && (v == ref_word);
-                else if (inside != 0) flat = false;
+        for (int s = 0; s < 2; s++) {
+            const int i = threadIdx.x + s * kXcThreads;
+            src[s] = nullptr;
+            ring_off[s] = -1;
+            xg[s] = 0;
+            if (i < nwords) {
+                const int p = i / (kRingXW / 4), w = i % (kRingXW / 4);
+                const int zz = z0 - g.wz + p;
+                xg[s] = x0 - 8 + 4 * w;
+                ring_off[s] = (p * g.R) * (kRingXW / 4) + w;
+                if (zz >= 0 && zz < g.nz && xg[s] + 3 >= 0 && xg[s] < g.nx)
+                    src[s] = bv + ((size_t)zz * g.ny) * g.nx;
             }
         }
-        ring32[(p * g.R + slot) * (kRingXW / 4) + w] = v;
     }
-    return flat;
-}
+    // issue the global loads of row yr into v[] (nothing here waits for them)
+    __device__ __forceinline__ void fetch(int yr, unsigned (&v)[2]) const {
+        const bool row_ok = yr >= 0 && yr < ny;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            v[s] = dummy;
+            if (row_ok && src[s] != nullptr) {
+                const uint8_t* a = src[s] + (size_t)yr * nx;
+                if (!bytewise) {  // nx % 4 == 0: the word is entirely inside the row
+                    v[s] = __ldg(reinterpret_cast<const unsigned*>(a + xg[s]));
+                } else {
+                    unsigned w = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int xx = xg[s] + b;
+                        w |= ((xx >= 0 && xx < nx) ? (unsigned)__ldg(a + xx) : kbin) << (8 * b);
+                    }
+                    v[s] = w;
+                }
+            }
+        }
+    }
+    // store row yr into the ring; returns whether every in-image word of this thread equals
+    // ref_word.  A row outside the image is all dummy and never flat (it changes the
+    // histograms when it enters or leaves); columns/planes outside the image are dummy in
+    // every row and are ignored.
+    __device__ __forceinline__ bool commit(unsigned* ring32, int yr, int slot_of_yr, const unsigned (&v)[2]) const {
+        const int slot = slot_of_yr * (kRingXW / 4);
+        bool flat = yr >= 0 && yr < ny;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            if (ring_off[s] < 0) continue;
+            reinterpret_cast<uint2*>(ring32)[ring_off[s] + slot] = make_uint2(offsets2(v[s]), offsets2(v[s] >> 16));
+            if (src[s] != nullptr) {
+                const bool whole = xg[s] >= 0 && xg[s] + 3 < nx;
+                flat = flat && whole && v[s] == ref_word;
+            }
+        }
+        return flat;
+    }
+};
 
 // grid (ceil(nx/32), ceil(nz/4)*nseg, nb), block 128.  Dynamic shared memory:
-//   hist [nw][128] u32 | h2s [2*nw] u32 | cols [ncols] u32 | ring [P][R][48] u8
+//   hist [nw][128] u32 | h2s [2*nw] u32 | cols [ncols] u32 | ring [P][R][48] u16
 // cols[c] = byte offset of column c inside the ring relative to (plane = warp, row slot 0,
-// x = lane): ((wz+dz)*R)*48 + 8 + dx.
-__global__ void __launch_bounds__(kXcThreads)
+// x = lane): ((wz+dz)*R)*96 + 2*(8 + dx).
+__global__ void __launch_bounds__(kXcThreads, 5)
 xcorr_ring_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
                   const unsigned* __restrict__ cols_g, const unsigned* __restrict__ h2,
                   const long long* __restrict__ vstat, const __grid_constant__ XrGeo g) {
@@ -310,6 +364,10 @@ xcorr_ring_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
     const int vol = blockIdx.z;
     for (int i = threadIdx.x; i < 2 * g.nw; i += kXcThreads) h2s[i] = i < g.k ? h2[(size_t)vol * 256 + i] : 0u;
     for (int i = threadIdx.x; i < g.ncols; i += kXcThreads) cols[i] = cols_g[i];
+    // group bounds in shared memory: indexing the kernel parameter with a runtime e would
+    // go through the (slow) indexed constant path
+    __shared__ int gs[17], ge[17];
+    if (threadIdx.x < 17) { gs[threadIdx.x] = g.gstart[threadIdx.x]; ge[threadIdx.x] = g.gend[threadIdx.x]; }
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x0 = blockIdx.x * 32;
@@ -324,9 +382,8 @@ xcorr_ring_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
     float* ov = out + (size_t)vol * nvox;
     const long long n2 = vstat[2 * vol], d2 = vstat[2 * vol + 1];
     const unsigned K = (unsigned)g.k;
-    const int Rm = g.R - 1;
     const unsigned hbase = (unsigned)__cvta_generic_to_shared(hist) + threadIdx.x * 4;
-    const unsigned tbase = (unsigned)__cvta_generic_to_shared(ring32) + warp * g.R * kRingXW + lane;
+    const unsigned tbase = (unsigned)__cvta_generic_to_shared(ring32) + warp * g.R * kRingXB + lane * 2;
 
     // Flat-region shortcut: when all 2*wy+2 ring rows a step touches hold one single value
     // (background, saturated tissue) the histogram cannot change, so the step is skipped and
@@ -337,21 +394,49 @@ xcorr_ring_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
         const int yy = min(max(y0 - g.wy, 0), g.ny - 1);
         ref_word = (unsigned)__ldg(bv + ((size_t)zz * g.ny + yy) * g.nx + xx) * 0x01010101u;
     }
+    RingLoader rl;
+    rl.init(bv, g, x0, z0, ref_word);
     int flat_rows = 0;   // block-uniform: number of most recent consecutive flat rows
-    for (int yr = y0 - g.wy; yr <= y0 + g.wy; yr++) {
-        const bool f = ring_load_row(ring32, bv, g, x0, z0, yr, ref_word);
-        flat_rows = __syncthreads_and(f) ? flat_rows + 1 : 0;
+    const int R = g.R;
+    int sy = ring_slot(y0, R);          // ring slot of row y (block-uniform, kept incrementally)
+    // preload rows y0-wy .. y0+wy, four rows of loads in flight at a time
+    {
+        int sl = ring_slot(y0 - g.wy, R);
+        for (int yr0 = y0 - g.wy; yr0 <= y0 + g.wy; yr0 += 4) {
+            unsigned v[4][2];
+#pragma unroll
+            for (int q = 0; q < 4; q++) rl.fetch(yr0 + q <= y0 + g.wy ? yr0 + q : -1, v[q]);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (yr0 + q > y0 + g.wy) break;   // block-uniform
+                const bool f = rl.commit(ring32, yr0 + q, sl, v[q]);
+                sl = slot_add(sl, 1, R);
+                flat_rows = __syncthreads_and(f) ? flat_rows + 1 : 0;
+            }
+        }
     }
+    // software prefetch: rows y+1+wy and y+2+wy are already in registers when step y starts
+    unsigned pfa[2], pfb[2];
+    rl.fetch(y0 + 1 + g.wy, pfa);
+    rl.fetch(y0 + 2 + g.wy, pfb);
     for (int w = 0; w < g.nw; w++) hist[w * kXcThreads + threadIdx.x] = 0u;
     __syncthreads();
 
-    if (active) {  // full ball around (x, y0, z)
-        for (int e = 0; e <= g.wy; e++)
-            for (int c = g.gstart[e]; c < g.gend[e]; c++) {
-                const unsigned co = cols[c];
-                for (int dy = -e; dy <= e; dy++)
-                    hist_bump(hbase, lds_u8(tbase + ((y0 + dy) & Rm) * kRingXW + co), 1);
-            }
+    if (active) {
+        if (flat_rows >= 2 * g.wy + 1) {
+            // the whole neighbourhood of the first voxel is one value: every column adds its
+            // 2e+1 voxels to one bin (ref, or the dummy bin for columns outside the image)
+            for (int e = 0; e <= g.wy; e++)
+                for (int c = gs[e]; c < ge[e]; c++)
+                    hist_bump(hbase, lds_u16(tbase + sy * kRingXB + cols[c]), 2 * e + 1);
+        } else {  // full ball around (x, y0, z)
+            for (int e = 0; e <= g.wy; e++)
+                for (int c = gs[e]; c < ge[e]; c++) {
+                    const unsigned co = cols[c];
+                    for (int dy = -e; dy <= e; dy++)
+                        hist_bump(hbase, lds_u16(tbase + slot_add(sy, dy, R) * kRingXB + co), 1);
+                }
+        }
     }
     float res = 0.0f;
     bool changed = true;   // block-uniform: did the last slide touch the histograms?
@@ -381,21 +466,24 @@ xcorr_ring_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
         if (active) ov[((size_t)z * g.ny + y) * g.nx + x] = res;
         if (y + 1 >= y1) break;
         // the slot of row y+1+wy last held row y+1+wy-R < y-1-wy: nobody reads it any more
-        const bool f = ring_load_row(ring32, bv, g, x0, z0, y + 1 + g.wy, ref_word);
+        const bool f = rl.commit(ring32, y + 1 + g.wy, slot_add(sy, 1 + g.wy, R), pfa);
+        pfa[0] = pfb[0]; pfa[1] = pfb[1];
+        rl.fetch(y + 3 + g.wy, pfb);
         flat_rows = __syncthreads_and(f) ? flat_rows + 1 : 0;
         changed = flat_rows < 2 * g.wy + 2;   // rows y-wy .. y+1+wy
         if (active && changed) {
             for (int e = 0; e <= g.wy; e++) {
-                const unsigned pin = tbase + ((y + 1 + e) & Rm) * kRingXW;
-                const unsigned pout = tbase + ((y - e) & Rm) * kRingXW;
-                int c = g.gstart[e];
-                const int cend = g.gend[e];
+                const unsigned pin = tbase + slot_add(sy, 1 + e, R) * kRingXB;
+                const unsigned pout = tbase + slot_add(sy, -e, R) * kRingXB;
+                int c = gs[e];
+                const int cend = ge[e];
+#pragma unroll 1
                 for (; c + 4 <= cend; c += 4) {
                     const uint4 co = *reinterpret_cast<const uint4*>(cols + c);   // gstart is 4-aligned
-                    const unsigned i0 = lds_u8(pin + co.x), o0 = lds_u8(pout + co.x);
-                    const unsigned i1 = lds_u8(pin + co.y), o1 = lds_u8(pout + co.y);
-                    const unsigned i2 = lds_u8(pin + co.z), o2 = lds_u8(pout + co.z);
-                    const unsigned i3 = lds_u8(pin + co.w), o3 = lds_u8(pout + co.w);
+                    const unsigned i0 = lds_u16(pin + co.x), o0 = lds_u16(pout + co.x);
+                    const unsigned i1 = lds_u16(pin + co.y), o1 = lds_u16(pout + co.y);
+                    const unsigned i2 = lds_u16(pin + co.z), o2 = lds_u16(pout + co.z);
+                    const unsigned i3 = lds_u16(pin + co.w), o3 = lds_u16(pout + co.w);
                     hist_move(hbase, i0, o0);
                     hist_move(hbase, i1, o1);
                     hist_move(hbase, i2, o2);
@@ -403,11 +491,12 @@ xcorr_ring_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
                 }
                 for (; c < cend; c++) {
                     const unsigned co = cols[c];
-                    const unsigned i0 = lds_u8(pin + co), o0 = lds_u8(pout + co);
+                    const unsigned i0 = lds_u16(pin + co), o0 = lds_u16(pout + co);
                     hist_move(hbase, i0, o0);
                 }
             }
         }
+        sy = slot_add(sy, 1, R);
     }
 }
 
@@ -508,14 +597,13 @@ extern "C" int32_t vx_cross_correlation(vx_ctx ctx, vx_img a, vx_img b, vx_img r
     // give the batch at least a few waves of CTAs
     const int seg = A->ny <= 64 ? A->ny : 64;
     const int nseg = (A->ny + seg - 1) / seg;
-    int ringR = 4;
-    while (ringR < 2 * wy + 3) ringR <<= 1;
+    const int ringR = 2 * wy + 3;   // rows y-wy .. y+1+wy of a step plus the one being written
     const int P = kXcWarps + 2 * wz;
     int rc = VX_OK;
     // ring offsets, sorted by y half-extent, every group padded to start 4-aligned
     std::vector<unsigned> ring_cols;
     XrGeo g;
-    bool ring_ok = wx <= 8 && wy <= 16;
+    bool ring_ok = wx <= 8 && wy <= 16 && P * (kRingXW / 4) <= 2 * kXcThreads;
     if (ring_ok) {
         for (int e = 0; e <= wy; e++) {
             while (ring_cols.size() & 3) ring_cols.push_back(0);   // alignment filler, never read
@@ -524,14 +612,14 @@ extern "C" int32_t vx_cross_correlation(vx_ctx ctx, vx_img a, vx_img b, vx_img r
             for (unsigned cw : cols) {
                 int dx = (int)(signed char)(cw & 0xffu), dz = (int)(signed char)((cw >> 8) & 0xffu), ey = (int)(cw >> 16);
                 if (ey != e) continue;
-                ring_cols.push_back((unsigned)(((wz + dz) * ringR) * kRingXW + 8 + dx));
+                ring_cols.push_back((unsigned)(((wz + dz) * ringR) * kRingXB + 2 * (8 + dx)));
                 cnt++;
             }
             g.gend[e] = g.gstart[e] + cnt;
         }
     }
     const size_t smem_ring = sizeof(unsigned) * ((size_t)nw * kXcThreads + ((2 * nw + 3) & ~3) + ((ring_cols.size() + 3) & ~(size_t)3)) +
-                             (size_t)P * ringR * kRingXW;
+                             (size_t)P * ringR * kRingXB;
     if (ring_ok && smem_ring <= 160 * 1024) {
         g.nx = A->nx; g.ny = A->ny; g.nz = A->nz; g.k = k;
         g.ncols = (int)ring_cols.size();
