@@ -1,0 +1,69 @@
+"""Turn the ncu outputs of scripts/gpu_profile.sh into the small text/JSON summaries committed
+under profiles/ (the .ncu-rep files themselves stay in gpurun_out/, which is scratch).
+
+    python scripts/summarize_ncu.py launches gpurun_out/launches.csv profiles/r01_launches_bench_b8.json
+    python scripts/summarize_ncu.py full gpurun_out/xcorr_full.ncu-rep profiles/r01_xcorr_ncu_full.json
+"""
+import csv
+import json
+import subprocess
+import sys
+from collections import defaultdict
+
+KEEP = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
+    "launch__shared_mem_per_block_static", "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers",
+    "launch__occupancy_limit_shared_mem", "smsp__inst_executed.sum", "sm__cycles_elapsed.avg",
+]
+
+
+def launches(src, dst):
+    per = defaultdict(lambda: [0, 0.0])
+    n = 0
+    with open(src, newline="") as f:
+        rows = [r for r in csv.reader(l for l in f if l.startswith('"'))]
+    hdr = rows[0]
+    ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    for r in rows[1:]:
+        name = r[ik].split("(")[0]
+        v = float(r[iv].replace(",", ""))
+        v = v / 1e3 if r[iu] in ("ns", "nsecond") else v * 1e3 if r[iu] in ("ms", "msecond") else v  # -> us
+        per[name][0] += 1
+        per[name][1] += v
+        n += 1
+    tot = sum(v[1] for v in per.values())
+    out = {"source": src, "launches": n, "total_us": round(tot, 1),
+           "note": "ncu --metrics gpu__time_duration.sum --clock-control none: per-launch times are cold-cache and "
+                   "serialised; compare SHARES with bench.py's CUDA-event shares, not absolutes",
+           "kernels": {k: {"launches": c, "total_us": round(t, 1), "share": round(t / tot, 4)}
+                       for k, (c, t) in sorted(per.items(), key=lambda kv: -kv[1][1])}}
+    json.dump(out, open(dst, "w"), indent=1)
+    for k, v in list(out["kernels"].items())[:12]:
+        print(f"{k:32s} {v['launches']:5d} {v['total_us']:12.1f} us {100 * v['share']:6.2f} %")
+
+
+def full(src, dst):
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    out = {"source": src, "captures": []}
+    for vals in rows[2:]:
+        rec = {"kernel": vals[hdr.index("Kernel Name")]}
+        for i, h in enumerate(hdr):
+            if h in KEEP:
+                rec[h] = {"value": vals[i], "unit": units[i]}
+        out["captures"].append(rec)
+    json.dump(out, open(dst, "w"), indent=1)
+    print(json.dumps(out["captures"][0], indent=1)[:3000])
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])

@@ -49,6 +49,7 @@ struct Ctx {
     uint64_t id = 0;
     cudaStream_t streams[kMaxStreams] = {};
     std::atomic<int> next_stream{0};
+    std::vector<int> free_streams;  // indices handed back by exited threads (guarded by mu)
     std::mutex mu;  // guards pools and accounting below
     std::vector<cudaEvent_t> event_pool;
     std::vector<cudaEvent_t> timing_pool;  // timing-enabled events for the profiler

@@ -75,20 +75,40 @@ Ctx* get_ctx(vx_ctx h) {
 }
 
 // ---- streams ------------------------------------------------------------------
+// A host thread keeps one stream index per context for its whole life.  When the thread
+// exits (worker threads of a scheduler come and go) its indices return to the context's
+// free list, so the next new thread inherits the stream AND the blocks cached on it;
+// without this every short-lived thread would start on a cold allocator.
+struct ThreadStreams {
+    std::vector<std::pair<Ctx*, int>> mine;
+    ~ThreadStreams() {
+        for (auto& p : mine) {
+            std::lock_guard<std::mutex> lk(p.first->mu);
+            p.first->free_streams.push_back(p.second);
+        }
+    }
+};
+
 int my_stream_index(Ctx* c) {
-    static thread_local std::vector<std::pair<uint64_t, int>> mine;
-    for (auto& p : mine)
-        if (p.first == c->id) return p.second;
-    int idx = c->next_stream.fetch_add(1) % kMaxStreams;
+    static thread_local ThreadStreams ts;
+    for (auto& p : ts.mine)
+        if (p.first == c) return p.second;
+    int idx;
     {
         std::lock_guard<std::mutex> lk(c->mu);
+        if (!c->free_streams.empty()) {
+            idx = c->free_streams.back();
+            c->free_streams.pop_back();
+        } else {
+            idx = c->next_stream.fetch_add(1) % kMaxStreams;
+        }
         if (!c->streams[idx]) {
             cudaStream_t st = nullptr;
             if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return 0;
             c->streams[idx] = st;
         }
     }
-    mine.emplace_back(c->id, idx);
+    ts.mine.emplace_back(c, idx);
     return idx;
 }
 
