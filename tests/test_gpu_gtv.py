@@ -55,3 +55,30 @@ def test_maze_reachability_2d(ctx, oracle):
         assert np.array_equal(it.globals["fromStart"].numpy()[0, 0], want)
         assert it.globals["reachesExit"].v[0] == 1.0     # a perfect maze connects start and exit
         assert it.globals["dead"].numpy().sum() == 0
+
+
+def test_specs_from_files(ctx, oracle, tmp_path):
+    """examples/*.imgql run unchanged from disk: PNG and NIfTI in, PNG and NIfTI out."""
+    import os
+    import shutil
+    from gtv_ref import gtv_oracle
+    from voxlogica_b200 import io as vio
+    from voxlogica_b200.imgql import run_file
+    from voxlogica_b200.synth import brats_like, maze
+    ex = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples")
+    for name in ("maze.imgql", "gtv.imgql"):
+        shutil.copy(os.path.join(ex, name), tmp_path / name)
+    img = maze(20, seed=3)
+    vio.write_png(str(tmp_path / "maze.png"), img)
+    it = run_file(ctx, str(tmp_path / "maze.imgql"), conn=6)
+    assert it.printed["solvable"][0] == 1.0
+    path = (img.sum(axis=2) > 0).astype(np.uint8)
+    start = np.zeros_like(path); start[1, 1] = 1
+    want = oracle.through(start, path, 6)
+    assert np.array_equal(vio.read_png(str(tmp_path / "fromStart.png")), want * 255)
+    vol = brats_like(seed=11, shape=(40, 64, 72))
+    vio.write_nifti(str(tmp_path / "flair.nii.gz"), vol)
+    it = run_file(ctx, str(tmp_path / "gtv.imgql"))
+    ref = gtv_oracle(oracle, vol)
+    got, sp = vio.read_nifti(str(tmp_path / "gtv.nii.gz"))
+    assert np.array_equal(got.astype(np.uint8), ref["gtv"]) and it.printed["gtvVolume"][0] == ref["gtv"].sum()

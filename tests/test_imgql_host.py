@@ -69,3 +69,40 @@ def test_synthetic_generators():
     corridors = (m.sum(axis=2) > 0)
     assert ndi.label(corridors)[1] == 1                 # a perfect maze is one 4-connected component
     assert corridors.sum() == 2 * 64 - 1                # spanning tree: n cells + n-1 passages
+
+
+def test_nifti_and_png_roundtrip(tmp_path):
+    from voxlogica_b200 import io as vio
+    rng = np.random.default_rng(3)
+    vol = rng.random((5, 7, 9), dtype=np.float32)
+    for name in ("v.nii", "v.nii.gz"):
+        p = str(tmp_path / name)
+        vio.write_nifti(p, vol, (0.5, 1.25, 3.0))
+        back, sp = vio.read_nifti(p)
+        assert np.array_equal(back, vol) and sp == (0.5, 1.25, 3.0)
+    m = (vol > 0.5).astype(np.uint8)
+    vio.write_nifti(str(tmp_path / "m.nii.gz"), m)
+    back, sp = vio.read_nifti(str(tmp_path / "m.nii.gz"))
+    assert np.array_equal(back, m.astype(np.float32)) and sp == (1.0, 1.0, 1.0)
+    # big-endian file with a scale slope: byte-swap the little-endian header fields by hand
+    import struct
+    hdr = bytearray(open(str(tmp_path / "v.nii"), "rb").read()[:352])
+    be = bytearray(352)
+    struct.pack_into(">i", be, 0, 348)
+    struct.pack_into(">8h", be, 40, *struct.unpack_from("<8h", hdr, 40))
+    struct.pack_into(">hh", be, 70, 4, 16)
+    struct.pack_into(">8f", be, 76, *struct.unpack_from("<8f", hdr, 76))
+    struct.pack_into(">f", be, 108, 352.0)
+    struct.pack_into(">ff", be, 112, 2.0, 1.0)
+    be[344:348] = b"n+1\0"
+    ints = rng.integers(-100, 100, size=vol.shape).astype(">i2")
+    with open(str(tmp_path / "be.nii"), "wb") as f:
+        f.write(bytes(be)); f.write(ints.tobytes())
+    back, _ = vio.read_nifti(str(tmp_path / "be.nii"))
+    assert np.array_equal(back, ints.astype(np.float32) * 2 + 1)
+    from voxlogica_b200.synth import maze
+    img = maze(8, seed=1)
+    vio.write_png(str(tmp_path / "maze.png"), img)
+    assert np.array_equal(vio.read_png(str(tmp_path / "maze.png")), img)
+    ch = vio.load_image(str(tmp_path / "maze.png"))
+    assert set(ch) == {"red", "green", "blue"} and ch["red"][0].shape == (1,) + img.shape[:2]

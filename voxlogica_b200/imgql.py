@@ -226,6 +226,18 @@ class Number:
         return f"Number({self.v.tolist()})"
 
 
+class Loaded:
+    """Result of ``load``: the channels of one image file, each an HBM-resident f32 Image."""
+
+    def __init__(self, channels: Dict[str, Image]):
+        self.channels = channels
+
+    def channel(self, name: str) -> Image:
+        if name in self.channels:
+            return self.channels[name]
+        raise KeyError(f"ImgQL: image has no {name!r} channel (has {sorted(self.channels)})")
+
+
 def _is_img(v):
     return isinstance(v, Image)
 
@@ -234,6 +246,7 @@ class Interpreter:
     def __init__(self, ctx: Context, loader: Optional[Callable[[str], Image]] = None, conn: int = 26):
         self.ctx = ctx
         self.loader = loader
+        self.saver = None                    # optional callable(path, Image) run by `save`
         self.conn = conn                     # adjacency of near/through
         self.globals: Dict[str, object] = {}
         self.functions: Dict[str, Tuple[List[str], object]] = {}
@@ -259,7 +272,7 @@ class Interpreter:
                 img = self.loader(st[2])
                 self.globals[st[1]] = img
                 if self.base is None:
-                    self.base = img
+                    self.base = next(iter(img.channels.values())) if isinstance(img, Loaded) else img
             elif kind == "let":
                 _, name, params, body = st
                 if params is None:
@@ -268,6 +281,8 @@ class Interpreter:
                     self.functions[name] = (params, body)
             elif kind == "save":
                 self.saved[st[1]] = self.eval(st[2], {})
+                if self.saver is not None:
+                    self.saver(st[1], self.saved[st[1]])
             elif kind == "print":
                 v = self.eval(st[2], {})
                 self.printed[st[1]] = v.v.copy() if isinstance(v, Number) else v
@@ -327,7 +342,11 @@ class Interpreter:
         if fn == "neg":
             return Number(-a[0].v) if isinstance(a[0], Number) else c.arith_scalar(a[0], "r-", 0.0)
         table = {
-            "intensity": lambda x: x,     # single-channel images: the identity
+            "intensity": self._intensity,
+            "red": lambda x: x.channel("red"),
+            "green": lambda x: x.channel("green"),
+            "blue": lambda x: x.channel("blue"),
+            "alpha": lambda x: x.channel("alpha"),
             "border": lambda: c.border(self._like()),
             "tt": lambda: c.tt(self._like()),
             "ff": lambda: c.ff(self._like()),
@@ -353,6 +372,17 @@ class Interpreter:
         if fn not in table:
             raise NameError(f"ImgQL: unknown operator {fn!r}")
         return table[fn](*a)
+
+    def _intensity(self, x):
+        """single-channel: the identity; RGB: Rec.709 luma 0.2126 r + 0.7152 g + 0.0722 b [RECALL]"""
+        if not isinstance(x, Loaded):
+            return x
+        if "intensity" in x.channels:
+            return x.channels["intensity"]
+        c = self.ctx
+        r, g, b = (x.channel(n) for n in ("red", "green", "blue"))
+        return c.arith(c.arith(c.arith_scalar(r, "*", 0.2126), "+", c.arith_scalar(g, "*", 0.7152)), "+",
+                       c.arith_scalar(b, "*", 0.0722))
 
     def _infix(self, op, l, r):
         c = self.ctx
@@ -389,6 +419,34 @@ def run_spec(ctx: Context, src: str, images: Dict[str, Image], conn: int = 26) -
     """Run an ImgQL spec whose `load` statements name entries of ``images``."""
     it = Interpreter(ctx, loader=lambda name: images[name], conn=conn)
     return it.run(src)
+
+
+def run_file(ctx: Context, path: str, conn: int = 26) -> Interpreter:
+    """Run an .imgql file: `load` reads NIfTI / PNG files (relative to the spec's directory) into
+    HBM, `save` writes the result next to it (boolean -> u8 mask, numbers -> f32)."""
+    import os
+
+    from . import io as vio
+
+    base = os.path.dirname(os.path.abspath(path))
+    spacing = {}
+
+    def loader(name):
+        chans = vio.load_image(os.path.join(base, name))
+        out = {}
+        for k, (arr, sp) in chans.items():
+            out[k] = ctx.upload(arr, spacing=sp)
+            spacing["sp"] = sp
+        return Loaded(out)
+
+    def saver(name, val):
+        if isinstance(val, Image):
+            vio.save_image(os.path.join(base, name), val.numpy()[0], spacing.get("sp", (1.0, 1.0, 1.0)))
+
+    it = Interpreter(ctx, loader=loader, conn=conn)
+    it.saver = saver
+    with open(path) as f:
+        return it.run(f.read())
 
 
 def run_gtv(ctx: Context, flair: Image, conn: int = 26) -> Dict[str, object]:
