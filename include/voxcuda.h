@@ -119,6 +119,19 @@ VX_API int32_t vx_release(vx_img img);
 /* View of volumes [first, first+count) of a batch as a new batch (copies). */
 VX_API int32_t vx_batch_slice(vx_ctx ctx, vx_img img, int32_t first, int32_t count, vx_img* out);
 
+/* Slab helpers (one oversized volume split along z across GPUs):
+ * planes [z0, z0+nz) of every volume as a new image; the parts stacked along z. */
+VX_API int32_t vx_crop_z(vx_ctx ctx, vx_img img, int32_t z0, int32_t nz, vx_img* out);
+VX_API int32_t vx_concat_z(vx_ctx ctx, const vx_img* parts, int32_t n_parts, vx_img* out);
+/* Copy an image to another context of the same process (another GPU; NVLink peer copy).
+ * Keep the source referenced until vx_sync(dst_ctx). */
+VX_API int32_t vx_transfer(vx_ctx dst_ctx, vx_img img, vx_img* out);
+/* Interop with other CUDA code of the process (e.g. an NCCL halo exchange): the raw device
+ * pointer of an image, valid while a reference is held, and the calling thread's CUDA stream
+ * (as a cudaStream_t).  vx_upload / vx_download also accept DEVICE pointers as `host`. */
+VX_API int32_t vx_device_ptr(vx_ctx ctx, vx_img img, void** ptr);
+VX_API int32_t vx_stream_handle(vx_ctx ctx, void** stream);
+
 /* Pinned host staging memory for the end-to-end path. */
 VX_API int32_t vx_host_alloc(size_t bytes, void** out);
 VX_API int32_t vx_host_free(void* p);
@@ -236,6 +249,14 @@ VX_API int32_t vx_dist_gt(vx_ctx ctx, vx_img a, float r, vx_img* out);
  * (0 when either histogram has zero variance).  m, M: one value per volume. */
 VX_API int32_t vx_cross_correlation(vx_ctx ctx, vx_img a, vx_img b, vx_img region, float rho,
                                     const double* m, const double* M, int32_t k, vx_img* out);
+
+/* The two halves of vx_cross_correlation, for callers that own only a slab of the volume:
+ * the k-bin histogram of b over region (h2: nb*k counters, accumulated on the host across
+ * slabs by the caller) and the correlation map against a given h2. */
+VX_API int32_t vx_region_histogram(vx_ctx ctx, vx_img b, vx_img region, const double* m,
+                                   const double* M, int32_t k, uint64_t* h2);
+VX_API int32_t vx_cross_correlation_h2(vx_ctx ctx, vx_img a, const uint64_t* h2, float rho,
+                                       const double* m, const double* M, int32_t k, vx_img* out);
 
 /* --------------------------------------------- A7/A9/A11 reductions and normalisation
  * Scalar results: `out` points to nb doubles (one per volume of the batch). */

@@ -179,6 +179,14 @@ def cross_correlation(rho, a, b, region, m, M, k, spacing=None, textbook=False):
     return out
 
 
+def cross_correlation_h2(rho, a, h2, m, M, k, spacing=None):
+    a = _f32(a); h2 = np.ascontiguousarray(h2, dtype=np.uint64)
+    nx, ny, nz = _dims(a); out = np.empty_like(a)
+    lib().or_cross_correlation_h2(_p(a), _p(h2), C.c_float(rho), C.c_double(m), C.c_double(M), int(k),
+                                  _p(out), nx, ny, nz, _sp(spacing))
+    return out
+
+
 # ---- reductions ------------------------------------------------------------------------
 def volume(a):
     a = _u8(a); return lib().or_volume(_p(a), C.c_size_t(a.size))

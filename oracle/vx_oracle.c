@@ -416,16 +416,8 @@ static int in_ball(int dx, int dy, int dz, const float sp[3], double r2) {
 /* textbook = 0: exact-integer form  (k*P - n1*n2) / sqrt((k*S11 - n1^2)(k*S22 - n2^2))
  * textbook = 1: sum((h1-mean1)(h2-mean2)) / sqrt(sum((h1-mean1)^2) sum((h2-mean2)^2))
  * The two agree to rounding; the first is the arithmetic contract of the CUDA path. */
-OR_API void or_cross_correlation(const float* a, const float* b, const uint8_t* region, float rho,
-                                 double m, double M, int k, float* out, int nx, int ny, int nz,
-                                 const float sp[3], int textbook) {
-    size_t n = nvox(nx, ny, nz);
-    long long* h2 = (long long*)calloc(k, sizeof(long long));
-    for (size_t i = 0; i < n; i++)
-        if (region[i]) {
-            int bi = bin_of(b[i], m, M, k);
-            if (bi >= 0) h2[bi]++;
-        }
+static void xcorr_core(const float* a, const long long* h2, float rho, double m, double M, int k,
+                       float* out, int nx, int ny, int nz, const float sp[3], int textbook) {
     long long n2 = 0;
     unsigned long long s22 = 0;
     for (int i = 0; i < k; i++) {
@@ -498,6 +490,29 @@ OR_API void or_cross_correlation(const float* a, const float* b, const uint8_t* 
         free(h1);
     }
     free(off);
+}
+
+OR_API void or_cross_correlation(const float* a, const float* b, const uint8_t* region, float rho,
+                                 double m, double M, int k, float* out, int nx, int ny, int nz,
+                                 const float sp[3], int textbook) {
+    size_t n = nvox(nx, ny, nz);
+    long long* h2 = (long long*)calloc(k, sizeof(long long));
+    for (size_t i = 0; i < n; i++)
+        if (region[i]) {
+            int bi = bin_of(b[i], m, M, k);
+            if (bi >= 0) h2[bi]++;
+        }
+    xcorr_core(a, h2, rho, m, M, k, out, nx, ny, nz, sp, textbook);
+    free(h2);
+}
+
+/* The same with the region histogram h2 given by the caller (a slab of a larger volume whose
+ * region histogram was accumulated over all slabs). */
+OR_API void or_cross_correlation_h2(const float* a, const unsigned long long* h2u, float rho, double m,
+                                    double M, int k, float* out, int nx, int ny, int nz, const float sp[3]) {
+    long long* h2 = (long long*)calloc(k, sizeof(long long));
+    for (int i = 0; i < k; i++) h2[i] = (long long)h2u[i];
+    xcorr_core(a, h2, rho, m, M, k, out, nx, ny, nz, sp, 0);
     free(h2);
 }
 

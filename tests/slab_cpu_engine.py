@@ -1,0 +1,52 @@
+"""Oracle-backed local engine for the CPU (gloo) tests of voxlogica_b200/slab.py.  TEST
+INFRASTRUCTURE: it lets world_size-2 gloo runs exercise the slab host logic (partition, halo
+exchange, boundary-label merge) without a GPU.  Arrays are numpy [1][nz][ny][nx]."""
+import numpy as np
+import torch
+
+import oracle as orc
+
+
+class OracleEngine:
+    def __init__(self, spacing=(1.0, 1.0, 1.0)):
+        self.sp = tuple(spacing)
+
+    def nz(self, x): return x.shape[1]
+    def crop_z(self, x, z0, n): return np.ascontiguousarray(x[:, z0:z0 + n])
+    def concat_z(self, parts): return np.ascontiguousarray(np.concatenate(list(parts), axis=1))
+
+    def to_tensor(self, x):
+        a = x[0]
+        if a.dtype == np.uint32:
+            a = a.view(np.int32)
+        return torch.from_numpy(np.ascontiguousarray(a))
+
+    def from_tensor(self, t, like):
+        a = t.numpy()
+        if a.dtype == np.int32:
+            a = a.view(np.uint32)
+        return np.ascontiguousarray(a[None])
+
+    def zeros_u8(self, like): return np.zeros(like.shape, np.uint8)
+    def not_(self, a): return orc.not_(a[0])[None]
+    def and_(self, a, b): return orc.and_(a[0], b[0])[None]
+    def or_(self, a, b): return orc.or_(a[0], b[0])[None]
+    def cmp_scalar(self, a, op, s): return orc.cmp_scalar(a[0], op, s)[None]
+    def near(self, a, conn): return orc.near(a[0], conn)[None]
+    def interior(self, a, conn): return orc.interior(a[0], conn)[None]
+    def through(self, a, b, conn): return orc.through(a[0], b[0], conn)[None]
+    def components(self, a, conn): return orc.components(a[0], conn).astype(np.uint32)[None]
+    def dist(self, op, r, a): return orc.dist_cmp(a[0], op, r, self.sp)[None]
+
+    def region_histogram(self, b, region, m, M, k):
+        v = b[0][region[0] != 0].astype(np.float64)
+        v = v[(v >= m) & (v < M)]
+        idx = np.minimum(((v - m) * k / (M - m)).astype(np.int64), k - 1)
+        return np.bincount(idx, minlength=k).astype(np.uint64)
+
+    def cross_correlation_h2(self, rho, a, h2, m, M, k):
+        return orc.cross_correlation_h2(rho, a[0], np.asarray(h2, dtype=np.uint64), m, M, k, self.sp)[None]
+
+    def volume(self, a): return float(orc.volume(a[0]))
+    def min(self, a): return float(orc.min_(a[0]))
+    def max(self, a): return float(orc.max_(a[0]))

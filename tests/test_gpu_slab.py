@@ -1,0 +1,159 @@
+"""Slab decomposition on the GPU.
+
+(1) single-GPU: two "ranks" as two host threads of one process, each with its own libvoxcuda
+    stream, joined by an in-process communicator -- the whole CudaEngine path (zero-copy tensor
+    views, crop/concat, halo planes, boundary-label merge) against the single-image result;
+(2) multi-GPU: scripts/slab_gpu.py under torchrun with NCCL when the box has >= 2 GPUs.
+"""
+import os
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class ThreadComm:
+    """SlabComm look-alike for `world` threads of one process (tensors stay on the device)."""
+
+    class Shared:
+        def __init__(self, world):
+            self.world = world
+            self.barrier = threading.Barrier(world)
+            self.slots = {}
+            self.lock = threading.Lock()
+
+    def __init__(self, shared, rank):
+        self.s, self.rank, self.world = shared, rank, shared.world
+
+    def _swap(self, key, value):
+        with self.s.lock:
+            self.s.slots[(key, self.rank)] = value
+        self.s.barrier.wait()
+        vals = [self.s.slots[(key, r)] for r in range(self.world)]
+        self.s.barrier.wait()
+        return vals
+
+    def exchange_planes(self, to_lower, to_upper):
+        import torch
+        torch.cuda.synchronize()
+        vals = self._swap("x", (to_lower.clone(), to_upper.clone()))
+        torch.cuda.synchronize()
+        lo = vals[self.rank - 1][1] if self.rank > 0 else None
+        hi = vals[self.rank + 1][0] if self.rank + 1 < self.world else None
+        return lo, hi
+
+    def all_gather_rows(self, t):
+        import torch
+        torch.cuda.synchronize()
+        return torch.cat(self._swap("g", t.clone()), dim=0)
+
+    def all_reduce(self, values, op, device):
+        arr = np.array(self._swap("r", list(values)), dtype=np.float64)
+        return {"sum": arr.sum(0), "min": arr.min(0), "max": arr.max(0)}[op]
+
+    def all_reduce_i64(self, arr, device):
+        return np.sum(np.array(self._swap("i", np.asarray(arr, dtype=np.int64))), axis=0)
+
+
+def test_slab_helpers_single_gpu(ctx):
+    rng = np.random.default_rng(1)
+    v = rng.random((2, 9, 6, 20), dtype=np.float32)
+    img = ctx.upload(v)
+    assert np.array_equal(ctx.crop_z(img, 2, 4).numpy(), v[:, 2:6])
+    parts = [ctx.crop_z(img, 0, 3), ctx.crop_z(img, 3, 1), ctx.crop_z(img, 4, 5)]
+    assert np.array_equal(ctx.concat_z(parts).numpy(), v)
+    t = ctx.as_tensor(img)
+    ctx.sync()
+    assert tuple(t.shape) == v.shape and np.array_equal(t.cpu().numpy(), v)
+    back = ctx.from_tensor(t * 2.0)
+    assert np.array_equal(back.numpy(), v * 2.0)
+    m = (rng.random(v.shape) < 0.5).astype(np.uint8)
+    mi = ctx.upload(m)
+    h2 = ctx.region_histogram(img, mi, 0.0, 1.0, 16)
+    want = np.stack([np.bincount(np.minimum((v[b][m[b] != 0].astype(np.float64) * 16).astype(int), 15),
+                                 minlength=16) for b in range(2)])
+    assert np.array_equal(h2, want.astype(np.uint64))
+    a = ctx.cross_correlation(2.0, img, img, mi, 0.0, 1.0, 16).numpy()
+    b = ctx.cross_correlation_h2(2.0, img, h2, 0.0, 1.0, 16).numpy()
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_ops_two_threads_one_gpu(ctx, world):
+    from voxlogica_b200.slab import CudaEngine, SlabOps, slab_bounds
+    rng = np.random.default_rng(42)
+    shape = (21, 40, 64)
+    sp = (1.0, 1.0, 1.5)
+    b = (rng.random(shape) < 0.2).astype(np.uint8)
+    for z in range(shape[0]):
+        b[z, 3 + (z % 3), 2:60] |= np.uint8(z % 2 == 0)
+        b[z, 4, 2 if (z // 2) % 2 == 0 else 59] = 1
+    a = np.zeros(shape, np.uint8); a[0, 3, 2] = 1
+    sparse = (rng.random(shape) < 0.004).astype(np.uint8)
+    f = rng.random(shape, dtype=np.float32)
+    Bi, Ai, Si, Fi = (ctx.upload(x, spacing=sp) for x in (b, a, sparse, f))
+    want = {}
+    for conn in (6, 26):
+        want[f"near{conn}"] = ctx.near(Bi, conn).numpy()[0]
+        want[f"interior{conn}"] = ctx.interior(Bi, conn).numpy()[0]
+        want[f"through{conn}"] = ctx.through(Ai, Bi, conn).numpy()[0]
+    for r in (2.5, 4.0):
+        want[f"distlt{r}"] = ctx.distlt(r, Si).numpy()[0]
+        want[f"flt{r}"] = ctx.distlt(r, ctx.distgeq(r, ctx.not_(ctx.near(Si)))).numpy()[0]
+    want["xcorr"] = ctx.cross_correlation(3.0, Fi, Fi, Bi, 0.0, 1.0, 16).numpy()[0]
+    assert want["through6"].sum() > a.sum() and want["through6"][shape[0] - 1].any()   # crosses every slab
+    shared = ThreadComm.Shared(world)
+    errors, results = [], {}
+
+    def run(rank):
+        try:
+            ops = SlabOps(CudaEngine(ctx), ThreadComm(shared, rank))
+            up = lambda arr, s: ctx.upload(arr, spacing=s)
+            A, B, S, F = (ops.scatter_from_global(up, x, sp) for x in (a, b, sparse, f))
+            got = {}
+            for conn in (6, 26):
+                got[f"near{conn}"] = ops.near(B, conn)
+                got[f"interior{conn}"] = ops.interior(B, conn)
+                got[f"through{conn}"] = ops.through(A, B, conn)
+            for r in (2.5, 4.0):
+                got[f"distlt{r}"] = ops.distlt(r, S)
+                got[f"flt{r}"] = ops.flt(r, ops.near(S))
+            got["xcorr"] = ops.cross_correlation(3.0, F, F, B, 0.0, 1.0, 16)
+            vol = ops.volume(B)
+            z0, z1 = slab_bounds(shape[0], world)[rank]
+            for k, sl in got.items():
+                g = sl.data.numpy()[0]
+                w = want[k][z0:z1]
+                if not np.array_equal(g.view(np.uint32) if g.dtype == np.float32 else g,
+                                      w.view(np.uint32) if w.dtype == np.float32 else w):
+                    errors.append((rank, k))
+            if vol != float(b.sum()):
+                errors.append((rank, "volume"))
+            results[rank] = True
+        except Exception as ex:  # pragma: no cover
+            errors.append((rank, repr(ex)))
+            shared.barrier.abort()
+
+    ths = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in ths]
+    [t.join(timeout=300) for t in ths]
+    assert not errors, errors
+    assert len(results) == world
+
+
+def test_slab_multi_gpu_nccl():
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 4)}",
+           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "scripts", "slab_gpu.py"),
+           "--size", "96", "--check"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "SLAB CHECK OK" in out.stdout

@@ -1,0 +1,100 @@
+"""world_size-2 (and 3) gloo runs of the slab decomposition (voxlogica_b200/slab.py) on CPU:
+the host logic -- partition, halo exchange, boundary-label merge, scalar all-reduce -- with an
+oracle-backed local engine, checked against the oracle on the WHOLE volume."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    for p in (HERE, os.path.dirname(HERE), os.path.join(os.path.dirname(HERE), "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    import oracle as orc
+    from slab_cpu_engine import OracleEngine
+    from voxlogica_b200.slab import SlabComm, SlabOps, slab_bounds
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        sp = (1.0, 1.0, 1.5)
+        ops = SlabOps(OracleEngine(sp), SlabComm())
+        rng = np.random.default_rng(42)
+        shape = (13, 18, 22)
+        up = lambda a, s: np.ascontiguousarray(a)[None]
+        fails = []
+
+        def check(name, slab, want):
+            z0, z1 = slab_bounds(shape[0], world)[rank]
+            got = slab.data[0]
+            if not np.array_equal(got.view(np.uint32) if got.dtype == np.float32 else got,
+                                  want[z0:z1].view(np.uint32) if want.dtype == np.float32 else want[z0:z1]):
+                fails.append(name)
+
+        # a snake that crosses the slab boundaries several times + random clutter
+        b = (rng.random(shape) < 0.22).astype(np.uint8)
+        for z in range(shape[0]):
+            b[z, 3 + (z % 3), 2:20] = 1 if z % 2 == 0 else b[z, 3 + (z % 3), 2:20]
+            b[z, 4, 2 if (z // 2) % 2 == 0 else 19] = 1
+        a = np.zeros(shape, np.uint8); a[0, 3, 2] = 1; a[shape[0] - 1, 10, 10] = b[shape[0] - 1, 10, 10]
+        A, B = ops.scatter_from_global(up, a, sp), ops.scatter_from_global(up, b, sp)
+        for conn in (6, 26):
+            check(f"near{conn}", ops.near(B, conn), orc.near(b, conn))
+            check(f"interior{conn}", ops.interior(B, conn), orc.interior(b, conn))
+            check(f"through{conn}", ops.through(A, B, conn), orc.through(a, b, conn))
+            check(f"touch{conn}", ops.touch(B, A, conn), orc.touch(b, a, conn))
+            check(f"grow{conn}", ops.grow(A, B, conn), orc.grow(a, b, conn))
+        sparse = (rng.random(shape) < 0.01).astype(np.uint8)
+        S = ops.scatter_from_global(up, sparse, sp)
+        for r in (1.0, 2.5, 4.0):
+            check(f"distlt{r}", ops.distlt(r, S), orc.distlt(r, sparse, sp))
+            check(f"distgeq{r}", ops.distgeq(r, S), orc.distgeq(r, sparse, sp))
+            check(f"flt{r}", ops.flt(r, ops.near(S)), orc.flt(r, orc.near(sparse), sp))
+        f = rng.random(shape, dtype=np.float32)
+        F = ops.scatter_from_global(up, f, sp)
+        want = orc.cross_correlation(3.0, f, f, b, 0.0, 1.0, 16, sp)
+        check("xcorr", ops.cross_correlation(3.0, F, F, B, 0.0, 1.0, 16), want)
+        if ops.volume(B) != float(b.sum()): fails.append("volume")
+        if ops.min(F) != float(f.min()) or ops.max(F) != float(f.max()): fails.append("minmax")
+        check("lt", ops.cmp_scalar(F, "<", 0.3), orc.cmp_scalar(f, "<", 0.3))
+        q.put((rank, fails))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_ops_match_whole_volume_oracle(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=240) for _ in range(world)]
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    for rank, fails in res:
+        assert not fails, f"rank {rank}: {fails}"
+
+
+def test_boundary_graph_and_bounds():
+    from voxlogica_b200.slab import resolve_boundary_graph, slab_bounds
+    assert slab_bounds(10, 3) == [(0, 4), (4, 7), (7, 10)]
+    with pytest.raises(ValueError):
+        slab_bounds(2, 3)
+    # chain 1-2-3-4 with 4 reached, separate pair 7-8 not reached
+    pairs = np.array([[1, 2], [3, 2], [3, 4], [7, 8]], dtype=np.int64)
+    assert sorted(resolve_boundary_graph(pairs, np.array([4]))) == [1, 2, 3]
+    assert resolve_boundary_graph(pairs, np.array([], dtype=np.int64)).size == 0
+    assert resolve_boundary_graph(np.zeros((0, 2), np.int64), np.array([4])).size == 0

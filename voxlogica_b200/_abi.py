@@ -58,6 +58,11 @@ SIGNATURES = {
     "vx_retain": [u64],
     "vx_release": [u64],
     "vx_batch_slice": [u64, u64, i32, i32, P(u64)],
+    "vx_crop_z": [u64, u64, i32, i32, P(u64)],
+    "vx_concat_z": [u64, P(u64), i32, P(u64)],
+    "vx_transfer": [u64, u64, P(u64)],
+    "vx_device_ptr": [u64, u64, P(C.c_void_p)],
+    "vx_stream_handle": [u64, P(C.c_void_p)],
     "vx_host_alloc": [C.c_size_t, P(C.c_void_p)],
     "vx_host_free": [C.c_void_p],
     "vx_mem_info": [u64, P(u64), P(u64), P(u64)],
@@ -91,6 +96,8 @@ SIGNATURES = {
     "vx_dist_geq": [u64, u64, f32, P(u64)],
     "vx_dist_gt": [u64, u64, f32, P(u64)],
     "vx_cross_correlation": [u64, u64, u64, u64, f32, P(f64), P(f64), i32, P(u64)],
+    "vx_region_histogram": [u64, u64, u64, P(f64), P(f64), i32, P(u64)],
+    "vx_cross_correlation_h2": [u64, u64, P(u64), f32, P(f64), P(f64), i32, P(u64)],
     "vx_volume": [u64, u64, P(f64)],
     "vx_min": [u64, u64, P(f64)],
     "vx_max": [u64, u64, P(f64)],

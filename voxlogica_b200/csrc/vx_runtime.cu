@@ -430,7 +430,7 @@ int32_t vx_upload_batch(vx_ctx ctx, const void* host, int32_t dtype, int32_t nx,
     VX_TRY(g.begin(ctx));
     Image* im = nullptr;
     VX_TRY(new_image(g.c, dtype, nx, ny, nz, nb, spacing, &im));
-    cudaError_t e = cudaMemcpyAsync(im->d, host, im->bytes, cudaMemcpyHostToDevice, g.st);
+    cudaError_t e = cudaMemcpyAsync(im->d, host, im->bytes, cudaMemcpyDefault, g.st);
     if (e != cudaSuccess) {
         drop(im);
         return fail(VX_E_CUDA, "upload failed: %s", cudaGetErrorString(e));
@@ -451,7 +451,7 @@ int32_t vx_download(vx_ctx ctx, vx_img img, void* host, size_t bytes) {
     VX_TRY(g.input(img, &im, 0));
     VX_REQUIRE(bytes == im->bytes, VX_E_INVALID_ARG, "download size %zu != image size %zu", bytes,
                im->bytes);
-    VX_CUDA(cudaMemcpyAsync(host, im->d, bytes, cudaMemcpyDeviceToHost, g.st));
+    VX_CUDA(cudaMemcpyAsync(host, im->d, bytes, cudaMemcpyDefault, g.st));
     VX_CUDA(cudaStreamSynchronize(g.st));
     return g.finish_scalar();
 }
@@ -501,6 +501,105 @@ int32_t vx_batch_slice(vx_ctx ctx, vx_img img, int32_t first, int32_t count, vx_
         return fail(VX_E_CUDA, "slice copy failed: %s", cudaGetErrorString(e));
     }
     return g.finish(o, out);
+}
+
+// ---- slab helpers: z ranges of every volume of a batch -------------------------------------
+int32_t vx_crop_z(vx_ctx ctx, vx_img img, int32_t z0, int32_t nz, vx_img* out) {
+    VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");
+    OpGuard g;
+    VX_TRY(g.begin(ctx));
+    Image* im = nullptr;
+    VX_TRY(g.input(img, &im, 0));
+    VX_REQUIRE(z0 >= 0 && nz > 0 && z0 + nz <= im->nz, VX_E_INVALID_ARG,
+               "planes [%d,%d) outside a volume of %d planes", z0, z0 + nz, im->nz);
+    Image* o = nullptr;
+    VX_TRY(new_image(g.c, im->dtype, im->nx, im->ny, nz, im->nb, im->sp, &o));
+    const size_t es = im->bytes / im->count();
+    const size_t plane = (size_t)im->nx * im->ny * es;
+    cudaError_t e = cudaMemcpy2DAsync(o->d, plane * nz, (const char*)im->d + plane * z0, plane * im->nz,
+                                      plane * nz, im->nb, cudaMemcpyDeviceToDevice, g.st);
+    if (e != cudaSuccess) {
+        drop(o);
+        return fail(VX_E_CUDA, "crop copy failed: %s", cudaGetErrorString(e));
+    }
+    return g.finish(o, out);
+}
+
+int32_t vx_concat_z(vx_ctx ctx, const vx_img* parts, int32_t n_parts, vx_img* out) {
+    VX_REQUIRE(out != nullptr && parts != nullptr && n_parts >= 1 && n_parts <= 64, VX_E_INVALID_ARG,
+               "bad argument (1..64 parts)");
+    OpGuard g;
+    VX_TRY(g.begin(ctx));
+    std::vector<Image*> ims(n_parts, nullptr);
+    int nz = 0;
+    for (int i = 0; i < n_parts; i++) {
+        VX_TRY(g.input(parts[i], &ims[i], 0));
+        VX_REQUIRE(ims[i]->dtype == ims[0]->dtype && ims[i]->nx == ims[0]->nx && ims[i]->ny == ims[0]->ny &&
+                       ims[i]->nb == ims[0]->nb,
+                   VX_E_SHAPE_MISMATCH, "part %d differs in dtype, nx, ny or nb", i);
+        nz += ims[i]->nz;
+    }
+    Image* o = nullptr;
+    VX_TRY(new_image(g.c, ims[0]->dtype, ims[0]->nx, ims[0]->ny, nz, ims[0]->nb, ims[0]->sp, &o));
+    const size_t es = o->bytes / o->count();
+    const size_t plane = (size_t)o->nx * o->ny * es;
+    int z = 0;
+    for (int i = 0; i < n_parts; i++) {
+        cudaError_t e = cudaMemcpy2DAsync((char*)o->d + plane * z, plane * nz, ims[i]->d, plane * ims[i]->nz,
+                                          plane * ims[i]->nz, o->nb, cudaMemcpyDeviceToDevice, g.st);
+        if (e != cudaSuccess) {
+            drop(o);
+            return fail(VX_E_CUDA, "concat copy failed: %s", cudaGetErrorString(e));
+        }
+        z += ims[i]->nz;
+    }
+    return g.finish(o, out);
+}
+
+// Copy an image into another context (another GPU of the same process): peer-to-peer over
+// NVLink when the devices can reach each other, staged by the driver otherwise.
+int32_t vx_transfer(vx_ctx dst_ctx, vx_img img, vx_img* out) {
+    VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");
+    Image* im = get_img(img);
+    VX_REQUIRE(im != nullptr, VX_E_INVALID_ARG, "invalid image handle");
+    OpGuard g;
+    VX_TRY(g.begin(dst_ctx));
+    Ctx* src = im->ctx;
+    Image* o = nullptr;
+    VX_TRY(new_image(g.c, im->dtype, im->nx, im->ny, im->nz, im->nb, im->sp, &o));
+    // order the copy after the producer of `img` (an event of another device may be waited on)
+    cudaError_t e = cudaStreamWaitEvent(g.st, im->ready, 0);
+    if (e == cudaSuccess)
+        e = cudaMemcpyPeerAsync(o->d, g.c->device, im->d, src->device, im->bytes, g.st);
+    if (e != cudaSuccess) {
+        drop(o);
+        return fail(VX_E_CUDA, "transfer failed: %s", cudaGetErrorString(e));
+    }
+    // the source must outlive the copy: the caller keeps its reference until vx_sync(dst_ctx)
+    VX_TRY(publish(g.c, o, g.s));
+    *out = o->handle;
+    return VX_OK;
+}
+
+// Interop with other CUDA users of the process (torch.distributed / NCCL in the slab path):
+// the raw device pointer of an image and the CUDA stream of the calling thread.  Work
+// enqueued by the library on that stream before the call is ordered before anything the
+// caller enqueues on it afterwards.
+int32_t vx_device_ptr(vx_ctx ctx, vx_img img, void** ptr) {
+    VX_REQUIRE(ptr != nullptr, VX_E_INVALID_ARG, "ptr is NULL");
+    OpGuard g;
+    VX_TRY(g.begin(ctx));
+    Image* im = nullptr;
+    VX_TRY(g.input(img, &im, 0));   // makes the producer's work visible to this thread's stream
+    *ptr = im->d;
+    return g.finish_scalar();
+}
+int32_t vx_stream_handle(vx_ctx ctx, void** stream) {
+    VX_REQUIRE(stream != nullptr, VX_E_INVALID_ARG, "stream is NULL");
+    OpGuard g;
+    VX_TRY(g.begin(ctx));
+    *stream = (void*)g.st;
+    return VX_OK;
 }
 
 int32_t vx_host_alloc(size_t bytes, void** out) {

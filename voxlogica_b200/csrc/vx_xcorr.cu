@@ -527,45 +527,23 @@ static bool build_columns(const float sp[3], float rho, std::vector<unsigned>* c
     return true;
 }
 
-}  // namespace vx
-
-using namespace vx;
-
-extern "C" int32_t vx_cross_correlation(vx_ctx ctx, vx_img a, vx_img b, vx_img region, float rho,
-                                        const double* m, const double* M, int32_t k, vx_img* out) {
-    VX_REQUIRE(out != nullptr && m != nullptr && M != nullptr, VX_E_INVALID_ARG, "NULL argument");
-    VX_REQUIRE(k >= 1 && k <= kXcMaxBins, VX_E_UNSUPPORTED, "k = %d bins; supported range is [1,%d]", k,
-               kXcMaxBins);
-    VX_REQUIRE(rho == rho, VX_E_INVALID_ARG, "rho is NaN");
-    OpGuard og;
-    VX_TRY(og.begin(ctx));
-    Image *A = nullptr, *B = nullptr, *R = nullptr;
-    VX_TRY(og.input(a, &A, VX_F32));
-    VX_TRY(og.input(b, &B, VX_F32));
-    VX_TRY(og.input(region, &R, VX_U8));
-    VX_TRY(same_shape(A, B));
-    VX_TRY(same_shape(A, R));
+// Shared back end: bins of A, statistics of the given region histogram d_h2 ([nb][256] u32 on
+// the device, already final) and the sliding-ball kernel.  Frees d_mM and d_h2.
+static int xcorr_run(OpGuard& og, Image* A, double* d_mM, unsigned* d_h2, float rho, int32_t k, vx_img* out) {
     std::vector<unsigned> cols;
     long long ball = 0;
     VX_REQUIRE(build_columns(A->sp, rho, &cols, &ball) && ball <= 65535 && cols.size() <= 8192,
                VX_E_UNSUPPORTED, "radius %g is too large for the sliding-histogram kernel", (double)rho);
     const int nb = A->nb;
     const size_t nvox = A->nvox(), total = A->count();
-    // device scratch: m/M, bins, h2, vstat, columns
-    double* d_mM = nullptr;
     uint8_t* d_bins = nullptr;
-    unsigned *d_h2 = nullptr, *d_cols = nullptr;
+    unsigned* d_cols = nullptr;
     long long* d_vstat = nullptr;
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(double) * 2 * nb, (void**)&d_mM));
     VX_TRY(scratch_alloc(og.c, og.s, total, (void**)&d_bins));
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * 256 * nb, (void**)&d_h2));
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(long long) * 2 * nb, (void**)&d_vstat));
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (cols.size() + 128), (void**)&d_cols));
-    VX_CUDA(cudaMemcpyAsync(d_mM, m, sizeof(double) * nb, cudaMemcpyHostToDevice, og.st));
-    VX_CUDA(cudaMemcpyAsync(d_mM + nb, M, sizeof(double) * nb, cudaMemcpyHostToDevice, og.st));
     if (!cols.empty())
         VX_CUDA(cudaMemcpyAsync(d_cols, cols.data(), sizeof(unsigned) * cols.size(), cudaMemcpyHostToDevice, og.st));
-    VX_CUDA(cudaMemsetAsync(d_h2, 0, sizeof(unsigned) * 256 * nb, og.st));
     int per_vol = (int)((nvox + 256 * 8 - 1) / (256 * 8));
     int cap = (kNumSMs * 8 + nb - 1) / nb;
     dim3 sgrid(per_vol < cap ? per_vol : cap, nb);
@@ -574,11 +552,6 @@ extern "C" int32_t vx_cross_correlation(vx_ctx ctx, vx_img a, vx_img b, vx_img r
         xc_bin_kernel<<<sgrid, 256, 0, og.st>>>((const float*)A->d, d_bins, nvox, d_mM, nb, k);
     }
     VX_TRY(check_launch("xc_bin_kernel"));
-    {
-        VX_LAUNCH(og.c, og.s, "xc_region_hist_kernel");
-        xc_region_hist_kernel<<<sgrid, 256, 0, og.st>>>((const float*)B->d, (const uint8_t*)R->d, nvox, d_mM, nb, k, d_h2);
-    }
-    VX_TRY(check_launch("xc_region_hist_kernel"));
     {
         VX_LAUNCH(og.c, og.s, "xc_stat_kernel");
         xc_stat_kernel<<<nb, 1, 0, og.st>>>(d_h2, k, d_vstat);
@@ -664,4 +637,108 @@ extern "C" int32_t vx_cross_correlation(vx_ctx ctx, vx_img a, vx_img b, vx_img r
     if (rc == VX_OK) rc = scratch_free(og.c, og.s, d_cols);
     if (rc != VX_OK) { drop(O); return rc; }
     return og.finish(O, out);
+}
+
+}  // namespace vx
+
+
+using namespace vx;
+
+// h2 of b over region into d_h2 ([nb][256] u32, zeroed here)
+static int region_hist(OpGuard& og, Image* B, Image* R, const double* d_mM, int32_t k, unsigned* d_h2) {
+    const int nb = B->nb;
+    const size_t nvox = B->nvox();
+    VX_CUDA(cudaMemsetAsync(d_h2, 0, sizeof(unsigned) * 256 * nb, og.st));
+    int per_vol = (int)((nvox + 256 * 8 - 1) / (256 * 8));
+    int cap = (kNumSMs * 8 + nb - 1) / nb;
+    dim3 sgrid(per_vol < cap ? per_vol : cap, nb);
+    {
+        VX_LAUNCH(og.c, og.s, "xc_region_hist_kernel");
+        xc_region_hist_kernel<<<sgrid, 256, 0, og.st>>>((const float*)B->d, (const uint8_t*)R->d, nvox, d_mM, nb, k, d_h2);
+    }
+    return check_launch("xc_region_hist_kernel");
+}
+
+static int upload_mM(OpGuard& og, int nb, const double* m, const double* M, double** d_mM) {
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(double) * 2 * nb, (void**)d_mM));
+    VX_CUDA(cudaMemcpyAsync(*d_mM, m, sizeof(double) * nb, cudaMemcpyHostToDevice, og.st));
+    VX_CUDA(cudaMemcpyAsync(*d_mM + nb, M, sizeof(double) * nb, cudaMemcpyHostToDevice, og.st));
+    return VX_OK;
+}
+
+extern "C" int32_t vx_cross_correlation(vx_ctx ctx, vx_img a, vx_img b, vx_img region, float rho,
+                                        const double* m, const double* M, int32_t k, vx_img* out) {
+    VX_REQUIRE(out != nullptr && m != nullptr && M != nullptr, VX_E_INVALID_ARG, "NULL argument");
+    VX_REQUIRE(k >= 1 && k <= kXcMaxBins, VX_E_UNSUPPORTED, "k = %d bins; supported range is [1,%d]", k,
+               kXcMaxBins);
+    VX_REQUIRE(rho == rho, VX_E_INVALID_ARG, "rho is NaN");
+    OpGuard og;
+    VX_TRY(og.begin(ctx));
+    Image *A = nullptr, *B = nullptr, *R = nullptr;
+    VX_TRY(og.input(a, &A, VX_F32));
+    VX_TRY(og.input(b, &B, VX_F32));
+    VX_TRY(og.input(region, &R, VX_U8));
+    VX_TRY(same_shape(A, B));
+    VX_TRY(same_shape(A, R));
+    double* d_mM = nullptr;
+    unsigned* d_h2 = nullptr;
+    VX_TRY(upload_mM(og, A->nb, m, M, &d_mM));
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * 256 * A->nb, (void**)&d_h2));
+    VX_TRY(region_hist(og, B, R, d_mM, k, d_h2));
+    return xcorr_run(og, A, d_mM, d_h2, rho, k, out);
+}
+
+extern "C" int32_t vx_region_histogram(vx_ctx ctx, vx_img b, vx_img region, const double* m,
+                                       const double* M, int32_t k, uint64_t* h2) {
+    VX_REQUIRE(h2 != nullptr && m != nullptr && M != nullptr, VX_E_INVALID_ARG, "NULL argument");
+    VX_REQUIRE(k >= 1 && k <= kXcMaxBins, VX_E_UNSUPPORTED, "k = %d bins; supported range is [1,%d]", k,
+               kXcMaxBins);
+    OpGuard og;
+    VX_TRY(og.begin(ctx));
+    Image *B = nullptr, *R = nullptr;
+    VX_TRY(og.input(b, &B, VX_F32));
+    VX_TRY(og.input(region, &R, VX_U8));
+    VX_TRY(same_shape(B, R));
+    const int nb = B->nb;
+    double* d_mM = nullptr;
+    unsigned* d_h2 = nullptr;
+    VX_TRY(upload_mM(og, nb, m, M, &d_mM));
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * 256 * nb, (void**)&d_h2));
+    VX_TRY(region_hist(og, B, R, d_mM, k, d_h2));
+    std::vector<unsigned> host((size_t)256 * nb);
+    VX_CUDA(cudaMemcpyAsync(host.data(), d_h2, sizeof(unsigned) * 256 * nb, cudaMemcpyDeviceToHost, og.st));
+    VX_CUDA(cudaStreamSynchronize(og.st));
+    for (int v = 0; v < nb; v++)
+        for (int i = 0; i < k; i++) h2[(size_t)v * k + i] = host[(size_t)v * 256 + i];
+    VX_TRY(scratch_free(og.c, og.s, d_mM));
+    VX_TRY(scratch_free(og.c, og.s, d_h2));
+    return og.finish_scalar();
+}
+
+extern "C" int32_t vx_cross_correlation_h2(vx_ctx ctx, vx_img a, const uint64_t* h2, float rho,
+                                           const double* m, const double* M, int32_t k, vx_img* out) {
+    VX_REQUIRE(out != nullptr && h2 != nullptr && m != nullptr && M != nullptr, VX_E_INVALID_ARG, "NULL argument");
+    VX_REQUIRE(k >= 1 && k <= kXcMaxBins, VX_E_UNSUPPORTED, "k = %d bins; supported range is [1,%d]", k,
+               kXcMaxBins);
+    VX_REQUIRE(rho == rho, VX_E_INVALID_ARG, "rho is NaN");
+    OpGuard og;
+    VX_TRY(og.begin(ctx));
+    Image* A = nullptr;
+    VX_TRY(og.input(a, &A, VX_F32));
+    const int nb = A->nb;
+    std::vector<unsigned> host((size_t)256 * nb, 0u);
+    for (int v = 0; v < nb; v++)
+        for (int i = 0; i < k; i++) {
+            const uint64_t c = h2[(size_t)v * k + i];
+            VX_REQUIRE(c <= 0xffffffffull, VX_E_UNSUPPORTED, "region histogram counter %llu exceeds 32 bits",
+                       (unsigned long long)c);
+            host[(size_t)v * 256 + i] = (unsigned)c;
+        }
+    double* d_mM = nullptr;
+    unsigned* d_h2 = nullptr;
+    VX_TRY(upload_mM(og, nb, m, M, &d_mM));
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * 256 * nb, (void**)&d_h2));
+    // pageable source: cudaMemcpyAsync stages it before returning, `host` may die afterwards
+    VX_CUDA(cudaMemcpyAsync(d_h2, host.data(), sizeof(unsigned) * 256 * nb, cudaMemcpyHostToDevice, og.st));
+    return xcorr_run(og, A, d_mM, d_h2, rho, k, out);
 }

@@ -161,6 +161,62 @@ class Context:
     def batch_slice(self, img: Image, first: int, count: int) -> Image:
         return self._out(lambda o: self.lib.vx_batch_slice(self.handle, img.handle, first, count, o))
 
+    # ------------------------------------------------------------------ slab helpers / interop
+    def crop_z(self, img: Image, z0: int, nz: int) -> Image:
+        return self._out(lambda o: self.lib.vx_crop_z(self.handle, img.handle, int(z0), int(nz), o))
+
+    def concat_z(self, parts: Sequence[Image]) -> Image:
+        arr = (A.u64 * len(parts))(*[p.handle for p in parts])
+        return self._out(lambda o: self.lib.vx_concat_z(self.handle, arr, len(parts), o))
+
+    def transfer_from(self, img: Image) -> Image:
+        """copy an image of ANOTHER context (GPU) of this process into this one (peer copy)"""
+        return self._out(lambda o: self.lib.vx_transfer(self.handle, img.handle, o))
+
+    def device_ptr(self, img: Image) -> int:
+        p = C.c_void_p()
+        check(self.lib.vx_device_ptr(self.handle, img.handle, C.byref(p)))
+        return p.value or 0
+
+    def stream_handle(self) -> int:
+        p = C.c_void_p()
+        check(self.lib.vx_stream_handle(self.handle, C.byref(p)))
+        return p.value or 0
+
+    def as_tensor(self, img: Image):
+        """zero-copy torch view [nb][nz][ny][nx] of an image (CUDA array interface).  The view
+        is ordered after the image's producer on THIS thread's library stream; synchronise
+        (``sync()``) before handing it to code running on another stream."""
+        import torch
+
+        dt, nx, ny, nz, nb, _ = img.info()
+        typestr = {A.VX_U8: "|u1", A.VX_F32: "<f4", A.VX_U32: "<u4"}[dt]
+
+        class _View:
+            pass
+
+        v = _View()
+        v.__cuda_array_interface__ = {"shape": (nb, nz, ny, nx), "typestr": typestr,
+                                      "data": (self.device_ptr(img), False), "version": 3, "strides": None}
+        v._keepalive = img
+        if dt == A.VX_U32:   # torch has no first-class uint32 arithmetic: expose the bits as int32
+            v.__cuda_array_interface__["typestr"] = "<i4"
+        t = torch.as_tensor(v, device=f"cuda:{self.device}")
+        t._vx_keepalive = img
+        return t
+
+    def from_tensor(self, t, spacing=None) -> Image:
+        """device tensor [nb][nz][ny][nx] (uint8 / float32 / int32 bits of u32) -> new image (D2D copy)"""
+        import torch
+
+        t = t.contiguous()
+        dt = {torch.uint8: np.uint8, torch.float32: np.float32, torch.int32: np.uint32}[t.dtype]
+        if t.is_cuda:
+            torch.cuda.current_stream(t.device).synchronize()
+        img = self.upload_ptr(t.data_ptr(), dt, tuple(t.shape), spacing)
+        self.sync()          # the source tensor may be freed by torch as soon as we return
+        return img
+
     # ------------------------------------------------------------------ helpers
     def _out(self, call) -> Image:
         out = A.u64()
@@ -281,6 +337,20 @@ class Context:
         mm, MM = self._per_volume(m, nb, A.f64), self._per_volume(M, nb, A.f64)
         return self._out(lambda o: self.lib.vx_cross_correlation(
             self.handle, a.handle, b.handle, region.handle, float(rho), mm, MM, int(k), o))
+
+    def region_histogram(self, b: Image, region: Image, m, M, k: int) -> np.ndarray:
+        nb = b.nb
+        mm, MM = self._per_volume(m, nb, A.f64), self._per_volume(M, nb, A.f64)
+        buf = (A.u64 * (nb * int(k)))()
+        check(self.lib.vx_region_histogram(self.handle, b.handle, region.handle, mm, MM, int(k), buf))
+        return np.frombuffer(buf, dtype=np.uint64).reshape(nb, int(k)).copy()
+
+    def cross_correlation_h2(self, rho: float, a: Image, h2, m, M, k: int) -> Image:
+        nb = a.nb
+        mm, MM = self._per_volume(m, nb, A.f64), self._per_volume(M, nb, A.f64)
+        h = np.ascontiguousarray(np.broadcast_to(np.asarray(h2, dtype=np.uint64), (nb, int(k))))
+        return self._out(lambda o: self.lib.vx_cross_correlation_h2(
+            self.handle, a.handle, h.ctypes.data_as(C.POINTER(A.u64)), float(rho), mm, MM, int(k), o))
 
     # ------------------------------------------------------------------ reductions
     def volume(self, a: Image) -> np.ndarray:

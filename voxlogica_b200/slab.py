@@ -1,0 +1,361 @@
+"""Slab decomposition of ONE oversized volume across ranks.
+
+A volume [nz][ny][nx] is split along z into contiguous slabs, one per rank (one process per
+GPU, ``torch.distributed``: NCCL over NVLink on the GPUs, gloo in the CPU tests).  Every
+operator has at most one exchange step:
+
+    pointwise ............ none
+    volume / min / max ... one scalar all-reduce
+    near / interior ...... 1-plane halo from each z-neighbour (send/recv)
+    distlt / distgeq ..... ceil(r / sz)-plane halo (the interval test only looks r far)
+    crossCorrelation ..... ceil(rho / sz)-plane halo of `a` + all-reduce of the region histogram
+    through .............. local union-find per slab, exchange of the boundary label planes,
+                           all-gather of the cross-slab label equivalences and of the labels
+                           already reached by a seed, union-find over that (small) boundary graph
+                           replicated on every rank, then one more local pass seeded with the
+                           labels that became reachable through a neighbour
+
+The local work is done by an *engine* (``CudaEngine`` = libvoxcuda through the C ABI; the CPU
+tests plug in an oracle-backed engine to exercise exactly this host logic with gloo).  Planes
+travel as torch tensors: zero-copy views of the HBM-resident images on the GPU path.
+
+Not decomposed yet: ``percentiles`` (needs a distributed sort), ``maxvol`` and the f32 ``edt``
+map (z pass needs an axis re-partition); they raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def slab_bounds(nz: int, world: int) -> List[Tuple[int, int]]:
+    """[z0, z1) of every rank: as even as possible, earlier ranks get the extra planes."""
+    if world < 1 or nz < world:
+        raise ValueError(f"cannot split {nz} planes over {world} ranks")
+    base, extra = divmod(nz, world)
+    out, z = [], 0
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        out.append((z, z + n))
+        z += n
+    return out
+
+
+@dataclass
+class Slab:
+    """One rank's part of a distributed volume."""
+    data: object                 # engine array: planes [z0, z1) as [1][nz_local][ny][nx]
+    z0: int
+    z1: int
+    nz_global: int
+    spacing: Tuple[float, float, float] = (1.0, 1.0, 1.0)
+
+    def like(self, data) -> "Slab":
+        return Slab(data, self.z0, self.z1, self.nz_global, self.spacing)
+
+
+class CudaEngine:
+    """Local operations of one rank on libvoxcuda images (voxlogica_b200.ops.Context)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    # geometry / movement
+    def nz(self, x):
+        return x.shape[1]
+
+    def crop_z(self, x, z0, n):
+        return self.ctx.crop_z(x, z0, n)
+
+    def concat_z(self, parts):
+        return self.ctx.concat_z(list(parts))
+
+    def to_tensor(self, x):
+        t = self.ctx.as_tensor(x)
+        self.ctx.sync()                      # producer finished: safe on torch's streams
+        return t[0]
+
+    def from_tensor(self, t, like):
+        return self.ctx.from_tensor(t[None], spacing=like.spacing)
+
+    def zeros_u8(self, like):
+        return self.ctx.ff(like)
+
+    # operators
+    def not_(self, a): return self.ctx.not_(a)
+    def and_(self, a, b): return self.ctx.and_(a, b)
+    def or_(self, a, b): return self.ctx.or_(a, b)
+    def cmp_scalar(self, a, op, s): return self.ctx.cmp_scalar(a, op, s)
+    def near(self, a, conn): return self.ctx.near(a, conn)
+    def interior(self, a, conn): return self.ctx.interior(a, conn)
+    def through(self, a, b, conn): return self.ctx.through(a, b, conn)
+    def components(self, a, conn): return self.ctx.components(a, conn)
+
+    def dist(self, op, r, a):
+        return {"<": self.ctx.distlt, "<=": self.ctx.distleq, ">=": self.ctx.distgeq, ">": self.ctx.distgt}[op](r, a)
+
+    def region_histogram(self, b, region, m, M, k): return self.ctx.region_histogram(b, region, m, M, k)[0]
+    def cross_correlation_h2(self, rho, a, h2, m, M, k): return self.ctx.cross_correlation_h2(rho, a, h2, m, M, k)
+    def volume(self, a): return float(self.ctx.volume(a)[0])
+    def min(self, a): return float(self.ctx.min(a)[0])
+    def max(self, a): return float(self.ctx.max(a)[0])
+
+
+class SlabComm:
+    """The collective side: a torch.distributed process group (NCCL or gloo)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def exchange_planes(self, to_lower, to_upper):
+        """send `to_lower` to rank-1 and `to_upper` to rank+1 (tensors or None at the ends);
+        returns (from_lower, from_upper), None where there is no neighbour."""
+        import torch
+        dist = self.dist
+        ops, from_lower, from_upper = [], None, None
+        if self.rank > 0:
+            from_lower = torch.empty_like(to_lower)
+            ops.append(dist.P2POp(dist.isend, to_lower.contiguous(), self.rank - 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, from_lower, self.rank - 1, self.group))
+        if self.rank + 1 < self.world:
+            from_upper = torch.empty_like(to_upper)
+            ops.append(dist.P2POp(dist.isend, to_upper.contiguous(), self.rank + 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, from_upper, self.rank + 1, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            if to_lower.is_cuda:
+                torch.cuda.current_stream(to_lower.device).synchronize()
+        return from_lower, from_upper
+
+    def all_gather_rows(self, t):
+        """all-gather of [n_i, c] int64 tensors with different n_i -> one [sum n_i, c] tensor"""
+        import torch
+        dist = self.dist
+        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+        sizes = [torch.zeros_like(n) for _ in range(self.world)]
+        dist.all_gather(sizes, n, group=self.group)
+        sizes = [int(s.item()) for s in sizes]
+        cap = max(max(sizes), 1)
+        pad = torch.zeros((cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad[: t.shape[0]] = t
+        bufs = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(bufs, pad, group=self.group)
+        return torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
+
+    def all_reduce(self, values: Sequence[float], op: str, device) -> np.ndarray:
+        import torch
+        t = torch.tensor(list(values), dtype=torch.float64, device=device)
+        red = {"sum": self.dist.ReduceOp.SUM, "min": self.dist.ReduceOp.MIN, "max": self.dist.ReduceOp.MAX}[op]
+        self.dist.all_reduce(t, op=red, group=self.group)
+        return t.cpu().numpy()
+
+    def all_reduce_i64(self, arr: np.ndarray, device) -> np.ndarray:
+        import torch
+        t = torch.as_tensor(np.asarray(arr, dtype=np.int64), device=device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
+
+class SlabOps:
+    """ImgQL operators on Slab values.  Same names and argument order as ops.Context."""
+
+    def __init__(self, engine, comm: SlabComm):
+        self.e = engine
+        self.c = comm
+
+    # ------------------------------------------------------------------ distribution
+    def scatter_from_global(self, upload, vol: np.ndarray, spacing=(1.0, 1.0, 1.0)) -> Slab:
+        """test/harness helper: every rank holds the global array and keeps its slab"""
+        z0, z1 = slab_bounds(vol.shape[0], self.c.world)[self.c.rank]
+        return Slab(upload(np.ascontiguousarray(vol[z0:z1]), spacing), z0, z1, vol.shape[0], tuple(spacing))
+
+    def _device_of(self, x: Slab):
+        return self.e.to_tensor(self.e.crop_z(x.data, 0, 1)).device
+
+    # ------------------------------------------------------------------ halo machinery
+    def _with_halo(self, x: Slab, h: int):
+        """-> (extended array, planes added below, planes added above)"""
+        if h <= 0 or self.c.world == 1:
+            return x.data, 0, 0
+        nzl = self.e.nz(x.data)
+        if h > nzl:
+            raise ValueError(f"halo of {h} planes exceeds a slab of {nzl} planes: use fewer ranks")
+        lo = self.e.to_tensor(self.e.crop_z(x.data, 0, h))
+        hi = self.e.to_tensor(self.e.crop_z(x.data, nzl - h, h))
+        from_lower, from_upper = self.c.exchange_planes(lo, hi)
+        parts, below, above = [], 0, 0
+        if from_lower is not None:
+            parts.append(self.e.from_tensor(from_lower, x))
+            below = h
+        parts.append(x.data)
+        if from_upper is not None:
+            parts.append(self.e.from_tensor(from_upper, x))
+            above = h
+        return (self.e.concat_z(parts) if len(parts) > 1 else x.data), below, above
+
+    def _halo_op(self, x: Slab, h: int, fn) -> Slab:
+        ext, below, above = self._with_halo(x, h)
+        out = fn(ext)
+        if below or above:
+            out = self.e.crop_z(out, below, self.e.nz(x.data))
+        return x.like(out)
+
+    # ------------------------------------------------------------------ local operators
+    def not_(self, a: Slab) -> Slab: return a.like(self.e.not_(a.data))
+    def and_(self, a: Slab, b: Slab) -> Slab: return a.like(self.e.and_(a.data, b.data))
+    def or_(self, a: Slab, b: Slab) -> Slab: return a.like(self.e.or_(a.data, b.data))
+    def cmp_scalar(self, a: Slab, op: str, s: float) -> Slab: return a.like(self.e.cmp_scalar(a.data, op, s))
+
+    # ------------------------------------------------------------------ reductions
+    def volume(self, a: Slab) -> float:
+        return float(self.c.all_reduce([self.e.volume(a.data)], "sum", self._device_of(a))[0])
+
+    def min(self, a: Slab) -> float:
+        return float(self.c.all_reduce([self.e.min(a.data)], "min", self._device_of(a))[0])
+
+    def max(self, a: Slab) -> float:
+        return float(self.c.all_reduce([self.e.max(a.data)], "max", self._device_of(a))[0])
+
+    # ------------------------------------------------------------------ halo operators
+    def near(self, a: Slab, conn: int = 26) -> Slab:
+        return self._halo_op(a, 1, lambda x: self.e.near(x, conn))
+
+    def interior(self, a: Slab, conn: int = 26) -> Slab:
+        return self._halo_op(a, 1, lambda x: self.e.interior(x, conn))
+
+    def _dist(self, op: str, r: float, a: Slab) -> Slab:
+        h = 0 if not (r > 0) else int(math.ceil(float(r) / float(a.spacing[2])))
+        h = min(h, a.nz_global)
+        return self._halo_op(a, h, lambda x: self.e.dist(op, r, x))
+
+    def distlt(self, r, a): return self._dist("<", r, a)
+    def distleq(self, r, a): return self._dist("<=", r, a)
+    def distgeq(self, r, a): return self._dist(">=", r, a)
+    def distgt(self, r, a): return self._dist(">", r, a)
+
+    def flt(self, r, a: Slab) -> Slab:
+        return self.distlt(r, self.distgeq(r, self.not_(a)))
+
+    def cross_correlation(self, rho: float, a: Slab, b: Slab, region: Slab, m: float, M: float, k: int) -> Slab:
+        h2_local = np.asarray(self.e.region_histogram(b.data, region.data, m, M, k), dtype=np.int64)
+        h2 = self.c.all_reduce_i64(h2_local, self._device_of(a)).astype(np.uint64)
+        h = 0 if not (rho > 0) else min(int(math.ceil(float(rho) / float(a.spacing[2]))), a.nz_global)
+        return self._halo_op(a, h, lambda x: self.e.cross_correlation_h2(rho, x, h2, m, M, k))
+
+    # ------------------------------------------------------------------ reachability
+    def through(self, a: Slab, b: Slab, conn: int = 26) -> Slab:
+        """union of the connected components of b (global, across slabs) that contain a voxel of a"""
+        import torch
+        e, c = self.e, self.c
+        r0 = e.through(a.data, b.data, conn)
+        if c.world == 1:
+            return b.like(r0)
+        nzl = e.nz(b.data)
+        labels = e.components(b.data, conn)
+        lab_bot = e.to_tensor(e.crop_z(labels, 0, 1))[0].to(torch.int64) & 0xffffffff
+        lab_top = e.to_tensor(e.crop_z(labels, nzl - 1, 1))[0].to(torch.int64) & 0xffffffff
+        hit_bot = e.to_tensor(e.crop_z(r0, 0, 1))[0] != 0
+        hit_top = e.to_tensor(e.crop_z(r0, nzl - 1, 1))[0] != 0
+        tag = (c.rank + 1) << 32                       # global id of a local label: (rank+1, label)
+        gid_bot = torch.where(lab_bot > 0, lab_bot + tag, torch.zeros_like(lab_bot))
+        gid_top = torch.where(lab_top > 0, lab_top + tag, torch.zeros_like(lab_top))
+        # the upper neighbour needs my top plane, I need the lower neighbour's top plane
+        below_top, _ = c.exchange_planes(gid_bot, gid_top)   # from_lower = what rank-1 sent "to_upper"
+        pairs = torch.zeros((0, 2), dtype=torch.int64, device=gid_bot.device)
+        if below_top is not None:
+            pairs = boundary_pairs(below_top, gid_bot, conn)
+        reached = torch.unique(torch.cat([gid_bot[hit_bot], gid_top[hit_top]]))
+        all_pairs = c.all_gather_rows(pairs).cpu().numpy()
+        all_reached = c.all_gather_rows(reached[:, None]).cpu().numpy()[:, 0]
+        newly = resolve_boundary_graph(all_pairs, all_reached)
+        mine = newly[(newly >> 32) == c.rank + 1]
+        if mine.size == 0:
+            return b.like(r0)
+        mine_t = torch.as_tensor(mine, device=gid_bot.device)
+        seed_bot = torch.isin(gid_bot, mine_t).to(torch.uint8)
+        seed_top = torch.isin(gid_top, mine_t).to(torch.uint8)
+        # extra seeds live on the two boundary planes only
+        parts = []
+        if nzl == 1:
+            parts.append(e.from_tensor((seed_bot | seed_top)[None], b))
+        else:
+            parts.append(e.from_tensor(seed_bot[None], b))
+            if nzl > 2:
+                parts.append(e.crop_z(e.zeros_u8(b.data), 0, nzl - 2))
+            parts.append(e.from_tensor(seed_top[None], b))
+        extra = e.concat_z(parts) if len(parts) > 1 else parts[0]
+        return b.like(e.through(e.or_(a.data, extra), b.data, conn))
+
+    def touch(self, a: Slab, b: Slab, conn: int = 26) -> Slab:
+        return self.and_(a, self.through(self.near(b, conn), a, conn))
+
+    def grow(self, a: Slab, b: Slab, conn: int = 26) -> Slab:
+        return self.or_(a, self.touch(b, a, conn))
+
+    # ------------------------------------------------------------------ not decomposed yet
+    def percentiles(self, *a, **k):
+        raise NotImplementedError("percentiles on slabs needs a distributed sort (DESIGN.md section 6)")
+
+    def maxvol(self, *a, **k):
+        raise NotImplementedError("maxvol on slabs is not implemented yet (DESIGN.md section 6)")
+
+    def edt(self, *a, **k):
+        raise NotImplementedError("the f32 distance map on slabs needs a z re-partition (DESIGN.md section 6)")
+
+
+def boundary_pairs(lower, upper, conn: int):
+    """unique (id in the plane below, id in the plane above) pairs of adjacent foreground voxels.
+    lower/upper: [ny][nx] int64 ids, 0 = background.  6-adjacency: same (y, x); 26: 3x3."""
+    import torch
+    ny, nx = lower.shape
+    out = []
+    shifts = [(0, 0)] if conn == 6 else [(dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+    for dy, dx in shifts:
+        ys, ye = max(0, -dy), min(ny, ny - dy)
+        xs, xe = max(0, -dx), min(nx, nx - dx)
+        if ys >= ye or xs >= xe:
+            continue
+        u = upper[ys:ye, xs:xe]
+        l = lower[ys + dy:ye + dy, xs + dx:xe + dx]
+        m = (u > 0) & (l > 0)
+        if bool(m.any()):
+            out.append(torch.unique(torch.stack([l[m], u[m]], dim=1), dim=0))
+    if not out:
+        return torch.zeros((0, 2), dtype=torch.int64, device=lower.device)
+    return torch.unique(torch.cat(out, dim=0), dim=0)
+
+
+def resolve_boundary_graph(pairs: np.ndarray, reached: np.ndarray) -> np.ndarray:
+    """Union-find over the boundary-label graph (replicated on every rank).  Returns the ids
+    that are NOT in `reached` but share a class with an id that is: those components become
+    reachable through a neighbouring slab."""
+    if pairs.size == 0:
+        return np.zeros(0, dtype=np.int64)
+    ids, inv = np.unique(pairs.ravel(), return_inverse=True)
+    edges = inv.reshape(-1, 2)
+    parent = np.arange(ids.size)
+    # vectorised union-find: hook the larger root under the smaller, then pointer-jump
+    while True:
+        ra, rb = parent[edges[:, 0]], parent[edges[:, 1]]
+        lo, hi = np.minimum(ra, rb), np.maximum(ra, rb)
+        changed = lo != hi
+        if not changed.any():
+            break
+        np.minimum.at(parent, hi[changed], lo[changed])
+        while True:
+            nxt = parent[parent]
+            if np.array_equal(nxt, parent):
+                break
+            parent = nxt
+    is_reached = np.isin(ids, reached)
+    root_reached = np.zeros(ids.size, dtype=bool)
+    np.logical_or.at(root_reached, parent, is_reached)
+    return ids[root_reached[parent] & ~is_reached].astype(np.int64)
