@@ -158,6 +158,89 @@ edt_axis_kernel(const float* __restrict__ gin, void* __restrict__ gout_,
     else reinterpret_cast<uint8_t*>(gout_)[idx] = (uint8_t)((best < T ? 1 : 0) ^ invert);
 }
 
+// ------------------------------------------------------------------ lower-envelope y / z passes
+// Maurer / Meijster style separable pass: out[i] = min_j ( g[j] + s2 * (i - j)^2 ) computed in
+// O(n) per column with a stack of the parabolas on the lower envelope (partial Voronoi
+// diagram of the column), one THREAD per column so that a warp reads/writes 32 consecutive x.
+// Only used when the arithmetic is exact in integers (integer spacings, every squared
+// distance below 2^24): then binary32 is exact too and the result equals the arithmetic
+// contract in the header bit for bit.  The stack lives in a scratch array laid out
+// [depth][column] (coalesced while neighbouring columns have similar depths); its top entry
+// stays in registers, so a step that neither pops nor pushes touches no memory but g[u].
+//   entry = (s: position of the parabola, t: first index where it is the minimum, g: its height)
+__device__ __forceinline__ uint2 env_pack(int s_, int t_, int g_) { return make_uint2((unsigned)s_ | ((unsigned)t_ << 16), (unsigned)g_); }
+
+template <int AXIS, int MODE>
+__global__ void __launch_bounds__(128)
+edt_env_kernel(const float* __restrict__ gin, void* __restrict__ gout_, uint2* __restrict__ stack,
+               int nx, int ny, int nz, size_t ncols, int s2, float T, int invert) {
+    const size_t col = (size_t)blockIdx.x * 128 + threadIdx.x;
+    if (col >= ncols) return;
+    size_t base, stride;
+    int n;
+    if (AXIS == 1) {   // col = (vol*nz + z) * nx + x
+        const size_t pz = col / nx;
+        base = pz * (size_t)ny * nx + (col - pz * nx);
+        stride = nx; n = ny;
+    } else {           // col = vol * (ny*nx) + y*nx + x
+        const size_t plane = (size_t)ny * nx;
+        const size_t vol = col / plane;
+        base = vol * plane * nz + (col - vol * plane);
+        stride = plane; n = nz;
+    }
+    uint2* st = stack + col;
+    int q = -1, ts = 0, tt = 0, tg = 0;   // top of the stack (entry q) lives in registers
+    constexpr int PF = 4;
+    for (int u0 = 0; u0 < n; u0 += PF) {
+        float gv[PF];
+#pragma unroll
+        for (int e = 0; e < PF; e++) gv[e] = (u0 + e < n) ? __ldg(gin + base + (size_t)(u0 + e) * stride) : INFINITY;
+#pragma unroll
+        for (int e = 0; e < PF; e++) {
+            if (!(gv[e] < INFINITY)) continue;   // no feature reaches this cell from the previous axes
+            const int u = u0 + e, gu = (int)gv[e];
+            if (q < 0) { q = 0; ts = u; tt = 0; tg = gu; continue; }
+            // drop the parabolas that the new one beats at the start of their own interval
+            while (true) {
+                const int d1 = tt - ts, d2 = tt - u;
+                if (tg + s2 * d1 * d1 > gu + s2 * d2 * d2) {
+                    if (--q < 0) break;
+                    const uint2 en = st[(size_t)q * ncols];
+                    ts = (int)(en.x & 0xffffu); tt = (int)(en.x >> 16); tg = (int)en.y;
+                } else break;
+            }
+            if (q < 0) { q = 0; ts = u; tt = 0; tg = gu; continue; }
+            // first index where parabola u is strictly below parabola ts
+            const int num = s2 * (u * u - ts * ts) + gu - tg, den = 2 * s2 * (u - ts);
+            int sep = num / den;
+            if (num < 0 && sep * den != num) sep--;   // floor
+            const int w = sep + 1;
+            if (w < n) {
+                st[(size_t)q * ncols] = env_pack(ts, tt, tg);
+                q++; ts = u; tt = w; tg = gu;
+            }
+        }
+    }
+    float* of = reinterpret_cast<float*>(gout_);
+    uint8_t* ob = reinterpret_cast<uint8_t*>(gout_);
+    for (int u = n - 1; u >= 0; u--) {
+        float best = INFINITY;
+        if (q >= 0) {
+            const int d = u - ts;
+            best = (float)(tg + s2 * d * d);
+        }
+        const size_t o = base + (size_t)u * stride;
+        if (MODE == EDT_MID) of[o] = best;
+        else if (MODE == EDT_SQRT) of[o] = __fsqrt_rn(best);
+        else ob[o] = (uint8_t)((best < T ? 1 : 0) ^ invert);
+        if (q > 0 && u == tt) {
+            q--;
+            const uint2 en = st[(size_t)q * ncols];
+            ts = (int)(en.x & 0xffffu); tt = (int)(en.x >> 16); tg = (int)en.y;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ bit-domain ball dilation
 // pack: one thread per 32-voxel word of a row
 __device__ __forceinline__ unsigned nib_of(unsigned w) {
@@ -324,14 +407,41 @@ static int edt_passes(OpGuard& og, const Image* A, void* out, int final_mode, fl
                                                      A->nx, A->ny, A->nz, rows, A->sp[0]);
     }
     VX_TRY(check_launch("edt_x_kernel"));
+    // exact-integer fast path per axis: every spacing up to this axis is a small integer and no
+    // squared distance can reach 2^24, so binary32 arithmetic is exact and the O(n)
+    // lower-envelope pass yields the contract's value bit for bit
+    auto int_spacing = [](float sp) { return sp >= 1.0f && sp <= 64.0f && sp == floorf(sp); };
+    auto span2 = [](float sp, int n) { double d = (double)sp * (n - 1); return d * d; };
+    const bool ix = int_spacing(A->sp[0]), iy = int_spacing(A->sp[1]), iz = int_spacing(A->sp[2]);
+    const double bound_y = span2(A->sp[0], A->nx) + span2(A->sp[1], A->ny);
+    const double bound_z = bound_y + span2(A->sp[2], A->nz);
+    const bool env_y = ix && iy && bound_y < 16777216.0 && A->ny <= 65535 && A->ny > 1;
+    const bool env_z = ix && iy && iz && bound_z < 16777216.0 && A->nz <= 65535 && A->nz > 1;
+    uint2* stack = nullptr;
+    if (env_y || env_z) VX_TRY(scratch_alloc(og.c, og.s, sizeof(uint2) * total, (void**)&stack));
     const unsigned grid = (unsigned)((total + kEdtThreads - 1) / kEdtThreads);
-    {
+    if (env_y) {
+        const size_t ncols = (size_t)A->nb * A->nz * A->nx;
+        const int s2 = (int)(A->sp[1] * A->sp[1]);
+        VX_LAUNCH(og.c, og.s, "edt_env_kernel_y");
+        edt_env_kernel<1, EDT_MID><<<(unsigned)((ncols + 127) / 128), 128, 0, og.st>>>(
+            g1, g2, stack, A->nx, A->ny, A->nz, ncols, s2, 0.f, 0);
+    } else {
         VX_LAUNCH(og.c, og.s, "edt_axis_kernel_y");
         edt_axis_kernel<1, EDT_MID><<<grid, kEdtThreads, 0, og.st>>>(g1, g2, rowflag, A->nx, A->ny, A->nz,
                                                                     total, A->sp[1], 0.f, 0);
     }
-    VX_TRY(check_launch("edt_axis_kernel_y"));
-    {
+    VX_TRY(check_launch("edt y pass"));
+    if (env_z) {
+        const size_t ncols = (size_t)A->nb * A->ny * A->nx;
+        const int s2 = (int)(A->sp[2] * A->sp[2]);
+        VX_LAUNCH(og.c, og.s, "edt_env_kernel_z");
+        const unsigned eg = (unsigned)((ncols + 127) / 128);
+        if (final_mode == EDT_SQRT)
+            edt_env_kernel<2, EDT_SQRT><<<eg, 128, 0, og.st>>>(g2, out, stack, A->nx, A->ny, A->nz, ncols, s2, 0.f, 0);
+        else
+            edt_env_kernel<2, EDT_THRESH><<<eg, 128, 0, og.st>>>(g2, out, stack, A->nx, A->ny, A->nz, ncols, s2, T, invert);
+    } else {
         VX_LAUNCH(og.c, og.s, "edt_axis_kernel_z");
         if (final_mode == EDT_SQRT)
             edt_axis_kernel<2, EDT_SQRT><<<grid, kEdtThreads, 0, og.st>>>(g2, out, planeflag, A->nx, A->ny,
@@ -340,7 +450,8 @@ static int edt_passes(OpGuard& og, const Image* A, void* out, int final_mode, fl
             edt_axis_kernel<2, EDT_THRESH><<<grid, kEdtThreads, 0, og.st>>>(g2, out, planeflag, A->nx, A->ny,
                                                                            A->nz, total, A->sp[2], T, invert);
     }
-    VX_TRY(check_launch("edt_axis_kernel_z"));
+    VX_TRY(check_launch("edt z pass"));
+    if (stack) VX_TRY(scratch_free(og.c, og.s, stack));
     VX_TRY(scratch_free(og.c, og.s, g1));
     VX_TRY(scratch_free(og.c, og.s, g2));
     return scratch_free(og.c, og.s, flags);
