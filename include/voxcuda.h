@@ -258,6 +258,10 @@ VX_API int32_t vx_region_histogram(vx_ctx ctx, vx_img b, vx_img region, const do
 VX_API int32_t vx_cross_correlation_h2(vx_ctx ctx, vx_img a, const uint64_t* h2, float rho,
                                        const double* m, const double* M, int32_t k, vx_img* out);
 
+/* Host-only: the k+1 break points of the binning (edges[i] = smallest binary32 whose bin is >= i;
+ * edges[0]: smallest value >= m, edges[k]: smallest value >= M).  Needs no device. */
+VX_API int32_t vx_xcorr_bin_edges(double m, double M, int32_t k, float* edges);
+
 /* --------------------------------------------- A7/A9/A11 reductions and normalisation
  * Scalar results: `out` points to nb doubles (one per volume of the batch). */
 VX_API int32_t vx_volume(vx_ctx ctx, vx_img a, double* out);

@@ -285,6 +285,24 @@ def test_percentiles(ctx, oracle, shape):
     assert np.all(empty == 0)
 
 
+@pytest.mark.parametrize("lo,hi,note", [(0.5, 0.5, "all keys equal: 0 sort passes"),
+                                        (1.0, 1.0000305, "8 significant bits: 1 pass"),
+                                        (1.0, 1.01, "17 bits: 2 passes"),
+                                        (0.1, 1.0, "26 bits: 3 passes (the GTV case)"),
+                                        (-3.0, 1.0e6, "mixed signs, many octaves: 4 passes")])
+def test_percentiles_key_ranges(ctx, oracle, lo, hi, note):
+    """the radix sort only sorts the bits in which the keys differ (device-side pass count)"""
+    rng = np.random.default_rng(33)
+    shape = (2, 10, 30, 48)
+    a = (lo + (hi - lo) * rng.random(shape)).astype(np.float32)
+    a[0, 0, 0, :2] = [lo, hi]
+    m = rnd_mask(shape, 0.8, 34)
+    m[0, 0, 0, :2] = 1
+    got = ctx.percentiles(ctx.upload(a), ctx.upload(m), 0.0).numpy()
+    want = per_volume(oracle.percentiles, a, m, correction=0.0)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), note
+
+
 # ------------------------------------------------------------------ cross correlation
 @pytest.mark.parametrize("shape,rho,k", [((2, 9, 20, 48), 2.0, 10), ((1, 7, 13, 37), 3.0, 100),
                                          ((1, 1, 33, 70), 5.0, 16), ((1, 12, 70, 40), 5.0, 100)])

@@ -106,3 +106,123 @@ def test_nifti_and_png_roundtrip(tmp_path):
     assert np.array_equal(vio.read_png(str(tmp_path / "maze.png")), img)
     ch = vio.load_image(str(tmp_path / "maze.png"))
     assert set(ch) == {"red", "green", "blue"} and ch["red"][0].shape == (1,) + img.shape[:2]
+
+
+class _FakeImage:
+    pass
+
+
+def test_pointwise_fusion_compiles_correct_programs():
+    """The lazy pointwise DAG of the ImgQL driver must compile to vx_fused_pointwise programs that
+    compute what the operator-by-operator evaluation computes (checked with a numpy interpreter of
+    the register machine of include/voxcuda.h standing in for the device)."""
+    from voxlogica_b200 import _abi as A
+    from voxlogica_b200 import imgql
+    from voxlogica_b200.ops import Image
+
+    class FakeImage(Image):
+        __slots__ = ("arr",)
+        _next = [1]
+
+        def __init__(self, arr):
+            self.ctx, self.handle, self.arr = None, FakeImage._next[0], arr
+            FakeImage._next[0] += 1
+
+        def __del__(self):
+            pass
+
+        dtype = property(lambda self: self.arr.dtype.type)
+        nb = property(lambda self: self.arr.shape[0])
+        shape = property(lambda self: self.arr.shape)
+
+        def numpy(self):
+            return self.arr
+
+    launches = []
+    CMP = [np.less, np.less_equal, np.greater, np.greater_equal, np.equal, np.not_equal]
+    AR = [np.add, np.subtract, np.multiply, np.divide, lambda x, y: y - x, lambda x, y: y / x, np.minimum, np.maximum]
+
+    class FakeCtx:
+        def fused(self, prog, leaves, bs):
+            assert len(prog) <= A.VXP_MAX_OPS and len(leaves) <= A.VXP_MAX_LEAVES
+            launches.append(len(prog))
+            R = {}
+            for opc, dst, a, b, aux, imm in prog:
+                assert 0 <= dst < A.VXP_MAX_REGS
+                if opc == A.VXP_LOAD: R[dst] = leaves[a].arr
+                elif opc == A.VXP_NOT: R[dst] = (1 - R[a]).astype(np.uint8)
+                elif opc == A.VXP_AND: R[dst] = R[a] & R[b]
+                elif opc == A.VXP_OR: R[dst] = R[a] | R[b]
+                elif opc == A.VXP_CMPS: R[dst] = CMP[aux](R[a], np.float32(imm)).astype(np.uint8)
+                elif opc == A.VXP_CMPSB: R[dst] = CMP[aux](R[a], bs[b][:, None, None, None]).astype(np.uint8)
+                elif opc == A.VXP_CMP: R[dst] = CMP[aux](R[a], R[b]).astype(np.uint8)
+                elif opc == A.VXP_ARITHS: R[dst] = AR[aux](R[a], np.float32(imm)).astype(np.float32)
+                elif opc == A.VXP_ARITH: R[dst] = AR[aux](R[a], R[b]).astype(np.float32)
+                elif opc == A.VXP_SELECT: R[dst] = np.where(R[a] != 0, R[b], np.float32(imm)).astype(np.float32)
+                else: raise AssertionError(opc)
+                last = dst
+            return FakeImage(R[last])
+
+    rng = np.random.default_rng(0)
+    shp = (2, 3, 4, 5)
+    x, y = rng.random(shp, dtype=np.float32), rng.random(shp, dtype=np.float32)
+    m = (rng.random(shp) < 0.5).astype(np.uint8)
+    it = imgql.Interpreter(FakeCtx(), loader=lambda n: {"x": FakeImage(x), "y": FakeImage(y), "m": FakeImage(m)}[n])
+    it.run("""
+        load x = "x"
+        load y = "y"
+        load m = "m"
+        let a = (x >. 0.3) & !(y <. 0.6) | m
+        let b = mask((x + y) * 2 - 1 / (y + 1), a & (x <. y))
+        let c = a & a
+        let wide = ((x >. 0.1) & (x >. 0.2) & (x >. 0.3) & (x >. 0.4) & (x >. 0.5) & (x >. 0.6) & (x >. 0.7) & (x >. 0.8)) | ((y >. 0.1) & (y >. 0.2) & (y >. 0.3) & (y >. 0.4) & (y >. 0.5) & (y >. 0.6) & (y >. 0.7) & (y >. 0.8)) | ((y <. 0.15) & (x <. 0.25) & !m)
+    """)
+    g = it.globals
+    a_want = (((x > np.float32(0.3)) & ~(y < np.float32(0.6))) | (m != 0)).astype(np.uint8)
+    assert np.array_equal(g["a"].numpy(), a_want)
+    assert launches == [len(launches) and launches[0]] and launches[0] <= 10       # ONE program for the whole chain
+    t = ((x + y) * np.float32(2) - (np.float32(1) / (y + np.float32(1)))).astype(np.float32)
+    b_want = np.where((a_want != 0) & (x < y), t, np.float32(0))
+    assert np.array_equal(g["b"].numpy(), b_want)
+    assert np.array_equal(g["c"].numpy(), a_want)
+    wide = np.zeros(shp, bool) | (x > np.float32(0.8)) | (y > np.float32(0.8)) | ((y < np.float32(0.15)) & (x < np.float32(0.25)) & (m == 0))
+    assert np.array_equal(g["wide"].numpy(), wide.astype(np.uint8))
+    # unfused evaluation is still available
+    it2 = imgql.Interpreter(FakeCtx(), fuse=False)
+    assert it2.fuse is False
+
+
+def test_xcorr_bin_edges_reproduce_the_binning_exactly():
+    """The CUDA kernels bin with a host-computed table of break points instead of one binary64
+    division per voxel; the table must reproduce bin_of (oracle/vx_oracle.c) for EVERY float."""
+    import ctypes as C
+    from voxlogica_b200 import _abi
+    lib = _abi.load_library()
+    rng = np.random.default_rng(5)
+
+    def oracle_bin(v, m, M, k):
+        dv = v.astype(np.float64)
+        t = ((dv - m) * k) / (M - m)
+        with np.errstate(invalid="ignore"):
+            i = np.minimum(t.astype(np.int64), k - 1)
+        return np.where((dv >= m) & (dv < M), i, k)
+
+    cases = [(0.0, 1.0, 100), (0.1, 0.9, 32), (-3.7, 12.25, 254), (1e-3, 1.0000001e-3, 7), (0.0, 0.97265625, 100),
+             (5.0, 5.0, 10), (2.0, 1.0, 10), (-1e30, 1e30, 3), (0.0, 1e-40, 5)]
+    for m, M, k in cases:
+        e = (C.c_float * (k + 1))()
+        assert lib.vx_xcorr_bin_edges(m, M, k, e) == 0
+        e = np.frombuffer(e, dtype=np.float32)
+        if not M > m:
+            assert np.all(np.isinf(e))
+            continue
+        assert np.all(e[1:].astype(np.float64) >= e[:-1].astype(np.float64))
+        lo, hi = np.float32(m), np.float32(M)
+        span = float(hi) - float(lo)
+        v = np.concatenate([
+            rng.uniform(float(lo) - 0.1 * abs(span) - 1e-30, float(hi) + 0.1 * abs(span) + 1e-30, 200000).astype(np.float32),
+            e, np.nextafter(e, np.float32(-np.inf)), np.nextafter(e, np.float32(np.inf)),
+            np.array([0.0, -0.0, np.inf, -np.inf, lo, hi], dtype=np.float32)])
+        got = np.searchsorted(e[1:k].astype(np.float64), v.astype(np.float64), side="right")
+        got = np.where((v >= e[0]) & (v < e[k]), got, k)
+        assert np.array_equal(got, oracle_bin(v, m, M, k)), (m, M, k)

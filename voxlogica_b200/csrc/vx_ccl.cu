@@ -6,11 +6,12 @@
 //
 // Algorithm (B200-first; not the OpenCL branch's ~29 relabelling sweeps, p.78).
 // Everything after the first pass works on 32-voxel bit words, one THREAD per word:
-//   1. init     one warp per row: ballot the foreground into bit words and create the
-//               "anchors" of every x-run: the run start (parent = itself) and, where a
-//               run crosses a word boundary, the first voxel of the next word (parent =
-//               run start).  Only anchors ever get a parent entry, so the label array is
-//               written sparsely (a few entries per word instead of 32);
+//   1. init     pack the foreground into bit words (128-bit loads) and create the "anchors"
+//               of every x-run: the run start (parent = itself) and, where a run crosses a
+//               word boundary, the first voxel of the next word (parent = the anchor of the
+//               run's segment in the previous word; lanes trade their words by shuffle).
+//               Only anchors ever get a parent entry, so the label array is written
+//               sparsely (a few entries per word instead of 32);
 //   2. merge    per word, contacts with the backward neighbour rows ((y-1,z), (y-1,z-1),
 //               (y,z-1), (y+1,z-1) for 26-adjacency; (y-1,z), (y,z-1) for 6) are found
 //               with bit operations on the neighbour words; one union per place where a
@@ -117,35 +118,36 @@ __device__ __forceinline__ WordPos word_pos(const Geo& g) {
     return p;
 }
 
-// ---- 1. init: one warp per row ------------------------------------------------------------
+// ---- 1. init: one thread per word ----------------------------------------------------------
+// 32 voxels are read with two 128-bit loads and packed to a bit word; the anchors of the word
+// get their first parents: a run start points at itself, bit 0 of a run that continues from
+// the previous word points at that word's last segment (a chain of at most nwx links along a
+// row, removed by the first find).  The previous word's bits come from the neighbouring lane.
+__device__ __forceinline__ unsigned load_bits32(const uint8_t* __restrict__ src, int nx, int x0);
+
 __global__ void __launch_bounds__(kCclThreads)
-ccl_init_kernel(const uint8_t* __restrict__ img, unsigned* __restrict__ L,
+ccl_init_kernel(const uint8_t* __restrict__ img, unsigned* __restrict__ Lall,
                 unsigned* __restrict__ bits, Geo g) {
-    const unsigned long long row = ((unsigned long long)blockIdx.x * kCclThreads + threadIdx.x) >> 5;
-    if (row >= g.rows) return;  // whole warp
-    const int lane = threadIdx.x & 31;
-    const unsigned long long rv = row % ((unsigned long long)g.nz * g.ny);  // row inside its volume
-    const size_t gbase = (size_t)row * g.nx;       // global offset of the row
-    const unsigned lbase = (unsigned)(rv * g.nx);  // linear index of x = 0 inside the volume
-    int carry = -1;  // x where the run reaching into this word started, -1 if none
-    for (int w = 0; w < g.nwx; w++) {
-        const int x = w * 32 + lane;
-        const bool fg = x < g.nx && img[gbase + x] != 0;
-        const unsigned m = __ballot_sync(0xffffffffu, fg);
-        if (lane == 0) bits[row * g.nwx + w] = m;
-        if (fg) {
-            const bool left = lane > 0 ? ((m >> (lane - 1)) & 1u) : (carry >= 0);
-            if (!left) L[gbase + x] = lbase + (unsigned)x;               // run start
-            else if (lane == 0) L[gbase + x] = lbase + (unsigned)carry;  // word-boundary anchor
-        }
-        if (m >> 31) {
-            const int ones = __clz(~m);  // leading ones (32 when the word is full)
-            if (ones < 32) carry = w * 32 + 32 - ones;
-            else if (carry < 0) carry = w * 32;
-        } else {
-            carry = -1;
-        }
+    const WordPos p = word_pos(g);
+    unsigned m = 0;
+    if (p.ok) {
+        m = load_bits32(img + p.row * g.nx + (size_t)p.w * 32, g.nx, p.w * 32);
+        bits[p.wid] = m;
     }
+    unsigned prev_m = __shfl_up_sync(0xffffffffu, m, 1);
+    if (!p.ok) return;
+    if (p.w == 0) prev_m = 0;
+    else if ((threadIdx.x & 31) == 0)
+        prev_m = load_bits32(img + p.row * g.nx + (size_t)(p.w - 1) * 32, g.nx, (p.w - 1) * 32);
+    if (m == 0) return;
+    unsigned* L = Lall + (size_t)p.vol * g.nvox;
+    unsigned starts = m & ~((m << 1) | (prev_m >> 31));
+    while (starts) {
+        const int j = __ffs(starts) - 1;
+        starts &= starts - 1;
+        L[p.lin0 + j] = p.lin0 + j;
+    }
+    if ((m & 1u) && (prev_m >> 31)) L[p.lin0] = p.lin0 - 32 + seg_start(prev_m, 31);
 }
 
 // ---- 2. merge: one thread per word ----------------------------------------------------------
@@ -410,15 +412,14 @@ static int ccl_label(OpGuard& og, const Image* B, bool full, unsigned** L_out, u
                      Geo* geo, unsigned* grid_out) {
     Geo g = make_geo(B);
     unsigned long long blocks = (g.nwords + kCclThreads - 1) / kCclThreads;
-    unsigned long long iblocks = (g.rows * 32 + kCclThreads - 1) / kCclThreads;
-    VX_REQUIRE(iblocks < 0x7fffffffull, VX_E_UNSUPPORTED, "batch too large for one launch");
+    VX_REQUIRE(blocks < 0x7fffffffull, VX_E_UNSUPPORTED, "batch too large for one launch");
     unsigned grid = (unsigned)blocks;
     unsigned *L = nullptr, *bits = nullptr;
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * B->count(), (void**)&L));
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * g.nwords, (void**)&bits));
     {
         VX_LAUNCH(og.c, og.s, "ccl_init_kernel");
-        ccl_init_kernel<<<(unsigned)iblocks, kCclThreads, 0, og.st>>>((const uint8_t*)B->d, L, bits, g);
+        ccl_init_kernel<<<grid, kCclThreads, 0, og.st>>>((const uint8_t*)B->d, L, bits, g);
     }
     VX_TRY(check_launch("ccl_init_kernel"));
     {

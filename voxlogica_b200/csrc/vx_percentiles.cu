@@ -8,10 +8,14 @@
 // Device algorithm, per volume of the batch and with no host round trip:
 //   1. compact the masked voxels into packed (sortable key << 32 | voxel index) pairs
 //      (block-aggregated: one atomicAdd per 4096 voxels);
-//   2. stable LSD radix sort of the pairs, 4 passes of 8 bits.  The unit of work is a
-//      warp-owned chunk of 2048 keys: digits are ranked inside the warp with
-//      match.any, running offsets live in warp-private shared memory, so no block
-//      barrier and no atomics are needed inside a pass;
+//   2. stable LSD radix sort of the pairs with 9-bit digits.  Only the bits in which the
+//      keys of the batch actually differ are sorted: the compaction records min and max key,
+//      a one-thread kernel turns their xor into the number of passes (3 for intensities
+//      within a few octaves, 4 at most), and the kernels of the remaining passes exit at
+//      once -- all decided on the device, the host never waits.  The unit of work is a
+//      warp-owned chunk of 2048 keys: digits are ranked inside the warp with match.any,
+//      running offsets live in warp-private shared memory, so no block barrier and no
+//      atomics are needed inside a pass;
 //   3. every sorted position finds the start of its run of equal keys (its rank) and
 //      scatters the normalised rank back to its voxel.
 #include "vx_internal.h"
@@ -21,6 +25,10 @@ namespace vx {
 constexpr int kPcThreads = 256;
 constexpr int kWarpChunk = 2048;                 // keys owned by one warp in a sort pass
 constexpr int kRounds = kWarpChunk / 32;
+constexpr int kRadixBits = 9;
+constexpr int kDigits = 1 << kRadixBits;         // 512
+constexpr int kMaxPasses = (32 + kRadixBits - 1) / kRadixBits;   // 4
+// plan[0] = number of passes to run, plan[1] = min key, plan[2] = max key (whole batch)
 
 __device__ __forceinline__ unsigned sortable_key(float v) {
     v = v + 0.0f;  // -0.0 -> +0.0 so that both zeros get the same rank
@@ -34,9 +42,11 @@ __device__ __forceinline__ unsigned sortable_key(float v) {
 // grid (blocks, nb).  Each block walks tiles of 256*16 voxels of its volume.
 __global__ void __launch_bounds__(kPcThreads)
 pc_compact_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mask, size_t nvox,
-                  unsigned long long* __restrict__ pairs, unsigned* __restrict__ count) {
+                  unsigned long long* __restrict__ pairs, unsigned* __restrict__ count,
+                  unsigned* __restrict__ plan) {
     __shared__ unsigned warp_tot[kPcThreads / 32];
     __shared__ unsigned tile_base;
+    unsigned kmin = 0xffffffffu, kmax = 0u;
     const size_t vol = blockIdx.y;
     const float* a = img + vol * nvox;
     const uint8_t* m = mask + vol * nvox;
@@ -90,27 +100,47 @@ pc_compact_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mas
 #pragma unroll
         for (int e = 0; e < 16; e++) {
             if ((bits >> e) & 1u) {
-                po[pos] = ((unsigned long long)sortable_key(v[e]) << 32) | (unsigned)(first + e);
+                const unsigned key = sortable_key(v[e]);
+                kmin = min(kmin, key);
+                kmax = max(kmax, key);
+                po[pos] = ((unsigned long long)key << 32) | (unsigned)(first + e);
                 pos++;
             }
         }
         __syncthreads();  // tile_base / warp_tot reuse
     }
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    if (lane == 0 && kmin <= kmax) {
+        atomicMin(plan + 1, kmin);
+        atomicMax(plan + 2, kmax);
+    }
+}
+
+__global__ void rs_plan_kernel(unsigned* __restrict__ plan) {
+    const unsigned kmin = plan[1], kmax = plan[2];
+    unsigned bits = 0;
+    if (kmin <= kmax && kmin != kmax) bits = 32u - (unsigned)__clz(kmin ^ kmax);
+    plan[0] = (bits + kRadixBits - 1) / kRadixBits;   // 0 when every key is the same
 }
 
 // ---- 2. radix sort passes --------------------------------------------------------------
 // table layout: [vol][digit][chunk]  (chunk-major inside a digit so the scan is one sweep)
 __global__ void __launch_bounds__(kPcThreads)
-rs_hist_kernel(const unsigned long long* __restrict__ pairs, const unsigned* __restrict__ count, size_t nvox,
-               unsigned* __restrict__ table, int nchunks_max, int shift) {
-    __shared__ unsigned cnt[kPcThreads / 32][256];
+rs_hist_kernel(const unsigned long long* __restrict__ buf0, const unsigned long long* __restrict__ buf1,
+               const unsigned* __restrict__ count, size_t nvox, unsigned* __restrict__ table, int nchunks_max,
+               int pass, const unsigned* __restrict__ plan) {
+    __shared__ unsigned cnt[kPcThreads / 32][kDigits];
+    if ((unsigned)pass >= plan[0]) return;
+    const unsigned long long* pairs = (pass & 1) ? buf1 : buf0;
+    const int shift = pass * kRadixBits;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t vol = blockIdx.y;
     const unsigned n = count[vol];
     const unsigned chunk = blockIdx.x * (kPcThreads / 32) + warp;
     const unsigned nchunks = (n + kWarpChunk - 1) / kWarpChunk;
     if (chunk >= nchunks) return;
-    for (int d = lane; d < 256; d += 32) cnt[warp][d] = 0;
+    for (int d = lane; d < kDigits; d += 32) cnt[warp][d] = 0;
     __syncwarp();
     const unsigned long long* k = pairs + vol * nvox;
     const unsigned base = chunk * kWarpChunk;
@@ -119,29 +149,30 @@ rs_hist_kernel(const unsigned long long* __restrict__ pairs, const unsigned* __r
         bool ok = p < n;
         unsigned active = __ballot_sync(0xffffffffu, ok);
         if (ok) {
-            unsigned d = (unsigned)(k[p] >> (32 + shift)) & 0xffu;
+            unsigned d = ((unsigned)(k[p] >> 32) >> shift) & (kDigits - 1);
             unsigned peers = __match_any_sync(active, d);
             if ((peers & ((1u << lane) - 1u)) == 0) cnt[warp][d] += __popc(peers);
         }
         __syncwarp();
     }
-    unsigned* tab = table + (vol * 256) * (size_t)nchunks_max;
-    for (int d = lane; d < 256; d += 32) tab[(size_t)d * nchunks_max + chunk] = cnt[warp][d];
+    unsigned* tab = table + (vol * kDigits) * (size_t)nchunks_max;
+    for (int d = lane; d < kDigits; d += 32) tab[(size_t)d * nchunks_max + chunk] = cnt[warp][d];
 }
 
-// grid (256, nb): block (d, vol) turns row d of the table (one count per chunk) into an
+// grid (kDigits, nb): block (d, vol) turns row d of the table (one count per chunk) into an
 // exclusive prefix over chunks and records the row total; the digit bases are then a
 // 256-entry scan that every scatter warp does for itself.
 __global__ void __launch_bounds__(256)
 rs_rowscan_kernel(const unsigned* __restrict__ count, unsigned* __restrict__ table,
-                  unsigned* __restrict__ totals, int nchunks_max) {
+                  unsigned* __restrict__ totals, int nchunks_max, int pass, const unsigned* __restrict__ plan) {
     __shared__ unsigned wsum[8];
     __shared__ unsigned carry_s;
+    if ((unsigned)pass >= plan[0]) return;
     const size_t vol = blockIdx.y;
     const unsigned d = blockIdx.x;
     const unsigned n = count[vol];
     const unsigned nchunks = (n + kWarpChunk - 1) / kWarpChunk;
-    unsigned* row = table + (vol * 256 + d) * (size_t)nchunks_max;
+    unsigned* row = table + (vol * kDigits + d) * (size_t)nchunks_max;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
@@ -169,26 +200,31 @@ rs_rowscan_kernel(const unsigned* __restrict__ count, unsigned* __restrict__ tab
         if (threadIdx.x == 0) carry_s = carry + tot;
         __syncthreads();
     }
-    if (threadIdx.x == 0) totals[vol * 256 + d] = carry_s;
+    if (threadIdx.x == 0) totals[vol * kDigits + d] = carry_s;
 }
 
 __global__ void __launch_bounds__(kPcThreads)
-rs_scatter_kernel(const unsigned long long* __restrict__ pairs_in, unsigned long long* __restrict__ pairs_out,
+rs_scatter_kernel(unsigned long long* __restrict__ buf0, unsigned long long* __restrict__ buf1,
                   const unsigned* __restrict__ count, size_t nvox, const unsigned* __restrict__ table,
-                  const unsigned* __restrict__ totals, int nchunks_max, int shift) {
-    __shared__ unsigned off[kPcThreads / 32][256];
+                  const unsigned* __restrict__ totals, int nchunks_max, int pass, const unsigned* __restrict__ plan) {
+    __shared__ unsigned off[kPcThreads / 32][kDigits];
+    if ((unsigned)pass >= plan[0]) return;
+    const unsigned long long* pairs_in = (pass & 1) ? buf1 : buf0;
+    unsigned long long* pairs_out = (pass & 1) ? buf0 : buf1;
+    const int shift = pass * kRadixBits;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t vol = blockIdx.y;
     const unsigned n = count[vol];
     const unsigned chunk = blockIdx.x * (kPcThreads / 32) + warp;
     const unsigned nchunks = (n + kWarpChunk - 1) / kWarpChunk;
     if (chunk >= nchunks) return;
-    const unsigned* tab = table + (vol * 256) * (size_t)nchunks_max;
-    {   // digit bases: exclusive scan of the 256 row totals, 8 digits per lane
-        const unsigned* tot = totals + vol * 256;
-        unsigned t[8], sum = 0;
+    const unsigned* tab = table + (vol * kDigits) * (size_t)nchunks_max;
+    {   // digit bases: exclusive scan of the row totals, kDigits/32 digits per lane
+        constexpr int PL = kDigits / 32;
+        const unsigned* tot = totals + vol * kDigits;
+        unsigned t[PL], sum = 0;
 #pragma unroll
-        for (int j = 0; j < 8; j++) { t[j] = tot[lane * 8 + j]; sum += t[j]; }
+        for (int j = 0; j < PL; j++) { t[j] = tot[lane * PL + j]; sum += t[j]; }
         unsigned incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -197,8 +233,8 @@ rs_scatter_kernel(const unsigned long long* __restrict__ pairs_in, unsigned long
         }
         unsigned base = incl - sum;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int d = lane * 8 + j;
+        for (int j = 0; j < PL; j++) {
+            const int d = lane * PL + j;
             off[warp][d] = base + tab[(size_t)d * nchunks_max + chunk];
             base += t[j];
         }
@@ -213,7 +249,7 @@ rs_scatter_kernel(const unsigned long long* __restrict__ pairs_in, unsigned long
         unsigned active = __ballot_sync(0xffffffffu, ok);
         if (ok) {
             const unsigned long long kv = pi[p];
-            unsigned d = (unsigned)(kv >> (32 + shift)) & 0xffu;
+            unsigned d = ((unsigned)(kv >> 32) >> shift) & (kDigits - 1);
             unsigned peers = __match_any_sync(active, d);
             unsigned rank = __popc(peers & ((1u << lane) - 1u));
             int leader = __ffs(peers) - 1;
@@ -231,8 +267,10 @@ rs_scatter_kernel(const unsigned long long* __restrict__ pairs_in, unsigned long
 
 // ---- 3. ranks ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(kPcThreads)
-pc_rank_kernel(const unsigned long long* __restrict__ pairs, const unsigned* __restrict__ count,
-               size_t nvox, float* __restrict__ out, double correction) {
+pc_rank_kernel(const unsigned long long* __restrict__ buf0, const unsigned long long* __restrict__ buf1,
+               const unsigned* __restrict__ count, size_t nvox, float* __restrict__ out, double correction,
+               const unsigned* __restrict__ plan) {
+    const unsigned long long* pairs = (plan[0] & 1u) ? buf1 : buf0;   // where the last pass wrote
     const size_t vol = blockIdx.y;
     const unsigned n = count[vol];
     const unsigned long long* k = pairs + vol * nvox;
@@ -283,13 +321,15 @@ extern "C" int32_t vx_percentiles(vx_ctx ctx, vx_img a, vx_img mask, double corr
     const int nb = A->nb;
     const int nchunks_max = (int)((nvox + kWarpChunk - 1) / kWarpChunk);
     unsigned long long* buf = nullptr;
-    unsigned *count = nullptr, *table = nullptr, *totals = nullptr;
+    unsigned *count = nullptr, *table = nullptr, *totals = nullptr, *plan = nullptr;
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned long long) * total * 2, (void**)&buf));
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * nb, (void**)&count));
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (size_t)nb * 256 * nchunks_max, (void**)&table));
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (size_t)nb * 256, (void**)&totals));
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (nb + 4), (void**)&count));
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (size_t)nb * kDigits * nchunks_max, (void**)&table));
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (size_t)nb * kDigits, (void**)&totals));
     unsigned long long *k0 = buf, *k1 = buf + total;
-    VX_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned) * nb, og.st));
+    plan = count + nb;   // {passes, min key, max key}
+    VX_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned) * (nb + 4), og.st));
+    VX_CUDA(cudaMemsetAsync(plan + 1, 0xff, sizeof(unsigned), og.st));
     Image* O = nullptr;
     VX_TRY(new_image(og.c, VX_F32, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
     int rc = VX_OK;
@@ -300,31 +340,34 @@ extern "C" int32_t vx_percentiles(vx_ctx ctx, vx_img a, vx_img mask, double corr
         int cap = (kNumSMs * 8 + nb - 1) / nb;
         dim3 grid(per_vol < cap ? per_vol : cap, nb);
         { VX_LAUNCH(og.c, og.s, "pc_compact_kernel");
-          pc_compact_kernel<<<grid, kPcThreads, 0, og.st>>>((const float*)A->d, (const uint8_t*)M->d, nvox, k0, count); }
+          pc_compact_kernel<<<grid, kPcThreads, 0, og.st>>>((const float*)A->d, (const uint8_t*)M->d, nvox, k0, count, plan); }
         rc = check_launch("pc_compact_kernel");
     }
+    if (rc == VX_OK) {
+        { VX_LAUNCH(og.c, og.s, "rs_plan_kernel");
+          rs_plan_kernel<<<1, 1, 0, og.st>>>(plan); }
+        rc = check_launch("rs_plan_kernel");
+    }
     dim3 sgrid((nchunks_max + kPcThreads / 32 - 1) / (kPcThreads / 32), nb);
-    for (int pass = 0; pass < 4 && rc == VX_OK; pass++) {
-        const int shift = pass * 8;
+    for (int pass = 0; pass < kMaxPasses && rc == VX_OK; pass++) {
         { VX_LAUNCH(og.c, og.s, "rs_hist_kernel");
-          rs_hist_kernel<<<sgrid, kPcThreads, 0, og.st>>>(k0, count, nvox, table, nchunks_max, shift); }
+          rs_hist_kernel<<<sgrid, kPcThreads, 0, og.st>>>(k0, k1, count, nvox, table, nchunks_max, pass, plan); }
         rc = check_launch("rs_hist_kernel");
         if (rc != VX_OK) break;
         { VX_LAUNCH(og.c, og.s, "rs_rowscan_kernel");
-          rs_rowscan_kernel<<<dim3(256, nb), 256, 0, og.st>>>(count, table, totals, nchunks_max); }
+          rs_rowscan_kernel<<<dim3(kDigits, nb), 256, 0, og.st>>>(count, table, totals, nchunks_max, pass, plan); }
         rc = check_launch("rs_rowscan_kernel");
         if (rc != VX_OK) break;
         { VX_LAUNCH(og.c, og.s, "rs_scatter_kernel");
-          rs_scatter_kernel<<<sgrid, kPcThreads, 0, og.st>>>(k0, k1, count, nvox, table, totals, nchunks_max, shift); }
+          rs_scatter_kernel<<<sgrid, kPcThreads, 0, og.st>>>(k0, k1, count, nvox, table, totals, nchunks_max, pass, plan); }
         rc = check_launch("rs_scatter_kernel");
-        unsigned long long* t = k0; k0 = k1; k1 = t;
     }
     if (rc == VX_OK) {
         int per_vol = (int)((nvox + kPcThreads - 1) / kPcThreads);
         int cap = (kNumSMs * 8 + nb - 1) / nb;
         dim3 grid(per_vol < cap ? per_vol : cap, nb);
         { VX_LAUNCH(og.c, og.s, "pc_rank_kernel");
-          pc_rank_kernel<<<grid, kPcThreads, 0, og.st>>>(k0, count, nvox, (float*)O->d, correction); }
+          pc_rank_kernel<<<grid, kPcThreads, 0, og.st>>>(k0, k1, count, nvox, (float*)O->d, correction, plan); }
         rc = check_launch("pc_rank_kernel");
     }
     if (rc == VX_OK) rc = scratch_free(og.c, og.s, buf);

@@ -18,6 +18,7 @@
 // 162 instead of 515 for rho = 5), maintaining S11 and n1 incrementally
 // (+-(2h+1)).  P is a k-term dot product against h2 (broadcast reads).
 #include <math.h>
+#include <string.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -44,33 +45,94 @@ __host__ __device__ __forceinline__ int xc_bin_of(float v, double m, double M, i
     return i;
 }
 
-// grid (blocks, nb)
-__global__ void __launch_bounds__(256)
-xc_bin_kernel(const float* __restrict__ a, uint8_t* __restrict__ bins, size_t nvox,
-              const double* __restrict__ mM, int nb, int k) {
-    const size_t vol = blockIdx.y;
-    const double m = mM[vol], M = mM[nb + vol];
-    const float* src = a + vol * nvox;
-    uint8_t* dst = bins + vol * nvox;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvox; i += (size_t)gridDim.x * 256)
-        dst[i] = (uint8_t)xc_bin_of(src[i], m, M, k);
+// Binning without a binary64 division per voxel.  bin_of is monotone in v, so it is fully
+// described by its k+1 break points edge[i] = smallest binary32 whose bin is >= i (edge[0]:
+// smallest value >= m, edge[k]: smallest value >= M).  The host finds them with xc_bin_of
+// itself (a few evaluations per edge), the kernels then need one float guess and a couple
+// of float compares per voxel -- and produce exactly xc_bin_of(v) for every v.
+constexpr int kEdgeStride = 256;   // floats per volume in the edge table (k + 1 <= 255 used)
+
+__device__ __forceinline__ unsigned bin_from_edges(float v, const float* __restrict__ e, int k, float inv_w) {
+    if (!(v >= e[0]) || !(v < e[k])) return (unsigned)k;   // outside [m, M) or NaN: the dummy bin
+    int g = (int)((v - e[0]) * inv_w);
+    g = g < 0 ? 0 : (g > k - 1 ? k - 1 : g);
+    while (g > 0 && v < e[g]) g--;
+    while (g < k - 1 && v >= e[g + 1]) g++;
+    return (unsigned)g;
 }
 
-// histogram of b over region: grid (blocks, nb), h2 is [nb][256] (zeroed by the caller)
+// grid (blocks, nb): 16 voxels per thread (4 x float4 in, one uint4 out) when nvox % 16 == 0
 __global__ void __launch_bounds__(256)
-xc_region_hist_kernel(const float* __restrict__ b, const uint8_t* __restrict__ region, size_t nvox,
-                      const double* __restrict__ mM, int nb, int k, unsigned* __restrict__ h2) {
-    __shared__ unsigned sh[256];
-    sh[threadIdx.x] = 0;
-    __syncthreads();
+xc_bin_kernel(const float* __restrict__ a, uint8_t* __restrict__ bins, size_t nvox,
+              const float* __restrict__ edges, int k) {
+    __shared__ float e[kEdgeStride];
     const size_t vol = blockIdx.y;
-    const double m = mM[vol], M = mM[nb + vol];
-    const float* src = b + vol * nvox;
+    for (int i = threadIdx.x; i <= k; i += 256) e[i] = edges[vol * kEdgeStride + i];
+    __syncthreads();
+    const float inv_w = (e[k] > e[0]) ? (float)k / (e[k] - e[0]) : 0.0f;
+    const float* src = a + vol * nvox;
+    uint8_t* dst = bins + vol * nvox;
+    if ((nvox & 15) == 0) {
+        const size_t ng = nvox >> 4;
+        for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < ng; g += (size_t)gridDim.x * 256) {
+            const float4* p = reinterpret_cast<const float4*>(src) + g * 4;
+            unsigned w[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float4 f = __ldg(p + q);
+                w[q] = bin_from_edges(f.x, e, k, inv_w) | (bin_from_edges(f.y, e, k, inv_w) << 8) |
+                       (bin_from_edges(f.z, e, k, inv_w) << 16) | (bin_from_edges(f.w, e, k, inv_w) << 24);
+            }
+            reinterpret_cast<uint4*>(dst)[g] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    } else {
+        for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvox; i += (size_t)gridDim.x * 256)
+            dst[i] = (uint8_t)bin_from_edges(src[i], e, k, inv_w);
+    }
+}
+
+// histogram of b over region: grid (blocks, nb), h2 is [nb][256] (zeroed by the caller).
+// BINNED: `b` already holds u8 bins (b is the image that was binned for the sliding pass).
+template <bool BINNED>
+__global__ void __launch_bounds__(256)
+xc_region_hist_kernel(const void* __restrict__ b_, const uint8_t* __restrict__ region, size_t nvox,
+                      const float* __restrict__ edges, int k, unsigned* __restrict__ h2) {
+    __shared__ unsigned sh[256];
+    __shared__ float e[kEdgeStride];
+    sh[threadIdx.x] = 0;
+    const size_t vol = blockIdx.y;
+    for (int i = threadIdx.x; i <= k; i += 256) e[i] = edges[vol * kEdgeStride + i];
+    __syncthreads();
+    const float inv_w = (e[k] > e[0]) ? (float)k / (e[k] - e[0]) : 0.0f;
     const uint8_t* reg = region + vol * nvox;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvox; i += (size_t)gridDim.x * 256) {
-        if (reg[i] == 0) continue;
-        int bin = xc_bin_of(src[i], m, M, k);
-        if (bin < k) atomicAdd(&sh[bin], 1u);
+    if ((nvox & 15) == 0) {
+        const size_t ng = nvox >> 4;
+        for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < ng; g += (size_t)gridDim.x * 256) {
+            const uint4 r = __ldg(reinterpret_cast<const uint4*>(reg) + g);
+            if ((r.x | r.y | r.z | r.w) == 0) continue;    // regions are small: most groups are empty
+            const unsigned rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (rw[q] == 0) continue;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (((rw[q] >> (8 * j)) & 0xffu) == 0) continue;
+                    const size_t i = (g << 4) + 4 * q + j;
+                    unsigned bin;
+                    if (BINNED) bin = reinterpret_cast<const uint8_t*>(b_)[vol * nvox + i];
+                    else bin = bin_from_edges(reinterpret_cast<const float*>(b_)[vol * nvox + i], e, k, inv_w);
+                    if (bin < (unsigned)k) atomicAdd(&sh[bin], 1u);
+                }
+            }
+        }
+    } else {
+        for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvox; i += (size_t)gridDim.x * 256) {
+            if (reg[i] == 0) continue;
+            unsigned bin;
+            if (BINNED) bin = reinterpret_cast<const uint8_t*>(b_)[vol * nvox + i];
+            else bin = bin_from_edges(reinterpret_cast<const float*>(b_)[vol * nvox + i], e, k, inv_w);
+            if (bin < (unsigned)k) atomicAdd(&sh[bin], 1u);
+        }
     }
     __syncthreads();
     if (sh[threadIdx.x]) atomicAdd(h2 + vol * 256 + threadIdx.x, sh[threadIdx.x]);
@@ -527,31 +589,132 @@ static bool build_columns(const float sp[3], float rho, std::vector<unsigned>* c
     return true;
 }
 
-// Shared back end: bins of A, statistics of the given region histogram d_h2 ([nb][256] u32 on
-// the device, already final) and the sliding-ball kernel.  Frees d_mM and d_h2.
-static int xcorr_run(OpGuard& og, Image* A, double* d_mM, unsigned* d_h2, float rho, int32_t k, vx_img* out) {
+// ---- host: exact break points of xc_bin_of --------------------------------------------------
+static unsigned fkey(float f) {
+    unsigned u;
+    memcpy(&u, &f, 4);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+static float fromkey(unsigned key) {
+    unsigned u = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+// edge[i] (i = 0..k) = smallest binary32 v with  v >= m  and ( v >= M  or  xc_bin_of(v) >= i )
+static void compute_edges(double m, double M, int k, float* e) {
+    if (!(M > m)) {   // empty or NaN range: nothing is ever counted
+        for (int i = 0; i <= k; i++) e[i] = INFINITY;
+        return;
+    }
+    auto pred = [&](unsigned key, int i) {
+        const float v = fromkey(key);
+        const double dv = (double)v;
+        if (!(dv >= m)) return false;
+        if (!(dv < M)) return true;
+        return xc_bin_of(v, m, M, k) >= i;
+    };
+    const unsigned kmin = fkey(-INFINITY), kmax = fkey(INFINITY);
+    for (int i = 0; i <= k; i++) {
+        // analytic guess, then gallop in units of ulps to bracket the break point, then bisect
+        double guess = m + (M - m) * ((double)i / (double)k);
+        float gf = (float)guess;
+        if (!(gf == gf)) gf = 0.0f;
+        unsigned lo, hi, c = fkey(gf);
+        if (c < kmin) c = kmin;
+        if (c > kmax) c = kmax;
+        if (pred(c, i)) {   // answer <= c: walk down until pred fails
+            hi = c;
+            unsigned step = 1;
+            lo = c;
+            while (true) {
+                if (lo - kmin <= step) { lo = kmin; if (pred(lo, i)) { hi = lo; } break; }
+                lo -= step;
+                if (!pred(lo, i)) break;
+                hi = lo;
+                step <<= 1;
+            }
+            if (hi == kmin) { e[i] = fromkey(hi); continue; }
+        } else {            // answer > c
+            lo = c;
+            unsigned step = 1;
+            hi = c;
+            while (true) {
+                if (kmax - hi <= step) { hi = kmax; break; }
+                hi += step;
+                if (pred(hi, i)) break;
+                lo = hi;
+                step <<= 1;
+            }
+        }
+        // invariant: pred(lo) false, pred(hi) true (pred(+inf) is always true)
+        while (hi - lo > 1) {
+            const unsigned mid = lo + (hi - lo) / 2;
+            if (pred(mid, i)) hi = mid; else lo = mid;
+        }
+        e[i] = fromkey(hi);
+    }
+}
+
+static int upload_edges(OpGuard& og, int nb, const double* m, const double* M, int k, float** d_edges) {
+    std::vector<float> e((size_t)nb * kEdgeStride, INFINITY);
+    for (int v = 0; v < nb; v++) {
+        if (v > 0 && m[v] == m[v - 1] && M[v] == M[v - 1])
+            memcpy(&e[(size_t)v * kEdgeStride], &e[(size_t)(v - 1) * kEdgeStride], sizeof(float) * kEdgeStride);
+        else
+            compute_edges(m[v], M[v], k, &e[(size_t)v * kEdgeStride]);
+    }
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(float) * e.size(), (void**)d_edges));
+    // pageable source: staged by the runtime before the call returns
+    VX_CUDA(cudaMemcpyAsync(*d_edges, e.data(), sizeof(float) * e.size(), cudaMemcpyHostToDevice, og.st));
+    return VX_OK;
+}
+
+static dim3 stream_grid(size_t nvox, int nb) {
+    int per_vol = (int)((nvox + 256 * 16 - 1) / (256 * 16));
+    int cap = (kNumSMs * 8 + nb - 1) / nb;
+    return dim3(per_vol < cap ? per_vol : (cap < 1 ? 1 : cap), nb);
+}
+
+// u8 bins of A (dummy bin k for values that are not counted)
+static int xcorr_bins(OpGuard& og, Image* A, const float* d_edges, int32_t k, uint8_t** d_bins) {
+    VX_TRY(scratch_alloc(og.c, og.s, A->count(), (void**)d_bins));
+    {
+        VX_LAUNCH(og.c, og.s, "xc_bin_kernel");
+        xc_bin_kernel<<<stream_grid(A->nvox(), A->nb), 256, 0, og.st>>>((const float*)A->d, *d_bins, A->nvox(), d_edges, k);
+    }
+    return check_launch("xc_bin_kernel");
+}
+
+// h2 of `src` (f32 values, or u8 bins when binned) over region R into d_h2 ([nb][256] u32)
+static int region_hist(OpGuard& og, const void* src, bool binned, Image* R, const float* d_edges, int32_t k,
+                       unsigned* d_h2) {
+    const int nb = R->nb;
+    const size_t nvox = R->nvox();
+    VX_CUDA(cudaMemsetAsync(d_h2, 0, sizeof(unsigned) * 256 * nb, og.st));
+    {
+        VX_LAUNCH(og.c, og.s, "xc_region_hist_kernel");
+        if (binned)
+            xc_region_hist_kernel<true><<<stream_grid(nvox, nb), 256, 0, og.st>>>(src, (const uint8_t*)R->d, nvox, d_edges, k, d_h2);
+        else
+            xc_region_hist_kernel<false><<<stream_grid(nvox, nb), 256, 0, og.st>>>(src, (const uint8_t*)R->d, nvox, d_edges, k, d_h2);
+    }
+    return check_launch("xc_region_hist_kernel");
+}
+
+// Shared back end: statistics of the region histogram d_h2 ([nb][256] u32 on the device, final)
+// and the sliding-ball kernel over the bins.  Frees d_bins, d_edges and d_h2.
+static int xcorr_run(OpGuard& og, Image* A, uint8_t* d_bins, float* d_edges, unsigned* d_h2, float rho, int32_t k,
+                     vx_img* out) {
     std::vector<unsigned> cols;
     long long ball = 0;
     VX_REQUIRE(build_columns(A->sp, rho, &cols, &ball) && ball <= 65535 && cols.size() <= 8192,
                VX_E_UNSUPPORTED, "radius %g is too large for the sliding-histogram kernel", (double)rho);
     const int nb = A->nb;
-    const size_t nvox = A->nvox(), total = A->count();
-    uint8_t* d_bins = nullptr;
     unsigned* d_cols = nullptr;
     long long* d_vstat = nullptr;
-    VX_TRY(scratch_alloc(og.c, og.s, total, (void**)&d_bins));
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(long long) * 2 * nb, (void**)&d_vstat));
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (cols.size() + 128), (void**)&d_cols));
-    if (!cols.empty())
-        VX_CUDA(cudaMemcpyAsync(d_cols, cols.data(), sizeof(unsigned) * cols.size(), cudaMemcpyHostToDevice, og.st));
-    int per_vol = (int)((nvox + 256 * 8 - 1) / (256 * 8));
-    int cap = (kNumSMs * 8 + nb - 1) / nb;
-    dim3 sgrid(per_vol < cap ? per_vol : cap, nb);
-    {
-        VX_LAUNCH(og.c, og.s, "xc_bin_kernel");
-        xc_bin_kernel<<<sgrid, 256, 0, og.st>>>((const float*)A->d, d_bins, nvox, d_mM, nb, k);
-    }
-    VX_TRY(check_launch("xc_bin_kernel"));
     {
         VX_LAUNCH(og.c, og.s, "xc_stat_kernel");
         xc_stat_kernel<<<nb, 1, 0, og.st>>>(d_h2, k, d_vstat);
@@ -615,6 +778,8 @@ static int xcorr_run(OpGuard& og, Image* A, double* d_mM, unsigned* d_h2, float 
         XcGeo g;
         g.nx = A->nx; g.ny = A->ny; g.nz = A->nz; g.k = k;
         g.ncols = (int)cols.size();
+        if (!cols.empty())
+            VX_CUDA(cudaMemcpyAsync(d_cols, cols.data(), sizeof(unsigned) * cols.size(), cudaMemcpyHostToDevice, og.st));
         g.nw = nw; g.seg = seg; g.nseg = nseg;
         size_t smem = sizeof(unsigned) * ((size_t)g.nw * kXcThreads + 2 * g.nw + g.ncols);
         if (smem > 48 * 1024) {
@@ -630,7 +795,7 @@ static int xcorr_run(OpGuard& og, Image* A, double* d_mM, unsigned* d_h2, float 
             rc = check_launch("xcorr_direct_kernel");
         }
     }
-    if (rc == VX_OK) rc = scratch_free(og.c, og.s, d_mM);
+    if (rc == VX_OK) rc = scratch_free(og.c, og.s, d_edges);
     if (rc == VX_OK) rc = scratch_free(og.c, og.s, d_bins);
     if (rc == VX_OK) rc = scratch_free(og.c, og.s, d_h2);
     if (rc == VX_OK) rc = scratch_free(og.c, og.s, d_vstat);
@@ -643,28 +808,6 @@ static int xcorr_run(OpGuard& og, Image* A, double* d_mM, unsigned* d_h2, float 
 
 
 using namespace vx;
-
-// h2 of b over region into d_h2 ([nb][256] u32, zeroed here)
-static int region_hist(OpGuard& og, Image* B, Image* R, const double* d_mM, int32_t k, unsigned* d_h2) {
-    const int nb = B->nb;
-    const size_t nvox = B->nvox();
-    VX_CUDA(cudaMemsetAsync(d_h2, 0, sizeof(unsigned) * 256 * nb, og.st));
-    int per_vol = (int)((nvox + 256 * 8 - 1) / (256 * 8));
-    int cap = (kNumSMs * 8 + nb - 1) / nb;
-    dim3 sgrid(per_vol < cap ? per_vol : cap, nb);
-    {
-        VX_LAUNCH(og.c, og.s, "xc_region_hist_kernel");
-        xc_region_hist_kernel<<<sgrid, 256, 0, og.st>>>((const float*)B->d, (const uint8_t*)R->d, nvox, d_mM, nb, k, d_h2);
-    }
-    return check_launch("xc_region_hist_kernel");
-}
-
-static int upload_mM(OpGuard& og, int nb, const double* m, const double* M, double** d_mM) {
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(double) * 2 * nb, (void**)d_mM));
-    VX_CUDA(cudaMemcpyAsync(*d_mM, m, sizeof(double) * nb, cudaMemcpyHostToDevice, og.st));
-    VX_CUDA(cudaMemcpyAsync(*d_mM + nb, M, sizeof(double) * nb, cudaMemcpyHostToDevice, og.st));
-    return VX_OK;
-}
 
 extern "C" int32_t vx_cross_correlation(vx_ctx ctx, vx_img a, vx_img b, vx_img region, float rho,
                                         const double* m, const double* M, int32_t k, vx_img* out) {
@@ -680,12 +823,16 @@ extern "C" int32_t vx_cross_correlation(vx_ctx ctx, vx_img a, vx_img b, vx_img r
     VX_TRY(og.input(region, &R, VX_U8));
     VX_TRY(same_shape(A, B));
     VX_TRY(same_shape(A, R));
-    double* d_mM = nullptr;
+    float* d_edges = nullptr;
     unsigned* d_h2 = nullptr;
-    VX_TRY(upload_mM(og, A->nb, m, M, &d_mM));
+    uint8_t* d_bins = nullptr;
+    VX_TRY(upload_edges(og, A->nb, m, M, k, &d_edges));
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * 256 * A->nb, (void**)&d_h2));
-    VX_TRY(region_hist(og, B, R, d_mM, k, d_h2));
-    return xcorr_run(og, A, d_mM, d_h2, rho, k, out);
+    VX_TRY(xcorr_bins(og, A, d_edges, k, &d_bins));
+    // similarTo(a) correlates an image with itself: its bins are already there
+    if (A == B) VX_TRY(region_hist(og, d_bins, true, R, d_edges, k, d_h2));
+    else VX_TRY(region_hist(og, B->d, false, R, d_edges, k, d_h2));
+    return xcorr_run(og, A, d_bins, d_edges, d_h2, rho, k, out);
 }
 
 extern "C" int32_t vx_region_histogram(vx_ctx ctx, vx_img b, vx_img region, const double* m,
@@ -700,17 +847,17 @@ extern "C" int32_t vx_region_histogram(vx_ctx ctx, vx_img b, vx_img region, cons
     VX_TRY(og.input(region, &R, VX_U8));
     VX_TRY(same_shape(B, R));
     const int nb = B->nb;
-    double* d_mM = nullptr;
+    float* d_edges = nullptr;
     unsigned* d_h2 = nullptr;
-    VX_TRY(upload_mM(og, nb, m, M, &d_mM));
+    VX_TRY(upload_edges(og, nb, m, M, k, &d_edges));
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * 256 * nb, (void**)&d_h2));
-    VX_TRY(region_hist(og, B, R, d_mM, k, d_h2));
+    VX_TRY(region_hist(og, B->d, false, R, d_edges, k, d_h2));
     std::vector<unsigned> host((size_t)256 * nb);
     VX_CUDA(cudaMemcpyAsync(host.data(), d_h2, sizeof(unsigned) * 256 * nb, cudaMemcpyDeviceToHost, og.st));
     VX_CUDA(cudaStreamSynchronize(og.st));
     for (int v = 0; v < nb; v++)
         for (int i = 0; i < k; i++) h2[(size_t)v * k + i] = host[(size_t)v * 256 + i];
-    VX_TRY(scratch_free(og.c, og.s, d_mM));
+    VX_TRY(scratch_free(og.c, og.s, d_edges));
     VX_TRY(scratch_free(og.c, og.s, d_h2));
     return og.finish_scalar();
 }
@@ -734,11 +881,24 @@ extern "C" int32_t vx_cross_correlation_h2(vx_ctx ctx, vx_img a, const uint64_t*
                        (unsigned long long)c);
             host[(size_t)v * 256 + i] = (unsigned)c;
         }
-    double* d_mM = nullptr;
+    float* d_edges = nullptr;
     unsigned* d_h2 = nullptr;
-    VX_TRY(upload_mM(og, nb, m, M, &d_mM));
+    uint8_t* d_bins = nullptr;
+    VX_TRY(upload_edges(og, nb, m, M, k, &d_edges));
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * 256 * nb, (void**)&d_h2));
     // pageable source: cudaMemcpyAsync stages it before returning, `host` may die afterwards
     VX_CUDA(cudaMemcpyAsync(d_h2, host.data(), sizeof(unsigned) * 256 * nb, cudaMemcpyHostToDevice, og.st));
-    return xcorr_run(og, A, d_mM, d_h2, rho, k, out);
+    VX_TRY(xcorr_bins(og, A, d_edges, k, &d_bins));
+    return xcorr_run(og, A, d_bins, d_edges, d_h2, rho, k, out);
+}
+
+// Host-only helper (no device needed): the k+1 break points of the crossCorrelation binning for
+// one (m, M), as used by the kernels.  Exposed so the exactness of the table can be tested on
+// a machine without a GPU.
+extern "C" int32_t vx_xcorr_bin_edges(double m, double M, int32_t k, float* edges) {
+    VX_REQUIRE(edges != nullptr, VX_E_INVALID_ARG, "edges is NULL");
+    VX_REQUIRE(k >= 1 && k <= kXcMaxBins, VX_E_UNSUPPORTED, "k = %d bins; supported range is [1,%d]", k,
+               kXcMaxBins);
+    compute_edges(m, M, k, edges);
+    return VX_OK;
 }

@@ -215,6 +215,169 @@ class Parser:
         raise SyntaxError(f"ImgQL: unexpected token {s!r}")
 
 
+# ---------------------------------------------------------------------------- pointwise fusion
+# "boolean and intensity pointwise chains ... fused along the DAG" (BASELINE.json north_star):
+# pointwise operators do not run when they are applied; they build a Lazy node.  When a
+# non-pointwise operator (or save / print / numpy()) needs the value, the whole pending sub-DAG
+# is compiled into ONE vx_fused_pointwise program: leaf images are read once, the root is
+# written once, intermediates stay in registers / shared memory.
+_B, _F = "b", "f"
+
+
+class Lazy:
+    """A pending pointwise expression over HBM-resident leaves."""
+
+    __slots__ = ("ctx", "op", "args", "aux", "imm", "kind", "_img", "__weakref__")
+
+    def __init__(self, ctx, op, args, kind, aux=0, imm=0.0):
+        self.ctx, self.op, self.args, self.kind, self.aux, self.imm = ctx, op, tuple(args), kind, aux, imm
+        self._img = None
+
+    # -- the Image protocol used by the evaluator, the tests and the bench
+    def force(self) -> Image:
+        if self._img is None:
+            try:
+                self._img = _compile_and_run(self)
+            except _FusionLimit:
+                for a in self.args:       # too wide for one program: materialise the operands
+                    force(a)
+                self._img = _compile_and_run(self)
+            self.args = ()            # drop the sub-DAG: its leaves may be freed now
+        return self._img
+
+    def numpy(self):
+        return self.force().numpy()
+
+    @property
+    def handle(self):
+        return self.force().handle
+
+    @property
+    def nb(self):
+        return _first_leaf(self).nb
+
+    @property
+    def shape(self):
+        return _first_leaf(self).shape
+
+    @property
+    def spacing(self):
+        return _first_leaf(self).spacing
+
+
+class _FusionLimit(RuntimeError):
+    pass
+
+
+def _first_leaf(v):
+    while isinstance(v, Lazy):
+        if v._img is not None:
+            return v._img
+        v = next(a for a in v.args if isinstance(a, (Lazy, Image)))
+    return v
+
+
+def force(v):
+    """Lazy -> Image (anything else is returned unchanged)"""
+    return v.force() if isinstance(v, Lazy) else v
+
+
+def _count_ops(v, seen) -> int:
+    if not isinstance(v, Lazy) or v._img is not None or id(v) in seen:
+        return 0
+    seen.add(id(v))
+    return 1 + sum(_count_ops(a, seen) for a in v.args)
+
+
+def _compile_and_run(root: "Lazy") -> Image:
+    from . import _abi as A
+    ctx = root.ctx
+    # keep programs inside the limits of the register machine: materialise big operands first
+    while True:
+        leaves, seen = {}, set()
+
+        def scan(v):
+            if isinstance(v, Lazy) and v._img is None:
+                if id(v) not in seen:
+                    seen.add(id(v))
+                    for a in v.args:
+                        scan(a)
+            elif isinstance(v, (Lazy, Image)):
+                leaves[force(v).handle] = force(v)
+        scan(root)
+        if len(leaves) <= A.VXP_MAX_LEAVES and len(seen) + len(leaves) <= A.VXP_MAX_OPS - 4 and len(seen) <= 40:
+            break
+        big = max((a for a in root.args if isinstance(a, Lazy) and a._img is None),
+                  key=lambda a: _count_ops(a, set()), default=None)
+        if big is None:
+            raise _FusionLimit("pointwise expression does not fit the fusion limits")
+        big.force()
+    leaf_idx = {h: i for i, h in enumerate(leaves)}
+    leaf_imgs = list(leaves.values())
+    # post-order emission with use counts for register reuse
+    uses = {}
+
+    def count(v):
+        if isinstance(v, Lazy) and v._img is None:
+            uses[id(v)] = uses.get(id(v), 0) + 1
+            if uses[id(v)] == 1:
+                for a in v.args:
+                    count(a)
+        elif isinstance(v, (Lazy, Image)):
+            h = force(v).handle
+            uses[("leaf", h)] = uses.get(("leaf", h), 0) + 1
+    count(root)
+    prog, reg_of, free = [], {}, list(range(A.VXP_MAX_REGS - 1, -1, -1))
+    scalars = []
+
+    def release(key):
+        uses[key] -= 1
+        if uses[key] == 0:
+            free.append(reg_of.pop(key))
+
+    def emit(v):
+        if isinstance(v, Lazy) and v._img is None:
+            key = id(v)
+            if key in reg_of:
+                return key
+            keys = [emit(a) for a in v.args if isinstance(a, (Lazy, Image))]
+            regs = [reg_of[k] for k in keys]
+            for k in keys:
+                release(k)
+            if not free:
+                raise _FusionLimit("out of fusion registers")
+            dst = free.pop()
+            a = regs[0] if regs else 0
+            b = regs[1] if len(regs) > 1 else 0
+            opcode, aux, imm = v.op, v.aux, v.imm
+            if opcode in (A.VXP_CMPSB, A.VXP_ARITHSB):
+                b = len(scalars)
+                scalars.append(np.asarray(v.imm, dtype=np.float32))
+                imm = 0.0
+            prog.append((opcode, dst, a, b, int(aux), float(imm)))
+            reg_of[key] = dst
+            return key
+        h = force(v).handle
+        key = ("leaf", h)
+        if key not in reg_of:
+            if not free:
+                raise _FusionLimit("out of fusion registers")
+            dst = free.pop()
+            prog.append((A.VXP_LOAD, dst, leaf_idx[h], 0, 0, 0.0))
+            reg_of[key] = dst
+        return key
+    try:
+        emit(root)
+    finally:
+        # the recursive closures above refer to themselves through their own cells: clear them,
+        # otherwise the leaf images stay alive until Python's cyclic collector happens to run
+        # (and their HBM blocks miss the allocator's free lists for the next batch)
+        scan = count = emit = release = None
+        leaves.clear(); uses.clear(); reg_of.clear()
+    bs = np.stack(scalars) if scalars else None
+    return ctx.fused(prog, leaf_imgs, bs)
+
+
 # ---------------------------------------------------------------------------- evaluator
 class Number:
     """An ImgQL number: one value per volume of the batch."""
@@ -239,12 +402,14 @@ class Loaded:
 
 
 def _is_img(v):
-    return isinstance(v, Image)
+    return isinstance(v, (Image, Lazy))
 
 
 class Interpreter:
-    def __init__(self, ctx: Context, loader: Optional[Callable[[str], Image]] = None, conn: int = 26):
+    def __init__(self, ctx: Context, loader: Optional[Callable[[str], Image]] = None, conn: int = 26,
+                 fuse: bool = True):
         self.ctx = ctx
+        self.fuse = fuse                     # build Lazy nodes for pointwise operators
         self.loader = loader
         self.saver = None                    # optional callable(path, Image) run by `save`
         self.conn = conn                     # adjacency of near/through
@@ -257,9 +422,33 @@ class Interpreter:
         self.n_tasks = 0                     # operator calls actually executed
 
     # -- program level
+    _SCALAR_FNS = ("min", "max", "volume")
+
+    def _hoist_scalars(self, stmts):
+        """The reference's scheduler runs independent tasks in parallel, so a global reduction of
+        a LOADED image (min/max of the input, needed later as histogram range) is computed at
+        the start, not where the spec text happens to mention it.  This pre-pass finds such
+        calls (arguments built only from loaded images and `intensity`/channel selectors) and
+        evaluates them right away; the memo then serves the later uses.  Evaluating them late
+        would drain the CUDA stream in the middle of the pipeline just to read one number."""
+        loaded = {k for k, v in self.globals.items() if isinstance(v, (Image, Loaded))}
+        found = []
+        for st in stmts:
+            if st[0] == "let":
+                _find_hoistable(st[3], loaded, self._SCALAR_FNS, found)
+            elif st[0] in ("save", "print"):
+                _find_hoistable(st[2], loaded, self._SCALAR_FNS, found)
+        for e in found:
+            self.eval(e, {})
+
     def run(self, src: str):
-        for st in Parser(src).program():
+        stmts = Parser(src).program()
+        hoisted = False
+        for i, st in enumerate(stmts):
             kind = st[0]
+            if not hoisted and kind not in ("import", "load"):
+                self._hoist_scalars(stmts[i:])
+                hoisted = True
             if kind == "import":
                 if st[1].endswith("stdlib.imgql"):
                     self.run(STDLIB)
@@ -280,7 +469,7 @@ class Interpreter:
                 else:
                     self.functions[name] = (params, body)
             elif kind == "save":
-                self.saved[st[1]] = self.eval(st[2], {})
+                self.saved[st[1]] = force(self.eval(st[2], {}))
                 if self.saver is not None:
                     self.saver(st[1], self.saved[st[1]])
             elif kind == "print":
@@ -338,9 +527,12 @@ class Interpreter:
         if fn.startswith("infix:"):
             return self._infix(fn[6:], a[0], a[1])
         if fn == "prefix:!":
-            return c.not_(a[0])
+            return self._pw_not(a[0])
         if fn == "neg":
-            return Number(-a[0].v) if isinstance(a[0], Number) else c.arith_scalar(a[0], "r-", 0.0)
+            return Number(-a[0].v) if isinstance(a[0], Number) else self._pw_arith_scalar(a[0], "r-", 0.0)
+        if fn == "mask":
+            return self._pw_mask(a[0], a[1])
+        a = [force(x) for x in a]     # every other operator needs materialised operands
         table = {
             "intensity": self._intensity,
             "red": lambda x: x.channel("red"),
@@ -364,7 +556,6 @@ class Interpreter:
             "min": lambda x: Number(c.min(x)),
             "max": lambda x: Number(c.max(x)),
             "constant": lambda v: c.constant(self._like(), v.v[0]),
-            "mask": lambda x, m: c.mask(x, m, 0.0),
             "percentiles": lambda x, m, corr=None: c.percentiles(x, m, 0.0 if corr is None else corr.v[0]),
             "crossCorrelation": lambda rho, x, y, reg, m, M, k: c.cross_correlation(
                 rho.v[0], x, y, reg, m.v, M.v, int(k.v[0])),
@@ -379,45 +570,111 @@ class Interpreter:
             return x
         if "intensity" in x.channels:
             return x.channels["intensity"]
-        c = self.ctx
         r, g, b = (x.channel(n) for n in ("red", "green", "blue"))
-        return c.arith(c.arith(c.arith_scalar(r, "*", 0.2126), "+", c.arith_scalar(g, "*", 0.7152)), "+",
-                       c.arith_scalar(b, "*", 0.0722))
+        return self._pw_arith(self._pw_arith(self._pw_arith_scalar(r, "*", 0.2126), "+",
+                                             self._pw_arith_scalar(g, "*", 0.7152)), "+",
+                              self._pw_arith_scalar(b, "*", 0.0722))
+
+    # -- pointwise constructors: Lazy nodes when fusing, direct calls otherwise
+    def _pw_not(self, x):
+        from . import _abi as A
+        if not self.fuse:
+            return self.ctx.not_(force(x))
+        return Lazy(self.ctx, A.VXP_NOT, [x], _B)
+
+    def _pw_bool(self, core, l, r):
+        from . import _abi as A
+        if not self.fuse:
+            return self.ctx.and_(force(l), force(r)) if core == "&" else self.ctx.or_(force(l), force(r))
+        return Lazy(self.ctx, A.VXP_AND if core == "&" else A.VXP_OR, [l, r], _B)
+
+    def _pw_cmp_scalar(self, x, k, s):
+        from . import _abi as A
+        from .ops import _CMP
+        if not self.fuse:
+            return self.ctx.cmp_scalar(force(x), k, s)
+        if np.ndim(s) == 0:
+            return Lazy(self.ctx, A.VXP_CMPS, [x], _B, _CMP[k], float(s))
+        return Lazy(self.ctx, A.VXP_CMPSB, [x], _B, _CMP[k], np.broadcast_to(np.asarray(s, np.float32), (x.nb,)))
+
+    def _pw_cmp(self, l, k, r):
+        from . import _abi as A
+        from .ops import _CMP
+        if not self.fuse:
+            return self.ctx.cmp(force(l), k, force(r))
+        return Lazy(self.ctx, A.VXP_CMP, [l, r], _B, _CMP[k])
+
+    def _pw_arith_scalar(self, x, op, s):
+        from . import _abi as A
+        from .ops import _ARITH
+        if not self.fuse:
+            return self.ctx.arith_scalar(force(x), op, s)
+        if np.ndim(s) == 0:
+            return Lazy(self.ctx, A.VXP_ARITHS, [x], _F, _ARITH[op], float(s))
+        return Lazy(self.ctx, A.VXP_ARITHSB, [x], _F, _ARITH[op], np.broadcast_to(np.asarray(s, np.float32), (x.nb,)))
+
+    def _pw_arith(self, l, op, r):
+        from . import _abi as A
+        from .ops import _ARITH
+        if not self.fuse:
+            return self.ctx.arith(force(l), op, force(r))
+        return Lazy(self.ctx, A.VXP_ARITH, [l, r], _F, _ARITH[op])
+
+    def _pw_mask(self, x, m):
+        from . import _abi as A
+        if not self.fuse:
+            return self.ctx.mask(force(x), force(m), 0.0)
+        return Lazy(self.ctx, A.VXP_SELECT, [m, x], _F, 0, 0.0)
 
     def _infix(self, op, l, r):
-        c = self.ctx
         core = op.strip(".")
         cmp_map = {"<": "<", "<=": "<=", ">": ">", ">=": ">=", "=": "==", "==": "==", "!=": "!="}
         swap = {"<": ">", "<=": ">=", ">": "<", ">=": "<=", "==": "==", "!=": "!="}
         if core in ("&", "|"):
-            return c.and_(l, r) if core == "&" else c.or_(l, r)
+            return self._pw_bool(core, l, r)
         li, ri = _is_img(l), _is_img(r)
         scal = lambda n: n.v[0] if n.v.size == 1 else n.v
         if core in cmp_map:
             k = cmp_map[core]
             if li and ri:
-                return c.cmp(l, k, r)
+                return self._pw_cmp(l, k, r)
             if li:
-                return c.cmp_scalar(l, k, scal(r))
+                return self._pw_cmp_scalar(l, k, scal(r))
             if ri:
-                return c.cmp_scalar(r, swap[k], scal(l))
+                return self._pw_cmp_scalar(r, swap[k], scal(l))
             return Number({"<": np.less, "<=": np.less_equal, ">": np.greater, ">=": np.greater_equal,
                            "==": np.equal, "!=": np.not_equal}[k](l.v, r.v).astype(np.float64))
         if core in ("+", "-", "*", "/"):
             if li and ri:
-                return c.arith(l, core, r)
+                return self._pw_arith(l, core, r)
             if li:
-                return c.arith_scalar(l, core, scal(r))
+                return self._pw_arith_scalar(l, core, scal(r))
             if ri:
                 rop = {"+": "+", "*": "*", "-": "r-", "/": "r/"}[core]
-                return c.arith_scalar(r, rop, scal(l))
+                return self._pw_arith_scalar(r, rop, scal(l))
             return Number({"+": np.add, "-": np.subtract, "*": np.multiply, "/": np.divide}[core](l.v, r.v))
         raise NameError(f"ImgQL: unknown infix operator {op!r}")
 
 
-def run_spec(ctx: Context, src: str, images: Dict[str, Image], conn: int = 26) -> Interpreter:
+def _closed_over_loads(e, loaded) -> bool:
+    if isinstance(e, Var):
+        return e.name in loaded
+    if isinstance(e, Call):
+        return e.fn in ("intensity", "red", "green", "blue", "alpha") and all(_closed_over_loads(a, loaded) for a in e.args)
+    return False
+
+
+def _find_hoistable(e, loaded, fns, found) -> None:
+    if isinstance(e, Call):
+        if e.fn in fns and len(e.args) == 1 and _closed_over_loads(e.args[0], loaded) and e not in found:
+            found.append(e)
+        for a in e.args:
+            _find_hoistable(a, loaded, fns, found)
+
+
+def run_spec(ctx: Context, src: str, images: Dict[str, Image], conn: int = 26, fuse: bool = True) -> Interpreter:
     """Run an ImgQL spec whose `load` statements name entries of ``images``."""
-    it = Interpreter(ctx, loader=lambda name: images[name], conn=conn)
+    it = Interpreter(ctx, loader=lambda name: images[name], conn=conn, fuse=fuse)
     return it.run(src)
 
 
