@@ -17,23 +17,36 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def blob_slab(shape, z0, z1, seed=7, coarse=24):
-    """thresholded band-limited noise, generated per slab (deterministic in the global z)"""
+def blob_slab(shape, z0, z1, device, seed=7, coarse=24):
+    """planes [z0, z1) of a thresholded band-limited noise volume, generated on the GPU (torch is
+    plumbing here: trilinear upsampling of a coarse seeded grid that is identical on all ranks)"""
+    import torch
+    import torch.nn.functional as F
     nz, ny, nx = shape
-    rng = np.random.default_rng(seed)
+    g = torch.Generator().manual_seed(seed)
     cz, cy, cx = nz // coarse + 2, ny // coarse + 2, nx // coarse + 2
-    c = rng.random((cz, cy, cx)).astype(np.float32)
-    from scipy import ndimage as ndi
-    zz = (np.arange(z0, z1, dtype=np.float32) + 0.5) / coarse
-    yy = (np.arange(ny, dtype=np.float32) + 0.5) / coarse
-    xx = (np.arange(nx, dtype=np.float32) + 0.5) / coarse
-    out = np.empty((z1 - z0, ny, nx), np.uint8)
-    step = 16
-    for s in range(0, z1 - z0, step):
-        g = np.meshgrid(zz[s:s + step], yy, xx, indexing="ij")
-        v = ndi.map_coordinates(c, [a.ravel() for a in g], order=1, mode="nearest").reshape(g[0].shape)
-        out[s:s + step] = v > 0.58
+    c = torch.rand((1, 1, cz, cy, cx), generator=g).to(device)
+    out = torch.empty((z1 - z0, ny, nx), dtype=torch.uint8, device=device)
+    ys = (torch.arange(ny, device=device, dtype=torch.float32) + 0.5) / (coarse * (cy - 1)) * 2 - 1
+    xs = (torch.arange(nx, device=device, dtype=torch.float32) + 0.5) / (coarse * (cx - 1)) * 2 - 1
+    step = 8
+    for s in range(z0, z1, step):
+        e = min(s + step, z1)
+        zs = (torch.arange(s, e, device=device, dtype=torch.float32) + 0.5) / (coarse * (cz - 1)) * 2 - 1
+        gz, gy, gx = torch.meshgrid(zs, ys, xs, indexing="ij")
+        grid = torch.stack([gx, gy, gz], dim=-1)[None]
+        v = F.grid_sample(c, grid, mode="bilinear", padding_mode="border", align_corners=True)[0, 0]
+        out[s - z0:e - z0] = (v > 0.58).to(torch.uint8)
     return out
+
+
+def _last_plane_mask(ops, B, rank, world, local):
+    import torch
+    nzl, ny, nx = B.data.shape[1:]
+    m = torch.zeros((nzl, ny, nx), dtype=torch.uint8, device=f"cuda:{local}")
+    if rank == world - 1:
+        m[-1] = 1
+    return m
 
 
 def main():
@@ -55,18 +68,19 @@ def main():
     shape = (n, n, n)
     z0, z1 = slab_bounds(n, world)[rank]
     sp = (1.0, 1.0, 1.0)
-    b_local = blob_slab(shape, z0, z1)
-    B = Slab(ctx.upload(b_local, spacing=sp), z0, z1, n, sp)
-    seed = np.zeros_like(b_local)
+    b_t = blob_slab(shape, z0, z1, f"cuda:{local}")
+    B = Slab(ctx.from_tensor(b_t[None], spacing=sp), z0, z1, n, sp)
+    seed_t = torch.zeros_like(b_t)
     if rank == 0:
-        seed[0] = b_local[0]                      # everything connected to the first plane
-    A = Slab(ctx.upload(seed, spacing=sp), z0, z1, n, sp)
+        seed_t[0] = b_t[0]                        # everything connected to the first plane
+    A = Slab(ctx.from_tensor(seed_t[None], spacing=sp), z0, z1, n, sp)
+    del seed_t
 
     if args.check:
         # gather the whole volume on every rank, run single-GPU, compare slabs
         parts = [torch.empty((slab_bounds(n, world)[r][1] - slab_bounds(n, world)[r][0], n, n), dtype=torch.uint8,
                              device=f"cuda:{local}") for r in range(world)]
-        dist.all_gather(parts, torch.as_tensor(b_local, device=f"cuda:{local}"))
+        dist.all_gather(parts, b_t)
         whole = torch.cat(parts).cpu().numpy()
         W = ctx.upload(whole, spacing=sp)
         wseed = np.zeros_like(whole); wseed[0] = whole[0]
@@ -102,6 +116,9 @@ def main():
         dist.destroy_process_group()
         sys.exit(0 if not any(flags) else 1)
 
+    del b_t
+    torch.cuda.empty_cache()
+
     def timed(fn):
         for _ in range(1):
             fn()
@@ -117,13 +134,19 @@ def main():
         return float(np.median(ts))
 
     res = {}
+    fg = ops.volume(B)
+    reach = {}
     for name, fn in (("near26", lambda: ops.near(B, 26)), ("through26", lambda: ops.through(A, B, 26)),
                      ("distlt5", lambda: ops.distlt(5.0, B)), ("flt2", lambda: ops.flt(2.0, B)),
                      ("volume", lambda: ops.volume(B))):
         s = timed(fn)
         res[name] = {"ms": round(1e3 * s, 3), "gvox_per_s": round(n ** 3 / s / 1e9, 2)}
+    reach["foreground_voxels"] = fg
+    reach["reached_from_first_plane"] = ops.volume(ops.through(A, B, 26))
+    reach["reached_last_plane"] = ops.volume(ops.and_(ops.through(A, B, 26), Slab(
+        ctx.from_tensor(_last_plane_mask(ops, B, rank, world, local)[None], spacing=sp), z0, z1, n, sp)))
     if rank == 0:
-        print(json.dumps({"slab_bench": {"size": n, "n_gpus": world, "voxels": n ** 3, "ops": res,
+        print(json.dumps({"slab_bench": {"size": n, "n_gpus": world, "voxels": n ** 3, "ops": res, "check": reach,
                                          "timing": "host clock around device-synchronised regions, max over ranks"}}),
               flush=True)
     dist.destroy_process_group()
