@@ -48,18 +48,21 @@ __device__ __forceinline__ unsigned find_root(const unsigned* L, unsigned x) {
     return x;
 }
 
+// find with path splitting: every node visited is re-pointed at its grandparent (atomicMin can
+// only replace a parent by an ancestor, so concurrent unions never lose a link).  Splitting
+// halves the path for every later find through these nodes; with min-index linking the
+// trees of a percolating component get deep, and compressing only the end points left
+// finds walking hundreds of L2-latency hops (ncu: long-scoreboard bound).
 __device__ __forceinline__ unsigned find_compress(unsigned* L, unsigned x) {
     unsigned p = __ldcg(L + x) & kIdx;
-    if (p == x) return x;
-    unsigned r = p, q = __ldcg(L + r) & kIdx;
-    if (q == r) return r;  // depth 1: nothing to compress
-    while (q != r) {
-        r = q;
-        q = __ldcg(L + r) & kIdx;
+    while (p != x) {
+        const unsigned gp = __ldcg(L + p) & kIdx;
+        if (gp == p) return p;
+        atomicMin(L + x, gp);
+        x = p;
+        p = gp;
     }
-    atomicMin(L + x, r);
-    atomicMin(L + p, r);
-    return r;
+    return x;
 }
 
 __device__ __forceinline__ void unite(unsigned* L, unsigned a, unsigned b) {
@@ -150,60 +153,95 @@ ccl_init_kernel(const uint8_t* __restrict__ img, unsigned* __restrict__ Lall,
     if ((m & 1u) && (prev_m >> 31)) L[p.lin0] = p.lin0 - 32 + seg_start(prev_m, 31);
 }
 
-// ---- 2. merge: one thread per word ----------------------------------------------------------
+// ---- 2. merge: one thread per word finds the contacts, the block unites them together -------
+// Finding contacts is bit arithmetic on a word and its backward neighbour rows; uniting is
+// pointer chasing through L2.  On noisy masks a word has tens of contacts: if each thread
+// united its own, a warp would crawl through them with 2-3 live lanes (ncu: 2.7 active
+// threads per instruction, long-scoreboard bound).  So contacts are first written as (a, b)
+// pairs into a block queue in shared memory, then all 256 threads drain the queue, one
+// union per lane: every lane of a warp has an independent chain of loads in flight.
+constexpr int kQCap = 4096;   // pairs per block and drain round (32 KB); overflow unites directly
+
 template <bool FULL>
 __global__ void __launch_bounds__(kCclThreads)
 ccl_merge_kernel(unsigned* __restrict__ Lall, const unsigned* __restrict__ bits, Geo g) {
+    __shared__ uint2 q[kQCap];
+    __shared__ unsigned qn;
     const WordPos p = word_pos(g);
-    if (!p.ok) return;
+    // volume of the block's first word; a block spans at most two volumes (bit 31 of a pair's
+    // first index says "the second one"; indices inside a volume are < 2^31)
+    const unsigned long long words_per_vol = (unsigned long long)g.nwx * g.ny * g.nz;
+    const unsigned vol0 = (unsigned)(((unsigned long long)blockIdx.x * kCclThreads) / words_per_vol);
+    if (threadIdx.x == 0) qn = 0;
+    __syncthreads();
     const unsigned* brow = bits + p.row * g.nwx;
-    const unsigned m = __ldg(brow + p.w);
-    if (m == 0) return;
-    const unsigned prev_m = p.w > 0 ? __ldg(brow + p.w - 1) : 0u;
+    const unsigned m = p.ok ? __ldg(brow + p.w) : 0u;
+    const unsigned prev_m = (p.ok && p.w > 0) ? __ldg(brow + p.w - 1) : 0u;
     const unsigned left = (m << 1) | (prev_m >> 31);  // bit j: voxel j-1 of the same row is set
+    const unsigned vtag = (p.vol != vol0) ? kFlag : 0u;
     unsigned* L = Lall + (size_t)p.vol * g.nvox;
+    const bool far_vol = p.vol > vol0 + 1;   // cannot happen while a volume has >= 256 words; then unite directly
 
     const int ndir = FULL ? 4 : 2;
     const int dys[4] = {-1, 0, -1, 1};
     const int dzs[4] = {0, -1, -1, -1};
+    for (int d0 = 0; d0 < ndir; d0 += 2) {
 #pragma unroll
-    for (int d = 0; d < ndir; d++) {
-        const int yy = p.y + dys[d], zz = p.z + dzs[d];
-        if (yy < 0 || yy >= g.ny || zz < 0) continue;
-        const long long drow = (long long)dzs[d] * g.ny + dys[d];
-        const unsigned* nrow = brow + drow * g.nwx;
-        const unsigned nc = __ldg(nrow + p.w);
-        const unsigned np = p.w > 0 ? __ldg(nrow + p.w - 1) : 0u;
-        const unsigned nn = (FULL && p.w + 1 < g.nwx) ? __ldg(nrow + p.w + 1) : 0u;
-        // neighbour bits relative to voxel j:  N0 = same x, Nm = x-1, Np = x+1
-        const unsigned N0 = nc;
-        const unsigned Nm = (nc << 1) | (np >> 31);
-        const unsigned Np = (nc >> 1) | (nn << 31);
-        const unsigned nlin0 = (unsigned)((long long)p.lin0 + drow * g.nx);  // neighbour word, bit 0
-        unsigned first, second;
-        if (FULL) {
-            first = m & Np & ~N0;             // a neighbour run begins at x+1 next to voxel x
-            second = m & ~left & (N0 | Nm);   // this run begins at x and touches x or x-1 below
-        } else {
-            first = 0;
-            second = m & N0 & ~(left & Nm);   // face contact that the voxel to the left did not see
+        for (int dd = 0; dd < 2; dd++) {
+            const int d = d0 + dd;
+            const int yy = p.y + dys[d], zz = p.z + dzs[d];
+            if (m == 0 || yy < 0 || yy >= g.ny || zz < 0) continue;
+            const long long drow = (long long)dzs[d] * g.ny + dys[d];
+            const unsigned* nrow = brow + drow * g.nwx;
+            const unsigned nc = __ldg(nrow + p.w);
+            const unsigned np = p.w > 0 ? __ldg(nrow + p.w - 1) : 0u;
+            const unsigned nn = (FULL && p.w + 1 < g.nwx) ? __ldg(nrow + p.w + 1) : 0u;
+            // neighbour bits relative to voxel j:  N0 = same x, Nm = x-1, Np = x+1
+            const unsigned N0 = nc;
+            const unsigned Nm = (nc << 1) | (np >> 31);
+            const unsigned Np = (nc >> 1) | (nn << 31);
+            const unsigned nlin0 = (unsigned)((long long)p.lin0 + drow * g.nx);  // neighbour word, bit 0
+            unsigned first, second;
+            if (FULL) {
+                first = m & Np & ~N0;             // a neighbour run begins at x+1 next to voxel x
+                second = m & ~left & (N0 | Nm);   // this run begins at x and touches x or x-1 below
+            } else {
+                first = 0;
+                second = m & N0 & ~(left & Nm);   // face contact that the voxel to the left did not see
+            }
+            const unsigned cnt = __popc(first) + __popc(second);
+            if (cnt == 0) continue;
+            unsigned slot = far_vol ? kQCap : atomicAdd(&qn, cnt);
+            while (first) {
+                const int j = __ffs(first) - 1;
+                first &= first - 1;
+                // the neighbour voxel x+1 starts its run, so it is an anchor itself (bit 0 of the
+                // next word when j == 31)
+                const unsigned a = p.lin0 + seg_start(m, j), b = nlin0 + j + 1;
+                if (slot < kQCap) q[slot++] = make_uint2(a | vtag, b);
+                else unite(L, a, b);
+            }
+            while (second) {
+                const int j = __ffs(second) - 1;
+                second &= second - 1;
+                unsigned b;
+                if ((N0 >> j) & 1u) b = nlin0 + seg_start(nc, j);
+                else if (j > 0) b = nlin0 + seg_start(nc, j - 1);
+                else b = nlin0 - 32 + seg_start(np, 31);
+                const unsigned a = p.lin0 + seg_start(m, j);
+                if (slot < kQCap) q[slot++] = make_uint2(a | vtag, b);
+                else unite(L, a, b);
+            }
         }
-        while (first) {
-            const int j = __ffs(first) - 1;
-            first &= first - 1;
-            // the neighbour voxel x+1 starts its run, so it is an anchor itself (bit 0 of the
-            // next word when j == 31)
-            unite(L, p.lin0 + seg_start(m, j), nlin0 + j + 1);
+        __syncthreads();
+        const unsigned n = qn < (unsigned)kQCap ? qn : (unsigned)kQCap;
+        for (unsigned i = threadIdx.x; i < n; i += kCclThreads) {
+            const uint2 e = q[i];
+            unite(Lall + (size_t)(vol0 + (e.x >> 31)) * g.nvox, e.x & kIdx, e.y);
         }
-        while (second) {
-            const int j = __ffs(second) - 1;
-            second &= second - 1;
-            unsigned b;
-            if ((N0 >> j) & 1u) b = nlin0 + seg_start(nc, j);
-            else if (j > 0) b = nlin0 + seg_start(nc, j - 1);
-            else b = nlin0 - 32 + seg_start(np, 31);
-            unite(L, p.lin0 + seg_start(m, j), b);
-        }
+        __syncthreads();
+        if (threadIdx.x == 0) qn = 0;
+        __syncthreads();
     }
 }
 

@@ -25,6 +25,7 @@ namespace vx {
 constexpr int kPcThreads = 256;
 constexpr int kWarpChunk = 2048;                 // keys owned by one warp in a sort pass
 constexpr int kRounds = kWarpChunk / 32;
+constexpr int kPrefetch = 8;                     // rounds whose global loads are issued together
 constexpr int kRadixBits = 9;
 constexpr int kDigits = 1 << kRadixBits;         // 512
 constexpr int kMaxPasses = (32 + kRadixBits - 1) / kRadixBits;   // 4
@@ -144,16 +145,25 @@ rs_hist_kernel(const unsigned long long* __restrict__ buf0, const unsigned long 
     __syncwarp();
     const unsigned long long* k = pairs + vol * nvox;
     const unsigned base = chunk * kWarpChunk;
-    for (int r = 0; r < kRounds; r++) {
-        unsigned p = base + r * 32 + lane;
-        bool ok = p < n;
-        unsigned active = __ballot_sync(0xffffffffu, ok);
-        if (ok) {
-            unsigned d = ((unsigned)(k[p] >> 32) >> shift) & (kDigits - 1);
-            unsigned peers = __match_any_sync(active, d);
-            if ((peers & ((1u << lane) - 1u)) == 0) cnt[warp][d] += __popc(peers);
+    for (int r0 = 0; r0 < kRounds; r0 += kPrefetch) {
+        unsigned keyhi[kPrefetch];   // the loads of kPrefetch rounds are in flight together
+#pragma unroll
+        for (int j = 0; j < kPrefetch; j++) {
+            const unsigned p = base + (r0 + j) * 32 + lane;
+            keyhi[j] = p < n ? (unsigned)(__ldcs(k + p) >> 32) : 0u;
         }
-        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < kPrefetch; j++) {
+            const unsigned p = base + (r0 + j) * 32 + lane;
+            const bool ok = p < n;
+            const unsigned active = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const unsigned d = (keyhi[j] >> shift) & (kDigits - 1);
+                const unsigned peers = __match_any_sync(active, d);
+                if ((peers & ((1u << lane) - 1u)) == 0) cnt[warp][d] += __popc(peers);
+            }
+            __syncwarp();
+        }
     }
     unsigned* tab = table + (vol * kDigits) * (size_t)nchunks_max;
     for (int d = lane; d < kDigits; d += 32) tab[(size_t)d * nchunks_max + chunk] = cnt[warp][d];
@@ -243,25 +253,34 @@ rs_scatter_kernel(unsigned long long* __restrict__ buf0, unsigned long long* __r
     const unsigned long long* pi = pairs_in + vol * nvox;
     unsigned long long* po = pairs_out + vol * nvox;
     const unsigned base = chunk * kWarpChunk;
-    for (int r = 0; r < kRounds; r++) {
-        unsigned p = base + r * 32 + lane;
-        bool ok = p < n;
-        unsigned active = __ballot_sync(0xffffffffu, ok);
-        if (ok) {
-            const unsigned long long kv = pi[p];
-            unsigned d = ((unsigned)(kv >> 32) >> shift) & (kDigits - 1);
-            unsigned peers = __match_any_sync(active, d);
-            unsigned rank = __popc(peers & ((1u << lane) - 1u));
-            int leader = __ffs(peers) - 1;
-            unsigned start = 0;
-            if (lane == leader) {
-                start = off[warp][d];
-                off[warp][d] = start + __popc(peers);
-            }
-            start = __shfl_sync(peers, start, leader);
-            po[start + rank] = kv;
+    for (int r0 = 0; r0 < kRounds; r0 += kPrefetch) {
+        unsigned long long kvs[kPrefetch];   // kPrefetch independent loads in flight per lane
+#pragma unroll
+        for (int j = 0; j < kPrefetch; j++) {
+            const unsigned p = base + (r0 + j) * 32 + lane;
+            kvs[j] = p < n ? __ldcs(pi + p) : 0ull;
         }
-        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < kPrefetch; j++) {
+            const unsigned p = base + (r0 + j) * 32 + lane;
+            const bool ok = p < n;
+            const unsigned active = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const unsigned long long kv = kvs[j];
+                const unsigned d = ((unsigned)(kv >> 32) >> shift) & (kDigits - 1);
+                const unsigned peers = __match_any_sync(active, d);
+                const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+                const int leader = __ffs(peers) - 1;
+                unsigned start = 0;
+                if (lane == leader) {
+                    start = off[warp][d];
+                    off[warp][d] = start + __popc(peers);
+                }
+                start = __shfl_sync(peers, start, leader);
+                po[start + rank] = kv;
+            }
+            __syncwarp();
+        }
     }
 }
 
