@@ -190,6 +190,30 @@ def run_reference(args):
     }), flush=True)
 
 
+def bind_to_gpu_numa(local: int):
+    """Best effort: run this rank (and allocate its pinned staging buffers) on the NUMA node its GPU
+    hangs off, so the host<->device copies of the e2e path do not cross the socket interconnect.
+    Returns a short description for the JSON line; silently does nothing where sysfs says nothing."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        dev = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{dev}/numa_node").read().strip())
+        if node < 0:
+            return f"{dev}: numa_node unknown"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"{dev}: node {node} has no allowed cpu"
+        os.sched_setaffinity(0, cpus)
+        return f"{dev}: node {node}, {len(cpus)} cpus"
+    except Exception as e:  # pragma: no cover
+        return f"unavailable ({type(e).__name__})"
+
+
 # --------------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch
@@ -205,6 +229,7 @@ def run_ours(args):
     from voxlogica_b200 import Context
     from voxlogica_b200.imgql import run_gtv
 
+    numa = bind_to_gpu_numa(local) if world > 1 else "not bound (single rank)"
     ctx = Context(local)
     B = args.batch
     shape4 = (B,) + BRATS
@@ -343,7 +368,7 @@ def run_ours(args):
                    "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB f32 batch per step)",
                    "data_note": "min(batch,4) generated volumes per rank + axis flips"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-                "ms_per_step": ms_e2e / args.steps, "host_threads": nthr,
+                "ms_per_step": ms_e2e / args.steps, "host_threads": nthr, "numa": numa,
                 "timing": "host perf_counter around K steps with all streams synchronised on both sides"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",

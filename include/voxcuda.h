@@ -132,6 +132,16 @@ VX_API int32_t vx_transfer(vx_ctx dst_ctx, vx_img img, vx_img* out);
 VX_API int32_t vx_device_ptr(vx_ctx ctx, vx_img img, void** ptr);
 VX_API int32_t vx_stream_handle(vx_ctx ctx, void** stream);
 
+/* Peer-visible device memory ("mailboxes") for the slab path: vx_ipc_alloc returns device memory
+ * and a 64-byte CUDA IPC handle another PROCESS on the same node passes to vx_ipc_open to map
+ * it (threads of the same process use the raw pointer).  vx_copy_planes_to packs planes
+ * [z0, z0+nz) of every volume of an image into raw device memory on the caller's stream. */
+VX_API int32_t vx_ipc_alloc(vx_ctx ctx, size_t bytes, void** ptr, void* handle64);
+VX_API int32_t vx_ipc_open(vx_ctx ctx, const void* handle64, void** ptr);
+VX_API int32_t vx_ipc_close(vx_ctx ctx, void* ptr);
+VX_API int32_t vx_ipc_free(vx_ctx ctx, void* ptr);
+VX_API int32_t vx_copy_planes_to(vx_ctx ctx, vx_img img, int32_t z0, int32_t nz, void* dst);
+
 /* Pinned host staging memory for the end-to-end path. */
 VX_API int32_t vx_host_alloc(size_t bytes, void** out);
 VX_API int32_t vx_host_free(void* p);
@@ -213,6 +223,14 @@ VX_API int32_t vx_fused_pointwise(vx_ctx ctx, const vx_op* program, int32_t n_op
 VX_API int32_t vx_border(vx_ctx ctx, vx_img like, vx_img* out);
 VX_API int32_t vx_near(vx_ctx ctx, vx_img a, int32_t conn, vx_img* out);
 VX_API int32_t vx_interior(vx_ctx ctx, vx_img a, int32_t conn, vx_img* out);
+/* The same for one z-slab of a larger volume, fused with the halo exchange: the planes z = -1 and
+ * z = nz are read by the kernel from lo_plane / hi_plane (nb*ny*nx bytes of device-accessible
+ * memory each -- typically a neighbour GPU's mailbox mapped with vx_ipc_open, pulled over NVLink
+ * while the kernel runs; NULL where the volume ends).  The caller orders their producers first. */
+VX_API int32_t vx_near_halo(vx_ctx ctx, vx_img a, int32_t conn, const void* lo_plane,
+                            const void* hi_plane, vx_img* out);
+VX_API int32_t vx_interior_halo(vx_ctx ctx, vx_img a, int32_t conn, const void* lo_plane,
+                                const void* hi_plane, vx_img* out);
 
 /* --------------------------------------------- A3 reachability (Greta.pdf p.32-38, p.78)
  * through(a, b): union of the connected components of b (adjacency `conn`) that

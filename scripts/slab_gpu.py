@@ -54,6 +54,7 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--peer", action="store_true", help="fused halo: kernels read neighbour planes from IPC peer memory")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -65,6 +66,8 @@ def main():
     ctx = Context(local)
     ops = SlabOps(CudaEngine(ctx), SlabComm())
     n = args.size
+    if args.peer:
+        ops.enable_peer_halo(n, n)
     shape = (n, n, n)
     z0, z1 = slab_bounds(n, world)[rank]
     sp = (1.0, 1.0, 1.0)
@@ -146,7 +149,7 @@ def main():
     reach["reached_last_plane"] = ops.volume(ops.and_(ops.through(A, B, 26), Slab(
         ctx.from_tensor(_last_plane_mask(ops, B, rank, world, local)[None], spacing=sp), z0, z1, n, sp)))
     if rank == 0:
-        print(json.dumps({"slab_bench": {"size": n, "n_gpus": world, "voxels": n ** 3, "ops": res, "check": reach,
+        print(json.dumps({"slab_bench": {"size": n, "n_gpus": world, "voxels": n ** 3, "peer_halo": bool(args.peer), "ops": res, "check": reach,
                                          "timing": "host clock around device-synchronised regions, max over ranks"}}),
               flush=True)
     dist.destroy_process_group()

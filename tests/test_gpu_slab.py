@@ -47,6 +47,14 @@ class ThreadComm:
         hi = vals[self.rank + 1][0] if self.rank + 1 < self.world else None
         return lo, hi
 
+    def barrier(self):
+        self.s.barrier.wait()
+
+    def share_mailbox(self, ctx, ptr, handle):
+        ptrs = self._swap("m", ptr)            # same process: the raw device pointers are valid
+        return (ptrs[self.rank - 1] if self.rank > 0 else None,
+                ptrs[self.rank + 1] if self.rank + 1 < self.world else None)
+
     def all_gather_rows(self, t):
         import torch
         torch.cuda.synchronize()
@@ -83,8 +91,8 @@ def test_slab_helpers_single_gpu(ctx):
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_slab_ops_two_threads_one_gpu(ctx, world):
+@pytest.mark.parametrize("world,peer", [(2, False), (3, False), (2, True), (3, True)])
+def test_slab_ops_two_threads_one_gpu(ctx, world, peer):
     from voxlogica_b200.slab import CudaEngine, SlabOps, slab_bounds
     rng = np.random.default_rng(42)
     shape = (21, 40, 64)
@@ -113,6 +121,8 @@ def test_slab_ops_two_threads_one_gpu(ctx, world):
     def run(rank):
         try:
             ops = SlabOps(CudaEngine(ctx), ThreadComm(shared, rank))
+            if peer:      # fused halo: boundary planes read from the neighbour's mailbox by the kernel
+                ops.enable_peer_halo(shape[1], shape[2])
             up = lambda arr, s: ctx.upload(arr, spacing=s)
             A, B, S, F = (ops.scatter_from_global(up, x, sp) for x in (a, b, sparse, f))
             got = {}
@@ -146,14 +156,15 @@ def test_slab_ops_two_threads_one_gpu(ctx, world):
     assert len(results) == world
 
 
-def test_slab_multi_gpu_nccl():
+@pytest.mark.parametrize("peer", [False, True])
+def test_slab_multi_gpu_nccl(peer):
     import torch
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 4)}",
-           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "scripts", "slab_gpu.py"),
-           "--size", "96", "--check"]
+           "--master-addr", "127.0.0.1", "--master-port", "29517" if not peer else "29518",
+           os.path.join(ROOT, "scripts", "slab_gpu.py"), "--size", "96", "--check"] + (["--peer"] if peer else [])
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "SLAB CHECK OK" in out.stdout

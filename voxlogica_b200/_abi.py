@@ -63,6 +63,11 @@ SIGNATURES = {
     "vx_transfer": [u64, u64, P(u64)],
     "vx_device_ptr": [u64, u64, P(C.c_void_p)],
     "vx_stream_handle": [u64, P(C.c_void_p)],
+    "vx_ipc_alloc": [u64, C.c_size_t, P(C.c_void_p), C.c_void_p],
+    "vx_ipc_open": [u64, C.c_void_p, P(C.c_void_p)],
+    "vx_ipc_close": [u64, C.c_void_p],
+    "vx_ipc_free": [u64, C.c_void_p],
+    "vx_copy_planes_to": [u64, u64, i32, i32, C.c_void_p],
     "vx_host_alloc": [C.c_size_t, P(C.c_void_p)],
     "vx_host_free": [C.c_void_p],
     "vx_mem_info": [u64, P(u64), P(u64), P(u64)],
@@ -86,6 +91,8 @@ SIGNATURES = {
     "vx_border": [u64, u64, P(u64)],
     "vx_near": [u64, u64, i32, P(u64)],
     "vx_interior": [u64, u64, i32, P(u64)],
+    "vx_near_halo": [u64, u64, i32, C.c_void_p, C.c_void_p, P(u64)],
+    "vx_interior_halo": [u64, u64, i32, C.c_void_p, C.c_void_p, P(u64)],
     "vx_through": [u64, u64, u64, i32, P(u64)],
     "vx_components": [u64, u64, i32, P(u64)],
     "vx_maxvol": [u64, u64, i32, P(u64)],

@@ -28,21 +28,30 @@ __device__ __forceinline__ uint4 or4(uint4 a, uint4 b) {
     return make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w);
 }
 
+// lo / hi: optional halo planes [ny][nx] standing for z = -1 and z = nz (the boundary planes of
+// the neighbouring slabs of a z-decomposed volume; they may live in a peer GPU's memory, read
+// over NVLink).  nullptr = the volume really ends there.
 template <bool FULL, bool ERODE>
 __device__ __forceinline__ Plane load_plane(const uint8_t* __restrict__ vol, int nx, int ny, int nz,
                                             int xc, int y, int z, bool col_ok, bool need_l,
-                                            bool need_r) {
+                                            bool need_r, const uint8_t* __restrict__ lo,
+                                            const uint8_t* __restrict__ hi) {
     Plane p;
     p.c = make_uint4(0, 0, 0, 0);
     p.s = make_uint4(0, 0, 0, 0);
     p.lb = p.rb = 0;
-    if (!col_ok || z < 0 || z >= nz) return p;
+    if (!col_ok) return p;
+    const uint8_t* plane;
+    if (z >= 0 && z < nz) plane = vol + (size_t)z * ny * nx;
+    else if (z == -1 && lo != nullptr) plane = lo;
+    else if (z == nz && hi != nullptr) plane = hi;
+    else return p;
     const unsigned flip = ERODE ? 0x01010101u : 0u;
 #pragma unroll
     for (int dy = -1; dy <= 1; dy++) {
         int yy = y + dy;
         if (yy < 0 || yy >= ny) continue;
-        const uint8_t* row = vol + ((size_t)z * ny + yy) * nx + (size_t)xc * 16;
+        const uint8_t* row = plane + (size_t)yy * nx + (size_t)xc * 16;
         uint4 w = __ldg(reinterpret_cast<const uint4*>(row));
         w.x ^= flip; w.y ^= flip; w.z ^= flip; w.w ^= flip;
         if (FULL || dy == 0) {
@@ -59,7 +68,8 @@ __device__ __forceinline__ Plane load_plane(const uint8_t* __restrict__ vol, int
 // grid: x = strips * ceil(ny/16), y = ceil(nz/ZL), z = nb;  block (16,16)
 template <bool FULL, bool ERODE>
 __global__ void __launch_bounds__(256)
-morph16_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int nx, int ny, int nz) {
+morph16_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int nx, int ny, int nz,
+               const uint8_t* __restrict__ lo_all, const uint8_t* __restrict__ hi_all) {
     const int ncx = nx >> 4;
     const int nstrips = (ncx + 15) >> 4;
     const int strip = blockIdx.x % nstrips, yblk = blockIdx.x / nstrips;
@@ -73,12 +83,14 @@ morph16_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int nx
     const bool col_ok = xc < ncx && y < ny;
     const bool need_l = col_ok && lane16 == 0 && xc > 0;           // left neighbour in another strip
     const bool need_r = col_ok && lane16 == 15 && xc + 1 < ncx;    // right neighbour in another strip
+    const uint8_t* lo = lo_all ? lo_all + (size_t)blockIdx.z * nx * ny : nullptr;
+    const uint8_t* hi = hi_all ? hi_all + (size_t)blockIdx.z * nx * ny : nullptr;
 
-    Plane prev = load_plane<FULL, ERODE>(vol, nx, ny, nz, xc, y, z0 - 1, col_ok, need_l, need_r);
-    Plane cur = load_plane<FULL, ERODE>(vol, nx, ny, nz, xc, y, z0, col_ok, need_l, need_r);
+    Plane prev = load_plane<FULL, ERODE>(vol, nx, ny, nz, xc, y, z0 - 1, col_ok, need_l, need_r, lo, hi);
+    Plane cur = load_plane<FULL, ERODE>(vol, nx, ny, nz, xc, y, z0, col_ok, need_l, need_r, lo, hi);
     const int zend = min(z0 + kMorphZL, nz);
     for (int z = z0; z < zend; z++) {
-        Plane next = load_plane<FULL, ERODE>(vol, nx, ny, nz, xc, y, z + 1, col_ok, need_l, need_r);
+        Plane next = load_plane<FULL, ERODE>(vol, nx, ny, nz, xc, y, z + 1, col_ok, need_l, need_r, lo, hi);
         uint4 C, E;
         unsigned lb, rb;
         if (FULL) {
@@ -116,7 +128,8 @@ morph16_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int nx
 template <bool FULL, bool ERODE>
 __global__ void __launch_bounds__(256)
 morph_generic_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int nx, int ny,
-                     int nz, size_t total) {
+                     int nz, size_t total, const uint8_t* __restrict__ lo_all,
+                     const uint8_t* __restrict__ hi_all) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     int x = (int)(i % nx);
@@ -124,11 +137,16 @@ morph_generic_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
     int y = (int)(t % ny);
     t /= ny;
     int z = (int)(t % nz);
-    const uint8_t* vol = in + (t / nz) * (size_t)nx * ny * nz;
+    const size_t v_idx = t / nz;
+    const uint8_t* vol = in + v_idx * (size_t)nx * ny * nz;
     unsigned acc = 0;
     for (int dz = -1; dz <= 1; dz++) {
         int zz = z + dz;
-        if (zz < 0 || zz >= nz) continue;
+        const uint8_t* plane;
+        if (zz >= 0 && zz < nz) plane = vol + (size_t)zz * ny * nx;
+        else if (zz == -1 && lo_all != nullptr) plane = lo_all + v_idx * (size_t)nx * ny;
+        else if (zz == nz && hi_all != nullptr) plane = hi_all + v_idx * (size_t)nx * ny;
+        else continue;
         for (int dy = -1; dy <= 1; dy++) {
             int yy = y + dy;
             if (yy < 0 || yy >= ny) continue;
@@ -136,7 +154,7 @@ morph_generic_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
                 int xx = x + dx;
                 if (xx < 0 || xx >= nx) continue;
                 if (!FULL && (dx != 0) + (dy != 0) + (dz != 0) > 1) continue;
-                unsigned v = vol[((size_t)zz * ny + yy) * nx + xx] != 0;
+                unsigned v = plane[(size_t)yy * nx + xx] != 0;
                 acc |= ERODE ? (v ^ 1u) : v;
             }
         }
@@ -175,7 +193,8 @@ border16_kernel(uint4* __restrict__ out, int ncx, int nx, int ny, int nz, size_t
     out[i] = v;
 }
 
-static int morph(vx_ctx ctx, vx_img a, int conn, bool erode, vx_img* out) {
+static int morph(vx_ctx ctx, vx_img a, int conn, bool erode, const void* lo_plane, const void* hi_plane,
+                 vx_img* out) {
     VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");
     VX_REQUIRE(conn == VX_CONN_FACE || conn == VX_CONN_FULL, VX_E_INVALID_ARG,
                "adjacency must be 6 or 26, got %d", conn);
@@ -187,6 +206,8 @@ static int morph(vx_ctx ctx, vx_img a, int conn, bool erode, vx_img* out) {
     VX_TRY(new_image(g.c, VX_U8, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
     const uint8_t* in = (const uint8_t*)A->d;
     uint8_t* o = (uint8_t*)O->d;
+    const uint8_t* lo = (const uint8_t*)lo_plane;
+    const uint8_t* hi = (const uint8_t*)hi_plane;
     const bool full = conn == VX_CONN_FULL;
     const char* name;
     if ((A->nx & 15) == 0) {
@@ -195,19 +216,19 @@ static int morph(vx_ctx ctx, vx_img a, int conn, bool erode, vx_img* out) {
         dim3 grid(nstrips * ((A->ny + 15) / 16), (A->nz + kMorphZL - 1) / kMorphZL, A->nb);
         dim3 block(16, 16);
         VX_LAUNCH(g.c, g.s, name);
-        if (full && !erode) morph16_kernel<true, false><<<grid, block, 0, g.st>>>(in, o, A->nx, A->ny, A->nz);
-        else if (full) morph16_kernel<true, true><<<grid, block, 0, g.st>>>(in, o, A->nx, A->ny, A->nz);
-        else if (!erode) morph16_kernel<false, false><<<grid, block, 0, g.st>>>(in, o, A->nx, A->ny, A->nz);
-        else morph16_kernel<false, true><<<grid, block, 0, g.st>>>(in, o, A->nx, A->ny, A->nz);
+        if (full && !erode) morph16_kernel<true, false><<<grid, block, 0, g.st>>>(in, o, A->nx, A->ny, A->nz, lo, hi);
+        else if (full) morph16_kernel<true, true><<<grid, block, 0, g.st>>>(in, o, A->nx, A->ny, A->nz, lo, hi);
+        else if (!erode) morph16_kernel<false, false><<<grid, block, 0, g.st>>>(in, o, A->nx, A->ny, A->nz, lo, hi);
+        else morph16_kernel<false, true><<<grid, block, 0, g.st>>>(in, o, A->nx, A->ny, A->nz, lo, hi);
     } else {
         name = "morph_generic_kernel";
         size_t total = A->count();
         unsigned grid = (unsigned)((total + 255) / 256);
         VX_LAUNCH(g.c, g.s, name);
-        if (full && !erode) morph_generic_kernel<true, false><<<grid, 256, 0, g.st>>>(in, o, A->nx, A->ny, A->nz, total);
-        else if (full) morph_generic_kernel<true, true><<<grid, 256, 0, g.st>>>(in, o, A->nx, A->ny, A->nz, total);
-        else if (!erode) morph_generic_kernel<false, false><<<grid, 256, 0, g.st>>>(in, o, A->nx, A->ny, A->nz, total);
-        else morph_generic_kernel<false, true><<<grid, 256, 0, g.st>>>(in, o, A->nx, A->ny, A->nz, total);
+        if (full && !erode) morph_generic_kernel<true, false><<<grid, 256, 0, g.st>>>(in, o, A->nx, A->ny, A->nz, total, lo, hi);
+        else if (full) morph_generic_kernel<true, true><<<grid, 256, 0, g.st>>>(in, o, A->nx, A->ny, A->nz, total, lo, hi);
+        else if (!erode) morph_generic_kernel<false, false><<<grid, 256, 0, g.st>>>(in, o, A->nx, A->ny, A->nz, total, lo, hi);
+        else morph_generic_kernel<false, true><<<grid, 256, 0, g.st>>>(in, o, A->nx, A->ny, A->nz, total, lo, hi);
     }
     int r = check_launch(name);
     if (r != VX_OK) { drop(O); return r; }
@@ -220,8 +241,20 @@ using namespace vx;
 
 extern "C" {
 
-int32_t vx_near(vx_ctx ctx, vx_img a, int32_t conn, vx_img* out) { return morph(ctx, a, conn, false, out); }
-int32_t vx_interior(vx_ctx ctx, vx_img a, int32_t conn, vx_img* out) { return morph(ctx, a, conn, true, out); }
+int32_t vx_near(vx_ctx ctx, vx_img a, int32_t conn, vx_img* out) { return morph(ctx, a, conn, false, nullptr, nullptr, out); }
+int32_t vx_interior(vx_ctx ctx, vx_img a, int32_t conn, vx_img* out) { return morph(ctx, a, conn, true, nullptr, nullptr, out); }
+// near / interior of one z-slab of a larger volume, fused with the halo: the planes at z = -1
+// and z = nz are read straight from `lo_plane` / `hi_plane` (nb * ny * nx bytes each, NULL at
+// the real end of the volume), which may be peer-GPU memory mapped with vx_ipc_open -- the
+// kernel then pulls the neighbour's boundary plane over NVLink while it computes, and no
+// extended copy of the slab is ever built.  The caller orders the planes' producers before
+// this call (they belong to another stream or process).
+int32_t vx_near_halo(vx_ctx ctx, vx_img a, int32_t conn, const void* lo_plane, const void* hi_plane, vx_img* out) {
+    return morph(ctx, a, conn, false, lo_plane, hi_plane, out);
+}
+int32_t vx_interior_halo(vx_ctx ctx, vx_img a, int32_t conn, const void* lo_plane, const void* hi_plane, vx_img* out) {
+    return morph(ctx, a, conn, true, lo_plane, hi_plane, out);
+}
 
 int32_t vx_border(vx_ctx ctx, vx_img like, vx_img* out) {
     VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");

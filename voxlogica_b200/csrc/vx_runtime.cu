@@ -602,6 +602,62 @@ int32_t vx_stream_handle(vx_ctx ctx, void** stream) {
     return VX_OK;
 }
 
+// ---- peer-visible mailboxes (CUDA IPC) for the slab path ------------------------------------
+int32_t vx_ipc_alloc(vx_ctx ctx, size_t bytes, void** ptr, void* handle64) {
+    VX_REQUIRE(ptr != nullptr && handle64 != nullptr && bytes > 0, VX_E_INVALID_ARG, "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    OpGuard g;
+    VX_TRY(g.begin(ctx));
+    VX_CUDA(cudaMalloc(ptr, bytes));
+    VX_CUDA(cudaMemset(*ptr, 0, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *ptr);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        memset(handle64, 0, 64);   // same-process use (raw pointer) still works
+    } else {
+        memcpy(handle64, &h, 64);
+    }
+    return VX_OK;
+}
+int32_t vx_ipc_open(vx_ctx ctx, const void* handle64, void** ptr) {
+    VX_REQUIRE(ptr != nullptr && handle64 != nullptr, VX_E_INVALID_ARG, "bad argument");
+    OpGuard g;
+    VX_TRY(g.begin(ctx));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    VX_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return VX_OK;
+}
+int32_t vx_ipc_close(vx_ctx ctx, void* ptr) {
+    OpGuard g;
+    VX_TRY(g.begin(ctx));
+    if (ptr) VX_CUDA(cudaIpcCloseMemHandle(ptr));
+    return VX_OK;
+}
+int32_t vx_ipc_free(vx_ctx ctx, void* ptr) {
+    OpGuard g;
+    VX_TRY(g.begin(ctx));
+    if (ptr) VX_CUDA(cudaFree(ptr));
+    return VX_OK;
+}
+// planes [z0, z0+nz) of every volume of `img`, densely packed ([nb][nz][ny][nx]), into raw device
+// memory `dst` (e.g. this rank's mailbox), on the calling thread's stream
+int32_t vx_copy_planes_to(vx_ctx ctx, vx_img img, int32_t z0, int32_t nz, void* dst) {
+    VX_REQUIRE(dst != nullptr, VX_E_INVALID_ARG, "dst is NULL");
+    OpGuard g;
+    VX_TRY(g.begin(ctx));
+    Image* im = nullptr;
+    VX_TRY(g.input(img, &im, 0));
+    VX_REQUIRE(z0 >= 0 && nz > 0 && z0 + nz <= im->nz, VX_E_INVALID_ARG,
+               "planes [%d,%d) outside a volume of %d planes", z0, z0 + nz, im->nz);
+    const size_t es = im->bytes / im->count();
+    const size_t plane = (size_t)im->nx * im->ny * es;
+    VX_CUDA(cudaMemcpy2DAsync(dst, plane * nz, (const char*)im->d + plane * z0, plane * im->nz, plane * nz,
+                              im->nb, cudaMemcpyDeviceToDevice, g.st));
+    return g.finish_scalar();
+}
+
 int32_t vx_host_alloc(size_t bytes, void** out) {
     VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");
     VX_CUDA(cudaMallocHost(out, bytes ? bytes : 1));

@@ -483,6 +483,11 @@ xcorr_ring_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
     rl.fetch(y0 + 2 + g.wy, pfb);
     for (int w = 0; w < g.nw; w++) hist[w * kXcThreads + threadIdx.x] = 0u;
     __syncthreads();
+    // words of h2 that hold a non-zero count (block-uniform; wlo > whi when the region is empty)
+    int wlo = g.nw, whi = -1;
+    for (int w = 0; w < g.nw; w++)
+        if (h2s[2 * w] | h2s[2 * w + 1]) { wlo = min(wlo, w); whi = w; }
+    const bool p32 = (unsigned long long)g.ball * (unsigned long long)n2 < 0xffffffffull;
 
     if (active) {
         if (flat_rows >= 2 * g.wy + 1) {
@@ -504,14 +509,39 @@ xcorr_ring_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
     bool changed = true;   // block-uniform: did the last slide touch the histograms?
     for (int y = y0; y < y1; y++) {
         if (active && changed) {
+            // S11 over all bins; the dot product with h2 only over the words where h2 is not
+            // zero (a region's intensities occupy a few of the k bins), in 32 bits when
+            // ball * n2 cannot overflow them
             unsigned long long P = 0;
             unsigned S2 = 0;
-            for (int w = 0; w < g.nw; w++) {
+            for (int w = 0; w < wlo; w++) {
                 const unsigned v = hist[w * kXcThreads + threadIdx.x];
-                const uint2 hh = *reinterpret_cast<const uint2*>(h2s + 2 * w);
                 const unsigned lo = v & 0xffffu, hi = v >> 16;
-                P += (unsigned long long)lo * hh.x;
-                P += (unsigned long long)hi * hh.y;
+                S2 += lo * lo + hi * hi;
+            }
+            if (p32) {
+                unsigned P32 = 0;
+                for (int w = wlo; w <= whi; w++) {
+                    const unsigned v = hist[w * kXcThreads + threadIdx.x];
+                    const uint2 hh = *reinterpret_cast<const uint2*>(h2s + 2 * w);
+                    const unsigned lo = v & 0xffffu, hi = v >> 16;
+                    P32 += lo * hh.x + hi * hh.y;
+                    S2 += lo * lo + hi * hi;
+                }
+                P = P32;
+            } else {
+                for (int w = wlo; w <= whi; w++) {
+                    const unsigned v = hist[w * kXcThreads + threadIdx.x];
+                    const uint2 hh = *reinterpret_cast<const uint2*>(h2s + 2 * w);
+                    const unsigned lo = v & 0xffffu, hi = v >> 16;
+                    P += (unsigned long long)lo * hh.x;
+                    P += (unsigned long long)hi * hh.y;
+                    S2 += lo * lo + hi * hi;
+                }
+            }
+            for (int w = whi + 1; w < g.nw; w++) {
+                const unsigned v = hist[w * kXcThreads + threadIdx.x];
+                const unsigned lo = v & 0xffffu, hi = v >> 16;
                 S2 += lo * lo + hi * hi;
             }
             // remove the dummy bin K (not-counted voxels) from the statistics
@@ -731,8 +761,15 @@ static int xcorr_run(OpGuard& og, Image* A, uint8_t* d_bins, float* d_edges, uns
     const int nw = (k + 2) / 2;   // k bins + the dummy bin k
     // y segments: long enough to amortise the initial full-ball build, short enough to
     // give the batch at least a few waves of CTAs
-    const int seg = A->ny <= 64 ? A->ny : 64;
-    const int nseg = (A->ny + seg - 1) / seg;
+    // (the build costs |ball| bumps, a step 2 * #columns moves: ~5% at 64 rows for rho = 5)
+    int nseg = (A->ny + 63) / 64;
+    {
+        const long long ctas_per_seg = (long long)((A->nx + 31) / 32) * ((A->nz + kXcWarps - 1) / kXcWarps) * A->nb;
+        const long long want = 4LL * kNumSMs * 5;   // four waves at five resident CTAs per SM
+        while (nseg > 1 && ctas_per_seg * (nseg - 1) >= want) nseg--;
+    }
+    const int seg = (A->ny + nseg - 1) / nseg;
+    nseg = (A->ny + seg - 1) / seg;
     const int ringR = 2 * wy + 3;   // rows y-wy .. y+1+wy of a step plus the one being written
     const int P = kXcWarps + 2 * wz;
     int rc = VX_OK;

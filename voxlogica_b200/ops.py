@@ -173,6 +173,32 @@ class Context:
         """copy an image of ANOTHER context (GPU) of this process into this one (peer copy)"""
         return self._out(lambda o: self.lib.vx_transfer(self.handle, img.handle, o))
 
+    def ipc_alloc(self, nbytes: int):
+        """-> (device pointer, 64-byte IPC handle) of a zero-filled peer-visible buffer"""
+        p = C.c_void_p()
+        h = C.create_string_buffer(64)
+        check(self.lib.vx_ipc_alloc(self.handle, int(nbytes), C.byref(p), h))
+        return p.value, h.raw
+
+    def ipc_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        check(self.lib.vx_ipc_open(self.handle, C.create_string_buffer(handle, 64), C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr: int) -> None:
+        check(self.lib.vx_ipc_close(self.handle, C.c_void_p(ptr)))
+
+    def ipc_free(self, ptr: int) -> None:
+        check(self.lib.vx_ipc_free(self.handle, C.c_void_p(ptr)))
+
+    def copy_planes_to(self, img: Image, z0: int, nz: int, dst_ptr: int) -> None:
+        check(self.lib.vx_copy_planes_to(self.handle, img.handle, int(z0), int(nz), C.c_void_p(dst_ptr)))
+
+    def near_halo(self, a: Image, conn: int, lo_ptr: int, hi_ptr: int, erode: bool = False) -> Image:
+        fn = self.lib.vx_interior_halo if erode else self.lib.vx_near_halo
+        return self._out(lambda o: fn(self.handle, a.handle, conn, C.c_void_p(lo_ptr or None),
+                                      C.c_void_p(hi_ptr or None), o))
+
     def device_ptr(self, img: Image) -> int:
         p = C.c_void_p()
         check(self.lib.vx_device_ptr(self.handle, img.handle, C.byref(p)))

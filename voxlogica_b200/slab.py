@@ -6,7 +6,11 @@ operator has at most one exchange step:
 
     pointwise ............ none
     volume / min / max ... one scalar all-reduce
-    near / interior ...... 1-plane halo from each z-neighbour (send/recv)
+    near / interior ...... 1-plane halo from each z-neighbour: either send/recv + an extended copy
+                           of the slab, or (``SlabOps.enable_peer_halo``) FUSED: every rank
+                           publishes its two boundary planes in a CUDA-IPC mailbox and the
+                           dilation kernel reads the neighbours' planes straight out of peer
+                           memory over NVLink -- no extended slab, no crop, one barrier
     distlt / distgeq ..... ceil(r / sz)-plane halo (the interval test only looks r far)
     crossCorrelation ..... ceil(rho / sz)-plane halo of `a` + all-reduce of the region histogram
     through .............. local union-find per slab, exchange of the boundary label planes,
@@ -135,6 +139,18 @@ class SlabComm:
                 torch.cuda.current_stream(to_lower.device).synchronize()
         return from_lower, from_upper
 
+    def barrier(self):
+        self.dist.barrier(group=self.group)
+
+    def share_mailbox(self, ctx, ptr: int, handle: bytes):
+        """exchange CUDA IPC handles; returns the device pointers of the (lower, upper) neighbours'
+        mailboxes mapped into this process (None at the ends)"""
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, handle, group=self.group)
+        lower = ctx.ipc_open(handles[self.rank - 1]) if self.rank > 0 else None
+        upper = ctx.ipc_open(handles[self.rank + 1]) if self.rank + 1 < self.world else None
+        return lower, upper
+
     def all_gather_rows(self, t):
         """all-gather of [n_i, c] int64 tensors with different n_i -> one [sum n_i, c] tensor"""
         import torch
@@ -164,12 +180,51 @@ class SlabComm:
         return t.cpu().numpy()
 
 
+class PeerHalo:
+    """Double-buffered boundary-plane mailboxes in peer-visible device memory.
+
+    Layout of one rank's mailbox: [parity 0|1][side 0 = my bottom plane, 1 = my top plane][ny*nx].
+    Protocol per operator: write own planes into mailbox[parity] on the library stream,
+    synchronise the stream, barrier, launch the fused kernel with pointers INTO THE NEIGHBOURS'
+    mailboxes, flip parity.  The barrier of operator k+1 is passed only after every rank has
+    drained its stream, i.e. after all kernels of operator k have finished reading, so
+    overwriting parity k's slots in operator k+2 is safe without a second barrier."""
+
+    def __init__(self, ctx, comm, plane_bytes: int):
+        self.ctx, self.comm, self.plane = ctx, comm, int(plane_bytes)
+        self.ptr, handle = ctx.ipc_alloc(4 * self.plane)
+        self.lower, self.upper = comm.share_mailbox(ctx, self.ptr, handle)
+        self.parity = 0
+
+    def slot(self, base: int, parity: int, side: int) -> int:
+        return base + (2 * parity + side) * self.plane
+
+
 class SlabOps:
     """ImgQL operators on Slab values.  Same names and argument order as ops.Context."""
 
     def __init__(self, engine, comm: SlabComm):
         self.e = engine
         self.c = comm
+        self.peer: Optional[PeerHalo] = None
+
+    def enable_peer_halo(self, ny: int, nx: int) -> None:
+        """collective: allocate and exchange the IPC mailboxes for [ny][nx] u8 boundary planes"""
+        self.peer = PeerHalo(self.e.ctx, self.c, ny * nx)
+
+    def _near_peer(self, a: Slab, conn: int, erode: bool) -> Slab:
+        ph, ctx = self.peer, self.e.ctx
+        nzl = self.e.nz(a.data)
+        par = ph.parity
+        ctx.copy_planes_to(a.data, 0, 1, ph.slot(ph.ptr, par, 0))
+        ctx.copy_planes_to(a.data, nzl - 1, 1, ph.slot(ph.ptr, par, 1))
+        ctx.sync()
+        self.c.barrier()
+        lo = ph.slot(ph.lower, par, 1) if ph.lower else 0     # the lower neighbour's TOP plane
+        hi = ph.slot(ph.upper, par, 0) if ph.upper else 0     # the upper neighbour's BOTTOM plane
+        out = ctx.near_halo(a.data, conn, lo, hi, erode)
+        ph.parity ^= 1
+        return a.like(out)
 
     # ------------------------------------------------------------------ distribution
     def scatter_from_global(self, upload, vol: np.ndarray, spacing=(1.0, 1.0, 1.0)) -> Slab:
@@ -226,9 +281,13 @@ class SlabOps:
 
     # ------------------------------------------------------------------ halo operators
     def near(self, a: Slab, conn: int = 26) -> Slab:
+        if self.peer is not None and self.c.world > 1:
+            return self._near_peer(a, conn, False)
         return self._halo_op(a, 1, lambda x: self.e.near(x, conn))
 
     def interior(self, a: Slab, conn: int = 26) -> Slab:
+        if self.peer is not None and self.c.world > 1:
+            return self._near_peer(a, conn, True)
         return self._halo_op(a, 1, lambda x: self.e.interior(x, conn))
 
     def _dist(self, op: str, r: float, a: Slab) -> Slab:
