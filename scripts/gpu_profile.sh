@@ -13,4 +13,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-fi
 CMD2="python scripts/bench_ops.py --shape brats --batch 8 --reps 1 --only xcorr"
 $CMD2 > gpurun_out/plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:xcorr_ring -s 2 -c 1 -o gpurun_out/xcorr_full -f $CMD2 > gpurun_out/ncu_full.log 2>&1
+python scripts/bench_ops.py --shape brats --batch 16 --reps 5 --out gpurun_out/ops_brats_b16.json > /dev/null 2>&1
+python scripts/bench_ops.py --shape 512 --batch 1 --reps 5 --out gpurun_out/ops_512.json > /dev/null 2>&1
 ls -la gpurun_out
