@@ -241,6 +241,22 @@ VX_API int32_t vx_through(vx_ctx ctx, vx_img a, vx_img b, int32_t conn, vx_img* 
  * first voxel in raster order -- a canonical labelling, so it is comparable
  * bit-for-bit with any other implementation after the same canonicalisation. */
 VX_API int32_t vx_components(vx_ctx ctx, vx_img a, int32_t conn, vx_img* out);
+/* The stages of vx_through as separate calls on a kept union-find state, for a caller that owns
+ * only one z-slab of a larger volume: label the local slab once, seed it,
+ * read the labels and "reached" flags of its boundary planes (a label is 1 + the linear index of
+ * the component's first voxel inside the slab), flag further components by label after the
+ * boundary equivalences have been resolved with the neighbours, then select.  Calls on one
+ * state must be issued in program order (any thread); the state owns device scratch until
+ * vx_ccl_destroy. */
+typedef uint64_t vx_ccl;
+VX_API int32_t vx_ccl_create(vx_ctx ctx, vx_img b, int32_t conn, vx_ccl* out);
+VX_API int32_t vx_ccl_seed(vx_ctx ctx, vx_ccl state, vx_img a);
+VX_API int32_t vx_ccl_plane(vx_ctx ctx, vx_ccl state, int32_t z, vx_img* labels_u32, vx_img* reached_u8);
+/* labels: n values, host or device memory; single-volume states only */
+VX_API int32_t vx_ccl_flag(vx_ctx ctx, vx_ccl state, const uint32_t* labels, uint64_t n);
+VX_API int32_t vx_ccl_select(vx_ctx ctx, vx_ccl state, vx_img* out);
+VX_API int32_t vx_ccl_destroy(vx_ctx ctx, vx_ccl state);
+
 /* A8 maxvol: the component(s) of a with the largest voxel count (all of them on ties). */
 VX_API int32_t vx_maxvol(vx_ctx ctx, vx_img a, int32_t conn, vx_img* out);
 

@@ -123,6 +123,8 @@ def test_slab_ops_two_threads_one_gpu(ctx, world, peer):
             ops = SlabOps(CudaEngine(ctx), ThreadComm(shared, rank))
             if peer:      # fused halo: boundary planes read from the neighbour's mailbox by the kernel
                 ops.enable_peer_halo(shape[1], shape[2])
+            else:         # and the three-pass `through` without the kept union-find state
+                ops.use_ccl_state = False
             up = lambda arr, s: ctx.upload(arr, spacing=s)
             A, B, S, F = (ops.scatter_from_global(up, x, sp) for x in (a, b, sparse, f))
             got = {}

@@ -95,6 +95,12 @@ SIGNATURES = {
     "vx_interior_halo": [u64, u64, i32, C.c_void_p, C.c_void_p, P(u64)],
     "vx_through": [u64, u64, u64, i32, P(u64)],
     "vx_components": [u64, u64, i32, P(u64)],
+    "vx_ccl_create": [u64, u64, i32, P(u64)],
+    "vx_ccl_seed": [u64, u64, u64],
+    "vx_ccl_plane": [u64, u64, i32, P(u64), P(u64)],
+    "vx_ccl_flag": [u64, u64, C.c_void_p, u64],
+    "vx_ccl_select": [u64, u64, P(u64)],
+    "vx_ccl_destroy": [u64, u64],
     "vx_maxvol": [u64, u64, i32, P(u64)],
     "vx_edt": [u64, u64, P(u64)],
     "vx_edt_signed": [u64, u64, i32, P(u64)],

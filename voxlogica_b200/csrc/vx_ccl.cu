@@ -435,6 +435,45 @@ ccl_max_kernel(const unsigned* __restrict__ Lall, const unsigned* __restrict__ b
     if (v) atomicMax(vmax + p.vol, v);
 }
 
+// ---- slab support: labels / reached flags of one z plane, flagging roots by label -----------
+// one thread per word of plane z of every volume
+__global__ void __launch_bounds__(kCclThreads)
+ccl_plane_kernel(const unsigned* __restrict__ Lall, const unsigned* __restrict__ bits,
+                 unsigned* __restrict__ labels, uint8_t* __restrict__ reached, Geo g, int z) {
+    const unsigned long long words_per_plane = (unsigned long long)g.nwx * g.ny;
+    const unsigned long long t = (unsigned long long)blockIdx.x * kCclThreads + threadIdx.x;
+    if (t >= words_per_plane * g.nb) return;
+    const unsigned vol = (unsigned)(t / words_per_plane);
+    const unsigned long long wp = t % words_per_plane;
+    const int y = (int)(wp / g.nwx), w = (int)(wp % g.nwx);
+    const unsigned long long wid = ((unsigned long long)vol * g.nz + z) * words_per_plane + wp;
+    const unsigned m = __ldg(bits + wid);
+    const unsigned* L = Lall + (size_t)vol * g.nvox;
+    const unsigned lin0 = (unsigned)(((unsigned long long)z * g.ny + y) * g.nx + (unsigned)w * 32u);
+    const int x0 = w * 32, lim = min(32, g.nx - x0);
+    const size_t o = ((size_t)vol * g.ny + y) * g.nx + x0;
+    unsigned rest = m;
+    for (int b = 0; b < lim; b++) { labels[o + b] = 0u; reached[o + b] = 0; }
+    while (rest) {
+        const int st = __ffs(rest) - 1;
+        const unsigned sm = seg_mask(m, st);
+        rest &= ~sm;
+        const unsigned r = find_root(L, lin0 + st);
+        const uint8_t hit = (__ldcg(L + r) & kFlag) ? 1 : 0;
+        for (int b = st; b < lim && ((sm >> b) & 1u); b++) { labels[o + b] = r + 1u; reached[o + b] = hit; }
+    }
+}
+
+__global__ void ccl_flag_labels_kernel(unsigned* __restrict__ L, const unsigned* __restrict__ labels, size_t n,
+                                       unsigned nvox) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned lab = labels[i];
+    if (lab == 0 || lab > nvox) return;
+    const unsigned r = find_root(L, lab - 1u);
+    atomicOr(L + r, kFlag);
+}
+
 static Geo make_geo(const Image* b) {
     Geo g;
     g.nx = b->nx; g.ny = b->ny; g.nz = b->nz; g.nb = b->nb;
@@ -579,6 +618,164 @@ int32_t vx_maxvol(vx_ctx ctx, vx_img a, int32_t conn, vx_img* out) {
     if (r == VX_OK) r = scratch_free(og.c, og.s, vmax);
     if (r != VX_OK) { drop(O); return r; }
     return og.finish(O, out);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- CCL state (slab decomposition)
+namespace vx {
+struct CclState {
+    Ctx* c = nullptr;
+    unsigned *L = nullptr, *bits = nullptr;
+    Geo g;
+    unsigned grid = 0;
+    int nx = 0, ny = 0, nz = 0, nb = 0;
+    float sp[3] = {1.f, 1.f, 1.f};
+    cudaEvent_t ev = nullptr;   // last operation enqueued on the state
+    int home = 0;               // stream the scratch memory belongs to
+};
+static std::mutex g_ccl_mu;
+static std::vector<CclState*> g_ccl(1, nullptr);
+
+static CclState* get_state(vx_ccl h) {
+    std::lock_guard<std::mutex> lk(g_ccl_mu);
+    if (h == 0 || h >= g_ccl.size()) return nullptr;
+    return g_ccl[h];
+}
+// order this thread's stream after the last operation on the state
+static int state_enter(OpGuard& og, vx_ctx ctx, vx_ccl h, CclState** st) {
+    VX_TRY(og.begin(ctx));
+    *st = get_state(h);
+    VX_REQUIRE(*st != nullptr && (*st)->c == og.c, VX_E_INVALID_ARG, "invalid CCL state handle");
+    VX_CUDA(cudaStreamWaitEvent(og.st, (*st)->ev, 0));
+    return VX_OK;
+}
+static int state_leave(OpGuard& og, CclState* st) {
+    VX_CUDA(cudaEventRecord(st->ev, og.st));
+    return VX_OK;
+}
+}  // namespace vx
+
+extern "C" {
+
+int32_t vx_ccl_create(vx_ctx ctx, vx_img b, int32_t conn, vx_ccl* out) {
+    VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");
+    VX_REQUIRE(conn == VX_CONN_FACE || conn == VX_CONN_FULL, VX_E_INVALID_ARG,
+               "adjacency must be 6 or 26, got %d", conn);
+    OpGuard og;
+    VX_TRY(og.begin(ctx));
+    Image* B = nullptr;
+    VX_TRY(og.input(b, &B, VX_U8));
+    CclState* st = new CclState();
+    st->c = og.c; st->home = og.s;
+    st->nx = B->nx; st->ny = B->ny; st->nz = B->nz; st->nb = B->nb;
+    st->sp[0] = B->sp[0]; st->sp[1] = B->sp[1]; st->sp[2] = B->sp[2];
+    int rc = ccl_label(og, B, conn == VX_CONN_FULL, &st->L, &st->bits, &st->g, &st->grid);
+    if (rc == VX_OK && cudaEventCreateWithFlags(&st->ev, cudaEventDisableTiming) != cudaSuccess)
+        rc = fail(VX_E_CUDA, "event creation failed");
+    if (rc != VX_OK) { delete st; return rc; }
+    VX_TRY(state_leave(og, st));
+    VX_TRY(og.finish_scalar());
+    std::lock_guard<std::mutex> lk(g_ccl_mu);
+    g_ccl.push_back(st);
+    *out = g_ccl.size() - 1;
+    return VX_OK;
+}
+
+int32_t vx_ccl_seed(vx_ctx ctx, vx_ccl state, vx_img a) {
+    OpGuard og;
+    CclState* st = nullptr;
+    VX_TRY(state_enter(og, ctx, state, &st));
+    Image* A = nullptr;
+    VX_TRY(og.input(a, &A, VX_U8));
+    VX_REQUIRE(A->nx == st->nx && A->ny == st->ny && A->nz == st->nz && A->nb == st->nb, VX_E_SHAPE_MISMATCH,
+               "seed image does not have the shape of the labelled image");
+    {
+        VX_LAUNCH(og.c, og.s, "ccl_seed_kernel");
+        ccl_seed_kernel<<<st->grid, kCclThreads, 0, og.st>>>((const uint8_t*)A->d, st->L, st->bits, st->g);
+    }
+    VX_TRY(check_launch("ccl_seed_kernel"));
+    VX_TRY(state_leave(og, st));
+    return og.finish_scalar();
+}
+
+int32_t vx_ccl_plane(vx_ctx ctx, vx_ccl state, int32_t z, vx_img* labels, vx_img* reached) {
+    VX_REQUIRE(labels != nullptr && reached != nullptr, VX_E_INVALID_ARG, "NULL output");
+    OpGuard og;
+    CclState* st = nullptr;
+    VX_TRY(state_enter(og, ctx, state, &st));
+    VX_REQUIRE(z >= 0 && z < st->nz, VX_E_INVALID_ARG, "plane %d outside [0,%d)", z, st->nz);
+    Image *Lb = nullptr, *Rc = nullptr;
+    VX_TRY(new_image(og.c, VX_U32, st->nx, st->ny, 1, st->nb, st->sp, &Lb));
+    int rc = new_image(og.c, VX_U8, st->nx, st->ny, 1, st->nb, st->sp, &Rc);
+    if (rc != VX_OK) { drop(Lb); return rc; }
+    const unsigned long long words = (unsigned long long)st->g.nwx * st->ny * st->nb;
+    {
+        VX_LAUNCH(og.c, og.s, "ccl_plane_kernel");
+        ccl_plane_kernel<<<(unsigned)((words + kCclThreads - 1) / kCclThreads), kCclThreads, 0, og.st>>>(
+            st->L, st->bits, (unsigned*)Lb->d, (uint8_t*)Rc->d, st->g, z);
+    }
+    rc = check_launch("ccl_plane_kernel");
+    if (rc == VX_OK) rc = state_leave(og, st);
+    if (rc == VX_OK) rc = publish(og.c, Lb, og.s);
+    if (rc == VX_OK) rc = publish(og.c, Rc, og.s);
+    if (rc != VX_OK) { drop(Lb); drop(Rc); return rc; }
+    *labels = Lb->handle;
+    *reached = Rc->handle;
+    return VX_OK;
+}
+
+int32_t vx_ccl_flag(vx_ctx ctx, vx_ccl state, const uint32_t* labels, uint64_t n) {
+    OpGuard og;
+    CclState* st = nullptr;
+    VX_TRY(state_enter(og, ctx, state, &st));
+    VX_REQUIRE(st->nb == 1, VX_E_UNSUPPORTED, "vx_ccl_flag takes a single-volume state (labels are per volume)");
+    if (n == 0) return VX_OK;
+    VX_REQUIRE(labels != nullptr, VX_E_INVALID_ARG, "labels is NULL");
+    unsigned* d = nullptr;
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * n, (void**)&d));
+    VX_CUDA(cudaMemcpyAsync(d, labels, sizeof(unsigned) * n, cudaMemcpyDefault, og.st));
+    {
+        VX_LAUNCH(og.c, og.s, "ccl_flag_labels_kernel");
+        ccl_flag_labels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, og.st>>>(st->L, d, (size_t)n, (unsigned)st->g.nvox);
+    }
+    VX_TRY(check_launch("ccl_flag_labels_kernel"));
+    VX_TRY(scratch_free(og.c, og.s, d));
+    return state_leave(og, st);
+}
+
+int32_t vx_ccl_select(vx_ctx ctx, vx_ccl state, vx_img* out) {
+    VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");
+    OpGuard og;
+    CclState* st = nullptr;
+    VX_TRY(state_enter(og, ctx, state, &st));
+    Image* O = nullptr;
+    VX_TRY(new_image(og.c, VX_U8, st->nx, st->ny, st->nz, st->nb, st->sp, &O));
+    {
+        VX_LAUNCH(og.c, og.s, "ccl_select_kernel");
+        ccl_select_kernel<SEL_THROUGH><<<st->grid, kCclThreads, 0, og.st>>>(st->L, st->bits, O->d, nullptr, nullptr, st->g);
+    }
+    int rc = check_launch("ccl_select_kernel");
+    if (rc == VX_OK) rc = state_leave(og, st);
+    if (rc != VX_OK) { drop(O); return rc; }
+    return og.finish(O, out);
+}
+
+int32_t vx_ccl_destroy(vx_ctx ctx, vx_ccl state) {
+    OpGuard og;
+    CclState* st = nullptr;
+    VX_TRY(state_enter(og, ctx, state, &st));
+    {
+        std::lock_guard<std::mutex> lk(g_ccl_mu);
+        g_ccl[state] = nullptr;
+    }
+    // the scratch goes back to the free list of the calling stream, which is ordered after the
+    // last operation on the state
+    scratch_free(og.c, og.s, st->L);
+    scratch_free(og.c, og.s, st->bits);
+    cudaEventDestroy(st->ev);
+    delete st;
+    return VX_OK;
 }
 
 }  // extern "C"

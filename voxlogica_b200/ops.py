@@ -337,6 +337,31 @@ class Context:
     def components(self, a: Image, conn: int = A.VX_CONN_FULL) -> Image:
         return self._out(lambda o: self.lib.vx_components(self.handle, a.handle, conn, o))
 
+    # kept union-find state (the stages of `through`, for slab decomposition)
+    def ccl_create(self, b: Image, conn: int = A.VX_CONN_FULL) -> int:
+        h = A.u64()
+        check(self.lib.vx_ccl_create(self.handle, b.handle, conn, C.byref(h)))
+        return h.value
+
+    def ccl_seed(self, state: int, a: Image) -> None:
+        check(self.lib.vx_ccl_seed(self.handle, state, a.handle))
+
+    def ccl_plane(self, state: int, z: int):
+        """-> (u32 label image, u8 reached image) of plane z, each [nb][1][ny][nx]"""
+        l, r = A.u64(), A.u64()
+        check(self.lib.vx_ccl_plane(self.handle, state, int(z), C.byref(l), C.byref(r)))
+        return Image(self, l.value), Image(self, r.value)
+
+    def ccl_flag(self, state: int, labels) -> None:
+        arr = np.ascontiguousarray(labels, dtype=np.uint32)
+        check(self.lib.vx_ccl_flag(self.handle, state, arr.ctypes.data_as(C.c_void_p), arr.size))
+
+    def ccl_select(self, state: int) -> Image:
+        return self._out(lambda o: self.lib.vx_ccl_select(self.handle, state, o))
+
+    def ccl_destroy(self, state: int) -> None:
+        check(self.lib.vx_ccl_destroy(self.handle, state))
+
     def maxvol(self, a: Image, conn: int = A.VX_CONN_FULL) -> Image:
         return self._out(lambda o: self.lib.vx_maxvol(self.handle, a.handle, conn, o))
 

@@ -98,6 +98,19 @@ class CudaEngine:
     def through(self, a, b, conn): return self.ctx.through(a, b, conn)
     def components(self, a, conn): return self.ctx.components(a, conn)
 
+    # the stages of `through` on a kept union-find state: one local labelling instead of three
+    def ccl_create(self, b, conn): return self.ctx.ccl_create(b, conn)
+    def ccl_seed(self, st, a): self.ctx.ccl_seed(st, a)
+    def ccl_flag(self, st, labels): self.ctx.ccl_flag(st, labels)
+    def ccl_select(self, st): return self.ctx.ccl_select(st)
+    def ccl_destroy(self, st): self.ctx.ccl_destroy(st)
+
+    def ccl_plane(self, st, z):
+        lab, hit = self.ctx.ccl_plane(st, z)
+        tl, th = self.ctx.as_tensor(lab), self.ctx.as_tensor(hit)
+        self.ctx.sync()
+        return tl[0, 0], th[0, 0]
+
     def dist(self, op, r, a):
         return {"<": self.ctx.distlt, "<=": self.ctx.distleq, ">=": self.ctx.distgeq, ">": self.ctx.distgt}[op](r, a)
 
@@ -156,15 +169,15 @@ class SlabComm:
         import torch
         dist = self.dist
         n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
-        sizes = [torch.zeros_like(n) for _ in range(self.world)]
-        dist.all_gather(sizes, n, group=self.group)
-        sizes = [int(s.item()) for s in sizes]
+        sizes = torch.zeros(self.world, dtype=torch.int64, device=t.device)
+        dist.all_gather_into_tensor(sizes, n, group=self.group)
+        sizes = sizes.tolist()                       # one host sync
         cap = max(max(sizes), 1)
         pad = torch.zeros((cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         pad[: t.shape[0]] = t
-        bufs = [torch.empty_like(pad) for _ in range(self.world)]
-        dist.all_gather(bufs, pad, group=self.group)
-        return torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
+        buf = torch.empty((self.world * cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(buf, pad, group=self.group)
+        return torch.cat([buf[r * cap: r * cap + s] for r, s in enumerate(sizes)], dim=0)
 
     def all_reduce(self, values: Sequence[float], op: str, device) -> np.ndarray:
         import torch
@@ -207,6 +220,7 @@ class SlabOps:
         self.e = engine
         self.c = comm
         self.peer: Optional[PeerHalo] = None
+        self.use_ccl_state = True     # `through` on a kept union-find state when the engine has one
 
     def enable_peer_halo(self, ny: int, nx: int) -> None:
         """collective: allocate and exchange the IPC mailboxes for [ny][nx] u8 boundary planes"""
@@ -314,15 +328,24 @@ class SlabOps:
         """union of the connected components of b (global, across slabs) that contain a voxel of a"""
         import torch
         e, c = self.e, self.c
-        r0 = e.through(a.data, b.data, conn)
         if c.world == 1:
-            return b.like(r0)
+            return b.like(e.through(a.data, b.data, conn))
         nzl = e.nz(b.data)
-        labels = e.components(b.data, conn)
-        lab_bot = e.to_tensor(e.crop_z(labels, 0, 1))[0].to(torch.int64) & 0xffffffff
-        lab_top = e.to_tensor(e.crop_z(labels, nzl - 1, 1))[0].to(torch.int64) & 0xffffffff
-        hit_bot = e.to_tensor(e.crop_z(r0, 0, 1))[0] != 0
-        hit_top = e.to_tensor(e.crop_z(r0, nzl - 1, 1))[0] != 0
+        stateful = self.use_ccl_state and hasattr(e, "ccl_create")
+        if stateful:
+            st = e.ccl_create(b.data, conn)
+            e.ccl_seed(st, a.data)
+            lab_bot, hit_bot = e.ccl_plane(st, 0)
+            lab_top, hit_top = e.ccl_plane(st, nzl - 1)
+            lab_bot, lab_top = lab_bot.to(torch.int64) & 0xffffffff, lab_top.to(torch.int64) & 0xffffffff
+            hit_bot, hit_top = hit_bot != 0, hit_top != 0
+        else:
+            r0 = e.through(a.data, b.data, conn)
+            labels = e.components(b.data, conn)
+            lab_bot = e.to_tensor(e.crop_z(labels, 0, 1))[0].to(torch.int64) & 0xffffffff
+            lab_top = e.to_tensor(e.crop_z(labels, nzl - 1, 1))[0].to(torch.int64) & 0xffffffff
+            hit_bot = e.to_tensor(e.crop_z(r0, 0, 1))[0] != 0
+            hit_top = e.to_tensor(e.crop_z(r0, nzl - 1, 1))[0] != 0
         tag = (c.rank + 1) << 32                       # global id of a local label: (rank+1, label)
         gid_bot = torch.where(lab_bot > 0, lab_bot + tag, torch.zeros_like(lab_bot))
         gid_top = torch.where(lab_top > 0, lab_top + tag, torch.zeros_like(lab_top))
@@ -336,6 +359,12 @@ class SlabOps:
         all_reached = c.all_gather_rows(reached[:, None]).cpu().numpy()[:, 0]
         newly = resolve_boundary_graph(all_pairs, all_reached)
         mine = newly[(newly >> 32) == c.rank + 1]
+        if stateful:
+            if mine.size:
+                e.ccl_flag(st, (mine & 0xffffffff).astype(np.uint32))
+            out = e.ccl_select(st)
+            e.ccl_destroy(st)
+            return b.like(out)
         if mine.size == 0:
             return b.like(r0)
         mine_t = torch.as_tensor(mine, device=gid_bot.device)
@@ -372,9 +401,15 @@ class SlabOps:
 
 def boundary_pairs(lower, upper, conn: int):
     """unique (id in the plane below, id in the plane above) pairs of adjacent foreground voxels.
-    lower/upper: [ny][nx] int64 ids, 0 = background.  6-adjacency: same (y, x); 26: 3x3."""
+    lower/upper: [ny][nx] int64 ids (tag << 32 | label), 0 = background.  6-adjacency: same
+    (y, x); 26: 3x3.  All ids of one plane carry the same tag, so a pair is packed into ONE int64
+    (label_below << 32 | label_above) and de-duplicated with a single 1-D unique."""
     import torch
     ny, nx = lower.shape
+    mask32 = 0xffffffff
+    tag_l = int(lower.max().item()) >> 32 << 32 if lower.numel() else 0
+    tag_u = int(upper.max().item()) >> 32 << 32 if upper.numel() else 0
+    lo32, up32 = lower & mask32, upper & mask32
     out = []
     shifts = [(0, 0)] if conn == 6 else [(dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
     for dy, dx in shifts:
@@ -382,39 +417,31 @@ def boundary_pairs(lower, upper, conn: int):
         xs, xe = max(0, -dx), min(nx, nx - dx)
         if ys >= ye or xs >= xe:
             continue
-        u = upper[ys:ye, xs:xe]
-        l = lower[ys + dy:ye + dy, xs + dx:xe + dx]
+        u = up32[ys:ye, xs:xe]
+        l = lo32[ys + dy:ye + dy, xs + dx:xe + dx]
         m = (u > 0) & (l > 0)
-        if bool(m.any()):
-            out.append(torch.unique(torch.stack([l[m], u[m]], dim=1), dim=0))
-    if not out:
+        out.append(((l << 32) | u)[m])
+    packed = torch.unique(torch.cat(out)) if out else torch.zeros(0, dtype=torch.int64, device=lower.device)
+    if packed.numel() == 0:
         return torch.zeros((0, 2), dtype=torch.int64, device=lower.device)
-    return torch.unique(torch.cat(out, dim=0), dim=0)
+    # (packed >> 32) of a value with bit 63 set would sign-extend: labels are < 2^31, so it cannot
+    return torch.stack([(packed >> 32) + tag_l, (packed & mask32) + tag_u], dim=1)
 
 
 def resolve_boundary_graph(pairs: np.ndarray, reached: np.ndarray) -> np.ndarray:
-    """Union-find over the boundary-label graph (replicated on every rank).  Returns the ids
-    that are NOT in `reached` but share a class with an id that is: those components become
+    """Connected components of the boundary-label graph (replicated on every rank).  Returns the
+    ids that are NOT in `reached` but share a class with an id that is: those components become
     reachable through a neighbouring slab."""
     if pairs.size == 0:
         return np.zeros(0, dtype=np.int64)
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
     ids, inv = np.unique(pairs.ravel(), return_inverse=True)
     edges = inv.reshape(-1, 2)
-    parent = np.arange(ids.size)
-    # vectorised union-find: hook the larger root under the smaller, then pointer-jump
-    while True:
-        ra, rb = parent[edges[:, 0]], parent[edges[:, 1]]
-        lo, hi = np.minimum(ra, rb), np.maximum(ra, rb)
-        changed = lo != hi
-        if not changed.any():
-            break
-        np.minimum.at(parent, hi[changed], lo[changed])
-        while True:
-            nxt = parent[parent]
-            if np.array_equal(nxt, parent):
-                break
-            parent = nxt
+    n = ids.size
+    graph = coo_matrix((np.ones(edges.shape[0], dtype=np.int8), (edges[:, 0], edges[:, 1])), shape=(n, n))
+    ncomp, comp = connected_components(graph, directed=False)
     is_reached = np.isin(ids, reached)
-    root_reached = np.zeros(ids.size, dtype=bool)
-    np.logical_or.at(root_reached, parent, is_reached)
-    return ids[root_reached[parent] & ~is_reached].astype(np.int64)
+    comp_reached = np.zeros(ncomp, dtype=bool)
+    comp_reached[comp[is_reached]] = True
+    return ids[comp_reached[comp] & ~is_reached].astype(np.int64)
