@@ -31,6 +31,22 @@ constexpr int kDigits = 1 << kRadixBits;         // 512
 constexpr int kMaxPasses = (32 + kRadixBits - 1) / kRadixBits;   // 4
 // plan[0] = number of passes to run, plan[1] = min key, plan[2] = max key (whole batch)
 
+// Lanes of `active` whose digit equals this lane's digit.  match.any does this in one instruction
+// but serialises over the distinct values in the warp (up to 32 with 512 digits; ncu: 70% of
+// the scatter kernel's stalls were waiting for it); kRadixBits ballots take constant time.
+__device__ __forceinline__ unsigned digit_peers(unsigned active, unsigned d, int nbits) {
+    unsigned peers = active;
+#pragma unroll
+    for (int b = 0; b < 9; b++) {
+        if (b < nbits) {
+            const bool bit = (d >> b) & 1u;
+            const unsigned bal = __ballot_sync(active, bit);
+            peers &= bit ? bal : ~bal;
+        }
+    }
+    return peers;
+}
+
 __device__ __forceinline__ unsigned sortable_key(float v) {
     v = v + 0.0f;  // -0.0 -> +0.0 so that both zeros get the same rank
     unsigned u = __float_as_uint(v);
@@ -159,7 +175,7 @@ rs_hist_kernel(const unsigned long long* __restrict__ buf0, const unsigned long 
             const unsigned active = __ballot_sync(0xffffffffu, ok);
             if (ok) {
                 const unsigned d = (keyhi[j] >> shift) & (kDigits - 1);
-                const unsigned peers = __match_any_sync(active, d);
+                const unsigned peers = digit_peers(active, d, kRadixBits);
                 if ((peers & ((1u << lane) - 1u)) == 0) cnt[warp][d] += __popc(peers);
             }
             __syncwarp();
@@ -268,7 +284,7 @@ rs_scatter_kernel(unsigned long long* __restrict__ buf0, unsigned long long* __r
             if (ok) {
                 const unsigned long long kv = kvs[j];
                 const unsigned d = ((unsigned)(kv >> 32) >> shift) & (kDigits - 1);
-                const unsigned peers = __match_any_sync(active, d);
+                const unsigned peers = digit_peers(active, d, kRadixBits);
                 const unsigned rank = __popc(peers & ((1u << lane) - 1u));
                 const int leader = __ffs(peers) - 1;
                 unsigned start = 0;
