@@ -264,6 +264,13 @@ VX_API int32_t vx_maxvol(vx_ctx ctx, vx_img a, int32_t conn, vx_img* out);
  * edt: exact Euclidean distance (physical units, image spacing) from every voxel
  * to the nearest voxel of a; 0 inside a; +inf when a is empty in that volume. */
 VX_API int32_t vx_edt(vx_ctx ctx, vx_img a, vx_img* out);
+/* The two halves of vx_edt for a caller that owns one z-slab of a larger volume: the squared
+ * distance after the x and y passes (in-plane, +inf where a plane holds no feature), and the z
+ * pass + square root on such a map once its columns have been re-partitioned so that every
+ * column is complete.  max_in: an upper bound of the finite values of
+ * `sq` (selects the exact-integer lower-envelope pass when everything stays below 2^24). */
+VX_API int32_t vx_edt_sq_xy(vx_ctx ctx, vx_img a, vx_img* out);
+VX_API int32_t vx_edt_z_from_sq(vx_ctx ctx, vx_img sq, double max_in, vx_img* out);
 /* Signed variant following the Maurer signed-distance convention: outside as
  * vx_edt; inside, minus the distance to the nearest voxel of a that has a
  * background neighbour (`conn`); 0 on those boundary voxels. */

@@ -99,6 +99,7 @@ def main():
             "through6": (lambda: ops.through(A, B, 6), lambda: ctx.through(WS, W, 6)),
             "distlt5": (lambda: ops.distlt(5.0, B), lambda: ctx.distlt(5.0, W)),
             "flt2": (lambda: ops.flt(2.0, B), lambda: ctx.distlt(2.0, ctx.distgeq(2.0, ctx.not_(W)))),
+            "edt": (lambda: ops.edt(B), lambda: ctx.edt(W)),
             "xcorr": (lambda: ops.cross_correlation(3.0, F, F, B, 0.0, 1.0, 32),
                       lambda: ctx.cross_correlation(3.0, FW, FW, W, 0.0, 1.0, 32)),
         }
@@ -141,7 +142,7 @@ def main():
     reach = {}
     for name, fn in (("near26", lambda: ops.near(B, 26)), ("through26", lambda: ops.through(A, B, 26)),
                      ("distlt5", lambda: ops.distlt(5.0, B)), ("flt2", lambda: ops.flt(2.0, B)),
-                     ("volume", lambda: ops.volume(B))):
+                     ("edt", lambda: ops.edt(B)), ("volume", lambda: ops.volume(B))):
         s = timed(fn)
         res[name] = {"ms": round(1e3 * s, 3), "gvox_per_s": round(n ** 3 / s / 1e9, 2)}
     reach["foreground_voxels"] = fg

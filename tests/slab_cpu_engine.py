@@ -38,6 +38,31 @@ class OracleEngine:
     def components(self, a, conn): return orc.components(a[0], conn).astype(np.uint32)[None]
     def dist(self, op, r, a): return orc.dist_cmp(a[0], op, r, self.sp)[None]
 
+    # the two halves of the distance transform, restated with the arithmetic contract of
+    # oracle/vx_oracle.c (binary32, one rounding per step, minimum over explicit offsets)
+    def edt_sq_xy(self, a):
+        v = a[0] != 0
+        nz, ny, nx = v.shape
+        sx, sy = np.float32(self.sp[0]), np.float32(self.sp[1])
+        out = np.full(v.shape, np.inf, np.float32)
+        dx2 = ((np.arange(nx, dtype=np.float32)[:, None] - np.arange(nx, dtype=np.float32)[None, :]) * sx) ** 2
+        for z in range(nz):
+            g1 = np.where(v[z][:, None, :], dx2[None].astype(np.float32), np.float32(np.inf)).min(axis=2)  # [ny][nx]
+            for y in range(ny):
+                dy2 = ((np.arange(ny, dtype=np.float32) - np.float32(y)) * sy) ** 2
+                out[z, y] = (g1 + dy2[:, None].astype(np.float32)).astype(np.float32).min(axis=0)
+        return out[None]
+
+    def edt_z_from_sq(self, sq, max_in):
+        g = sq[0]
+        nz = g.shape[0]
+        sz = np.float32(self.sp[2])
+        out = np.empty_like(g)
+        for z in range(nz):
+            dz2 = ((np.arange(nz, dtype=np.float32) - np.float32(z)) * sz) ** 2
+            out[z] = np.sqrt((g + dz2[:, None, None].astype(np.float32)).astype(np.float32).min(axis=0))
+        return out[None]
+
     def region_histogram(self, b, region, m, M, k):
         v = b[0][region[0] != 0].astype(np.float64)
         v = v[(v >= m) & (v < M)]

@@ -55,6 +55,13 @@ class ThreadComm:
         return (ptrs[self.rank - 1] if self.rank > 0 else None,
                 ptrs[self.rank + 1] if self.rank + 1 < self.world else None)
 
+    def exchange(self, send, recv_shapes):
+        import torch
+        torch.cuda.synchronize()
+        allsend = self._swap("e", [t.clone() for t in send])
+        torch.cuda.synchronize()
+        return [allsend[r][self.rank] for r in range(self.world)]
+
     def all_gather_rows(self, t):
         import torch
         torch.cuda.synchronize()
@@ -114,6 +121,7 @@ def test_slab_ops_two_threads_one_gpu(ctx, world, peer):
         want[f"distlt{r}"] = ctx.distlt(r, Si).numpy()[0]
         want[f"flt{r}"] = ctx.distlt(r, ctx.distgeq(r, ctx.not_(ctx.near(Si)))).numpy()[0]
     want["xcorr"] = ctx.cross_correlation(3.0, Fi, Fi, Bi, 0.0, 1.0, 16).numpy()[0]
+    want["edt"] = ctx.edt(Si).numpy()[0]
     assert want["through6"].sum() > a.sum() and want["through6"][shape[0] - 1].any()   # crosses every slab
     shared = ThreadComm.Shared(world)
     errors, results = [], {}
@@ -136,6 +144,7 @@ def test_slab_ops_two_threads_one_gpu(ctx, world, peer):
                 got[f"distlt{r}"] = ops.distlt(r, S)
                 got[f"flt{r}"] = ops.flt(r, ops.near(S))
             got["xcorr"] = ops.cross_correlation(3.0, F, F, B, 0.0, 1.0, 16)
+            got["edt"] = ops.edt(S)
             vol = ops.volume(B)
             z0, z1 = slab_bounds(shape[0], world)[rank]
             for k, sl in got.items():

@@ -61,6 +61,9 @@ def _worker(rank, world, port, q):
             check(f"distlt{r}", ops.distlt(r, S), orc.distlt(r, sparse, sp))
             check(f"distgeq{r}", ops.distgeq(r, S), orc.distgeq(r, sparse, sp))
             check(f"flt{r}", ops.flt(r, ops.near(S)), orc.flt(r, orc.near(sparse), sp))
+        want = orc.edt(sparse, sp)
+        check("edt", ops.edt(S), want)
+        check("edt_dense", ops.edt(B), orc.edt(b, sp))
         f = rng.random(shape, dtype=np.float32)
         F = ops.scatter_from_global(up, f, sp)
         want = orc.cross_correlation(3.0, f, f, b, 0.0, 1.0, 16, sp)

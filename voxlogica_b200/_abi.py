@@ -104,6 +104,8 @@ SIGNATURES = {
     "vx_maxvol": [u64, u64, i32, P(u64)],
     "vx_edt": [u64, u64, P(u64)],
     "vx_edt_signed": [u64, u64, i32, P(u64)],
+    "vx_edt_sq_xy": [u64, u64, P(u64)],
+    "vx_edt_z_from_sq": [u64, u64, f64, P(u64)],
     "vx_dist_lt": [u64, u64, f32, P(u64)],
     "vx_dist_leq": [u64, u64, f32, P(u64)],
     "vx_dist_geq": [u64, u64, f32, P(u64)],

@@ -503,6 +503,78 @@ static int edt_passes(OpGuard& og, const Image* A, void* out, int final_mode, fl
     return scratch_free(og.c, og.s, flags);
 }
 
+// ---- the two halves of the transform, for a caller that owns one z-slab ----
+// x and y passes only: squared distance inside each plane (+inf where the plane has no feature)
+static int edt_xy_only(OpGuard& og, const Image* A, float* out) {
+    const size_t total = A->count();
+    const unsigned long long rows = (unsigned long long)A->nb * A->nz * A->ny;
+    VX_REQUIRE(A->nx <= kMaxRowWords * 32, VX_E_UNSUPPORTED, "vx_edt supports nx <= %d", kMaxRowWords * 32);
+    const size_t n_rowflag = (size_t)A->nb * A->nz * ((A->ny + 31) / 32);
+    const size_t n_planeflag = (size_t)A->nb * ((A->nz + 31) / 32);
+    unsigned* flags = nullptr;
+    float* g1 = nullptr;
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (n_rowflag + n_planeflag), (void**)&flags));
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(float) * total, (void**)&g1));
+    VX_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (n_rowflag + n_planeflag), og.st));
+    {
+        VX_LAUNCH(og.c, og.s, "edt_x_kernel");
+        unsigned grid = (unsigned)((rows + kEdtThreads / 32 - 1) / (kEdtThreads / 32));
+        edt_x_kernel<<<grid, kEdtThreads, 0, og.st>>>((const uint8_t*)A->d, g1, flags, flags + n_rowflag, A->nx, A->ny,
+                                                     A->nz, rows, A->sp[0]);
+    }
+    VX_TRY(check_launch("edt_x_kernel"));
+    auto int_spacing = [](float sp) { return sp >= 1.0f && sp <= 64.0f && sp == floorf(sp); };
+    auto span2 = [](float sp, int n) { double d = (double)sp * (n - 1); return d * d; };
+    const bool env_y = int_spacing(A->sp[0]) && int_spacing(A->sp[1]) &&
+                       span2(A->sp[0], A->nx) + span2(A->sp[1], A->ny) < 16777216.0 && A->ny <= 65535 && A->ny > 1;
+    if (env_y) {
+        uint2* stack = nullptr;
+        VX_TRY(scratch_alloc(og.c, og.s, sizeof(uint2) * total, (void**)&stack));
+        const size_t ncols = (size_t)A->nb * A->nz * A->nx;
+        { VX_LAUNCH(og.c, og.s, "edt_env_kernel_y");
+          edt_env_kernel<1, EDT_MID><<<(unsigned)((ncols + 127) / 128), 128, 0, og.st>>>(
+              g1, out, stack, A->nx, A->ny, A->nz, ncols, (int)(A->sp[1] * A->sp[1]), 0.f, 0); }
+        VX_TRY(check_launch("edt y pass"));
+        VX_TRY(scratch_free(og.c, og.s, stack));
+    } else {
+        { VX_LAUNCH(og.c, og.s, "edt_axis_kernel_y");
+          edt_axis_kernel<1, EDT_MID><<<(unsigned)((total + kEdtThreads - 1) / kEdtThreads), kEdtThreads, 0, og.st>>>(
+              g1, out, flags, A->nx, A->ny, A->nz, total, A->sp[1], 0.f, 0); }
+        VX_TRY(check_launch("edt y pass"));
+    }
+    VX_TRY(scratch_free(og.c, og.s, g1));
+    return scratch_free(og.c, og.s, flags);
+}
+
+// z pass only, on a squared in-plane distance map; max_in bounds its finite values
+static int edt_z_only(OpGuard& og, const Image* S, float* out, double max_in) {
+    const size_t total = S->count();
+    auto int_spacing = [](float sp) { return sp >= 1.0f && sp <= 64.0f && sp == floorf(sp); };
+    const double span = (double)S->sp[2] * (S->nz - 1);
+    const bool env_z = int_spacing(S->sp[0]) && int_spacing(S->sp[1]) && int_spacing(S->sp[2]) &&
+                       max_in + span * span < 16777216.0 && S->nz <= 65535 && S->nz > 1;
+    if (env_z) {
+        uint2* stack = nullptr;
+        VX_TRY(scratch_alloc(og.c, og.s, sizeof(uint2) * total, (void**)&stack));
+        const size_t ncols = (size_t)S->nb * S->ny * S->nx;
+        { VX_LAUNCH(og.c, og.s, "edt_env_kernel_z");
+          edt_env_kernel<2, EDT_SQRT><<<(unsigned)((ncols + 127) / 128), 128, 0, og.st>>>(
+              (const float*)S->d, out, stack, S->nx, S->ny, S->nz, ncols, (int)(S->sp[2] * S->sp[2]), 0.f, 0); }
+        VX_TRY(check_launch("edt z pass"));
+        return scratch_free(og.c, og.s, stack);
+    }
+    // exact scan over all planes (no emptiness information for a map that came from elsewhere)
+    const size_t n_planeflag = (size_t)S->nb * ((S->nz + 31) / 32);
+    unsigned* planeflag = nullptr;
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * n_planeflag, (void**)&planeflag));
+    VX_CUDA(cudaMemsetAsync(planeflag, 0xff, sizeof(unsigned) * n_planeflag, og.st));
+    { VX_LAUNCH(og.c, og.s, "edt_axis_kernel_z");
+      edt_axis_kernel<2, EDT_SQRT><<<(unsigned)((total + kEdtThreads - 1) / kEdtThreads), kEdtThreads, 0, og.st>>>(
+          (const float*)S->d, out, planeflag, S->nx, S->ny, S->nz, total, S->sp[2], 0.f, 0); }
+    VX_TRY(check_launch("edt z pass"));
+    return scratch_free(og.c, og.s, planeflag);
+}
+
 static int dist_threshold(vx_ctx ctx, vx_img a, float r, bool strict, int invert, vx_img* out) {
     VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");
     VX_REQUIRE(r == r, VX_E_INVALID_ARG, "radius is NaN");
@@ -583,6 +655,32 @@ int32_t vx_edt(vx_ctx ctx, vx_img a, vx_img* out) {
     Image* O = nullptr;
     VX_TRY(new_image(og.c, VX_F32, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
     int rc = edt_passes(og, A, O->d, EDT_SQRT, 0.f, 0);
+    if (rc != VX_OK) { drop(O); return rc; }
+    return og.finish(O, out);
+}
+
+int32_t vx_edt_sq_xy(vx_ctx ctx, vx_img a, vx_img* out) {
+    VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");
+    OpGuard og;
+    VX_TRY(og.begin(ctx));
+    Image* A = nullptr;
+    VX_TRY(og.input(a, &A, VX_U8));
+    Image* O = nullptr;
+    VX_TRY(new_image(og.c, VX_F32, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
+    int rc = edt_xy_only(og, A, (float*)O->d);
+    if (rc != VX_OK) { drop(O); return rc; }
+    return og.finish(O, out);
+}
+
+int32_t vx_edt_z_from_sq(vx_ctx ctx, vx_img sq, double max_in, vx_img* out) {
+    VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");
+    OpGuard og;
+    VX_TRY(og.begin(ctx));
+    Image* S = nullptr;
+    VX_TRY(og.input(sq, &S, VX_F32));
+    Image* O = nullptr;
+    VX_TRY(new_image(og.c, VX_F32, S->nx, S->ny, S->nz, S->nb, S->sp, &O));
+    int rc = edt_z_only(og, S, (float*)O->d, max_in);
     if (rc != VX_OK) { drop(O); return rc; }
     return og.finish(O, out);
 }

@@ -368,6 +368,12 @@ class Context:
     def edt(self, a: Image) -> Image:
         return self._out(lambda o: self.lib.vx_edt(self.handle, a.handle, o))
 
+    def edt_sq_xy(self, a: Image) -> Image:
+        return self._out(lambda o: self.lib.vx_edt_sq_xy(self.handle, a.handle, o))
+
+    def edt_z_from_sq(self, sq: Image, max_in: float) -> Image:
+        return self._out(lambda o: self.lib.vx_edt_z_from_sq(self.handle, sq.handle, float(max_in), o))
+
     def edt_signed(self, a: Image, conn: int = A.VX_CONN_FULL) -> Image:
         return self._out(lambda o: self.lib.vx_edt_signed(self.handle, a.handle, conn, o))
 

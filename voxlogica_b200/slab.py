@@ -23,8 +23,12 @@ The local work is done by an *engine* (``CudaEngine`` = libvoxcuda through the C
 tests plug in an oracle-backed engine to exercise exactly this host logic with gloo).  Planes
 travel as torch tensors: zero-copy views of the HBM-resident images on the GPU path.
 
-Not decomposed yet: ``percentiles`` (needs a distributed sort), ``maxvol`` and the f32 ``edt``
-map (z pass needs an axis re-partition); they raise NotImplementedError.
+    edt (f32 map) ........ x and y passes local, then an all-to-all re-partition of the columns
+                           (each rank gets a range of rows of EVERY plane), z pass + sqrt on
+                           complete columns, all-to-all back
+
+Not decomposed yet: ``percentiles`` (needs a distributed sort) and ``maxvol``; they raise
+NotImplementedError.
 """
 from __future__ import annotations
 
@@ -111,6 +115,9 @@ class CudaEngine:
         self.ctx.sync()
         return tl[0, 0], th[0, 0]
 
+    def edt_sq_xy(self, a): return self.ctx.edt_sq_xy(a)
+    def edt_z_from_sq(self, sq, max_in): return self.ctx.edt_z_from_sq(sq, max_in)
+
     def dist(self, op, r, a):
         return {"<": self.ctx.distlt, "<=": self.ctx.distleq, ">=": self.ctx.distgeq, ">": self.ctx.distgt}[op](r, a)
 
@@ -154,6 +161,25 @@ class SlabComm:
 
     def barrier(self):
         self.dist.barrier(group=self.group)
+
+    def exchange(self, send, recv_shapes):
+        """personalised all-to-all built from point-to-point operations (works with NCCL and gloo)"""
+        import torch
+        dist = self.dist
+        recv = [torch.empty(shape, dtype=send[0].dtype, device=send[0].device) for shape in recv_shapes]
+        ops = []
+        for r in range(self.world):
+            if r == self.rank:
+                recv[r].copy_(send[r])
+                continue
+            ops.append(dist.P2POp(dist.isend, send[r].contiguous(), r, self.group))
+            ops.append(dist.P2POp(dist.irecv, recv[r], r, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            if send[0].is_cuda:
+                torch.cuda.current_stream(send[0].device).synchronize()
+        return recv
 
     def share_mailbox(self, ctx, ptr: int, handle: bytes):
         """exchange CUDA IPC handles; returns the device pointers of the (lower, upper) neighbours'
@@ -388,6 +414,38 @@ class SlabOps:
     def grow(self, a: Slab, b: Slab, conn: int = 26) -> Slab:
         return self.or_(a, self.touch(b, a, conn))
 
+    # ------------------------------------------------------------------ distance map
+    def edt(self, a: Slab) -> Slab:
+        """exact Euclidean distance map (f32): x and y passes on the local slab, then the columns
+        are re-partitioned (rank r gets rows [y0_r, y1_r) of EVERY plane), the z pass and the
+        square root run on complete columns, and the result travels back to the z-slabs."""
+        import torch
+        e, c = self.e, self.c
+        if c.world == 1:
+            sq = e.edt_sq_xy(a.data)
+            t = e.to_tensor(sq)
+            nz, ny, nx = t.shape
+            bound = (a.spacing[0] * (nx - 1)) ** 2 + (a.spacing[1] * (ny - 1)) ** 2
+            return a.like(e.edt_z_from_sq(sq, bound))
+        sq = e.to_tensor(e.edt_sq_xy(a.data))                    # [nzl][ny][nx]
+        nzl, ny, nx = sq.shape
+        zb = slab_bounds(a.nz_global, c.world)
+        if ny < c.world:
+            raise ValueError(f"cannot re-partition {ny} rows over {c.world} ranks")
+        yb = slab_bounds(ny, c.world)
+        my0, my1 = yb[c.rank]
+        # forward: my planes, every rank's rows  ->  every rank's planes, my rows
+        send = [sq[:, y0:y1, :].contiguous() for (y0, y1) in yb]
+        recv = c.exchange(send, [(z1 - z0, my1 - my0, nx) for (z0, z1) in zb])
+        cols = torch.cat(recv, dim=0)                            # [nz][my rows][nx]
+        bound = (a.spacing[0] * (nx - 1)) ** 2 + (a.spacing[1] * (ny - 1)) ** 2
+        like = Slab(None, 0, a.nz_global, a.nz_global, a.spacing)
+        d = e.to_tensor(e.edt_z_from_sq(e.from_tensor(cols, like), bound))
+        # back: my rows of every plane -> my planes, all rows
+        send = [d[z0:z1].contiguous() for (z0, z1) in zb]
+        recv = c.exchange(send, [(nzl, y1 - y0, nx) for (y0, y1) in yb])
+        return a.like(e.from_tensor(torch.cat(recv, dim=1), a))
+
     # ------------------------------------------------------------------ not decomposed yet
     def percentiles(self, *a, **k):
         raise NotImplementedError("percentiles on slabs needs a distributed sort (DESIGN.md section 6)")
@@ -395,8 +453,6 @@ class SlabOps:
     def maxvol(self, *a, **k):
         raise NotImplementedError("maxvol on slabs is not implemented yet (DESIGN.md section 6)")
 
-    def edt(self, *a, **k):
-        raise NotImplementedError("the f32 distance map on slabs needs a z re-partition (DESIGN.md section 6)")
 
 
 def boundary_pairs(lower, upper, conn: int):
