@@ -310,7 +310,7 @@ def run_ours(args):
     import threading
     del flair
     nthr = max(1, args.threads)
-    pins_in = [ctx.host_alloc(B * NVOX * 4) for _ in range(nthr)]
+    pins_in = [ctx.host_alloc(B * NVOX * 4, write_combined=args.wc) for _ in range(nthr)]
     pins_out = [ctx.host_alloc(B * NVOX) for _ in range(nthr)]
     for t in range(nthr):
         C.memmove(pins_in[t], host.ctypes.data, host.nbytes)
@@ -417,6 +417,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--threads", type=int, default=3,
                     help="host threads (= CUDA streams of the library) that take the steps in turn")
+    ap.add_argument("--wc", action="store_true", help="write-combined pinned staging buffers for the uploads")
     ap.add_argument("--no-prof", action="store_true", help="keep per-kernel events out of the timed region")
     args = ap.parse_args()
     if args.impl == "reference":

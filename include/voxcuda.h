@@ -144,6 +144,9 @@ VX_API int32_t vx_copy_planes_to(vx_ctx ctx, vx_img img, int32_t z0, int32_t nz,
 
 /* Pinned host staging memory for the end-to-end path. */
 VX_API int32_t vx_host_alloc(size_t bytes, void** out);
+/* Write-combined pinned memory: for upload staging buffers the CPU only writes (sequentially)
+ * and the GPU reads -- not snooped during the DMA; very slow for CPU reads. */
+VX_API int32_t vx_host_alloc_wc(size_t bytes, void** out);
 VX_API int32_t vx_host_free(void* p);
 
 /* Device-memory accounting ("garbage collection", Greta.pdf p.78-79): live image

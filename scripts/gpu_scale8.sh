@@ -15,4 +15,11 @@ for f in sorted(glob.glob("gpurun_out/scale8_n*.json")):
 P
 tail -3 gpurun_out/scale8.err
 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 scripts/slab_gpu.py --size 128 --check 2>&1 | grep -E "SLAB|Error|error" | head
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29522 scripts/slab_gpu.py --size 2048 --reps 2 > gpurun_out/slab_2048_n8.json 2> gpurun_out/slab8.err; tail -1 gpurun_out/slab_2048_n8.json; tail -3 gpurun_out/slab8.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29523 scripts/slab_gpu.py --size 128 --check --peer 2>&1 | grep -E "SLAB|Error|error" | head
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29522 scripts/slab_gpu.py --size 2048 --reps 2 --peer > gpurun_out/slab_2048_n8.json 2> gpurun_out/slab8.err; tail -1 gpurun_out/slab_2048_n8.json; tail -3 gpurun_out/slab8.err
+python scripts/batch256.py > gpurun_out/batch256_n1.json 2>> gpurun_out/scale8.err; tail -1 gpurun_out/batch256_n1.json
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29524 scripts/batch256.py > gpurun_out/batch256_n8.json 2>> gpurun_out/scale8.err; tail -1 gpurun_out/batch256_n8.json
+grep -h numa gpurun_out/scale8_n8.json | head -c 0; python - <<'P'
+import json
+d=json.loads(open("gpurun_out/scale8_n8.json").read().strip().splitlines()[-1]); print("numa:", d["e2e"].get("numa"))
+P

@@ -69,6 +69,7 @@ SIGNATURES = {
     "vx_ipc_free": [u64, C.c_void_p],
     "vx_copy_planes_to": [u64, u64, i32, i32, C.c_void_p],
     "vx_host_alloc": [C.c_size_t, P(C.c_void_p)],
+    "vx_host_alloc_wc": [C.c_size_t, P(C.c_void_p)],
     "vx_host_free": [C.c_void_p],
     "vx_mem_info": [u64, P(u64), P(u64), P(u64)],
     "vx_mem_trim": [u64, u64],

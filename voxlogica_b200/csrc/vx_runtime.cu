@@ -663,6 +663,11 @@ int32_t vx_host_alloc(size_t bytes, void** out) {
     VX_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
     return VX_OK;
 }
+int32_t vx_host_alloc_wc(size_t bytes, void** out) {
+    VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");
+    VX_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocWriteCombined));
+    return VX_OK;
+}
 int32_t vx_host_free(void* p) {
     if (p) VX_CUDA(cudaFreeHost(p));
     return VX_OK;

@@ -150,9 +150,10 @@ class Context:
     def download_ptr(self, img: Image, ptr: int, nbytes: int) -> None:
         check(self.lib.vx_download(self.handle, img.handle, C.c_void_p(ptr), nbytes))
 
-    def host_alloc(self, nbytes: int) -> int:
+    def host_alloc(self, nbytes: int, write_combined: bool = False) -> int:
         p = C.c_void_p()
-        check(self.lib.vx_host_alloc(nbytes, C.byref(p)))
+        fn = self.lib.vx_host_alloc_wc if write_combined else self.lib.vx_host_alloc
+        check(fn(nbytes, C.byref(p)))
         return p.value
 
     def host_free(self, ptr: int) -> None:
