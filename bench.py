@@ -39,11 +39,17 @@ NVOX = BRATS[0] * BRATS[1] * BRATS[2]
 # algorithmic HBM bytes per voxel per launch (SURVEY.md section 8d / DESIGN.md kernel table)
 ALG_BYTES = {
     "xcorr_kernel": 5.0,             # u8 bins in, f32 coefficient out (13 B/voxel for the whole operator)
-    "pointwise_program_kernel": None,  # depends on the program; reported per launch mix
+    "pointwise_program_kernel": None,  # depends on the program (5 for a threshold, 8/12 for arithmetic)
+    "boolean_program_kernel": None,    # 2 (not) or 3 (and/or) per instruction chain
     "morph16_kernel": 2.0, "ball_or_kernel": 1.0 + 1.0 / 8, "pack_bits_kernel": 1.0 + 1.0 / 8,
-    "ccl_init_kernel": 5.0, "ccl_merge_kernel": 4.0, "ccl_select_kernel": 5.0, "ccl_seed_kernel": 1.0,
-    "xc_bin_kernel": 5.0, "xc_region_hist_kernel": 5.0, "pc_compact_kernel": 5.0, "pc_rank_kernel": 12.0,
-    "rs_hist_kernel": 4.0, "rs_scatter_kernel": 16.0, "reduce_f32_kernel": 4.0, "reduce_volume_kernel": 1.0,
+    "xdilate_bits_kernel": None,     # 1/8 in, emax/8 out: depends on the radius
+    # union-find kernels as launched by `through`: bits in/out are 1/8 B per voxel, labels are sparse
+    "ccl_init_kernel": 1.0 + 1.0 / 8, "ccl_merge_kernel": None, "ccl_flatten_kernel": None,
+    "ccl_select_kernel": 1.0 + 1.0 / 8, "ccl_seed_kernel": 1.0 + 1.0 / 8,
+    "xc_bin_kernel": 5.0, "xc_region_hist_kernel": 2.0, "pc_compact_kernel": 5.0,
+    # the sort kernels move 8-byte pairs of the MASKED voxels only: no per-voxel figure
+    "pc_rank_kernel": None, "rs_hist_kernel": None, "rs_scatter_kernel": None, "rs_rowscan_kernel": None,
+    "reduce_f32_kernel": 4.0, "reduce_volume_kernel": 1.0,
     "border_kernel": 1.0, "edt_x_kernel": 5.0, "edt_axis_kernel_y": 8.0, "edt_axis_kernel_z": 8.0,
 }
 
@@ -340,6 +346,24 @@ def run_ours(args):
     ms_e2e = (time.perf_counter() - t0) * 1e3      # all streams drained: host clock around device work
     barrier()
 
+    # ---- per-kernel table from an untimed pass with ONE host thread (one stream): launch
+    # durations without other streams' kernels sharing the SMs, which is what a roofline
+    # fraction of a single kernel means.  (Inside the timed region `args.threads` streams overlap,
+    # so the per-launch times there include waiting for SMs held by other steps' kernels.)
+    serial = {}
+    if rank == 0 and not args.no_prof:
+        flair = ctx.upload(host)
+        ctx.sync()
+        step_resident(flair)
+        ctx.sync()
+        ctx.prof_reset(); ctx.prof_enable(True)
+        for _ in range(4):
+            step_resident(flair)
+        ctx.sync()
+        ctx.prof_enable(False)
+        serial = ctx.prof_report()
+        del flair
+
     if dist is not None:
         t = torch.tensor([ms, ms_e2e], device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -374,6 +398,16 @@ def run_ours(args):
     kernels = {k: {"launches": c, "ms_total": round(m, 4), "share": round(m / tot_ms, 4),
                    "gvox_per_s": round(B * NVOX / ((m / c) * 1e-3) / 1e9, 2)}
                for k, (c, m) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    peak_v = peak
+    kernels_serial = {}
+    ser_tot = sum(v[1] for v in serial.values()) or 1.0
+    for k, (c, m) in sorted(serial.items(), key=lambda kv: -kv[1][1]):
+        row = {"launches_per_step": c / 4.0, "avg_launch_ms": round(m / c, 5), "share": round(m / ser_tot, 4)}
+        ab = ALG_BYTES.get(k)
+        if ab:
+            gbs = ab * per_launch_vox / ((m / c) * 1e-3) / 1e9
+            row.update({"alg_bytes_per_voxel": ab, "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak_v, 4)})
+        kernels_serial[k] = row
     cb = cpu_baseline(os.cpu_count() or 1) if world == 1 and not args.no_cpu_baseline else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -398,6 +432,10 @@ def run_ours(args):
                              "wavefronts, 70% issue active, DRAM 0.9%), not by HBM (SURVEY.md 8d); the fraction "
                              "against HBM is reported as the contract requires" if name == "xcorr_kernel" else ""},
         "kernels": kernels,
+        "kernels_serial": {"note": "one host thread / one stream, 4 untimed steps after the timed region: "
+                                   "per-launch durations without cross-stream sharing of the SMs; "
+                                   "achieved_gbs = algorithmic bytes per launch / duration",
+                           "ms_per_step": round(ser_tot / 4.0, 4), "kernels": kernels_serial},
         "clocks": clocks,
         "cpu_baseline": cb,
         "gtv_voxels_last_step": [float(v) for v in (vols if vols is not None else [])][:4],

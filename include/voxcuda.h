@@ -315,6 +315,10 @@ VX_API int32_t vx_max(vx_ctx ctx, vx_img a, double* out);
 VX_API int32_t vx_min_masked(vx_ctx ctx, vx_img a, vx_img mask, double* out);
 VX_API int32_t vx_max_masked(vx_ctx ctx, vx_img a, vx_img mask, double* out);
 VX_API int32_t vx_sum(vx_ctx ctx, vx_img a, double* out);
+/* min and max of every volume from ONE pass over the image (the histogram range of
+ * crossCorrelation, Greta.pdf p.48 similarTo: min(intensity(flair)), max(intensity(flair))).
+ * mask = 0: whole image.  Same values as vx_min / vx_max. */
+VX_API int32_t vx_minmax(vx_ctx ctx, vx_img a, vx_img mask, double* out_min, double* out_max);
 /* percentiles(img, mask, correction): for a voxel x in mask,
  *   ( #{y in mask : img(y) < img(x)} + correction * #{y in mask : img(y) = img(x)} ) / |mask|
  * and 0 outside the mask (Greta.pdf p.52 percentiles(intensity, brain)). */

@@ -110,6 +110,8 @@ module Native =
     [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
     extern int vx_max(uint64 ctx, uint64 a, double[] out)
     [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_minmax(uint64 ctx, uint64 a, uint64 mask, double[] outMin, double[] outMax)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
     extern int vx_percentiles(uint64 ctx, uint64 a, uint64 mask, double correction, uint64& out)
 
 exception VoxCudaException of code: int * message: string
@@ -159,6 +161,11 @@ type CudaModel(device: int) =
     member _.Volume(a: ImageHandle) = let r = [| 0.0 |] in check (Native.vx_volume (ctx, a.Value, r)); r.[0]
     member _.Min(a: ImageHandle) = let r = [| 0.0 |] in check (Native.vx_min (ctx, a.Value, r)); r.[0]
     member _.Max(a: ImageHandle) = let r = [| 0.0 |] in check (Native.vx_max (ctx, a.Value, r)); r.[0]
+    /// min and max from one pass (the scheduler can serve both `min(img)` and `max(img)` tasks from it)
+    member _.MinMax(a: ImageHandle) =
+        let lo, hi = [| 0.0 |], [| 0.0 |]
+        check (Native.vx_minmax (ctx, a.Value, 0UL, lo, hi))
+        lo.[0], hi.[0]
 
     /// pinned managed array -> HBM (dtype 1 = u8 boolean, 2 = f32 number)
     member _.Upload(data: Array, dtype: int, nx: int, ny: int, nz: int, spacing: float32[]) =

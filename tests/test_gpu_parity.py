@@ -266,6 +266,17 @@ def test_reductions(ctx, oracle, shape):
     assert np.array_equal(ctx.min(A, M), [oracle.min_(a[i], m[i]) for i in range(nb)])
     assert np.array_equal(ctx.max(A, M), [oracle.max_(a[i], m[i]) for i in range(nb)])
     np.testing.assert_allclose(ctx.sum(A), [oracle.sum_(a[i]) for i in range(nb)], rtol=1e-9, atol=1e-9)
+    # one-pass min+max: the same values as the separate reductions, masked or not, NaNs skipped
+    lo, hi = ctx.minmax(A)
+    assert np.array_equal(lo, ctx.min(A)) and np.array_equal(hi, ctx.max(A))
+    lo, hi = ctx.minmax(A, M)
+    assert np.array_equal(lo, ctx.min(A, M)) and np.array_equal(hi, ctx.max(A, M))
+    b = a.copy()
+    b.reshape(nb, -1)[:, ::7] = np.nan
+    lo, hi = ctx.minmax(ctx.upload(b))
+    for i in range(nb):      # a volume of NaNs only has no minimum: +inf / -inf, like an empty mask
+        some = not np.all(np.isnan(b[i]))
+        assert lo[i] == (np.nanmin(b[i]) if some else np.inf) and hi[i] == (np.nanmax(b[i]) if some else -np.inf)
 
 
 @pytest.mark.parametrize("shape", SHAPES + [(2, 12, 40, 50)])
@@ -333,6 +344,54 @@ def test_cross_correlation_spacing_and_empty_region(ctx, oracle):
     assert np.array_equal(got[0].view(np.uint32), want.view(np.uint32))
     none = ctx.cross_correlation(3.0, A, A, ctx.ff(A), 0.0, 1.0, 20).numpy()
     assert np.all(none == 0)
+
+
+def test_cross_correlation_wide_ball_and_out_of_range(ctx, oracle):
+    """radius beyond the ring kernel's x halo (the direct sliding kernel), values outside [m, M),
+    NaN voxels (never counted), an interval with m == M (nothing counted: all zeros)"""
+    shape = (1, 5, 24, 40)
+    rng = np.random.default_rng(35)
+    a = rng.random(shape).astype(np.float32) * 2 - 0.5        # a third of the values fall outside [0, 1)
+    a[0, 2, 3, 4:9] = np.nan
+    reg = rnd_mask(shape, 0.4, 36)
+    A, R = ctx.upload(a), ctx.upload(reg)
+    for rho in (9.0, 0.0):
+        got = ctx.cross_correlation(rho, A, A, R, 0.0, 1.0, 12).numpy()[0]
+        want = oracle.cross_correlation(rho, a[0], a[0], reg[0], 0.0, 1.0, 12)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), rho
+    assert np.all(ctx.cross_correlation(2.0, A, A, R, 0.5, 0.5, 12).numpy() == 0)
+    with pytest.raises(Exception):
+        ctx.cross_correlation(2.0, A, A, R, 0.0, 1.0, 255)     # more bins than the u8 bin image can hold
+
+
+def test_large_radius_distance_fallback(ctx, oracle):
+    """radii whose ball does not fit the bit-dilation tables take the exact-EDT threshold path"""
+    shape = (1, 6, 40, 150)
+    a = rnd_mask(shape, 0.0008, 37)
+    a[0, 0, 0, 0] = 1
+    for sp in ((1.0, 1.0, 1.0), (0.5, 1.0, 2.0)):
+        A = ctx.upload(a, spacing=sp)
+        for r in (33.0, 40.5):
+            assert np.array_equal(ctx.distlt(r, A).numpy()[0], oracle.distlt(r, a[0], sp)), (sp, r)
+            assert np.array_equal(ctx.distgt(r, A).numpy()[0], oracle.distgt(r, a[0], sp)), (sp, r)
+
+
+def test_limits_are_reported(ctx):
+    """a volume of 2^31 voxels or more is refused with VX_E_UNSUPPORTED (slab-decompose it),
+    shape and dtype mismatches with their own codes -- never a crash"""
+    from voxlogica_b200 import _abi as A
+    import ctypes as C
+    out = A.u64()
+    rc = ctx.lib.vx_upload_batch(ctx.handle, C.c_void_p(1), A.VX_U8, 2048, 2048, 512, 1, None, C.byref(out))
+    assert rc == A.VX_E_UNSUPPORTED and b"slab" in ctx.lib.vx_last_error()
+    a = ctx.upload(np.zeros((2, 3, 4), np.uint8))
+    b = ctx.upload(np.zeros((2, 3, 5), np.uint8))
+    f = ctx.upload(np.zeros((2, 3, 4), np.float32))
+    for fn, code in ((lambda: ctx.and_(a, b), A.VX_E_SHAPE_MISMATCH), (lambda: ctx.near(f), A.VX_E_DTYPE),
+                     (lambda: ctx.near(a, 18), A.VX_E_INVALID_ARG), (lambda: ctx.crop_z(a, 1, 5), A.VX_E_INVALID_ARG)):
+        with pytest.raises(A.VoxError) as ei:
+            fn()
+        assert ei.value.code == code
 
 
 # ------------------------------------------------------------------ runtime

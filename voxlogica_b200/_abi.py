@@ -121,6 +121,7 @@ SIGNATURES = {
     "vx_min_masked": [u64, u64, u64, P(f64)],
     "vx_max_masked": [u64, u64, u64, P(f64)],
     "vx_sum": [u64, u64, P(f64)],
+    "vx_minmax": [u64, u64, u64, P(f64), P(f64)],
     "vx_percentiles": [u64, u64, u64, f64, P(u64)],
     "vx_event_create": [u64, P(u64)],
     "vx_event_record": [u64, u64],

@@ -344,14 +344,16 @@ ball_or_kernel(const unsigned* __restrict__ D, uint8_t* __restrict__ out, int nx
     unsigned acc = 0;
     if (y >= wy && y + wy < ny && z >= wz && z + wz < nz) {
         int t = 0;
-        for (; t + 4 <= nball; t += 4) {
+        // entries come centre-first: next to a dense feature set (the erosion half of
+        // `filter`: distgeq(r, !a)) the word is full after a few of them and the rest is skipped
+        for (; t + 4 <= nball && acc != 0xffffffffu; t += 4) {
             const unsigned a0 = __ldg(base + __ldg(boff + t)), a1 = __ldg(base + __ldg(boff + t + 1));
             const unsigned a2 = __ldg(base + __ldg(boff + t + 2)), a3 = __ldg(base + __ldg(boff + t + 3));
             acc |= (a0 | a1) | (a2 | a3);
         }
         for (; t < nball; t++) acc |= __ldg(base + __ldg(boff + t));
     } else {
-        for (int t = 0; t < nball; t++) {
+        for (int t = 0; t < nball && acc != 0xffffffffu; t++) {
             const int dyz = __ldg(bdyz + t);
             const int yy = y + (int)(signed char)(dyz & 0xff), zz = z + (int)(signed char)((dyz >> 8) & 0xff);
             if (yy < 0 || yy >= ny || zz < 0 || zz >= nz) continue;
@@ -610,9 +612,15 @@ static int dist_threshold(vx_ctx ctx, vx_img a, float r, bool strict, int invert
             std::vector<long long> tab((size_t)ball.n + ((size_t)ball.n + 1) / 2);
             int* dyz = reinterpret_cast<int*>(tab.data() + ball.n);
             int wy = 0, wz = 0;
-            for (int t = 0; t < ball.n; t++) {
-                tab[t] = (long long)ball.e[t] * (long long)nwords + ((long long)ball.dz[t] * A->ny + ball.dy[t]) * nwx;
-                dyz[t] = (int)(uint8_t)ball.dy[t] | ((int)(uint8_t)ball.dz[t] << 8);
+            std::vector<int> order(ball.n);
+            for (int t = 0; t < ball.n; t++) order[t] = t;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) {   // centre first
+                return ball.dy[a] * ball.dy[a] + ball.dz[a] * ball.dz[a] < ball.dy[b] * ball.dy[b] + ball.dz[b] * ball.dz[b];
+            });
+            for (int i = 0; i < ball.n; i++) {
+                const int t = order[i];
+                tab[i] = (long long)ball.e[t] * (long long)nwords + ((long long)ball.dz[t] * A->ny + ball.dy[t]) * nwx;
+                dyz[i] = (int)(uint8_t)ball.dy[t] | ((int)(uint8_t)ball.dz[t] << 8);
                 wy = std::max(wy, std::abs((int)ball.dy[t]));
                 wz = std::max(wz, std::abs((int)ball.dz[t]));
             }

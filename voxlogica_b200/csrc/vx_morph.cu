@@ -19,57 +19,67 @@ namespace vx {
 constexpr int kMorphZL = 16;  // planes marched by one thread
 
 struct Plane {
-    uint4 c;        // FULL: OR of rows y-1,y,y+1;  FACE: row y
-    uint4 s;        // FACE only: OR of rows y-1,y+1
+    uint4 c;        // FULL: rows y-1,y,y+1 combined;  FACE: row y
+    uint4 s;        // FACE only: rows y-1,y+1 combined
     unsigned lb, rb;  // edge bytes (x-1, x+16) of `c`, only meaningful on strip-edge lanes
 };
 
-__device__ __forceinline__ uint4 or4(uint4 a, uint4 b) {
-    return make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w);
+// Dilation combines with OR, erosion with AND; a voxel outside the image is the identity of
+// the combine (0 resp. 1), so it never dilates in and never erodes.
+template <bool ERODE>
+__device__ __forceinline__ unsigned comb(unsigned a, unsigned b) { return ERODE ? (a & b) : (a | b); }
+template <bool ERODE>
+__device__ __forceinline__ uint4 comb4(uint4 a, uint4 b) {
+    return make_uint4(comb<ERODE>(a.x, b.x), comb<ERODE>(a.y, b.y), comb<ERODE>(a.z, b.z), comb<ERODE>(a.w, b.w));
 }
 
+// rows y-1, y, y+1 of one plane at this thread's 16 voxels; p = address of the centre row's
+// chunk, nullptr when the plane does not exist.  Everything that does not depend on z (row
+// validity, strip-edge flags, the row pitch) is computed once by the caller: the z loop is
+// three 128-bit loads and a dozen logic instructions (the first version re-derived every
+// address with 64-bit multiplies: 190 instructions per plane, issue-bound at 69 %).
+template <bool FULL, bool ERODE>
+__device__ __forceinline__ Plane load_plane(const uint8_t* __restrict__ p, int nx, bool up, bool dn, bool need_l,
+                                            bool need_r) {
+    constexpr unsigned ID = ERODE ? 0x01010101u : 0u;
+    Plane r;
+    r.c = r.s = make_uint4(ID, ID, ID, ID);
+    r.lb = r.rb = ID & 1u;
+    if (p == nullptr) return r;
+    const uint4 wc = __ldg(reinterpret_cast<const uint4*>(p));
+    uint4 wu = make_uint4(ID, ID, ID, ID), wd = wu;
+    if (up) wu = __ldg(reinterpret_cast<const uint4*>(p - nx));
+    if (dn) wd = __ldg(reinterpret_cast<const uint4*>(p + nx));
+    if (FULL) {
+        r.c = comb4<ERODE>(comb4<ERODE>(wc, wu), wd);
+        if (need_l) {
+            r.lb = __ldg(p - 1);
+            if (up) r.lb = comb<ERODE>(r.lb, (unsigned)__ldg(p - nx - 1));
+            if (dn) r.lb = comb<ERODE>(r.lb, (unsigned)__ldg(p + nx - 1));
+        }
+        if (need_r) {
+            r.rb = __ldg(p + 16);
+            if (up) r.rb = comb<ERODE>(r.rb, (unsigned)__ldg(p - nx + 16));
+            if (dn) r.rb = comb<ERODE>(r.rb, (unsigned)__ldg(p + nx + 16));
+        }
+    } else {
+        r.c = wc;
+        r.s = comb4<ERODE>(wu, wd);
+        if (need_l) r.lb = __ldg(p - 1);
+        if (need_r) r.rb = __ldg(p + 16);
+    }
+    return r;
+}
+
+// grid: x = strips * ceil(ny/16), y = ceil(nz/ZL), z = nb;  block (16,16).
 // lo / hi: optional halo planes [ny][nx] standing for z = -1 and z = nz (the boundary planes of
 // the neighbouring slabs of a z-decomposed volume; they may live in a peer GPU's memory, read
 // over NVLink).  nullptr = the volume really ends there.
 template <bool FULL, bool ERODE>
-__device__ __forceinline__ Plane load_plane(const uint8_t* __restrict__ vol, int nx, int ny, int nz,
-                                            int xc, int y, int z, bool col_ok, bool need_l,
-                                            bool need_r, const uint8_t* __restrict__ lo,
-                                            const uint8_t* __restrict__ hi) {
-    Plane p;
-    p.c = make_uint4(0, 0, 0, 0);
-    p.s = make_uint4(0, 0, 0, 0);
-    p.lb = p.rb = 0;
-    if (!col_ok) return p;
-    const uint8_t* plane;
-    if (z >= 0 && z < nz) plane = vol + (size_t)z * ny * nx;
-    else if (z == -1 && lo != nullptr) plane = lo;
-    else if (z == nz && hi != nullptr) plane = hi;
-    else return p;
-    const unsigned flip = ERODE ? 0x01010101u : 0u;
-#pragma unroll
-    for (int dy = -1; dy <= 1; dy++) {
-        int yy = y + dy;
-        if (yy < 0 || yy >= ny) continue;
-        const uint8_t* row = plane + (size_t)yy * nx + (size_t)xc * 16;
-        uint4 w = __ldg(reinterpret_cast<const uint4*>(row));
-        w.x ^= flip; w.y ^= flip; w.z ^= flip; w.w ^= flip;
-        if (FULL || dy == 0) {
-            p.c = or4(p.c, w);
-            if (need_l) p.lb |= (unsigned)(__ldg(row - 1) ^ (ERODE ? 1 : 0));
-            if (need_r) p.rb |= (unsigned)(__ldg(row + 16) ^ (ERODE ? 1 : 0));
-        } else {
-            p.s = or4(p.s, w);
-        }
-    }
-    return p;
-}
-
-// grid: x = strips * ceil(ny/16), y = ceil(nz/ZL), z = nb;  block (16,16)
-template <bool FULL, bool ERODE>
 __global__ void __launch_bounds__(256)
 morph16_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int nx, int ny, int nz,
                const uint8_t* __restrict__ lo_all, const uint8_t* __restrict__ hi_all) {
+    constexpr unsigned IDB = ERODE ? 1u : 0u;
     const int ncx = nx >> 4;
     const int nstrips = (ncx + 15) >> 4;
     const int strip = blockIdx.x % nstrips, yblk = blockIdx.x / nstrips;
@@ -77,48 +87,51 @@ morph16_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int nx
     const int xc = strip * 16 + lane16;
     const int y = yblk * 16 + threadIdx.y;
     const int z0 = blockIdx.y * kMorphZL;
-    const size_t voff = (size_t)blockIdx.z * nx * ny * nz;
-    const uint8_t* vol = in + voff;
-    uint8_t* ovol = out + voff;
+    const size_t ps = (size_t)nx * ny;
+    const size_t voff = (size_t)blockIdx.z * ps * nz;
     const bool col_ok = xc < ncx && y < ny;
     const bool need_l = col_ok && lane16 == 0 && xc > 0;           // left neighbour in another strip
     const bool need_r = col_ok && lane16 == 15 && xc + 1 < ncx;    // right neighbour in another strip
-    const uint8_t* lo = lo_all ? lo_all + (size_t)blockIdx.z * nx * ny : nullptr;
-    const uint8_t* hi = hi_all ? hi_all + (size_t)blockIdx.z * nx * ny : nullptr;
+    const bool up = y > 0, dn = y + 1 < ny;
+    const size_t roff = (size_t)y * nx + (size_t)xc * 16;          // this thread's chunk inside a plane
+    const uint8_t* lo = (lo_all && col_ok) ? lo_all + (size_t)blockIdx.z * ps + roff : nullptr;
+    const uint8_t* hi = (hi_all && col_ok) ? hi_all + (size_t)blockIdx.z * ps + roff : nullptr;
+    const uint8_t* pz = in + voff + (size_t)z0 * ps + roff;        // plane z0
+    uint8_t* oz = out + voff + (size_t)z0 * ps + roff;
 
-    Plane prev = load_plane<FULL, ERODE>(vol, nx, ny, nz, xc, y, z0 - 1, col_ok, need_l, need_r, lo, hi);
-    Plane cur = load_plane<FULL, ERODE>(vol, nx, ny, nz, xc, y, z0, col_ok, need_l, need_r, lo, hi);
+    Plane prev = load_plane<FULL, ERODE>(!col_ok ? nullptr : (z0 > 0 ? pz - ps : lo), nx, up, dn, need_l, need_r);
+    Plane cur = load_plane<FULL, ERODE>(col_ok ? pz : nullptr, nx, up, dn, need_l, need_r);
     const int zend = min(z0 + kMorphZL, nz);
     for (int z = z0; z < zend; z++) {
-        Plane next = load_plane<FULL, ERODE>(vol, nx, ny, nz, xc, y, z + 1, col_ok, need_l, need_r, lo, hi);
+        pz += ps;
+        Plane next = load_plane<FULL, ERODE>(!col_ok ? nullptr : (z + 1 < nz ? pz : hi), nx, up, dn, need_l, need_r);
         uint4 C, E;
         unsigned lb, rb;
         if (FULL) {
-            C = or4(or4(prev.c, cur.c), next.c);
-            E = make_uint4(0, 0, 0, 0);
-            lb = prev.lb | cur.lb | next.lb;
-            rb = prev.rb | cur.rb | next.rb;
+            C = comb4<ERODE>(comb4<ERODE>(prev.c, cur.c), next.c);
+            E = C;   // unused
+            lb = comb<ERODE>(comb<ERODE>(prev.lb, cur.lb), next.lb);
+            rb = comb<ERODE>(comb<ERODE>(prev.rb, cur.rb), next.rb);
         } else {
             C = cur.c;
-            E = or4(or4(prev.c, next.c), cur.s);
+            E = comb4<ERODE>(comb4<ERODE>(prev.c, next.c), cur.s);
             lb = cur.lb;
             rb = cur.rb;
         }
         // bytes just outside this thread's 16 voxels, from the neighbouring lanes
-        unsigned from_left = __shfl_up_sync(0xffffffffu, C.w >> 24, 1, 16);
-        unsigned from_right = __shfl_down_sync(0xffffffffu, C.x & 0xffu, 1, 16);
-        unsigned L = lane16 == 0 ? lb : from_left;
+        const unsigned from_left = __shfl_up_sync(0xffffffffu, C.w >> 24, 1, 16);
+        const unsigned from_right = __shfl_down_sync(0xffffffffu, C.x & 0xffu, 1, 16);
+        const unsigned L = lane16 == 0 ? lb : from_left;
         unsigned R = lane16 == 15 ? rb : from_right;
-        if (xc + 1 >= ncx) R = 0;  // last chunk of the row: nothing to the right
+        if (xc + 1 >= ncx) R = IDB;  // last chunk of the row: nothing to the right
         uint4 r;
-        r.x = C.x | (C.x << 8) | L | (C.x >> 8) | (C.y << 24);
-        r.y = C.y | (C.y << 8) | (C.x >> 24) | (C.y >> 8) | (C.z << 24);
-        r.z = C.z | (C.z << 8) | (C.y >> 24) | (C.z >> 8) | (C.w << 24);
-        r.w = C.w | (C.w << 8) | (C.z >> 24) | (C.w >> 8) | (R << 24);
-        r = or4(r, E);
-        if (ERODE) { r.x ^= 0x01010101u; r.y ^= 0x01010101u; r.z ^= 0x01010101u; r.w ^= 0x01010101u; }
-        if (col_ok)
-            *reinterpret_cast<uint4*>(ovol + ((size_t)z * ny + y) * nx + (size_t)xc * 16) = r;
+        r.x = comb<ERODE>(comb<ERODE>(C.x, (C.x << 8) | L), __funnelshift_r(C.x, C.y, 8));
+        r.y = comb<ERODE>(comb<ERODE>(C.y, __funnelshift_l(C.x, C.y, 8)), __funnelshift_r(C.y, C.z, 8));
+        r.z = comb<ERODE>(comb<ERODE>(C.z, __funnelshift_l(C.y, C.z, 8)), __funnelshift_r(C.z, C.w, 8));
+        r.w = comb<ERODE>(comb<ERODE>(C.w, __funnelshift_l(C.z, C.w, 8)), (C.w >> 8) | (R << 24));
+        if (!FULL) r = comb4<ERODE>(r, E);
+        if (col_ok) *reinterpret_cast<uint4*>(oz) = r;
+        oz += ps;
         prev = cur;
         cur = next;
     }

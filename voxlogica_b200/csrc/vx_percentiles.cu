@@ -13,19 +13,18 @@
 //      a one-thread kernel turns their xor into the number of passes (3 for intensities
 //      within a few octaves, 4 at most), and the kernels of the remaining passes exit at
 //      once -- all decided on the device, the host never waits.  The unit of work is a
-//      warp-owned chunk of 2048 keys: digits are ranked inside the warp with match.any,
-//      running offsets live in warp-private shared memory, so no block barrier and no
-//      atomics are needed inside a pass;
+//      block-owned tile of 4096 keys: digits are ranked inside each warp with ballots
+//      (running counts in warp-private shared memory, no atomics), the tile is reordered in
+//      shared memory and written out as runs of consecutive keys per digit;
 //   3. every sorted position finds the start of its run of equal keys (its rank) and
 //      scatters the normalised rank back to its voxel.
+#include <algorithm>
+
 #include "vx_internal.h"
 
 namespace vx {
 
 constexpr int kPcThreads = 256;
-constexpr int kWarpChunk = 2048;                 // keys owned by one warp in a sort pass
-constexpr int kRounds = kWarpChunk / 32;
-constexpr int kPrefetch = 8;                     // rounds whose global loads are issued together
 constexpr int kRadixBits = 9;
 constexpr int kDigits = 1 << kRadixBits;         // 512
 constexpr int kMaxPasses = (32 + kRadixBits - 1) / kRadixBits;   // 4
@@ -142,69 +141,86 @@ __global__ void rs_plan_kernel(unsigned* __restrict__ plan) {
 }
 
 // ---- 2. radix sort passes --------------------------------------------------------------
-// table layout: [vol][digit][chunk]  (chunk-major inside a digit so the scan is one sweep)
-__global__ void __launch_bounds__(kPcThreads)
+// The unit of work is a block-owned TILE of kTile keys; warp w owns keys [w*512, (w+1)*512) of
+// the tile, so position order = (warp, round, lane) and the ranking is stable.
+// table layout: [vol][digit][tile]  (tile-major inside a digit so the scan is one sweep)
+constexpr int kTile = 4096;
+constexpr int kTileWarps = kPcThreads / 32;        // 8
+constexpr int kWarpKeys = kTile / kTileWarps;      // 512
+constexpr int kWarpRounds = kWarpKeys / 32;        // 16
+
+__global__ void __launch_bounds__(kPcThreads, 6)
 rs_hist_kernel(const unsigned long long* __restrict__ buf0, const unsigned long long* __restrict__ buf1,
-               const unsigned* __restrict__ count, size_t nvox, unsigned* __restrict__ table, int nchunks_max,
+               const unsigned* __restrict__ count, size_t nvox, unsigned* __restrict__ table, int ntiles_max,
                int pass, const unsigned* __restrict__ plan) {
-    __shared__ unsigned cnt[kPcThreads / 32][kDigits];
+    // warp-private counters, plain read-modify-write by the leader lane of every digit group
+    // (no shared-memory atomics: they cost 2 cycles per lane)
+    __shared__ unsigned short cnt[kTileWarps][kDigits];
     if ((unsigned)pass >= plan[0]) return;
     const unsigned long long* pairs = (pass & 1) ? buf1 : buf0;
     const int shift = pass * kRadixBits;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t vol = blockIdx.y;
     const unsigned n = count[vol];
-    const unsigned chunk = blockIdx.x * (kPcThreads / 32) + warp;
-    const unsigned nchunks = (n + kWarpChunk - 1) / kWarpChunk;
-    if (chunk >= nchunks) return;
-    for (int d = lane; d < kDigits; d += 32) cnt[warp][d] = 0;
-    __syncwarp();
-    const unsigned long long* k = pairs + vol * nvox;
-    const unsigned base = chunk * kWarpChunk;
-    for (int r0 = 0; r0 < kRounds; r0 += kPrefetch) {
-        unsigned keyhi[kPrefetch];   // the loads of kPrefetch rounds are in flight together
+    // the high words (keys) only: 16 independent loads per lane in flight
+    const unsigned* khi = reinterpret_cast<const unsigned*>(pairs + vol * nvox) + 1;
+    unsigned* tab = table + (vol * kDigits) * (size_t)ntiles_max;
+    const unsigned ntiles = (n + kTile - 1) / kTile;
+    // a block walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...: the grid is sized for the SMs,
+    // not for the volume (the host does not know how many voxels the mask holds)
+    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const unsigned base = tile * kTile + warp * kWarpKeys;
+        unsigned key[kWarpRounds];
 #pragma unroll
-        for (int j = 0; j < kPrefetch; j++) {
-            const unsigned p = base + (r0 + j) * 32 + lane;
-            keyhi[j] = p < n ? (unsigned)(__ldcs(k + p) >> 32) : 0u;
+        for (int r = 0; r < kWarpRounds; r++) {
+            const unsigned p = base + r * 32 + lane;
+            key[r] = p < n ? __ldcs(khi + 2 * (size_t)p) : 0u;
         }
+        for (int d = lane; d < kDigits; d += 32) cnt[warp][d] = 0;
+        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < kPrefetch; j++) {
-            const unsigned p = base + (r0 + j) * 32 + lane;
+        for (int r = 0; r < kWarpRounds; r++) {
+            const unsigned p = base + r * 32 + lane;
             const bool ok = p < n;
             const unsigned active = __ballot_sync(0xffffffffu, ok);
             if (ok) {
-                const unsigned d = (keyhi[j] >> shift) & (kDigits - 1);
+                const unsigned d = (key[r] >> shift) & (kDigits - 1);
                 const unsigned peers = digit_peers(active, d, kRadixBits);
-                if ((peers & ((1u << lane) - 1u)) == 0) cnt[warp][d] += __popc(peers);
+                if ((peers & ((1u << lane) - 1u)) == 0) cnt[warp][d] = (unsigned short)(cnt[warp][d] + __popc(peers));
             }
             __syncwarp();
         }
+        __syncthreads();
+        for (int d = threadIdx.x; d < kDigits; d += kPcThreads) {
+            unsigned t = 0;
+#pragma unroll
+            for (int w = 0; w < kTileWarps; w++) t += cnt[w][d];
+            tab[(size_t)d * ntiles_max + tile] = t;
+        }
+        __syncthreads();   // the counters are zeroed again by the next tile
     }
-    unsigned* tab = table + (vol * kDigits) * (size_t)nchunks_max;
-    for (int d = lane; d < kDigits; d += 32) tab[(size_t)d * nchunks_max + chunk] = cnt[warp][d];
 }
 
-// grid (kDigits, nb): block (d, vol) turns row d of the table (one count per chunk) into an
-// exclusive prefix over chunks and records the row total; the digit bases are then a
-// 256-entry scan that every scatter warp does for itself.
+// grid (kDigits, nb): block (d, vol) turns row d of the table (one count per tile) into an
+// exclusive prefix over tiles and records the row total; the digit bases are then a
+// 512-entry scan that every scatter block does for itself.
 __global__ void __launch_bounds__(256)
 rs_rowscan_kernel(const unsigned* __restrict__ count, unsigned* __restrict__ table,
-                  unsigned* __restrict__ totals, int nchunks_max, int pass, const unsigned* __restrict__ plan) {
+                  unsigned* __restrict__ totals, int ntiles_max, int pass, const unsigned* __restrict__ plan) {
     __shared__ unsigned wsum[8];
     __shared__ unsigned carry_s;
     if ((unsigned)pass >= plan[0]) return;
     const size_t vol = blockIdx.y;
     const unsigned d = blockIdx.x;
     const unsigned n = count[vol];
-    const unsigned nchunks = (n + kWarpChunk - 1) / kWarpChunk;
-    unsigned* row = table + (vol * kDigits + d) * (size_t)nchunks_max;
+    const unsigned ntiles = (n + kTile - 1) / kTile;
+    unsigned* row = table + (vol * kDigits + d) * (size_t)ntiles_max;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    for (unsigned base = 0; base < nchunks; base += 256) {
+    for (unsigned base = 0; base < ntiles; base += 256) {
         const unsigned i = base + threadIdx.x;
-        const unsigned v = i < nchunks ? row[i] : 0u;
+        const unsigned v = i < ntiles ? row[i] : 0u;
         unsigned incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -221,7 +237,7 @@ rs_rowscan_kernel(const unsigned* __restrict__ count, unsigned* __restrict__ tab
             tot += t;
         }
         const unsigned carry = carry_s;
-        if (i < nchunks) row[i] = carry + wbase + incl - v;
+        if (i < ntiles) row[i] = carry + wbase + incl - v;
         __syncthreads();
         if (threadIdx.x == 0) carry_s = carry + tot;
         __syncthreads();
@@ -229,11 +245,41 @@ rs_rowscan_kernel(const unsigned* __restrict__ count, unsigned* __restrict__ tab
     if (threadIdx.x == 0) totals[vol * kDigits + d] = carry_s;
 }
 
-__global__ void __launch_bounds__(kPcThreads)
+// exclusive scan over the block of the per-thread pair (a, b) = values of digits 2t, 2t+1;
+// returns the exclusive prefix of digit 2t (digit 2t+1 starts at the return value + a)
+__device__ __forceinline__ unsigned block_excl_scan_pairs(unsigned a, unsigned b, unsigned* wsum) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned sum = a + b;
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    unsigned wbase = 0;
+#pragma unroll
+    for (int w = 0; w < kTileWarps; w++)
+        if (w < warp) wbase += wsum[w];
+    __syncthreads();   // wsum may be reused by the next scan
+    return wbase + incl - sum;
+}
+
+// Scatter of one tile.  Keys are ranked inside the block, written to shared memory in digit
+// order and leave it as runs of consecutive keys of one digit going to consecutive addresses
+// (8 keys = 64 B on average).  Scattering each key straight from its lane costs one partial
+// 32-byte sector write per 8-byte key: ncu showed 5x DRAM write amplification plus the sector
+// fills (654 MB read + 761 MB written for a 148 MB pass) and 8 % issue activity.
+__global__ void __launch_bounds__(kPcThreads, 4)
 rs_scatter_kernel(unsigned long long* __restrict__ buf0, unsigned long long* __restrict__ buf1,
                   const unsigned* __restrict__ count, size_t nvox, const unsigned* __restrict__ table,
-                  const unsigned* __restrict__ totals, int nchunks_max, int pass, const unsigned* __restrict__ plan) {
-    __shared__ unsigned off[kPcThreads / 32][kDigits];
+                  const unsigned* __restrict__ totals, int ntiles_max, int pass, const unsigned* __restrict__ plan) {
+    __shared__ unsigned long long stage[kTile];             // 32 KB
+    __shared__ unsigned short wcnt[kTileWarps][kDigits];    // per-warp digit counts, then warp offsets
+    __shared__ unsigned dstart[kDigits];                    // first tile-local position of digit d
+    __shared__ unsigned gbase[kDigits];                     // global position of this tile's first key of digit d
+    __shared__ unsigned wsum[kTileWarps];
     if ((unsigned)pass >= plan[0]) return;
     const unsigned long long* pairs_in = (pass & 1) ? buf1 : buf0;
     unsigned long long* pairs_out = (pass & 1) ? buf0 : buf1;
@@ -241,62 +287,95 @@ rs_scatter_kernel(unsigned long long* __restrict__ buf0, unsigned long long* __r
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t vol = blockIdx.y;
     const unsigned n = count[vol];
-    const unsigned chunk = blockIdx.x * (kPcThreads / 32) + warp;
-    const unsigned nchunks = (n + kWarpChunk - 1) / kWarpChunk;
-    if (chunk >= nchunks) return;
-    const unsigned* tab = table + (vol * kDigits) * (size_t)nchunks_max;
-    {   // digit bases: exclusive scan of the row totals, kDigits/32 digits per lane
-        constexpr int PL = kDigits / 32;
-        const unsigned* tot = totals + vol * kDigits;
-        unsigned t[PL], sum = 0;
-#pragma unroll
-        for (int j = 0; j < PL; j++) { t[j] = tot[lane * PL + j]; sum += t[j]; }
-        unsigned incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        unsigned base = incl - sum;
-#pragma unroll
-        for (int j = 0; j < PL; j++) {
-            const int d = lane * PL + j;
-            off[warp][d] = base + tab[(size_t)d * nchunks_max + chunk];
-            base += t[j];
-        }
-    }
-    __syncwarp();
-    const unsigned long long* pi = pairs_in + vol * nvox;
+    const unsigned ntiles = (n + kTile - 1) / kTile;
+    if (blockIdx.x >= ntiles) return;
     unsigned long long* po = pairs_out + vol * nvox;
-    const unsigned base = chunk * kWarpChunk;
-    for (int r0 = 0; r0 < kRounds; r0 += kPrefetch) {
-        unsigned long long kvs[kPrefetch];   // kPrefetch independent loads in flight per lane
+    const unsigned* tab = table + (vol * kDigits) * (size_t)ntiles_max;
+    // global start of every digit (exclusive scan of the row totals): once per block
+    const int d0 = 2 * threadIdx.x, d1 = d0 + 1;
+    unsigned dig0, dig1;
+    {
+        const unsigned* tot = totals + vol * kDigits;
+        const unsigned t0 = tot[d0], t1 = tot[d1];
+        dig0 = block_excl_scan_pairs(t0, t1, wsum);
+        dig1 = dig0 + t0;
+    }
+    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const unsigned tile_n = min((unsigned)kTile, n - tile * kTile);
+        const unsigned long long* pi = pairs_in + vol * nvox + (size_t)tile * kTile;
+        // 1. loads first (16 independent 8-byte loads per lane), counters zeroed meanwhile
+        unsigned long long kv[kWarpRounds];
 #pragma unroll
-        for (int j = 0; j < kPrefetch; j++) {
-            const unsigned p = base + (r0 + j) * 32 + lane;
-            kvs[j] = p < n ? __ldcs(pi + p) : 0ull;
+        for (int r = 0; r < kWarpRounds; r++) {
+            const unsigned p = warp * kWarpKeys + r * 32 + lane;
+            kv[r] = p < tile_n ? __ldcs(pi + p) : 0ull;
         }
+        const unsigned tb0 = tab[(size_t)d0 * ntiles_max + tile], tb1 = tab[(size_t)d1 * ntiles_max + tile];
+        for (int d = lane; d < kDigits; d += 32) wcnt[warp][d] = 0;
+        __syncwarp();
+        // 2. rank of every key among the keys of its digit inside its warp
+        unsigned short lrank[kWarpRounds];
 #pragma unroll
-        for (int j = 0; j < kPrefetch; j++) {
-            const unsigned p = base + (r0 + j) * 32 + lane;
-            const bool ok = p < n;
+        for (int r = 0; r < kWarpRounds; r++) {
+            const unsigned p = warp * kWarpKeys + r * 32 + lane;
+            const bool ok = p < tile_n;
             const unsigned active = __ballot_sync(0xffffffffu, ok);
+            unsigned prev = 0, rank = 0;
+            int leader = 0;
             if (ok) {
-                const unsigned long long kv = kvs[j];
-                const unsigned d = ((unsigned)(kv >> 32) >> shift) & (kDigits - 1);
+                const unsigned d = ((unsigned)(kv[r] >> 32) >> shift) & (kDigits - 1);
                 const unsigned peers = digit_peers(active, d, kRadixBits);
-                const unsigned rank = __popc(peers & ((1u << lane) - 1u));
-                const int leader = __ffs(peers) - 1;
-                unsigned start = 0;
+                rank = __popc(peers & ((1u << lane) - 1u));
+                leader = __ffs(peers) - 1;
                 if (lane == leader) {
-                    start = off[warp][d];
-                    off[warp][d] = start + __popc(peers);
+                    prev = wcnt[warp][d];
+                    wcnt[warp][d] = (unsigned short)(prev + __popc(peers));
                 }
-                start = __shfl_sync(peers, start, leader);
-                po[start + rank] = kv;
             }
+            prev = __shfl_sync(0xffffffffu, prev, leader);   // all lanes take part; one instruction
+            lrank[r] = (unsigned short)(prev + rank);
             __syncwarp();
         }
+        __syncthreads();
+        // 3. per digit: offsets of the warps inside the digit, tile-local start, global base
+        {
+            unsigned c0 = 0, c1 = 0;
+#pragma unroll
+            for (int w = 0; w < kTileWarps; w++) {
+                const unsigned a = wcnt[w][d0], b = wcnt[w][d1];
+                wcnt[w][d0] = (unsigned short)c0;
+                wcnt[w][d1] = (unsigned short)c1;
+                c0 += a;
+                c1 += b;
+            }
+            const unsigned s0 = block_excl_scan_pairs(c0, c1, wsum);
+            dstart[d0] = s0;
+            dstart[d1] = s0 + c0;
+            gbase[d0] = dig0 + tb0;
+            gbase[d1] = dig1 + tb1;
+        }
+        __syncthreads();
+        // 4. keys into shared memory in digit order
+#pragma unroll
+        for (int r = 0; r < kWarpRounds; r++) {
+            const unsigned p = warp * kWarpKeys + r * 32 + lane;
+            if (p < tile_n) {
+                const unsigned d = ((unsigned)(kv[r] >> 32) >> shift) & (kDigits - 1);
+                stage[dstart[d] + wcnt[warp][d] + lrank[r]] = kv[r];
+            }
+        }
+        __syncthreads();
+        // 5. out: consecutive threads write consecutive keys of a run
+#pragma unroll
+        for (int i = 0; i < kTile / kPcThreads; i++) {
+            const unsigned p = i * kPcThreads + threadIdx.x;
+            if (p < tile_n) {
+                const unsigned long long v = stage[p];
+                const unsigned d = ((unsigned)(v >> 32) >> shift) & (kDigits - 1);
+                po[gbase[d] + (p - dstart[d])] = v;
+            }
+        }
+        __syncthreads();   // stage / wcnt / dstart / gbase are rewritten by the next tile
     }
 }
 
@@ -311,12 +390,33 @@ pc_rank_kernel(const unsigned long long* __restrict__ buf0, const unsigned long 
     const unsigned long long* k = pairs + vol * nvox;
     float* o = out + vol * nvox;
     auto key_at = [&](unsigned i) { return (unsigned)(k[i] >> 32); };
-    for (unsigned p = blockIdx.x * kPcThreads + threadIdx.x; p < n; p += gridDim.x * kPcThreads) {
-        const unsigned long long kv = k[p];
+    const int lane = threadIdx.x & 31;
+    // a warp owns 32 consecutive sorted positions: the start of a run of equal keys (= the rank
+    // of all its members) is found with one ballot of the run heads.  With f32 intensities a
+    // few per cent of the keys have a twin, so nearly every warp holds a tie somewhere: a
+    // per-lane binary search made the whole warp walk ~20 dependent loads for it.
+    for (unsigned pb = blockIdx.x * kPcThreads + (threadIdx.x & ~31u); pb < n; pb += gridDim.x * kPcThreads) {
+        const unsigned p = pb + lane;
+        const bool ok = p < n;
+        const unsigned long long kv = ok ? k[p] : 0ull;
         const unsigned key = (unsigned)(kv >> 32);
-        unsigned less = p;
-        if (p > 0 && key_at(p - 1) == key) {  // inside a run of equal keys: lower bound
-            unsigned lo = 0, hi = p;
+        unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
+        if (lane == 0 && pb > 0) prev = key_at(pb - 1);
+        const bool head = ok && (p == 0 || key != prev);
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        unsigned tails = 0;
+        if (correction != 0.0) {   // kernel-uniform: run ends are only needed for the tie correction
+            const unsigned next = __shfl_down_sync(0xffffffffu, key, 1);
+            const bool tail = ok && (p + 1 >= n || (lane == 31 ? key_at(p + 1) != key : next != key));
+            tails = __ballot_sync(0xffffffffu, tail);
+        }
+        if (!ok) continue;
+        const unsigned below = heads & (0xffffffffu >> (31 - lane));
+        unsigned less;
+        if (below) {
+            less = pb + (31 - __clz(below));
+        } else {   // the run began before this warp's first position: lower bound
+            unsigned lo = 0, hi = pb;
             while (lo < hi) {
                 unsigned mid = (lo + hi) >> 1;
                 if (key_at(mid) < key) lo = mid + 1; else hi = mid;
@@ -325,9 +425,12 @@ pc_rank_kernel(const unsigned long long* __restrict__ buf0, const unsigned long 
         }
         double num = (double)less;
         if (correction != 0.0) {
-            unsigned up = p + 1;
-            if (up < n && key_at(up) == key) {  // upper bound
-                unsigned lo = up, hi = n;
+            const unsigned above = tails & (0xffffffffu << lane);
+            unsigned up;   // one past the last member of the run
+            if (above) {
+                up = pb + (__ffs(above) - 1) + 1;
+            } else {   // the run continues beyond this warp: upper bound
+                unsigned lo = pb + 32, hi = n;
                 while (lo < hi) {
                     unsigned mid = (lo + hi) >> 1;
                     if (key_at(mid) <= key) lo = mid + 1; else hi = mid;
@@ -354,12 +457,12 @@ extern "C" int32_t vx_percentiles(vx_ctx ctx, vx_img a, vx_img mask, double corr
     VX_TRY(same_shape(A, M));
     const size_t nvox = A->nvox(), total = A->count();
     const int nb = A->nb;
-    const int nchunks_max = (int)((nvox + kWarpChunk - 1) / kWarpChunk);
+    const int ntiles_max = (int)((nvox + kTile - 1) / kTile);
     unsigned long long* buf = nullptr;
     unsigned *count = nullptr, *table = nullptr, *totals = nullptr, *plan = nullptr;
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned long long) * total * 2, (void**)&buf));
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (nb + 4), (void**)&count));
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (size_t)nb * kDigits * nchunks_max, (void**)&table));
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (size_t)nb * kDigits * ntiles_max, (void**)&table));
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (size_t)nb * kDigits, (void**)&totals));
     unsigned long long *k0 = buf, *k1 = buf + total;
     plan = count + nb;   // {passes, min key, max key}
@@ -383,18 +486,21 @@ extern "C" int32_t vx_percentiles(vx_ctx ctx, vx_img a, vx_img mask, double corr
           rs_plan_kernel<<<1, 1, 0, og.st>>>(plan); }
         rc = check_launch("rs_plan_kernel");
     }
-    dim3 sgrid((nchunks_max + kPcThreads / 32 - 1) / (kPcThreads / 32), nb);
+    // tiles are walked by a grid sized for the SMs: ~6 (histogram) / 4 (scatter) resident blocks each
+    const int hx = std::max(1, std::min(ntiles_max, (kNumSMs * 6 + nb - 1) / nb));
+    const int sx = std::max(1, std::min(ntiles_max, (kNumSMs * 4 + nb - 1) / nb));
+    dim3 hgrid(hx, nb), sgrid(sx, nb);
     for (int pass = 0; pass < kMaxPasses && rc == VX_OK; pass++) {
         { VX_LAUNCH(og.c, og.s, "rs_hist_kernel");
-          rs_hist_kernel<<<sgrid, kPcThreads, 0, og.st>>>(k0, k1, count, nvox, table, nchunks_max, pass, plan); }
+          rs_hist_kernel<<<hgrid, kPcThreads, 0, og.st>>>(k0, k1, count, nvox, table, ntiles_max, pass, plan); }
         rc = check_launch("rs_hist_kernel");
         if (rc != VX_OK) break;
         { VX_LAUNCH(og.c, og.s, "rs_rowscan_kernel");
-          rs_rowscan_kernel<<<dim3(kDigits, nb), 256, 0, og.st>>>(count, table, totals, nchunks_max, pass, plan); }
+          rs_rowscan_kernel<<<dim3(kDigits, nb), 256, 0, og.st>>>(count, table, totals, ntiles_max, pass, plan); }
         rc = check_launch("rs_rowscan_kernel");
         if (rc != VX_OK) break;
         { VX_LAUNCH(og.c, og.s, "rs_scatter_kernel");
-          rs_scatter_kernel<<<sgrid, kPcThreads, 0, og.st>>>(k0, k1, count, nvox, table, totals, nchunks_max, pass, plan); }
+          rs_scatter_kernel<<<sgrid, kPcThreads, 0, og.st>>>(k0, k1, count, nvox, table, totals, ntiles_max, pass, plan); }
         rc = check_launch("rs_scatter_kernel");
     }
     if (rc == VX_OK) {

@@ -10,7 +10,7 @@ namespace vx {
 
 constexpr int kRedThreads = 256;
 
-enum RedKind { RED_VOLUME = 0, RED_MIN = 1, RED_MAX = 2, RED_SUM = 3 };
+enum RedKind { RED_VOLUME = 0, RED_MIN = 1, RED_MAX = 2, RED_SUM = 3, RED_MINMAX = 4 };
 
 __device__ __forceinline__ double red_identity(int kind) {
     return kind == RED_MIN ? (double)INFINITY : kind == RED_MAX ? -(double)INFINITY : 0.0;
@@ -37,6 +37,10 @@ __device__ __forceinline__ double block_reduce(double v) {
 }
 
 // grid = (blocks_per_volume, nb).  u8 volume count.
+__device__ __forceinline__ unsigned count16(uint4 w) {
+    return __popc(__vcmpne4(w.x, 0) & 0x01010101u) + __popc(__vcmpne4(w.y, 0) & 0x01010101u) +
+           __popc(__vcmpne4(w.z, 0) & 0x01010101u) + __popc(__vcmpne4(w.w, 0) & 0x01010101u);
+}
 __global__ void __launch_bounds__(kRedThreads)
 reduce_volume_kernel(const uint8_t* __restrict__ a, size_t nvox, double* __restrict__ partial) {
     const size_t lo = (size_t)blockIdx.y * nvox, hi = lo + nvox;
@@ -47,79 +51,118 @@ reduce_volume_kernel(const uint8_t* __restrict__ a, size_t nvox, double* __restr
     if (alo < ahi) {
         const uint4* p = reinterpret_cast<const uint4*>(a + alo);
         const size_t n16 = (ahi - alo) >> 4;
-        for (size_t i = tid; i < n16; i += nth) {
-            uint4 w = __ldg(p + i);
-            cnt += __popc(__vcmpne4(w.x, 0) & 0x01010101u) + __popc(__vcmpne4(w.y, 0) & 0x01010101u) +
-                   __popc(__vcmpne4(w.z, 0) & 0x01010101u) + __popc(__vcmpne4(w.w, 0) & 0x01010101u);
-        }
+        for (size_t i = tid; i < n16; i += nth) cnt += count16(__ldg(p + i));
         // ragged head and tail of this volume
-        for (size_t i = lo + tid; i < alo; i += nth) cnt += a[i] != 0;
-        for (size_t i = ahi + tid; i < hi; i += nth) cnt += a[i] != 0;
+        for (size_t j = lo + tid; j < alo; j += nth) cnt += a[j] != 0;
+        for (size_t j = ahi + tid; j < hi; j += nth) cnt += a[j] != 0;
     } else {
-        for (size_t i = lo + tid; i < hi; i += nth) cnt += a[i] != 0;
+        for (size_t j = lo + tid; j < hi; j += nth) cnt += a[j] != 0;
     }
     double v = block_reduce<RED_SUM>((double)cnt);  // exact: counts < 2^53
     if (threadIdx.x == 0) partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = v;
 }
 
+// Accumulators of the f32 reductions.  min / max are exact in binary32 (fminf / fmaxf skip
+// NaNs like their binary64 versions on the converted values would); the sum accumulates in
+// binary64 in a fixed order.  RED_MINMAX produces both extrema from ONE read of the image.
+template <int KIND>
+struct Acc {
+    float mn = INFINITY, mx = -INFINITY;
+    double sum = 0.0;
+    __device__ __forceinline__ void take(float x) {
+        if (KIND == RED_MIN || KIND == RED_MINMAX) mn = fminf(mn, x);
+        if (KIND == RED_MAX || KIND == RED_MINMAX) mx = fmaxf(mx, x);
+        if (KIND == RED_SUM) sum += (double)x;
+    }
+    __device__ __forceinline__ void take4(float4 w, unsigned mk) {
+        if (mk & 0xffu) take(w.x);
+        if ((mk >> 8) & 0xffu) take(w.y);
+        if ((mk >> 16) & 0xffu) take(w.z);
+        if (mk >> 24) take(w.w);
+    }
+};
+
+// partial layout: [nb][per_volume] (RED_MINMAX: the maxima follow at + nb * per_volume)
 template <int KIND, bool MASKED>
 __global__ void __launch_bounds__(kRedThreads)
 reduce_f32_kernel(const float* __restrict__ a, const uint8_t* __restrict__ m, size_t nvox,
                   double* __restrict__ partial) {
     const size_t lo = (size_t)blockIdx.y * nvox, hi = lo + nvox;
     const size_t alo = (lo + 3) & ~(size_t)3, ahi = hi & ~(size_t)3;
-    double acc = red_identity(KIND);
+    Acc<KIND> acc;
     const size_t tid = (size_t)blockIdx.x * kRedThreads + threadIdx.x;
     const size_t nth = (size_t)gridDim.x * kRedThreads;
-    auto take = [&](float x, unsigned mk) {
-        if (!MASKED || mk) acc = red_combine(KIND, acc, (double)x);
+    auto mask4 = [&](size_t i) -> unsigned {
+        return MASKED ? __ldg(reinterpret_cast<const unsigned*>(m + alo + 4 * i)) : 0x01010101u;
     };
     if (alo < ahi) {
         const float4* p = reinterpret_cast<const float4*>(a + alo);
         const size_t n4 = (ahi - alo) >> 2;
-        for (size_t i = tid; i < n4; i += nth) {
-            float4 w = __ldg(p + i);
-            unsigned mk = 0x01010101u;
-            if (MASKED) mk = *reinterpret_cast<const unsigned*>(m + alo + 4 * i);
-            take(w.x, mk & 0xffu); take(w.y, (mk >> 8) & 0xffu);
-            take(w.z, (mk >> 16) & 0xffu); take(w.w, mk >> 24);
+        size_t i = tid;
+        for (; i + 3 * nth < n4; i += 4 * nth) {   // four independent loads in flight
+            const float4 w0 = __ldg(p + i), w1 = __ldg(p + i + nth), w2 = __ldg(p + i + 2 * nth),
+                         w3 = __ldg(p + i + 3 * nth);
+            const unsigned k0 = mask4(i), k1 = mask4(i + nth), k2 = mask4(i + 2 * nth), k3 = mask4(i + 3 * nth);
+            acc.take4(w0, k0); acc.take4(w1, k1); acc.take4(w2, k2); acc.take4(w3, k3);
         }
-        for (size_t i = lo + tid; i < alo; i += nth) take(a[i], MASKED ? m[i] : 1);
-        for (size_t i = ahi + tid; i < hi; i += nth) take(a[i], MASKED ? m[i] : 1);
+        for (; i < n4; i += nth) acc.take4(__ldg(p + i), mask4(i));
+        for (size_t j = lo + tid; j < alo; j += nth) if (!MASKED || m[j]) acc.take(a[j]);
+        for (size_t j = ahi + tid; j < hi; j += nth) if (!MASKED || m[j]) acc.take(a[j]);
     } else {
-        for (size_t i = lo + tid; i < hi; i += nth) take(a[i], MASKED ? m[i] : 1);
+        for (size_t j = lo + tid; j < hi; j += nth) if (!MASKED || m[j]) acc.take(a[j]);
     }
-    double v = block_reduce<KIND>(acc);
-    if (threadIdx.x == 0) partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = v;
+    const size_t slot = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    if (KIND == RED_MIN || KIND == RED_MINMAX) {
+        const double v = block_reduce<RED_MIN>((double)acc.mn);
+        if (threadIdx.x == 0) partial[slot] = v;
+    }
+    if (KIND == RED_MINMAX) __syncthreads();   // block_reduce's staging array is reused
+    if (KIND == RED_MAX || KIND == RED_MINMAX) {
+        const double v = block_reduce<RED_MAX>((double)acc.mx);
+        if (threadIdx.x == 0) partial[slot + (KIND == RED_MINMAX ? (size_t)gridDim.y * gridDim.x : 0)] = v;
+    }
+    if (KIND == RED_SUM) {
+        const double v = block_reduce<RED_SUM>(acc.sum);
+        if (threadIdx.x == 0) partial[slot] = v;
+    }
 }
 
-// one block per volume, fixed combination order
+// one block per (volume, result), fixed combination order.  grid (nb, nres): result r of kind
+// kinds[r] reads partial + r * nb * per_volume and writes out + r * nb.
 template <int KIND>
-__global__ void __launch_bounds__(kRedThreads)
-reduce_final_kernel(const double* __restrict__ partial, int per_volume, double* __restrict__ out) {
+__device__ __forceinline__ double final_of(const double* __restrict__ part, int per_volume) {
     double acc = red_identity(KIND);
-    for (int i = threadIdx.x; i < per_volume; i += kRedThreads)
-        acc = red_combine(KIND, acc, partial[(size_t)blockIdx.x * per_volume + i]);
-    double v = block_reduce<KIND>(acc);
-    if (threadIdx.x == 0) out[blockIdx.x] = v;
+    for (int i = threadIdx.x; i < per_volume; i += kRedThreads) acc = red_combine(KIND, acc, part[i]);
+    return block_reduce<KIND>(acc);
+}
+__global__ void __launch_bounds__(kRedThreads)
+reduce_final_kernel(const double* __restrict__ partial, int per_volume, double* __restrict__ out, int kind0, int kind1) {
+    const int kind = blockIdx.y == 0 ? kind0 : kind1;
+    const double* part = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * per_volume;
+    double v;
+    if (kind == RED_MIN) v = final_of<RED_MIN>(part, per_volume);
+    else if (kind == RED_MAX) v = final_of<RED_MAX>(part, per_volume);
+    else v = final_of<RED_SUM>(part, per_volume);
+    if (threadIdx.x == 0) out[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = v;
 }
 
-// Runs the reduction and leaves nb doubles in device memory `d_out` (scratch owned by caller)
+// Runs the reduction and leaves nb doubles (RED_MINMAX: nb minima, then nb maxima) in device
+// memory `d_out` (scratch owned by the caller)
 int reduce_device(OpGuard& g, int kind, const Image* a, const Image* mask, double* d_out) {
     const size_t nvox = a->nvox();
     int per_volume = (int)((nvox + (size_t)kRedThreads * 16 * 4 - 1) / ((size_t)kRedThreads * 16 * 4));
     int cap = (kNumSMs * 8 + a->nb - 1) / a->nb;
     if (per_volume > cap) per_volume = cap;
     if (per_volume < 1) per_volume = 1;
+    const int nres = kind == RED_MINMAX ? 2 : 1;
     double* d_part = nullptr;
-    VX_TRY(scratch_alloc(g.c, g.s, sizeof(double) * (size_t)per_volume * a->nb, (void**)&d_part));
+    VX_TRY(scratch_alloc(g.c, g.s, sizeof(double) * (size_t)per_volume * a->nb * nres, (void**)&d_part));
     dim3 grid(per_volume, a->nb);
+    int k0 = RED_SUM, k1 = RED_SUM;
     if (kind == RED_VOLUME) {
         { VX_LAUNCH(g.c, g.s, "reduce_volume_kernel");
           reduce_volume_kernel<<<grid, kRedThreads, 0, g.st>>>((const uint8_t*)a->d, nvox, d_part); }
         VX_TRY(check_launch("reduce_volume_kernel"));
-        { VX_LAUNCH(g.c, g.s, "reduce_final_kernel");
-          reduce_final_kernel<RED_SUM><<<a->nb, kRedThreads, 0, g.st>>>(d_part, per_volume, d_out); }
     } else {
         const float* p = (const float*)a->d;
         const uint8_t* m = mask ? (const uint8_t*)mask->d : nullptr;
@@ -128,14 +171,16 @@ int reduce_device(OpGuard& g, int kind, const Image* a, const Image* mask, doubl
           else if (kind == RED_MIN) reduce_f32_kernel<RED_MIN, true><<<grid, kRedThreads, 0, g.st>>>(p, m, nvox, d_part);
           else if (kind == RED_MAX && !m) reduce_f32_kernel<RED_MAX, false><<<grid, kRedThreads, 0, g.st>>>(p, m, nvox, d_part);
           else if (kind == RED_MAX) reduce_f32_kernel<RED_MAX, true><<<grid, kRedThreads, 0, g.st>>>(p, m, nvox, d_part);
+          else if (kind == RED_MINMAX && !m) reduce_f32_kernel<RED_MINMAX, false><<<grid, kRedThreads, 0, g.st>>>(p, m, nvox, d_part);
+          else if (kind == RED_MINMAX) reduce_f32_kernel<RED_MINMAX, true><<<grid, kRedThreads, 0, g.st>>>(p, m, nvox, d_part);
           else if (!m) reduce_f32_kernel<RED_SUM, false><<<grid, kRedThreads, 0, g.st>>>(p, m, nvox, d_part);
           else reduce_f32_kernel<RED_SUM, true><<<grid, kRedThreads, 0, g.st>>>(p, m, nvox, d_part); }
         VX_TRY(check_launch("reduce_f32_kernel"));
-        { VX_LAUNCH(g.c, g.s, "reduce_final_kernel");
-          if (kind == RED_MIN) reduce_final_kernel<RED_MIN><<<a->nb, kRedThreads, 0, g.st>>>(d_part, per_volume, d_out);
-          else if (kind == RED_MAX) reduce_final_kernel<RED_MAX><<<a->nb, kRedThreads, 0, g.st>>>(d_part, per_volume, d_out);
-          else reduce_final_kernel<RED_SUM><<<a->nb, kRedThreads, 0, g.st>>>(d_part, per_volume, d_out); }
+        k0 = kind == RED_MINMAX ? RED_MIN : kind;
+        k1 = RED_MAX;
     }
+    { VX_LAUNCH(g.c, g.s, "reduce_final_kernel");
+      reduce_final_kernel<<<dim3(a->nb, nres), kRedThreads, 0, g.st>>>(d_part, per_volume, d_out, k0, k1); }
     VX_TRY(check_launch("reduce_final_kernel"));
     return scratch_free(g.c, g.s, d_part);
 }
@@ -159,6 +204,28 @@ static int reduce_to_host(vx_ctx ctx, int kind, vx_img a, vx_img mask, double* o
     return g.finish_scalar();
 }
 
+// min and max of every volume from one pass over the image (crossCorrelation's histogram range
+// min(img) .. max(img) costs one read of the image instead of two)
+static int minmax_to_host(vx_ctx ctx, vx_img a, vx_img mask, double* out_min, double* out_max) {
+    VX_REQUIRE(out_min != nullptr && out_max != nullptr, VX_E_INVALID_ARG, "out is NULL");
+    OpGuard g;
+    VX_TRY(g.begin(ctx));
+    Image *A = nullptr, *M = nullptr;
+    VX_TRY(g.input(a, &A, VX_F32));
+    if (mask) {
+        VX_TRY(g.input(mask, &M, VX_U8));
+        VX_TRY(same_shape(A, M));
+    }
+    double* d_out = nullptr;
+    VX_TRY(scratch_alloc(g.c, g.s, sizeof(double) * A->nb * 2, (void**)&d_out));
+    VX_TRY(reduce_device(g, RED_MINMAX, A, M, d_out));
+    VX_CUDA(cudaMemcpyAsync(out_min, d_out, sizeof(double) * A->nb, cudaMemcpyDeviceToHost, g.st));
+    VX_CUDA(cudaMemcpyAsync(out_max, d_out + A->nb, sizeof(double) * A->nb, cudaMemcpyDeviceToHost, g.st));
+    VX_TRY(scratch_free(g.c, g.s, d_out));
+    VX_CUDA(cudaStreamSynchronize(g.st));
+    return g.finish_scalar();
+}
+
 }  // namespace vx
 
 using namespace vx;
@@ -168,6 +235,9 @@ int32_t vx_volume(vx_ctx ctx, vx_img a, double* out) { return reduce_to_host(ctx
 int32_t vx_min(vx_ctx ctx, vx_img a, double* out) { return reduce_to_host(ctx, RED_MIN, a, 0, out); }
 int32_t vx_max(vx_ctx ctx, vx_img a, double* out) { return reduce_to_host(ctx, RED_MAX, a, 0, out); }
 int32_t vx_sum(vx_ctx ctx, vx_img a, double* out) { return reduce_to_host(ctx, RED_SUM, a, 0, out); }
+int32_t vx_minmax(vx_ctx ctx, vx_img a, vx_img mask, double* out_min, double* out_max) {
+    return minmax_to_host(ctx, a, mask, out_min, out_max);
+}
 int32_t vx_min_masked(vx_ctx ctx, vx_img a, vx_img mask, double* out) {
     VX_REQUIRE(mask != 0, VX_E_INVALID_ARG, "mask handle is 0");
     return reduce_to_host(ctx, RED_MIN, a, mask, out);

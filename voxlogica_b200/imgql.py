@@ -438,6 +438,17 @@ class Interpreter:
                 _find_hoistable(st[3], loaded, self._SCALAR_FNS, found)
             elif st[0] in ("save", "print"):
                 _find_hoistable(st[2], loaded, self._SCALAR_FNS, found)
+        # min(e) and max(e) of the same image: ONE pass (vx_minmax) serves both tasks
+        for e in found:
+            twin = next((f for f in found if f is not e and {e.fn, f.fn} == {"min", "max"} and f.args == e.args), None)
+            if e.fn == "min" and twin is not None:
+                arg = self.eval(e.args[0], {})
+                klo, khi = self._key("min", [arg]), self._key("max", [arg])
+                if klo not in self.memo and khi not in self.memo:
+                    lo, hi = self.ctx.minmax(force(arg))
+                    self.memo[klo] = (Number(lo), [arg])
+                    self.memo[khi] = (Number(hi), [arg])
+                    self.n_tasks += 2
         for e in found:
             self.eval(e, {})
 

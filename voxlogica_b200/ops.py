@@ -424,6 +424,12 @@ class Context:
             return self._scalars(lambda b: self.lib.vx_max(self.handle, a.handle, b), a.nb)
         return self._scalars(lambda b: self.lib.vx_max_masked(self.handle, a.handle, mask.handle, b), a.nb)
 
+    def minmax(self, a: Image, mask: Optional[Image] = None):
+        """(min, max) per volume from one pass over the image"""
+        lo, hi = (A.f64 * a.nb)(), (A.f64 * a.nb)()
+        check(self.lib.vx_minmax(self.handle, a.handle, mask.handle if mask is not None else 0, lo, hi))
+        return np.array(lo[:], dtype=np.float64), np.array(hi[:], dtype=np.float64)
+
     def sum(self, a: Image) -> np.ndarray:
         return self._scalars(lambda b: self.lib.vx_sum(self.handle, a.handle, b), a.nb)
 
