@@ -394,60 +394,21 @@ struct RingLoader {
     // ref_word.  A row outside the image is all dummy and never flat (it changes the
     // histograms when it enters or leaves); columns/planes outside the image are dummy in
     // every row and are ignored.
-    // mn / mx: smallest and largest counted bin (< k) among this thread's words of the row
-    // (k resp. 0 when it holds none)
-    __device__ __forceinline__ bool commit(unsigned* ring32, int yr, int slot_of_yr, const unsigned (&v)[2],
-                                           unsigned& mn, unsigned& mx) const {
+    __device__ __forceinline__ bool commit(unsigned* ring32, int yr, int slot_of_yr, const unsigned (&v)[2]) const {
         const int slot = slot_of_yr * (kRingXW / 4);
         bool flat = yr >= 0 && yr < ny;
-        unsigned lo4 = 0xffffffffu, hi4 = 0u;
 #pragma unroll
         for (int s = 0; s < 2; s++) {
             if (ring_off[s] < 0) continue;
-            lo4 = __vminu4(lo4, v[s]);                                   // the dummy bin k is above every real bin
-            hi4 = __vmaxu4(hi4, v[s] & ~__vcmpeq4(v[s], dummy));         // ... and does not count as a maximum
             reinterpret_cast<uint2*>(ring32)[ring_off[s] + slot] = make_uint2(offsets2(v[s]), offsets2(v[s] >> 16));
             if (src[s] != nullptr) {
                 const bool whole = xg[s] >= 0 && xg[s] + 3 < nx;
                 flat = flat && whole && v[s] == ref_word;
             }
         }
-        lo4 = __vminu4(lo4, lo4 >> 16); lo4 = __vminu4(lo4, lo4 >> 8);
-        hi4 = __vmaxu4(hi4, hi4 >> 16); hi4 = __vmaxu4(hi4, hi4 >> 8);
-        mn = lo4 & 0xffu;
-        mx = hi4 & 0xffu;
         return flat;
     }
 };
-
-// Range of the bins present in the ring: every warp records the smallest / largest counted bin of
-// each row it stores (one byte per warp and ring slot); the block-wide range of a step is the
-// min / max over all slots.  The histograms of the step are zero outside that range, so the
-// S11 / dot-product sweep only visits its words: in tissue a 13 x 14 x 48 window spans 10-25 of
-// the 100 bins, and the sweep was a quarter of the kernel's instructions.
-struct BinRange {
-    uint4 mn[10], mx[10];   // 40 slots x 4 warps, one byte each
-};
-__device__ __forceinline__ void range_store(BinRange& br, int slot, int warp, int lane, unsigned mn, unsigned mx) {
-    mn = __reduce_min_sync(0xffffffffu, mn);
-    mx = __reduce_max_sync(0xffffffffu, mx);
-    if (lane == 0) {
-        reinterpret_cast<unsigned char*>(br.mn)[slot * 4 + warp] = (unsigned char)mn;
-        reinterpret_cast<unsigned char*>(br.mx)[slot * 4 + warp] = (unsigned char)mx;
-    }
-}
-__device__ __forceinline__ void range_of(const BinRange& br, int R, unsigned& lo, unsigned& hi) {
-    unsigned a = 0xffffffffu, b = 0u;
-    for (int i = 0; 4 * i < R; i++) {
-        const uint4 x = br.mn[i], y = br.mx[i];
-        a = __vminu4(__vminu4(a, x.x), __vminu4(__vminu4(x.y, x.z), x.w));
-        b = __vmaxu4(__vmaxu4(b, y.x), __vmaxu4(__vmaxu4(y.y, y.z), y.w));
-    }
-    a = __vminu4(a, a >> 16); a = __vminu4(a, a >> 8);
-    b = __vmaxu4(b, b >> 16); b = __vmaxu4(b, b >> 8);
-    lo = a & 0xffu;
-    hi = b & 0xffu;
-}
 
 // grid (ceil(nx/32), ceil(nz/4)*nseg, nb), block 128.  Dynamic shared memory:
 //   hist [nw][128] u32 | h2s [2*nw] u32 | cols [ncols] u32 | ring [P][R][48] u16
@@ -469,12 +430,6 @@ xcorr_ring_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
     // go through the (slow) indexed constant path
     __shared__ int gs[17], ge[17];
     if (threadIdx.x < 17) { gs[threadIdx.x] = g.gstart[threadIdx.x]; ge[threadIdx.x] = g.gend[threadIdx.x]; }
-    __shared__ BinRange br;
-    if (threadIdx.x < 10) {   // slots never written (and the spare ones) hold the empty range
-        br.mn[threadIdx.x] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-        br.mx[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x0 = blockIdx.x * 32;
@@ -516,9 +471,7 @@ xcorr_ring_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 if (yr0 + q > y0 + g.wy) break;   // block-uniform
-                unsigned rmn, rmx;
-                const bool f = rl.commit(ring32, yr0 + q, sl, v[q], rmn, rmx);
-                range_store(br, sl, warp, lane, rmn, rmx);
+                const bool f = rl.commit(ring32, yr0 + q, sl, v[q]);
                 sl = slot_add(sl, 1, R);
                 flat_rows = __syncthreads_and(f) ? flat_rows + 1 : 0;
             }
@@ -561,18 +514,14 @@ xcorr_ring_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
             // ball * n2 cannot overflow them
             unsigned long long P = 0;
             unsigned S2 = 0;
-            unsigned blo, bhi;
-            range_of(br, R, blo, bhi);           // block-uniform; blo > bhi: no counted voxel in the ring
-            const int rl_ = blo > bhi ? 1 : (int)(blo >> 1), rh_ = blo > bhi ? 0 : (int)(bhi >> 1);
-            const int pl = max(rl_, wlo), ph = min(rh_, whi);   // words where h1 and h2 can both be non-zero
-            for (int w = rl_; w <= min(rh_, pl - 1); w++) {
+            for (int w = 0; w < wlo; w++) {
                 const unsigned v = hist[w * kXcThreads + threadIdx.x];
                 const unsigned lo = v & 0xffffu, hi = v >> 16;
                 S2 += lo * lo + hi * hi;
             }
             if (p32) {
                 unsigned P32 = 0;
-                for (int w = pl; w <= ph; w++) {
+                for (int w = wlo; w <= whi; w++) {
                     const unsigned v = hist[w * kXcThreads + threadIdx.x];
                     const uint2 hh = *reinterpret_cast<const uint2*>(h2s + 2 * w);
                     const unsigned lo = v & 0xffffu, hi = v >> 16;
@@ -581,7 +530,7 @@ xcorr_ring_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
                 }
                 P = P32;
             } else {
-                for (int w = pl; w <= ph; w++) {
+                for (int w = wlo; w <= whi; w++) {
                     const unsigned v = hist[w * kXcThreads + threadIdx.x];
                     const uint2 hh = *reinterpret_cast<const uint2*>(h2s + 2 * w);
                     const unsigned lo = v & 0xffffu, hi = v >> 16;
@@ -590,7 +539,7 @@ xcorr_ring_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
                     S2 += lo * lo + hi * hi;
                 }
             }
-            for (int w = max(rl_, max(ph, pl - 1) + 1); w <= rh_; w++) {
+            for (int w = whi + 1; w < g.nw; w++) {
                 const unsigned v = hist[w * kXcThreads + threadIdx.x];
                 const unsigned lo = v & 0xffffu, hi = v >> 16;
                 S2 += lo * lo + hi * hi;
@@ -598,7 +547,7 @@ xcorr_ring_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
             // remove the dummy bin K (not-counted voxels) from the statistics
             const unsigned vd = hist[(K >> 1) * kXcThreads + threadIdx.x];
             const unsigned hd = (K & 1u) ? (vd >> 16) : (vd & 0xffffu);
-            if ((int)(K >> 1) >= rl_ && (int)(K >> 1) <= rh_) S2 -= hd * hd;   // only if the sweep saw its word
+            S2 -= hd * hd;
             const long long n1 = (long long)g.ball - (long long)hd;
             const long long num = (long long)K * (long long)P - n1 * n2;
             const long long d1 = (long long)K * (long long)S2 - n1 * n1;
@@ -609,10 +558,7 @@ xcorr_ring_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
         if (active) ov[((size_t)z * g.ny + y) * g.nx + x] = res;
         if (y + 1 >= y1) break;
         // the slot of row y+1+wy last held row y+1+wy-R < y-1-wy: nobody reads it any more
-        unsigned rmn, rmx;
-        const int sl_new = slot_add(sy, 1 + g.wy, R);
-        const bool f = rl.commit(ring32, y + 1 + g.wy, sl_new, pfa, rmn, rmx);
-        range_store(br, sl_new, warp, lane, rmn, rmx);
+        const bool f = rl.commit(ring32, y + 1 + g.wy, slot_add(sy, 1 + g.wy, R), pfa);
         pfa[0] = pfb[0]; pfa[1] = pfb[1];
         rl.fetch(y + 3 + g.wy, pfb);
         flat_rows = __syncthreads_and(f) ? flat_rows + 1 : 0;
