@@ -26,3 +26,19 @@ def gtv_oracle(o, flair, conn=26, spacing=None, stages=None):
     r["tumStatCC"] = o.flt(2.0, o.cmp_scalar(r["tumSim"], ">", 0.6), spacing)
     r["gtv"] = o.grow(r["growTum"], r["tumStatCC"], conn)
     return r
+
+
+def texture_oracle(o, mods, conn=26, spacing=None):
+    """BASELINE config 4 (voxlogica_b200.imgql.TEXTURE_SPEC) composed from oracle operators.
+    mods: {"flair","t1","t1c","t2"} -> f32 [nz][ny][nx]."""
+    r = gtv_oracle(o, mods["flair"], conn, spacing, stages="pre_similarity")
+    sims = []
+    for name in ("flair", "t1", "t1c", "t2"):
+        a = np.ascontiguousarray(mods[name], dtype=np.float32)
+        sims.append(o.cross_correlation(5.0, a, a, r["growTum"], o.min_(a), o.max_(a), 100, spacing))
+    r["simFlair"], r["simT1"], r["simT1c"], r["simT2"] = sims
+    acc = o.arith(o.arith(o.arith(sims[0], "+", sims[1]), "+", sims[2]), "+", sims[3])
+    r["texture"] = o.arith_scalar(acc, "/", 4.0)
+    r["similar"] = o.flt(2.0, o.and_(o.cmp_scalar(r["texture"], ">", 0.6), r["brain"]), spacing)
+    r["tumour"] = o.grow(r["growTum"], r["similar"], conn)
+    return r

@@ -28,6 +28,26 @@ def test_gtv_spec_matches_oracle(ctx, oracle, shape, seeds):
     assert got["_tasks"] < 60     # hash-consing: shared sub-terms evaluated once
 
 
+def test_texture_spec_matches_oracle(ctx, oracle):
+    """BASELINE config 4: crossCorrelation texture similarity on four co-registered modalities,
+    batched, against the oracle composition (bit-exact, the f32 coefficient maps included)."""
+    from gtv_ref import texture_oracle
+    from voxlogica_b200.imgql import run_texture
+    from voxlogica_b200.synth import MODALITIES, brats_multimodal
+    shape, seeds = (40, 64, 80), (1234, 21)
+    subj = [brats_multimodal(s, shape) for s in seeds]
+    imgs = {m: ctx.upload(np.stack([sj[m] for sj in subj])) for m in MODALITIES}
+    got = run_texture(ctx, imgs)
+    for i, sj in enumerate(subj):
+        want = texture_oracle(oracle, sj)
+        for name in ("growTum", "similar", "tumour"):
+            assert np.array_equal(got[name].numpy()[i], want[name]), (name, seeds[i])
+        for name in ("simFlair", "simT1", "simT1c", "simT2", "texture"):
+            assert np.array_equal(got[name].numpy()[i].view(np.uint32), want[name].view(np.uint32)), (name, seeds[i])
+        assert got["_printed"]["tumourVolume"][i] == want["tumour"].sum()
+    assert got["tumour"].numpy().sum() > 0
+
+
 def test_maze_reachability_2d(ctx, oracle):
     """BASELINE configs[0]: 2D maze, colour thresholds -> near -> through (reach)."""
     from voxlogica_b200.imgql import run_spec

@@ -71,6 +71,28 @@ def test_synthetic_generators():
     assert corridors.sum() == 2 * 64 - 1                # spanning tree: n cells + n-1 passages
 
 
+def test_texture_spec_parses_and_oracle_finds_the_lesion(oracle):
+    """BASELINE config 4 on the CPU side: the multi-modal spec parses, the synthetic modalities share
+    their anatomy, and the oracle composition of the spec segments the lesion."""
+    from gtv_ref import texture_oracle
+    from voxlogica_b200 import synth
+    from voxlogica_b200.imgql import TEXTURE_SPEC, Parser
+    st = Parser(TEXTURE_SPEC).program()
+    assert [s[1] for s in st if s[0] == "load"] == ["flair", "t1", "t1c", "t2"]
+    assert {"simFlair", "simT1", "simT1c", "simT2", "texture", "tumour"} <= {s[1] for s in st if s[0] == "let"}
+    with open(os.path.join(ROOT, "examples", "texture.imgql")) as f:
+        assert len(Parser(f.read()).program()) == len(st)
+    shape = (40, 64, 80)
+    mods = synth.brats_multimodal(1234, shape)
+    assert tuple(mods) == synth.MODALITIES
+    head = mods["flair"] > 0
+    for name, v in mods.items():
+        assert v.dtype == np.float32 and v.shape == shape and np.array_equal(v > 0, head), name
+    r = texture_oracle(oracle, mods)
+    assert r["growTum"].sum() > 0 and r["tumour"].sum() >= r["growTum"].sum()
+    assert np.all(r["tumour"] <= r["brain"]) and -1.0 <= r["texture"].min() and r["texture"].max() <= 1.0
+
+
 def test_nifti_and_png_roundtrip(tmp_path):
     from voxlogica_b200 import io as vio
     rng = np.random.default_rng(3)

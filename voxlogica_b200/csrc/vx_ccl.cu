@@ -426,21 +426,32 @@ ccl_zero_roots_kernel(const unsigned* __restrict__ Lall, const unsigned* __restr
         if ((Lall[vbase + p.lin0 + j] & kIdx) == p.lin0 + j) cnt[vbase + p.lin0 + j] = 0;
     }
 }
-// step 2: one atomicAdd per run segment (all its voxels share a root)
+// step 2: every run segment adds its length to its root's counter.  Lanes of a warp whose
+// segments share a root (the normal case inside a large component: one hot counter) first add
+// up among themselves and issue ONE atomicAdd; a per-segment atomic serialised on that counter
+// in L2 and made this the longest kernel of maxvol.
 __global__ void __launch_bounds__(kCclThreads)
 ccl_count_kernel(const unsigned* __restrict__ Lall, const unsigned* __restrict__ bits,
                  unsigned* __restrict__ cnt, Geo g) {
     const WordPos p = word_pos(g);
-    if (!p.ok) return;
-    const unsigned m = __ldg(bits + p.wid);
+    const unsigned m = p.ok ? __ldg(bits + p.wid) : 0u;
     const unsigned* L = Lall + (size_t)p.vol * g.nvox;
+    const int lane = threadIdx.x & 31;
     unsigned rest = m;
-    while (rest) {
-        const int st = __ffs(rest) - 1;
-        const unsigned sm = seg_mask(m, st);
-        rest &= ~sm;
-        const unsigned r = find_root(L, p.lin0 + st);
-        atomicAdd(cnt + (size_t)p.vol * g.nvox + r, (unsigned)__popc(sm));
+    while (__any_sync(0xffffffffu, rest != 0u)) {
+        const bool has = rest != 0u;
+        unsigned r = 0, c = 0;
+        if (has) {
+            const int st = __ffs(rest) - 1;
+            const unsigned sm = seg_mask(m, st);
+            rest &= ~sm;
+            r = find_root(L, p.lin0 + st);
+            c = (unsigned)__popc(sm);
+        }
+        const unsigned long long key = has ? (((unsigned long long)p.vol << 32) | r) : ~0ull;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const unsigned total = __reduce_add_sync(peers, c);
+        if (has && lane == __ffs(peers) - 1) atomicAdd(cnt + (size_t)p.vol * g.nvox + r, total);
     }
 }
 // step 3: per-volume maximum over roots

@@ -799,15 +799,19 @@ static int xcorr_run(OpGuard& og, Image* A, uint8_t* d_bins, float* d_edges, uns
         g.seg = seg; g.nseg = nseg; g.nw = nw; g.wy = wy; g.wz = wz; g.R = ringR; g.P = P;
         g.ball = (int)ball;
         VX_CUDA(cudaMemcpyAsync(d_cols, ring_cols.data(), sizeof(unsigned) * ring_cols.size(), cudaMemcpyHostToDevice, og.st));
-        if (smem_ring > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(xcorr_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ring);
+        // 5 resident CTAs per SM (96 registers, ~44 KB): measured on B200 against 4 and 3 (extra
+        // dynamic shared memory), alone and with other streams' kernels co-resident: 7.13 / 7.69 /
+        // 8.98 ms per 16-volume launch, and the whole GTV step got slower with fewer CTAs as well
+        const size_t smem_launch = smem_ring;
+        if (smem_launch > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(xcorr_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_launch);
             if (e != cudaSuccess) rc = fail(VX_E_CUDA, "smem attribute: %s", cudaGetErrorString(e));
         }
         if (rc == VX_OK) {
             dim3 grid((A->nx + 31) / 32, ((A->nz + kXcWarps - 1) / kXcWarps) * nseg, nb);
             {
                 VX_LAUNCH(og.c, og.s, "xcorr_kernel");
-                xcorr_ring_kernel<<<grid, kXcThreads, smem_ring, og.st>>>(d_bins, (float*)O->d, d_cols, d_h2, d_vstat, g);
+                xcorr_ring_kernel<<<grid, kXcThreads, smem_launch, og.st>>>(d_bins, (float*)O->d, d_cols, d_h2, d_vstat, g);
             }
             rc = check_launch("xcorr_kernel");
         }

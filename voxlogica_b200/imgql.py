@@ -61,6 +61,33 @@ save "gtv" gtv
 print "gtvVolume" volume(gtv)
 """
 
+# BASELINE config 4: texture similarity on co-registered modalities.  The tumour seed region
+# (growTum of the GTV spec, from FLAIR) is compared with every voxel's neighbourhood in each
+# modality (Greta.pdf p.43 "Texture analysis", p.53); the mean coefficient is thresholded.
+TEXTURE_SPEC = """
+import "stdlib.imgql"
+load flair = "flair"
+load t1 = "t1"
+load t1c = "t1c"
+load t2 = "t2"
+let background   = touch(intensity(flair) <. 0.1, border)
+let brain        = complement(background)
+let normFlair    = percentiles(intensity(flair), brain)
+let hyperIntense = filter(5.0, normFlair >. 0.95)
+let veryIntense  = filter(2.0, normFlair >. 0.86)
+let growTum      = grow(hyperIntense, veryIntense)
+let simFlair = crossCorrelation(5, intensity(flair), intensity(flair), growTum, min(intensity(flair)), max(intensity(flair)), 100)
+let simT1    = crossCorrelation(5, intensity(t1), intensity(t1), growTum, min(intensity(t1)), max(intensity(t1)), 100)
+let simT1c   = crossCorrelation(5, intensity(t1c), intensity(t1c), growTum, min(intensity(t1c)), max(intensity(t1c)), 100)
+let simT2    = crossCorrelation(5, intensity(t2), intensity(t2), growTum, min(intensity(t2)), max(intensity(t2)), 100)
+let texture  = (simFlair +. simT1 +. simT1c +. simT2) /. 4
+let similar  = filter(2.0, (texture >. 0.6) & brain)
+let tumour   = grow(growTum, similar)
+save "texture" texture
+save "tumour" tumour
+print "tumourVolume" volume(tumour)
+"""
+
 # ---------------------------------------------------------------------------- lexer
 _TOKEN = re.compile(r"""
     (?P<ws>\s+|//[^\n]*)
@@ -715,6 +742,15 @@ def run_file(ctx: Context, path: str, conn: int = 26) -> Interpreter:
     it.saver = saver
     with open(path) as f:
         return it.run(f.read())
+
+
+def run_texture(ctx: Context, images: Dict[str, Image], conn: int = 26) -> Dict[str, object]:
+    """The multi-modal texture-similarity spec (BASELINE config 4) on (batched) flair/t1/t1c/t2."""
+    it = run_spec(ctx, TEXTURE_SPEC, images, conn)
+    out = dict(it.globals)
+    out["_tasks"] = it.n_tasks
+    out["_printed"] = it.printed
+    return out
 
 
 def run_gtv(ctx: Context, flair: Image, conn: int = 26) -> Dict[str, object]:

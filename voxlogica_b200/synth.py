@@ -57,6 +57,30 @@ def brats_like(seed: int = 1234, shape=BRATS_SHAPE) -> np.ndarray:
     return np.clip(vol, 0.0, 1.0).astype(np.float32)
 
 
+MODALITIES = ("flair", "t1", "t1c", "t2")
+
+
+def brats_multimodal(seed: int = 1234, shape=BRATS_SHAPE) -> dict:
+    """Four co-registered modalities of one synthetic subject (SURVEY.md section 8d, config 4:
+    seeds seed..seed+3, shared anatomy).  `flair` is brats_like(seed); the others keep its head,
+    rim and lesion geometry (they are derived from the noise-free part of its intensities) but
+    have their own tissue contrast, lesion contrast and noise -- like T1 / T1c / T2 of a
+    BraTS case, where the lesion is dark, ring-bright and bright respectively."""
+    flair = brats_like(seed, shape)
+    head = flair > 0.0
+    lesion = ndi.uniform_filter(flair, 3) > 0.72          # core + halo of the lesions, denoised
+    out = {"flair": flair}
+    contrast = {"t1": (0.55, -0.35, 0.25), "t1c": (0.50, -0.20, 0.75), "t2": (0.20, 0.55, 0.85)}
+    for i, name in enumerate(MODALITIES[1:], start=1):
+        rng = np.random.default_rng(seed + i)
+        base, slope, les = contrast[name]
+        tissue = base + slope * (flair - 0.375) + 0.10 * (_smooth_noise(rng, shape, coarse=16) - 0.5)
+        vol = np.where(lesion, np.float32(les) + 0.05 * (_smooth_noise(rng, shape, coarse=8) - 0.5), tissue)
+        vol = vol + rng.normal(0.0, 0.02, size=shape).astype(np.float32)
+        out[name] = np.where(head, np.clip(vol, 0.01, 1.0), 0.0).astype(np.float32)
+    return out
+
+
 def brats_batch(seeds, shape=BRATS_SHAPE) -> np.ndarray:
     return np.stack([brats_like(int(s), shape) for s in seeds])
 
