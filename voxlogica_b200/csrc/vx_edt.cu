@@ -281,13 +281,7 @@ __device__ __forceinline__ unsigned nib_of(unsigned w) {
 __device__ __forceinline__ unsigned bits16(uint4 v) {
     return nib_of(v.x) | (nib_of(v.y) << 4) | (nib_of(v.z) << 8) | (nib_of(v.w) << 12);
 }
-__global__ void __launch_bounds__(kEdtThreads)
-pack_bits_kernel(const uint8_t* __restrict__ img, unsigned* __restrict__ bits, int nx, int nwx,
-                 unsigned long long nwords) {
-    const unsigned long long wid = (unsigned long long)blockIdx.x * kEdtThreads + threadIdx.x;
-    if (wid >= nwords) return;
-    const unsigned long long row = wid / nwx;
-    const int w = (int)(wid % nwx);
+__device__ __forceinline__ unsigned pack_word(const uint8_t* __restrict__ img, unsigned long long row, int w, int nx) {
     const int x0 = w * 32;
     const uint8_t* src = img + row * nx + x0;
     unsigned m = 0;
@@ -298,18 +292,31 @@ pack_bits_kernel(const uint8_t* __restrict__ img, unsigned* __restrict__ bits, i
         const int lim = min(32, nx - x0);
         for (int b = 0; b < lim; b++) m |= (unsigned)(src[b] != 0) << b;
     }
-    bits[wid] = m;
+    return m;
 }
 
-// D[e][word] = row dilated by +-e voxels in x, for e = 1..emax (D[0] = the packed bits)
+// One thread per 32-voxel word: D[0][word] = the packed bits, D[e][word] = the row dilated by
+// +-e voxels in x for e = 1..emax (the neighbouring words come from the neighbouring lanes;
+// only the first and last lane of a warp pack theirs again), rowany[row] = 1 when the row
+// holds a set voxel.
 __global__ void __launch_bounds__(kEdtThreads)
-xdilate_bits_kernel(unsigned* __restrict__ D, int nwx, unsigned long long nwords, int emax) {
+pack_bits_kernel(const uint8_t* __restrict__ img, unsigned* __restrict__ D, int nx, int nwx,
+                 unsigned long long nwords, int emax, uint8_t* __restrict__ rowany) {
     const unsigned long long wid = (unsigned long long)blockIdx.x * kEdtThreads + threadIdx.x;
-    if (wid >= nwords) return;
-    const int w = (int)(wid % nwx);
-    const unsigned cur = D[wid];
-    const unsigned prev = w > 0 ? D[wid - 1] : 0u;
-    const unsigned next = w + 1 < nwx ? D[wid + 1] : 0u;
+    const bool ok = wid < nwords;
+    const unsigned long long row = (ok ? wid : 0) / nwx;
+    const int w = (int)((ok ? wid : 0) % nwx);
+    const unsigned cur = ok ? pack_word(img, row, w, nx) : 0u;
+    unsigned prev = __shfl_up_sync(0xffffffffu, cur, 1), next = __shfl_down_sync(0xffffffffu, cur, 1);
+    if (!ok) return;
+    D[wid] = cur;
+    if (cur != 0u && rowany != nullptr) rowany[row] = 1;   // zeroed by the caller; every writer stores 1
+    if (emax <= 0) return;
+    const int lane = threadIdx.x & 31;
+    if (w == 0) prev = 0u;
+    else if (lane == 0) prev = pack_word(img, row, w - 1, nx);
+    if (w + 1 >= nwx) next = 0u;
+    else if (lane == 31) next = pack_word(img, row, w + 1, nx);
     unsigned acc = cur;
     for (int e = 1; e <= emax; e++) {
         acc |= (cur << e) | (prev >> (32 - e)) | (cur >> e) | (next << (32 - e));
@@ -333,7 +340,28 @@ __device__ __forceinline__ unsigned bytes_of(unsigned nib) {
 __global__ void __launch_bounds__(kEdtThreads)
 ball_or_kernel(const unsigned* __restrict__ D, uint8_t* __restrict__ out, int nx, int ny, int nz,
                int nwx, unsigned long long nwords, const long long* __restrict__ boff,
-               const int* __restrict__ bdyz, int nball, int wy, int wz, int invert) {
+               const int* __restrict__ bdyz, int nball, int wy, int wz, int invert,
+               const uint8_t* __restrict__ rowany) {
+    // Rows of the input that hold no set voxel are flagged by the packing kernel.  When no row
+    // that any word of this block can reach is occupied, the block writes its (constant) output
+    // without touching the bit rows: the dilation half of `filter` runs on what an erosion left
+    // over, which is empty almost everywhere.  The reachable rows are tested conservatively as
+    // intervals of the linear row index (row + dz*ny + dy), which may include a few rows of the
+    // neighbouring planes.
+    bool block_empty = false;
+    if (rowany != nullptr) {
+        const unsigned long long w_first = (unsigned long long)blockIdx.x * kEdtThreads;
+        const unsigned long long w_last = min(w_first + kEdtThreads, nwords) - 1;
+        const long long r0 = (long long)(w_first / nwx) - wy, r1 = (long long)(w_last / nwx) + wy;
+        const long long rows_total = (long long)(nwords / nwx);
+        const int span = (int)(r1 - r0 + 1);
+        int found = 0;
+        for (int i = threadIdx.x; i < span * (2 * wz + 1); i += kEdtThreads) {
+            const long long r = r0 + (i % span) + (long long)(i / span - wz) * ny;
+            if (r >= 0 && r < rows_total && rowany[r]) found = 1;
+        }
+        block_empty = !__syncthreads_or(found);
+    }
     const unsigned long long wid = (unsigned long long)blockIdx.x * kEdtThreads + threadIdx.x;
     if (wid >= nwords) return;
     const unsigned long long row = wid / nwx;
@@ -341,8 +369,14 @@ ball_or_kernel(const unsigned* __restrict__ D, uint8_t* __restrict__ out, int nx
     const int y = (int)(row % ny);
     const int z = (int)((row / ny) % nz);
     const unsigned* base = D + wid;
-    unsigned acc = 0;
-    if (y >= wy && y + wy < ny && z >= wz && z + wz < nz) {
+    // bits beyond the end of the row count as set for the saturation test (they are never
+    // stored): otherwise the last word of every row -- four lanes of each warp at nx = 240 --
+    // can never fill up and keeps its whole warp in the loop
+    const unsigned pad = (w + 1) * 32 > nx ? 0xffffffffu << (nx - w * 32) : 0u;
+    unsigned acc = pad;
+    if (block_empty) {
+        // nothing within reach
+    } else if (y >= wy && y + wy < ny && z >= wz && z + wz < nz) {
         int t = 0;
         // entries come centre-first: next to a dense feature set (the erosion half of
         // `filter`: distgeq(r, !a)) the word is full after a few of them and the rest is skipped
@@ -351,7 +385,7 @@ ball_or_kernel(const unsigned* __restrict__ D, uint8_t* __restrict__ out, int nx
             const unsigned a2 = __ldg(base + __ldg(boff + t + 2)), a3 = __ldg(base + __ldg(boff + t + 3));
             acc |= (a0 | a1) | (a2 | a3);
         }
-        for (; t < nball; t++) acc |= __ldg(base + __ldg(boff + t));
+        for (; t < nball && acc != 0xffffffffu; t++) acc |= __ldg(base + __ldg(boff + t));
     } else {
         for (int t = 0; t < nball && acc != 0xffffffffu; t++) {
             const int dyz = __ldg(bdyz + t);
@@ -360,6 +394,7 @@ ball_or_kernel(const unsigned* __restrict__ D, uint8_t* __restrict__ out, int nx
             acc |= __ldg(base + __ldg(boff + t));
         }
     }
+    acc &= ~pad;
     if (invert) acc = ~acc;
     const int x0 = w * 32;
     uint8_t* dst = out + row * nx + x0;
@@ -594,17 +629,19 @@ static int dist_threshold(vx_ctx ctx, vx_img a, float r, bool strict, int invert
         const int nwx = (A->nx + 31) / 32;
         const unsigned long long nwords = (unsigned long long)A->nb * A->nz * A->ny * nwx;
         unsigned* D = nullptr;
+        uint8_t* rowany = nullptr;
+        const size_t nrows = (size_t)(nwords / nwx);
         rc = scratch_alloc(og.c, og.s, sizeof(unsigned) * nwords * (emax + 1), (void**)&D);
+        if (rc == VX_OK) rc = scratch_alloc(og.c, og.s, nrows, (void**)&rowany);
+        if (rc == VX_OK) {
+            cudaError_t ce = cudaMemsetAsync(rowany, 0, nrows, og.st);
+            if (ce != cudaSuccess) rc = fail(VX_E_CUDA, "memset: %s", cudaGetErrorString(ce));
+        }
         const unsigned grid = (unsigned)((nwords + kEdtThreads - 1) / kEdtThreads);
         if (rc == VX_OK) {
             { VX_LAUNCH(og.c, og.s, "pack_bits_kernel");
-              pack_bits_kernel<<<grid, kEdtThreads, 0, og.st>>>((const uint8_t*)A->d, D, A->nx, nwx, nwords); }
+              pack_bits_kernel<<<grid, kEdtThreads, 0, og.st>>>((const uint8_t*)A->d, D, A->nx, nwx, nwords, emax, rowany); }
             rc = check_launch("pack_bits_kernel");
-        }
-        if (rc == VX_OK && emax > 0) {
-            { VX_LAUNCH(og.c, og.s, "xdilate_bits_kernel");
-              xdilate_bits_kernel<<<grid, kEdtThreads, 0, og.st>>>(D, nwx, nwords, emax); }
-            rc = check_launch("xdilate_bits_kernel");
         }
         long long* boff = nullptr;
         if (rc == VX_OK && ball.n > 0) {
@@ -632,7 +669,7 @@ static int dist_threshold(vx_ctx ctx, vx_img a, float r, bool strict, int invert
             if (rc == VX_OK) {
                 { VX_LAUNCH(og.c, og.s, "ball_or_kernel");
                   ball_or_kernel<<<grid, kEdtThreads, 0, og.st>>>(D, (uint8_t*)O->d, A->nx, A->ny, A->nz, nwx, nwords, boff,
-                                                                 reinterpret_cast<const int*>(boff + ball.n), ball.n, wy, wz, invert); }
+                                                                 reinterpret_cast<const int*>(boff + ball.n), ball.n, wy, wz, invert, rowany); }
                 rc = check_launch("ball_or_kernel");
             }
             if (boff) scratch_free(og.c, og.s, boff);
@@ -641,6 +678,7 @@ static int dist_threshold(vx_ctx ctx, vx_img a, float r, bool strict, int invert
             if (ce != cudaSuccess) rc = fail(VX_E_CUDA, "memset: %s", cudaGetErrorString(ce));
         }
         if (rc == VX_OK) rc = scratch_free(og.c, og.s, D);
+        if (rc == VX_OK && rowany) rc = scratch_free(og.c, og.s, rowany);
     } else {
         rc = edt_passes(og, A, O->d, EDT_THRESH, T, invert);
     }
