@@ -380,10 +380,14 @@ def run_ours(args):
     value = total_vol / (ms / 1e3)
     e2e = total_vol / (ms_e2e / 1e3)
     peak, how = peaks()
-    # dominant kernel by device time
+    # dominant kernel by device time: chosen in the single-stream table when there is one (the
+    # timed region overlaps `args.threads` streams, which stretches the short kernels of one step
+    # while they wait for SMs held by another step's crossCorrelation launch)
     tot_ms = sum(v[1] for v in prof.values()) or 1.0
-    top = max(prof.items(), key=lambda kv: kv[1][1])
-    name, (cnt, kms) = top
+    ser_total = sum(v[1] for v in serial.values())
+    name = max((serial or prof).items(), key=lambda kv: kv[1][1])[0]
+    cnt, kms = prof.get(name, (serial or prof)[name])
+    share_serial = (serial[name][1] / ser_total) if serial and ser_total else None
     per_launch_vox = B * NVOX
     alg = ALG_BYTES.get(name) or 5.0
     achieved = alg * per_launch_vox / ((kms / cnt) * 1e-3) / 1e9
@@ -426,7 +430,13 @@ def run_ours(args):
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": how, "traffic": traffic,
-                     "alg_bytes_per_voxel": alg, "avg_launch_ms": kms / cnt, "share_of_step": kms / tot_ms,
+                     "alg_bytes_per_voxel": alg, "avg_launch_ms": kms / cnt,
+                     # comparable with the ncu launch list (profiles/), which serialises the launches
+                     "share_of_step": share_serial if share_serial is not None else kms / tot_ms,
+                     "share_of_step_how": ("single-stream pass after the timed region (kernels_serial)"
+                                           if share_serial is not None else "timed region"),
+                     "share_of_timed_region_event_time": kms / tot_ms,
+                     "avg_launch_ms_single_stream": (serial[name][1] / serial[name][0]) if name in serial else None,
                      "traffic_unit": "bytes per launch (dram read+write, ncu --set full, profiles/traffic.json)",
                      "note": "xcorr_kernel is bound by the shared-memory LSU pipe (ncu: 72% of peak shared "
                              "wavefronts, 70% issue active, DRAM 0.9%), not by HBM (SURVEY.md 8d); the fraction "
