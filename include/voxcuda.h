@@ -258,6 +258,14 @@ VX_API int32_t vx_ccl_plane(vx_ctx ctx, vx_ccl state, int32_t z, vx_img* labels_
 /* labels: n values, host or device memory; single-volume states only */
 VX_API int32_t vx_ccl_flag(vx_ctx ctx, vx_ccl state, const uint32_t* labels, uint64_t n);
 VX_API int32_t vx_ccl_select(vx_ctx ctx, vx_ccl state, vx_img* out);
+/* Component sizes on a kept state -- the local part of a slab-decomposed maxvol (single-volume
+ * states).  vx_ccl_count counts the voxels of every local component and returns the largest
+ * count (host blocks); vx_ccl_sizes looks up the counts of the components with the given labels
+ * (labels / sizes: n values, host or device memory; host blocks); vx_ccl_flag_size flags every
+ * component of exactly `size` voxels, like vx_ccl_flag does by label, for vx_ccl_select. */
+VX_API int32_t vx_ccl_count(vx_ctx ctx, vx_ccl state, uint64_t* local_max);
+VX_API int32_t vx_ccl_sizes(vx_ctx ctx, vx_ccl state, const uint32_t* labels, uint64_t n, uint32_t* sizes);
+VX_API int32_t vx_ccl_flag_size(vx_ctx ctx, vx_ccl state, uint32_t size);
 VX_API int32_t vx_ccl_destroy(vx_ctx ctx, vx_ccl state);
 
 /* A8 maxvol: the component(s) of a with the largest voxel count (all of them on ties). */

@@ -37,6 +37,41 @@ class OracleEngine:
     def through(self, a, b, conn): return orc.through(a[0], b[0], conn)[None]
     def components(self, a, conn): return orc.components(a[0], conn).astype(np.uint32)[None]
     def dist(self, op, r, a): return orc.dist_cmp(a[0], op, r, self.sp)[None]
+    def maxvol(self, a, conn): return orc.maxvol(a[0], conn)[None]
+
+    # kept union-find state (vx_ccl_* of the C ABI), restated on oracle labels
+    class _State:
+        def __init__(self, lab):
+            self.lab = lab                                    # uint32 [nz][ny][nx], 0 = background
+            self.flag = np.zeros(int(lab.max()) + 1, bool)    # per label: selected / reached
+            self.cnt = None
+
+    def ccl_create(self, b, conn): return self._State(orc.components(b[0], conn).astype(np.uint32))
+
+    def ccl_seed(self, st, a):
+        st.flag[np.unique(st.lab[a[0] != 0])] = True
+        st.flag[0] = False
+
+    def ccl_plane(self, st, z):
+        lab = st.lab[z]
+        return (torch.from_numpy(np.ascontiguousarray(lab).view(np.int32)),
+                torch.from_numpy(st.flag[lab].astype(np.uint8)))
+
+    def ccl_flag(self, st, labels): st.flag[np.asarray(labels, dtype=np.int64)] = True
+
+    def ccl_count(self, st):
+        st.cnt = np.bincount(st.lab.ravel(), minlength=st.flag.size)
+        st.cnt[0] = 0
+        return int(st.cnt.max())
+
+    def ccl_sizes(self, st, labels): return st.cnt[np.asarray(labels, dtype=np.int64)].astype(np.uint32)
+
+    def ccl_flag_size(self, st, size):
+        st.flag |= st.cnt == size
+        st.flag[0] = False
+
+    def ccl_select(self, st): return st.flag[st.lab].astype(np.uint8)[None]
+    def ccl_destroy(self, st): pass
 
     # the two halves of the distance transform, restated with the arithmetic contract of
     # oracle/vx_oracle.c (binary32, one rounding per step, minimum over explicit offsets)

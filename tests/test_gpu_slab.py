@@ -117,6 +117,13 @@ def test_slab_ops_two_threads_one_gpu(ctx, world, peer):
         want[f"near{conn}"] = ctx.near(Bi, conn).numpy()[0]
         want[f"interior{conn}"] = ctx.interior(Bi, conn).numpy()[0]
         want[f"through{conn}"] = ctx.through(Ai, Bi, conn).numpy()[0]
+        want[f"maxvol{conn}"] = ctx.maxvol(Bi, conn).numpy()[0]
+    # two equally large components in the first and the last slab: both must survive
+    t = np.zeros(shape, np.uint8)
+    t[0:2, 1, 1:13] = 1; t[shape[0] - 2:, 16, 1:13] = 1; t[:, 9, 11] = 1    # 24, 24 and 21 voxels
+    Ti = ctx.upload(t, spacing=sp)
+    want["maxvol_ties"] = ctx.maxvol(Ti, 6).numpy()[0]
+    assert want["maxvol_ties"].sum() == 48 and want["maxvol26"].sum() > 0
     for r in (2.5, 4.0):
         want[f"distlt{r}"] = ctx.distlt(r, Si).numpy()[0]
         want[f"flt{r}"] = ctx.distlt(r, ctx.distgeq(r, ctx.not_(ctx.near(Si)))).numpy()[0]
@@ -140,6 +147,8 @@ def test_slab_ops_two_threads_one_gpu(ctx, world, peer):
                 got[f"near{conn}"] = ops.near(B, conn)
                 got[f"interior{conn}"] = ops.interior(B, conn)
                 got[f"through{conn}"] = ops.through(A, B, conn)
+                got[f"maxvol{conn}"] = ops.maxvol(B, conn)
+            got["maxvol_ties"] = ops.maxvol(ops.scatter_from_global(up, t, sp), 6)
             for r in (2.5, 4.0):
                 got[f"distlt{r}"] = ops.distlt(r, S)
                 got[f"flt{r}"] = ops.flt(r, ops.near(S))

@@ -55,6 +55,21 @@ def _worker(rank, world, port, q):
             check(f"through{conn}", ops.through(A, B, conn), orc.through(a, b, conn))
             check(f"touch{conn}", ops.touch(B, A, conn), orc.touch(b, a, conn))
             check(f"grow{conn}", ops.grow(A, B, conn), orc.grow(a, b, conn))
+            ops.use_ccl_state = False                      # the stateless variant of the same merge
+            check(f"through{conn}/stateless", ops.through(A, B, conn), orc.through(a, b, conn))
+            ops.use_ccl_state = True
+            check(f"maxvol{conn}", ops.maxvol(B, conn), orc.maxvol(b, conn))
+        # largest component: two equal winners in different slabs + a smaller one that spans all of them
+        t = np.zeros(shape, np.uint8)
+        t[0:2, 1, 1:9] = 1                                  # 16 voxels, first slab
+        t[shape[0] - 2:, 16, 1:9] = 1                       # 16 voxels, last slab
+        t[:, 9, 11] = 1                                     # 13 voxels through every slab
+        T = ops.scatter_from_global(up, t, sp)
+        check("maxvol/ties", ops.maxvol(T, 6), orc.maxvol(t, 6))
+        t[:, 9, 12:15] = 1                                  # now the spanning one wins with 52
+        check("maxvol/spanning", ops.maxvol(ops.scatter_from_global(up, t, sp), 26), orc.maxvol(t, 26))
+        check("maxvol/empty", ops.maxvol(ops.scatter_from_global(up, np.zeros(shape, np.uint8), sp), 26),
+              np.zeros(shape, np.uint8))
         sparse = (rng.random(shape) < 0.01).astype(np.uint8)
         S = ops.scatter_from_global(up, sparse, sp)
         for r in (1.0, 2.5, 4.0):
@@ -89,6 +104,18 @@ def test_slab_ops_match_whole_volume_oracle(world):
     assert all(p.exitcode == 0 for p in procs)
     for rank, fails in res:
         assert not fails, f"rank {rank}: {fails}"
+
+
+def test_boundary_class_sizes():
+    from voxlogica_b200.slab import boundary_class_sizes
+    # classes {1,2,3} (sizes 5+7+1), {4} alone (9), {7,8} (2 + 2^33: beyond 32 bits)
+    pairs = np.array([[1, 2], [3, 2], [7, 8]], dtype=np.int64)
+    sizes = np.array([[1, 5], [2, 7], [3, 1], [4, 9], [7, 2], [8, 2 ** 33]], dtype=np.int64)
+    ids, tot = boundary_class_sizes(pairs, sizes)
+    assert dict(zip(ids.tolist(), tot.tolist())) == {1: 13, 2: 13, 3: 13, 4: 9, 7: 2 + 2 ** 33, 8: 2 + 2 ** 33}
+    ids, tot = boundary_class_sizes(np.zeros((0, 2), np.int64), sizes[:2])
+    assert tot.tolist() == [5, 7]
+    assert boundary_class_sizes(np.zeros((0, 2), np.int64), np.zeros((0, 2), np.int64))[0].size == 0
 
 
 def test_boundary_graph_and_bounds():

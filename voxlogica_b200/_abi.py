@@ -101,6 +101,9 @@ SIGNATURES = {
     "vx_ccl_plane": [u64, u64, i32, P(u64), P(u64)],
     "vx_ccl_flag": [u64, u64, C.c_void_p, u64],
     "vx_ccl_select": [u64, u64, P(u64)],
+    "vx_ccl_count": [u64, u64, P(u64)],
+    "vx_ccl_sizes": [u64, u64, C.c_void_p, u64, C.c_void_p],
+    "vx_ccl_flag_size": [u64, u64, C.c_uint32],
     "vx_ccl_destroy": [u64, u64],
     "vx_maxvol": [u64, u64, i32, P(u64)],
     "vx_edt": [u64, u64, P(u64)],

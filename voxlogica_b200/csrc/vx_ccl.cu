@@ -514,6 +514,36 @@ __global__ void ccl_flag_labels_kernel(unsigned* __restrict__ L, const unsigned*
     atomicOr(L + r, kFlag);
 }
 
+// sizes[i] = voxel count of the component whose label is labels[i] (0 for label 0 / invalid)
+__global__ void ccl_sizes_kernel(const unsigned* __restrict__ L, const unsigned* __restrict__ cnt,
+                                 const unsigned* __restrict__ labels, size_t n, unsigned nvox,
+                                 unsigned* __restrict__ sizes) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned lab = labels[i];
+    sizes[i] = (lab == 0 || lab > nvox) ? 0u : cnt[find_root(L, lab - 1u)];
+}
+
+// flag every root whose component holds exactly `size` voxels (one thread per word; roots are run starts)
+__global__ void __launch_bounds__(kCclThreads)
+ccl_flag_size_kernel(unsigned* __restrict__ Lall, const unsigned* __restrict__ bits,
+                     const unsigned* __restrict__ cnt, unsigned size, Geo g) {
+    const WordPos p = word_pos(g);
+    if (!p.ok) return;
+    const unsigned* brow = bits + p.row * g.nwx;
+    const unsigned m = __ldg(brow + p.w);
+    if (m == 0) return;
+    const unsigned prev_m = p.w > 0 ? __ldg(brow + p.w - 1) : 0u;
+    unsigned starts = m & ~((m << 1) | (prev_m >> 31));
+    const size_t vbase = (size_t)p.vol * g.nvox;
+    while (starts) {
+        const int j = __ffs(starts) - 1;
+        starts &= starts - 1;
+        const size_t a = vbase + p.lin0 + j;
+        if ((Lall[a] & kIdx) == p.lin0 + j && cnt[a] == size) atomicOr(Lall + a, kFlag);
+    }
+}
+
 static Geo make_geo(const Image* b) {
     Geo g;
     g.nx = b->nx; g.ny = b->ny; g.nz = b->nz; g.nb = b->nb;
@@ -667,6 +697,7 @@ namespace vx {
 struct CclState {
     Ctx* c = nullptr;
     unsigned *L = nullptr, *bits = nullptr;
+    unsigned* cnt = nullptr;    // per-root voxel counts, allocated by vx_ccl_count
     Geo g;
     unsigned grid = 0;
     int nx = 0, ny = 0, nz = 0, nb = 0;
@@ -801,6 +832,80 @@ int32_t vx_ccl_select(vx_ctx ctx, vx_ccl state, vx_img* out) {
     return og.finish(O, out);
 }
 
+// ---- component sizes on a kept state: the local part of a slab-decomposed maxvol -------------
+int32_t vx_ccl_count(vx_ctx ctx, vx_ccl state, uint64_t* local_max) {
+    VX_REQUIRE(local_max != nullptr, VX_E_INVALID_ARG, "local_max is NULL");
+    OpGuard og;
+    CclState* st = nullptr;
+    VX_TRY(state_enter(og, ctx, state, &st));
+    VX_REQUIRE(st->nb == 1, VX_E_UNSUPPORTED, "vx_ccl_count takes a single-volume state");
+    unsigned* vmax = nullptr;
+    if (st->cnt == nullptr) VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * st->g.nvox, (void**)&st->cnt));
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned), (void**)&vmax));
+    VX_CUDA(cudaMemsetAsync(vmax, 0, sizeof(unsigned), og.st));
+    {
+        VX_LAUNCH(og.c, og.s, "ccl_zero_roots_kernel");
+        ccl_zero_roots_kernel<<<st->grid, kCclThreads, 0, og.st>>>(st->L, st->bits, st->cnt, st->g);
+    }
+    VX_TRY(check_launch("ccl_zero_roots_kernel"));
+    {
+        VX_LAUNCH(og.c, og.s, "ccl_count_kernel");
+        ccl_count_kernel<<<st->grid, kCclThreads, 0, og.st>>>(st->L, st->bits, st->cnt, st->g);
+    }
+    VX_TRY(check_launch("ccl_count_kernel"));
+    {
+        VX_LAUNCH(og.c, og.s, "ccl_max_kernel");
+        ccl_max_kernel<<<st->grid, kCclThreads, 0, og.st>>>(st->L, st->bits, st->cnt, vmax, st->g);
+    }
+    VX_TRY(check_launch("ccl_max_kernel"));
+    unsigned h = 0;
+    VX_CUDA(cudaMemcpyAsync(&h, vmax, sizeof(unsigned), cudaMemcpyDeviceToHost, og.st));
+    VX_TRY(scratch_free(og.c, og.s, vmax));
+    VX_TRY(state_leave(og, st));
+    VX_CUDA(cudaStreamSynchronize(og.st));
+    *local_max = h;
+    return og.finish_scalar();
+}
+
+int32_t vx_ccl_sizes(vx_ctx ctx, vx_ccl state, const uint32_t* labels, uint64_t n, uint32_t* sizes) {
+    OpGuard og;
+    CclState* st = nullptr;
+    VX_TRY(state_enter(og, ctx, state, &st));
+    VX_REQUIRE(st->nb == 1, VX_E_UNSUPPORTED, "vx_ccl_sizes takes a single-volume state");
+    VX_REQUIRE(st->cnt != nullptr, VX_E_INVALID_ARG, "call vx_ccl_count first");
+    if (n == 0) return og.finish_scalar();
+    VX_REQUIRE(labels != nullptr && sizes != nullptr, VX_E_INVALID_ARG, "NULL argument");
+    unsigned *d = nullptr, *o = nullptr;
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * n, (void**)&d));
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * n, (void**)&o));
+    VX_CUDA(cudaMemcpyAsync(d, labels, sizeof(unsigned) * n, cudaMemcpyDefault, og.st));
+    {
+        VX_LAUNCH(og.c, og.s, "ccl_sizes_kernel");
+        ccl_sizes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, og.st>>>(st->L, st->cnt, d, (size_t)n, (unsigned)st->g.nvox, o);
+    }
+    VX_TRY(check_launch("ccl_sizes_kernel"));
+    VX_CUDA(cudaMemcpyAsync(sizes, o, sizeof(unsigned) * n, cudaMemcpyDefault, og.st));
+    VX_TRY(scratch_free(og.c, og.s, d));
+    VX_TRY(scratch_free(og.c, og.s, o));
+    VX_TRY(state_leave(og, st));
+    VX_CUDA(cudaStreamSynchronize(og.st));
+    return og.finish_scalar();
+}
+
+int32_t vx_ccl_flag_size(vx_ctx ctx, vx_ccl state, uint32_t size) {
+    OpGuard og;
+    CclState* st = nullptr;
+    VX_TRY(state_enter(og, ctx, state, &st));
+    VX_REQUIRE(st->cnt != nullptr, VX_E_INVALID_ARG, "call vx_ccl_count first");
+    if (size != 0) {
+        VX_LAUNCH(og.c, og.s, "ccl_flag_size_kernel");
+        ccl_flag_size_kernel<<<st->grid, kCclThreads, 0, og.st>>>(st->L, st->bits, st->cnt, size, st->g);
+    }
+    VX_TRY(check_launch("ccl_flag_size_kernel"));
+    VX_TRY(state_leave(og, st));
+    return og.finish_scalar();
+}
+
 int32_t vx_ccl_destroy(vx_ctx ctx, vx_ccl state) {
     OpGuard og;
     CclState* st = nullptr;
@@ -813,6 +918,7 @@ int32_t vx_ccl_destroy(vx_ctx ctx, vx_ccl state) {
     // last operation on the state
     scratch_free(og.c, og.s, st->L);
     scratch_free(og.c, og.s, st->bits);
+    if (st->cnt) scratch_free(og.c, og.s, st->cnt);
     cudaEventDestroy(st->ev);
     delete st;
     return VX_OK;

@@ -360,6 +360,22 @@ class Context:
     def ccl_select(self, state: int) -> Image:
         return self._out(lambda o: self.lib.vx_ccl_select(self.handle, state, o))
 
+    def ccl_count(self, state: int) -> int:
+        """count the voxels of every local component; returns the largest count"""
+        m = A.u64()
+        check(self.lib.vx_ccl_count(self.handle, state, C.byref(m)))
+        return int(m.value)
+
+    def ccl_sizes(self, state: int, labels) -> np.ndarray:
+        arr = np.ascontiguousarray(np.asarray(labels, dtype=np.uint32))
+        out = np.zeros(arr.size, np.uint32)
+        check(self.lib.vx_ccl_sizes(self.handle, state, arr.ctypes.data_as(C.c_void_p), arr.size,
+                                    out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def ccl_flag_size(self, state: int, size: int) -> None:
+        check(self.lib.vx_ccl_flag_size(self.handle, state, int(size)))
+
     def ccl_destroy(self, state: int) -> None:
         check(self.lib.vx_ccl_destroy(self.handle, state))
 

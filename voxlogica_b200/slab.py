@@ -108,6 +108,10 @@ class CudaEngine:
     def ccl_flag(self, st, labels): self.ctx.ccl_flag(st, labels)
     def ccl_select(self, st): return self.ctx.ccl_select(st)
     def ccl_destroy(self, st): self.ctx.ccl_destroy(st)
+    def ccl_count(self, st): return self.ctx.ccl_count(st)
+    def ccl_sizes(self, st, labels): return self.ctx.ccl_sizes(st, labels)
+    def ccl_flag_size(self, st, size): self.ctx.ccl_flag_size(st, size)
+    def maxvol(self, a, conn): return self.ctx.maxvol(a, conn)
 
     def ccl_plane(self, st, z):
         lab, hit = self.ctx.ccl_plane(st, z)
@@ -450,8 +454,53 @@ class SlabOps:
     def percentiles(self, *a, **k):
         raise NotImplementedError("percentiles on slabs needs a distributed sort (DESIGN.md section 6)")
 
-    def maxvol(self, *a, **k):
-        raise NotImplementedError("maxvol on slabs is not implemented yet (DESIGN.md section 6)")
+    # ------------------------------------------------------------------ largest component
+    def maxvol(self, a: Slab, conn: int = 26) -> Slab:
+        """the connected component(s) of a (global, across slabs) with the largest voxel count.
+        Every rank labels and counts its slab once (kept union-find state); the labels of the two
+        boundary planes with their local counts are all-gathered together with the cross-slab
+        label equivalences; the classes of the (small) boundary graph are resolved on every rank
+        and their counts summed.  The global maximum is the larger of the largest local count
+        (an all-reduce) and the largest class sum; winners are the local components of exactly
+        that size plus the members of the winning classes."""
+        import torch
+        e, c = self.e, self.c
+        if c.world == 1:
+            return a.like(e.maxvol(a.data, conn))
+        if not hasattr(e, "ccl_count"):
+            raise NotImplementedError("maxvol on slabs needs an engine with a kept union-find state")
+        nzl = e.nz(a.data)
+        st = e.ccl_create(a.data, conn)
+        local_max = int(e.ccl_count(st))
+        lab_bot, _ = e.ccl_plane(st, 0)
+        lab_top, _ = e.ccl_plane(st, nzl - 1)
+        lab_bot, lab_top = lab_bot.to(torch.int64) & 0xffffffff, lab_top.to(torch.int64) & 0xffffffff
+        tag = (c.rank + 1) << 32
+        gid_bot = torch.where(lab_bot > 0, lab_bot + tag, torch.zeros_like(lab_bot))
+        gid_top = torch.where(lab_top > 0, lab_top + tag, torch.zeros_like(lab_top))
+        below_top, _ = c.exchange_planes(gid_bot, gid_top)
+        pairs = torch.zeros((0, 2), dtype=torch.int64, device=gid_bot.device)
+        if below_top is not None:
+            pairs = boundary_pairs(below_top, gid_bot, conn)
+        mine = torch.unique(torch.cat([lab_bot[lab_bot > 0], lab_top[lab_top > 0]]))
+        sizes = np.asarray(e.ccl_sizes(st, mine.cpu().numpy().astype(np.uint32)), dtype=np.int64)
+        rows = torch.stack([mine + tag, torch.as_tensor(sizes, device=mine.device)], dim=1) if mine.numel() else \
+            torch.zeros((0, 2), dtype=torch.int64, device=gid_bot.device)
+        all_pairs = c.all_gather_rows(pairs).cpu().numpy()
+        all_sizes = c.all_gather_rows(rows).cpu().numpy()
+        ids, totals = boundary_class_sizes(all_pairs, all_sizes)
+        gmax = int(c.all_reduce([float(local_max)], "max", gid_bot.device)[0])
+        if totals.size:
+            gmax = max(gmax, int(totals.max()))
+        if gmax > 0:
+            if gmax <= 0xffffffff:
+                e.ccl_flag_size(st, gmax)        # components that are the largest on their own
+            win = ids[(totals == gmax) & ((ids >> 32) == c.rank + 1)]
+            if win.size:
+                e.ccl_flag(st, (win & 0xffffffff).astype(np.uint32))
+        out = e.ccl_select(st)
+        e.ccl_destroy(st)
+        return a.like(out)
 
 
 
@@ -482,6 +531,28 @@ def boundary_pairs(lower, upper, conn: int):
         return torch.zeros((0, 2), dtype=torch.int64, device=lower.device)
     # (packed >> 32) of a value with bit 63 set would sign-extend: labels are < 2^31, so it cannot
     return torch.stack([(packed >> 32) + tag_l, (packed & mask32) + tag_u], dim=1)
+
+
+def boundary_class_sizes(pairs: np.ndarray, sizes: np.ndarray):
+    """pairs: [m, 2] ids joined across a slab boundary; sizes: [n, 2] rows (id, local voxel count)
+    of EVERY boundary component.  Returns (ids, total): for each id the voxel count of its class
+    (the global component it belongs to) -- int64, a component can exceed 2^32 voxels."""
+    if sizes.size == 0:
+        return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    ids = np.unique(np.concatenate([sizes[:, 0], pairs.ravel()]).astype(np.int64))
+    n = ids.size
+    own = np.zeros(n, dtype=np.int64)
+    own[np.searchsorted(ids, sizes[:, 0])] = sizes[:, 1]
+    if pairs.size:
+        e0, e1 = np.searchsorted(ids, pairs[:, 0]), np.searchsorted(ids, pairs[:, 1])
+        graph = coo_matrix((np.ones(e0.size, dtype=np.int8), (e0, e1)), shape=(n, n))
+        ncomp, comp = connected_components(graph, directed=False)
+    else:
+        ncomp, comp = n, np.arange(n)
+    total = np.bincount(comp, weights=own.astype(np.float64), minlength=ncomp)   # exact below 2^53
+    return ids, np.rint(total[comp]).astype(np.int64)
 
 
 def resolve_boundary_graph(pairs: np.ndarray, reached: np.ndarray) -> np.ndarray:
