@@ -38,9 +38,9 @@ __device__ __forceinline__ unsigned digit_peers(unsigned active, unsigned d, int
 #pragma unroll
     for (int b = 0; b < 9; b++) {
         if (b < nbits) {
-            const bool bit = (d >> b) & 1u;
-            const unsigned bal = __ballot_sync(active, bit);
-            peers &= bit ? bal : ~bal;
+            const int m = (int)(d << (31 - b)) >> 31;      // 0 or ~0: bit b of the digit, as a mask
+            const unsigned bal = __ballot_sync(active, m < 0);
+            peers &= ~(bal ^ (unsigned)m);
         }
     }
     return peers;
@@ -178,17 +178,27 @@ rs_hist_kernel(const unsigned long long* __restrict__ buf0, const unsigned long 
         }
         for (int d = lane; d < kDigits; d += 32) cnt[warp][d] = 0;
         __syncwarp();
+        if ((unsigned long long)(tile + 1) * kTile <= n) {   // a full tile (all but the last of a volume): no bounds work
 #pragma unroll
-        for (int r = 0; r < kWarpRounds; r++) {
-            const unsigned p = base + r * 32 + lane;
-            const bool ok = p < n;
-            const unsigned active = __ballot_sync(0xffffffffu, ok);
-            if (ok) {
+            for (int r = 0; r < kWarpRounds; r++) {
                 const unsigned d = (key[r] >> shift) & (kDigits - 1);
-                const unsigned peers = digit_peers(active, d, kRadixBits);
+                const unsigned peers = digit_peers(0xffffffffu, d, kRadixBits);
                 if ((peers & ((1u << lane) - 1u)) == 0) cnt[warp][d] = (unsigned short)(cnt[warp][d] + __popc(peers));
+                __syncwarp();
             }
-            __syncwarp();
+        } else {
+#pragma unroll
+            for (int r = 0; r < kWarpRounds; r++) {
+                const unsigned p = base + r * 32 + lane;
+                const bool ok = p < n;
+                const unsigned active = __ballot_sync(0xffffffffu, ok);
+                if (ok) {
+                    const unsigned d = (key[r] >> shift) & (kDigits - 1);
+                    const unsigned peers = digit_peers(active, d, kRadixBits);
+                    if ((peers & ((1u << lane) - 1u)) == 0) cnt[warp][d] = (unsigned short)(cnt[warp][d] + __popc(peers));
+                }
+                __syncwarp();
+            }
         }
         __syncthreads();
         for (int d = threadIdx.x; d < kDigits; d += kPcThreads) {
@@ -315,26 +325,44 @@ rs_scatter_kernel(unsigned long long* __restrict__ buf0, unsigned long long* __r
         __syncwarp();
         // 2. rank of every key among the keys of its digit inside its warp
         unsigned short lrank[kWarpRounds];
+        if (tile_n == (unsigned)kTile) {   // a full tile: no bounds work in the rounds
 #pragma unroll
-        for (int r = 0; r < kWarpRounds; r++) {
-            const unsigned p = warp * kWarpKeys + r * 32 + lane;
-            const bool ok = p < tile_n;
-            const unsigned active = __ballot_sync(0xffffffffu, ok);
-            unsigned prev = 0, rank = 0;
-            int leader = 0;
-            if (ok) {
+            for (int r = 0; r < kWarpRounds; r++) {
                 const unsigned d = ((unsigned)(kv[r] >> 32) >> shift) & (kDigits - 1);
-                const unsigned peers = digit_peers(active, d, kRadixBits);
-                rank = __popc(peers & ((1u << lane) - 1u));
-                leader = __ffs(peers) - 1;
+                const unsigned peers = digit_peers(0xffffffffu, d, kRadixBits);
+                const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+                const int leader = __ffs(peers) - 1;
+                unsigned prev = 0;
                 if (lane == leader) {
                     prev = wcnt[warp][d];
                     wcnt[warp][d] = (unsigned short)(prev + __popc(peers));
                 }
+                prev = __shfl_sync(0xffffffffu, prev, leader);
+                lrank[r] = (unsigned short)(prev + rank);
+                __syncwarp();
             }
-            prev = __shfl_sync(0xffffffffu, prev, leader);   // all lanes take part; one instruction
-            lrank[r] = (unsigned short)(prev + rank);
-            __syncwarp();
+        } else {
+#pragma unroll
+            for (int r = 0; r < kWarpRounds; r++) {
+                const unsigned p = warp * kWarpKeys + r * 32 + lane;
+                const bool ok = p < tile_n;
+                const unsigned active = __ballot_sync(0xffffffffu, ok);
+                unsigned prev = 0, rank = 0;
+                int leader = 0;
+                if (ok) {
+                    const unsigned d = ((unsigned)(kv[r] >> 32) >> shift) & (kDigits - 1);
+                    const unsigned peers = digit_peers(active, d, kRadixBits);
+                    rank = __popc(peers & ((1u << lane) - 1u));
+                    leader = __ffs(peers) - 1;
+                    if (lane == leader) {
+                        prev = wcnt[warp][d];
+                        wcnt[warp][d] = (unsigned short)(prev + __popc(peers));
+                    }
+                }
+                prev = __shfl_sync(0xffffffffu, prev, leader);   // all lanes take part; one instruction
+                lrank[r] = (unsigned short)(prev + rank);
+                __syncwarp();
+            }
         }
         __syncthreads();
         // 3. per digit: offsets of the warps inside the digit, tile-local start, global base
