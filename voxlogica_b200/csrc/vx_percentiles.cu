@@ -514,9 +514,12 @@ extern "C" int32_t vx_percentiles(vx_ctx ctx, vx_img a, vx_img mask, double corr
           rs_plan_kernel<<<1, 1, 0, og.st>>>(plan); }
         rc = check_launch("rs_plan_kernel");
     }
-    // one block per tile of the largest possible mask (blocks beyond the actual count exit at once;
-    // an SM-sized grid walking the tiles was measured 15 % slower: fewer blocks in flight)
-    const int hx = ntiles_max, sx = ntiles_max;
+    // Blocks walk the tiles with a grid stride.  The grid is sized for the largest mask that
+    // keeps one tile per block up to a few thousand blocks per volume: an SM-sized grid was
+    // measured 15 % slower (fewer blocks in flight), one block per POSSIBLE tile launches
+    // thousands of blocks that only learn that the mask's count ends before their tile.
+    const int gx = std::min(ntiles_max, std::max(1024, 8192 / nb));
+    const int hx = gx, sx = gx;
     dim3 hgrid(hx, nb), sgrid(sx, nb);
     for (int pass = 0; pass < kMaxPasses && rc == VX_OK; pass++) {
         { VX_LAUNCH(og.c, og.s, "rs_hist_kernel");
@@ -535,7 +538,10 @@ extern "C" int32_t vx_percentiles(vx_ctx ctx, vx_img a, vx_img mask, double corr
         // one block per 256 sorted positions, volume-major block order: the scattered 4-byte
         // stores of one volume land while its 36 MB output is L2-resident, instead of
         // spreading over the whole batch (write amplification at batch 16: 2x slower)
-        int per_vol = (int)((nvox + kPcThreads - 1) / kPcThreads);
+        // (a bounded number of blocks per volume, each walking the sorted positions with a grid stride: one
+        // block per 256 voxels of the whole volume meant 400 k blocks per launch that only found
+        // out that their positions lie beyond the mask's count)
+        int per_vol = (int)std::min<size_t>((nvox + kPcThreads - 1) / kPcThreads, (size_t)std::max(4096, 131072 / nb));
         dim3 grid(per_vol, nb);
         { VX_LAUNCH(og.c, og.s, "pc_rank_kernel");
           pc_rank_kernel<<<grid, kPcThreads, 0, og.st>>>(k0, k1, count, nvox, (float*)O->d, correction, plan); }
