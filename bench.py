@@ -41,8 +41,8 @@ ALG_BYTES = {
     "xcorr_kernel": 5.0,             # u8 bins in, f32 coefficient out (13 B/voxel for the whole operator)
     "pointwise_program_kernel": None,  # depends on the program (5 for a threshold, 8/12 for arithmetic)
     "boolean_program_kernel": None,    # 2 (not) or 3 (and/or) per instruction chain
-    "morph16_kernel": 2.0, "ball_or_kernel": 1.0 + 1.0 / 8, "pack_bits_kernel": 1.0 + 1.0 / 8,
-    "xdilate_bits_kernel": None,     # 1/8 in, emax/8 out: depends on the radius
+    "morph16_kernel": 2.0, "ball_or_kernel": 1.0 + 1.0 / 8,
+    "pack_bits_kernel": 1.0 + 1.0 / 8,   # u8 in, packed rows out (+ emax pre-dilated levels, emax/8 more)
     # union-find kernels as launched by `through`: bits in/out are 1/8 B per voxel, labels are sparse
     "ccl_init_kernel": 1.0 + 1.0 / 8, "ccl_merge_kernel": None, "ccl_flatten_kernel": None,
     "ccl_select_kernel": 1.0 + 1.0 / 8, "ccl_seed_kernel": 1.0 + 1.0 / 8,
