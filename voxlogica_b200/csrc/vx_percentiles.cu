@@ -62,6 +62,9 @@ pc_compact_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mas
                   unsigned* __restrict__ plan) {
     __shared__ unsigned warp_tot[kPcThreads / 32];
     __shared__ unsigned tile_base;
+    // the pairs of a tile are collected in shared memory and leave it as one contiguous run:
+    // storing them straight from the lanes meant 32 partial-sector writes per store instruction
+    __shared__ unsigned long long stage[kPcThreads * 16];
     unsigned kmin = 0xffffffffu, kmax = 0u;
     const size_t vol = blockIdx.y;
     const float* a = img + vol * nvox;
@@ -111,19 +114,21 @@ pc_compact_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mas
             total += t;
         }
         if (threadIdx.x == 0) tile_base = total ? atomicAdd(count + vol, total) : 0u;
-        __syncthreads();
-        unsigned pos = tile_base + wbase + incl - c;
+        unsigned pos = wbase + incl - c;    // position inside the tile
 #pragma unroll
         for (int e = 0; e < 16; e++) {
             if ((bits >> e) & 1u) {
                 const unsigned key = sortable_key(v[e]);
                 kmin = min(kmin, key);
                 kmax = max(kmax, key);
-                po[pos] = ((unsigned long long)key << 32) | (unsigned)(first + e);
+                stage[pos] = ((unsigned long long)key << 32) | (unsigned)(first + e);
                 pos++;
             }
         }
-        __syncthreads();  // tile_base / warp_tot reuse
+        __syncthreads();
+        const unsigned tb = tile_base;
+        for (unsigned i = threadIdx.x; i < total; i += kPcThreads) po[tb + i] = stage[i];
+        __syncthreads();  // tile_base / warp_tot / stage reuse
     }
     kmin = __reduce_min_sync(0xffffffffu, kmin);
     kmax = __reduce_max_sync(0xffffffffu, kmax);
