@@ -97,6 +97,8 @@ def main():
             "interior6": (lambda: ops.interior(B, 6), lambda: ctx.interior(W, 6)),
             "through26": (lambda: ops.through(A, B, 26), lambda: ctx.through(WS, W, 26)),
             "through6": (lambda: ops.through(A, B, 6), lambda: ctx.through(WS, W, 6)),
+            "maxvol26": (lambda: ops.maxvol(B, 26), lambda: ctx.maxvol(W, 26)),
+            "maxvol6": (lambda: ops.maxvol(B, 6), lambda: ctx.maxvol(W, 6)),
             "distlt5": (lambda: ops.distlt(5.0, B), lambda: ctx.distlt(5.0, W)),
             "flt2": (lambda: ops.flt(2.0, B), lambda: ctx.distlt(2.0, ctx.distgeq(2.0, ctx.not_(W)))),
             "edt": (lambda: ops.edt(B), lambda: ctx.edt(W)),
@@ -141,6 +143,7 @@ def main():
     fg = ops.volume(B)
     reach = {}
     for name, fn in (("near26", lambda: ops.near(B, 26)), ("through26", lambda: ops.through(A, B, 26)),
+                     ("maxvol26", lambda: ops.maxvol(B, 26)),
                      ("distlt5", lambda: ops.distlt(5.0, B)), ("flt2", lambda: ops.flt(2.0, B)),
                      ("edt", lambda: ops.edt(B)), ("volume", lambda: ops.volume(B))):
         s = timed(fn)
