@@ -332,6 +332,18 @@ VX_API int32_t vx_minmax(vx_ctx ctx, vx_img a, vx_img mask, double* out_min, dou
  * and 0 outside the mask (Greta.pdf p.52 percentiles(intensity, brain)). */
 VX_API int32_t vx_percentiles(vx_ctx ctx, vx_img a, vx_img mask, double correction, vx_img* out);
 
+/* Building blocks of a slab-decomposed percentiles (one rank of a z-slab decomposition,
+ * DESIGN.md section 6): compact the masked voxels of the local slab into (sortable key << 32 |
+ * voxel index) pairs, sort pairs by key, rank sorted pairs against a global count (the ranks are
+ * written at dst[payload]), scatter values back into an image by payload.  All buffers are
+ * caller-owned DEVICE memory; single-volume images; the calls block until the result is there. */
+VX_API int32_t vx_pc_pairs(vx_ctx ctx, vx_img a, vx_img mask, uint64_t* pairs_dev, uint64_t capacity, uint64_t* n);
+VX_API int32_t vx_pc_sort(vx_ctx ctx, uint64_t* pairs_dev, uint64_t n, uint64_t* scratch_dev);
+VX_API int32_t vx_pc_rank(vx_ctx ctx, const uint64_t* sorted_dev, uint64_t n, uint64_t less_before,
+                          uint64_t n_total, double correction, float* dst_dev);
+VX_API int32_t vx_pc_scatter(vx_ctx ctx, const uint64_t* pairs_dev, const float* values_dev, uint64_t n,
+                             vx_img like, vx_img* out);
+
 /* --------------------------------------------- measurement helpers
  * Events are recorded on the calling thread's stream of the context. */
 VX_API int32_t vx_event_create(vx_ctx ctx, vx_evt* out);

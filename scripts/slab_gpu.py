@@ -99,6 +99,7 @@ def main():
             "through6": (lambda: ops.through(A, B, 6), lambda: ctx.through(WS, W, 6)),
             "maxvol26": (lambda: ops.maxvol(B, 26), lambda: ctx.maxvol(W, 26)),
             "maxvol6": (lambda: ops.maxvol(B, 6), lambda: ctx.maxvol(W, 6)),
+            "percentiles": (lambda: ops.percentiles(F, B, 0.5), lambda: ctx.percentiles(FW, W, 0.5)),
             "distlt5": (lambda: ops.distlt(5.0, B), lambda: ctx.distlt(5.0, W)),
             "flt2": (lambda: ops.flt(2.0, B), lambda: ctx.distlt(2.0, ctx.distgeq(2.0, ctx.not_(W)))),
             "edt": (lambda: ops.edt(B), lambda: ctx.edt(W)),

@@ -38,6 +38,37 @@ class OracleEngine:
     def components(self, a, conn): return orc.components(a[0], conn).astype(np.uint32)[None]
     def dist(self, op, r, a): return orc.dist_cmp(a[0], op, r, self.sp)[None]
     def maxvol(self, a, conn): return orc.maxvol(a[0], conn)[None]
+    def percentiles(self, a, mask, correction): return orc.percentiles(a[0], mask[0], correction)[None]
+
+    # building blocks of the distributed percentiles (vx_pc_* of the C ABI) in numpy
+    @staticmethod
+    def _sortable(v):
+        u = (v.astype(np.float32) + np.float32(0.0)).view(np.uint32).astype(np.uint64)
+        return np.where(u & 0x80000000, (~u) & 0xffffffff, u | 0x80000000).astype(np.uint64)
+
+    def pc_pairs(self, a, mask):
+        idx = np.flatnonzero(mask[0].ravel() != 0).astype(np.uint64)
+        keys = self._sortable(a[0].ravel()[idx.astype(np.int64)])
+        return torch.from_numpy(((keys << np.uint64(32)) | idx).view(np.int64))
+
+    def pc_sort(self, pairs):
+        p = pairs.numpy().view(np.uint64)
+        order = np.argsort(p >> np.uint64(32), kind="stable")
+        return torch.from_numpy(np.ascontiguousarray(p[order]).view(np.int64))
+
+    def pc_rank(self, sorted_pairs, less_before, n_total, correction):
+        p = sorted_pairs.numpy().view(np.uint64)
+        keys, payload = p >> np.uint64(32), (p & np.uint64(0xffffffff)).astype(np.int64)
+        less = np.searchsorted(keys, keys, side="left").astype(np.float64)
+        equal = np.searchsorted(keys, keys, side="right").astype(np.float64) - less
+        out = np.zeros(p.size, np.float32)
+        out[payload] = ((float(less_before) + less + correction * equal) / float(n_total)).astype(np.float32)
+        return torch.from_numpy(out)
+
+    def pc_scatter(self, pairs, values, like):
+        out = np.zeros(like[0].size, np.float32)
+        out[(pairs.numpy().view(np.uint64) & np.uint64(0xffffffff)).astype(np.int64)] = values.numpy()
+        return out.reshape(like.shape)
 
     # kept union-find state (vx_ccl_* of the C ABI), restated on oracle labels
     class _State:

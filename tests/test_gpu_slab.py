@@ -128,7 +128,18 @@ def test_slab_ops_two_threads_one_gpu(ctx, world, peer):
         want[f"distlt{r}"] = ctx.distlt(r, Si).numpy()[0]
         want[f"flt{r}"] = ctx.distlt(r, ctx.distgeq(r, ctx.not_(ctx.near(Si)))).numpy()[0]
     want["xcorr"] = ctx.cross_correlation(3.0, Fi, Fi, Bi, 0.0, 1.0, 16).numpy()[0]
+    # rank normalisation with ties, negative values and both zeros; mask = b
+    gvals = f.copy()
+    gvals[rng.random(shape) < 0.25] = 0.5
+    gvals[rng.random(shape) < 0.05] *= -1.0
+    gvals[0, 0, :2] = [0.0, -0.0]
+    Gi = ctx.upload(gvals, spacing=sp)
+    for corr in (0.0, 0.5):
+        want[f"percentiles{corr}"] = ctx.percentiles(Gi, Bi, corr).numpy()[0]
+    one = np.zeros(shape, np.uint8); one[shape[0] - 1, 2, 3] = 1
+    want["percentiles_one"] = ctx.percentiles(Gi, ctx.upload(one, spacing=sp)).numpy()[0]
     want["edt"] = ctx.edt(Si).numpy()[0]
+    want["percentiles_empty"] = np.zeros(shape, np.float32)
     assert want["through6"].sum() > a.sum() and want["through6"][shape[0] - 1].any()   # crosses every slab
     shared = ThreadComm.Shared(world)
     errors, results = [], {}
@@ -153,6 +164,11 @@ def test_slab_ops_two_threads_one_gpu(ctx, world, peer):
                 got[f"distlt{r}"] = ops.distlt(r, S)
                 got[f"flt{r}"] = ops.flt(r, ops.near(S))
             got["xcorr"] = ops.cross_correlation(3.0, F, F, B, 0.0, 1.0, 16)
+            G = ops.scatter_from_global(up, gvals, sp)
+            for corr in (0.0, 0.5):
+                got[f"percentiles{corr}"] = ops.percentiles(G, B, corr)
+            got["percentiles_one"] = ops.percentiles(G, ops.scatter_from_global(up, one, sp))
+            got["percentiles_empty"] = ops.percentiles(G, ops.scatter_from_global(up, np.zeros(shape, np.uint8), sp))
             got["edt"] = ops.edt(S)
             vol = ops.volume(B)
             z0, z1 = slab_bounds(shape[0], world)[rank]

@@ -83,6 +83,18 @@ def _worker(rank, world, port, q):
         F = ops.scatter_from_global(up, f, sp)
         want = orc.cross_correlation(3.0, f, f, b, 0.0, 1.0, 16, sp)
         check("xcorr", ops.cross_correlation(3.0, F, F, B, 0.0, 1.0, 16), want)
+        # rank normalisation: ties (a quarter of the voxels share one value), negative values, both zeros
+        g = f.copy()
+        g[rng.random(shape) < 0.25] = 0.5
+        g[rng.random(shape) < 0.05] *= -1.0
+        g[0, 0, :2] = [0.0, -0.0]
+        G = ops.scatter_from_global(up, g, sp)
+        for corr in (0.0, 0.5):
+            check(f"percentiles/{corr}", ops.percentiles(G, B, corr), orc.percentiles(g, b, correction=corr))
+        empty = np.zeros(shape, np.uint8)
+        check("percentiles/empty", ops.percentiles(G, ops.scatter_from_global(up, empty, sp)), np.zeros(shape, np.float32))
+        one = empty.copy(); one[shape[0] - 1, 2, 3] = 1     # every masked voxel on the last rank
+        check("percentiles/one", ops.percentiles(G, ops.scatter_from_global(up, one, sp)), orc.percentiles(g, one))
         if ops.volume(B) != float(b.sum()): fails.append("volume")
         if ops.min(F) != float(f.min()) or ops.max(F) != float(f.max()): fails.append("minmax")
         check("lt", ops.cmp_scalar(F, "<", 0.3), orc.cmp_scalar(f, "<", 0.3))

@@ -125,6 +125,10 @@ SIGNATURES = {
     "vx_max_masked": [u64, u64, u64, P(f64)],
     "vx_sum": [u64, u64, P(f64)],
     "vx_minmax": [u64, u64, u64, P(f64), P(f64)],
+    "vx_pc_pairs": [u64, u64, u64, C.c_void_p, u64, P(u64)],
+    "vx_pc_sort": [u64, C.c_void_p, u64, C.c_void_p],
+    "vx_pc_rank": [u64, C.c_void_p, u64, u64, u64, f64, C.c_void_p],
+    "vx_pc_scatter": [u64, C.c_void_p, C.c_void_p, u64, u64, P(u64)],
     "vx_percentiles": [u64, u64, u64, f64, P(u64)],
     "vx_event_create": [u64, P(u64)],
     "vx_event_record": [u64, u64],

@@ -476,6 +476,66 @@ pc_rank_kernel(const unsigned long long* __restrict__ buf0, const unsigned long 
     }
 }
 
+// ---- building blocks of a slab-decomposed percentiles (single volume, caller-owned buffers) ----
+// ranks by payload: the pair at sorted position p holds key and a payload (an index into the
+// caller's receive order); dst[payload] = (less_before + #local keys below + correction * #equal) / n_total
+__global__ void __launch_bounds__(kPcThreads)
+pc_rank_payload_kernel(const unsigned long long* __restrict__ k, unsigned n, unsigned long long less_before,
+                       double n_total, double correction, float* __restrict__ dst) {
+    auto key_at = [&](unsigned i) { return (unsigned)(k[i] >> 32); };
+    const int lane = threadIdx.x & 31;
+    for (unsigned pb = blockIdx.x * kPcThreads + (threadIdx.x & ~31u); pb < n; pb += gridDim.x * kPcThreads) {
+        const unsigned p = pb + lane;
+        const bool ok = p < n;
+        const unsigned long long kv = ok ? k[p] : 0ull;
+        const unsigned key = (unsigned)(kv >> 32);
+        unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
+        if (lane == 0 && pb > 0) prev = key_at(pb - 1);
+        const unsigned heads = __ballot_sync(0xffffffffu, ok && (p == 0 || key != prev));
+        const unsigned next = __shfl_down_sync(0xffffffffu, key, 1);
+        const bool tail = ok && (p + 1 >= n || (lane == 31 ? key_at(p + 1) != key : next != key));
+        const unsigned tails = __ballot_sync(0xffffffffu, tail);
+        if (!ok) continue;
+        const unsigned below = heads & (0xffffffffu >> (31 - lane));
+        unsigned less;
+        if (below) {
+            less = pb + (31 - __clz(below));
+        } else {
+            unsigned lo = 0, hi = pb;
+            while (lo < hi) { unsigned mid = (lo + hi) >> 1; if (key_at(mid) < key) lo = mid + 1; else hi = mid; }
+            less = lo;
+        }
+        double num = (double)(less_before + less);
+        if (correction != 0.0) {
+            const unsigned above = tails & (0xffffffffu << lane);
+            unsigned up;
+            if (above) {
+                up = pb + (__ffs(above) - 1) + 1;
+            } else {
+                unsigned lo = pb + 32, hi = n;
+                while (lo < hi) { unsigned mid = (lo + hi) >> 1; if (key_at(mid) <= key) lo = mid + 1; else hi = mid; }
+                up = lo;
+            }
+            num = __dadd_rn(num, __dmul_rn(correction, (double)(up - less)));
+        }
+        dst[(unsigned)kv] = (float)__ddiv_rn(num, n_total);
+    }
+}
+
+// out[payload(pairs[i])] = values[i]
+__global__ void __launch_bounds__(kPcThreads)
+pc_scatter_payload_kernel(const unsigned long long* __restrict__ pairs, const float* __restrict__ values,
+                          unsigned long long n, float* __restrict__ out) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * kPcThreads + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * kPcThreads)
+        out[(unsigned)pairs[i]] = values[i];
+}
+
+__global__ void pc_set_plan_kernel(unsigned* __restrict__ count, unsigned* __restrict__ plan, unsigned n, unsigned passes) {
+    count[0] = n;
+    plan[0] = passes;
+}
+
 }  // namespace vx
 
 using namespace vx;
@@ -559,3 +619,121 @@ extern "C" int32_t vx_percentiles(vx_ctx ctx, vx_img a, vx_img mask, double corr
     if (rc != VX_OK) { drop(O); return rc; }
     return og.finish(O, out);
 }
+
+
+// ------------------------------------------------------------------------------------------
+// Building blocks of a slab-decomposed percentiles.  The caller (one rank
+// of voxlogica_b200/slab.py) owns the pair buffers in DEVICE memory; a pair is
+// (sortable key << 32) | payload.  Single-volume images only.
+extern "C" {
+
+int32_t vx_pc_pairs(vx_ctx ctx, vx_img a, vx_img mask, uint64_t* pairs_dev, uint64_t capacity, uint64_t* n_out) {
+    VX_REQUIRE(n_out != nullptr, VX_E_INVALID_ARG, "n_out is NULL");
+    OpGuard og;
+    VX_TRY(og.begin(ctx));
+    Image *A = nullptr, *M = nullptr;
+    VX_TRY(og.input(a, &A, VX_F32));
+    VX_TRY(og.input(mask, &M, VX_U8));
+    VX_TRY(same_shape(A, M));
+    VX_REQUIRE(A->nb == 1, VX_E_UNSUPPORTED, "vx_pc_pairs takes a single-volume image");
+    const size_t nvox = A->nvox();
+    VX_REQUIRE(pairs_dev != nullptr && capacity >= nvox, VX_E_INVALID_ARG,
+               "the pair buffer must hold one entry per voxel (%zu)", nvox);
+    unsigned* count = nullptr;
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * 8, (void**)&count));
+    VX_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned) * 8, og.st));
+    int per_vol = (int)((nvox + (size_t)kPcThreads * 16 - 1) / ((size_t)kPcThreads * 16));
+    dim3 grid(per_vol < kNumSMs * 8 ? per_vol : kNumSMs * 8, 1);
+    { VX_LAUNCH(og.c, og.s, "pc_compact_kernel");
+      pc_compact_kernel<<<grid, kPcThreads, 0, og.st>>>((const float*)A->d, (const uint8_t*)M->d, nvox,
+                                                       (unsigned long long*)pairs_dev, count, count + 4); }
+    VX_TRY(check_launch("pc_compact_kernel"));
+    unsigned h = 0;
+    VX_CUDA(cudaMemcpyAsync(&h, count, sizeof(unsigned), cudaMemcpyDeviceToHost, og.st));
+    VX_TRY(scratch_free(og.c, og.s, count));
+    VX_CUDA(cudaStreamSynchronize(og.st));
+    *n_out = h;
+    return og.finish_scalar();
+}
+
+// stable LSD sort of n pairs by their keys (all 32 key bits: four passes, the result ends in
+// pairs_dev); scratch_dev: n entries.  n < 2^32.
+int32_t vx_pc_sort(vx_ctx ctx, uint64_t* pairs_dev, uint64_t n, uint64_t* scratch_dev) {
+    OpGuard og;
+    VX_TRY(og.begin(ctx));
+    if (n == 0) return og.finish_scalar();
+    VX_REQUIRE(pairs_dev != nullptr && scratch_dev != nullptr, VX_E_INVALID_ARG, "NULL buffer");
+    VX_REQUIRE(n < 0xffffffffull, VX_E_UNSUPPORTED, "more than 2^32 - 1 pairs");
+    const int ntiles = (int)((n + kTile - 1) / kTile);
+    unsigned *count = nullptr, *table = nullptr, *totals = nullptr;
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * 8, (void**)&count));
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (size_t)kDigits * ntiles, (void**)&table));
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * kDigits, (void**)&totals));
+    unsigned* plan = count + 4;
+    pc_set_plan_kernel<<<1, 1, 0, og.st>>>(count, plan, (unsigned)n, (unsigned)kMaxPasses);
+    VX_TRY(check_launch("pc_set_plan_kernel"));
+    unsigned long long *k0 = (unsigned long long*)pairs_dev, *k1 = (unsigned long long*)scratch_dev;
+    const int gx = std::min(ntiles, 8192);
+    for (int pass = 0; pass < kMaxPasses; pass++) {
+        { VX_LAUNCH(og.c, og.s, "rs_hist_kernel");
+          rs_hist_kernel<<<dim3(gx, 1), kPcThreads, 0, og.st>>>(k0, k1, count, (size_t)n, table, ntiles, pass, plan); }
+        VX_TRY(check_launch("rs_hist_kernel"));
+        { VX_LAUNCH(og.c, og.s, "rs_rowscan_kernel");
+          rs_rowscan_kernel<<<dim3(kDigits, 1), 256, 0, og.st>>>(count, table, totals, ntiles, pass, plan); }
+        VX_TRY(check_launch("rs_rowscan_kernel"));
+        { VX_LAUNCH(og.c, og.s, "rs_scatter_kernel");
+          rs_scatter_kernel<<<dim3(gx, 1), kPcThreads, 0, og.st>>>(k0, k1, count, (size_t)n, table, totals, ntiles, pass, plan); }
+        VX_TRY(check_launch("rs_scatter_kernel"));
+    }
+    static_assert(kMaxPasses % 2 == 0, "an even number of passes leaves the result in the first buffer");
+    VX_TRY(scratch_free(og.c, og.s, count));
+    VX_TRY(scratch_free(og.c, og.s, table));
+    VX_TRY(scratch_free(og.c, og.s, totals));
+    VX_CUDA(cudaStreamSynchronize(og.st));
+    return og.finish_scalar();
+}
+
+// ranks of n SORTED pairs, written at dst_dev[payload]:
+//   (less_before + #{local keys below} + correction * #{local keys equal}) / n_total
+int32_t vx_pc_rank(vx_ctx ctx, const uint64_t* sorted_dev, uint64_t n, uint64_t less_before, uint64_t n_total,
+                   double correction, float* dst_dev) {
+    OpGuard og;
+    VX_TRY(og.begin(ctx));
+    if (n == 0) return og.finish_scalar();
+    VX_REQUIRE(sorted_dev != nullptr && dst_dev != nullptr && n_total > 0 && n < 0xffffffffull, VX_E_INVALID_ARG,
+               "invalid arguments");
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + kPcThreads - 1) / kPcThreads, 131072);
+    { VX_LAUNCH(og.c, og.s, "pc_rank_payload_kernel");
+      pc_rank_payload_kernel<<<grid, kPcThreads, 0, og.st>>>((const unsigned long long*)sorted_dev, (unsigned)n,
+                                                            (unsigned long long)less_before, (double)n_total, correction, dst_dev); }
+    VX_TRY(check_launch("pc_rank_payload_kernel"));
+    VX_CUDA(cudaStreamSynchronize(og.st));
+    return og.finish_scalar();
+}
+
+// new f32 image shaped like `like`: out[payload(pairs[i])] = values[i], 0 elsewhere
+int32_t vx_pc_scatter(vx_ctx ctx, const uint64_t* pairs_dev, const float* values_dev, uint64_t n, vx_img like, vx_img* out) {
+    VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");
+    OpGuard og;
+    VX_TRY(og.begin(ctx));
+    Image* L = nullptr;
+    VX_TRY(og.input(like, &L, 0));
+    VX_REQUIRE(L->nb == 1, VX_E_UNSUPPORTED, "vx_pc_scatter takes a single-volume image");
+    VX_REQUIRE(n <= L->nvox() && (n == 0 || (pairs_dev != nullptr && values_dev != nullptr)), VX_E_INVALID_ARG,
+               "invalid arguments");
+    Image* O = nullptr;
+    VX_TRY(new_image(og.c, VX_F32, L->nx, L->ny, L->nz, 1, L->sp, &O));
+    int rc = VX_OK;
+    if (cudaMemsetAsync(O->d, 0, O->bytes, og.st) != cudaSuccess) rc = fail(VX_E_CUDA, "memset failed");
+    if (rc == VX_OK && n > 0) {
+        const unsigned grid = (unsigned)std::min<uint64_t>((n + kPcThreads - 1) / kPcThreads, 131072);
+        { VX_LAUNCH(og.c, og.s, "pc_scatter_payload_kernel");
+          pc_scatter_payload_kernel<<<grid, kPcThreads, 0, og.st>>>((const unsigned long long*)pairs_dev, values_dev,
+                                                                   (unsigned long long)n, (float*)O->d); }
+        rc = check_launch("pc_scatter_payload_kernel");
+    }
+    if (rc != VX_OK) { drop(O); return rc; }
+    return og.finish(O, out);
+}
+
+}  // extern "C"

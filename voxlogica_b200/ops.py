@@ -449,6 +449,50 @@ class Context:
     def sum(self, a: Image) -> np.ndarray:
         return self._scalars(lambda b: self.lib.vx_sum(self.handle, a.handle, b), a.nb)
 
+    # building blocks of the slab-decomposed percentiles: torch device tensors of int64 pairs
+    # (sortable key << 32 | payload) owned by the caller; see voxlogica_b200/slab.py
+    def _torch_ready(self, *tensors):
+        import torch
+        for t in tensors:
+            if t is not None and t.is_cuda:
+                torch.cuda.current_stream(t.device).synchronize()
+
+    def pc_pairs(self, a: Image, mask: Image):
+        """masked voxels of a single-volume image -> int64 tensor [n] of (key << 32 | voxel index)"""
+        import torch
+        _, nx, ny, nz, nb, _ = a.info()
+        buf = torch.empty(nx * ny * nz, dtype=torch.int64, device=f"cuda:{self.device}")
+        self._torch_ready(buf)
+        n = A.u64()
+        check(self.lib.vx_pc_pairs(self.handle, a.handle, mask.handle, C.c_void_p(buf.data_ptr()), buf.numel(), C.byref(n)))
+        return buf[: int(n.value)].clone()
+
+    def pc_sort(self, pairs):
+        """stable sort of the pairs by their (unsigned) keys; returns a new tensor"""
+        import torch
+        out, scratch = pairs.contiguous().clone(), torch.empty_like(pairs)
+        self._torch_ready(out, scratch)
+        check(self.lib.vx_pc_sort(self.handle, C.c_void_p(out.data_ptr()), out.numel(), C.c_void_p(scratch.data_ptr())))
+        return out
+
+    def pc_rank(self, sorted_pairs, less_before: int, n_total: int, correction: float = 0.0):
+        """f32 tensor r with r[payload] = (less_before + #keys below + correction * #equal) / n_total"""
+        import torch
+        dst = torch.zeros(sorted_pairs.numel(), dtype=torch.float32, device=sorted_pairs.device)
+        self._torch_ready(sorted_pairs, dst)
+        check(self.lib.vx_pc_rank(self.handle, C.c_void_p(sorted_pairs.data_ptr()), sorted_pairs.numel(), int(less_before),
+                                  int(n_total), float(correction), C.c_void_p(dst.data_ptr())))
+        return dst
+
+    def pc_scatter(self, pairs, values, like: Image) -> Image:
+        """new f32 image: out[payload(pairs[i])] = values[i], 0 elsewhere"""
+        pairs, values = pairs.contiguous(), values.contiguous()
+        self._torch_ready(pairs, values)
+        img = self._out(lambda o: self.lib.vx_pc_scatter(self.handle, C.c_void_p(pairs.data_ptr()),
+                                                         C.c_void_p(values.data_ptr()), pairs.numel(), like.handle, o))
+        self.sync()          # the tensors may be freed by torch as soon as we return
+        return img
+
     def percentiles(self, a: Image, mask: Image, correction: float = 0.0) -> Image:
         return self._out(lambda o: self.lib.vx_percentiles(self.handle, a.handle, mask.handle,
                                                            float(correction), o))

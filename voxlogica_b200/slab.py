@@ -112,6 +112,11 @@ class CudaEngine:
     def ccl_sizes(self, st, labels): return self.ctx.ccl_sizes(st, labels)
     def ccl_flag_size(self, st, size): self.ctx.ccl_flag_size(st, size)
     def maxvol(self, a, conn): return self.ctx.maxvol(a, conn)
+    def percentiles(self, a, mask, correction): return self.ctx.percentiles(a, mask, correction)
+    def pc_pairs(self, a, mask): return self.ctx.pc_pairs(a, mask)
+    def pc_sort(self, pairs): return self.ctx.pc_sort(pairs)
+    def pc_rank(self, pairs, less_before, n_total, correction): return self.ctx.pc_rank(pairs, less_before, n_total, correction)
+    def pc_scatter(self, pairs, values, like): return self.ctx.pc_scatter(pairs, values, like)
 
     def ccl_plane(self, st, z):
         lab, hit = self.ctx.ccl_plane(st, z)
@@ -176,8 +181,11 @@ class SlabComm:
             if r == self.rank:
                 recv[r].copy_(send[r])
                 continue
-            ops.append(dist.P2POp(dist.isend, send[r].contiguous(), r, self.group))
-            ops.append(dist.P2POp(dist.irecv, recv[r], r, self.group))
+            # empty messages are skipped on both sides (sender and receiver know the sizes)
+            if send[r].numel():
+                ops.append(dist.P2POp(dist.isend, send[r].contiguous(), r, self.group))
+            if recv[r].numel():
+                ops.append(dist.P2POp(dist.irecv, recv[r], r, self.group))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
@@ -450,9 +458,56 @@ class SlabOps:
         recv = c.exchange(send, [(nzl, y1 - y0, nx) for (y0, y1) in yb])
         return a.like(e.from_tensor(torch.cat(recv, dim=1), a))
 
-    # ------------------------------------------------------------------ not decomposed yet
-    def percentiles(self, *a, **k):
-        raise NotImplementedError("percentiles on slabs needs a distributed sort (DESIGN.md section 6)")
+    # ------------------------------------------------------------------ rank normalisation
+    def percentiles(self, a: Slab, mask: Slab, correction: float = 0.0) -> Slab:
+        """rank of every masked voxel among ALL masked voxels of the distributed volume -- an exact
+        distributed sort by sampling: every rank compacts and sorts its (key, voxel) pairs, the
+        key space is cut at W-1 splitters taken from a sample of every rank's sorted keys, each
+        rank receives the pairs of its key range (a personalised all-to-all of contiguous slices),
+        sorts them and ranks them against the global count (equal keys always meet on one rank,
+        so ties are resolved there), and the ranks travel back the same way."""
+        import torch
+        e, c = self.e, self.c
+        if c.world == 1:
+            return a.like(e.percentiles(a.data, mask.data, correction))
+        W = c.world
+        pairs = e.pc_sort(e.pc_pairs(a.data, mask.data))              # int64: key << 32 | voxel index
+        dev = pairs.device
+        keys = (pairs >> 32) & 0xffffffff                              # unsigned key as a non-negative int64
+        n = int(pairs.numel())
+        # splitters: up to 1024 evenly spaced sorted keys per rank
+        if n:
+            idx = torch.linspace(0, n - 1, min(n, 1024), device=dev).round().to(torch.int64)
+            sample = keys[idx]
+        else:
+            sample = torch.zeros(0, dtype=torch.int64, device=dev)
+        allsamp = torch.sort(c.all_gather_rows(sample[:, None])[:, 0]).values
+        if allsamp.numel():
+            pos = (torch.arange(1, W, device=dev, dtype=torch.float64) * allsamp.numel() / W).floor().to(torch.int64)
+            splitters = allsamp[pos.clamp(max=allsamp.numel() - 1)]
+        else:
+            splitters = torch.zeros(W - 1, dtype=torch.int64, device=dev)
+        cuts = torch.searchsorted(keys, splitters, right=False).tolist() if n else [0] * (W - 1)
+        bounds = [0] + cuts + [n]                                      # rank r gets keys in [splitter r-1, splitter r)
+        send = [pairs[bounds[r]:bounds[r + 1]] for r in range(W)]
+        sizes = c.all_gather_rows(torch.tensor([[bounds[r + 1] - bounds[r] for r in range(W)]],
+                                               dtype=torch.int64, device=dev)).cpu().numpy()   # [source][destination]
+        recv = c.exchange(send, [(int(sizes[s, c.rank]),) for s in range(W)])
+        got = torch.cat(recv) if recv else torch.zeros(0, dtype=torch.int64, device=dev)
+        m = int(got.numel())
+        per_dest = sizes.sum(axis=0)
+        less_before, n_total = int(per_dest[:c.rank].sum()), int(per_dest.sum())
+        # payload := position in the receive order, so that the ranks can be sent back slice by slice
+        tagged = (got & ~0xffffffff) | torch.arange(m, dtype=torch.int64, device=dev)
+        if m and n_total:
+            ranks_recv = e.pc_rank(e.pc_sort(tagged), less_before, n_total, correction)
+        else:
+            ranks_recv = torch.zeros(m, dtype=torch.float32, device=dev)
+        offs = np.concatenate([[0], np.cumsum(sizes[:, c.rank])]).astype(np.int64)
+        back = c.exchange([ranks_recv[int(offs[s]):int(offs[s + 1])] for s in range(W)],
+                          [(bounds[r + 1] - bounds[r],) for r in range(W)])
+        ranks_local = torch.cat(back) if back else torch.zeros(0, dtype=torch.float32, device=dev)
+        return a.like(e.pc_scatter(pairs, ranks_local, a.data))
 
     # ------------------------------------------------------------------ largest component
     def maxvol(self, a: Slab, conn: int = 26) -> Slab:
