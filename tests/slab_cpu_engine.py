@@ -38,6 +38,7 @@ class OracleEngine:
     def components(self, a, conn): return orc.components(a[0], conn).astype(np.uint32)[None]
     def dist(self, op, r, a): return orc.dist_cmp(a[0], op, r, self.sp)[None]
     def maxvol(self, a, conn): return orc.maxvol(a[0], conn)[None]
+    def border(self, like): return orc.border(like[0])[None]
     def percentiles(self, a, mask, correction): return orc.percentiles(a[0], mask[0], correction)[None]
 
     # building blocks of the distributed percentiles (vx_pc_* of the C ABI) in numpy

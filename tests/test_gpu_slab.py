@@ -192,6 +192,50 @@ def test_slab_ops_two_threads_one_gpu(ctx, world, peer):
     assert len(results) == world
 
 
+@pytest.mark.parametrize("world,peer", [(2, True), (3, False)])
+def test_gtv_spec_on_slabs_equals_whole_volume(ctx, world, peer):
+    """the whole GTV spec with every operator slab-decomposed (threads as ranks on one GPU) against the
+    ImgQL driver on the whole volume: every named intermediate, the f32 maps bit for bit"""
+    from voxlogica_b200.imgql import run_gtv
+    from voxlogica_b200.slab import CudaEngine, SlabOps, slab_bounds
+    from voxlogica_b200.synth import brats_like
+    shape, sp = (48, 80, 96), (1.0, 1.0, 1.0)
+    flair = brats_like(seed=1234, shape=shape)
+    whole = run_gtv(ctx, ctx.upload(flair[None], spacing=sp))
+    names = ("background", "brain", "normFlair", "hyperIntense", "veryIntense", "growTum", "tumSim", "tumStatCC", "gtv")
+    want = {k: whole[k].numpy()[0] for k in names}
+    assert want["gtv"].sum() > 0
+    shared = ThreadComm.Shared(world)
+    errors, done = [], {}
+
+    def run(rank):
+        try:
+            ops = SlabOps(CudaEngine(ctx), ThreadComm(shared, rank))
+            if peer:
+                ops.enable_peer_halo(shape[1], shape[2])
+            F = ops.scatter_from_global(lambda arr, s: ctx.upload(arr, spacing=s), flair, sp)
+            got = ops.gtv(F)
+            z0, z1 = slab_bounds(shape[0], world)[rank]
+            for k in names:
+                g_, w_ = got[k].data.numpy()[0], want[k][z0:z1]
+                if g_.dtype == np.float32:
+                    g_, w_ = g_.view(np.uint32), w_.view(np.uint32)
+                if not np.array_equal(g_, w_):
+                    errors.append((rank, k))
+            if got["gtvVolume"] != float(want["gtv"].sum()):
+                errors.append((rank, "gtvVolume"))
+            done[rank] = True
+        except Exception as ex:  # pragma: no cover
+            errors.append((rank, repr(ex)))
+            shared.barrier.abort()
+
+    ths = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in ths]
+    [t.join(timeout=300) for t in ths]
+    assert not errors, errors
+    assert len(done) == world
+
+
 @pytest.mark.parametrize("peer", [False, True])
 def test_slab_multi_gpu_nccl(peer):
     import torch

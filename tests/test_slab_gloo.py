@@ -95,6 +95,24 @@ def _worker(rank, world, port, q):
         check("percentiles/empty", ops.percentiles(G, ops.scatter_from_global(up, empty, sp)), np.zeros(shape, np.float32))
         one = empty.copy(); one[shape[0] - 1, 2, 3] = 1     # every masked voxel on the last rank
         check("percentiles/one", ops.percentiles(G, ops.scatter_from_global(up, one, sp)), orc.percentiles(g, one))
+        check("border", ops.border(B), orc.border(b))
+        # the whole GTV spec on slabs == the oracle composition on the whole volume
+        from gtv_ref import gtv_oracle
+        from voxlogica_b200.synth import brats_like
+        gshape = (40, 64, 80)
+        flair = brats_like(seed=1234, shape=gshape)
+        gops = SlabOps(OracleEngine((1.0, 1.0, 1.0)), ops.c)
+        want_g = gtv_oracle(orc, flair)
+        got_g = gops.gtv(gops.scatter_from_global(up, flair, (1.0, 1.0, 1.0)))
+        gz0, gz1 = slab_bounds(gshape[0], world)[rank]
+        for name in ("background", "brain", "normFlair", "hyperIntense", "veryIntense", "growTum", "tumSim", "tumStatCC", "gtv"):
+            gg, ww = got_g[name].data[0], want_g[name][gz0:gz1]
+            if gg.dtype == np.float32:
+                gg, ww = gg.view(np.uint32), ww.view(np.uint32)
+            if not np.array_equal(gg, ww):
+                fails.append("gtv/" + name)
+        if got_g["gtvVolume"] != float(want_g["gtv"].sum()) or want_g["gtv"].sum() == 0:
+            fails.append("gtv/volume")
         if ops.volume(B) != float(b.sum()): fails.append("volume")
         if ops.min(F) != float(f.min()) or ops.max(F) != float(f.max()): fails.append("minmax")
         check("lt", ops.cmp_scalar(F, "<", 0.3), orc.cmp_scalar(f, "<", 0.3))

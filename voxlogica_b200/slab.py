@@ -112,6 +112,7 @@ class CudaEngine:
     def ccl_sizes(self, st, labels): return self.ctx.ccl_sizes(st, labels)
     def ccl_flag_size(self, st, size): self.ctx.ccl_flag_size(st, size)
     def maxvol(self, a, conn): return self.ctx.maxvol(a, conn)
+    def border(self, like): return self.ctx.border(like)
     def percentiles(self, a, mask, correction): return self.ctx.percentiles(a, mask, correction)
     def pc_pairs(self, a, mask): return self.ctx.pc_pairs(a, mask)
     def pc_sort(self, pairs): return self.ctx.pc_sort(pairs)
@@ -457,6 +458,45 @@ class SlabOps:
         send = [d[z0:z1].contiguous() for (z0, z1) in zb]
         recv = c.exchange(send, [(nzl, y1 - y0, nx) for (y0, y1) in yb])
         return a.like(e.from_tensor(torch.cat(recv, dim=1), a))
+
+    # ------------------------------------------------------------------ border and the GTV spec
+    def border(self, like: Slab) -> Slab:
+        """voxels on the outer faces of the GLOBAL volume: x / y faces on every plane, full planes
+        only where the slab really ends the volume (a cut between two slabs is not a face)"""
+        e, c = self.e, self.c
+        if c.world == 1:
+            return like.like(e.border(like.data))
+        nzl = e.nz(like.data)
+        one = e.crop_z(like.data, 0, 1)
+        ring = e.border(one)                       # an axis of extent 1 has no faces: x / y faces only
+        full = e.not_(e.zeros_u8(one))             # a real z face
+        zfaces = like.nz_global > 1
+        bottom = full if (zfaces and like.z0 == 0) else ring
+        top = full if (zfaces and like.z1 == like.nz_global) else ring
+        if nzl == 1:
+            return like.like(bottom if (zfaces and like.z0 == 0) else top)
+        parts = [bottom]
+        if nzl > 2:
+            parts.append(e.crop_z(e.border(like.data), 1, nzl - 2))   # interior planes of a local border are rings
+        parts.append(top)
+        return like.like(e.concat_z(parts))
+
+    def gtv(self, flair: Slab, conn: int = 26) -> dict:
+        """the GTV segmentation spec of Greta.pdf p.48 (imgql.GTV_SPEC) on a slab-decomposed volume:
+        every operator of the spec is a distributed one here"""
+        r = {}
+        r["background"] = self.touch(self.cmp_scalar(flair, "<", 0.1), self.border(flair), conn)
+        r["brain"] = self.not_(r["background"])
+        r["normFlair"] = self.percentiles(flair, r["brain"])
+        r["hyperIntense"] = self.flt(5.0, self.cmp_scalar(r["normFlair"], ">", 0.95))
+        r["veryIntense"] = self.flt(2.0, self.cmp_scalar(r["normFlair"], ">", 0.86))
+        r["growTum"] = self.grow(r["hyperIntense"], r["veryIntense"], conn)
+        m, M = self.min(flair), self.max(flair)
+        r["tumSim"] = self.cross_correlation(5.0, flair, flair, r["growTum"], m, M, 100)
+        r["tumStatCC"] = self.flt(2.0, self.cmp_scalar(r["tumSim"], ">", 0.6))
+        r["gtv"] = self.grow(r["growTum"], r["tumStatCC"], conn)
+        r["gtvVolume"] = self.volume(r["gtv"])
+        return r
 
     # ------------------------------------------------------------------ rank normalisation
     def percentiles(self, a: Slab, mask: Slab, correction: float = 0.0) -> Slab:
