@@ -116,6 +116,20 @@ def main():
         vol = ops.volume(B)
         if vol != float(whole.sum()):
             bad.append("volume")
+        # the whole GTV spec, every operator slab-decomposed, against the ImgQL driver on the whole volume
+        from voxlogica_b200.imgql import run_gtv
+        from voxlogica_b200.synth import brats_like
+        flair = brats_like(seed=1234, shape=shape)
+        ref = run_gtv(ctx, ctx.upload(flair[None], spacing=sp))
+        got_g = ops.gtv(Slab(ctx.upload(flair[z0:z1], spacing=sp), z0, z1, n, sp))
+        for name in ("background", "normFlair", "growTum", "tumSim", "gtv"):
+            g_, w_ = got_g[name].data.numpy()[0], ref[name].numpy()[0][z0:z1]
+            if g_.dtype == np.float32:
+                g_, w_ = g_.view(np.uint32), w_.view(np.uint32)
+            if not np.array_equal(g_, w_):
+                bad.append("gtv/" + name)
+        if got_g["gtvVolume"] != float(ref["gtv"].numpy().sum()):
+            bad.append("gtv/volume")
         flags = [None] * world
         dist.all_gather_object(flags, bad)
         if rank == 0:
