@@ -32,6 +32,11 @@ class OracleEngine:
     def and_(self, a, b): return orc.and_(a[0], b[0])[None]
     def or_(self, a, b): return orc.or_(a[0], b[0])[None]
     def cmp_scalar(self, a, op, s): return orc.cmp_scalar(a[0], op, s)[None]
+    def cmp(self, a, op, b): return orc.cmp(a[0], op, b[0])[None]
+    def arith_scalar(self, a, op, s): return orc.arith_scalar(a[0], op, s)[None]
+    def arith(self, a, op, b): return orc.arith(a[0], op, b[0])[None]
+    def mask(self, a, m, fill=0.0): return orc.mask(a[0], m[0], fill)[None]
+    def to_f32(self, a): return orc.to_f32(a[0])[None]
     def near(self, a, conn): return orc.near(a[0], conn)[None]
     def interior(self, a, conn): return orc.interior(a[0], conn)[None]
     def through(self, a, b, conn): return orc.through(a[0], b[0], conn)[None]

@@ -224,6 +224,18 @@ def test_gtv_spec_on_slabs_equals_whole_volume(ctx, world, peer):
                     errors.append((rank, k))
             if got["gtvVolume"] != float(want["gtv"].sum()):
                 errors.append((rank, "gtvVolume"))
+            # the spec TEXT through the ImgQL driver on slabs
+            from voxlogica_b200.imgql import GTV_SPEC
+            from voxlogica_b200.slab import run_spec_on_slabs
+            it = run_spec_on_slabs(ops, GTV_SPEC, {"flair": F})
+            for k in ("normFlair", "tumSim", "gtv"):
+                g_, w_ = it.globals[k].data.numpy()[0], want[k][z0:z1]
+                if g_.dtype == np.float32:
+                    g_, w_ = g_.view(np.uint32), w_.view(np.uint32)
+                if not np.array_equal(g_, w_):
+                    errors.append((rank, "imgql/" + k))
+            if it.printed["gtvVolume"][0] != float(want["gtv"].sum()):
+                errors.append((rank, "imgql/gtvVolume"))
             done[rank] = True
         except Exception as ex:  # pragma: no cover
             errors.append((rank, repr(ex)))

@@ -113,6 +113,31 @@ def _worker(rank, world, port, q):
                 fails.append("gtv/" + name)
         if got_g["gtvVolume"] != float(want_g["gtv"].sum()) or want_g["gtv"].sum() == 0:
             fails.append("gtv/volume")
+        # ... and the spec TEXT through the ImgQL driver on slabs (existing .imgql specs run unchanged)
+        from voxlogica_b200.imgql import GTV_SPEC
+        from voxlogica_b200.slab import run_spec_on_slabs
+        it = run_spec_on_slabs(gops, GTV_SPEC, {"flair": gops.scatter_from_global(up, flair, (1.0, 1.0, 1.0))})
+        for name in ("brain", "normFlair", "growTum", "tumSim", "gtv"):
+            gg, ww = it.globals[name].data[0], want_g[name][gz0:gz1]
+            if gg.dtype == np.float32:
+                gg, ww = gg.view(np.uint32), ww.view(np.uint32)
+            if not np.array_equal(gg, ww):
+                fails.append("imgql/" + name)
+        if it.printed["gtvVolume"][0] != float(want_g["gtv"].sum()):
+            fails.append("imgql/volume")
+        extra = run_spec_on_slabs(gops, """
+            load f = "f"
+            let c = constant(0.25)
+            let hot = (f >. c) & !(f >=. 0.9) | ff
+            let n = volume(hot & tt)
+            let scaled = (f *. 2 +. 1) /. max(f)
+            """, {"f": gops.scatter_from_global(up, flair, (1.0, 1.0, 1.0))})
+        hot = ((flair > np.float32(0.25)) & ~(flair >= np.float32(0.9)))
+        if extra.globals["n"].v[0] != float(hot.sum()):
+            fails.append("imgql/pointwise")
+        sc = ((flair * np.float32(2) + np.float32(1)) / np.float32(flair.max())).astype(np.float32)
+        if not np.array_equal(extra.globals["scaled"].data[0], sc[gz0:gz1]):
+            fails.append("imgql/arith")
         if ops.volume(B) != float(b.sum()): fails.append("volume")
         if ops.min(F) != float(f.min()) or ops.max(F) != float(f.max()): fails.append("minmax")
         check("lt", ops.cmp_scalar(F, "<", 0.3), orc.cmp_scalar(f, "<", 0.3))

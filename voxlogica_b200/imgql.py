@@ -429,7 +429,9 @@ class Loaded:
 
 
 def _is_img(v):
-    return isinstance(v, (Image, Lazy))
+    # `is_image`: image-like values of other back ends of the driver (a z-slab of a distributed
+    # volume, voxlogica_b200.slab.Slab)
+    return isinstance(v, (Image, Lazy)) or getattr(v, "is_image", False)
 
 
 class Interpreter:
@@ -458,7 +460,7 @@ class Interpreter:
         calls (arguments built only from loaded images and `intensity`/channel selectors) and
         evaluates them right away; the memo then serves the later uses.  Evaluating them late
         would drain the CUDA stream in the middle of the pipeline just to read one number."""
-        loaded = {k for k, v in self.globals.items() if isinstance(v, (Image, Loaded))}
+        loaded = {k for k, v in self.globals.items() if isinstance(v, Loaded) or _is_img(v)}
         found = []
         for st in stmts:
             if st[0] == "let":

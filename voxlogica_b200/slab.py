@@ -61,6 +61,9 @@ class Slab:
     nz_global: int
     spacing: Tuple[float, float, float] = (1.0, 1.0, 1.0)
 
+    is_image = True              # the ImgQL driver treats a slab as an image value
+    nb = 1
+
     def like(self, data) -> "Slab":
         return Slab(data, self.z0, self.z1, self.nz_global, self.spacing)
 
@@ -97,6 +100,11 @@ class CudaEngine:
     def and_(self, a, b): return self.ctx.and_(a, b)
     def or_(self, a, b): return self.ctx.or_(a, b)
     def cmp_scalar(self, a, op, s): return self.ctx.cmp_scalar(a, op, s)
+    def cmp(self, a, op, b): return self.ctx.cmp(a, op, b)
+    def arith_scalar(self, a, op, s): return self.ctx.arith_scalar(a, op, s)
+    def arith(self, a, op, b): return self.ctx.arith(a, op, b)
+    def mask(self, a, m, fill=0.0): return self.ctx.mask(a, m, fill)
+    def to_f32(self, a): return self.ctx.to_f32(a)
     def near(self, a, conn): return self.ctx.near(a, conn)
     def interior(self, a, conn): return self.ctx.interior(a, conn)
     def through(self, a, b, conn): return self.ctx.through(a, b, conn)
@@ -321,6 +329,12 @@ class SlabOps:
     def and_(self, a: Slab, b: Slab) -> Slab: return a.like(self.e.and_(a.data, b.data))
     def or_(self, a: Slab, b: Slab) -> Slab: return a.like(self.e.or_(a.data, b.data))
     def cmp_scalar(self, a: Slab, op: str, s: float) -> Slab: return a.like(self.e.cmp_scalar(a.data, op, s))
+    def cmp(self, a: Slab, op: str, b: Slab) -> Slab: return a.like(self.e.cmp(a.data, op, b.data))
+    def arith_scalar(self, a: Slab, op: str, s: float) -> Slab: return a.like(self.e.arith_scalar(a.data, op, s))
+    def arith(self, a: Slab, op: str, b: Slab) -> Slab: return a.like(self.e.arith(a.data, op, b.data))
+    def mask(self, a: Slab, m: Slab, fill: float = 0.0) -> Slab: return a.like(self.e.mask(a.data, m.data, fill))
+    def ff(self, like: Slab) -> Slab: return like.like(self.e.zeros_u8(like.data))
+    def tt(self, like: Slab) -> Slab: return like.like(self.e.not_(self.e.zeros_u8(like.data)))
 
     # ------------------------------------------------------------------ reductions
     def volume(self, a: Slab) -> float:
@@ -667,3 +681,36 @@ def resolve_boundary_graph(pairs: np.ndarray, reached: np.ndarray) -> np.ndarray
     comp_reached = np.zeros(ncomp, dtype=bool)
     comp_reached[comp[is_reached]] = True
     return ids[comp_reached[comp] & ~is_reached].astype(np.int64)
+
+
+class SlabContext:
+    """The operator table of ops.Context on Slab values, for the ImgQL driver: with it an .imgql
+    spec runs unchanged on a volume that is spread over the ranks of a process group
+    (`run_spec_on_slabs`).  Scalars are per volume as in ops.Context: arrays of one element."""
+
+    def __init__(self, ops: "SlabOps"):
+        self.o = ops
+
+    def __getattr__(self, name):           # not_ and_ or_ cmp cmp_scalar arith arith_scalar mask near interior
+        return getattr(self.o, name)       # through maxvol dist* edt percentiles border tt ff: same signatures
+
+    def volume(self, a): return np.array([self.o.volume(a)])
+    def min(self, a, mask=None): return np.array([self.o.min(a)])
+    def max(self, a, mask=None): return np.array([self.o.max(a)])
+    def minmax(self, a, mask=None): return np.array([self.o.min(a)]), np.array([self.o.max(a)])
+
+    def constant(self, like, value):
+        zero = like.like(self.o.e.to_f32(self.o.e.zeros_u8(like.data)))
+        return self.o.arith_scalar(zero, "+", float(value))
+
+    def cross_correlation(self, rho, a, b, region, m, M, k):
+        return self.o.cross_correlation(rho, a, b, region, float(np.ravel(m)[0]), float(np.ravel(M)[0]), int(k))
+
+
+def run_spec_on_slabs(ops: "SlabOps", src: str, images: dict, conn: int = 26):
+    """Run an ImgQL spec whose `load` statements name Slab values of `images` (every rank calls
+    this with its own slabs).  Pointwise operators are applied one by one (no fusion across the
+    adapter); returns the interpreter (globals / saved / printed as in imgql.run_spec)."""
+    from .imgql import Interpreter
+    it = Interpreter(SlabContext(ops), loader=lambda name: images[name], conn=conn, fuse=False)
+    return it.run(src)
