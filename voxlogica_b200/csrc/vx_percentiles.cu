@@ -413,21 +413,16 @@ rs_scatter_kernel(unsigned long long* __restrict__ buf0, unsigned long long* __r
 }
 
 // ---- 3. ranks ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPcThreads)
-pc_rank_kernel(const unsigned long long* __restrict__ buf0, const unsigned long long* __restrict__ buf1,
-               const unsigned* __restrict__ count, size_t nvox, float* __restrict__ out, double correction,
-               const unsigned* __restrict__ plan) {
-    const unsigned long long* pairs = (plan[0] & 1u) ? buf1 : buf0;   // where the last pass wrote
-    const size_t vol = blockIdx.y;
-    const unsigned n = count[vol];
-    const unsigned long long* k = pairs + vol * nvox;
-    float* o = out + vol * nvox;
+// Ranks of the sorted pairs k[0, n): dst[payload] = (less_before + #keys below + correction *
+// #keys equal) / n_total.  A warp owns 32 consecutive sorted positions: the start of a run of
+// equal keys (= the rank of all its members) is found with one ballot of the run heads.  With f32
+// intensities a few per cent of the keys have a twin, so nearly every warp holds a tie somewhere:
+// a per-lane binary search made the whole warp walk ~20 dependent loads for it.
+__device__ __forceinline__ void rank_sorted_pairs(const unsigned long long* __restrict__ k, unsigned n,
+                                                  unsigned long long less_before, double n_total,
+                                                  double correction, float* __restrict__ dst) {
     auto key_at = [&](unsigned i) { return (unsigned)(k[i] >> 32); };
     const int lane = threadIdx.x & 31;
-    // a warp owns 32 consecutive sorted positions: the start of a run of equal keys (= the rank
-    // of all its members) is found with one ballot of the run heads.  With f32 intensities a
-    // few per cent of the keys have a twin, so nearly every warp holds a tie somewhere: a
-    // per-lane binary search made the whole warp walk ~20 dependent loads for it.
     for (unsigned pb = blockIdx.x * kPcThreads + (threadIdx.x & ~31u); pb < n; pb += gridDim.x * kPcThreads) {
         const unsigned p = pb + lane;
         const bool ok = p < n;
@@ -456,7 +451,7 @@ pc_rank_kernel(const unsigned long long* __restrict__ buf0, const unsigned long 
             }
             less = lo;
         }
-        double num = (double)less;
+        double num = (double)(less_before + less);
         if (correction != 0.0) {
             const unsigned above = tails & (0xffffffffu << lane);
             unsigned up;   // one past the last member of the run
@@ -472,8 +467,19 @@ pc_rank_kernel(const unsigned long long* __restrict__ buf0, const unsigned long 
             }
             num = __dadd_rn(num, __dmul_rn(correction, (double)(up - less)));
         }
-        o[(unsigned)kv] = (float)__ddiv_rn(num, (double)n);
+        dst[(unsigned)kv] = (float)__ddiv_rn(num, n_total);
     }
+}
+
+// the batch: grid (blocks, nb); the payload is the voxel index, so the ranks land in the image
+__global__ void __launch_bounds__(kPcThreads)
+pc_rank_kernel(const unsigned long long* __restrict__ buf0, const unsigned long long* __restrict__ buf1,
+               const unsigned* __restrict__ count, size_t nvox, float* __restrict__ out, double correction,
+               const unsigned* __restrict__ plan) {
+    const unsigned long long* pairs = (plan[0] & 1u) ? buf1 : buf0;   // where the last pass wrote
+    const size_t vol = blockIdx.y;
+    const unsigned n = count[vol];
+    rank_sorted_pairs(pairs + vol * nvox, n, 0ull, (double)n, correction, out + vol * nvox);
 }
 
 // ---- building blocks of a slab-decomposed percentiles (single volume, caller-owned buffers) ----
@@ -482,44 +488,7 @@ pc_rank_kernel(const unsigned long long* __restrict__ buf0, const unsigned long 
 __global__ void __launch_bounds__(kPcThreads)
 pc_rank_payload_kernel(const unsigned long long* __restrict__ k, unsigned n, unsigned long long less_before,
                        double n_total, double correction, float* __restrict__ dst) {
-    auto key_at = [&](unsigned i) { return (unsigned)(k[i] >> 32); };
-    const int lane = threadIdx.x & 31;
-    for (unsigned pb = blockIdx.x * kPcThreads + (threadIdx.x & ~31u); pb < n; pb += gridDim.x * kPcThreads) {
-        const unsigned p = pb + lane;
-        const bool ok = p < n;
-        const unsigned long long kv = ok ? k[p] : 0ull;
-        const unsigned key = (unsigned)(kv >> 32);
-        unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
-        if (lane == 0 && pb > 0) prev = key_at(pb - 1);
-        const unsigned heads = __ballot_sync(0xffffffffu, ok && (p == 0 || key != prev));
-        const unsigned next = __shfl_down_sync(0xffffffffu, key, 1);
-        const bool tail = ok && (p + 1 >= n || (lane == 31 ? key_at(p + 1) != key : next != key));
-        const unsigned tails = __ballot_sync(0xffffffffu, tail);
-        if (!ok) continue;
-        const unsigned below = heads & (0xffffffffu >> (31 - lane));
-        unsigned less;
-        if (below) {
-            less = pb + (31 - __clz(below));
-        } else {
-            unsigned lo = 0, hi = pb;
-            while (lo < hi) { unsigned mid = (lo + hi) >> 1; if (key_at(mid) < key) lo = mid + 1; else hi = mid; }
-            less = lo;
-        }
-        double num = (double)(less_before + less);
-        if (correction != 0.0) {
-            const unsigned above = tails & (0xffffffffu << lane);
-            unsigned up;
-            if (above) {
-                up = pb + (__ffs(above) - 1) + 1;
-            } else {
-                unsigned lo = pb + 32, hi = n;
-                while (lo < hi) { unsigned mid = (lo + hi) >> 1; if (key_at(mid) <= key) lo = mid + 1; else hi = mid; }
-                up = lo;
-            }
-            num = __dadd_rn(num, __dmul_rn(correction, (double)(up - less)));
-        }
-        dst[(unsigned)kv] = (float)__ddiv_rn(num, n_total);
-    }
+    rank_sorted_pairs(k, n, less_before, n_total, correction, dst);
 }
 
 // out[payload(pairs[i])] = values[i]
