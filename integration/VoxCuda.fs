@@ -4,7 +4,8 @@
 // compiled; it is kept mechanical (one DllImport per export of include/voxcuda.h, blittable types
 // only) so that a maintainer can drop it next to the SimpleITK-backed model and register the same
 // operator names.  The Python table voxlogica_b200/_abi.py::SIGNATURES is the tested twin of the
-// declarations below (tests/test_imgql_host.py checks that every symbol of the header is exported).
+// declarations below (tests/test_imgql_host.py checks that every symbol of the header is exported by
+// the library AND declared here with the same number of parameters).
 //
 // Mapping to the reference: VoxLogicA's evaluator hands each task of the operator DAG to the model
 // layer (Greta.pdf p.7, p.43); the F# sources are not in the mounted reference (SURVEY.md section 0),
@@ -13,6 +14,17 @@ namespace VoxLogicA.Cuda
 
 open System
 open System.Runtime.InteropServices
+
+
+/// one instruction of a fused pointwise program (vx_op of include/voxcuda.h)
+[<Struct; StructLayout(LayoutKind.Sequential)>]
+type VxOp =
+    val mutable opcode: int
+    val mutable dst: int
+    val mutable a: int
+    val mutable b: int
+    val mutable aux: int
+    val mutable imm: float32
 
 module Native =
     [<Literal>]
@@ -114,6 +126,114 @@ module Native =
     [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
     extern int vx_percentiles(uint64 ctx, uint64 a, uint64 mask, double correction, uint64& out)
 
+
+    // ---- the remaining exports of include/voxcuda.h (generated from the header, one per VX_API
+    // function: single-volume upload, batch slicing, the fusion hook, per-volume scalar operands,
+    // masked reductions, the slab building blocks, events / profiling).  Device or host-or-device
+    // buffers are nativeint; scalar outputs are byrefs.
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_upload(uint64 ctx, nativeint host, int dtype, int nx, int ny, int nz, float32[] spacing, uint64& out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_batch_slice(uint64 ctx, uint64 img, int first, int count, uint64& out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_crop_z(uint64 ctx, uint64 img, int z0, int nz, uint64& out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_concat_z(uint64 ctx, uint64[] parts, int n_parts, uint64& out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_transfer(uint64 dst_ctx, uint64 img, uint64& out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_device_ptr(uint64 ctx, uint64 img, nativeint& ptr)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_stream_handle(uint64 ctx, nativeint& stream)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_ipc_alloc(uint64 ctx, unativeint bytes, nativeint& ptr, nativeint handle64)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_ipc_open(uint64 ctx, nativeint handle64, nativeint& ptr)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_ipc_close(uint64 ctx, nativeint ptr)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_ipc_free(uint64 ctx, nativeint ptr)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_copy_planes_to(uint64 ctx, uint64 img, int z0, int nz, nativeint dst)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_host_alloc(unativeint bytes, nativeint& out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_host_alloc_wc(unativeint bytes, nativeint& out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_host_free(nativeint p)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_cmp_scalar_batch(uint64 ctx, uint64 a, int op, float32[] scalars, uint64& out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_arith_scalar_batch(uint64 ctx, uint64 a, int op, float32[] scalars, uint64& out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_fused_pointwise(uint64 ctx, VxOp[] program, int n_ops, uint64[] leaves, int n_leaves, float32[] batch_scalars, int n_scalars, uint64& out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_near_halo(uint64 ctx, uint64 a, int conn, nativeint lo_plane, nativeint hi_plane, uint64& out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_interior_halo(uint64 ctx, uint64 a, int conn, nativeint lo_plane, nativeint hi_plane, uint64& out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_ccl_create(uint64 ctx, uint64 b, int conn, uint64& out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_ccl_seed(uint64 ctx, uint64 state, uint64 a)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_ccl_plane(uint64 ctx, uint64 state, int z, uint64& labels_u32, uint64& reached_u8)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_ccl_flag(uint64 ctx, uint64 state, nativeint labels, uint64 n)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_ccl_select(uint64 ctx, uint64 state, uint64& out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_ccl_count(uint64 ctx, uint64 state, uint64& local_max)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_ccl_sizes(uint64 ctx, uint64 state, nativeint labels, uint64 n, nativeint sizes)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_ccl_flag_size(uint64 ctx, uint64 state, uint32 size)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_ccl_destroy(uint64 ctx, uint64 state)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_edt_sq_xy(uint64 ctx, uint64 a, uint64& out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_edt_z_from_sq(uint64 ctx, uint64 sq, double max_in, uint64& out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_region_histogram(uint64 ctx, uint64 b, uint64 region, double[] m, double[] M, int k, uint64[] h2)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_cross_correlation_h2(uint64 ctx, uint64 a, uint64[] h2, float32 rho, double[] m, double[] M, int k, uint64& out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_xcorr_bin_edges(double m, double M, int k, float32[] edges)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_min_masked(uint64 ctx, uint64 a, uint64 mask, double[] out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_max_masked(uint64 ctx, uint64 a, uint64 mask, double[] out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_sum(uint64 ctx, uint64 a, double[] out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_pc_pairs(uint64 ctx, uint64 a, uint64 mask, nativeint pairs_dev, uint64 capacity, uint64& n)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_pc_sort(uint64 ctx, nativeint pairs_dev, uint64 n, nativeint scratch_dev)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_pc_rank(uint64 ctx, nativeint sorted_dev, uint64 n, uint64 less_before, uint64 n_total, double correction, nativeint dst_dev)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_pc_scatter(uint64 ctx, nativeint pairs_dev, nativeint values_dev, uint64 n, uint64 like, uint64& out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_event_create(uint64 ctx, uint64& out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_event_record(uint64 ctx, uint64 ev)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_event_sync(uint64 ev)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_event_elapsed_ms(uint64 start, uint64 stop, float32& ms)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_event_destroy(uint64 ev)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_launch_count(uint64 ctx, uint64& out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_prof_enable(uint64 ctx, int on)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_prof_reset(uint64 ctx)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_prof_report(uint64 ctx, nativeint buf, unativeint buf_bytes)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_flush_l2(uint64 ctx)
+
 exception VoxCudaException of code: int * message: string
 
 /// Owns one reference of a device-resident image.  Finalisers may run on any thread:
@@ -157,6 +277,13 @@ type CudaModel(device: int) =
     member _.CrossCorrelation(rho: float, a: ImageHandle, b: ImageHandle, region: ImageHandle, m: float, M: float, k: int) =
         let mutable o = 0UL
         check (Native.vx_cross_correlation (ctx, a.Value, b.Value, region.Value, float32 rho, [| m |], [| M |], k, &o))
+        new ImageHandle(o)
+    /// a whole boolean / arithmetic sub-DAG in ONE launch: the evaluator may hand over a maximal
+    /// pointwise sub-term of the operator DAG instead of one task per operator (include/voxcuda.h: vx_op)
+    member _.Fused(program: VxOp[], leaves: ImageHandle[]) =
+        let mutable o = 0UL
+        let hs = leaves |> Array.map (fun l -> l.Value)
+        check (Native.vx_fused_pointwise (ctx, program, program.Length, hs, hs.Length, null, 0, &o))
         new ImageHandle(o)
     member _.Volume(a: ImageHandle) = let r = [| 0.0 |] in check (Native.vx_volume (ctx, a.Value, r)); r.[0]
     member _.Min(a: ImageHandle) = let r = [| 0.0 |] in check (Native.vx_min (ctx, a.Value, r)); r.[0]

@@ -23,6 +23,24 @@ def test_library_exports_every_declared_symbol():
     assert lib.vx_version() >= 100
 
 
+def test_fsharp_binding_declares_every_export():
+    """integration/VoxCuda.fs (the P/Invoke table a VoxLogicA maintainer adds; never compiled here) must
+    declare every VX_API function of include/voxcuda.h with the same number of parameters"""
+    with open(os.path.join(ROOT, "include", "voxcuda.h")) as f:
+        header = f.read()
+    with open(os.path.join(ROOT, "integration", "VoxCuda.fs")) as f:
+        fs = f.read()
+    protos = re.findall(r"VX_API\s+[\w\s\*]+?\b(vx_\w+)\s*\(([^;]*?)\)\s*;", header, flags=re.S)
+    decl = dict(re.findall(r"extern\s+\w+\s+(vx_\w+)\s*\(([^)]*)\)", fs))
+    assert len(protos) > 80
+    for name, args in protos:
+        assert name in decl, f"{name} has no DllImport in VoxCuda.fs"
+        n_c = 0 if args.strip() in ("", "void") else len(args.split(","))
+        n_fs = 0 if not decl[name].strip() else len(decl[name].split(","))
+        assert n_c == n_fs, f"{name}: {n_c} parameters in the header, {n_fs} in VoxCuda.fs"
+    assert set(decl) == {n for n, _ in protos}
+
+
 def test_init_without_gpu_fails_loudly():
     """No CPU fallback: without a CUDA device vx_init reports VX_E_CUDA."""
     import ctypes as C
