@@ -23,6 +23,21 @@ def test_library_exports_every_declared_symbol():
     assert lib.vx_version() >= 100
 
 
+def test_ctypes_table_matches_the_header():
+    """voxlogica_b200/_abi.py::SIGNATURES (the tested twin of the F# table) has every export of the header
+    with the same number of parameters"""
+    from voxlogica_b200 import _abi
+    with open(os.path.join(ROOT, "include", "voxcuda.h")) as f:
+        header = f.read()
+    protos = re.findall(r"VX_API\s+[\w\s\*]+?\b(vx_\w+)\s*\(([^;]*?)\)\s*;", header, flags=re.S)
+    for name, args in protos:
+        if name in ("vx_version", "vx_last_error"):        # bound by hand (non-status return types)
+            continue
+        assert name in _abi.SIGNATURES, name
+        n_c = 0 if args.strip() in ("", "void") else len(args.split(","))
+        assert n_c == len(_abi.SIGNATURES[name]), name
+
+
 def test_fsharp_binding_declares_every_export():
     """integration/VoxCuda.fs (the P/Invoke table a VoxLogicA maintainer adds; never compiled here) must
     declare every VX_API function of include/voxcuda.h with the same number of parameters"""
