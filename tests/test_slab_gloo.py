@@ -91,6 +91,11 @@ def _worker(rank, world, port, q):
         G = ops.scatter_from_global(up, g, sp)
         for corr in (0.0, 0.5):
             check(f"percentiles/{corr}", ops.percentiles(G, B, corr), orc.percentiles(g, b, correction=corr))
+        const = np.full(shape, 0.75, np.float32)           # every key equal: one rank receives everything
+        check("percentiles/constant", ops.percentiles(ops.scatter_from_global(up, const, sp), B, 0.5),
+              orc.percentiles(const, b, correction=0.5))
+        few = rng.integers(0, 3, shape).astype(np.float32)  # three distinct values: splitters coincide
+        check("percentiles/few", ops.percentiles(ops.scatter_from_global(up, few, sp), B, 0.0), orc.percentiles(few, b))
         empty = np.zeros(shape, np.uint8)
         check("percentiles/empty", ops.percentiles(G, ops.scatter_from_global(up, empty, sp)), np.zeros(shape, np.float32))
         one = empty.copy(); one[shape[0] - 1, 2, 3] = 1     # every masked voxel on the last rank
