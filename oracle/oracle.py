@@ -23,10 +23,32 @@ CMP = {"<": 0, "<=": 1, ">": 2, ">=": 3, "==": 4, "!=": 5}
 ARITH = {"+": 0, "-": 1, "*": 2, "/": 3, "r-": 4, "r/": 5, "min": 6, "max": 7}
 
 
+def _cpu_stamp() -> str:
+    """Feature flags of this host's CPU: the library is built -march=native, so a copy built on
+    another machine (the build container vs the GPU box) must be rebuilt before it is loaded."""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                return " ".join(sorted(line.split(":", 1)[1].split()))
+    except OSError:
+        pass
+    return "unknown"
+
+
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "vx_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "--no-print-directory"], stdout=subprocess.DEVNULL)
+    stamp_file = os.path.join(_HERE, "_build", "cpu_flags.txt")
+    stamp = _cpu_stamp()
+    try:
+        same_cpu = open(stamp_file).read() == stamp
+    except OSError:
+        same_cpu = False
+    if (force or not same_cpu or not os.path.exists(_SO)
+            or os.path.getmtime(_SO) < os.path.getmtime(src)
+            or os.path.getmtime(_SO) < os.path.getmtime(os.path.join(_HERE, "Makefile"))):
+        subprocess.check_call(["make", "-C", _HERE, "--no-print-directory", "-B"], stdout=subprocess.DEVNULL)
+        with open(stamp_file, "w") as f:
+            f.write(stamp)
     return _SO
 
 

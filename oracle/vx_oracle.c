@@ -413,18 +413,32 @@ static int in_ball(int dx, int dy, int dz, const float sp[3], double r2) {
     s = s + az * az;
     return s <= r2;
 }
+/* (double) of the exact integer k*S22 - n2^2.  The integer can exceed 63 bits (one bin of a
+ * region histogram holding > 4.3e8 voxels with k = 100), so it is formed in 128 bits; the
+ * int128 -> binary64 conversion is correctly rounded (libgcc __floattidf).  *positive = d2 > 0. */
+static double region_d2(const long long* h2, int k, long long* n2_out, int* positive) {
+    unsigned __int128 s22 = 0;
+    long long n2 = 0;
+    for (int i = 0; i < k; i++) {
+        n2 += h2[i];
+        s22 += (unsigned __int128)(unsigned long long)h2[i] * (unsigned long long)h2[i];
+    }
+    __int128 d2 = (__int128)((unsigned __int128)k * s22) - (__int128)n2 * (__int128)n2;
+    *n2_out = n2;
+    *positive = d2 > 0;
+    return (double)d2;
+}
+
 /* textbook = 0: exact-integer form  (k*P - n1*n2) / sqrt((k*S11 - n1^2)(k*S22 - n2^2))
  * textbook = 1: sum((h1-mean1)(h2-mean2)) / sqrt(sum((h1-mean1)^2) sum((h2-mean2)^2))
- * The two agree to rounding; the first is the arithmetic contract of the CUDA path. */
+ * The two agree to rounding; the first is the arithmetic contract of the CUDA path.
+ * Every voxel's bin is computed once up front (bin_of is a pure function of the voxel);
+ * the neighbourhood histogram is still rebuilt from the whole ball for every voxel. */
 static void xcorr_core(const float* a, const long long* h2, float rho, double m, double M, int k,
                        float* out, int nx, int ny, int nz, const float sp[3], int textbook) {
     long long n2 = 0;
-    unsigned long long s22 = 0;
-    for (int i = 0; i < k; i++) {
-        n2 += h2[i];
-        s22 += (unsigned long long)h2[i] * (unsigned long long)h2[i];
-    }
-    long long d2 = (long long)((unsigned long long)k * s22 - (unsigned long long)n2 * (unsigned long long)n2);
+    int d2pos = 0;
+    const double d2d = region_d2(h2, k, &n2, &d2pos);
     double r2 = (double)rho * (double)rho;
     int wx = 0, wy = 0, wz = 0;
     if (rho >= 0.0f) {
@@ -443,18 +457,23 @@ static void xcorr_core(const float* a, const long long* h2, float rho, double m,
                         off[3 * noff] = dx; off[3 * noff + 1] = dy; off[3 * noff + 2] = dz;
                         noff++;
                     }
+    const size_t n = nvox(nx, ny, nz);
+    int16_t* bins = (int16_t*)malloc((n ? n : 1) * sizeof(int16_t));
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n; i++) bins[i] = (int16_t)bin_of(a[i], m, M, k);
 #pragma omp parallel
     {
-        long long* h1 = (long long*)malloc(k * sizeof(long long));
+        int* h1 = (int*)malloc((size_t)k * sizeof(int));
 #pragma omp for schedule(dynamic, 1)
         for (int z = 0; z < nz; z++)
             for (int y = 0; y < ny; y++)
                 for (int x = 0; x < nx; x++) {
-                    memset(h1, 0, k * sizeof(long long));
+                    memset(h1, 0, (size_t)k * sizeof(int));
+                    const int inner = x >= wx && x + wx < nx && y >= wy && y + wy < ny && z >= wz && z + wz < nz;
                     for (int o = 0; o < noff; o++) {
                         int xx = x + off[3 * o], yy = y + off[3 * o + 1], zz = z + off[3 * o + 2];
-                        if (xx < 0 || xx >= nx || yy < 0 || yy >= ny || zz < 0 || zz >= nz) continue;
-                        int bi = bin_of(a[((size_t)zz * ny + yy) * nx + xx], m, M, k);
+                        if (!inner && (xx < 0 || xx >= nx || yy < 0 || yy >= ny || zz < 0 || zz >= nz)) continue;
+                        int bi = bins[((size_t)zz * ny + yy) * nx + xx];
                         if (bi >= 0) h1[bi]++;
                     }
                     float res = 0.0f;
@@ -462,12 +481,12 @@ static void xcorr_core(const float* a, const long long* h2, float rho, double m,
                         long long n1 = 0, s11 = 0, p = 0;
                         for (int i = 0; i < k; i++) {
                             n1 += h1[i];
-                            s11 += h1[i] * h1[i];
-                            p += h1[i] * h2[i];
+                            s11 += (long long)h1[i] * h1[i];
+                            p += (long long)h1[i] * h2[i];
                         }
                         long long num = (long long)k * p - n1 * n2;
                         long long d1 = (long long)k * s11 - n1 * n1;
-                        if (d1 > 0 && d2 > 0) res = (float)((double)num / sqrt((double)d1 * (double)d2));
+                        if (d1 > 0 && d2pos) res = (float)((double)num / sqrt((double)d1 * d2d));
                     } else {
                         double m1 = 0, m2 = 0;
                         for (int i = 0; i < k; i++) {
@@ -489,6 +508,7 @@ static void xcorr_core(const float* a, const long long* h2, float rho, double m,
                 }
         free(h1);
     }
+    free(bins);
     free(off);
 }
 
@@ -516,4 +536,14 @@ OR_API void or_cross_correlation_h2(const float* a, const unsigned long long* h2
     free(h2);
 }
 
-OR_API int or_version(void) { return 100; }
+/* Host-side check value for the device's 128-bit statistic: (double)(k*S22 - n2^2) and its sign. */
+OR_API double or_region_d2(const unsigned long long* h2u, int k, int* positive) {
+    long long* h2 = (long long*)calloc(k, sizeof(long long));
+    for (int i = 0; i < k; i++) h2[i] = (long long)h2u[i];
+    long long n2;
+    double d = region_d2(h2, k, &n2, positive);
+    free(h2);
+    return d;
+}
+
+OR_API int or_version(void) { return 101; }
