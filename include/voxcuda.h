@@ -313,6 +313,10 @@ VX_API int32_t vx_cross_correlation_h2(vx_ctx ctx, vx_img a, const uint64_t* h2,
 /* Host-only: the k+1 break points of the binning (edges[i] = smallest binary32 whose bin is >= i;
  * edges[0]: smallest value >= m, edges[k]: smallest value >= M).  Needs no device. */
 VX_API int32_t vx_xcorr_bin_edges(double m, double M, int32_t k, float* edges);
+/* Host-only: the region statistic of the correlation's denominator for one k-bin histogram h2
+ * (counters < 2^32): *d2 = (double)(k*sum(h2^2) - sum(h2)^2), the exact integer formed in 128 bits
+ * and rounded once; *positive = the integer is > 0.  Needs no device. */
+VX_API int32_t vx_xcorr_region_stat(const uint64_t* h2, int32_t k, double* d2, int32_t* positive);
 
 /* --------------------------------------------- A7/A9/A11 reductions and normalisation
  * Scalar results: `out` points to nb doubles (one per volume of the batch). */

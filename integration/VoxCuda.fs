@@ -200,6 +200,8 @@ module Native =
     [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
     extern int vx_xcorr_bin_edges(double m, double M, int k, float32[] edges)
     [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_xcorr_region_stat(uint64[] h2, int k, double& d2, int& positive)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
     extern int vx_min_masked(uint64 ctx, uint64 a, uint64 mask, double[] out)
     [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
     extern int vx_max_masked(uint64 ctx, uint64 a, uint64 mask, double[] out)

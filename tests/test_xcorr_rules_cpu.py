@@ -76,3 +76,41 @@ def test_sliding_histograms_equal_recounting(oracle, sp, rho, k):
     got = sliding_xcorr(a, b, region, rho, 0.0, 1.0, k, sp)
     want = oracle.cross_correlation(rho, a, b, region, 0.0, 1.0, k, sp)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_region_statistic_128bit():
+    """k*S22 - n2^2 exceeds 63 bits once a bin holds > 4.3e8 voxels (a 1024^3 region, the 2048^3 slab
+    path): the library's two-limb arithmetic + hand-written rounding (vx_xcorr_region_stat, the
+    function xc_stat_kernel runs on the device) against the oracle's __int128 and Python integers."""
+    import ctypes as C
+
+    import oracle as orc
+    from voxlogica_b200 import _abi
+
+    lib = _abi.load_library()
+    olib = orc.lib()
+    olib.or_region_d2.restype = C.c_double
+    rng = np.random.default_rng(11)
+    cases = []
+    for k in (1, 2, 7, 100, 254):
+        cases.append((k, np.zeros(k, np.uint64)))
+        cases.append((k, np.full(k, 0xffffffff, np.uint64)))                 # the largest legal histogram
+        h = np.zeros(k, np.uint64); h[k // 2] = 600_000_000; cases.append((k, h))   # one huge bin (ADVICE r1)
+        h = np.zeros(k, np.uint64); h[0] = 0xffffffff; h[-1] = 1; cases.append((k, h))
+        for _ in range(40):
+            mag = int(rng.integers(1, 33))
+            cases.append((k, rng.integers(0, 2 ** mag, size=k, dtype=np.uint64)))
+        for _ in range(10):   # ties of the rounding: sparse histograms with huge counters
+            h = np.zeros(k, np.uint64)
+            h[rng.integers(0, k, size=min(k, 3))] = rng.integers(2 ** 31, 2 ** 32, size=min(k, 3), dtype=np.uint64)
+            cases.append((k, h))
+    for k, h in cases:
+        hv = [int(x) for x in h]
+        exact = k * sum(x * x for x in hv) - sum(hv) ** 2
+        assert exact >= 0
+        d2 = C.c_double(); pos = C.c_int32()
+        assert lib.vx_xcorr_region_stat(h.ctypes.data_as(C.POINTER(C.c_uint64)), k, C.byref(d2), C.byref(pos)) == 0
+        opos = C.c_int()
+        od2 = olib.or_region_d2(h.ctypes.data_as(C.c_void_p), k, C.byref(opos))
+        assert d2.value == float(exact) == od2, (k, hv[:4], d2.value, float(exact), od2)   # int -> float is RN-even
+        assert bool(pos.value) == (exact > 0) == bool(opos.value)

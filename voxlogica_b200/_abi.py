@@ -118,6 +118,7 @@ SIGNATURES = {
     "vx_region_histogram": [u64, u64, u64, P(f64), P(f64), i32, P(u64)],
     "vx_cross_correlation_h2": [u64, u64, P(u64), f32, P(f64), P(f64), i32, P(u64)],
     "vx_xcorr_bin_edges": [f64, f64, i32, P(f32)],
+    "vx_xcorr_region_stat": [P(u64), i32, P(f64), P(i32)],
     "vx_volume": [u64, u64, P(f64)],
     "vx_min": [u64, u64, P(f64)],
     "vx_max": [u64, u64, P(f64)],

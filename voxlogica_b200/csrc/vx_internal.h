@@ -117,6 +117,30 @@ void drop(Image* img);  // release one reference
 int scratch_alloc(Ctx* c, int s, size_t bytes, void** out);
 int scratch_free(Ctx* c, int s, void* p);
 
+// RAII device scratch bound to (context, stream index): every block goes back to the stream's
+// free list when the holder leaves scope -- on success and on every early return alike.  Safe
+// right after the kernels were enqueued: blocks are recycled on the same stream, in order.
+struct Scratch {
+    Ctx* c;
+    int s;
+    std::vector<void*> blocks;
+    Scratch(Ctx* c_, int s_) : c(c_), s(s_) {}
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
+    ~Scratch() {
+        for (void* p : blocks) dev_free(c, s, p);
+    }
+    template <typename T>
+    int alloc(size_t bytes, T** out) {
+        void* p = nullptr;
+        int rc = dev_alloc(c, s, bytes, &p);
+        if (rc != VX_OK) return rc;
+        blocks.push_back(p);
+        *out = static_cast<T*>(p);
+        return VX_OK;
+    }
+};
+
 // ---- launch accounting / profiling ----------------------------------------
 struct LaunchScope {
     Ctx* c;

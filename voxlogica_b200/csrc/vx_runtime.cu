@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include "vx_internal.h"
+#include "vx_tma.h"
 
 namespace vx {
 
@@ -283,6 +284,45 @@ void drop(Image* im) {
 int scratch_alloc(Ctx* c, int s, size_t bytes, void** out) { return dev_alloc(c, s, bytes, out); }
 int scratch_free(Ctx* c, int s, void* p) {
     dev_free(c, s, p);
+    return VX_OK;
+}
+
+// ---- TMA tensor maps ------------------------------------------------------------
+// cuTensorMapEncodeTiled comes from the driver through the runtime's entry-point query: the
+// library links the static CUDA runtime only.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static std::mutex mu;
+    static EncodeTiledFn fn = nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+int tma_encode_u8_4d(CUtensorMap* map, const void* base, const uint64_t dims[4], const uint64_t strides[3],
+                     const uint32_t box[4]) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    VX_REQUIRE(fn != nullptr, VX_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t gd[4] = {dims[0], dims[1], dims[2], dims[3]};
+    cuuint64_t gs[3] = {strides[0], strides[1], strides[2]};
+    cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(base), gd, gs, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VX_REQUIRE(r == CUDA_SUCCESS, VX_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (dims %llu x %llu x %llu x %llu)",
+               (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+               (unsigned long long)dims[3]);
     return VX_OK;
 }
 

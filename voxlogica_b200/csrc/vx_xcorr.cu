@@ -7,16 +7,14 @@
 // is the Pearson correlation of the two k-vectors.  Written with exact integers:
 //     r = (k*P - n1*n2) / sqrt( (k*S11 - n1^2) * (k*S22 - n2^2) ),
 //     P = sum h1_i h2_i,  S11 = sum h1_i^2,  S22 = sum h2_i^2,  n = sum h
-// so the only roundings are two int64->binary64 conversions, one product, one sqrt and
+// so the only roundings are two integer->binary64 conversions, one product, one sqrt and
 // one division -- the same IEEE operations the oracle performs, hence bit-exact.
 //
-// This operator is NOT memory-bound: a radius-5 ball has 515 voxels.  The kernel
-// slides the ball along y: lanes of a warp are 32 consecutive x (coalesced u8 bin
-// loads), each thread owns a private k-bin histogram in shared memory (two u16 bins
-// per 32-bit word, word index = pair*T + tid, so a warp never bank-conflicts) and per
-// step only touches the voxels entering and leaving the ball (2 x #(dx,dz) columns,
-// 162 instead of 515 for rho = 5), maintaining S11 and n1 incrementally
-// (+-(2h+1)).  P is a k-term dot product against h2 (broadcast reads).
+// Pipeline: xc_bin_kernel turns the f32 image into u8 CODES (code = bin + 1, 0 = not
+// counted: outside [m, M), NaN, and -- through the TMA zero fill -- outside the image);
+// xc_region_hist_kernel + xc_stat_kernel build the region statistics; the sliding-ball kernel
+// (xcorr_tma_kernel, below) produces the coefficients.  This operator is NOT memory-bound: a
+// radius-5 ball has 515 voxels and the work is counter updates in shared memory.
 #include <math.h>
 #include <string.h>
 
@@ -25,16 +23,17 @@
 #include <vector>
 
 #include "vx_internal.h"
+#include "vx_tma.h"
 
 namespace vx {
 
 constexpr int kXcThreads = 128;
 constexpr int kXcWarps = kXcThreads / 32;
-constexpr int kXcMaxBins = 254;  // bins are stored as u8; value k = not counted
+constexpr int kXcMaxBins = 254;  // codes are u8: 1..k, 0 = not counted
 
 __host__ __device__ __forceinline__ int xc_bin_of(float v, double m, double M, int k) {
     double dv = (double)v;
-    if (!(dv >= m) || !(dv < M)) return k;  // the dummy bin: not counted
+    if (!(dv >= m) || !(dv < M)) return k;  // not counted
 #ifdef __CUDA_ARCH__
     double t = __ddiv_rn(__dmul_rn(__dsub_rn(dv, m), (double)k), __dsub_rn(M, m));
 #else
@@ -52,18 +51,22 @@ __host__ __device__ __forceinline__ int xc_bin_of(float v, double m, double M, i
 // of float compares per voxel -- and produce exactly xc_bin_of(v) for every v.
 constexpr int kEdgeStride = 256;   // floats per volume in the edge table (k + 1 <= 255 used)
 
-__device__ __forceinline__ unsigned bin_from_edges(float v, const float* __restrict__ e, int k, float inv_w) {
-    if (!(v >= e[0]) || !(v < e[k])) return (unsigned)k;   // outside [m, M) or NaN: the dummy bin
+// code of a value: bin + 1, or 0 when the value is not counted
+__device__ __forceinline__ unsigned code_from_edges(float v, const float* __restrict__ e, int k, float inv_w) {
+    if (!(v >= e[0]) || !(v < e[k])) return 0u;   // outside [m, M) or NaN
     int g = (int)((v - e[0]) * inv_w);
     g = g < 0 ? 0 : (g > k - 1 ? k - 1 : g);
     while (g > 0 && v < e[g]) g--;
     while (g < k - 1 && v >= e[g + 1]) g++;
-    return (unsigned)g;
+    return (unsigned)g + 1u;
 }
 
-// grid (blocks, nb): 16 voxels per thread (4 x float4 in, one uint4 out) when nvox % 16 == 0
+// The code image has its own row pitch (a multiple of 16 bytes, what a TMA tensor map needs);
+// bytes between nx and the pitch are never read as data.
+// grid (blocks, nb): 16 voxels per thread (4 x float4 in, one uint4 out) when pitch == nx and
+// nvox % 16 == 0, else one voxel per thread and step.
 __global__ void __launch_bounds__(256)
-xc_bin_kernel(const float* __restrict__ a, uint8_t* __restrict__ bins, size_t nvox,
+xc_bin_kernel(const float* __restrict__ a, uint8_t* __restrict__ codes, size_t nvox, int nx, int pitch,
               const float* __restrict__ edges, int k) {
     __shared__ float e[kEdgeStride];
     const size_t vol = blockIdx.y;
@@ -71,8 +74,8 @@ xc_bin_kernel(const float* __restrict__ a, uint8_t* __restrict__ bins, size_t nv
     __syncthreads();
     const float inv_w = (e[k] > e[0]) ? (float)k / (e[k] - e[0]) : 0.0f;
     const float* src = a + vol * nvox;
-    uint8_t* dst = bins + vol * nvox;
-    if ((nvox & 15) == 0) {
+    if (pitch == nx && (nvox & 15) == 0) {
+        uint8_t* dst = codes + vol * nvox;
         const size_t ng = nvox >> 4;
         for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < ng; g += (size_t)gridDim.x * 256) {
             const float4* p = reinterpret_cast<const float4*>(src) + g * 4;
@@ -80,22 +83,25 @@ xc_bin_kernel(const float* __restrict__ a, uint8_t* __restrict__ bins, size_t nv
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const float4 f = __ldg(p + q);
-                w[q] = bin_from_edges(f.x, e, k, inv_w) | (bin_from_edges(f.y, e, k, inv_w) << 8) |
-                       (bin_from_edges(f.z, e, k, inv_w) << 16) | (bin_from_edges(f.w, e, k, inv_w) << 24);
+                w[q] = code_from_edges(f.x, e, k, inv_w) | (code_from_edges(f.y, e, k, inv_w) << 8) |
+                       (code_from_edges(f.z, e, k, inv_w) << 16) | (code_from_edges(f.w, e, k, inv_w) << 24);
             }
             reinterpret_cast<uint4*>(dst)[g] = make_uint4(w[0], w[1], w[2], w[3]);
         }
     } else {
-        for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvox; i += (size_t)gridDim.x * 256)
-            dst[i] = (uint8_t)bin_from_edges(src[i], e, k, inv_w);
+        uint8_t* dst = codes + vol * (nvox / nx) * (size_t)pitch;
+        for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvox; i += (size_t)gridDim.x * 256) {
+            const size_t row = i / nx;
+            dst[row * pitch + (i - row * nx)] = (uint8_t)code_from_edges(src[i], e, k, inv_w);
+        }
     }
 }
 
 // histogram of b over region: grid (blocks, nb), h2 is [nb][256] (zeroed by the caller).
-// BINNED: `b` already holds u8 bins (b is the image that was binned for the sliding pass).
-template <bool BINNED>
+// CODED: `b` is the code image of the sliding pass (b is the image that was binned for it).
+template <bool CODED>
 __global__ void __launch_bounds__(256)
-xc_region_hist_kernel(const void* __restrict__ b_, const uint8_t* __restrict__ region, size_t nvox,
+xc_region_hist_kernel(const void* __restrict__ b_, const uint8_t* __restrict__ region, size_t nvox, int nx, int pitch,
                       const float* __restrict__ edges, int k, unsigned* __restrict__ h2) {
     __shared__ unsigned sh[256];
     __shared__ float e[kEdgeStride];
@@ -105,6 +111,15 @@ xc_region_hist_kernel(const void* __restrict__ b_, const uint8_t* __restrict__ r
     __syncthreads();
     const float inv_w = (e[k] > e[0]) ? (float)k / (e[k] - e[0]) : 0.0f;
     const uint8_t* reg = region + vol * nvox;
+    auto code_at = [&](size_t i) -> unsigned {
+        if (CODED) {
+            const uint8_t* cb = reinterpret_cast<const uint8_t*>(b_);
+            if (pitch == nx) return cb[vol * nvox + i];
+            const size_t row = i / nx;
+            return cb[(vol * (nvox / nx) + row) * (size_t)pitch + (i - row * nx)];
+        }
+        return code_from_edges(reinterpret_cast<const float*>(b_)[vol * nvox + i], e, k, inv_w);
+    };
     if ((nvox & 15) == 0) {
         const size_t ng = nvox >> 4;
         for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < ng; g += (size_t)gridDim.x * 256) {
@@ -117,44 +132,98 @@ xc_region_hist_kernel(const void* __restrict__ b_, const uint8_t* __restrict__ r
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     if (((rw[q] >> (8 * j)) & 0xffu) == 0) continue;
-                    const size_t i = (g << 4) + 4 * q + j;
-                    unsigned bin;
-                    if (BINNED) bin = reinterpret_cast<const uint8_t*>(b_)[vol * nvox + i];
-                    else bin = bin_from_edges(reinterpret_cast<const float*>(b_)[vol * nvox + i], e, k, inv_w);
-                    if (bin < (unsigned)k) atomicAdd(&sh[bin], 1u);
+                    const unsigned code = code_at((g << 4) + 4 * q + j);
+                    if (code) atomicAdd(&sh[code - 1], 1u);
                 }
             }
         }
     } else {
         for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvox; i += (size_t)gridDim.x * 256) {
             if (reg[i] == 0) continue;
-            unsigned bin;
-            if (BINNED) bin = reinterpret_cast<const uint8_t*>(b_)[vol * nvox + i];
-            else bin = bin_from_edges(reinterpret_cast<const float*>(b_)[vol * nvox + i], e, k, inv_w);
-            if (bin < (unsigned)k) atomicAdd(&sh[bin], 1u);
+            const unsigned code = code_at(i);
+            if (code) atomicAdd(&sh[code - 1], 1u);
         }
     }
     __syncthreads();
     if (sh[threadIdx.x]) atomicAdd(h2 + vol * 256 + threadIdx.x, sh[threadIdx.x]);
 }
 
-// per volume: vstat[2*vol] = n2, vstat[2*vol+1] = k*S22 - n2^2
-__global__ void xc_stat_kernel(const unsigned* __restrict__ h2, int k, long long* __restrict__ vstat) {
-    const int vol = blockIdx.x * blockDim.x + threadIdx.x;
-    if (vol >= (int)gridDim.x * (int)blockDim.x) return;
-    long long n2 = 0;
-    unsigned long long s22 = 0;
-    for (int i = 0; i < k; i++) {
-        unsigned long long h = h2[(size_t)vol * 256 + i];
-        n2 += (long long)h;
-        s22 += h * h;
+// Statistics of one region histogram, shared by every voxel of the volume.
+struct XcStat {
+    long long n2;     // sum of h2
+    double d2d;       // (double)(k*S22 - n2^2), the exact integer correctly rounded
+    int d2pos;        // k*S22 - n2^2 > 0
+    int clo, chi;     // codes (bin + 1) of the first and last non-empty bin; clo > chi: region empty
+    int pad;
+};
+
+// k*S22 - n2^2 needs more than 64 bits once a bin holds > 4.3e8 voxels (k = 100): it is formed
+// in 128 bits and rounded to binary64 by hand (round to nearest even), which is what the
+// oracle's (double)(__int128) conversion produces.
+__host__ __device__ inline double u128_to_double(unsigned long long hi, unsigned long long lo) {
+    if (hi == 0) return (double)lo;   // exact conversion rule of the language (RN)
+    int lz = 0;
+    for (unsigned long long t = hi; !(t >> 63); t <<= 1) lz++;
+    const int nbits = 128 - lz;            // > 64
+    const int shift = nbits - 53;          // 12 .. 75
+    unsigned long long mant, rem_hi, rem_lo;   // value = mant * 2^shift + rem
+    if (shift >= 64) {
+        mant = hi >> (shift - 64);
+        rem_hi = (shift == 64) ? 0 : (hi & ((1ull << (shift - 64)) - 1));
+        rem_lo = lo;
+    } else {
+        mant = (hi << (64 - shift)) | (lo >> shift);
+        rem_hi = 0;
+        rem_lo = lo & ((1ull << shift) - 1);
     }
-    vstat[2 * vol] = n2;
-    vstat[2 * vol + 1] = (long long)((unsigned long long)k * s22 - (unsigned long long)n2 * (unsigned long long)n2);
+    // half = 2^(shift-1)
+    const unsigned long long half_hi = shift > 64 ? (1ull << (shift - 65)) : 0;
+    const unsigned long long half_lo = shift > 64 ? 0 : (1ull << (shift - 1));
+    const bool gt = rem_hi > half_hi || (rem_hi == half_hi && rem_lo > half_lo);
+    const bool eq = rem_hi == half_hi && rem_lo == half_lo;
+    if (gt || (eq && (mant & 1ull))) mant++;
+    return ldexp((double)mant, shift);     // mant <= 2^53: exact
+}
+
+__host__ __device__ inline XcStat xc_region_stat(const unsigned* h, int k) {
+    XcStat s;
+    s.n2 = 0; s.clo = 1; s.chi = 0; s.pad = 0;
+    unsigned long long s_hi = 0, s_lo = 0;   // S22 in 128 bits
+    bool any = false;
+    for (int i = 0; i < k; i++) {
+        const unsigned long long v = h[i];
+        if (v) { if (!any) s.clo = i + 1; s.chi = i + 1; any = true; }
+        s.n2 += (long long)v;
+        const unsigned long long sq = v * v;   // < 2^64
+        const unsigned long long nlo = s_lo + sq;
+        s_hi += nlo < s_lo;
+        s_lo = nlo;
+    }
+    // k * S22 (k < 2^8, S22 < 2^72): schoolbook on 32-bit limbs
+    const unsigned long long kk = (unsigned long long)k;
+    const unsigned long long p0 = (s_lo & 0xffffffffull) * kk, p1 = (s_lo >> 32) * kk;
+    unsigned long long lo = p0 + (p1 << 32);
+    unsigned long long hi = s_hi * kk + (p1 >> 32) + (lo < p0);
+    // n2^2 (n2 < 2^40)
+    const unsigned long long n = (unsigned long long)s.n2, nl = n & 0xffffffffull, nh = n >> 32;
+    const unsigned long long ll = nl * nl, lh = nl * nh, hh = nh * nh;
+    unsigned long long q_lo = ll + (lh << 33);
+    unsigned long long q_hi = hh + (lh >> 31) + (q_lo < ll);
+    // difference (>= 0 by Cauchy-Schwarz)
+    const unsigned long long d_lo = lo - q_lo;
+    const unsigned long long d_hi = hi - q_hi - (lo < q_lo);
+    s.d2pos = (d_hi | d_lo) != 0;
+    s.d2d = u128_to_double(d_hi, d_lo);
+    return s;
+}
+
+__global__ void xc_stat_kernel(const unsigned* __restrict__ h2, int k, int nb, XcStat* __restrict__ vstat) {
+    const int vol = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vol < nb) vstat[vol] = xc_region_stat(h2 + (size_t)vol * 256, k);
 }
 
 struct XcGeo {
-    int nx, ny, nz, k, ncols, seg, nseg, nw;  // nw = histogram words per thread = ceil(k/2)
+    int nx, ny, nz, k, ncols, seg, nseg, nw, pitch;  // nw = histogram words per thread = ceil(k/2)
 };
 
 __device__ __forceinline__ void hist_add(unsigned char* hb, unsigned bin, unsigned& S2, unsigned& n1) {
@@ -172,14 +241,16 @@ __device__ __forceinline__ void hist_sub(unsigned char* hb, unsigned bin, unsign
     *p = (unsigned short)(h - 1u);
 }
 
-// grid (ceil(nx/32), ceil(nz*nseg/4), nb), block 128.  Dynamic shared memory:
+// Fallback for balls the TMA kernel cannot hold (more than 8 voxels wide in x, or a histogram
+// that does not fit beside the ring): scattered global byte loads, u16 counters, one voxel
+// column per thread.  grid (ceil(nx/32), ceil(nz*nseg/4), nb), block 128.  Dynamic shared memory:
 //   hist  [nw][128] u32   private histograms (two u16 bins per word)
 //   h2s   [2*nw]    u32   region histogram of this volume (zero padded)
 //   cols  [ncols]   u32   ball columns: dx | dz<<8 | ey<<16 (dx,dz as signed bytes)
 __global__ void __launch_bounds__(kXcThreads)
-xcorr_direct_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
+xcorr_direct_kernel(const uint8_t* __restrict__ codes, float* __restrict__ out,
              const unsigned* __restrict__ cols_g, const unsigned* __restrict__ h2,
-             const long long* __restrict__ vstat, XcGeo g) {
+             const XcStat* __restrict__ vstat, XcGeo g) {
     extern __shared__ __align__(16) unsigned smem[];
     unsigned* hist = smem;
     unsigned* h2s = smem + (size_t)g.nw * kXcThreads;
@@ -198,9 +269,10 @@ xcorr_direct_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
     const int y1 = min(g.ny, y0 + g.seg);
     if (y0 >= y1) return;
     const size_t nvox = (size_t)g.nx * g.ny * g.nz;
-    const uint8_t* bv = bins + (size_t)vol * nvox;
+    const uint8_t* bv = codes + (size_t)vol * g.pitch * g.ny * g.nz;
     float* ov = out + (size_t)vol * nvox;
-    const long long n2 = vstat[2 * vol], d2 = vstat[2 * vol + 1];
+    const XcStat vs = vstat[vol];
+    const long long n2 = vs.n2;
     const unsigned K = (unsigned)g.k;
     unsigned char* hb = reinterpret_cast<unsigned char*>(hist) + threadIdx.x * 4;
 
@@ -214,10 +286,10 @@ xcorr_direct_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
         const int ey = (int)(cw >> 16);
         if (xx < 0 || xx >= g.nx || zz < 0 || zz >= g.nz) continue;
         const int ya = max(0, y0 - ey), yb = min(g.ny - 1, y0 + ey);
-        const uint8_t* colp = bv + ((size_t)zz * g.ny) * g.nx + xx;
+        const uint8_t* colp = bv + ((size_t)zz * g.ny) * g.pitch + xx;
         for (int yy = ya; yy <= yb; yy++) {
-            unsigned b = __ldg(colp + (size_t)yy * g.nx);
-            if (b < K) hist_add(hb, b, S2, n1);
+            unsigned b = __ldg(colp + (size_t)yy * g.pitch);
+            if (b) hist_add(hb, b - 1u, S2, n1);
         }
     }
     for (int y = y0; y < y1; y++) {
@@ -231,8 +303,8 @@ xcorr_direct_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
         const long long num = (long long)K * (long long)P - (long long)n1 * n2;
         const long long d1 = (long long)K * (long long)S2 - (long long)n1 * (long long)n1;
         float res = 0.0f;
-        if (d1 > 0 && d2 > 0)
-            res = (float)__ddiv_rn((double)num, __dsqrt_rn(__dmul_rn((double)d1, (double)d2)));
+        if (d1 > 0 && vs.d2pos)
+            res = (float)__ddiv_rn((double)num, __dsqrt_rn(__dmul_rn((double)d1, vs.d2d)));
         ov[((size_t)z * g.ny + y) * g.nx + x] = res;
         if (y + 1 >= y1) break;
         // ---- slide the ball to y+1
@@ -242,15 +314,15 @@ xcorr_direct_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
             const int zz = z + (int)(signed char)((cw >> 8) & 0xffu);
             const int ey = (int)(cw >> 16);
             if (xx < 0 || xx >= g.nx || zz < 0 || zz >= g.nz) continue;
-            const uint8_t* colp = bv + ((size_t)zz * g.ny) * g.nx + xx;
+            const uint8_t* colp = bv + ((size_t)zz * g.ny) * g.pitch + xx;
             const int yin = y + 1 + ey, yout = y - ey;
             if (yin < g.ny) {
-                unsigned b = __ldg(colp + (size_t)yin * g.nx);
-                if (b < K) hist_add(hb, b, S2, n1);
+                unsigned b = __ldg(colp + (size_t)yin * g.pitch);
+                if (b) hist_add(hb, b - 1u, S2, n1);
             }
             if (yout >= 0) {
-                unsigned b = __ldg(colp + (size_t)yout * g.nx);
-                if (b < K) hist_sub(hb, b, S2, n1);
+                unsigned b = __ldg(colp + (size_t)yout * g.pitch);
+                if (b) hist_sub(hb, b - 1u, S2, n1);
             }
         }
     }
@@ -258,337 +330,298 @@ xcorr_direct_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
 
 
 // ---------------------------------------------------------------------------------------
-// Ring-buffered variant (the default).  A block = 4 warps = 4 consecutive z planes of one
-// 32-voxel x chunk, marching together along a y segment.  The u8 bins the block needs
-// (x0-8..x0+39, 4+2*wz planes) are staged in a shared-memory ring of R >= 2*wy+3 rows:
-// every step the block fetches ONE new row per plane with coalesced 32-bit loads (168
-// words for rho = 5) instead of 162 scattered global byte loads per thread, and every
-// bin read of the inner loop is a conflict-free LDS (32 lanes = 32 consecutive bytes).
+// TMA-fed sliding-ball kernel (the default).  Design, with the B200 measurements behind it
+// (scripts/ubench/smem_ops.cu, profiles/r02_ubench_smem.txt):
 //
-// The inner loop is branch-free: voxels that are not counted (outside [m,M) or outside
-// the image) carry the dummy bin k, which has its own histogram slot; its count is
-// subtracted when the coefficient is emitted (n1 = |ball| - h[k], S11 excludes h[k]^2,
-// h2[k] = 0).  Columns are sorted by their y half-extent so that the ring-row offsets of
-// the entering / leaving voxels are loop invariants of each group, and all histogram
-// traffic uses explicit shared-space addresses.
-struct XrGeo {
-    int nx, ny, nz, k, ncols, seg, nseg, nw, ball;
-    int wy, wz, R, P;      // ring rows (2*wy+3) and planes (4 + 2*wz)
+//  * the operator is bound by shared-memory operations, not by HBM: every voxel step moves
+//    2 x #columns counters (162 for rho = 5) of a PRIVATE k-bin histogram.  On B200 a
+//    conflict-free ATOMS costs as much as one LDS (0.6-0.9 SM cycles per warp instruction),
+//    so a counter move is one `atom.shared.add.u32` instead of LDS + IADD + STS, and the
+//    value it returns is exactly what the incremental sum of squares needs:
+//        S11' - S11 = sum_in (2h+1) - sum_out (2h-1) = 2 (sum_in h - sum_out h) + 2 #columns
+//    (h = counter value before the move; the identity telescopes for ANY order in which the
+//    atomics of one thread are performed, because u32 counters may wrap transiently).
+//    No per-voxel sweep over the histogram is left except the dot product with the region
+//    histogram, which only visits the bins where the region histogram is not zero.
+//  * counters are u32, hist[code][thread]: 32 lanes hit 32 banks, never a conflict.
+//    (k+1) x 4 bytes per thread bounds the block to 6 warps x 2 blocks per SM for k = 100.
+//  * a block = 6 warps = 6 consecutive z planes of one 32-voxel x chunk, marching along a y
+//    segment.  The u8 codes it needs (x0-16 .. x0+47, 6 + 2*wz planes) arrive in shared memory
+//    through TMA: a producer warp issues one `cp.async.bulk.tensor.4d` per chunk of 4 rows
+//    (box 64 x 4 x planes x 1, zero fill outside the image = the "not counted" code 0) into a
+//    ring of chunks guarded by mbarriers (full: bytes landed, ready: flat flags computed,
+//    empty: all 6 consumer warps are done with the chunk).  No __syncthreads in the loop.
+//  * flat-region shortcut per WARP: the producer marks every (row, plane) segment whose
+//    in-image bytes all equal one reference code; when all rows and planes a warp's slide
+//    touches are flat its histograms cannot change and the step is a plain store.
+constexpr int kXtWarps = 6;                  // consumer warps = z planes per block
+constexpr int kXtCons = kXtWarps * 32;       // histogram owners
+constexpr int kXtThreads = kXtCons + 32;     // + the producer warp
+constexpr int kXtCH = 4;                     // rows per TMA chunk
+constexpr int kXtRowB = 64;                  // bytes per window row: 16 + 32 + 16 voxels (the copy engine wants
+                                             // the innermost tile coordinate 16-byte aligned: measured, scripts/ubench/tma_probe.cu)
+constexpr int kXtHalo = 16;                  // voxels of x halo on either side
+constexpr int kXtMaxChunks = 12;
+constexpr int kXtLook = 2;                   // chunks in flight ahead of the flag pass
+constexpr unsigned kXtHS = kXtCons * 4;      // byte stride between two codes of one thread's histogram
+
+struct XtGeo {
+    int nx, ny, nz, k, seg, nseg, ball;
+    int ncols, nreal;          // length of the column table (with alignment filler) / real columns
+    int wy, wz, P, nchunk, pitch;
     int gstart[17], gend[17];  // columns with y half-extent e are [gstart[e], gend[e]), gstart 4-aligned
 };
-constexpr int kRingXW = 48;  // voxels per ring row: 8 + 32 + 8
-constexpr int kRingXB = 96;  // bytes per ring row (one u16 per voxel)
 
-// The ring does not hold bins but the byte offset of the bin's counter inside a thread's
-// histogram column: word pair index = bin >> 1 (stride kXcThreads*4 = 512 bytes), half =
-// bin & 1.  Converting once per loaded voxel saves five ALU instructions on each of the
-// 162 counter accesses per step.
-__device__ __forceinline__ unsigned bin_offset(unsigned bin) { return ((bin & 0xfeu) << 8) + ((bin & 1u) << 1); }
-__device__ __forceinline__ unsigned offsets2(unsigned two_bins) {  // bins in bits 0-7 and 8-15
-    return bin_offset(two_bins & 0xffu) | (bin_offset((two_bins >> 8) & 0xffu) << 16);
-}
-__device__ __forceinline__ unsigned lds_u16(unsigned addr) {
-    unsigned short v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+__device__ __forceinline__ unsigned lds_u8(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ int ring_slot(int yr, int R) {
-    int s = yr % R;
-    return s < 0 ? s + R : s;
-}
-// slot of (row with slot s) + d, for -R < d < R, without a division
-__device__ __forceinline__ int slot_add(int s, int d, int R) {
-    int t = s + d;
-    if (t >= R) t -= R;
-    if (t < 0) t += R;
-    return t;
-}
-// h[counter at offset] += delta on the calling thread's private histogram column (hbase =
-// shared address of its word 0)
-__device__ __forceinline__ void hist_bump(unsigned hbase, unsigned off, int delta) {
-    const unsigned a = hbase + off;
-    unsigned h;   // 32-bit registers: no PRMT juggling of 16-bit halves
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(h) : "r"(a));
-    h += delta;
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(h));
+__device__ __forceinline__ unsigned atoms_add(unsigned addr, unsigned delta) {
+    unsigned v;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(v) : "r"(addr), "r"(delta) : "memory");
+    return v;
 }
 
-// one voxel enters (counter offset oi), one leaves (oo): nothing to do when they are equal
-// (the common case in flat regions), otherwise two predicated read-modify-writes
-__device__ __forceinline__ void hist_move(unsigned hbase, unsigned oi, unsigned oo) {
-    const unsigned ai = hbase + oi;
-    const unsigned ao = hbase + oo;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        ".reg .u32 h, g;\n\t"
-        "setp.ne.u32 p, %0, %1;\n\t"
-        "@p ld.shared.u16 h, [%0];\n\t"
-        "@p ld.shared.u16 g, [%1];\n\t"
-        "@p add.u32 h, h, 1;\n\t"
-        "@p sub.u32 g, g, 1;\n\t"
-        "@p st.shared.u16 [%0], h;\n\t"
-        "@p st.shared.u16 [%1], g;\n\t"
-        "}" ::"r"(ai), "r"(ao) : "memory");
-}
+// grid (ceil(nx/32), ceil(nz/6)*nseg, nb), block 224.  Dynamic shared memory:
+//   ring [nchunk][P][4][64] u8 | hist [k+1][192] u32 | h2s [k+1] u32 | cols [ncols] u32 | rowmask [48] u32 |
+//   mbarriers [36] u64 | gs, ge [17] int
+// cols[c] = byte offset of column c inside a chunk relative to (plane = warp, x = lane):
+// (wz+dz)*256 + 16 + dx.
+__global__ void __launch_bounds__(kXtThreads, 2)
+xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ codes,
+                 float* __restrict__ out, const unsigned* __restrict__ cols_g, const unsigned* __restrict__ h2,
+                 const XcStat* __restrict__ vstat, const __grid_constant__ XtGeo g) {
+    extern __shared__ unsigned char xt_smem_raw[];
+    // TMA destinations must be 128-byte aligned: align the dynamic window by hand (128 spare bytes)
+    unsigned char* xt_smem = xt_smem_raw + ((128u - (smem_u32(xt_smem_raw) & 127u)) & 127u);
+    const int chunkB = g.P * kXtCH * kXtRowB;   // P is even: a multiple of 128
+    const int nbin = g.k + 1;
+    unsigned char* ring = xt_smem;
+    unsigned* hist = reinterpret_cast<unsigned*>(ring + (size_t)g.nchunk * chunkB);
+    unsigned* h2s = hist + (size_t)nbin * kXtCons;
+    unsigned* cols = h2s + ((nbin + 3) & ~3);
+    unsigned* rowmask = cols + ((g.ncols + 3) & ~3);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(rowmask + kXtMaxChunks * kXtCH);
+    int* gs = reinterpret_cast<int*>(bars + 3 * kXtMaxChunks);
+    int* ge = gs + 17;
 
-// Per-thread view of the ring rows: thread t owns ring words t and t+128 of every row
-// (a row is P planes x 12 words).  fetch() issues the global loads of one row into
-// registers, commit() stores them into the ring two steps later (software prefetch, so
-// the load latency hides behind the histogram work of the steps in between) and reports
-// whether every in-image word equals ref_word (the row is "flat").
-struct RingLoader {
-    const uint8_t* src[2];  // address of x = xg in row y = 0 of the word's plane (nullptr: plane outside)
-    int xg[2];              // x of the word's first byte (may be < 0 or >= nx)
-    int ring_off[2];        // word index inside ring row slot 0, -1: thread owns no such word
-    int nx, ny;
-    unsigned dummy, ref_word, kbin;
-    bool bytewise;
-
-    __device__ __forceinline__ void init(const uint8_t* bv, const XrGeo& g, int x0, int z0, unsigned ref) {
-        nx = g.nx; ny = g.ny;
-        kbin = (unsigned)g.k;
-        dummy = kbin * 0x01010101u;
-        ref_word = ref;
-        bytewise = (g.nx & 3) != 0;
-        const int nwords = g.P * (kRingXW / 4);
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-            const int i = threadIdx.x + s * kXcThreads;
-            src[s] = nullptr;
-            ring_off[s] = -1;
-            xg[s] = 0;
-            if (i < nwords) {
-                const int p = i / (kRingXW / 4), w = i % (kRingXW / 4);
-                const int zz = z0 - g.wz + p;
-                xg[s] = x0 - 8 + 4 * w;
-                ring_off[s] = (p * g.R) * (kRingXW / 4) + w;
-                if (zz >= 0 && zz < g.nz && xg[s] + 3 >= 0 && xg[s] < g.nx)
-                    src[s] = bv + ((size_t)zz * g.ny) * g.nx;
-            }
-        }
-    }
-    // issue the global loads of row yr into v[] (nothing here waits for them)
-    __device__ __forceinline__ void fetch(int yr, unsigned (&v)[2]) const {
-        const bool row_ok = yr >= 0 && yr < ny;
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-            v[s] = dummy;
-            if (row_ok && src[s] != nullptr) {
-                const uint8_t* a = src[s] + (size_t)yr * nx;
-                if (!bytewise) {  // nx % 4 == 0: the word is entirely inside the row
-                    v[s] = __ldg(reinterpret_cast<const unsigned*>(a + xg[s]));
-                } else {
-                    unsigned w = 0;
-#pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        const int xx = xg[s] + b;
-                        w |= ((xx >= 0 && xx < nx) ? (unsigned)__ldg(a + xx) : kbin) << (8 * b);
-                    }
-                    v[s] = w;
-                }
-            }
-        }
-    }
-    // store row yr into the ring; returns whether every in-image word of this thread equals
-    // ref_word.  A row outside the image is all dummy and never flat (it changes the
-    // histograms when it enters or leaves); columns/planes outside the image are dummy in
-    // every row and are ignored.
-    __device__ __forceinline__ bool commit(unsigned* ring32, int yr, int slot_of_yr, const unsigned (&v)[2]) const {
-        const int slot = slot_of_yr * (kRingXW / 4);
-        bool flat = yr >= 0 && yr < ny;
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-            if (ring_off[s] < 0) continue;
-            reinterpret_cast<uint2*>(ring32)[ring_off[s] + slot] = make_uint2(offsets2(v[s]), offsets2(v[s] >> 16));
-            if (src[s] != nullptr) {
-                const bool whole = xg[s] >= 0 && xg[s] + 3 < nx;
-                flat = flat && whole && v[s] == ref_word;
-            }
-        }
-        return flat;
-    }
-};
-
-// grid (ceil(nx/32), ceil(nz/4)*nseg, nb), block 128.  Dynamic shared memory:
-//   hist [nw][128] u32 | h2s [2*nw] u32 | cols [ncols] u32 | ring [P][R][48] u16
-// cols[c] = byte offset of column c inside the ring relative to (plane = warp, row slot 0,
-// x = lane): ((wz+dz)*R)*96 + 2*(8 + dx).
-__global__ void __launch_bounds__(kXcThreads, 5)
-xcorr_ring_kernel(const uint8_t* __restrict__ bins, float* __restrict__ out,
-                  const unsigned* __restrict__ cols_g, const unsigned* __restrict__ h2,
-                  const long long* __restrict__ vstat, const __grid_constant__ XrGeo g) {
-    extern __shared__ __align__(16) unsigned smem[];
-    unsigned* hist = smem;
-    unsigned* h2s = smem + (size_t)g.nw * kXcThreads;
-    unsigned* cols = h2s + ((2 * g.nw + 3) & ~3);
-    unsigned* ring32 = cols + ((g.ncols + 3) & ~3);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int vol = blockIdx.z;
-    for (int i = threadIdx.x; i < 2 * g.nw; i += kXcThreads) h2s[i] = i < g.k ? h2[(size_t)vol * 256 + i] : 0u;
-    for (int i = threadIdx.x; i < g.ncols; i += kXcThreads) cols[i] = cols_g[i];
-    // group bounds in shared memory: indexing the kernel parameter with a runtime e would
-    // go through the (slow) indexed constant path
-    __shared__ int gs[17], ge[17];
-    if (threadIdx.x < 17) { gs[threadIdx.x] = g.gstart[threadIdx.x]; ge[threadIdx.x] = g.gend[threadIdx.x]; }
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x0 = blockIdx.x * 32;
     const int zb = blockIdx.y / g.nseg, sg = blockIdx.y % g.nseg;
-    const int z0 = zb * kXcWarps;
-    const int x = x0 + lane, z = z0 + warp;
+    const int z0 = zb * kXtWarps;
     const int y0 = sg * g.seg;
-    const int y1 = min(g.ny, y0 + g.seg);
-    const bool active = x < g.nx && z < g.nz;
-    const size_t nvox = (size_t)g.nx * g.ny * g.nz;
-    const uint8_t* bv = bins + (size_t)vol * nvox;
-    float* ov = out + (size_t)vol * nvox;
-    const long long n2 = vstat[2 * vol], d2 = vstat[2 * vol + 1];
-    const unsigned K = (unsigned)g.k;
-    const unsigned hbase = (unsigned)__cvta_generic_to_shared(hist) + threadIdx.x * 4;
-    const unsigned tbase = (unsigned)__cvta_generic_to_shared(ring32) + warp * g.R * kRingXB + lane * 2;
+    const int T = min(g.ny, y0 + g.seg) - y0;        // rows of this segment (>= 1)
+    const int r0 = y0 - g.wy;                        // image row of ring row 0
+    const int total_chunks = (T + 2 * g.wy + kXtCH - 1) / kXtCH;
+    const unsigned bar0 = smem_u32(bars);
+    // barrier addresses: full[s] = bar0 + 8 s, ready[s] = + 8 (12 + s), empty[s] = + 8 (24 + s)
 
-    // Flat-region shortcut: when all 2*wy+2 ring rows a step touches hold one single value
-    // (background, saturated tissue) the histogram cannot change, so the step is skipped and
-    // the previous coefficient is stored again.  ref = bin of the first voxel of the block.
-    unsigned ref_word;
-    {
-        const int zz = min(max(z0 - g.wz, 0), g.nz - 1), xx = min(max(x0 - 8, 0), g.nx - 1);
-        const int yy = min(max(y0 - g.wy, 0), g.ny - 1);
-        ref_word = (unsigned)__ldg(bv + ((size_t)zz * g.ny + yy) * g.nx + xx) * 0x01010101u;
+    for (int i = tid; i < nbin; i += kXtThreads) h2s[i] = (i >= 1) ? h2[(size_t)vol * 256 + (i - 1)] : 0u;
+    for (int i = tid; i < g.ncols; i += kXtThreads) cols[i] = cols_g[i];
+    if (tid < 17) { gs[tid] = g.gstart[tid]; ge[tid] = g.gend[tid]; }
+    if (tid == 0) {
+        for (int s = 0; s < g.nchunk; s++) {
+            mbar_init(bar0 + 8 * s, 1);
+            mbar_init(bar0 + 8 * (kXtMaxChunks + s), 1);
+            mbar_init(bar0 + 8 * (2 * kXtMaxChunks + s), kXtWarps);
+        }
+        mbar_fence_init();
     }
-    RingLoader rl;
-    rl.init(bv, g, x0, z0, ref_word);
-    int flat_rows = 0;   // block-uniform: number of most recent consecutive flat rows
-    const int R = g.R;
-    int sy = ring_slot(y0, R);          // ring slot of row y (block-uniform, kept incrementally)
-    // preload rows y0-wy .. y0+wy, four rows of loads in flight at a time
-    {
-        int sl = ring_slot(y0 - g.wy, R);
-        for (int yr0 = y0 - g.wy; yr0 <= y0 + g.wy; yr0 += 4) {
-            unsigned v[4][2];
+    __syncthreads();
+
+    if (warp == kXtWarps) {
+        // ================================================================ producer warp
+        const unsigned ring_s = smem_u32(ring);
+        unsigned ref4;
+        {
+            const int zz = min(max(z0 - g.wz, 0), g.nz - 1), xx = min(max(x0 - kXtHalo, 0), g.nx - 1);
+            const int yy = min(max(r0, 0), g.ny - 1);
+            ref4 = (unsigned)__ldg(codes + (((size_t)vol * g.nz + zz) * g.ny + yy) * g.pitch + xx) * 0x01010101u;
+        }
+        const int nsegm = g.P * kXtCH;   // (plane, row) segments of a chunk
+        for (int j = 0; j < total_chunks + kXtLook; j++) {
+            if (j < total_chunks) {
+                const int slot = j % g.nchunk, use = j / g.nchunk;
+                if (use > 0) mbar_wait(bar0 + 8 * (2 * kXtMaxChunks + slot), (unsigned)(use - 1) & 1u);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(bar0 + 8 * slot, (unsigned)chunkB);
+                    tma_load_4d(ring_s + slot * chunkB, &tmap, bar0 + 8 * slot, x0 - kXtHalo, r0 + j * kXtCH, z0 - g.wz, vol);
+                }
+            }
+            const int jj = j - kXtLook;
+            if (jj >= 0) {
+                const int slot = jj % g.nchunk, use = jj / g.nchunk;
+                mbar_wait(bar0 + 8 * slot, (unsigned)use & 1u);
+                // flat flags of the chunk's segments: 16 words each, in-image bytes against ref4
+                unsigned m = 0;   // lanes 0..3: plane mask of ring row 4*slot + lane
+                for (int q = 0; q * 32 < nsegm; q++) {
+                    const int sgm = q * 32 + lane;
+                    bool flat = true;
+                    if (sgm < nsegm) {
+                        const int p = sgm >> 2, rr = sgm & 3;
+                        const int zz = z0 - g.wz + p;
+                        if (zz >= 0 && zz < g.nz) {
+                            const unsigned* w = reinterpret_cast<const unsigned*>(ring + (size_t)slot * chunkB + (p * kXtCH + rr) * kXtRowB);
+                            unsigned diff = 0;
 #pragma unroll
-            for (int q = 0; q < 4; q++) rl.fetch(yr0 + q <= y0 + g.wy ? yr0 + q : -1, v[q]);
+                            for (int i = 0; i < kXtRowB / 4; i++) {
+                                const int xa = x0 - kXtHalo + 4 * i;
+                                unsigned bm = 0;
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                if (yr0 + q > y0 + g.wy) break;   // block-uniform
-                const bool f = rl.commit(ring32, yr0 + q, sl, v[q]);
-                sl = slot_add(sl, 1, R);
-                flat_rows = __syncthreads_and(f) ? flat_rows + 1 : 0;
+                                for (int b = 0; b < 4; b++)
+                                    if (xa + b >= 0 && xa + b < g.nx) bm |= 0xffu << (8 * b);
+                                diff |= (w[i] ^ ref4) & bm;
+                            }
+                            flat = diff == 0;
+                        }
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, flat);
+                    if (lane < 4)
+                        for (int pp = 0; pp < 8; pp++) m |= ((bal >> (4 * pp + lane)) & 1u) << (8 * q + pp);
+                }
+                if (lane < 4) rowmask[slot * kXtCH + lane] = m;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar0 + 8 * (kXtMaxChunks + slot));
             }
         }
+        return;
     }
-    // software prefetch: rows y+1+wy and y+2+wy are already in registers when step y starts
-    unsigned pfa[2], pfb[2];
-    rl.fetch(y0 + 1 + g.wy, pfa);
-    rl.fetch(y0 + 2 + g.wy, pfb);
-    for (int w = 0; w < g.nw; w++) hist[w * kXcThreads + threadIdx.x] = 0u;
-    __syncthreads();
-    // words of h2 that hold a non-zero count (block-uniform; wlo > whi when the region is empty)
-    int wlo = g.nw, whi = -1;
-    for (int w = 0; w < g.nw; w++)
-        if (h2s[2 * w] | h2s[2 * w + 1]) { wlo = min(wlo, w); whi = w; }
-    const bool p32 = (unsigned long long)g.ball * (unsigned long long)n2 < 0xffffffffull;
 
-    if (active) {
-        if (flat_rows >= 2 * g.wy + 1) {
-            // the whole neighbourhood of the first voxel is one value: every column adds its
-            // 2e+1 voxels to one bin (ref, or the dummy bin for columns outside the image)
+    // ==================================================================== consumer warps
+    const int x = x0 + lane, z = z0 + warp;
+    const bool wactive = z < g.nz;            // warp-uniform
+    const bool active = wactive && x < g.nx;
+    const size_t nvox = (size_t)g.nx * g.ny * g.nz;
+    float* ov = out + (size_t)vol * nvox;
+    const XcStat vs = vstat[vol];
+    const long long n2 = vs.n2;
+    const long long K = (long long)g.k;
+    const unsigned hbase = smem_u32(hist) + tid * 4;
+    const unsigned tb = smem_u32(ring) + warp * (kXtCH * kXtRowB) + lane;
+    const unsigned pm = (1u << (2 * g.wz + 1)) - 1u;
+    const bool p32 = (unsigned long long)g.ball * (unsigned long long)n2 < 0xffffffffull;
+    const int wy2 = 2 * g.wy;
+
+    for (int c = 0; c < nbin; c++) hist[c * kXtCons + tid] = 0u;   // own column only
+
+    int waited = 0;   // chunks whose `ready` barrier this warp has passed
+    auto ensure = [&](int rel) {   // ring row `rel` (relative to r0) is in shared memory, flags included
+        const int c = rel >> 2;
+        while (waited <= c) {
+            mbar_wait(bar0 + 8 * (kXtMaxChunks + waited % g.nchunk), (unsigned)(waited / g.nchunk) & 1u);
+            waited++;
+        }
+    };
+    auto rowoff = [&](int rel) {   // byte offset of ring row `rel` (general form, used outside the loop)
+        return (unsigned)(((rel >> 2) % g.nchunk) * chunkB + (rel & 3) * kXtRowB);
+    };
+    int run = 0;      // consecutive flat rows (for this warp's planes) ending at the last examined row
+    auto examine = [&](int rel) {
+        const unsigned m = rowmask[((rel >> 2) % g.nchunk) * kXtCH + (rel & 3)];
+        run = (((m >> warp) & pm) == pm) ? run + 1 : 0;
+    };
+
+    ensure(wy2);
+    for (int rel = 0; rel <= wy2; rel++) examine(rel);
+    unsigned S = 0;   // sum over ALL codes (the dummy code 0 included) of h^2
+    if (wactive) {
+        if (run >= wy2 + 1) {
+            // the whole neighbourhood of the first voxel is one value per column: every column
+            // adds its 2e+1 voxels to one counter (the reference code, or code 0 outside the image)
+            const unsigned prow = tb + rowoff(g.wy);
             for (int e = 0; e <= g.wy; e++)
                 for (int c = gs[e]; c < ge[e]; c++)
-                    hist_bump(hbase, lds_u16(tbase + sy * kRingXB + cols[c]), 2 * e + 1);
-        } else {  // full ball around (x, y0, z)
+                    atoms_add(hbase + lds_u8(prow + cols[c]) * kXtHS, (unsigned)(2 * e + 1));
+        } else {
             for (int e = 0; e <= g.wy; e++)
                 for (int c = gs[e]; c < ge[e]; c++) {
                     const unsigned co = cols[c];
                     for (int dy = -e; dy <= e; dy++)
-                        hist_bump(hbase, lds_u16(tbase + slot_add(sy, dy, R) * kRingXB + co), 1);
+                        atoms_add(hbase + lds_u8(tb + rowoff(g.wy + dy) + co) * kXtHS, 1u);
                 }
+        }
+        for (int c = 0; c < nbin; c++) {
+            const unsigned h = hist[c * kXtCons + tid];
+            S += h * h;
         }
     }
+
     float res = 0.0f;
-    bool changed = true;   // block-uniform: did the last slide touch the histograms?
-    for (int y = y0; y < y1; y++) {
-        if (active && changed) {
-            // S11 over all bins; the dot product with h2 only over the words where h2 is not
-            // zero (a region's intensities occupy a few of the k bins), in 32 bits when
-            // ball * n2 cannot overflow them
+    bool dirty = true;    // warp-uniform: histograms changed since the last coefficient
+    int slot_t = 0;       // ring slot of the chunk that holds row t
+    for (int t = 0; t < T; t++) {
+        if (wactive && dirty) {
+            const unsigned hd = hist[tid];   // not-counted voxels of the ball (code 0)
             unsigned long long P = 0;
-            unsigned S2 = 0;
-            for (int w = 0; w < wlo; w++) {
-                const unsigned v = hist[w * kXcThreads + threadIdx.x];
-                const unsigned lo = v & 0xffffu, hi = v >> 16;
-                S2 += lo * lo + hi * hi;
-            }
             if (p32) {
                 unsigned P32 = 0;
-                for (int w = wlo; w <= whi; w++) {
-                    const unsigned v = hist[w * kXcThreads + threadIdx.x];
-                    const uint2 hh = *reinterpret_cast<const uint2*>(h2s + 2 * w);
-                    const unsigned lo = v & 0xffffu, hi = v >> 16;
-                    P32 += lo * hh.x + hi * hh.y;
-                    S2 += lo * lo + hi * hi;
-                }
+                for (int c = vs.clo; c <= vs.chi; c++) P32 += hist[c * kXtCons + tid] * h2s[c];
                 P = P32;
             } else {
-                for (int w = wlo; w <= whi; w++) {
-                    const unsigned v = hist[w * kXcThreads + threadIdx.x];
-                    const uint2 hh = *reinterpret_cast<const uint2*>(h2s + 2 * w);
-                    const unsigned lo = v & 0xffffu, hi = v >> 16;
-                    P += (unsigned long long)lo * hh.x;
-                    P += (unsigned long long)hi * hh.y;
-                    S2 += lo * lo + hi * hi;
-                }
+                for (int c = vs.clo; c <= vs.chi; c++) P += (unsigned long long)hist[c * kXtCons + tid] * h2s[c];
             }
-            for (int w = whi + 1; w < g.nw; w++) {
-                const unsigned v = hist[w * kXcThreads + threadIdx.x];
-                const unsigned lo = v & 0xffffu, hi = v >> 16;
-                S2 += lo * lo + hi * hi;
-            }
-            // remove the dummy bin K (not-counted voxels) from the statistics
-            const unsigned vd = hist[(K >> 1) * kXcThreads + threadIdx.x];
-            const unsigned hd = (K & 1u) ? (vd >> 16) : (vd & 0xffffu);
-            S2 -= hd * hd;
             const long long n1 = (long long)g.ball - (long long)hd;
-            const long long num = (long long)K * (long long)P - n1 * n2;
-            const long long d1 = (long long)K * (long long)S2 - n1 * n1;
+            const long long s11 = (long long)(S - hd * hd);
+            const long long num = K * (long long)P - n1 * n2;
+            const long long d1 = K * s11 - n1 * n1;
             res = 0.0f;
-            if (d1 > 0 && d2 > 0)
-                res = (float)__ddiv_rn((double)num, __dsqrt_rn(__dmul_rn((double)d1, (double)d2)));
+            if (d1 > 0 && vs.d2pos)
+                res = (float)__ddiv_rn((double)num, __dsqrt_rn(__dmul_rn((double)d1, vs.d2d)));
+            dirty = false;
         }
-        if (active) ov[((size_t)z * g.ny + y) * g.nx + x] = res;
-        if (y + 1 >= y1) break;
-        // the slot of row y+1+wy last held row y+1+wy-R < y-1-wy: nobody reads it any more
-        const bool f = rl.commit(ring32, y + 1 + g.wy, slot_add(sy, 1 + g.wy, R), pfa);
-        pfa[0] = pfb[0]; pfa[1] = pfb[1];
-        rl.fetch(y + 3 + g.wy, pfb);
-        flat_rows = __syncthreads_and(f) ? flat_rows + 1 : 0;
-        changed = flat_rows < 2 * g.wy + 2;   // rows y-wy .. y+1+wy
-        if (active && changed) {
+        if (active) ov[((size_t)z * g.ny + (y0 + t)) * g.nx + x] = res;
+        if (t + 1 >= T) break;
+        // ---- slide the ball from row y0+t to y0+t+1: ring rows t .. t+2wy+1
+        ensure(t + wy2 + 1);
+        examine(t + wy2 + 1);
+        if (wactive && run < wy2 + 2) {
+            unsigned A = 0;            // sum of counters before +1 minus sum of counters before -1
+            unsigned pi0 = 0, pi1 = 0, pi2 = 0, pi3 = 0, po0 = 0, po1 = 0, po2 = 0, po3 = 0;   // previous batch
+            const int tq = t & 3;
             for (int e = 0; e <= g.wy; e++) {
-                const unsigned pin = tbase + slot_add(sy, 1 + e, R) * kRingXB;
-                const unsigned pout = tbase + slot_add(sy, -e, R) * kRingXB;
                 int c = gs[e];
                 const int cend = ge[e];
+                if (c >= cend) continue;
+                int sin = slot_t + ((tq + g.wy + 1 + e) >> 2), sout = slot_t + ((tq + g.wy - e) >> 2);
+                if (sin >= g.nchunk) sin -= g.nchunk;
+                if (sout >= g.nchunk) sout -= g.nchunk;
+                const unsigned pin = tb + sin * chunkB + ((tq + g.wy + 1 + e) & 3) * kXtRowB;
+                const unsigned pout = tb + sout * chunkB + ((tq + g.wy - e) & 3) * kXtRowB;
 #pragma unroll 1
                 for (; c + 4 <= cend; c += 4) {
                     const uint4 co = *reinterpret_cast<const uint4*>(cols + c);   // gstart is 4-aligned
-                    const unsigned i0 = lds_u16(pin + co.x), o0 = lds_u16(pout + co.x);
-                    const unsigned i1 = lds_u16(pin + co.y), o1 = lds_u16(pout + co.y);
-                    const unsigned i2 = lds_u16(pin + co.z), o2 = lds_u16(pout + co.z);
-                    const unsigned i3 = lds_u16(pin + co.w), o3 = lds_u16(pout + co.w);
-                    hist_move(hbase, i0, o0);
-                    hist_move(hbase, i1, o1);
-                    hist_move(hbase, i2, o2);
-                    hist_move(hbase, i3, o3);
+                    unsigned i0 = lds_u8(pin + co.x), o0 = lds_u8(pout + co.x);
+                    unsigned i1 = lds_u8(pin + co.y), o1 = lds_u8(pout + co.y);
+                    unsigned i2 = lds_u8(pin + co.z), o2 = lds_u8(pout + co.z);
+                    unsigned i3 = lds_u8(pin + co.w), o3 = lds_u8(pout + co.w);
+                    A += (pi0 - po0) + (pi1 - po1) + (pi2 - po2) + (pi3 - po3);   // returns of the previous batch
+                    i0 = hbase + i0 * kXtHS; o0 = hbase + o0 * kXtHS;
+                    i1 = hbase + i1 * kXtHS; o1 = hbase + o1 * kXtHS;
+                    i2 = hbase + i2 * kXtHS; o2 = hbase + o2 * kXtHS;
+                    i3 = hbase + i3 * kXtHS; o3 = hbase + o3 * kXtHS;
+                    pi0 = atoms_add(i0, 1u); po0 = atoms_add(o0, 0xffffffffu);
+                    pi1 = atoms_add(i1, 1u); po1 = atoms_add(o1, 0xffffffffu);
+                    pi2 = atoms_add(i2, 1u); po2 = atoms_add(o2, 0xffffffffu);
+                    pi3 = atoms_add(i3, 1u); po3 = atoms_add(o3, 0xffffffffu);
                 }
                 for (; c < cend; c++) {
                     const unsigned co = cols[c];
-                    const unsigned i0 = lds_u16(pin + co), o0 = lds_u16(pout + co);
-                    hist_move(hbase, i0, o0);
+                    const unsigned ai = hbase + lds_u8(pin + co) * kXtHS, ao = hbase + lds_u8(pout + co) * kXtHS;
+                    A += atoms_add(ai, 1u) - atoms_add(ao, 0xffffffffu);
                 }
             }
+            A += (pi0 - po0) + (pi1 - po1) + (pi2 - po2) + (pi3 - po3);
+            S += 2u * A + 2u * (unsigned)g.nreal;
+            dirty = true;
         }
-        sy = slot_add(sy, 1, R);
+        // ring row t is dead after this slide; its chunk goes back to the producer with its last row
+        if ((t & 3) == 3) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 8 * (2 * kXtMaxChunks + slot_t));
+            slot_t = slot_t + 1 == g.nchunk ? 0 : slot_t + 1;
+        }
     }
 }
 
@@ -686,7 +719,7 @@ static void compute_edges(double m, double M, int k, float* e) {
     }
 }
 
-static int upload_edges(OpGuard& og, int nb, const double* m, const double* M, int k, float** d_edges) {
+static int upload_edges(OpGuard& og, Scratch& sc, int nb, const double* m, const double* M, int k, float** d_edges) {
     std::vector<float> e((size_t)nb * kEdgeStride, INFINITY);
     for (int v = 0; v < nb; v++) {
         if (v > 0 && m[v] == m[v - 1] && M[v] == M[v - 1])
@@ -694,7 +727,7 @@ static int upload_edges(OpGuard& og, int nb, const double* m, const double* M, i
         else
             compute_edges(m[v], M[v], k, &e[(size_t)v * kEdgeStride]);
     }
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(float) * e.size(), (void**)d_edges));
+    VX_TRY(sc.alloc(sizeof(float) * e.size(), d_edges));
     // pageable source: staged by the runtime before the call returns
     VX_CUDA(cudaMemcpyAsync(*d_edges, e.data(), sizeof(float) * e.size(), cudaMemcpyHostToDevice, og.st));
     return VX_OK;
@@ -706,141 +739,151 @@ static dim3 stream_grid(size_t nvox, int nb) {
     return dim3(per_vol < cap ? per_vol : (cap < 1 ? 1 : cap), nb);
 }
 
-// u8 bins of A (dummy bin k for values that are not counted)
-static int xcorr_bins(OpGuard& og, Image* A, const float* d_edges, int32_t k, uint8_t** d_bins) {
-    VX_TRY(scratch_alloc(og.c, og.s, A->count(), (void**)d_bins));
+static int code_pitch(int nx) { return (nx + 15) & ~15; }   // TMA: row stride a multiple of 16 bytes
+
+// u8 codes of A (0 for values that are not counted), rows padded to code_pitch(nx)
+static int xcorr_codes(OpGuard& og, Scratch& sc, Image* A, const float* d_edges, int32_t k, uint8_t** d_codes) {
+    const int pitch = code_pitch(A->nx);
+    VX_TRY(sc.alloc((size_t)pitch * A->ny * A->nz * A->nb + 64, d_codes));
     {
         VX_LAUNCH(og.c, og.s, "xc_bin_kernel");
-        xc_bin_kernel<<<stream_grid(A->nvox(), A->nb), 256, 0, og.st>>>((const float*)A->d, *d_bins, A->nvox(), d_edges, k);
+        xc_bin_kernel<<<stream_grid(A->nvox(), A->nb), 256, 0, og.st>>>((const float*)A->d, *d_codes, A->nvox(), A->nx,
+                                                                        pitch, d_edges, k);
     }
     return check_launch("xc_bin_kernel");
 }
 
-// h2 of `src` (f32 values, or u8 bins when binned) over region R into d_h2 ([nb][256] u32)
-static int region_hist(OpGuard& og, const void* src, bool binned, Image* R, const float* d_edges, int32_t k,
+// h2 of `src` (f32 values, or the u8 code image when coded) over region R into d_h2 ([nb][256] u32)
+static int region_hist(OpGuard& og, const void* src, bool coded, Image* R, const float* d_edges, int32_t k,
                        unsigned* d_h2) {
     const int nb = R->nb;
     const size_t nvox = R->nvox();
+    const int pitch = code_pitch(R->nx);
     VX_CUDA(cudaMemsetAsync(d_h2, 0, sizeof(unsigned) * 256 * nb, og.st));
     {
         VX_LAUNCH(og.c, og.s, "xc_region_hist_kernel");
-        if (binned)
-            xc_region_hist_kernel<true><<<stream_grid(nvox, nb), 256, 0, og.st>>>(src, (const uint8_t*)R->d, nvox, d_edges, k, d_h2);
+        if (coded)
+            xc_region_hist_kernel<true><<<stream_grid(nvox, nb), 256, 0, og.st>>>(src, (const uint8_t*)R->d, nvox, R->nx, pitch, d_edges, k, d_h2);
         else
-            xc_region_hist_kernel<false><<<stream_grid(nvox, nb), 256, 0, og.st>>>(src, (const uint8_t*)R->d, nvox, d_edges, k, d_h2);
+            xc_region_hist_kernel<false><<<stream_grid(nvox, nb), 256, 0, og.st>>>(src, (const uint8_t*)R->d, nvox, R->nx, pitch, d_edges, k, d_h2);
     }
     return check_launch("xc_region_hist_kernel");
 }
 
 // Shared back end: statistics of the region histogram d_h2 ([nb][256] u32 on the device, final)
-// and the sliding-ball kernel over the bins.  Frees d_bins, d_edges and d_h2.
-static int xcorr_run(OpGuard& og, Image* A, uint8_t* d_bins, float* d_edges, unsigned* d_h2, float rho, int32_t k,
-                     vx_img* out) {
+// and the sliding-ball kernel over the codes.
+static int xcorr_run(OpGuard& og, Scratch& sc, Image* A, const uint8_t* d_codes, const unsigned* d_h2, float rho,
+                     int32_t k, vx_img* out) {
     std::vector<unsigned> cols;
     long long ball = 0;
     VX_REQUIRE(build_columns(A->sp, rho, &cols, &ball) && ball <= 65535 && cols.size() <= 8192,
                VX_E_UNSUPPORTED, "radius %g is too large for the sliding-histogram kernel", (double)rho);
     const int nb = A->nb;
+    const int pitch = code_pitch(A->nx);
     unsigned* d_cols = nullptr;
-    long long* d_vstat = nullptr;
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(long long) * 2 * nb, (void**)&d_vstat));
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (cols.size() + 128), (void**)&d_cols));
+    XcStat* d_vstat = nullptr;
+    VX_TRY(sc.alloc(sizeof(XcStat) * nb, &d_vstat));
+    VX_TRY(sc.alloc(sizeof(unsigned) * (cols.size() + 128), &d_cols));
     {
         VX_LAUNCH(og.c, og.s, "xc_stat_kernel");
-        xc_stat_kernel<<<nb, 1, 0, og.st>>>(d_h2, k, d_vstat);
+        xc_stat_kernel<<<(nb + 63) / 64, 64, 0, og.st>>>(d_h2, k, nb, d_vstat);
     }
     VX_TRY(check_launch("xc_stat_kernel"));
-    Image* O = nullptr;
-    VX_TRY(new_image(og.c, VX_F32, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
     // geometry of the ball
     int wx = 0, wy = 0, wz = 0;
     for (unsigned cw : cols) {
         int dx = (int)(signed char)(cw & 0xffu), dz = (int)(signed char)((cw >> 8) & 0xffu), ey = (int)(cw >> 16);
         wx = std::max(wx, std::abs(dx)); wz = std::max(wz, std::abs(dz)); wy = std::max(wy, ey);
     }
-    const int nw = (k + 2) / 2;   // k bins + the dummy bin k
-    // y segments: long enough to amortise the initial full-ball build, short enough to
-    // give the batch at least a few waves of CTAs
-    // (the build costs |ball| bumps, a step 2 * #columns moves: ~5% at 64 rows for rho = 5)
-    int nseg = (A->ny + 63) / 64;
-    {
-        const long long ctas_per_seg = (long long)((A->nx + 31) / 32) * ((A->nz + kXcWarps - 1) / kXcWarps) * A->nb;
-        const long long want = 4LL * kNumSMs * 5;   // four waves at five resident CTAs per SM
-        while (nseg > 1 && ctas_per_seg * (nseg - 1) >= want) nseg--;
-    }
-    const int seg = (A->ny + nseg - 1) / nseg;
-    nseg = (A->ny + seg - 1) / seg;
-    const int ringR = 2 * wy + 3;   // rows y-wy .. y+1+wy of a step plus the one being written
-    const int P = kXcWarps + 2 * wz;
-    int rc = VX_OK;
-    // ring offsets, sorted by y half-extent, every group padded to start 4-aligned
-    std::vector<unsigned> ring_cols;
-    XrGeo g;
-    bool ring_ok = wx <= 8 && wy <= 16 && P * (kRingXW / 4) <= 2 * kXcThreads;
-    if (ring_ok) {
+    // ---- the TMA kernel: window 16 + 32 + 16 voxels wide, 6 + 2 wz planes, ring of 4-row chunks
+    const int P = kXtWarps + 2 * wz;
+    const int nchunk = 4 + wy / 2;   // live chunks (2 + wy/2) + kXtLook in flight
+    std::vector<unsigned> tcols;
+    XtGeo g;
+    memset(&g, 0, sizeof(g));
+    bool tma_ok = !cols.empty() && wx <= kXtHalo && wy <= 16 && P <= 32 && nchunk <= kXtMaxChunks;
+    if (tma_ok) {
         for (int e = 0; e <= wy; e++) {
-            while (ring_cols.size() & 3) ring_cols.push_back(0);   // alignment filler, never read
-            g.gstart[e] = (int)ring_cols.size();
+            while (tcols.size() & 3) tcols.push_back(0);   // alignment filler, never read
+            g.gstart[e] = (int)tcols.size();
             int cnt = 0;
             for (unsigned cw : cols) {
                 int dx = (int)(signed char)(cw & 0xffu), dz = (int)(signed char)((cw >> 8) & 0xffu), ey = (int)(cw >> 16);
                 if (ey != e) continue;
-                ring_cols.push_back((unsigned)(((wz + dz) * ringR) * kRingXB + 2 * (8 + dx)));
+                tcols.push_back((unsigned)((wz + dz) * (kXtCH * kXtRowB) + kXtHalo + dx));
                 cnt++;
             }
             g.gend[e] = g.gstart[e] + cnt;
         }
     }
-    const size_t smem_ring = sizeof(unsigned) * ((size_t)nw * kXcThreads + ((2 * nw + 3) & ~3) + ((ring_cols.size() + 3) & ~(size_t)3)) +
-                             (size_t)P * ringR * kRingXB;
-    if (ring_ok && smem_ring <= 160 * 1024) {
+    const int nbin = k + 1;
+    const size_t chunkB = (size_t)P * kXtCH * kXtRowB;
+    const size_t smem_tma = 128 + nchunk * chunkB +
+                            sizeof(unsigned) * ((size_t)nbin * kXtCons + ((nbin + 3) & ~3) + ((tcols.size() + 3) & ~(size_t)3) +
+                                                kXtMaxChunks * kXtCH) +
+                            sizeof(unsigned long long) * 3 * kXtMaxChunks + sizeof(int) * 34;
+    tma_ok = tma_ok && smem_tma <= 227 * 1024;
+    Image* O = nullptr;
+    VX_TRY(new_image(og.c, VX_F32, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
+    int rc = VX_OK;
+    if (tma_ok) {
+        // y segments: whole columns when the batch already fills the machine many times over (the
+        // initial full-ball build costs about three steps), shorter ones for small batches
+        const long long ctas_per_seg = (long long)((A->nx + 31) / 32) * ((A->nz + kXtWarps - 1) / kXtWarps) * nb;
+        const long long want = 20LL * kNumSMs * 2;
+        int nseg = (int)std::min<long long>((want + ctas_per_seg - 1) / ctas_per_seg, std::max(1, A->ny / 40));
+        nseg = std::max(1, nseg);
+        const int seg = (A->ny + nseg - 1) / nseg;
+        nseg = (A->ny + seg - 1) / seg;
         g.nx = A->nx; g.ny = A->ny; g.nz = A->nz; g.k = k;
-        g.ncols = (int)ring_cols.size();
-        g.seg = seg; g.nseg = nseg; g.nw = nw; g.wy = wy; g.wz = wz; g.R = ringR; g.P = P;
-        g.ball = (int)ball;
-        VX_CUDA(cudaMemcpyAsync(d_cols, ring_cols.data(), sizeof(unsigned) * ring_cols.size(), cudaMemcpyHostToDevice, og.st));
-        // 5 resident CTAs per SM (96 registers, ~44 KB): measured on B200 against 4 and 3 (extra
-        // dynamic shared memory), alone and with other streams' kernels co-resident: 7.13 / 7.69 /
-        // 8.98 ms per 16-volume launch, and the whole GTV step got slower with fewer CTAs as well
-        const size_t smem_launch = smem_ring;
-        if (smem_launch > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(xcorr_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_launch);
-            if (e != cudaSuccess) rc = fail(VX_E_CUDA, "smem attribute: %s", cudaGetErrorString(e));
+        g.seg = seg; g.nseg = nseg; g.ball = (int)ball;
+        g.ncols = (int)tcols.size(); g.nreal = (int)cols.size();
+        g.wy = wy; g.wz = wz; g.P = P; g.nchunk = nchunk; g.pitch = pitch;
+        CUtensorMap tmap;
+        const uint64_t dims[4] = {(uint64_t)A->nx, (uint64_t)A->ny, (uint64_t)A->nz, (uint64_t)nb};
+        const uint64_t strides[3] = {(uint64_t)pitch, (uint64_t)pitch * A->ny, (uint64_t)pitch * A->ny * A->nz};
+        const uint32_t box[4] = {(uint32_t)kXtRowB, (uint32_t)kXtCH, (uint32_t)P, 1u};
+        rc = tma_encode_u8_4d(&tmap, d_codes, dims, strides, box);
+        if (rc == VX_OK) {
+            cudaError_t e = cudaMemcpyAsync(d_cols, tcols.data(), sizeof(unsigned) * tcols.size(), cudaMemcpyHostToDevice, og.st);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(xcorr_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
+            if (e != cudaSuccess) rc = fail(VX_E_CUDA, "crossCorrelation set-up: %s", cudaGetErrorString(e));
         }
         if (rc == VX_OK) {
-            dim3 grid((A->nx + 31) / 32, ((A->nz + kXcWarps - 1) / kXcWarps) * nseg, nb);
+            dim3 grid((A->nx + 31) / 32, ((A->nz + kXtWarps - 1) / kXtWarps) * nseg, nb);
             {
                 VX_LAUNCH(og.c, og.s, "xcorr_kernel");
-                xcorr_ring_kernel<<<grid, kXcThreads, smem_launch, og.st>>>(d_bins, (float*)O->d, d_cols, d_h2, d_vstat, g);
+                xcorr_tma_kernel<<<grid, kXtThreads, smem_tma, og.st>>>(tmap, d_codes, (float*)O->d, d_cols, d_h2, d_vstat, g);
             }
             rc = check_launch("xcorr_kernel");
         }
     } else {
-        XcGeo g;
-        g.nx = A->nx; g.ny = A->ny; g.nz = A->nz; g.k = k;
-        g.ncols = (int)cols.size();
-        if (!cols.empty())
-            VX_CUDA(cudaMemcpyAsync(d_cols, cols.data(), sizeof(unsigned) * cols.size(), cudaMemcpyHostToDevice, og.st));
-        g.nw = nw; g.seg = seg; g.nseg = nseg;
-        size_t smem = sizeof(unsigned) * ((size_t)g.nw * kXcThreads + 2 * g.nw + g.ncols);
-        if (smem > 48 * 1024) {
+        XcGeo gd;
+        gd.nx = A->nx; gd.ny = A->ny; gd.nz = A->nz; gd.k = k; gd.pitch = pitch;
+        gd.ncols = (int)cols.size();
+        int nseg = (A->ny + 63) / 64;
+        const int seg = (A->ny + nseg - 1) / nseg;
+        nseg = (A->ny + seg - 1) / seg;
+        gd.nw = (k + 1) / 2; gd.seg = seg; gd.nseg = nseg;
+        if (!cols.empty()) {
+            cudaError_t e = cudaMemcpyAsync(d_cols, cols.data(), sizeof(unsigned) * cols.size(), cudaMemcpyHostToDevice, og.st);
+            if (e != cudaSuccess) rc = fail(VX_E_CUDA, "crossCorrelation set-up: %s", cudaGetErrorString(e));
+        }
+        size_t smem = sizeof(unsigned) * ((size_t)gd.nw * kXcThreads + 2 * gd.nw + gd.ncols);
+        if (rc == VX_OK && smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(xcorr_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) rc = fail(VX_E_CUDA, "smem attribute: %s", cudaGetErrorString(e));
         }
         if (rc == VX_OK) {
-            dim3 grid((A->nx + 31) / 32, (A->nz * g.nseg + kXcWarps - 1) / kXcWarps, nb);
+            dim3 grid((A->nx + 31) / 32, (A->nz * gd.nseg + kXcWarps - 1) / kXcWarps, nb);
             {
                 VX_LAUNCH(og.c, og.s, "xcorr_direct_kernel");
-                xcorr_direct_kernel<<<grid, kXcThreads, smem, og.st>>>(d_bins, (float*)O->d, d_cols, d_h2, d_vstat, g);
+                xcorr_direct_kernel<<<grid, kXcThreads, smem, og.st>>>(d_codes, (float*)O->d, d_cols, d_h2, d_vstat, gd);
             }
             rc = check_launch("xcorr_direct_kernel");
         }
     }
-    if (rc == VX_OK) rc = scratch_free(og.c, og.s, d_edges);
-    if (rc == VX_OK) rc = scratch_free(og.c, og.s, d_bins);
-    if (rc == VX_OK) rc = scratch_free(og.c, og.s, d_h2);
-    if (rc == VX_OK) rc = scratch_free(og.c, og.s, d_vstat);
-    if (rc == VX_OK) rc = scratch_free(og.c, og.s, d_cols);
     if (rc != VX_OK) { drop(O); return rc; }
     return og.finish(O, out);
 }
@@ -864,16 +907,17 @@ extern "C" int32_t vx_cross_correlation(vx_ctx ctx, vx_img a, vx_img b, vx_img r
     VX_TRY(og.input(region, &R, VX_U8));
     VX_TRY(same_shape(A, B));
     VX_TRY(same_shape(A, R));
+    Scratch sc(og.c, og.s);
     float* d_edges = nullptr;
     unsigned* d_h2 = nullptr;
-    uint8_t* d_bins = nullptr;
-    VX_TRY(upload_edges(og, A->nb, m, M, k, &d_edges));
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * 256 * A->nb, (void**)&d_h2));
-    VX_TRY(xcorr_bins(og, A, d_edges, k, &d_bins));
-    // similarTo(a) correlates an image with itself: its bins are already there
-    if (A == B) VX_TRY(region_hist(og, d_bins, true, R, d_edges, k, d_h2));
+    uint8_t* d_codes = nullptr;
+    VX_TRY(upload_edges(og, sc, A->nb, m, M, k, &d_edges));
+    VX_TRY(sc.alloc(sizeof(unsigned) * 256 * A->nb, &d_h2));
+    VX_TRY(xcorr_codes(og, sc, A, d_edges, k, &d_codes));
+    // similarTo(a) correlates an image with itself: its codes are already there
+    if (A == B) VX_TRY(region_hist(og, d_codes, true, R, d_edges, k, d_h2));
     else VX_TRY(region_hist(og, B->d, false, R, d_edges, k, d_h2));
-    return xcorr_run(og, A, d_bins, d_edges, d_h2, rho, k, out);
+    return xcorr_run(og, sc, A, d_codes, d_h2, rho, k, out);
 }
 
 extern "C" int32_t vx_region_histogram(vx_ctx ctx, vx_img b, vx_img region, const double* m,
@@ -888,18 +932,17 @@ extern "C" int32_t vx_region_histogram(vx_ctx ctx, vx_img b, vx_img region, cons
     VX_TRY(og.input(region, &R, VX_U8));
     VX_TRY(same_shape(B, R));
     const int nb = B->nb;
+    Scratch sc(og.c, og.s);
     float* d_edges = nullptr;
     unsigned* d_h2 = nullptr;
-    VX_TRY(upload_edges(og, nb, m, M, k, &d_edges));
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * 256 * nb, (void**)&d_h2));
+    VX_TRY(upload_edges(og, sc, nb, m, M, k, &d_edges));
+    VX_TRY(sc.alloc(sizeof(unsigned) * 256 * nb, &d_h2));
     VX_TRY(region_hist(og, B->d, false, R, d_edges, k, d_h2));
     std::vector<unsigned> host((size_t)256 * nb);
     VX_CUDA(cudaMemcpyAsync(host.data(), d_h2, sizeof(unsigned) * 256 * nb, cudaMemcpyDeviceToHost, og.st));
     VX_CUDA(cudaStreamSynchronize(og.st));
     for (int v = 0; v < nb; v++)
         for (int i = 0; i < k; i++) h2[(size_t)v * k + i] = host[(size_t)v * 256 + i];
-    VX_TRY(scratch_free(og.c, og.s, d_edges));
-    VX_TRY(scratch_free(og.c, og.s, d_h2));
     return og.finish_scalar();
 }
 
@@ -922,15 +965,16 @@ extern "C" int32_t vx_cross_correlation_h2(vx_ctx ctx, vx_img a, const uint64_t*
                        (unsigned long long)c);
             host[(size_t)v * 256 + i] = (unsigned)c;
         }
+    Scratch sc(og.c, og.s);
     float* d_edges = nullptr;
     unsigned* d_h2 = nullptr;
-    uint8_t* d_bins = nullptr;
-    VX_TRY(upload_edges(og, nb, m, M, k, &d_edges));
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * 256 * nb, (void**)&d_h2));
+    uint8_t* d_codes = nullptr;
+    VX_TRY(upload_edges(og, sc, nb, m, M, k, &d_edges));
+    VX_TRY(sc.alloc(sizeof(unsigned) * 256 * nb, &d_h2));
     // pageable source: cudaMemcpyAsync stages it before returning, `host` may die afterwards
     VX_CUDA(cudaMemcpyAsync(d_h2, host.data(), sizeof(unsigned) * 256 * nb, cudaMemcpyHostToDevice, og.st));
-    VX_TRY(xcorr_bins(og, A, d_edges, k, &d_bins));
-    return xcorr_run(og, A, d_bins, d_edges, d_h2, rho, k, out);
+    VX_TRY(xcorr_codes(og, sc, A, d_edges, k, &d_codes));
+    return xcorr_run(og, sc, A, d_codes, d_h2, rho, k, out);
 }
 
 // Host-only helper (no device needed): the k+1 break points of the crossCorrelation binning for
@@ -941,5 +985,24 @@ extern "C" int32_t vx_xcorr_bin_edges(double m, double M, int32_t k, float* edge
     VX_REQUIRE(k >= 1 && k <= kXcMaxBins, VX_E_UNSUPPORTED, "k = %d bins; supported range is [1,%d]", k,
                kXcMaxBins);
     compute_edges(m, M, k, edges);
+    return VX_OK;
+}
+
+// Host-only helper (no device needed): the region statistic the kernels use, (double)(k*S22 - n2^2)
+// formed in 128 bits, for one k-bin histogram.  Exposed so the two-limb arithmetic and the
+// hand-written rounding can be tested against the oracle's __int128 on a machine without a GPU.
+extern "C" int32_t vx_xcorr_region_stat(const uint64_t* h2, int32_t k, double* d2, int32_t* positive) {
+    VX_REQUIRE(h2 != nullptr && d2 != nullptr && positive != nullptr, VX_E_INVALID_ARG, "NULL argument");
+    VX_REQUIRE(k >= 1 && k <= kXcMaxBins, VX_E_UNSUPPORTED, "k = %d bins; supported range is [1,%d]", k,
+               kXcMaxBins);
+    unsigned h[256] = {0};
+    for (int i = 0; i < k; i++) {
+        VX_REQUIRE(h2[i] <= 0xffffffffull, VX_E_UNSUPPORTED, "region histogram counter %llu exceeds 32 bits",
+                   (unsigned long long)h2[i]);
+        h[i] = (unsigned)h2[i];
+    }
+    const XcStat s = xc_region_stat(h, k);
+    *d2 = s.d2d;
+    *positive = s.d2pos;
     return VX_OK;
 }
