@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <utility>
 #include <vector>
 
 #include "vx_internal.h"
@@ -368,7 +369,7 @@ constexpr unsigned kXtHS = kXtCons * 4;      // byte stride between two codes of
 struct XtGeo {
     int nx, ny, nz, k, seg, nseg, ball;
     int ncols, nreal;          // length of the column table (with alignment filler) / real columns
-    int wy, wz, P, nchunk, pitch;
+    int wx, wy, wz, P, nchunk, pitch;
     int gstart[17], gend[17];  // columns with y half-extent e are [gstart[e], gend[e]), gstart 4-aligned
 };
 
@@ -377,17 +378,110 @@ __device__ __forceinline__ unsigned lds_u8(unsigned addr) {
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+template <int OFF>
+__device__ __forceinline__ unsigned lds_u8_imm(unsigned addr) {   // LDS.U8 R, [R + imm]
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
 __device__ __forceinline__ unsigned atoms_add(unsigned addr, unsigned delta) {
     unsigned v;
     asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(v) : "r"(addr), "r"(delta) : "memory");
     return v;
 }
 
+// ---- balls known at compile time (unit spacing, integer rho^2): the column list as constant
+// expressions, so that the slide of the specialised kernel is straight-line code whose ring
+// reads carry their column offset as an immediate (7 instructions per counter pair: 2 LDS.U8,
+// 2 IMAD, 2 ATOMS, 1 IADD3) instead of a table-driven loop (11.5).
+constexpr int cisqrt(int v) {
+    int r = 0;
+    while ((r + 1) * (r + 1) <= v) r++;
+    return r;
+}
+template <int R2>
+struct BallCols {
+    static constexpr int W = cisqrt(R2);
+    static constexpr int MAXC = (2 * W + 1) * (2 * W + 1);
+    int n;
+    int dx[MAXC], dz[MAXC], e[MAXC];
+    constexpr BallCols() : n(0), dx{}, dz{}, e{} {
+        for (int z = -W; z <= W; z++)
+            for (int x = -W; x <= W; x++) {
+                const int rem = R2 - x * x - z * z;
+                if (rem < 0) continue;
+                dx[n] = x; dz[n] = z; e[n] = cisqrt(rem);
+                n++;
+            }
+    }
+};
+template <int R2>
+struct Ball {
+    static constexpr BallCols<R2> c{};
+    static constexpr int W = BallCols<R2>::W;
+};
+template <int R2>
+constexpr BallCols<R2> Ball<R2>::c;
+
+constexpr int kXtBatch = 14;   // counter pairs whose shared-memory operations are in flight together
+
+template <int R2, int I>
+__device__ __forceinline__ unsigned xt_ld(const unsigned* prow) {   // prow[e]: ring row of this column's voxel
+    constexpr int e = Ball<R2>::c.e[I];
+    constexpr int off = (Ball<R2>::W + Ball<R2>::c.dz[I]) * (kXtCH * kXtRowB) + kXtHalo + Ball<R2>::c.dx[I];
+    return lds_u8_imm<off>(prow[e]);
+}
+// one batch: all ring reads, then the counter addresses, then the atomics (+1 for the voxel that
+// enters the ball, -1 for the one that leaves); ri/ro receive the counters' previous values
+template <int R2, int BASE, int... J>
+__device__ __forceinline__ void xt_batch(std::integer_sequence<int, J...>, unsigned hbase, const unsigned* pin,
+                                         const unsigned* pout, unsigned* ri, unsigned* ro) {
+    ((ri[J] = xt_ld<R2, BASE + J>(pin)), ...);
+    ((ro[J] = xt_ld<R2, BASE + J>(pout)), ...);
+    ((ri[J] = hbase + ri[J] * kXtHS), ...);
+    ((ro[J] = hbase + ro[J] * kXtHS), ...);
+    ((ri[J] = atoms_add(ri[J], 1u)), ...);
+    ((ro[J] = atoms_add(ro[J], 0xffffffffu)), ...);
+}
+// all columns of the ball in batches; the previous batch's returns are summed after the next
+// batch's atomics were issued, so nothing waits for an atomic's round trip
+template <int R2, int BASE>
+__device__ __forceinline__ void xt_slide(unsigned hbase, const unsigned* pin, const unsigned* pout, unsigned& A,
+                                         const unsigned* pri, const unsigned* pro, int pn) {
+    constexpr int N = Ball<R2>::c.n;
+    if constexpr (BASE < N) {
+        constexpr int CNT = (N - BASE) < kXtBatch ? (N - BASE) : kXtBatch;
+        unsigned ri[kXtBatch], ro[kXtBatch];
+        xt_batch<R2, BASE>(std::make_integer_sequence<int, CNT>{}, hbase, pin, pout, ri, ro);
+#pragma unroll
+        for (int j = 0; j < kXtBatch; j++)
+            if (j < pn) A += pri[j] - pro[j];
+        xt_slide<R2, BASE + CNT>(hbase, pin, pout, A, ri, ro, CNT);
+    } else {
+#pragma unroll
+        for (int j = 0; j < kXtBatch; j++)
+            if (j < pn) A += pri[j] - pro[j];
+    }
+}
+
+// one row of the initial ball: columns whose half-extent reaches |dy| add their voxel of ring row
+// `prow`; with `flat` every column adds all its 2e+1 voxels at once (they hold one value)
+template <int R2, int I>
+__device__ __forceinline__ void xt_init_row(unsigned hbase, unsigned prow, int ady, bool flat) {
+    if constexpr (I < Ball<R2>::c.n) {
+        constexpr int e = Ball<R2>::c.e[I];
+        constexpr int off = (Ball<R2>::W + Ball<R2>::c.dz[I]) * (kXtCH * kXtRowB) + kXtHalo + Ball<R2>::c.dx[I];
+        if (e >= ady) atoms_add(hbase + lds_u8_imm<off>(prow) * kXtHS, flat ? (unsigned)(2 * e + 1) : 1u);
+        xt_init_row<R2, I + 1>(hbase, prow, ady, flat);
+    }
+}
+
 // grid (ceil(nx/32), ceil(nz/6)*nseg, nb), block 224.  Dynamic shared memory:
 //   ring [nchunk][P][4][64] u8 | hist [k+1][192] u32 | h2s [k+1] u32 | cols [ncols] u32 | rowmask [48] u32 |
 //   mbarriers [36] u64 | gs, ge [17] int
 // cols[c] = byte offset of column c inside a chunk relative to (plane = warp, x = lane):
-// (wz+dz)*256 + 16 + dx.
+// (wz+dz)*256 + 16 + dx.   R2 > 0: the ball is Ball<R2> (unit spacing), cols/gs/ge are not used.
+template <int R2>
 __global__ void __launch_bounds__(kXtThreads, 2)
 xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ codes,
                  float* __restrict__ out, const unsigned* __restrict__ cols_g, const unsigned* __restrict__ h2,
@@ -397,8 +491,9 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
     unsigned char* xt_smem = xt_smem_raw + ((128u - (smem_u32(xt_smem_raw) & 127u)) & 127u);
     const int chunkB = g.P * kXtCH * kXtRowB;   // P is even: a multiple of 128
     const int nbin = g.k + 1;
+    const int nchunk = g.nchunk;
     unsigned char* ring = xt_smem;
-    unsigned* hist = reinterpret_cast<unsigned*>(ring + (size_t)g.nchunk * chunkB);
+    unsigned* hist = reinterpret_cast<unsigned*>(ring + (size_t)nchunk * chunkB);
     unsigned* h2s = hist + (size_t)nbin * kXtCons;
     unsigned* cols = h2s + ((nbin + 3) & ~3);
     unsigned* rowmask = cols + ((g.ncols + 3) & ~3);
@@ -419,10 +514,12 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
     // barrier addresses: full[s] = bar0 + 8 s, ready[s] = + 8 (12 + s), empty[s] = + 8 (24 + s)
 
     for (int i = tid; i < nbin; i += kXtThreads) h2s[i] = (i >= 1) ? h2[(size_t)vol * 256 + (i - 1)] : 0u;
-    for (int i = tid; i < g.ncols; i += kXtThreads) cols[i] = cols_g[i];
-    if (tid < 17) { gs[tid] = g.gstart[tid]; ge[tid] = g.gend[tid]; }
+    if (R2 == 0) {
+        for (int i = tid; i < g.ncols; i += kXtThreads) cols[i] = cols_g[i];
+        if (tid < 17) { gs[tid] = g.gstart[tid]; ge[tid] = g.gend[tid]; }
+    }
     if (tid == 0) {
-        for (int s = 0; s < g.nchunk; s++) {
+        for (int s = 0; s < nchunk; s++) {
             mbar_init(bar0 + 8 * s, 1);
             mbar_init(bar0 + 8 * (kXtMaxChunks + s), 1);
             mbar_init(bar0 + 8 * (2 * kXtMaxChunks + s), kXtWarps);
@@ -436,25 +533,37 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
         const unsigned ring_s = smem_u32(ring);
         unsigned ref4;
         {
-            const int zz = min(max(z0 - g.wz, 0), g.nz - 1), xx = min(max(x0 - kXtHalo, 0), g.nx - 1);
+            const int zz = min(max(z0 - g.wz, 0), g.nz - 1), xx = min(max(x0 - g.wx, 0), g.nx - 1);
             const int yy = min(max(r0, 0), g.ny - 1);
             ref4 = (unsigned)__ldg(codes + (((size_t)vol * g.nz + zz) * g.ny + yy) * g.pitch + xx) * 0x01010101u;
         }
+        // bytes of a window row that matter for the flat test: inside the image and within the
+        // x reach of the ball around the block's 32 voxels
+        unsigned bm[kXtRowB / 4];
+#pragma unroll
+        for (int i = 0; i < kXtRowB / 4; i++) {
+            bm[i] = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int wxo = 4 * i + b, xa = x0 - kXtHalo + wxo;
+                if (xa >= 0 && xa < g.nx && wxo >= kXtHalo - g.wx && wxo < kXtHalo + 32 + g.wx) bm[i] |= 0xffu << (8 * b);
+            }
+        }
         const int nsegm = g.P * kXtCH;   // (plane, row) segments of a chunk
+        int i_slot = 0, f_slot = 0;      // ring slots of the next chunk to issue / to flag
+        unsigned i_par = 1, f_par = 0;   // parity of the `empty` phase to wait for / of the `full` phase
         for (int j = 0; j < total_chunks + kXtLook; j++) {
             if (j < total_chunks) {
-                const int slot = j % g.nchunk, use = j / g.nchunk;
-                if (use > 0) mbar_wait(bar0 + 8 * (2 * kXtMaxChunks + slot), (unsigned)(use - 1) & 1u);
+                if (j >= nchunk) mbar_wait(bar0 + 8 * (2 * kXtMaxChunks + i_slot), i_par);
                 if (lane == 0) {
-                    mbar_arrive_expect_tx(bar0 + 8 * slot, (unsigned)chunkB);
-                    tma_load_4d(ring_s + slot * chunkB, &tmap, bar0 + 8 * slot, x0 - kXtHalo, r0 + j * kXtCH, z0 - g.wz, vol);
+                    mbar_arrive_expect_tx(bar0 + 8 * i_slot, (unsigned)chunkB);
+                    tma_load_4d(ring_s + i_slot * chunkB, &tmap, bar0 + 8 * i_slot, x0 - kXtHalo, r0 + j * kXtCH, z0 - g.wz, vol);
                 }
+                if (++i_slot == nchunk) { i_slot = 0; if (j >= nchunk) i_par ^= 1u; else i_par = 0u; }
             }
-            const int jj = j - kXtLook;
-            if (jj >= 0) {
-                const int slot = jj % g.nchunk, use = jj / g.nchunk;
-                mbar_wait(bar0 + 8 * slot, (unsigned)use & 1u);
-                // flat flags of the chunk's segments: 16 words each, in-image bytes against ref4
+            if (j >= kXtLook) {
+                mbar_wait(bar0 + 8 * f_slot, f_par);
+                // flat flags of the chunk's segments: 16 words each against ref4
                 unsigned m = 0;   // lanes 0..3: plane mask of ring row 4*slot + lane
                 for (int q = 0; q * 32 < nsegm; q++) {
                     const int sgm = q * 32 + lane;
@@ -463,16 +572,13 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
                         const int p = sgm >> 2, rr = sgm & 3;
                         const int zz = z0 - g.wz + p;
                         if (zz >= 0 && zz < g.nz) {
-                            const unsigned* w = reinterpret_cast<const unsigned*>(ring + (size_t)slot * chunkB + (p * kXtCH + rr) * kXtRowB);
+                            const uint4* w = reinterpret_cast<const uint4*>(ring + (size_t)f_slot * chunkB + (p * kXtCH + rr) * kXtRowB);
                             unsigned diff = 0;
 #pragma unroll
-                            for (int i = 0; i < kXtRowB / 4; i++) {
-                                const int xa = x0 - kXtHalo + 4 * i;
-                                unsigned bm = 0;
-#pragma unroll
-                                for (int b = 0; b < 4; b++)
-                                    if (xa + b >= 0 && xa + b < g.nx) bm |= 0xffu << (8 * b);
-                                diff |= (w[i] ^ ref4) & bm;
+                            for (int i = 0; i < kXtRowB / 16; i++) {
+                                const uint4 v = w[i];
+                                diff |= ((v.x ^ ref4) & bm[4 * i]) | ((v.y ^ ref4) & bm[4 * i + 1]) |
+                                        ((v.z ^ ref4) & bm[4 * i + 2]) | ((v.w ^ ref4) & bm[4 * i + 3]);
                             }
                             flat = diff == 0;
                         }
@@ -481,9 +587,10 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
                     if (lane < 4)
                         for (int pp = 0; pp < 8; pp++) m |= ((bal >> (4 * pp + lane)) & 1u) << (8 * q + pp);
                 }
-                if (lane < 4) rowmask[slot * kXtCH + lane] = m;
+                if (lane < 4) rowmask[f_slot * kXtCH + lane] = m;
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar0 + 8 * (kXtMaxChunks + slot));
+                if (lane == 0) mbar_arrive(bar0 + 8 * (kXtMaxChunks + f_slot));
+                if (++f_slot == nchunk) { f_slot = 0; f_par ^= 1u; }
             }
         }
         return;
@@ -494,53 +601,64 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
     const bool wactive = z < g.nz;            // warp-uniform
     const bool active = wactive && x < g.nx;
     const size_t nvox = (size_t)g.nx * g.ny * g.nz;
-    float* ov = out + (size_t)vol * nvox;
+    float* ov = out + (size_t)vol * nvox + ((size_t)z * g.ny + y0) * g.nx + x;   // output of step 0
     const XcStat vs = vstat[vol];
     const long long n2 = vs.n2;
     const long long K = (long long)g.k;
     const unsigned hbase = smem_u32(hist) + tid * 4;
     const unsigned tb = smem_u32(ring) + warp * (kXtCH * kXtRowB) + lane;
-    const unsigned pm = (1u << (2 * g.wz + 1)) - 1u;
+    const unsigned pm = ((1u << (2 * g.wz + 1)) - 1u) << warp;
     const bool p32 = (unsigned long long)g.ball * (unsigned long long)n2 < 0xffffffffull;
-    const int wy2 = 2 * g.wy;
+    const int wy = g.wy, wy2 = 2 * g.wy;
 
     for (int c = 0; c < nbin; c++) hist[c * kXtCons + tid] = 0u;   // own column only
 
-    int waited = 0;   // chunks whose `ready` barrier this warp has passed
-    auto ensure = [&](int rel) {   // ring row `rel` (relative to r0) is in shared memory, flags included
-        const int c = rel >> 2;
-        while (waited <= c) {
-            mbar_wait(bar0 + 8 * (kXtMaxChunks + waited % g.nchunk), (unsigned)(waited / g.nchunk) & 1u);
-            waited++;
+    int w_slot = 0;        // ring slot of the next chunk whose `ready` barrier this warp waits for
+    unsigned w_par = 0;
+    int rows_ready = 0;    // ring rows [0, rows_ready) are in shared memory, flat flags included
+    auto ensure = [&](int rel) {
+        while (rows_ready <= rel) {
+            mbar_wait(bar0 + 8 * (kXtMaxChunks + w_slot), w_par);
+            if (++w_slot == nchunk) { w_slot = 0; w_par ^= 1u; }
+            rows_ready += kXtCH;
         }
     };
-    auto rowoff = [&](int rel) {   // byte offset of ring row `rel` (general form, used outside the loop)
-        return (unsigned)(((rel >> 2) % g.nchunk) * chunkB + (rel & 3) * kXtRowB);
+    const int x_lim = nchunk * kXtCH;
+    int x_idx = 0;         // rowmask index of the next ring row to examine (slot * 4 + row)
+    int run = 0;           // consecutive flat rows (for this warp's planes) ending at the last examined row
+    auto examine_next = [&]() {
+        run = ((rowmask[x_idx] & pm) == pm) ? run + 1 : 0;
+        if (++x_idx == x_lim) x_idx = 0;
     };
-    int run = 0;      // consecutive flat rows (for this warp's planes) ending at the last examined row
-    auto examine = [&](int rel) {
-        const unsigned m = rowmask[((rel >> 2) % g.nchunk) * kXtCH + (rel & 3)];
-        run = (((m >> warp) & pm) == pm) ? run + 1 : 0;
-    };
+    // byte offset of ring row `rel` (general form, used outside the loop)
+    auto rowoff = [&](int rel) { return (unsigned)(((rel >> 2) % nchunk) * chunkB + (rel & 3) * kXtRowB); };
 
     ensure(wy2);
-    for (int rel = 0; rel <= wy2; rel++) examine(rel);
+    for (int rel = 0; rel <= wy2; rel++) examine_next();
     unsigned S = 0;   // sum over ALL codes (the dummy code 0 included) of h^2
     if (wactive) {
-        if (run >= wy2 + 1) {
-            // the whole neighbourhood of the first voxel is one value per column: every column
-            // adds its 2e+1 voxels to one counter (the reference code, or code 0 outside the image)
-            const unsigned prow = tb + rowoff(g.wy);
-            for (int e = 0; e <= g.wy; e++)
-                for (int c = gs[e]; c < ge[e]; c++)
-                    atoms_add(hbase + lds_u8(prow + cols[c]) * kXtHS, (unsigned)(2 * e + 1));
+        const bool flat0 = run >= wy2 + 1;
+        if constexpr (R2 == 0) {
+            if (flat0) {
+                // the whole neighbourhood of the first voxel is one value per column: every column
+                // adds its 2e+1 voxels to one counter (the reference code, or code 0 outside the image)
+                const unsigned prow = tb + rowoff(wy);
+                for (int e = 0; e <= wy; e++)
+                    for (int c = gs[e]; c < ge[e]; c++)
+                        atoms_add(hbase + lds_u8(prow + cols[c]) * kXtHS, (unsigned)(2 * e + 1));
+            } else {
+                for (int e = 0; e <= wy; e++)
+                    for (int c = gs[e]; c < ge[e]; c++) {
+                        const unsigned co = cols[c];
+                        for (int dy = -e; dy <= e; dy++)
+                            atoms_add(hbase + lds_u8(tb + rowoff(wy + dy) + co) * kXtHS, 1u);
+                    }
+            }
         } else {
-            for (int e = 0; e <= g.wy; e++)
-                for (int c = gs[e]; c < ge[e]; c++) {
-                    const unsigned co = cols[c];
-                    for (int dy = -e; dy <= e; dy++)
-                        atoms_add(hbase + lds_u8(tb + rowoff(g.wy + dy) + co) * kXtHS, 1u);
-                }
+            // row by row: row dy of the ball holds the columns with half-extent >= |dy|.  A flat
+            // neighbourhood needs one row only, every column weighted by its 2e+1 voxels.
+            for (int dy = flat0 ? 0 : -wy; dy <= (flat0 ? 0 : wy); dy++)
+                xt_init_row<R2, 0>(hbase, tb + rowoff(wy + dy), dy < 0 ? -dy : dy, flat0);
         }
         for (int c = 0; c < nbin; c++) {
             const unsigned h = hist[c * kXtCons + tid];
@@ -571,56 +689,94 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
                 res = (float)__ddiv_rn((double)num, __dsqrt_rn(__dmul_rn((double)d1, vs.d2d)));
             dirty = false;
         }
-        if (active) ov[((size_t)z * g.ny + (y0 + t)) * g.nx + x] = res;
+        const int tq = t & 3;
+        // ---- four steps at once where nothing changes: the next four rows are flat as well, so
+        // the slides t .. t+3 move nothing and rows t .. t+3 all get the current coefficient
+        if (tq == 0 && t + 4 < T && run >= wy2 + 1) {
+            ensure(t + wy2 + 4);
+            int i1 = x_idx + 1, i2 = x_idx + 2, i3 = x_idx + 3;
+            if (i1 >= x_lim) i1 -= x_lim;
+            if (i2 >= x_lim) i2 -= x_lim;
+            if (i3 >= x_lim) i3 -= x_lim;
+            const unsigned m4 = rowmask[x_idx] & rowmask[i1] & rowmask[i2] & rowmask[i3];
+            if ((m4 & pm) == pm) {
+                if (active) {
+                    ov[0] = res; ov[g.nx] = res; ov[2 * (size_t)g.nx] = res; ov[3 * (size_t)g.nx] = res;
+                }
+                ov += 4 * (size_t)g.nx;
+                run += 4;
+                x_idx = x_idx + 4 >= x_lim ? x_idx + 4 - x_lim : x_idx + 4;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar0 + 8 * (2 * kXtMaxChunks + slot_t));
+                slot_t = slot_t + 1 == nchunk ? 0 : slot_t + 1;
+                t += 3;
+                continue;
+            }
+        }
+        if (active) *ov = res;
+        ov += g.nx;
         if (t + 1 >= T) break;
         // ---- slide the ball from row y0+t to y0+t+1: ring rows t .. t+2wy+1
         ensure(t + wy2 + 1);
-        examine(t + wy2 + 1);
+        examine_next();
         if (wactive && run < wy2 + 2) {
             unsigned A = 0;            // sum of counters before +1 minus sum of counters before -1
-            unsigned pi0 = 0, pi1 = 0, pi2 = 0, pi3 = 0, po0 = 0, po1 = 0, po2 = 0, po3 = 0;   // previous batch
-            const int tq = t & 3;
-            for (int e = 0; e <= g.wy; e++) {
-                int c = gs[e];
-                const int cend = ge[e];
-                if (c >= cend) continue;
-                int sin = slot_t + ((tq + g.wy + 1 + e) >> 2), sout = slot_t + ((tq + g.wy - e) >> 2);
-                if (sin >= g.nchunk) sin -= g.nchunk;
-                if (sout >= g.nchunk) sout -= g.nchunk;
-                const unsigned pin = tb + sin * chunkB + ((tq + g.wy + 1 + e) & 3) * kXtRowB;
-                const unsigned pout = tb + sout * chunkB + ((tq + g.wy - e) & 3) * kXtRowB;
+            if constexpr (R2 > 0) {
+                constexpr int W = Ball<R2>::W;
+                unsigned pin[W + 1], pout[W + 1];
+#pragma unroll
+                for (int e = 0; e <= W; e++) {
+                    int sin = slot_t + ((tq + W + 1 + e) >> 2), sout = slot_t + ((tq + W - e) >> 2);
+                    if (sin >= nchunk) sin -= nchunk;
+                    if (sout >= nchunk) sout -= nchunk;
+                    pin[e] = tb + sin * chunkB + ((tq + W + 1 + e) & 3) * kXtRowB;
+                    pout[e] = tb + sout * chunkB + ((tq + W - e) & 3) * kXtRowB;
+                }
+                xt_slide<R2, 0>(hbase, pin, pout, A, nullptr, nullptr, 0);
+            } else {
+                unsigned pi0 = 0, pi1 = 0, pi2 = 0, pi3 = 0, po0 = 0, po1 = 0, po2 = 0, po3 = 0;   // previous batch
+                for (int e = 0; e <= wy; e++) {
+                    int c = gs[e];
+                    const int cend = ge[e];
+                    if (c >= cend) continue;
+                    int sin = slot_t + ((tq + wy + 1 + e) >> 2), sout = slot_t + ((tq + wy - e) >> 2);
+                    if (sin >= nchunk) sin -= nchunk;
+                    if (sout >= nchunk) sout -= nchunk;
+                    const unsigned pin = tb + sin * chunkB + ((tq + wy + 1 + e) & 3) * kXtRowB;
+                    const unsigned pout = tb + sout * chunkB + ((tq + wy - e) & 3) * kXtRowB;
 #pragma unroll 1
-                for (; c + 4 <= cend; c += 4) {
-                    const uint4 co = *reinterpret_cast<const uint4*>(cols + c);   // gstart is 4-aligned
-                    unsigned i0 = lds_u8(pin + co.x), o0 = lds_u8(pout + co.x);
-                    unsigned i1 = lds_u8(pin + co.y), o1 = lds_u8(pout + co.y);
-                    unsigned i2 = lds_u8(pin + co.z), o2 = lds_u8(pout + co.z);
-                    unsigned i3 = lds_u8(pin + co.w), o3 = lds_u8(pout + co.w);
-                    A += (pi0 - po0) + (pi1 - po1) + (pi2 - po2) + (pi3 - po3);   // returns of the previous batch
-                    i0 = hbase + i0 * kXtHS; o0 = hbase + o0 * kXtHS;
-                    i1 = hbase + i1 * kXtHS; o1 = hbase + o1 * kXtHS;
-                    i2 = hbase + i2 * kXtHS; o2 = hbase + o2 * kXtHS;
-                    i3 = hbase + i3 * kXtHS; o3 = hbase + o3 * kXtHS;
-                    pi0 = atoms_add(i0, 1u); po0 = atoms_add(o0, 0xffffffffu);
-                    pi1 = atoms_add(i1, 1u); po1 = atoms_add(o1, 0xffffffffu);
-                    pi2 = atoms_add(i2, 1u); po2 = atoms_add(o2, 0xffffffffu);
-                    pi3 = atoms_add(i3, 1u); po3 = atoms_add(o3, 0xffffffffu);
+                    for (; c + 4 <= cend; c += 4) {
+                        const uint4 co = *reinterpret_cast<const uint4*>(cols + c);   // gstart is 4-aligned
+                        unsigned i0 = lds_u8(pin + co.x), o0 = lds_u8(pout + co.x);
+                        unsigned i1 = lds_u8(pin + co.y), o1 = lds_u8(pout + co.y);
+                        unsigned i2 = lds_u8(pin + co.z), o2 = lds_u8(pout + co.z);
+                        unsigned i3 = lds_u8(pin + co.w), o3 = lds_u8(pout + co.w);
+                        A += (pi0 - po0) + (pi1 - po1) + (pi2 - po2) + (pi3 - po3);   // returns of the previous batch
+                        i0 = hbase + i0 * kXtHS; o0 = hbase + o0 * kXtHS;
+                        i1 = hbase + i1 * kXtHS; o1 = hbase + o1 * kXtHS;
+                        i2 = hbase + i2 * kXtHS; o2 = hbase + o2 * kXtHS;
+                        i3 = hbase + i3 * kXtHS; o3 = hbase + o3 * kXtHS;
+                        pi0 = atoms_add(i0, 1u); po0 = atoms_add(o0, 0xffffffffu);
+                        pi1 = atoms_add(i1, 1u); po1 = atoms_add(o1, 0xffffffffu);
+                        pi2 = atoms_add(i2, 1u); po2 = atoms_add(o2, 0xffffffffu);
+                        pi3 = atoms_add(i3, 1u); po3 = atoms_add(o3, 0xffffffffu);
+                    }
+                    for (; c < cend; c++) {
+                        const unsigned co = cols[c];
+                        const unsigned ai = hbase + lds_u8(pin + co) * kXtHS, ao = hbase + lds_u8(pout + co) * kXtHS;
+                        A += atoms_add(ai, 1u) - atoms_add(ao, 0xffffffffu);
+                    }
                 }
-                for (; c < cend; c++) {
-                    const unsigned co = cols[c];
-                    const unsigned ai = hbase + lds_u8(pin + co) * kXtHS, ao = hbase + lds_u8(pout + co) * kXtHS;
-                    A += atoms_add(ai, 1u) - atoms_add(ao, 0xffffffffu);
-                }
+                A += (pi0 - po0) + (pi1 - po1) + (pi2 - po2) + (pi3 - po3);
             }
-            A += (pi0 - po0) + (pi1 - po1) + (pi2 - po2) + (pi3 - po3);
             S += 2u * A + 2u * (unsigned)g.nreal;
             dirty = true;
         }
         // ring row t is dead after this slide; its chunk goes back to the producer with its last row
-        if ((t & 3) == 3) {
+        if (tq == 3) {
             __syncwarp();
             if (lane == 0) mbar_arrive(bar0 + 8 * (2 * kXtMaxChunks + slot_t));
-            slot_t = slot_t + 1 == g.nchunk ? 0 : slot_t + 1;
+            slot_t = slot_t + 1 == nchunk ? 0 : slot_t + 1;
         }
     }
 }
@@ -838,7 +994,20 @@ static int xcorr_run(OpGuard& og, Scratch& sc, Image* A, const uint8_t* d_codes,
         g.nx = A->nx; g.ny = A->ny; g.nz = A->nz; g.k = k;
         g.seg = seg; g.nseg = nseg; g.ball = (int)ball;
         g.ncols = (int)tcols.size(); g.nreal = (int)cols.size();
-        g.wy = wy; g.wz = wz; g.P = P; g.nchunk = nchunk; g.pitch = pitch;
+        g.wx = wx; g.wy = wy; g.wz = wz; g.P = P; g.nchunk = nchunk; g.pitch = pitch;
+        // unit spacing and an integer-valued ball: the kernels with the column list compiled in
+        auto kern = xcorr_tma_kernel<0>;
+        if (A->sp[0] == 1.0f && A->sp[1] == 1.0f && A->sp[2] == 1.0f) {
+            const double r2 = (double)rho * (double)rho;
+            const int ir2 = (int)floor(r2);   // dx^2+dy^2+dz^2 <= rho^2  <=>  <= floor(rho^2) for integers
+            switch (ir2) {
+                case 4: kern = xcorr_tma_kernel<4>; break;
+                case 9: kern = xcorr_tma_kernel<9>; break;
+                case 16: kern = xcorr_tma_kernel<16>; break;
+                case 25: kern = xcorr_tma_kernel<25>; break;
+                default: break;
+            }
+        }
         CUtensorMap tmap;
         const uint64_t dims[4] = {(uint64_t)A->nx, (uint64_t)A->ny, (uint64_t)A->nz, (uint64_t)nb};
         const uint64_t strides[3] = {(uint64_t)pitch, (uint64_t)pitch * A->ny, (uint64_t)pitch * A->ny * A->nz};
@@ -847,14 +1016,14 @@ static int xcorr_run(OpGuard& og, Scratch& sc, Image* A, const uint8_t* d_codes,
         if (rc == VX_OK) {
             cudaError_t e = cudaMemcpyAsync(d_cols, tcols.data(), sizeof(unsigned) * tcols.size(), cudaMemcpyHostToDevice, og.st);
             if (e == cudaSuccess)
-                e = cudaFuncSetAttribute(xcorr_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
+                e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
             if (e != cudaSuccess) rc = fail(VX_E_CUDA, "crossCorrelation set-up: %s", cudaGetErrorString(e));
         }
         if (rc == VX_OK) {
             dim3 grid((A->nx + 31) / 32, ((A->nz + kXtWarps - 1) / kXtWarps) * nseg, nb);
             {
                 VX_LAUNCH(og.c, og.s, "xcorr_kernel");
-                xcorr_tma_kernel<<<grid, kXtThreads, smem_tma, og.st>>>(tmap, d_codes, (float*)O->d, d_cols, d_h2, d_vstat, g);
+                kern<<<grid, kXtThreads, smem_tma, og.st>>>(tmap, d_codes, (float*)O->d, d_cols, d_h2, d_vstat, g);
             }
             rc = check_launch("xcorr_kernel");
         }
