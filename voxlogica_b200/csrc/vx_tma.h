@@ -50,6 +50,11 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// the same for a thread nobody is waiting for (a copy-issuing thread whose slots free up well ahead
+// of need): back off between polls so that the polling does not take issue slots from the workers
+__device__ __forceinline__ void mbar_wait_relaxed(unsigned bar, unsigned parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(200);
+}
 // one tile of a rank-4 tensor map into shared memory; completes `bytes of the box` on the barrier
 __device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1,
                                             int c2, int c3) {

@@ -357,14 +357,21 @@ xcorr_direct_kernel(const uint8_t* __restrict__ codes, float* __restrict__ out,
 //    touches are flat its histograms cannot change and the step is a plain store.
 constexpr int kXtWarps = 6;                  // consumer warps = z planes per block
 constexpr int kXtCons = kXtWarps * 32;       // histogram owners
-constexpr int kXtThreads = kXtCons + 32;     // + the producer warp
+constexpr int kXtThreads = kXtCons + 64;     // + the copy warp and the flag warp
 constexpr int kXtCH = 4;                     // rows per TMA chunk
 constexpr int kXtRowB = 64;                  // bytes per window row: 16 + 32 + 16 voxels (the copy engine wants
                                              // the innermost tile coordinate 16-byte aligned: measured, scripts/ubench/tma_probe.cu)
 constexpr int kXtHalo = 16;                  // voxels of x halo on either side
-constexpr int kXtMaxChunks = 12;
-constexpr int kXtLook = 2;                   // chunks in flight ahead of the flag pass
+constexpr int kXtMaxChunks = 16;
+constexpr int kXtLook = 3;                   // ring chunks beyond the live ones: loads in flight / landed ahead
 constexpr unsigned kXtHS = kXtCons * 4;      // byte stride between two codes of one thread's histogram
+
+#ifdef XT_TRACE
+__device__ long long xt_trace[1024];
+#define XT_T(cond, idx) do { if ((cond) && blockIdx.x == 3 && blockIdx.y == 20 && blockIdx.z == 1) xt_trace[(idx)] = clock64(); } while (0)
+#else
+#define XT_T(cond, idx) do { } while (0)
+#endif
 
 struct XtGeo {
     int nx, ny, nz, k, seg, nseg, ball;
@@ -465,20 +472,34 @@ __device__ __forceinline__ void xt_slide(unsigned hbase, const unsigned* pin, co
 }
 
 // one row of the initial ball: columns whose half-extent reaches |dy| add their voxel of ring row
-// `prow`; with `flat` every column adds all its 2e+1 voxels at once (they hold one value)
-template <int R2, int I>
+// `prow`; with `flat` every column adds all its 2e+1 voxels at once (they hold one value).
+// Batched like the slide: the ring reads of a batch are issued before its atomics.
+template <int R2, int BASE, int... J>
+__device__ __forceinline__ void xt_init_batch(std::integer_sequence<int, J...>, unsigned hbase, unsigned prow, int ady,
+                                              bool flat) {
+    unsigned v[sizeof...(J)];
+    ((v[J] = (Ball<R2>::c.e[BASE + J] >= ady)
+                 ? lds_u8_imm<(Ball<R2>::W + Ball<R2>::c.dz[BASE + J]) * (kXtCH * kXtRowB) + kXtHalo + Ball<R2>::c.dx[BASE + J]>(prow)
+                 : 0u),
+     ...);
+    (((Ball<R2>::c.e[BASE + J] >= ady)
+          ? (void)atoms_add(hbase + v[J] * kXtHS, flat ? (unsigned)(2 * Ball<R2>::c.e[BASE + J] + 1) : 1u)
+          : (void)0),
+     ...);
+}
+template <int R2, int BASE>
 __device__ __forceinline__ void xt_init_row(unsigned hbase, unsigned prow, int ady, bool flat) {
-    if constexpr (I < Ball<R2>::c.n) {
-        constexpr int e = Ball<R2>::c.e[I];
-        constexpr int off = (Ball<R2>::W + Ball<R2>::c.dz[I]) * (kXtCH * kXtRowB) + kXtHalo + Ball<R2>::c.dx[I];
-        if (e >= ady) atoms_add(hbase + lds_u8_imm<off>(prow) * kXtHS, flat ? (unsigned)(2 * e + 1) : 1u);
-        xt_init_row<R2, I + 1>(hbase, prow, ady, flat);
+    constexpr int N = Ball<R2>::c.n;
+    if constexpr (BASE < N) {
+        constexpr int CNT = (N - BASE) < kXtBatch ? (N - BASE) : kXtBatch;
+        xt_init_batch<R2, BASE>(std::make_integer_sequence<int, CNT>{}, hbase, prow, ady, flat);
+        xt_init_row<R2, BASE + CNT>(hbase, prow, ady, flat);
     }
 }
 
-// grid (ceil(nx/32), ceil(nz/6)*nseg, nb), block 224.  Dynamic shared memory:
-//   ring [nchunk][P][4][64] u8 | hist [k+1][192] u32 | h2s [k+1] u32 | cols [ncols] u32 | rowmask [48] u32 |
-//   mbarriers [36] u64 | gs, ge [17] int
+// grid (ceil(nx/32), ceil(nz/6)*nseg, nb), block 256.  Dynamic shared memory:
+//   ring [nchunk][P][4][64] u8 | hist [k+1][192] u32 | h2s [k+1] u32 | cols [ncols] u32 | rowmask [64] u32 |
+//   mbarriers [48] u64 | gs, ge [17] int
 // cols[c] = byte offset of column c inside a chunk relative to (plane = warp, x = lane):
 // (wz+dz)*256 + 16 + dx.   R2 > 0: the ball is Ball<R2> (unit spacing), cols/gs/ge are not used.
 template <int R2>
@@ -494,7 +515,7 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
     const int nchunk = g.nchunk;
     unsigned char* ring = xt_smem;
     unsigned* hist = reinterpret_cast<unsigned*>(ring + (size_t)nchunk * chunkB);
-    unsigned* h2s = hist + (size_t)nbin * kXtCons;
+    unsigned* h2s = hist + (size_t)((nbin + 3) & ~3) * kXtCons;   // histogram rows padded to a multiple of 4 codes
     unsigned* cols = h2s + ((nbin + 3) & ~3);
     unsigned* rowmask = cols + ((g.ncols + 3) & ~3);
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(rowmask + kXtMaxChunks * kXtCH);
@@ -511,9 +532,9 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
     const int r0 = y0 - g.wy;                        // image row of ring row 0
     const int total_chunks = (T + 2 * g.wy + kXtCH - 1) / kXtCH;
     const unsigned bar0 = smem_u32(bars);
-    // barrier addresses: full[s] = bar0 + 8 s, ready[s] = + 8 (12 + s), empty[s] = + 8 (24 + s)
+    // barrier addresses: full[s] = bar0 + 8 s, ready[s] = + 8 (16 + s), empty[s] = + 8 (32 + s)
 
-    for (int i = tid; i < nbin; i += kXtThreads) h2s[i] = (i >= 1) ? h2[(size_t)vol * 256 + (i - 1)] : 0u;
+    for (int i = tid; i < ((nbin + 3) & ~3); i += kXtThreads) h2s[i] = (i >= 1 && i < nbin) ? h2[(size_t)vol * 256 + (i - 1)] : 0u;
     if (R2 == 0) {
         for (int i = tid; i < g.ncols; i += kXtThreads) cols[i] = cols_g[i];
         if (tid < 17) { gs[tid] = g.gstart[tid]; ge[tid] = g.gend[tid]; }
@@ -527,71 +548,83 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
         mbar_fence_init();
     }
     __syncthreads();
+    XT_T(tid == 0, 0);
 
     if (warp == kXtWarps) {
-        // ================================================================ producer warp
-        const unsigned ring_s = smem_u32(ring);
+        // ================================================================ copy warp
+        // issues the chunk loads as ring slots come back from the consumers; nothing else, so
+        // that up to (nchunk - live chunks) loads are in flight whatever the flag warp is doing
+        if (lane == 0) {
+            const unsigned ring_s = smem_u32(ring);
+            int slot = 0;
+            unsigned par = 0;   // parity of the `empty` phase that frees the slot for its next use
+            for (int j = 0; j < total_chunks; j++) {
+                if (j >= nchunk) mbar_wait_relaxed(bar0 + 8 * (2 * kXtMaxChunks + slot), par);
+                mbar_arrive_expect_tx(bar0 + 8 * slot, (unsigned)chunkB);
+                tma_load_4d(ring_s + slot * chunkB, &tmap, bar0 + 8 * slot, x0 - kXtHalo, r0 + j * kXtCH, z0 - g.wz, vol);
+                XT_T(true, 1 + j);
+                if (++slot == nchunk) { slot = 0; if (j >= nchunk) par ^= 1u; }
+            }
+        }
+        return;
+    }
+    if (warp == kXtWarps + 1) {
+        // ================================================================ flag warp
+        // marks every (plane, row) segment of a landed chunk whose relevant bytes all equal the
+        // block's reference code.  Lane = (segment of the round, 16-byte quarter): the 32 lanes
+        // read 512 consecutive bytes, a ballot folds the four quarters of each segment.
         unsigned ref4;
         {
             const int zz = min(max(z0 - g.wz, 0), g.nz - 1), xx = min(max(x0 - g.wx, 0), g.nx - 1);
             const int yy = min(max(r0, 0), g.ny - 1);
             ref4 = (unsigned)__ldg(codes + (((size_t)vol * g.nz + zz) * g.ny + yy) * g.pitch + xx) * 0x01010101u;
         }
-        // bytes of a window row that matter for the flat test: inside the image and within the
-        // x reach of the ball around the block's 32 voxels
-        unsigned bm[kXtRowB / 4];
+        // bytes of this lane's quarter that matter: inside the image and within the x reach of the
+        // ball around the block's 32 voxels
+        unsigned bm[4];
 #pragma unroll
-        for (int i = 0; i < kXtRowB / 4; i++) {
+        for (int i = 0; i < 4; i++) {
             bm[i] = 0;
 #pragma unroll
             for (int b = 0; b < 4; b++) {
-                const int wxo = 4 * i + b, xa = x0 - kXtHalo + wxo;
+                const int wxo = 16 * (lane & 3) + 4 * i + b, xa = x0 - kXtHalo + wxo;
                 if (xa >= 0 && xa < g.nx && wxo >= kXtHalo - g.wx && wxo < kXtHalo + 32 + g.wx) bm[i] |= 0xffu << (8 * b);
             }
         }
-        const int nsegm = g.P * kXtCH;   // (plane, row) segments of a chunk
-        int i_slot = 0, f_slot = 0;      // ring slots of the next chunk to issue / to flag
-        unsigned i_par = 1, f_par = 0;   // parity of the `empty` phase to wait for / of the `full` phase
-        for (int j = 0; j < total_chunks + kXtLook; j++) {
-            if (j < total_chunks) {
-                if (j >= nchunk) mbar_wait(bar0 + 8 * (2 * kXtMaxChunks + i_slot), i_par);
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(bar0 + 8 * i_slot, (unsigned)chunkB);
-                    tma_load_4d(ring_s + i_slot * chunkB, &tmap, bar0 + 8 * i_slot, x0 - kXtHalo, r0 + j * kXtCH, z0 - g.wz, vol);
-                }
-                if (++i_slot == nchunk) { i_slot = 0; if (j >= nchunk) i_par ^= 1u; else i_par = 0u; }
-            }
-            if (j >= kXtLook) {
-                mbar_wait(bar0 + 8 * f_slot, f_par);
-                // flat flags of the chunk's segments: 16 words each against ref4
-                unsigned m = 0;   // lanes 0..3: plane mask of ring row 4*slot + lane
-                for (int q = 0; q * 32 < nsegm; q++) {
-                    const int sgm = q * 32 + lane;
-                    bool flat = true;
-                    if (sgm < nsegm) {
-                        const int p = sgm >> 2, rr = sgm & 3;
-                        const int zz = z0 - g.wz + p;
-                        if (zz >= 0 && zz < g.nz) {
-                            const uint4* w = reinterpret_cast<const uint4*>(ring + (size_t)f_slot * chunkB + (p * kXtCH + rr) * kXtRowB);
-                            unsigned diff = 0;
+        const int nsegm = g.P * kXtCH;   // (plane, row) segments of a chunk, 8 per round
+        int slot = 0;
+        unsigned par = 0;
+        for (int j = 0; j < total_chunks; j++) {
+            mbar_wait(bar0 + 8 * slot, par);
+            XT_T(lane == 0, 100 + j);
+            const uint4* cbase = reinterpret_cast<const uint4*>(ring + (size_t)slot * chunkB);
+            unsigned m = 0;   // lanes 0..3: plane mask of ring row 4*slot + lane
+            for (int q0 = 0; q0 * 8 < nsegm; q0 += 4) {   // four rounds (8 planes) per trip: loads first
+                uint4 v[4];
+                bool need[4];
 #pragma unroll
-                            for (int i = 0; i < kXtRowB / 16; i++) {
-                                const uint4 v = w[i];
-                                diff |= ((v.x ^ ref4) & bm[4 * i]) | ((v.y ^ ref4) & bm[4 * i + 1]) |
-                                        ((v.z ^ ref4) & bm[4 * i + 2]) | ((v.w ^ ref4) & bm[4 * i + 3]);
-                            }
-                            flat = diff == 0;
-                        }
-                    }
-                    const unsigned bal = __ballot_sync(0xffffffffu, flat);
-                    if (lane < 4)
-                        for (int pp = 0; pp < 8; pp++) m |= ((bal >> (4 * pp + lane)) & 1u) << (8 * q + pp);
+                for (int u = 0; u < 4; u++) {
+                    const int sgm = (q0 + u) * 8 + (lane >> 2);   // plane 2q + (lane >> 4), row (lane >> 2) & 3
+                    const int zz = z0 - g.wz + (sgm >> 2);
+                    need[u] = sgm < nsegm && zz >= 0 && zz < g.nz;
+                    v[u] = need[u] ? cbase[(q0 + u) * 32 + lane] : make_uint4(ref4, ref4, ref4, ref4);
                 }
-                if (lane < 4) rowmask[f_slot * kXtCH + lane] = m;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar0 + 8 * (kXtMaxChunks + f_slot));
-                if (++f_slot == nchunk) { f_slot = 0; f_par ^= 1u; }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const bool flat = ((((v[u].x ^ ref4) & bm[0]) | ((v[u].y ^ ref4) & bm[1]) | ((v[u].z ^ ref4) & bm[2]) |
+                                        ((v[u].w ^ ref4) & bm[3])) == 0);
+                    const unsigned bal = __ballot_sync(0xffffffffu, flat);
+                    // row `lane & 3` of planes 2q and 2q+1: quarters at bits 4*row .. 4*row+3 (+16)
+                    const int sh = 4 * (lane & 3), q = q0 + u;
+                    m |= (((bal >> sh) & 0xfu) == 0xfu ? 1u : 0u) << (2 * q);
+                    m |= (((bal >> (16 + sh)) & 0xfu) == 0xfu ? 1u : 0u) << (2 * q + 1);
+                }
             }
+            if (lane < 4) rowmask[slot * kXtCH + lane] = m;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 8 * (kXtMaxChunks + slot));
+            XT_T(lane == 0, 200 + j);
+            if (++slot == nchunk) { slot = 0; par ^= 1u; }
         }
         return;
     }
@@ -633,7 +666,9 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
     // byte offset of ring row `rel` (general form, used outside the loop)
     auto rowoff = [&](int rel) { return (unsigned)(((rel >> 2) % nchunk) * chunkB + (rel & 3) * kXtRowB); };
 
+    XT_T(tid == 0, 300);
     ensure(wy2);
+    XT_T(tid == 0, 301);
     for (int rel = 0; rel <= wy2; rel++) examine_next();
     unsigned S = 0;   // sum over ALL codes (the dummy code 0 included) of h^2
     if (wactive) {
@@ -666,6 +701,7 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
         }
     }
 
+    XT_T(tid == 0, 302);
     float res = 0.0f;
     bool dirty = true;    // warp-uniform: histograms changed since the last coefficient
     int slot_t = 0;       // ring slot of the chunk that holds row t
@@ -673,12 +709,23 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
         if (wactive && dirty) {
             const unsigned hd = hist[tid];   // not-counted voxels of the ball (code 0)
             unsigned long long P = 0;
+            // four codes per trip: one broadcast LDS.128 of the region histogram, four counter loads;
+            // codes beyond chi (up to the padded end of h2s) meet zeros of h2s
             if (p32) {
                 unsigned P32 = 0;
-                for (int c = vs.clo; c <= vs.chi; c++) P32 += hist[c * kXtCons + tid] * h2s[c];
+                for (int c = vs.clo & ~3; c <= vs.chi; c += 4) {
+                    const uint4 w = *reinterpret_cast<const uint4*>(h2s + c);
+                    const unsigned* hc = hist + c * kXtCons + tid;
+                    P32 += hc[0] * w.x + hc[kXtCons] * w.y + hc[2 * kXtCons] * w.z + hc[3 * kXtCons] * w.w;
+                }
                 P = P32;
             } else {
-                for (int c = vs.clo; c <= vs.chi; c++) P += (unsigned long long)hist[c * kXtCons + tid] * h2s[c];
+                for (int c = vs.clo & ~3; c <= vs.chi; c += 4) {
+                    const uint4 w = *reinterpret_cast<const uint4*>(h2s + c);
+                    const unsigned* hc = hist + c * kXtCons + tid;
+                    P += (unsigned long long)hc[0] * w.x + (unsigned long long)hc[kXtCons] * w.y +
+                         (unsigned long long)hc[2 * kXtCons] * w.z + (unsigned long long)hc[3 * kXtCons] * w.w;
+                }
             }
             const long long n1 = (long long)g.ball - (long long)hd;
             const long long s11 = (long long)(S - hd * hd);
@@ -690,10 +737,12 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
             dirty = false;
         }
         const int tq = t & 3;
+        XT_T(tid == 0, 400 + t);
         // ---- four steps at once where nothing changes: the next four rows are flat as well, so
         // the slides t .. t+3 move nothing and rows t .. t+3 all get the current coefficient
         if (tq == 0 && t + 4 < T && run >= wy2 + 1) {
             ensure(t + wy2 + 4);
+            XT_T(tid == 0, 600 + t);
             int i1 = x_idx + 1, i2 = x_idx + 2, i3 = x_idx + 3;
             if (i1 >= x_lim) i1 -= x_lim;
             if (i2 >= x_lim) i2 -= x_lim;
@@ -953,7 +1002,7 @@ static int xcorr_run(OpGuard& og, Scratch& sc, Image* A, const uint8_t* d_codes,
     }
     // ---- the TMA kernel: window 16 + 32 + 16 voxels wide, 6 + 2 wz planes, ring of 4-row chunks
     const int P = kXtWarps + 2 * wz;
-    const int nchunk = 4 + wy / 2;   // live chunks (2 + wy/2) + kXtLook in flight
+    const int nchunk = 2 + wy / 2 + kXtLook;   // live chunks (2 + wy/2) + kXtLook in flight
     std::vector<unsigned> tcols;
     XtGeo g;
     memset(&g, 0, sizeof(g));
@@ -975,7 +1024,7 @@ static int xcorr_run(OpGuard& og, Scratch& sc, Image* A, const uint8_t* d_codes,
     const int nbin = k + 1;
     const size_t chunkB = (size_t)P * kXtCH * kXtRowB;
     const size_t smem_tma = 128 + nchunk * chunkB +
-                            sizeof(unsigned) * ((size_t)nbin * kXtCons + ((nbin + 3) & ~3) + ((tcols.size() + 3) & ~(size_t)3) +
+                            sizeof(unsigned) * ((size_t)((nbin + 3) & ~3) * kXtCons + ((nbin + 3) & ~3) + ((tcols.size() + 3) & ~(size_t)3) +
                                                 kXtMaxChunks * kXtCH) +
                             sizeof(unsigned long long) * 3 * kXtMaxChunks + sizeof(int) * 34;
     tma_ok = tma_ok && smem_tma <= 227 * 1024;
@@ -1145,6 +1194,13 @@ extern "C" int32_t vx_cross_correlation_h2(vx_ctx ctx, vx_img a, const uint64_t*
     VX_TRY(xcorr_codes(og, sc, A, d_edges, k, &d_codes));
     return xcorr_run(og, sc, A, d_codes, d_h2, rho, k, out);
 }
+
+#ifdef XT_TRACE
+extern "C" __attribute__((visibility("default"))) int32_t vx_debug_xt_trace(long long* out) {
+    cudaDeviceSynchronize();
+    return (int32_t)cudaMemcpyFromSymbol(out, vx::xt_trace, sizeof(long long) * 1024);
+}
+#endif
 
 // Host-only helper (no device needed): the k+1 break points of the crossCorrelation binning for
 // one (m, M), as used by the kernels.  Exposed so the exactness of the table can be tested on
