@@ -119,12 +119,12 @@ class ClockSampler:
 
 
 def make_batch(batch: int, rank: int, shape=BRATS) -> np.ndarray:
-    """`batch` distinct BraTS-like volumes: up to 4 generated (seeds per SURVEY 8d config 5),
-    the rest are axis flips of them (distinct data, identical statistics; generation of
-    a full-size volume costs ~1 s of host time)."""
-    from voxlogica_b200.synth import brats_like
+    """`batch` distinct BraTS-like volumes as a file holds them: int16 voxels (scl_slope 1/4095).
+    Up to 4 are generated (seeds per SURVEY 8d config 5), the rest are axis flips of them (distinct
+    data, identical statistics; generating a full-size volume costs ~1 s of host time)."""
+    from voxlogica_b200.synth import brats_like_int16
     uniq = min(batch, 4)
-    base = [brats_like(seed=rank * 64 + i, shape=shape) for i in range(uniq)]
+    base = [brats_like_int16(seed=rank * 64 + i, shape=shape)[0] for i in range(uniq)]
     vols = []
     for i in range(batch):
         v = base[i % uniq]
@@ -146,8 +146,9 @@ def cpu_gtv_sample(n_threads: int, shape, seed=1234):
     os.environ["OMP_NUM_THREADS"] = str(n_threads)
     import oracle as orc
     from gtv_ref import gtv_oracle
-    from voxlogica_b200.synth import brats_like
-    vol = brats_like(seed=seed, shape=shape)
+    from voxlogica_b200.synth import brats_like_int16, int16_to_f32
+    raw, slope = brats_like_int16(seed=seed, shape=shape)
+    vol = int16_to_f32(raw, slope)      # the f32 image the GPU arm forms on the device from the same int16 voxels
     orc.lib()
     t0 = time.perf_counter()
     gtv_oracle(orc, vol)
@@ -204,28 +205,54 @@ def run_reference(args):
     }), flush=True)
 
 
+def _cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        part = part.strip()
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
 def bind_to_gpu_numa(local: int):
-    """Best effort: run this rank (and allocate its pinned staging buffers) on the NUMA node its GPU
-    hangs off, so the host<->device copies of the e2e path do not cross the socket interconnect.
-    Returns a short description for the JSON line; silently does nothing where sysfs says nothing."""
+    """Run this rank (and allocate its pinned staging buffers) on the CPUs next to its GPU, so that the
+    host<->device copies of the e2e path do not cross the socket interconnect.  Source of the
+    affinity: sysfs numa_node of the GPU's PCI function; where the (virtualised) host reports -1
+    there, the "CPU Affinity" column of `nvidia-smi topo -m`.  Returns a description for the JSON line."""
     try:
         import torch
         pr = torch.cuda.get_device_properties(local)
         dev = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
-        node = int(open(f"/sys/bus/pci/devices/{dev}/numa_node").read().strip())
-        if node < 0:
-            return f"{dev}: numa_node unknown"
-        cpus = set()
-        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
+        cpus, how = set(), ""
+        try:
+            node = int(open(f"/sys/bus/pci/devices/{dev}/numa_node").read().strip())
+        except OSError:
+            node = -1
+        if node >= 0:
+            cpus = _cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read())
+            how = f"sysfs node {node}"
+        else:
+            out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+            import re
+            out = re.sub(r"\x1b\[[0-9;]*m", "", out)
+            lines = [ln for ln in out.splitlines() if ln.strip()]
+            hdr = [h.strip() for h in lines[0].split("\t")]
+            col = hdr.index("CPU Affinity")
+            for ln in lines[1:]:
+                f = [x.strip() for x in ln.split("\t")]
+                if f and f[0] == f"GPU{local}" and len(f) > col:
+                    cpus = _cpulist(f[col])
+                    how = "nvidia-smi topo CPU affinity"
+                    break
         cpus &= os.sched_getaffinity(0)
         if not cpus:
-            return f"{dev}: node {node} has no allowed cpu"
+            return f"{dev}: no usable affinity ({how or 'none reported'})"
         os.sched_setaffinity(0, cpus)
-        return f"{dev}: node {node}, {len(cpus)} cpus"
+        return f"{dev}: {how}, {len(cpus)} cpus ({min(cpus)}-{max(cpus)})"
     except Exception as e:  # pragma: no cover
-        return f"unavailable ({type(e).__name__})"
+        return f"unavailable ({type(e).__name__}: {e})"
 
 
 # --------------------------------------------------------------------------------- GPU arm
@@ -243,12 +270,13 @@ def run_ours(args):
     from voxlogica_b200 import Context
     from voxlogica_b200.imgql import run_gtv
 
-    numa = bind_to_gpu_numa(local) if world > 1 else "not bound (single rank)"
+    numa = bind_to_gpu_numa(local)
     ctx = Context(local)
     B = args.batch
     shape4 = (B,) + BRATS
-    host = make_batch(B, rank)
-    in_bytes, out_bytes = host.nbytes, B * NVOX
+    from voxlogica_b200.synth import INT16_SLOPE
+    host = make_batch(B, rank)                      # int16 voxels, as a NIfTI file holds them
+    in_bytes, out_bytes = host.nbytes, (B * NVOX + 7) // 8
 
     def barrier():
         if dist is not None:
@@ -266,7 +294,7 @@ def run_ours(args):
     # different threads overlap on the device, which fills the bubbles around the host-visible
     # scalars (min/max of the input, volume(gtv)) that every step has to wait for.
     import threading
-    flair = ctx.upload(host)
+    flair = ctx.upload_scaled(host, INT16_SLOPE)    # f32 in HBM = fl(raw * slope), formed on the device
     ctx.sync()
     nres = max(1, args.threads)
     last = [None] * nres
@@ -319,17 +347,17 @@ def run_ours(args):
     import threading
     del flair
     nthr = max(1, args.threads)
-    pins_in = [ctx.host_alloc(B * NVOX * 4, write_combined=args.wc) for _ in range(nthr)]
-    pins_out = [ctx.host_alloc(B * NVOX) for _ in range(nthr)]
+    pins_in = [ctx.host_alloc(host.nbytes, write_combined=args.wc) for _ in range(nthr)]
+    pins_out = [ctx.host_alloc(out_bytes) for _ in range(nthr)]
     for t in range(nthr):
         C.memmove(pins_in[t], host.ctypes.data, host.nbytes)
 
     def e2e_worker(t, nsteps, errors):
         try:
             for _ in range(t, nsteps, nthr):
-                f = ctx.upload_ptr(pins_in[t], np.float32, shape4)
+                f = ctx.upload_scaled_ptr(pins_in[t], np.int16, shape4, INT16_SLOPE)
                 out = run_gtv(ctx, f)
-                ctx.download_ptr(out["gtv"], pins_out[t], B * NVOX)
+                ctx.download_bits_ptr(out["gtv"], pins_out[t], out_bytes)
         except Exception as e:  # pragma: no cover
             errors.append(e)
 
@@ -343,6 +371,15 @@ def run_ours(args):
 
     run_e2e(2 * nthr)
     barrier()
+    # achieved host->device bandwidth of this rank with every rank copying at once (what bounds e2e
+    # when the host fabric is shared): five uploads of the batch from pinned memory, untimed otherwise
+    t0 = time.perf_counter()
+    for _ in range(5):
+        f = ctx.upload_scaled_ptr(pins_in[0], np.int16, shape4, INT16_SLOPE)
+        del f
+    ctx.sync()
+    h2d_gbs = 5 * host.nbytes / (time.perf_counter() - t0) / 1e9
+    barrier()
     t0 = time.perf_counter()
     run_e2e(args.steps)
     ctx.sync()
@@ -355,7 +392,7 @@ def run_ours(args):
     # so the per-launch times there include waiting for SMs held by other steps' kernels.)
     serial = {}
     if rank == 0:
-        flair = ctx.upload(host)
+        flair = ctx.upload_scaled(host, INT16_SLOPE)
         ctx.sync()
         step_resident(flair)
         ctx.sync()
@@ -423,10 +460,13 @@ def run_ours(args):
         "config": {"workload": WORKLOAD,
                    "volumes_per_step_per_gpu": B, "voxels_per_volume": NVOX, "adjacency": 26,
                    "sharding": "independent volumes per GPU, no collective", "host_threads": nres,
-                   "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB f32 batch per step)",
+                   "l2": f"inputs larger than L2 ({B * NVOX * 4 / 1e6:.0f} MB f32 batch per step)",
+                   "input": "int16 voxels with scl_slope 1/4095 (a NIfTI file's content); the f32 image is formed on "
+                            "the device by vx_upload_scaled, bit-identical to converting on the host",
                    "data_note": "min(batch,4) generated volumes per rank + axis flips"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                 "ms_per_step": ms_e2e / args.steps, "host_threads": nthr, "numa": numa,
+                "h2d_gbs_this_rank_all_ranks_copying": round(h2d_gbs, 2),
                 "timing": "host perf_counter around K steps with all streams synchronised on both sides"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -62,6 +62,9 @@ typedef uint64_t vx_evt; /* opaque timing event                         */
 #define VX_U8 1  /* boolean valuation, 0 or 1           */
 #define VX_F32 2 /* numeric valuation                    */
 #define VX_U32 3 /* component labels (vx_components)     */
+/* host-side voxel types accepted by vx_upload_scaled only (a file's native 16-bit integers) */
+#define VX_I16 4
+#define VX_U16 5
 
 /* comparison operators for vx_cmp / vx_cmp_scalar (ImgQL  <.  <=.  >.  >=.  =.) */
 #define VX_LT 0
@@ -109,8 +112,21 @@ VX_API int32_t vx_upload(vx_ctx ctx, const void* host, int32_t dtype, int32_t nx
                          int32_t nz, const float* spacing, vx_img* out);
 VX_API int32_t vx_upload_batch(vx_ctx ctx, const void* host, int32_t dtype, int32_t nx, int32_t ny,
                                int32_t nz, int32_t nb, const float* spacing, vx_img* out);
+/* Upload of a file's native 16-bit voxels (NIfTI datatype 4 INT16 / 512 UINT16, Greta.pdf p.48
+ * `load flair = "flair.nii.gz"`) together with the header's scl_slope / scl_inter: the numeric image
+ *     fl( fl( (float)raw * slope ) + inter )
+ * is formed on the device -- two binary32 roundings, no fused multiply-add, bit-identical to
+ * converting on the host and uploading f32 -- so the host->device copy moves 2 bytes per voxel
+ * instead of 4.  host_dtype: VX_I16 or VX_U16; slope 1, inter 0 give the plain conversion. */
+VX_API int32_t vx_upload_scaled(vx_ctx ctx, const void* host, int32_t host_dtype, float slope, float inter,
+                                int32_t nx, int32_t ny, int32_t nz, int32_t nb, const float* spacing,
+                                vx_img* out);
 /* Blocking copy of the whole image to host memory (`bytes` must equal its size). */
 VX_API int32_t vx_download(vx_ctx ctx, vx_img img, void* host, size_t bytes);
+/* Blocking copy of a boolean image as a bit stream: bit (i & 7) of byte (i >> 3) = voxel i of the
+ * batch (x fastest, then y, z, volume), unused bits of the last byte 0; `bytes` must equal
+ * ceil(voxels / 8).  The device->host copy moves 1 bit per voxel instead of 1 byte. */
+VX_API int32_t vx_download_bits(vx_ctx ctx, vx_img img, void* host, size_t bytes);
 /* Any out pointer may be NULL. */
 VX_API int32_t vx_info(vx_img img, int32_t* dtype, int32_t* nx, int32_t* ny, int32_t* nz,
                        int32_t* nb, float* spacing3);

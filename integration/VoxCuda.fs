@@ -46,6 +46,10 @@ module Native =
     [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
     extern int vx_download(uint64 ctx, uint64 img, nativeint host, unativeint bytes)
     [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_upload_scaled(uint64 ctx, nativeint host, int hostDtype, float32 slope, float32 inter, int nx, int ny, int nz, int nb, float32[] spacing, uint64& out)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_download_bits(uint64 ctx, uint64 img, nativeint host, unativeint bytes)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
     extern int vx_info(uint64 img, int& dtype, int& nx, int& ny, int& nz, int& nb, float32[] spacing3)
     [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
     extern int vx_retain(uint64 img)

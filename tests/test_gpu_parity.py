@@ -429,3 +429,33 @@ def test_concurrent_callers(ctx, oracle):
     [t.join() for t in ts]
     assert not errors
     assert all(np.array_equal(r, want) for r in results.values())
+
+
+# ------------------------------------------------------------------ transfers in the file's own width
+@pytest.mark.parametrize("dtype", [np.int16, np.uint16])
+def test_upload_scaled_matches_host_conversion(ctx, dtype):
+    """16-bit voxels + scl_slope/scl_inter converted on the device (vx_upload_scaled) against the host
+    loader's arithmetic raw.astype(f32) * slope + inter: the same bits (two roundings, no FMA)."""
+    rng = np.random.default_rng(41)
+    info = np.iinfo(dtype)
+    for shape in [(2, 5, 7, 13), (1, 3, 16, 24), (1, 1, 1, 1), (3, 2, 3, 5)]:
+        raw = rng.integers(info.min, info.max + 1, size=shape).astype(dtype)
+        raw.flat[0] = info.min
+        raw.flat[-1] = info.max
+        for slope, inter in [(1.0, 0.0), (1.0 / 4095.0, 0.0), (0.0007324442, -3.25), (-2.5, 1e-3), (3.0, 1e6)]:
+            got = ctx.upload_scaled(raw, slope, inter).numpy()
+            want = raw.astype(np.float32) * np.float32(slope) + np.float32(inter)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (shape, slope, inter)
+    with pytest.raises(Exception):
+        ctx.upload_scaled(np.zeros((2, 2, 2), np.int32))
+
+
+def test_download_bits(ctx):
+    rng = np.random.default_rng(43)
+    for shape in [(2, 5, 7, 13), (1, 3, 16, 32), (1, 1, 1, 1), (1, 1, 1, 33), (3, 4, 9, 31)]:
+        a = (rng.random(shape) < 0.4).astype(np.uint8)
+        img = ctx.upload(a)
+        assert np.array_equal(ctx.download_bits(img), a), shape
+    f = ctx.upload(np.zeros((1, 2, 2, 2), np.float32))
+    with pytest.raises(Exception):
+        ctx.download_bits(f)            # boolean images only

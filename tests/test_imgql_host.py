@@ -281,3 +281,30 @@ def test_xcorr_bin_edges_reproduce_the_binning_exactly():
         got = np.searchsorted(e[1:k].astype(np.float64), v.astype(np.float64), side="right")
         got = np.where((v >= e[0]) & (v < e[k]), got, k)
         assert np.array_equal(got, oracle_bin(v, m, M, k)), (m, M, k)
+
+
+def test_nifti_raw_reader_keeps_file_dtype_and_scaling(tmp_path):
+    """read_nifti_raw hands out the file's own voxels + scl_slope/scl_inter (what vx_upload_scaled takes);
+    read_nifti is the same data converted on the host."""
+    import struct
+
+    from voxlogica_b200 import io
+    a = np.random.default_rng(3).integers(0, 4096, size=(4, 5, 6)).astype(np.int16)
+    p = str(tmp_path / "v.nii.gz")
+    io.write_nifti(p, a, (1.0, 1.5, 2.0))
+    raw, slope, inter, sp = io.read_nifti_raw(p)
+    assert raw.dtype == np.int16 and np.array_equal(raw, a) and (slope, inter) == (1.0, 0.0) and sp == (1.0, 1.5, 2.0)
+    # patch scl_slope / scl_inter into the header
+    import gzip
+    blob = bytearray(gzip.open(p, "rb").read())
+    struct.pack_into("<ff", blob, 112, 1.0 / 4095.0, 0.25)
+    p2 = str(tmp_path / "w.nii")
+    open(p2, "wb").write(bytes(blob))
+    raw, slope, inter, _ = io.read_nifti_raw(p2)
+    arr, _ = io.read_nifti(p2)
+    assert np.array_equal(raw, a)
+    assert np.array_equal(arr, a.astype(np.float32) * np.float32(slope) + np.float32(inter))
+    struct.pack_into("<ff", blob, 112, 0.0, 5.0)      # slope 0: "no scaling" (NIfTI-1), inter ignored
+    open(p2, "wb").write(bytes(blob))
+    arr, _ = io.read_nifti(p2)
+    assert np.array_equal(arr, a.astype(np.float32))

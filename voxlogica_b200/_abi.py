@@ -19,6 +19,7 @@ VX_OK = 0
 VX_E_INVALID_ARG, VX_E_SHAPE_MISMATCH, VX_E_DTYPE, VX_E_OOM = -1, -2, -3, -4
 VX_E_CUDA, VX_E_NCCL, VX_E_UNSUPPORTED = -5, -6, -7
 VX_U8, VX_F32, VX_U32 = 1, 2, 3
+VX_I16, VX_U16 = 4, 5   # host-side voxel types of vx_upload_scaled
 VX_LT, VX_LE, VX_GT, VX_GE, VX_EQ, VX_NE = range(6)
 VX_ADD, VX_SUB, VX_MUL, VX_DIV, VX_RSUB, VX_RDIV, VX_MIN, VX_MAX = range(8)
 VX_CONN_FACE, VX_CONN_FULL = 6, 26
@@ -53,7 +54,9 @@ SIGNATURES = {
     "vx_sync": [u64],
     "vx_upload": [u64, C.c_void_p, i32, i32, i32, i32, P(f32), P(u64)],
     "vx_upload_batch": [u64, C.c_void_p, i32, i32, i32, i32, i32, P(f32), P(u64)],
+    "vx_upload_scaled": [u64, C.c_void_p, i32, f32, f32, i32, i32, i32, i32, P(f32), P(u64)],
     "vx_download": [u64, u64, C.c_void_p, C.c_size_t],
+    "vx_download_bits": [u64, u64, C.c_void_p, C.c_size_t],
     "vx_info": [u64, P(i32), P(i32), P(i32), P(i32), P(i32), P(f32)],
     "vx_retain": [u64],
     "vx_release": [u64],

@@ -403,6 +403,58 @@ int OpGuard::finish_scalar() {
     return VX_OK;
 }
 
+// ---- transfer kernels ---------------------------------------------------------
+// raw 16-bit voxels -> f32 with the file's slope/intercept, one rounding per operation (the host
+// loader computes raw.astype(f32) * slope + inter the same way); 8 voxels per thread
+template <typename T>
+__global__ void __launch_bounds__(256)
+convert16_kernel(const T* __restrict__ raw, float* __restrict__ out, size_t n, float slope, float inter) {
+    const size_t ng = n >> 3;
+    for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < ng; g += (size_t)gridDim.x * 256) {
+        const uint4 w = __ldg(reinterpret_cast<const uint4*>(raw) + g);
+        const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const T lo = (T)(ww[i] & 0xffffu), hi = (T)(ww[i] >> 16);
+            f[2 * i] = __fadd_rn(__fmul_rn((float)lo, slope), inter);
+            f[2 * i + 1] = __fadd_rn(__fmul_rn((float)hi, slope), inter);
+        }
+        float4* o = reinterpret_cast<float4*>(out) + 2 * g;
+        o[0] = make_float4(f[0], f[1], f[2], f[3]);
+        o[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {   // tail
+        const size_t i = (ng << 3) + threadIdx.x;
+        out[i] = __fadd_rn(__fmul_rn((float)raw[i], slope), inter);
+    }
+}
+
+// boolean image -> bit stream, 32 voxels per thread (two 16-byte loads, one word out)
+__global__ void __launch_bounds__(256)
+pack_stream_kernel(const uint8_t* __restrict__ a, unsigned* __restrict__ bits, size_t n) {
+    const size_t nw = (n + 31) >> 5;
+    for (size_t w = (size_t)blockIdx.x * 256 + threadIdx.x; w < nw; w += (size_t)gridDim.x * 256) {
+        unsigned out = 0;
+        if ((w << 5) + 32 <= n) {
+            const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(a) + 2 * w);
+            const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(a) + 2 * w + 1);
+            const unsigned ww[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                // bytes are 0/1 (any non-zero counts): gather the four low bits of the word
+                unsigned t = ww[i];
+                t = (t | (t >> 1) | (t >> 2) | (t >> 3) | (t >> 4) | (t >> 5) | (t >> 6) | (t >> 7)) & 0x01010101u;
+                out |= ((t * 0x01020408u) >> 24 & 0xfu) << (4 * i);
+            }
+        } else {
+            for (int i = 0; i < 32; i++)
+                if ((w << 5) + i < n && a[(w << 5) + i]) out |= 1u << i;
+        }
+        bits[w] = out;
+    }
+}
+
 }  // namespace vx
 
 using namespace vx;
@@ -481,6 +533,60 @@ int32_t vx_upload_batch(vx_ctx ctx, const void* host, int32_t dtype, int32_t nx,
 int32_t vx_upload(vx_ctx ctx, const void* host, int32_t dtype, int32_t nx, int32_t ny, int32_t nz,
                   const float* spacing, vx_img* out) {
     return vx_upload_batch(ctx, host, dtype, nx, ny, nz, 1, spacing, out);
+}
+
+int32_t vx_upload_scaled(vx_ctx ctx, const void* host, int32_t host_dtype, float slope, float inter,
+                         int32_t nx, int32_t ny, int32_t nz, int32_t nb, const float* spacing, vx_img* out) {
+    VX_REQUIRE(host != nullptr && out != nullptr, VX_E_INVALID_ARG, "NULL argument");
+    VX_REQUIRE(host_dtype == VX_I16 || host_dtype == VX_U16, VX_E_DTYPE,
+               "vx_upload_scaled takes VX_I16 or VX_U16 voxels, not dtype %d", host_dtype);
+    OpGuard g;
+    VX_TRY(g.begin(ctx));
+    Image* im = nullptr;
+    VX_TRY(new_image(g.c, VX_F32, nx, ny, nz, nb, spacing, &im));
+    const size_t n = im->count();
+    Scratch sc(g.c, g.s);
+    void* raw = nullptr;
+    int rc = sc.alloc(((n + 7) / 8 * 8) * 2, &raw);
+    if (rc == VX_OK) {
+        cudaError_t e = cudaMemcpyAsync(raw, host, n * 2, cudaMemcpyDefault, g.st);
+        if (e != cudaSuccess) rc = fail(VX_E_CUDA, "upload failed: %s", cudaGetErrorString(e));
+    }
+    if (rc == VX_OK) {
+        const int grid = grid_for(n / 8 + 1, 256, 8);
+        {
+            VX_LAUNCH(g.c, g.s, "convert16_kernel");
+            if (host_dtype == VX_I16)
+                convert16_kernel<short><<<grid, 256, 0, g.st>>>((const short*)raw, (float*)im->d, n, slope, inter);
+            else
+                convert16_kernel<unsigned short><<<grid, 256, 0, g.st>>>((const unsigned short*)raw, (float*)im->d, n, slope, inter);
+        }
+        rc = check_launch("convert16_kernel");
+    }
+    if (rc != VX_OK) { drop(im); return rc; }
+    return g.finish(im, out);
+}
+
+int32_t vx_download_bits(vx_ctx ctx, vx_img img, void* host, size_t bytes) {
+    VX_REQUIRE(host != nullptr, VX_E_INVALID_ARG, "host is NULL");
+    OpGuard g;
+    VX_TRY(g.begin(ctx));
+    Image* im = nullptr;
+    VX_TRY(g.input(img, &im, VX_U8));
+    const size_t n = im->count();
+    VX_REQUIRE(bytes == (n + 7) / 8, VX_E_INVALID_ARG, "download size %zu != ceil(%zu voxels / 8) = %zu", bytes, n,
+               (n + 7) / 8);
+    Scratch sc(g.c, g.s);
+    unsigned* bits = nullptr;
+    VX_TRY(sc.alloc(((n + 31) / 32) * 4, &bits));
+    {
+        VX_LAUNCH(g.c, g.s, "pack_stream_kernel");
+        pack_stream_kernel<<<grid_for((n + 31) / 32, 256, 8), 256, 0, g.st>>>((const uint8_t*)im->d, bits, n);
+    }
+    VX_TRY(check_launch("pack_stream_kernel"));
+    VX_CUDA(cudaMemcpyAsync(host, bits, bytes, cudaMemcpyDefault, g.st));
+    VX_CUDA(cudaStreamSynchronize(g.st));
+    return g.finish_scalar();
 }
 
 int32_t vx_download(vx_ctx ctx, vx_img img, void* host, size_t bytes) {

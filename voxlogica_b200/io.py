@@ -28,6 +28,18 @@ def _open(path: str, mode: str):
 
 def read_nifti(path: str) -> Tuple[np.ndarray, Tuple[float, float, float]]:
     """-> (f32 array [nz][ny][nx] (or [nt]... squeezed to 3D), (sx, sy, sz))"""
+    data, slope, inter, sp = read_nifti_raw(path)
+    arr = data.astype(np.float32)
+    if slope != 1.0 or inter != 0.0:
+        arr = arr * np.float32(slope) + np.float32(inter)
+    return np.ascontiguousarray(arr), sp
+
+
+def read_nifti_raw(path: str):
+    """-> (voxels in the file's own dtype [nz][ny][nx] (native byte order), slope, inter, (sx, sy, sz)) with
+    value = voxel * slope + inter (slope 1, inter 0 when the header asks for no scaling).  16-bit
+    files can go to the GPU as they are: ``Context.upload_scaled(raw, slope, inter)`` halves the
+    host->device bytes and gives the same f32 image as ``read_nifti`` + ``upload``."""
     with _open(path, "rb") as f:
         raw = f.read()
     if len(raw) < 348:
@@ -62,11 +74,11 @@ def read_nifti(path: str) -> Tuple[np.ndarray, Tuple[float, float, float]]:
     dt = np.dtype(_NIFTI_DTYPES[datatype]).newbyteorder(end)
     n = nx * ny * nz
     data = np.frombuffer(raw, dtype=dt, count=n, offset=max(vox_offset, 352))
-    arr = data.reshape(nz, ny, nx).astype(np.float32)
-    if slope not in (0.0, 1.0) or (inter != 0.0 and slope != 0.0):
-        arr = arr * np.float32(slope) + np.float32(inter)
+    data = np.ascontiguousarray(data.reshape(nz, ny, nx).astype(dt.newbyteorder("=")))
+    if slope == 0.0:      # NIfTI-1: a zero slope means "no scaling"
+        slope, inter = 1.0, 0.0
     sp = tuple(float(abs(p)) if p != 0 else 1.0 for p in pixdim[1:4])
-    return np.ascontiguousarray(arr), sp
+    return data, float(slope), float(inter), sp
 
 
 def write_nifti(path: str, arr: np.ndarray, spacing=(1.0, 1.0, 1.0)) -> None:

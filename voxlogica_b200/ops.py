@@ -140,6 +140,43 @@ class Context:
                                        nz, nb, sp, C.byref(out)))
         return Image(self, out.value)
 
+    def upload_scaled(self, raw: np.ndarray, slope: float = 1.0, inter: float = 0.0,
+                      spacing: Optional[Sequence[float]] = None) -> Image:
+        """16-bit file voxels (int16 / uint16, [nz][ny][nx] or batched 4D) -> f32 image
+        ``fl(fl(raw * slope) + inter)`` formed on the device: half the host->device bytes of an f32
+        upload, the same bits as ``raw.astype(f32) * f32(slope) + f32(inter)`` on the host."""
+        raw = np.asarray(raw)
+        if raw.dtype not in (np.int16, np.uint16):
+            raise TypeError("upload_scaled takes int16 or uint16 voxels")
+        if raw.ndim == 2:
+            raw = raw[None, None]
+        elif raw.ndim == 3:
+            raw = raw[None]
+        elif raw.ndim != 4:
+            raise ValueError("expected a 2D, 3D or batched 4D array")
+        raw = np.ascontiguousarray(raw)
+        return self.upload_scaled_ptr(raw.ctypes.data, raw.dtype, raw.shape, slope, inter, spacing)
+
+    def upload_scaled_ptr(self, ptr: int, dtype, shape, slope: float = 1.0, inter: float = 0.0, spacing=None) -> Image:
+        nb, nz, ny, nx = shape
+        sp = (A.f32 * 3)(*(spacing if spacing is not None else (1.0, 1.0, 1.0)))
+        code = A.VX_I16 if np.dtype(dtype) == np.int16 else A.VX_U16
+        out = A.u64()
+        check(self.lib.vx_upload_scaled(self.handle, C.c_void_p(ptr), code, float(slope), float(inter), nx, ny, nz,
+                                        nb, sp, C.byref(out)))
+        return Image(self, out.value)
+
+    def download_bits(self, img: Image) -> np.ndarray:
+        """boolean image -> u8 array [nb][nz][ny][nx] through the 1-bit-per-voxel transfer"""
+        dt, nx, ny, nz, nb, _ = img.info()
+        n = nb * nz * ny * nx
+        packed = np.empty((n + 7) // 8, np.uint8)
+        check(self.lib.vx_download_bits(self.handle, img.handle, packed.ctypes.data_as(C.c_void_p), packed.nbytes))
+        return np.unpackbits(packed, count=n, bitorder="little").reshape(nb, nz, ny, nx)
+
+    def download_bits_ptr(self, img: Image, ptr: int, nbytes: int) -> None:
+        check(self.lib.vx_download_bits(self.handle, img.handle, C.c_void_p(ptr), nbytes))
+
     def download(self, img: Image, out: Optional[np.ndarray] = None) -> np.ndarray:
         dt, nx, ny, nz, nb, _ = img.info()
         if out is None:

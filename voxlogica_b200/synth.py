@@ -57,6 +57,25 @@ def brats_like(seed: int = 1234, shape=BRATS_SHAPE) -> np.ndarray:
     return np.clip(vol, 0.0, 1.0).astype(np.float32)
 
 
+INT16_SCALE = 4095          # 12-bit acquisition range, as stored in a 16-bit NIfTI file
+INT16_SLOPE = np.float32(1.0 / INT16_SCALE)
+
+
+def brats_like_int16(seed: int = 1234, shape=BRATS_SHAPE):
+    """The same synthetic volume as a scanner / NIfTI file holds it: int16 voxels in [0, 4095] plus
+    the header's scl_slope (1/4095, scl_inter 0) that maps them back to [0, 1].  Returns
+    (raw int16 [nz][ny][nx], slope); the numeric image every arm works on is
+    ``raw.astype(f32) * slope`` (int16_to_f32), formed on the host or -- bit-identically -- by
+    vx_upload_scaled on the device."""
+    v = brats_like(seed, shape)
+    return np.rint(v * np.float32(INT16_SCALE)).astype(np.int16), INT16_SLOPE
+
+
+def int16_to_f32(raw: np.ndarray, slope=INT16_SLOPE, inter=0.0) -> np.ndarray:
+    """host-side twin of vx_upload_scaled: two binary32 roundings, multiply then add"""
+    return raw.astype(np.float32) * np.float32(slope) + np.float32(inter)
+
+
 MODALITIES = ("flair", "t1", "t1c", "t2")
 
 
