@@ -1,6 +1,7 @@
-"""Parity at BASELINE.json's full sizes through size-independent properties (the oracle is far too
-slow there) plus independent scipy checks where scipy finishes in seconds:
-BraTS shape 240x240x155 and a 256^3 cube of the config-3 generators."""
+"""Parity at BASELINE.json's full sizes: the whole GTV spec at the BraTS shape 240x240x155 against the
+oracle composition (bit-exact, the f32 maps included; ~10 s of CPU), size-independent properties
+and independent scipy checks, a 256^3 cube and the 512^3 cube of BASELINE config 3 (26-connectivity
+components + exact EDT of the three generators) against scipy.ndimage."""
 import numpy as np
 import pytest
 from scipy import ndimage as ndi
@@ -53,6 +54,24 @@ def test_brats_gtv_properties(ctx, flair):
     assert float(r["_printed"]["gtvVolume"][0]) == float(g["gtv"].sum())
 
 
+def test_brats_gtv_matches_oracle_at_full_size(ctx, oracle):
+    """BASELINE config 2 at its own size (Greta.pdf p.48): every named intermediate of the spec on
+    the benchmark's own input -- int16 voxels with scl_slope, converted on the device -- against the
+    oracle on the host-converted image.  normFlair and tumSim compared as bit patterns."""
+    from gtv_ref import gtv_oracle
+    from voxlogica_b200.imgql import run_gtv
+    from voxlogica_b200.synth import brats_like_int16, int16_to_f32
+    raw, slope = brats_like_int16(seed=1234, shape=BRATS)
+    got = run_gtv(ctx, ctx.upload_scaled(raw[None], slope))
+    want = gtv_oracle(oracle, int16_to_f32(raw, slope))
+    for name in ("background", "brain", "hyperIntense", "veryIntense", "growTum", "tumStatCC", "gtv"):
+        assert np.array_equal(got[name].numpy()[0], want[name]), name
+    for name in ("normFlair", "tumSim"):
+        assert np.array_equal(got[name].numpy()[0].view(np.uint32), want[name].view(np.uint32)), name
+    assert got["_printed"]["gtvVolume"][0] == want["gtv"].sum() > 0
+    assert np.array_equal(ctx.download_bits(got["gtv"])[0], want["gtv"])      # the e2e path's result format
+
+
 def test_brats_batch_equals_single(ctx, flair):
     """one launch over a batch computes exactly what separate launches compute"""
     from voxlogica_b200.imgql import run_gtv
@@ -90,3 +109,34 @@ def test_cube256_ccl_and_edt_vs_scipy(ctx, gen):
     for r in (3.0, 7.5):
         assert np.array_equal(ctx.distlt(r, A).numpy()[0], (want < r).astype(np.uint8))
         assert np.array_equal(ctx.distgeq(r, A).numpy()[0], (want >= r).astype(np.uint8))
+
+
+@pytest.mark.parametrize("gen", ["blobs", "bernoulli05", "bernoulli30", "bernoulli60", "sparse"])
+def test_cube512_ccl_and_edt(ctx, oracle, gen):
+    """BASELINE config 3 at its stated size: one 512^3 volume of every generator of the config.
+    26-connectivity components (partition + canonical labels) against scipy.ndimage.label; the exact
+    EDT of the config's two EDT inputs (blobs, sparse seeds) bit for bit against the CPU oracle (scipy's single-threaded EDT
+    needs 70 s per volume at this size; it checks the same kernels at 256^3 above)."""
+    from voxlogica_b200 import synth
+    shape = (512, 512, 512)
+    a = {"blobs": lambda: synth.blob_volume(shape),
+         "bernoulli05": lambda: synth.bernoulli_volume(shape, 0.05),
+         "bernoulli30": lambda: synth.bernoulli_volume(shape, 0.3),
+         "bernoulli60": lambda: synth.bernoulli_volume(shape, 0.6),
+         "sparse": lambda: synth.bernoulli_volume(shape, 1e-4)}[gen]()
+    A = ctx.upload(a)
+    lab = ctx.components(A, 26).numpy()[0]
+    ref, n = ndi.label(a, S26)
+    assert np.array_equal(lab != 0, a != 0)
+    # canonical labels: 1 + the raster index of the component's first voxel; equality with the
+    # relabelled scipy result proves that the partition is the same
+    first = ndi.minimum(np.arange(a.size, dtype=np.int64).reshape(shape), ref, index=np.arange(1, n + 1))
+    lut = np.zeros(n + 1, np.uint32)
+    lut[1:] = np.asarray(first, dtype=np.int64) + 1
+    assert np.array_equal(lab, lut[ref])
+    del lab, ref, lut, first
+    if gen in ("blobs", "sparse"):       # the EDT inputs of the config: (ii) blobs, (iii) sparse seeds
+        d = ctx.edt(A).numpy()[0]
+        want = oracle.edt(a)
+        assert np.array_equal(d.view(np.uint32), want.view(np.uint32))
+        assert np.array_equal(ctx.distlt(5.0, A).numpy()[0], (want < np.float32(5.0)).astype(np.uint8))

@@ -275,6 +275,9 @@ class Lazy:
     def numpy(self):
         return self.force().numpy()
 
+    def info(self):
+        return self.force().info()
+
     @property
     def handle(self):
         return self.force().handle
