@@ -255,6 +255,116 @@ def bind_to_gpu_numa(local: int):
         return f"unavailable ({type(e).__name__}: {e})"
 
 
+# --------------------------------------------------------------------------------- slab leg (N > 1)
+def slab_leg(ctx, dist, rank, world, local):
+    """BASELINE config 5b: ONE oversized volume slab-decomposed along z over the N ranks, after the
+    timed region.  (1) an on-box check: near26 / through26 / distlt(5) on a 640^3 volume in slabs
+    against the same operators on the whole volume (every rank runs the whole volume on its own GPU
+    and compares its slab, bit for bit); (2) per-operator times on the large volume (1024^3 at N=2,
+    1536^3 at N=4, 2048^3 at N=8) with the bytes each exchange moves over NVLink and the phases
+    of `through`, so that the exchange that dominates it is named."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from slab_gpu import blob_slab
+    from voxlogica_b200.slab import CudaEngine, Slab, SlabComm, SlabOps, slab_bounds
+    dev = f"cuda:{local}"
+    sp = (1.0, 1.0, 1.0)
+    out = {}
+
+    def make(n, ops):
+        z0, z1 = slab_bounds(n, world)[rank]
+        b_t = blob_slab((n, n, n), z0, z1, dev)
+        seed_t = torch.zeros_like(b_t)
+        if rank == 0:
+            seed_t[0] = b_t[0]                     # everything connected to the first plane
+        B = Slab(ctx.from_tensor(b_t[None], spacing=sp), z0, z1, n, sp)
+        A = Slab(ctx.from_tensor(seed_t[None], spacing=sp), z0, z1, n, sp)
+        return b_t, A, B, z0, z1
+
+    # ---- (1) check against the whole volume
+    n = 640
+    ops = SlabOps(CudaEngine(ctx), SlabComm())
+    ops.enable_peer_halo(n, n)
+    b_t, A, B, z0, z1 = make(n, ops)
+    parts = [torch.empty((b - a, n, n), dtype=torch.uint8, device=dev) for a, b in slab_bounds(n, world)]
+    dist.all_gather(parts, b_t)
+    whole = torch.cat(parts)
+    del parts
+    W = ctx.from_tensor(whole[None], spacing=sp)
+    wseed = torch.zeros_like(whole)
+    wseed[0] = whole[0]
+    WS = ctx.from_tensor(wseed[None], spacing=sp)
+    bad = []
+    for name, fs, fw in (("near26", lambda: ops.near(B, 26), lambda: ctx.near(W, 26)),
+                         ("through26", lambda: ops.through(A, B, 26), lambda: ctx.through(WS, W, 26)),
+                         ("distlt5", lambda: ops.distlt(5.0, B), lambda: ctx.distlt(5.0, W))):
+        r_slab, r_whole = fs(), fw()             # keep the images alive while their views are compared
+        got = ctx.as_tensor(r_slab.data)[0]
+        want = ctx.as_tensor(r_whole)[0][z0:z1]
+        ctx.sync()
+        if not torch.equal(got, want):
+            bad.append(name)
+        del got, want, r_slab, r_whole
+    flags = [None] * world
+    dist.all_gather_object(flags, bad)
+    out["check"] = "ok" if not any(flags) else f"FAILED {flags}"
+    out["check_volume"] = f"{n}^3 in {world} z-slabs vs the whole volume on one GPU: near26, through26, distlt(5), bit for bit"
+    del W, WS, whole, wseed, A, B, b_t, ops
+    torch.cuda.empty_cache()
+
+    # ---- (2) the large volume
+    n = {2: 1024, 4: 1536, 8: 2048}.get(world, 1024)
+    ops = SlabOps(CudaEngine(ctx), SlabComm())
+    ops.enable_peer_halo(n, n)
+    b_t, A, B, z0, z1 = make(n, ops)
+    del b_t
+    torch.cuda.empty_cache()
+
+    def timed(fn, reps=3):
+        fn()
+        ts = []
+        for _ in range(reps):
+            ctx.sync(); torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn()
+            ctx.sync(); torch.cuda.synchronize()
+            t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ts.append(float(t[0]))
+        return float(np.median(ts))
+
+    plane = n * n
+    res = {}
+    for name, fn, nvl in (
+            ("near26", lambda: ops.near(B, 26),
+             {"peer_reads_per_interior_rank": 2 * plane, "what": "two u8 boundary planes read from the neighbours' IPC mailboxes"}),
+            ("through26", lambda: ops.through(A, B, 26),
+             {"p2p_send_per_interior_rank": 2 * 8 * plane, "what": "boundary label planes (int64 global ids) to both neighbours, "
+              "then two all-gathers of the cross-slab pairs (16 B each) and reached ids (8 B each)"}),
+            ("distlt5", lambda: ops.distlt(5.0, B),
+             {"p2p_send_per_interior_rank": 2 * 5 * plane, "what": "five u8 halo planes to each neighbour"})):
+        sec = timed(fn)
+        res[name] = {"ms": round(1e3 * sec, 3), "gvox_per_s": round(n ** 3 / sec / 1e9, 2), "nvlink_bytes": nvl}
+    # phases of `through` (device-synchronised after every phase, so their sum exceeds the timed call)
+    ops.trace = {}
+    ops.through(A, B, 26)
+    tr, ops.trace = ops.trace, None
+    phases = {k: round(1e3 * v, 3) for k, v in tr.items() if isinstance(v, float)}
+    tmax = torch.tensor([phases.get(k, 0.0) for k in sorted(phases)], device=dev, dtype=torch.float64)
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    phases = {k: round(float(v), 3) for k, v in zip(sorted(phases), tmax.tolist())}
+    dom = max(phases, key=phases.get) if phases else None
+    res["through26"]["phases_ms_max_over_ranks"] = phases
+    res["through26"]["dominant_phase"] = dom
+    res["through26"]["pairs_gathered"] = tr.get("pairs_gathered")
+    res["through26"]["reached_gathered"] = tr.get("reached_gathered")
+    reached = ops.volume(ops.through(A, B, 26))
+    out.update({"volume": f"{n}^3 u8 (blobs), {world} z-slabs of {n // world} planes", "voxels": n ** 3, "ops": res,
+                "foreground_voxels": ops.volume(B), "reached_from_first_plane": reached,
+                "timing": "host clock around device-synchronised calls, max over ranks, median of 3"})
+    return out
+
+
 # --------------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch
@@ -404,6 +514,13 @@ def run_ours(args):
         serial = ctx.prof_report()
         del flair
 
+    slab = None
+    if dist is not None and not args.no_slab:
+        del pins_in, pins_out
+        try:
+            slab = slab_leg(ctx, dist, rank, world, local)
+        except Exception as e:  # the slab record must never take the bench line down
+            slab = {"error": f"{type(e).__name__}: {e}"}
     if dist is not None:
         t = torch.tensor([ms, ms_e2e], device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -487,6 +604,7 @@ def run_ours(args):
                            "ms_per_step": round(ser_tot / 4.0, 4), "kernels": kernels_serial},
         "clocks": clocks,
         "cpu_baseline": cb,
+        "slab": slab,
         "gtv_voxels_last_step": [float(v) for v in (vols if vols is not None else [])][:4],
     }
     print(json.dumps(line), flush=True)
@@ -505,6 +623,7 @@ def main():
     ap.add_argument("--threads", type=int, default=3,
                     help="host threads (= CUDA streams of the library) that take the steps in turn")
     ap.add_argument("--wc", action="store_true", help="write-combined pinned staging buffers for the uploads")
+    ap.add_argument("--no-slab", action="store_true", help="skip the slab-decomposed volume record of N > 1 runs")
     ap.add_argument("--prof-timed", action="store_true",
                     help="diagnosis: per-kernel CUDA events inside the timed region (default: untimed pass only)")
     args = ap.parse_args()

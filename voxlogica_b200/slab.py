@@ -27,8 +27,8 @@ travel as torch tensors: zero-copy views of the HBM-resident images on the GPU p
                            (each rank gets a range of rows of EVERY plane), z pass + sqrt on
                            complete columns, all-to-all back
 
-Not decomposed yet: ``percentiles`` (needs a distributed sort) and ``maxvol``; they raise
-NotImplementedError.
+``percentiles`` (distributed sample sort of the masked voxels) and ``maxvol`` (boundary classes
+summed over the ranks) are decomposed as well, see their docstrings.
 """
 from __future__ import annotations
 
@@ -268,6 +268,18 @@ class SlabOps:
         self.c = comm
         self.peer: Optional[PeerHalo] = None
         self.use_ccl_state = True     # `through` on a kept union-find state when the engine has one
+        self.trace: Optional[dict] = None   # when a dict: seconds per phase of `through` (device-synchronised)
+
+    def _tick(self, name: str, t0: float) -> float:
+        """phase timing for the bench: synchronise the device, add the elapsed seconds to trace[name]"""
+        if self.trace is None:
+            return t0
+        import time
+        if hasattr(self.e, "ctx"):
+            self.e.ctx.sync()
+        t1 = time.perf_counter()
+        self.trace[name] = self.trace.get(name, 0.0) + (t1 - t0)
+        return t1
 
     def enable_peer_halo(self, ny: int, nx: int) -> None:
         """collective: allocate and exchange the IPC mailboxes for [ny][nx] u8 boundary planes"""
@@ -302,8 +314,11 @@ class SlabOps:
         if h <= 0 or self.c.world == 1:
             return x.data, 0, 0
         nzl = self.e.nz(x.data)
-        if h > nzl:
-            raise ValueError(f"halo of {h} planes exceeds a slab of {nzl} planes: use fewer ranks")
+        # a halo comes from the immediate neighbour only; decide from the SMALLEST slab so that every
+        # rank raises together (deciding from the local slab left the other ranks inside the exchange)
+        smallest = min(z1 - z0 for z0, z1 in slab_bounds(x.nz_global, self.c.world))
+        if h > smallest:
+            raise ValueError(f"halo of {h} planes exceeds the smallest slab ({smallest} planes): use fewer ranks")
         lo = self.e.to_tensor(self.e.crop_z(x.data, 0, h))
         hi = self.e.to_tensor(self.e.crop_z(x.data, nzl - h, h))
         from_lower, from_upper = self.c.exchange_planes(lo, hi)
@@ -384,6 +399,8 @@ class SlabOps:
         if c.world == 1:
             return b.like(e.through(a.data, b.data, conn))
         nzl = e.nz(b.data)
+        import time
+        tk = time.perf_counter() if self.trace is not None else 0.0
         stateful = self.use_ccl_state and hasattr(e, "ccl_create")
         if stateful:
             st = e.ccl_create(b.data, conn)
@@ -402,21 +419,30 @@ class SlabOps:
         tag = (c.rank + 1) << 32                       # global id of a local label: (rank+1, label)
         gid_bot = torch.where(lab_bot > 0, lab_bot + tag, torch.zeros_like(lab_bot))
         gid_top = torch.where(lab_top > 0, lab_top + tag, torch.zeros_like(lab_top))
+        tk = self._tick("local_ccl_and_planes", tk)
         # the upper neighbour needs my top plane, I need the lower neighbour's top plane
         below_top, _ = c.exchange_planes(gid_bot, gid_top)   # from_lower = what rank-1 sent "to_upper"
+        tk = self._tick("exchange_label_planes", tk)
         pairs = torch.zeros((0, 2), dtype=torch.int64, device=gid_bot.device)
         if below_top is not None:
             pairs = boundary_pairs(below_top, gid_bot, conn)
         reached = torch.unique(torch.cat([gid_bot[hit_bot], gid_top[hit_top]]))
+        tk = self._tick("boundary_pairs", tk)
         all_pairs = c.all_gather_rows(pairs).cpu().numpy()
         all_reached = c.all_gather_rows(reached[:, None]).cpu().numpy()[:, 0]
+        tk = self._tick("all_gather_pairs_and_reached", tk)
+        if self.trace is not None:
+            self.trace["pairs_gathered"] = int(all_pairs.shape[0])
+            self.trace["reached_gathered"] = int(all_reached.shape[0])
         newly = resolve_boundary_graph(all_pairs, all_reached)
         mine = newly[(newly >> 32) == c.rank + 1]
+        tk = self._tick("resolve_boundary_graph_host", tk)
         if stateful:
             if mine.size:
                 e.ccl_flag(st, (mine & 0xffffffff).astype(np.uint32))
             out = e.ccl_select(st)
             e.ccl_destroy(st)
+            self._tick("flag_and_select", tk)
             return b.like(out)
         if mine.size == 0:
             return b.like(r0)
