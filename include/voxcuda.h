@@ -171,6 +171,19 @@ VX_API int32_t vx_mem_info(vx_ctx ctx, uint64_t* live_bytes, uint64_t* live_hand
                            uint64_t* pool_reserved);
 /* Return cached pool memory above `keep_bytes` to the driver. */
 VX_API int32_t vx_mem_trim(vx_ctx ctx, uint64_t keep_bytes);
+/* Device-memory budget of the context (the GPU may be shared with the host application's own
+ * work): a soft cap, in bytes, on the memory held by live images, scratch and the free lists
+ * together; 0 = no cap.  An allocation that would exceed it first hands every cached block back
+ * to the pool -- the path a real out-of-memory takes -- and fails with VX_E_OOM only if live data
+ * alone still does not leave room (Greta.pdf p.79: the reference's GPU branch died of exactly
+ * this at 4099 tasks for want of any policy). */
+VX_API int32_t vx_mem_set_budget(vx_ctx ctx, uint64_t bytes);
+/* Allocator counters: bytes in blocks currently handed out, bytes parked in the free lists, the
+ * high-water mark of their sum since the last vx_mem_set_budget call, and the number of
+ * allocations that succeeded only after the free lists were released.  Any out pointer may be
+ * NULL. */
+VX_API int32_t vx_mem_stats(vx_ctx ctx, uint64_t* in_use_bytes, uint64_t* cached_bytes, uint64_t* peak_bytes,
+                            uint64_t* oom_retries);
 
 /* ------------------------------------------------- A1/A2 pointwise operators
  * Greta.pdf p.30 (not, and, true), p.35 (or, false), p.43 ("Colour & thresholds"). */

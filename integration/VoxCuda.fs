@@ -59,6 +59,10 @@ module Native =
     extern int vx_mem_info(uint64 ctx, uint64& liveBytes, uint64& liveHandles, uint64& poolReserved)
     [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
     extern int vx_mem_trim(uint64 ctx, uint64 keepBytes)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_mem_set_budget(uint64 ctx, uint64 bytes)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_mem_stats(uint64 ctx, uint64& inUseBytes, uint64& cachedBytes, uint64& peakBytes, uint64& oomRetries)
 
     // ---- A1/A2 pointwise
     [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
@@ -257,47 +261,54 @@ type CudaModel(device: int) =
     let check rc =
         if rc <> 0 then
             raise (VoxCudaException(rc, Marshal.PtrToStringAnsi(Native.vx_last_error ())))
+    /// the status check of a call that took image handles: the handles are kept reachable until the
+    /// native call has returned (a raw uint64 handed to P/Invoke does not keep its SafeHandle alive, so
+    /// without this the finaliser thread could release an operand while the kernel launch is still
+    /// being set up; the library additionally pins every operand for the length of the call)
+    let checkKeeping (operands: ImageHandle list) rc =
+        for h in operands do GC.KeepAlive h
+        check rc
     do check (Native.vx_init (device, &ctx))
     let conn = 26 // SURVEY.md Q1: adjacency of near/through; 6 selects face adjacency
     let unary (f: uint64 * uint64 * byref<uint64> -> int) (a: ImageHandle) =
         let mutable o = 0UL
-        check (f (ctx, a.Value, &o))
+        checkKeeping [ a ] (f (ctx, a.Value, &o))
         new ImageHandle(o)
 
-    member _.Not(a: ImageHandle) = let mutable o = 0UL in check (Native.vx_not (ctx, a.Value, &o)); new ImageHandle(o)
-    member _.And(a: ImageHandle, b: ImageHandle) = let mutable o = 0UL in check (Native.vx_and (ctx, a.Value, b.Value, &o)); new ImageHandle(o)
-    member _.Or(a: ImageHandle, b: ImageHandle) = let mutable o = 0UL in check (Native.vx_or (ctx, a.Value, b.Value, &o)); new ImageHandle(o)
-    member _.Border(like: ImageHandle) = let mutable o = 0UL in check (Native.vx_border (ctx, like.Value, &o)); new ImageHandle(o)
-    member _.Near(a: ImageHandle) = let mutable o = 0UL in check (Native.vx_near (ctx, a.Value, conn, &o)); new ImageHandle(o)
-    member _.Interior(a: ImageHandle) = let mutable o = 0UL in check (Native.vx_interior (ctx, a.Value, conn, &o)); new ImageHandle(o)
-    member _.Through(a: ImageHandle, b: ImageHandle) = let mutable o = 0UL in check (Native.vx_through (ctx, a.Value, b.Value, conn, &o)); new ImageHandle(o)
-    member _.MaxVol(a: ImageHandle) = let mutable o = 0UL in check (Native.vx_maxvol (ctx, a.Value, conn, &o)); new ImageHandle(o)
-    member _.Lt(a: ImageHandle, s: float) = let mutable o = 0UL in check (Native.vx_cmp_scalar (ctx, a.Value, 0, float32 s, &o)); new ImageHandle(o)
-    member _.Leq(a: ImageHandle, s: float) = let mutable o = 0UL in check (Native.vx_cmp_scalar (ctx, a.Value, 1, float32 s, &o)); new ImageHandle(o)
-    member _.Gt(a: ImageHandle, s: float) = let mutable o = 0UL in check (Native.vx_cmp_scalar (ctx, a.Value, 2, float32 s, &o)); new ImageHandle(o)
-    member _.Geq(a: ImageHandle, s: float) = let mutable o = 0UL in check (Native.vx_cmp_scalar (ctx, a.Value, 3, float32 s, &o)); new ImageHandle(o)
-    member _.DistLt(r: float, a: ImageHandle) = let mutable o = 0UL in check (Native.vx_dist_lt (ctx, a.Value, float32 r, &o)); new ImageHandle(o)
-    member _.DistGeq(r: float, a: ImageHandle) = let mutable o = 0UL in check (Native.vx_dist_geq (ctx, a.Value, float32 r, &o)); new ImageHandle(o)
+    member _.Not(a: ImageHandle) = let mutable o = 0UL in checkKeeping [ a ] (Native.vx_not (ctx, a.Value, &o)); new ImageHandle(o)
+    member _.And(a: ImageHandle, b: ImageHandle) = let mutable o = 0UL in checkKeeping [ a; b ] (Native.vx_and (ctx, a.Value, b.Value, &o)); new ImageHandle(o)
+    member _.Or(a: ImageHandle, b: ImageHandle) = let mutable o = 0UL in checkKeeping [ a; b ] (Native.vx_or (ctx, a.Value, b.Value, &o)); new ImageHandle(o)
+    member _.Border(like: ImageHandle) = let mutable o = 0UL in checkKeeping [ like ] (Native.vx_border (ctx, like.Value, &o)); new ImageHandle(o)
+    member _.Near(a: ImageHandle) = let mutable o = 0UL in checkKeeping [ a ] (Native.vx_near (ctx, a.Value, conn, &o)); new ImageHandle(o)
+    member _.Interior(a: ImageHandle) = let mutable o = 0UL in checkKeeping [ a ] (Native.vx_interior (ctx, a.Value, conn, &o)); new ImageHandle(o)
+    member _.Through(a: ImageHandle, b: ImageHandle) = let mutable o = 0UL in checkKeeping [ a; b ] (Native.vx_through (ctx, a.Value, b.Value, conn, &o)); new ImageHandle(o)
+    member _.MaxVol(a: ImageHandle) = let mutable o = 0UL in checkKeeping [ a ] (Native.vx_maxvol (ctx, a.Value, conn, &o)); new ImageHandle(o)
+    member _.Lt(a: ImageHandle, s: float) = let mutable o = 0UL in checkKeeping [ a ] (Native.vx_cmp_scalar (ctx, a.Value, 0, float32 s, &o)); new ImageHandle(o)
+    member _.Leq(a: ImageHandle, s: float) = let mutable o = 0UL in checkKeeping [ a ] (Native.vx_cmp_scalar (ctx, a.Value, 1, float32 s, &o)); new ImageHandle(o)
+    member _.Gt(a: ImageHandle, s: float) = let mutable o = 0UL in checkKeeping [ a ] (Native.vx_cmp_scalar (ctx, a.Value, 2, float32 s, &o)); new ImageHandle(o)
+    member _.Geq(a: ImageHandle, s: float) = let mutable o = 0UL in checkKeeping [ a ] (Native.vx_cmp_scalar (ctx, a.Value, 3, float32 s, &o)); new ImageHandle(o)
+    member _.DistLt(r: float, a: ImageHandle) = let mutable o = 0UL in checkKeeping [ a ] (Native.vx_dist_lt (ctx, a.Value, float32 r, &o)); new ImageHandle(o)
+    member _.DistGeq(r: float, a: ImageHandle) = let mutable o = 0UL in checkKeeping [ a ] (Native.vx_dist_geq (ctx, a.Value, float32 r, &o)); new ImageHandle(o)
     member _.Percentiles(a: ImageHandle, mask: ImageHandle, correction: float) =
-        let mutable o = 0UL in check (Native.vx_percentiles (ctx, a.Value, mask.Value, correction, &o)); new ImageHandle(o)
+        let mutable o = 0UL in checkKeeping [ a; mask ] (Native.vx_percentiles (ctx, a.Value, mask.Value, correction, &o)); new ImageHandle(o)
     member _.CrossCorrelation(rho: float, a: ImageHandle, b: ImageHandle, region: ImageHandle, m: float, M: float, k: int) =
         let mutable o = 0UL
-        check (Native.vx_cross_correlation (ctx, a.Value, b.Value, region.Value, float32 rho, [| m |], [| M |], k, &o))
+        checkKeeping [ a; b; region ] (Native.vx_cross_correlation (ctx, a.Value, b.Value, region.Value, float32 rho, [| m |], [| M |], k, &o))
         new ImageHandle(o)
     /// a whole boolean / arithmetic sub-DAG in ONE launch: the evaluator may hand over a maximal
     /// pointwise sub-term of the operator DAG instead of one task per operator (include/voxcuda.h: vx_op)
     member _.Fused(program: VxOp[], leaves: ImageHandle[]) =
         let mutable o = 0UL
         let hs = leaves |> Array.map (fun l -> l.Value)
-        check (Native.vx_fused_pointwise (ctx, program, program.Length, hs, hs.Length, null, 0, &o))
+        checkKeeping (List.ofArray leaves) (Native.vx_fused_pointwise (ctx, program, program.Length, hs, hs.Length, null, 0, &o))
         new ImageHandle(o)
-    member _.Volume(a: ImageHandle) = let r = [| 0.0 |] in check (Native.vx_volume (ctx, a.Value, r)); r.[0]
-    member _.Min(a: ImageHandle) = let r = [| 0.0 |] in check (Native.vx_min (ctx, a.Value, r)); r.[0]
-    member _.Max(a: ImageHandle) = let r = [| 0.0 |] in check (Native.vx_max (ctx, a.Value, r)); r.[0]
+    member _.Volume(a: ImageHandle) = let r = [| 0.0 |] in checkKeeping [ a ] (Native.vx_volume (ctx, a.Value, r)); r.[0]
+    member _.Min(a: ImageHandle) = let r = [| 0.0 |] in checkKeeping [ a ] (Native.vx_min (ctx, a.Value, r)); r.[0]
+    member _.Max(a: ImageHandle) = let r = [| 0.0 |] in checkKeeping [ a ] (Native.vx_max (ctx, a.Value, r)); r.[0]
     /// min and max from one pass (the scheduler can serve both `min(img)` and `max(img)` tasks from it)
     member _.MinMax(a: ImageHandle) =
         let lo, hi = [| 0.0 |], [| 0.0 |]
-        check (Native.vx_minmax (ctx, a.Value, 0UL, lo, hi))
+        checkKeeping [ a ] (Native.vx_minmax (ctx, a.Value, 0UL, lo, hi))
         lo.[0], hi.[0]
 
     /// pinned managed array -> HBM (dtype 1 = u8 boolean, 2 = f32 number)
@@ -312,7 +323,7 @@ type CudaModel(device: int) =
             pin.Free()
     member _.Download(img: ImageHandle, dst: Array, bytes: int64) =
         let pin = GCHandle.Alloc(dst, GCHandleType.Pinned)
-        try check (Native.vx_download (ctx, img.Value, pin.AddrOfPinnedObject(), unativeint bytes))
+        try checkKeeping [ img ] (Native.vx_download (ctx, img.Value, pin.AddrOfPinnedObject(), unativeint bytes))
         finally pin.Free()
     interface IDisposable with
         member _.Dispose() = if ctx <> 0UL then (Native.vx_shutdown ctx |> ignore; ctx <- 0UL)

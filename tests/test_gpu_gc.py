@@ -1,0 +1,128 @@
+"""Device-memory GC under the reference's own stress.
+
+Greta.pdf p.79 / Image420: the reference's GPU branch runs formulas of 11 ... 8195 tasks; without
+garbage collection it dies with "Out of memory" at 4099 and 8195 tasks, with it the run completes
+at 0.34 ms/task (1027 tasks) ... 1.46 ms/task (8195).  Here: generated formulas of exactly those
+task counts (voxlogica_b200.synth.task_dag_spec) on ONE BraTS-sized volume, one launch per task as
+in the reference (fuse=False), under a device-memory budget (vx_mem_set_budget) far below what
+the formula's results add up to."""
+import json
+import os
+import time
+
+import numpy as np
+import pytest
+
+from voxlogica_b200 import _abi as A
+from voxlogica_b200 import imgql
+from voxlogica_b200.synth import BRATS_SHAPE, brats_like, task_dag_spec
+
+pytestmark = pytest.mark.gpu
+MB = 1 << 20
+BUDGET = 1024 * MB      # one f32 BraTS volume is 35.7 MB, a boolean one 8.9 MB: room for ~30-100 results
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+@pytest.fixture(scope="module")
+def volume(ctx):
+    img = ctx.upload(brats_like(seed=7)[None])
+    yield img
+    ctx.mem_set_budget(0)
+
+
+def test_gc_changes_no_result(ctx):
+    """same formula, small volume: collected and uncollected runs agree on every printed number and
+    on the last image, fused and unfused"""
+    vol = ctx.upload(brats_like(seed=3, shape=(20, 48, 64))[None])
+    spec = task_dag_spec(259, seed=11) + 'save "last" b0\n'
+    ref = imgql.run_spec(ctx, spec, {"vol": vol}, fuse=False, gc=False)
+    for fuse in (False, True):
+        it = imgql.run_spec(ctx, spec, {"vol": vol}, fuse=fuse, gc=True)
+        assert it.n_tasks == ref.n_tasks == 259
+        assert np.array_equal(it.printed["volume"], ref.printed["volume"])
+        assert np.array_equal(it.saved["last"].numpy(), ref.saved["last"].numpy())
+
+
+@pytest.mark.parametrize("n_tasks", [1027, 4099, 8195])
+def test_gc_stress_at_the_reference_task_counts(ctx, volume, n_tasks):
+    spec = task_dag_spec(n_tasks, seed={4099: 4101}.get(n_tasks, n_tasks))   # seeds whose last result is not empty
+    ctx.sync()
+    ctx.mem_trim(0)
+    base = ctx.mem_stats()["in_use_bytes"]
+    ctx.mem_set_budget(base + BUDGET)
+    launches = ctx.launch_count()
+    t0 = time.perf_counter()
+    it = imgql.run_spec(ctx, spec, {"vol": volume}, fuse=False, gc=True)
+    ctx.sync()
+    dt = time.perf_counter() - t0
+    st, mi = ctx.mem_stats(), ctx.mem_info()
+    assert it.n_tasks == n_tasks
+    vol_vox = float(it.printed["volume"][0])
+    del it
+    import gc
+    gc.collect()
+    # bounded: live blocks + free lists never exceeded the budget, and the driver pool did not grow past it either
+    assert st["peak_bytes"] <= base + BUDGET
+    assert mi["pool_reserved"] <= base + BUDGET + 64 * MB
+    # everything the formula produced has been collected again
+    assert ctx.mem_stats()["in_use_bytes"] <= base
+    rec = {"tasks": n_tasks, "volume_shape": list(BRATS_SHAPE), "wall_ms": round(dt * 1e3, 1),
+           "ms_per_task": round(dt * 1e3 / n_tasks, 4), "kernel_launches": ctx.launch_count() - launches,
+           "budget_mb": BUDGET // MB, "peak_mb": round((st["peak_bytes"] - base) / MB, 1),
+           "allocations_that_released_cache": st["oom_retries"], "result_voxels": vol_vox,
+           "reference": "Greta.pdf p.79: 1027 tasks 980 ms, 4099 tasks 4100 ms, 8195 tasks 12000 ms with GC (OpenCL, image size unstated)"}
+    print("gc stress:", json.dumps(rec))
+    if os.path.isdir(OUT):
+        with open(os.path.join(OUT, f"gc_stress_{n_tasks}.json"), "w") as f:
+            json.dump(rec, f, indent=1)
+    # the reference's GC run costs 0.95-1.46 ms per task; stay well under it
+    assert dt * 1e3 / n_tasks < 0.5
+
+
+def test_without_gc_the_budget_is_exhausted(ctx, volume):
+    """the reference's failure, reproduced: keeping every result of a 4099-task formula alive needs tens of
+    GB; under the budget the run stops with VX_E_OOM (an error code, not a crash), the context stays
+    usable and gives the memory back"""
+    spec = task_dag_spec(4099, seed=4099)
+    ctx.sync()
+    ctx.mem_trim(0)
+    base = ctx.mem_stats()["in_use_bytes"]
+    ctx.mem_set_budget(base + BUDGET)
+    with pytest.raises(A.VoxError) as ei:
+        imgql.run_spec(ctx, spec, {"vol": volume}, fuse=False, gc=False)
+    assert ei.value.code == A.VX_E_OOM and "budget" in str(ei.value)
+    del ei
+    import gc
+    gc.collect()
+    ctx.sync()
+    assert ctx.mem_stats()["in_use_bytes"] <= base
+    a = ctx.near(ctx.cmp_scalar(volume, ">", 0.5))          # still works
+    assert a.numpy().any()
+    ctx.mem_set_budget(0)
+
+
+def test_cached_blocks_are_released_before_an_allocation_fails(ctx, volume):
+    """free lists count against the budget: an allocation of a size the cache does not hold makes room by
+    handing cached blocks back (counted), and vx_mem_trim empties the cache on request"""
+    ctx.mem_set_budget(0)
+    ctx.sync()
+    ctx.mem_trim(0)                                                          # no cached f32-sized block left
+    masks = [ctx.cmp_scalar(volume, ">", 0.1 * i) for i in range(1, 9)]      # 8 x 8.9 MB
+    del masks
+    ctx.sync()
+    st0 = ctx.mem_stats()
+    assert st0["cached_bytes"] >= 8 * 8_900_000
+    ctx.mem_set_budget(st0["in_use_bytes"] + st0["cached_bytes"] + 4 * MB)     # no room for an f32 result
+    f = ctx.arith_scalar(volume, "*", 2.0)                                     # 35.7 MB, another size class
+    st1 = ctx.mem_stats()
+    assert st1["oom_retries"] == st0["oom_retries"] + 1
+    assert st1["cached_bytes"] < st0["cached_bytes"]
+    assert st1["in_use_bytes"] + st1["cached_bytes"] <= st0["in_use_bytes"] + st0["cached_bytes"] + 4 * MB
+    assert np.array_equal(f.numpy(), volume.numpy() * np.float32(2.0))
+    del f
+    ctx.mem_set_budget(0)
+    ctx.sync()
+    ctx.mem_trim(0)
+    assert ctx.mem_stats()["cached_bytes"] == 0
+    reserved = ctx.mem_info()["pool_reserved"]
+    assert reserved <= ctx.mem_stats()["in_use_bytes"] + 96 * MB               # the driver pool shrank too

@@ -4,6 +4,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -308,3 +309,66 @@ def test_nifti_raw_reader_keeps_file_dtype_and_scaling(tmp_path):
     open(p2, "wb").write(bytes(blob))
     arr, _ = io.read_nifti(p2)
     assert np.array_equal(arr, a.astype(np.float32))
+
+
+# ------------------------------------------------------------------ GC policy of the driver (no GPU)
+class _CountedImage:
+    """numpy-backed stand-in for an HBM image that counts how many are alive"""
+    is_image = True
+    live = 0
+    peak = 0
+
+    def __init__(self, a):
+        self.a = a
+        _CountedImage.live += 1
+        _CountedImage.peak = max(_CountedImage.peak, _CountedImage.live)
+
+    def __del__(self):
+        _CountedImage.live -= 1
+
+    nb = 1
+
+
+class _NumpyCtx:
+    """the operators task_dag_spec uses, on numpy arrays (scipy.ndimage for the spatial ones)"""
+    def __init__(self):
+        from scipy import ndimage as ndi
+        self.ndi, self.s26 = ndi, np.ones((3, 3, 3), bool)
+    def _w(self, a): return _CountedImage(a)
+    def not_(self, x): return self._w(~x.a)
+    def and_(self, x, y): return self._w(x.a & y.a)
+    def or_(self, x, y): return self._w(x.a | y.a)
+    def cmp_scalar(self, x, k, s): return self._w({">": np.greater, "<": np.less}[k](x.a, np.float32(s)))
+    def arith_scalar(self, x, op, s): return self._w({"*": np.multiply, "+": np.add}[op](x.a, np.float32(s)))
+    def arith(self, x, op, y): return self._w({"*": np.multiply, "+": np.add}[op](x.a, y.a))
+    def mask(self, x, m, fill): return self._w(np.where(m.a, x.a, np.float32(fill)))
+    def near(self, x, conn): return self._w(self.ndi.binary_dilation(x.a, self.s26))
+    def interior(self, x, conn): return self._w(self.ndi.binary_erosion(x.a, self.s26, border_value=1))
+    def distlt(self, r, x): return self._w(self.ndi.distance_transform_edt(~x.a) < r if x.a.any() else np.zeros_like(x.a))
+    def through(self, x, y, conn):
+        lab, _ = self.ndi.label(y.a, self.s26)
+        return self._w(np.isin(lab, np.unique(lab[x.a & y.a])) & y.a)
+    def volume(self, x): return np.array([float(x.a.sum())])
+
+
+@pytest.mark.parametrize("n_tasks", [11, 67, 259, 1027])
+def test_driver_gc_policy_bounds_live_images(n_tasks):
+    """Greta.pdf p.79: the reference's GPU branch needs garbage collection to survive 4099 tasks.
+    The driver's policy (weak memo + names dropped after their last use) keeps the number of live
+    images bounded by the formula's working set, not by its size, and changes no result."""
+    import gc as pygc
+    from voxlogica_b200 import imgql
+    from voxlogica_b200.synth import task_dag_spec
+    spec = task_dag_spec(n_tasks, seed=n_tasks)
+    vol = np.random.default_rng(5).random((6, 10, 12)).astype(np.float32)
+    res = {}
+    for mode in (False, True):
+        pygc.collect()
+        _CountedImage.live = _CountedImage.peak = 0
+        it = imgql.run_spec(_NumpyCtx(), spec, {"vol": _CountedImage(vol)}, fuse=False, gc=mode)
+        res[mode] = (float(it.printed["volume"][0]), it.n_tasks, _CountedImage.peak)
+        del it
+    assert res[True][0] == res[False][0]
+    assert res[True][1] == res[False][1] == n_tasks          # nothing was recomputed, nothing memo-merged
+    assert res[False][2] >= n_tasks - 4                      # without GC every result stays alive
+    assert res[True][2] <= 20                                # with GC: the working set (two windows of 6 + operands)

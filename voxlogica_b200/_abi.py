@@ -76,6 +76,8 @@ SIGNATURES = {
     "vx_host_free": [C.c_void_p],
     "vx_mem_info": [u64, P(u64), P(u64), P(u64)],
     "vx_mem_trim": [u64, u64],
+    "vx_mem_set_budget": [u64, u64],
+    "vx_mem_stats": [u64, P(u64), P(u64), P(u64), P(u64)],
     "vx_const_bool": [u64, u64, i32, P(u64)],
     "vx_const_f32": [u64, u64, f32, P(u64)],
     "vx_not": [u64, u64, P(u64)],

@@ -68,7 +68,19 @@ struct Ctx {
     std::unordered_map<void*, size_t> block_size;  // every block handed out by dev_alloc
     uint64_t cached_bytes = 0;
     uint64_t cache_limit = 0;  // bytes kept in the free lists before blocks go back to the pool
+    uint64_t alloc_bytes = 0;  // bytes of every block handed out by dev_alloc and not yet given back
+    uint64_t budget = 0;       // vx_mem_set_budget: soft cap on alloc_bytes + cached_bytes (0 = none)
+    uint64_t peak_bytes = 0;   // high-water mark of alloc_bytes + cached_bytes since the last vx_mem_set_budget
+    std::atomic<uint64_t> oom_retries{0};   // allocations that succeeded only after the cache was released
+    // First sticky CUDA fault seen on this context (illegal address, launch failure, ...): the CUDA
+    // context is unusable from then on, and every later call reports the fault instead of
+    // whatever error the dead context produces next.
+    std::atomic<int> fault{0};
+    char fault_msg[256] = "";
 };
+// Classify a CUDA error; sticky ones are latched on the context of the calling thread's current call.
+bool sticky_cuda_error(cudaError_t e);
+void latch_fault(cudaError_t e, const char* what);
 
 // Device memory for images and scratch, ordered on stream index s.
 int dev_alloc(Ctx* c, int s, size_t bytes, void** out);
@@ -80,10 +92,12 @@ int fail(int code, const char* fmt, ...);
 #define VX_CUDA(call)                                                                   \
     do {                                                                                \
         cudaError_t _e = (call);                                                        \
-        if (_e != cudaSuccess)                                                          \
+        if (_e != cudaSuccess) {                                                        \
+            vx::latch_fault(_e, #call);                                                 \
             return vx::fail(_e == cudaErrorMemoryAllocation ? VX_E_OOM : VX_E_CUDA,     \
                             "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e),     \
                             __FILE__, __LINE__);                                        \
+        }                                                                               \
     } while (0)
 #define VX_TRY(expr)               \
     do {                           \
@@ -97,9 +111,12 @@ int fail(int code, const char* fmt, ...);
 
 // ---- handles ---------------------------------------------------------------
 Ctx* get_ctx(vx_ctx h);
-Image* get_img(vx_img h);  // nullptr when invalid
+Image* get_img(vx_img h);  // nullptr when invalid; the pointer is only safe while a reference is held
+// Look the handle up and take a reference in one step (under the table lock): the image cannot be
+// freed by a concurrent vx_release between the look-up and the increment.  Pair with drop().
+Image* pin_img(vx_img h);
 // Stream of the calling thread in this context (created lazily, round-robin).
-int my_stream_index(Ctx* c);
+int my_stream_index(Ctx* c);   // -1 when the stream could not be created
 inline cudaStream_t stream_of(Ctx* c, int idx) { return c->streams[idx]; }
 
 // Allocate a new image on the calling thread's stream.  On success *out holds a
@@ -162,12 +179,18 @@ inline int grid_for(size_t work_items, int per_block, int ctas_per_sm) {
     return (int)(need < cap ? need : cap);
 }
 
-// RAII guard that validates common arguments and pins the inputs for one op.
+// RAII guard that validates common arguments and pins the inputs for one op: every input holds
+// one extra reference from input() until the guard dies, so a vx_release from another thread (a
+// .NET finaliser) cannot free an image -- or recycle its device block -- under a running call.
 struct OpGuard {
     Ctx* c = nullptr;
     int s = 0;
     cudaStream_t st = nullptr;
     std::vector<Image*> ins;
+    OpGuard() = default;
+    OpGuard(const OpGuard&) = delete;
+    OpGuard& operator=(const OpGuard&) = delete;
+    ~OpGuard();
     int begin(vx_ctx ctx);
     int input(vx_img h, Image** out, int want_dtype /*0 = any*/);
     int finish(Image* out_img, vx_img* out);  // publish output + mark inputs used

@@ -21,6 +21,26 @@
 namespace vx {
 
 static thread_local char g_err[512] = "";
+static thread_local Ctx* g_cur_ctx = nullptr;   // context of the call running on this thread (fault latch)
+
+bool sticky_cuda_error(cudaError_t e) {
+    switch (e) {
+        case cudaErrorIllegalAddress: case cudaErrorLaunchFailure: case cudaErrorIllegalInstruction:
+        case cudaErrorMisalignedAddress: case cudaErrorHardwareStackError: case cudaErrorInvalidPc:
+        case cudaErrorInvalidAddressSpace: case cudaErrorECCUncorrectable: case cudaErrorAssert:
+        case cudaErrorLaunchTimeout: case cudaErrorCudartUnloading: case cudaErrorDevicesUnavailable:
+            return true;
+        default:
+            return false;
+    }
+}
+void latch_fault(cudaError_t e, const char* what) {
+    Ctx* c = g_cur_ctx;
+    if (!c || !sticky_cuda_error(e)) return;
+    int expected = 0;
+    if (c->fault.compare_exchange_strong(expected, (int)e))
+        snprintf(c->fault_msg, sizeof(c->fault_msg), "%s (first seen in %s)", cudaGetErrorString(e), what);
+}
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -62,6 +82,19 @@ Image* get_img(vx_img h) {
     return g_imgs[slot];
 }
 
+Image* pin_img(vx_img h) {
+    uint32_t slot = (uint32_t)(h & 0xffffffffu), gen = (uint32_t)(h >> 32);
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    if (slot == 0 || slot >= g_imgs.size() || g_gen[slot] != gen || !g_imgs[slot]) return nullptr;
+    Image* im = g_imgs[slot];
+    // the last reference may be going away right now on another thread (rc already 0, the image
+    // still registered until drop() takes this lock): such a handle is dead
+    int rc = im->rc.load();
+    while (rc > 0 && !im->rc.compare_exchange_weak(rc, rc + 1)) {
+    }
+    return rc > 0 ? im : nullptr;
+}
+
 static void unregister_image(Image* im) {
     uint32_t slot = (uint32_t)(im->handle & 0xffffffffu);
     std::lock_guard<std::mutex> lk(g_tab_mu);
@@ -81,7 +114,8 @@ Ctx* get_ctx(vx_ctx h) {
 // free list, so the next new thread inherits the stream AND the blocks cached on it;
 // without this every short-lived thread would start on a cold allocator.
 struct ThreadStreams {
-    std::vector<std::pair<Ctx*, int>> mine;
+    std::vector<std::pair<Ctx*, int>> mine;     // indices this thread owns alone
+    std::vector<std::pair<Ctx*, int>> shared;   // indices shared with other threads (never recycled)
     ~ThreadStreams() {
         for (auto& p : mine) {
             std::lock_guard<std::mutex> lk(p.first->mu);
@@ -94,22 +128,34 @@ int my_stream_index(Ctx* c) {
     static thread_local ThreadStreams ts;
     for (auto& p : ts.mine)
         if (p.first == c) return p.second;
+    for (auto& p : ts.shared)
+        if (p.first == c) return p.second;
     int idx;
+    bool shared = false;
     {
         std::lock_guard<std::mutex> lk(c->mu);
         if (!c->free_streams.empty()) {
             idx = c->free_streams.back();
             c->free_streams.pop_back();
         } else {
-            idx = c->next_stream.fetch_add(1) % kMaxStreams;
+            const int n = c->next_stream.fetch_add(1);
+            shared = n >= kMaxStreams;     // more live threads than streams: share, round robin
+            idx = n % kMaxStreams;
         }
         if (!c->streams[idx]) {
             cudaStream_t st = nullptr;
-            if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return 0;
+            if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+                (void)cudaGetLastError();
+                if (!shared) c->free_streams.push_back(idx);
+                return -1;          // reported by the caller; never fall back to stream 0 silently
+            }
             c->streams[idx] = st;
         }
     }
-    ts.mine.emplace_back(c, idx);
+    // an index handed out beyond kMaxStreams is shared between threads: it must not be returned
+    // to the free list when one of them exits
+    if (!shared) ts.mine.emplace_back(c, idx);
+    else ts.shared.emplace_back(c, idx);
     return idx;
 }
 
@@ -138,8 +184,18 @@ static size_t round_block(size_t bytes) {
     return (bytes + g - 1) / g * g;
 }
 
+// Gives every cached block back to the pool and waits for the frees to take effect, so that the
+// retry that follows can actually reuse the memory.
+static void release_cache_and_wait(Ctx* c) {
+    dev_cache_release(c, 0);
+    for (int i = 0; i < kMaxStreams; i++)
+        if (c->streams[i]) cudaStreamSynchronize(c->streams[i]);
+    (void)cudaGetLastError();
+}
+
 int dev_alloc(Ctx* c, int s, size_t bytes, void** out) {
     const size_t sz = round_block(bytes ? bytes : 1);
+    bool over_budget = false;
     {
         std::lock_guard<std::mutex> lk(c->mu);
         auto it = c->cache[s].find(sz);
@@ -147,13 +203,31 @@ int dev_alloc(Ctx* c, int s, size_t bytes, void** out) {
             *out = it->second.back();
             it->second.pop_back();
             c->cached_bytes -= sz;
-            return VX_OK;
+            c->alloc_bytes += sz;
+            return VX_OK;   // cache -> in use: the sum (and its high-water mark) is unchanged
         }
+        over_budget = c->budget && c->alloc_bytes + c->cached_bytes + sz > c->budget;
+    }
+    bool retried = false;
+    if (over_budget) {
+        // the budget counts cached blocks: hand back as many as it takes to make room (stream-ordered
+        // frees; a block freed on the allocating stream is reusable at once, so no host wait here)
+        uint64_t keep = 0;
+        {
+            std::lock_guard<std::mutex> lk(c->mu);
+            if (c->alloc_bytes + sz > c->budget)
+                return fail(VX_E_OOM, "allocation of %zu bytes exceeds the memory budget (%llu bytes live, budget %llu)",
+                            sz, (unsigned long long)c->alloc_bytes, (unsigned long long)c->budget);
+            keep = c->budget - c->alloc_bytes - sz;
+        }
+        dev_cache_release(c, keep);
+        retried = true;
     }
     cudaError_t e = cudaMallocAsync(out, sz, c->streams[s]);
-    if (e == cudaErrorMemoryAllocation) {  // give the cached blocks back and retry once
+    if (e == cudaErrorMemoryAllocation) {  // give every cached block back, wait for the frees, retry once
         (void)cudaGetLastError();
-        dev_cache_release(c, 0);
+        release_cache_and_wait(c);
+        retried = true;
         e = cudaMallocAsync(out, sz, c->streams[s]);
     }
     if (e != cudaSuccess) {
@@ -161,8 +235,11 @@ int dev_alloc(Ctx* c, int s, size_t bytes, void** out) {
         return fail(e == cudaErrorMemoryAllocation ? VX_E_OOM : VX_E_CUDA,
                     "cudaMallocAsync(%zu bytes) failed: %s", sz, cudaGetErrorString(e));
     }
+    if (retried) c->oom_retries.fetch_add(1);
     std::lock_guard<std::mutex> lk(c->mu);
     c->block_size[*out] = sz;
+    c->alloc_bytes += sz;
+    if (c->alloc_bytes + c->cached_bytes > c->peak_bytes) c->peak_bytes = c->alloc_bytes + c->cached_bytes;
     return VX_OK;
 }
 
@@ -172,6 +249,7 @@ void dev_free(Ctx* c, int s, void* p) {
     auto it = c->block_size.find(p);
     if (it == c->block_size.end()) return;
     const size_t sz = it->second;
+    c->alloc_bytes -= sz;
     if (c->cached_bytes + sz > c->cache_limit) {  // over budget: hand it back to the pool
         c->block_size.erase(it);
         cudaFreeAsync(p, c->streams[s]);
@@ -212,6 +290,7 @@ int new_image(Ctx* c, int dtype, int nx, int ny, int nz, int nb, const float* sp
     VX_REQUIRE((size_t)nx * ny * nz < ((size_t)1 << 31), VX_E_UNSUPPORTED,
                "a single volume must have fewer than 2^31 voxels (slab-decompose it)");
     int s = my_stream_index(c);
+    VX_REQUIRE(s >= 0, VX_E_CUDA, "could not create a CUDA stream for the calling thread");
     Image* im = new Image();
     im->dtype = dtype;
     im->nx = nx; im->ny = ny; im->nz = nz; im->nb = nb;
@@ -375,20 +454,27 @@ int check_launch(const char* name) {
 int OpGuard::begin(vx_ctx ctx) {
     c = get_ctx(ctx);
     VX_REQUIRE(c != nullptr, VX_E_INVALID_ARG, "invalid context handle");
+    g_cur_ctx = c;
+    if (c->fault.load())
+        return fail(VX_E_CUDA, "the context is dead after an earlier CUDA fault: %s", c->fault_msg);
     VX_CUDA(cudaSetDevice(c->device));
     s = my_stream_index(c);
+    VX_REQUIRE(s >= 0, VX_E_CUDA, "could not create a CUDA stream for the calling thread");
     st = c->streams[s];
     return VX_OK;
 }
+OpGuard::~OpGuard() {
+    for (Image* im : ins) drop(im);   // the pins taken by input()
+}
 int OpGuard::input(vx_img h, Image** out, int want_dtype) {
-    Image* im = get_img(h);
+    Image* im = pin_img(h);
     VX_REQUIRE(im != nullptr, VX_E_INVALID_ARG, "invalid image handle %llu",
                (unsigned long long)h);
+    ins.push_back(im);   // pinned from here on, released by the destructor on every path
     VX_REQUIRE(im->ctx == c, VX_E_INVALID_ARG, "image belongs to another context");
     VX_REQUIRE(want_dtype == 0 || im->dtype == want_dtype, VX_E_DTYPE,
                "operand has dtype %d, expected %d", im->dtype, want_dtype);
     VX_TRY(use_input(c, im, s));
-    ins.push_back(im);
     *out = im;
     return VX_OK;
 }
@@ -616,9 +702,10 @@ int32_t vx_info(vx_img img, int32_t* dtype, int32_t* nx, int32_t* ny, int32_t* n
 }
 
 int32_t vx_retain(vx_img img) {
-    Image* im = get_img(img);
+    // look-up and increment under the table lock: a racing last vx_release cannot free the image
+    // between the two
+    Image* im = pin_img(img);
     VX_REQUIRE(im != nullptr, VX_E_INVALID_ARG, "invalid image handle");
-    im->rc.fetch_add(1);
     return VX_OK;
 }
 
@@ -830,6 +917,27 @@ int32_t vx_mem_info(vx_ctx ctx, uint64_t* live_bytes, uint64_t* live_handles,
         VX_CUDA(cudaMemPoolGetAttribute(c->pool, cudaMemPoolAttrReservedMemCurrent, &v));
         *pool_reserved = v;
     }
+    return VX_OK;
+}
+
+int32_t vx_mem_set_budget(vx_ctx ctx, uint64_t bytes) {
+    Ctx* c = get_ctx(ctx);
+    VX_REQUIRE(c != nullptr, VX_E_INVALID_ARG, "invalid context handle");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->budget = bytes;
+    c->peak_bytes = c->alloc_bytes + c->cached_bytes;
+    return VX_OK;
+}
+
+int32_t vx_mem_stats(vx_ctx ctx, uint64_t* in_use_bytes, uint64_t* cached_bytes, uint64_t* peak_bytes,
+                     uint64_t* oom_retries) {
+    Ctx* c = get_ctx(ctx);
+    VX_REQUIRE(c != nullptr, VX_E_INVALID_ARG, "invalid context handle");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (in_use_bytes) *in_use_bytes = c->alloc_bytes;
+    if (cached_bytes) *cached_bytes = c->cached_bytes;
+    if (peak_bytes) *peak_bytes = c->peak_bytes;
+    if (oom_retries) *oom_retries = c->oom_retries.load();
     return VX_OK;
 }
 

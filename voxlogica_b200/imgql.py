@@ -20,6 +20,7 @@ STDLIB below; the real stdlib.imgql is not in the mount.
 from __future__ import annotations
 
 import re
+import weakref
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Tuple
 
@@ -439,9 +440,20 @@ def _is_img(v):
 
 class Interpreter:
     def __init__(self, ctx: Context, loader: Optional[Callable[[str], Image]] = None, conn: int = 26,
-                 fuse: bool = True):
+                 fuse: bool = True, gc: bool = False):
         self.ctx = ctx
         self.fuse = fuse                     # build Lazy nodes for pointwise operators
+        # Device-memory GC policy (Greta.pdf p.78-79: the reference's GPU branch runs out of memory at
+        # 4099 tasks unless intermediate results are collected).  With gc=True an intermediate lives
+        # exactly as long as something can still consume it: the memo table holds image values
+        # weakly, and a `let`-bound name is dropped after the last statement that mentions it
+        # (directly or through a function body).  The handle's reference count then reaches zero and
+        # the block goes back to the stream's free list for the next task.  A value that is asked
+        # for again after it died is simply recomputed (operators have no side effects, p.7).
+        self.gc = gc
+        self._uid = weakref.WeakKeyDictionary()   # value -> serial number (memo keys must outlive id())
+        self._next_uid = 0
+        self._depth = 0
         self.loader = loader
         self.saver = None                    # optional callable(path, Image) run by `save`
         self.conn = conn                     # adjacency of near/through
@@ -484,9 +496,41 @@ class Interpreter:
         for e in found:
             self.eval(e, {})
 
+    def _last_uses(self, stmts):
+        """name -> index of the last statement that can read it (through function bodies too)"""
+        def names(e, acc):
+            if isinstance(e, Var):
+                acc.add(e.name)
+            elif isinstance(e, Call):
+                acc.add(e.fn)
+                for a in e.args:
+                    names(a, acc)
+            return acc
+        fn_reads = {n: names(b, set()) for n, (_, b) in self.functions.items()}
+        for st in stmts:
+            if st[0] == "let" and st[2] is not None:
+                fn_reads[st[1]] = names(st[3], set()) - set(st[2])
+        last = {}
+        for i, st in enumerate(stmts):
+            body = st[3] if st[0] == "let" else st[2] if st[0] in ("save", "print") else None
+            if body is None:
+                continue
+            reads, todo = set(), list(names(body, set()))
+            while todo:
+                n = todo.pop()
+                if n not in reads:
+                    reads.add(n)
+                    todo.extend(fn_reads.get(n, ()))
+            for n in reads:
+                last[n] = i
+        return last
+
     def run(self, src: str):
         stmts = Parser(src).program()
         hoisted = False
+        # imported files only define things for the importing program: liveness is decided at the top level
+        last_use = self._last_uses(stmts) if self.gc and not self._depth else None
+        self._depth += 1
         for i, st in enumerate(stmts):
             kind = st[0]
             if not hoisted and kind not in ("import", "load"):
@@ -518,6 +562,11 @@ class Interpreter:
             elif kind == "print":
                 v = self.eval(st[2], {})
                 self.printed[st[1]] = v.v.copy() if isinstance(v, Number) else v
+            if last_use is not None:
+                # liveness from the program text: a name nobody reads any more gives up its value
+                for name in [n for n, v in self.globals.items() if last_use.get(n, -1) <= i and _is_img(v)]:
+                    del self.globals[name]
+        self._depth -= 1
         return self
 
     # -- expression level.  Values are identified by id() for hash-consing.
@@ -547,16 +596,31 @@ class Interpreter:
         for a in args:
             if isinstance(a, Number):
                 ks.append(("n", a.v.tobytes()))
+            elif self.gc:
+                # serial numbers instead of id(): the memo does not keep operands alive in this
+                # mode, and a dead operand's id() may be handed to a new object
+                u = self._uid.get(a)
+                if u is None:
+                    u = self._uid[a] = self._next_uid
+                    self._next_uid += 1
+                ks.append(("u", u))
             else:
                 ks.append(("i", id(a)))
         return (fn, tuple(ks))
 
     def apply(self, fn, args):
         key = self._key(fn, args)
-        if key in self.memo:
-            return self.memo[key][0]
+        hit = self.memo.get(key)
+        if hit is not None:
+            val = hit[0]() if isinstance(hit[0], weakref.ref) else hit[0]
+            if val is not None:
+                return val
         val = self._apply(fn, args)
-        self.memo[key] = (val, args)   # keep args alive so id() stays unique
+        if self.gc and _is_img(val):
+            memo = self.memo
+            self.memo[key] = (weakref.ref(val, lambda _r, k=key: memo.pop(k, None)), None)
+        else:
+            self.memo[key] = (val, args)   # keep args alive so id() stays unique
         self.n_tasks += 1
         return val
 
@@ -715,9 +779,10 @@ def _find_hoistable(e, loaded, fns, found) -> None:
             _find_hoistable(a, loaded, fns, found)
 
 
-def run_spec(ctx: Context, src: str, images: Dict[str, Image], conn: int = 26, fuse: bool = True) -> Interpreter:
+def run_spec(ctx: Context, src: str, images: Dict[str, Image], conn: int = 26, fuse: bool = True,
+             gc: bool = False) -> Interpreter:
     """Run an ImgQL spec whose `load` statements name entries of ``images``."""
-    it = Interpreter(ctx, loader=lambda name: images[name], conn=conn, fuse=fuse)
+    it = Interpreter(ctx, loader=lambda name: images[name], conn=conn, fuse=fuse, gc=gc)
     return it.run(src)
 
 

@@ -579,3 +579,12 @@ class Context:
 
     def mem_trim(self, keep_bytes: int = 0) -> None:
         check(self.lib.vx_mem_trim(self.handle, keep_bytes))
+
+    def mem_set_budget(self, nbytes: int) -> None:
+        """soft cap on the device memory held by live images, scratch and the free lists (0 = none)"""
+        check(self.lib.vx_mem_set_budget(self.handle, int(nbytes)))
+
+    def mem_stats(self):
+        a, b, p, c = A.u64(), A.u64(), A.u64(), A.u64()
+        check(self.lib.vx_mem_stats(self.handle, C.byref(a), C.byref(b), C.byref(p), C.byref(c)))
+        return {"in_use_bytes": a.value, "cached_bytes": b.value, "peak_bytes": p.value, "oom_retries": c.value}

@@ -142,3 +142,45 @@ def bernoulli_volume(shape, p: float, seed: int = 7) -> np.ndarray:
 def blob_volume(shape, seed: int = 7, coarse: int = 24, q: float = 0.6) -> np.ndarray:
     s = _smooth_noise(np.random.default_rng(seed), shape, coarse)
     return (s > np.quantile(s[::4, ::4, ::4], q)).astype(np.uint8)
+
+
+def task_dag_spec(n_tasks: int, seed: int = 0, window: int = 6) -> str:
+    """ImgQL text of a generated formula that evaluates to exactly ``n_tasks`` operator tasks on
+    the image loaded as "vol" (Greta.pdf p.79/Image420 times formulas of 11 ... 8195 tasks; the
+    formulas themselves are not published, so this is a seeded stand-in): every `let` applies ONE
+    operator to results of the last ``window`` statements of the right type, boolean and numeric
+    results alternate through thresholds and `mask`, and no (operator, operands) pair repeats, so
+    memoisation cannot shrink the task count.  Tasks = intensity + the lets + the final volume."""
+    if n_tasks < 4:
+        raise ValueError("need at least 4 tasks")
+    rng = np.random.default_rng(seed)
+    out = ['load vol = "vol"', "let f0 = intensity(vol)", "let b0 = f0 >. 0.5"]
+    fs, bs, seen = ["f0"], ["b0"], {"f0 >. 0.5"}
+    # an operand is one of the last `window` results or, one time in four, the input itself (a formula
+    # built only from its own recent results decays to the empty or the full image within a few dozen steps)
+    pick = lambda pool: pool[0] if rng.random() < 0.25 else pool[-1 - int(rng.integers(0, min(window, len(pool))))]
+    for i in range(1, n_tasks - 2):
+        while True:
+            u = rng.random()
+            a, b, fa, fb = pick(bs), pick(bs), pick(fs), pick(fs)
+            c = round(float(rng.uniform(0.05, 0.95)), 3)
+            if u < 0.14:   term, kind = f"near({a})", "b"
+            elif u < 0.24: term, kind = f"interior({a})", "b"
+            elif u < 0.34: term, kind = f"{a} & {b}", "b"
+            elif u < 0.46: term, kind = f"{a} | {b}", "b"
+            elif u < 0.52: term, kind = f"!{a}", "b"
+            elif u < 0.55: term, kind = f"distlt(1.5, {a})", "b"
+            elif u < 0.57: term, kind = f"through({a}, {b})", "b"
+            elif u < 0.69: term, kind = f"{fa} >. {c}", "b"
+            elif u < 0.77: term, kind = f"{fa} + {fb}", "f"
+            elif u < 0.83: term, kind = f"{fa} * {fb}", "f"
+            elif u < 0.91: term, kind = f"{fa} *. {c}", "f"
+            else:          term, kind = f"mask({fa}, {a})", "f"
+            if term not in seen and not (("&" in term or "|" in term or "through" in term) and a == b):
+                break
+        seen.add(term)
+        name = f"{kind}{i}"
+        out.append(f"let {name} = {term}")
+        (bs if kind == "b" else fs).append(name)
+    out.append(f'print "volume" volume({bs[-1]})')
+    return "\n".join(out) + "\n"
