@@ -51,6 +51,8 @@ ALG_BYTES = {
     "xc_bin_kernel": 5.0, "xc_region_hist_kernel": 2.0, "pc_compact_kernel": 5.0,
     # the sort kernels move 8-byte pairs of the MASKED voxels only: no per-voxel figure
     "pc_rank_kernel": None, "rs_hist_kernel": None, "rs_scatter_kernel": None, "rs_rowscan_kernel": None,
+    # percentiles of a quantised (16-bit origin) image by counting: codes 2 + mask 1 in, f32 out
+    "pq_hist_kernel": 3.0, "pq_apply_kernel": 7.0,
     "reduce_f32_kernel": 4.0, "reduce_volume_kernel": 1.0,
     "border_kernel": 1.0, "edt_x_kernel": 5.0, "edt_axis_kernel_y": 8.0, "edt_axis_kernel_z": 8.0,
 }

@@ -117,7 +117,11 @@ VX_API int32_t vx_upload_batch(vx_ctx ctx, const void* host, int32_t dtype, int3
  *     fl( fl( (float)raw * slope ) + inter )
  * is formed on the device -- two binary32 roundings, no fused multiply-add, bit-identical to
  * converting on the host and uploading f32 -- so the host->device copy moves 2 bytes per voxel
- * instead of 4.  host_dtype: VX_I16 or VX_U16; slope 1, inter 0 give the plain conversion. */
+ * instead of 4.  host_dtype: VX_I16 or VX_U16; slope 1, inter 0 give the plain conversion.
+ * The 16-bit codes stay on the device with the image (2 more bytes per voxel) whenever the scaling is
+ * strictly monotone over the type's whole range: such an image has at most 65536 distinct values in
+ * the order of their codes, and vx_percentiles ranks it by counting (histogram, scan, table look-up)
+ * instead of sorting -- same bits, about a sixth of the time (VX_OPT_QUANTISED_PATHS turns this off). */
 VX_API int32_t vx_upload_scaled(vx_ctx ctx, const void* host, int32_t host_dtype, float slope, float inter,
                                 int32_t nx, int32_t ny, int32_t nz, int32_t nb, const float* spacing,
                                 vx_img* out);
@@ -392,6 +396,11 @@ VX_API int32_t vx_launch_count(vx_ctx ctx, uint64_t* out);
 VX_API int32_t vx_prof_enable(vx_ctx ctx, int32_t on);
 VX_API int32_t vx_prof_reset(vx_ctx ctx);
 VX_API int32_t vx_prof_report(vx_ctx ctx, char* buf, size_t buf_bytes);
+/* Context options.  VX_OPT_QUANTISED_PATHS (default 1): operators may use the 16-bit codes kept
+ * with images made by vx_upload_scaled (see there); 0 forces the general algorithms -- the results
+ * are identical, the switch exists for tests and measurements. */
+#define VX_OPT_QUANTISED_PATHS 1
+VX_API int32_t vx_set_option(vx_ctx ctx, int32_t option, int64_t value);
 /* Write a buffer larger than L2 so the next kernel starts cold. */
 VX_API int32_t vx_flush_l2(vx_ctx ctx);
 

@@ -60,6 +60,8 @@ module Native =
     [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
     extern int vx_mem_trim(uint64 ctx, uint64 keepBytes)
     [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int vx_set_option(uint64 ctx, int option, int64 value)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
     extern int vx_mem_set_budget(uint64 ctx, uint64 bytes)
     [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
     extern int vx_mem_stats(uint64 ctx, uint64& inUseBytes, uint64& cachedBytes, uint64& peakBytes, uint64& oomRetries)

@@ -314,6 +314,54 @@ def test_percentiles_key_ranges(ctx, oracle, lo, hi, note):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), note
 
 
+@pytest.mark.parametrize("dtype,slope,inter,lo,hi,note", [
+    (np.int16, 1.0 / 4095.0, 0.0, 0, 4096, "12-bit scanner data: the shared-memory window"),
+    (np.int16, 0.25, -3.0, -2000, 2000, "negative codes"),
+    (np.uint16, -2.5, 1e3, 0, 900, "decreasing scaling: value order = reversed code order"),
+    (np.uint16, 1.0, 0.0, 0, 65536, "the whole code range: global histogram and table"),
+    (np.int16, 1.0, 0.0, -32768, 32768, "whole signed range"),
+    (np.int16, 3.0, 0.5, 7, 8, "a single code"),
+])
+def test_percentiles_of_quantised_images(ctx, oracle, dtype, slope, inter, lo, hi, note):
+    """images uploaded as 16-bit codes (vx_upload_scaled) are ranked by counting instead of sorting:
+    bit-identical to the oracle and to the sorting path (VX_OPT_QUANTISED_PATHS = 0), ties at every level"""
+    from voxlogica_b200 import _abi as A
+    rng = np.random.default_rng(71)
+    for shape in [(2, 9, 30, 48), (3, 5, 7, 13), (1, 1, 1, 1)]:
+        raw = rng.integers(lo, hi, size=shape).astype(dtype)
+        raw[rng.random(shape) < 0.2] = dtype(lo)                 # one heavy tie
+        m = rnd_mask(shape, 0.7, 72)
+        img, M = ctx.upload_scaled(raw, slope, inter), ctx.upload(m)
+        f = raw.astype(np.float32) * np.float32(slope) + np.float32(inter)
+        assert np.array_equal(img.numpy().view(np.uint32), f.view(np.uint32))
+        for corr in (0.0, 0.5, 1.0):
+            want = per_volume(oracle.percentiles, f, m, correction=corr)
+            got = ctx.percentiles(img, M, corr).numpy()
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (note, shape, corr)
+            ctx.set_option(A.VX_OPT_QUANTISED_PATHS, 0)
+            try:
+                sort = ctx.percentiles(img, M, corr).numpy()
+            finally:
+                ctx.set_option(A.VX_OPT_QUANTISED_PATHS, 1)
+            assert np.array_equal(sort.view(np.uint32), want.view(np.uint32)), (note, shape, corr)
+        assert np.all(ctx.percentiles(img, ctx.ff(M)).numpy() == 0)          # empty mask
+        assert np.array_equal(ctx.percentiles(img, ctx.tt(M)).numpy().view(np.uint32),
+                              per_volume(oracle.percentiles, f, np.ones(shape, np.uint8), correction=0.0).view(np.uint32))
+
+
+def test_quantisation_tag_needs_a_strictly_monotone_scaling(ctx, oracle):
+    """slope 0 or a scaling that collapses neighbouring codes in binary32 gives no tag: the sort decides"""
+    rng = np.random.default_rng(73)
+    shape = (2, 6, 20, 32)
+    raw = rng.integers(-300, 300, size=shape).astype(np.int16)
+    m = rnd_mask(shape, 0.8, 74)
+    for slope, inter in [(0.0, 1.5), (1e-3, 1e6), (1.0, 3e8)]:
+        f = raw.astype(np.float32) * np.float32(slope) + np.float32(inter)
+        got = ctx.percentiles(ctx.upload_scaled(raw, slope, inter), ctx.upload(m), 0.5).numpy()
+        want = per_volume(oracle.percentiles, f, m, correction=0.5)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (slope, inter)
+
+
 # ------------------------------------------------------------------ cross correlation
 @pytest.mark.parametrize("shape,rho,k", [((2, 9, 20, 48), 2.0, 10), ((1, 7, 13, 37), 3.0, 100),
                                          ((1, 1, 33, 70), 5.0, 16), ((1, 12, 70, 40), 5.0, 100)])

@@ -19,6 +19,7 @@ VX_OK = 0
 VX_E_INVALID_ARG, VX_E_SHAPE_MISMATCH, VX_E_DTYPE, VX_E_OOM = -1, -2, -3, -4
 VX_E_CUDA, VX_E_NCCL, VX_E_UNSUPPORTED = -5, -6, -7
 VX_U8, VX_F32, VX_U32 = 1, 2, 3
+VX_OPT_QUANTISED_PATHS = 1
 VX_I16, VX_U16 = 4, 5   # host-side voxel types of vx_upload_scaled
 VX_LT, VX_LE, VX_GT, VX_GE, VX_EQ, VX_NE = range(6)
 VX_ADD, VX_SUB, VX_MUL, VX_DIV, VX_RSUB, VX_RDIV, VX_MIN, VX_MAX = range(8)
@@ -76,6 +77,7 @@ SIGNATURES = {
     "vx_host_free": [C.c_void_p],
     "vx_mem_info": [u64, P(u64), P(u64), P(u64)],
     "vx_mem_trim": [u64, u64],
+    "vx_set_option": [u64, i32, C.c_int64],
     "vx_mem_set_budget": [u64, u64],
     "vx_mem_stats": [u64, P(u64), P(u64), P(u64), P(u64)],
     "vx_const_bool": [u64, u64, i32, P(u64)],

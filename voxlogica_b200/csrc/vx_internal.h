@@ -35,6 +35,18 @@ struct Image {
     std::mutex mu;                // guards `foreign`
     std::vector<std::pair<int, cudaEvent_t>> foreign;  // last use on other streams
     uint64_t handle = 0;
+    // Quantisation tag (set by vx_upload_scaled, never inherited): the voxels are
+    //     v = fl(fl((float)q * q_slope) + q_inter)
+    // for the 16-bit codes q kept in q16 (same voxel order, owned by the image), and the map q -> v
+    // was verified on the host to be STRICTLY monotone over the whole code range -- so equal
+    // voxels have equal codes and the order of the codes is the order of the voxels.  Operators
+    // that only need the ORDER of the values (percentiles) may work on the codes: 65536 possible
+    // values make ranking a counting problem instead of a sort.  q16 also holds, after the codes,
+    // two ints: the smallest and the largest order-preserving code u (see q_ucode) of the batch.
+    void* q16 = nullptr;
+    int q_dtype = 0;              // VX_I16 / VX_U16, 0 = no tag
+    bool q_increasing = true;
+    const int* q_range() const { return reinterpret_cast<const int*>(static_cast<const char*>(q16) + ((count() + 7) / 8 * 8) * 2); }
     size_t nvox() const { return (size_t)nx * ny * nz; }       // per volume
     size_t count() const { return (size_t)nx * ny * nz * nb; }  // whole batch
 };
@@ -70,6 +82,7 @@ struct Ctx {
     uint64_t cache_limit = 0;  // bytes kept in the free lists before blocks go back to the pool
     uint64_t alloc_bytes = 0;  // bytes of every block handed out by dev_alloc and not yet given back
     uint64_t budget = 0;       // vx_mem_set_budget: soft cap on alloc_bytes + cached_bytes (0 = none)
+    std::atomic<int> quantised_paths{1};   // VX_OPT_QUANTISED_PATHS
     uint64_t peak_bytes = 0;   // high-water mark of alloc_bytes + cached_bytes since the last vx_mem_set_budget
     std::atomic<uint64_t> oom_retries{0};   // allocations that succeeded only after the cache was released
     // First sticky CUDA fault seen on this context (illegal address, launch failure, ...): the CUDA

@@ -19,6 +19,8 @@
 //   3. every sorted position finds the start of its run of equal keys (its rank) and
 //      scatters the normalised rank back to its voxel.
 #include <algorithm>
+#include <mutex>
+#include <type_traits>
 
 #include "vx_internal.h"
 
@@ -500,6 +502,177 @@ pc_scatter_payload_kernel(const unsigned long long* __restrict__ pairs, const fl
         out[(unsigned)pairs[i]] = values[i];
 }
 
+// ---- 4. quantised images: ranks by counting ------------------------------------------------
+// An image that carries the quantisation tag (vx_internal.h: built by vx_upload_scaled from 16-bit
+// voxels, value strictly monotone in the code) has at most 65536 distinct values, in the order of
+// their codes.  Its percentiles need no sort: a histogram of the masked codes, one scan per volume,
+// one table look-up per voxel -- 3 + 7 bytes per voxel of traffic instead of ~100 per masked voxel.
+// Bit for bit the result of the sorting path: the same exact integer counts enter the same
+// binary64 expression.
+constexpr int kPqCodes = 65536;
+constexpr int kPqWin = 8192;        // codes of the batch's range kept in shared memory (32 KB)
+
+template <typename T>
+__device__ __forceinline__ unsigned pq_ucode(unsigned h) {   // 16 raw bits -> order-preserving unsigned code
+    return std::is_signed<T>::value ? (h ^ 0x8000u) : h;
+}
+
+// grid (blocks, nb), dynamic shared memory kPqWin * 4.  hist is [nb][65536], zeroed by the caller.
+template <typename T>
+__global__ void __launch_bounds__(256)
+pq_hist_kernel(const T* __restrict__ q, const uint8_t* __restrict__ mask, size_t nvox, const int* __restrict__ qrange,
+               unsigned* __restrict__ hist) {
+    extern __shared__ unsigned pq_sh[];
+    const int ulo = qrange[0], uhi = qrange[1];
+    const int span = uhi - ulo + 1;
+    const bool win = span <= kPqWin;            // the usual case: 12-bit scanner data spans 4096 codes
+    const size_t vol = blockIdx.y;
+    unsigned* hv = hist + vol * kPqCodes;
+    if (win)
+        for (int i = threadIdx.x; i < span; i += 256) pq_sh[i] = 0u;
+    __syncthreads();
+    const T* qv = q + vol * nvox;
+    const uint8_t* mv = mask + vol * nvox;
+    auto add = [&](unsigned h) {
+        const int u = (int)pq_ucode<T>(h);
+        if (win) atomicAdd(&pq_sh[u - ulo], 1u); else atomicAdd(&hv[u], 1u);
+    };
+    // 16 voxels per thread and trip when the volume starts 16-byte aligned in both arrays
+    if ((nvox & 15) == 0) {
+        const size_t ng = nvox >> 4;
+        for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < ng; g += (size_t)gridDim.x * 256) {
+            const uint4 m = __ldg(reinterpret_cast<const uint4*>(mv) + g);
+            if ((m.x | m.y | m.z | m.w) == 0u) continue;
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(qv) + 2 * g);
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(qv) + 2 * g + 1);
+            const unsigned mw[4] = {m.x, m.y, m.z, m.w};
+            const unsigned qw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                if ((mw[i >> 2] >> (8 * (i & 3))) & 0xffu) add((qw[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+        }
+    } else {
+        for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvox; i += (size_t)gridDim.x * 256)
+            if (mv[i]) add((unsigned)(unsigned short)qv[i]);
+    }
+    if (win) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < span; i += 256) {
+            const unsigned c = pq_sh[i];
+            if (c) atomicAdd(&hv[ulo + i], c);
+        }
+    }
+}
+
+// One block of 1024 threads per volume: counts -> table[u] = (float)((#below + correction * #equal) / n),
+// "below" in VALUE order (descending codes when the scaling is decreasing).  Only the codes of the
+// batch's range are visited.
+__global__ void __launch_bounds__(1024)
+pq_table_kernel(const unsigned* __restrict__ hist, const int* __restrict__ qrange, float* __restrict__ table,
+                double correction, int increasing) {
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long carry_s;
+    const int ulo = qrange[0], uhi = qrange[1];
+    const int span = uhi - ulo + 1;
+    const size_t vol = blockIdx.x;
+    const unsigned* hv = hist + vol * kPqCodes;
+    float* tv = table + vol * kPqCodes;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // position p = 0 .. span-1 in value order; code u(p)
+    auto code_at = [&](int p) { return increasing ? ulo + p : uhi - p; };
+    // pass 1: total
+    unsigned long long tot = 0;
+    for (int p = threadIdx.x; p < span; p += 1024) tot += hv[code_at(p)];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0) wsum[warp] = tot;
+    __syncthreads();
+    unsigned long long n = 0;
+    for (int w = 0; w < 32; w++) n += wsum[w];
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    if (n == 0) return;    // empty mask: the output stays 0 and no table entry is read
+    const double nd = (double)n;
+    // pass 2: chunks of 1024 positions, exclusive scan inside the chunk + running carry
+    for (int p0 = 0; p0 < span; p0 += 1024) {
+        const int p = p0 + threadIdx.x;
+        const unsigned c = p < span ? hv[code_at(p)] : 0u;
+        unsigned long long incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned long long wbase = 0, chunk = 0;
+        for (int w = 0; w < 32; w++) {
+            const unsigned long long t = wsum[w];
+            if (w < warp) wbase += t;
+            chunk += t;
+        }
+        const unsigned long long less = carry_s + wbase + incl - c;
+        if (p < span && c) {
+            double num = (double)less;
+            if (correction != 0.0) num = __dadd_rn(num, __dmul_rn(correction, (double)c));
+            tv[code_at(p)] = (float)__ddiv_rn(num, nd);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s += chunk;
+        __syncthreads();
+    }
+}
+
+// out = mask ? table[code] : 0.  grid (blocks, nb), dynamic shared memory kPqWin * 4.
+template <typename T>
+__global__ void __launch_bounds__(256)
+pq_apply_kernel(const T* __restrict__ q, const uint8_t* __restrict__ mask, size_t nvox, const int* __restrict__ qrange,
+                const float* __restrict__ table, float* __restrict__ out) {
+    extern __shared__ unsigned pq_sh[];
+    float* tab = reinterpret_cast<float*>(pq_sh);
+    const int ulo = qrange[0], uhi = qrange[1];
+    const int span = uhi - ulo + 1;
+    const bool win = span <= kPqWin;
+    const size_t vol = blockIdx.y;
+    const float* tv = table + vol * kPqCodes;
+    if (win)
+        for (int i = threadIdx.x; i < span; i += 256) tab[i] = tv[ulo + i];
+    __syncthreads();
+    const T* qv = q + vol * nvox;
+    const uint8_t* mv = mask + vol * nvox;
+    float* ov = out + vol * nvox;
+    auto look = [&](unsigned h) {
+        const int u = (int)pq_ucode<T>(h);
+        return win ? tab[u - ulo] : __ldg(tv + u);
+    };
+    if ((nvox & 15) == 0) {
+        const size_t ng = nvox >> 4;
+        for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < ng; g += (size_t)gridDim.x * 256) {
+            const uint4 m = __ldg(reinterpret_cast<const uint4*>(mv) + g);
+            float4* o = reinterpret_cast<float4*>(ov) + 4 * g;
+            if ((m.x | m.y | m.z | m.w) == 0u) {
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                o[0] = z; o[1] = z; o[2] = z; o[3] = z;
+                continue;
+            }
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(qv) + 2 * g);
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(qv) + 2 * g + 1);
+            const unsigned mw[4] = {m.x, m.y, m.z, m.w};
+            const unsigned qw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            float r[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                r[i] = ((mw[i >> 2] >> (8 * (i & 3))) & 0xffu) ? look((qw[i >> 1] >> (16 * (i & 1))) & 0xffffu) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; j++) o[j] = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        }
+    } else {
+        for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvox; i += (size_t)gridDim.x * 256)
+            ov[i] = mv[i] ? look((unsigned)(unsigned short)qv[i]) : 0.f;
+    }
+}
+
 __global__ void pc_set_plan_kernel(unsigned* __restrict__ count, unsigned* __restrict__ plan, unsigned n, unsigned passes) {
     count[0] = n;
     plan[0] = passes;
@@ -508,6 +681,39 @@ __global__ void pc_set_plan_kernel(unsigned* __restrict__ count, unsigned* __res
 }  // namespace vx
 
 using namespace vx;
+
+// percentiles of a quantised image (the tag of vx_internal.h) by counting
+template <typename T>
+static int percentiles_quantised(OpGuard& og, Image* A, Image* M, double correction, Image* O) {
+    const size_t nvox = A->nvox();
+    const int nb = A->nb;
+    Scratch sc(og.c, og.s);
+    unsigned* hist = nullptr;
+    float* table = nullptr;
+    VX_TRY(sc.alloc(sizeof(unsigned) * (size_t)nb * kPqCodes, &hist));
+    VX_TRY(sc.alloc(sizeof(float) * (size_t)nb * kPqCodes, &table));
+    VX_CUDA(cudaMemsetAsync(hist, 0, sizeof(unsigned) * (size_t)nb * kPqCodes, og.st));
+    static std::once_flag once;
+    std::call_once(once, [] {
+        cudaFuncSetAttribute(pq_hist_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPqWin * 4);
+        cudaFuncSetAttribute(pq_apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPqWin * 4);
+    });
+    const T* q = static_cast<const T*>(A->q16);
+    const int* qrange = A->q_range();
+    // grid: a few blocks per SM in total, every block owns one volume's histogram window
+    const int per_vol = std::max(1, std::min((int)((nvox / 16 + 255) / 256), (kNumSMs * 6 + nb - 1) / nb));
+    { VX_LAUNCH(og.c, og.s, "pq_hist_kernel");
+      pq_hist_kernel<T><<<dim3(per_vol, nb), 256, kPqWin * 4, og.st>>>(q, (const uint8_t*)M->d, nvox, qrange, hist); }
+    VX_TRY(check_launch("pq_hist_kernel"));
+    { VX_LAUNCH(og.c, og.s, "pq_table_kernel");
+      pq_table_kernel<<<nb, 1024, 0, og.st>>>(hist, qrange, table, correction, A->q_increasing ? 1 : 0); }
+    VX_TRY(check_launch("pq_table_kernel"));
+    { VX_LAUNCH(og.c, og.s, "pq_apply_kernel");
+      pq_apply_kernel<T><<<dim3(per_vol, nb), 256, kPqWin * 4, og.st>>>(q, (const uint8_t*)M->d, nvox, qrange, table,
+                                                                       (float*)O->d); }
+    VX_TRY(check_launch("pq_apply_kernel"));
+    return VX_OK;
+}
 
 extern "C" int32_t vx_percentiles(vx_ctx ctx, vx_img a, vx_img mask, double correction, vx_img* out) {
     VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");
@@ -519,6 +725,14 @@ extern "C" int32_t vx_percentiles(vx_ctx ctx, vx_img a, vx_img mask, double corr
     VX_TRY(same_shape(A, M));
     const size_t nvox = A->nvox(), total = A->count();
     const int nb = A->nb;
+    if (A->q16 != nullptr && og.c->quantised_paths.load()) {   // at most 65536 distinct values: count, do not sort
+        Image* O = nullptr;
+        VX_TRY(new_image(og.c, VX_F32, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
+        const int rc = A->q_dtype == VX_I16 ? percentiles_quantised<short>(og, A, M, correction, O)
+                                            : percentiles_quantised<unsigned short>(og, A, M, correction, O);
+        if (rc != VX_OK) { drop(O); return rc; }
+        return og.finish(O, out);
+    }
     const int ntiles_max = (int)((nvox + kTile - 1) / kTile);
     unsigned long long* buf = nullptr;
     unsigned *count = nullptr, *table = nullptr, *totals = nullptr, *plan = nullptr;

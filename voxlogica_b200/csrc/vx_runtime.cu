@@ -15,6 +15,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <cmath>
+#include <type_traits>
+
 #include "vx_internal.h"
 #include "vx_tma.h"
 
@@ -353,6 +356,7 @@ void drop(Image* im) {
         put_event(c, p.second);
     }
     dev_free(c, im->home, im->d);
+    if (im->q16) dev_free(c, im->home, im->q16);
     put_event(c, im->ready);
     c->live_bytes -= im->bytes;
     c->live_handles -= 1;
@@ -492,9 +496,14 @@ int OpGuard::finish_scalar() {
 // ---- transfer kernels ---------------------------------------------------------
 // raw 16-bit voxels -> f32 with the file's slope/intercept, one rounding per operation (the host
 // loader computes raw.astype(f32) * slope + inter the same way); 8 voxels per thread
+// qrange[0] / qrange[1] receive the smallest / largest order-preserving code of the batch
+// (u = q + 32768 for int16, q for uint16; initialised to 65535 / 0 by the caller).
 template <typename T>
 __global__ void __launch_bounds__(256)
-convert16_kernel(const T* __restrict__ raw, float* __restrict__ out, size_t n, float slope, float inter) {
+convert16_kernel(const T* __restrict__ raw, float* __restrict__ out, size_t n, float slope, float inter,
+                 int* __restrict__ qrange) {
+    constexpr int bias = std::is_signed<T>::value ? 32768 : 0;
+    int lo_u = 65535, hi_u = 0;
     const size_t ng = n >> 3;
     for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < ng; g += (size_t)gridDim.x * 256) {
         const uint4 w = __ldg(reinterpret_cast<const uint4*>(raw) + g);
@@ -505,6 +514,8 @@ convert16_kernel(const T* __restrict__ raw, float* __restrict__ out, size_t n, f
             const T lo = (T)(ww[i] & 0xffffu), hi = (T)(ww[i] >> 16);
             f[2 * i] = __fadd_rn(__fmul_rn((float)lo, slope), inter);
             f[2 * i + 1] = __fadd_rn(__fmul_rn((float)hi, slope), inter);
+            lo_u = min(lo_u, min((int)lo, (int)hi) + bias);
+            hi_u = max(hi_u, max((int)lo, (int)hi) + bias);
         }
         float4* o = reinterpret_cast<float4*>(out) + 2 * g;
         o[0] = make_float4(f[0], f[1], f[2], f[3]);
@@ -513,7 +524,45 @@ convert16_kernel(const T* __restrict__ raw, float* __restrict__ out, size_t n, f
     if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {   // tail
         const size_t i = (ng << 3) + threadIdx.x;
         out[i] = __fadd_rn(__fmul_rn((float)raw[i], slope), inter);
+        lo_u = min(lo_u, (int)raw[i] + bias);
+        hi_u = max(hi_u, (int)raw[i] + bias);
     }
+    lo_u = __reduce_min_sync(0xffffffffu, lo_u);
+    hi_u = __reduce_max_sync(0xffffffffu, hi_u);
+    if ((threadIdx.x & 31) == 0 && lo_u <= hi_u) {
+        atomicMin(qrange, lo_u);
+        atomicMax(qrange + 1, hi_u);
+    }
+}
+
+// Is q -> fl(fl((float)q * slope) + inter) strictly monotone over every code of the type (as the
+// percentile ranks order values: -0.0 = +0.0, everything finite)?  65536 evaluations; the answer
+// for the last (dtype, slope, inter) is remembered, a loader sends the same scaling for every file.
+static int quant_monotone(int host_dtype, float slope, float inter) {   // +1 increasing, -1 decreasing, 0 neither
+    static std::mutex mu;
+    static int c_dtype = 0, c_ans = 0;
+    static float c_slope = 0.f, c_inter = 0.f;
+    std::lock_guard<std::mutex> lk(mu);
+    if (c_dtype == host_dtype && memcmp(&c_slope, &slope, 4) == 0 && memcmp(&c_inter, &inter, 4) == 0) return c_ans;
+    const int q0 = host_dtype == VX_I16 ? -32768 : 0;
+    auto val = [&](int q) {
+        volatile float p = (float)q * slope;   // two roundings, as the device computes it (no FMA)
+        volatile float v = p + inter;
+        return (float)v + 0.0f;
+    };
+    int ans = 0;
+    float prev = val(q0);
+    bool inc = true, dec = true, finite = std::isfinite(prev);
+    for (int i = 1; i < 65536 && finite && (inc || dec); i++) {
+        const float v = val(q0 + i);
+        finite = std::isfinite(v);
+        inc = inc && v > prev;
+        dec = dec && v < prev;
+        prev = v;
+    }
+    if (finite) ans = inc ? 1 : dec ? -1 : 0;
+    c_dtype = host_dtype; c_slope = slope; c_inter = inter; c_ans = ans;
+    return ans;
 }
 
 // boolean image -> bit stream, 32 voxels per thread (two 16-byte loads, one word out)
@@ -631,11 +680,16 @@ int32_t vx_upload_scaled(vx_ctx ctx, const void* host, int32_t host_dtype, float
     Image* im = nullptr;
     VX_TRY(new_image(g.c, VX_F32, nx, ny, nz, nb, spacing, &im));
     const size_t n = im->count();
-    Scratch sc(g.c, g.s);
+    // the 16-bit codes stay on the device with the image (the quantisation tag of vx_internal.h):
+    // 2 more bytes per voxel buy operators that rank values a counting pass instead of a sort
     void* raw = nullptr;
-    int rc = sc.alloc(((n + 7) / 8 * 8) * 2, &raw);
+    const size_t code_bytes = ((n + 7) / 8 * 8) * 2;
+    int rc = dev_alloc(g.c, im->home, code_bytes + 16, &raw);
+    int* qrange = rc == VX_OK ? reinterpret_cast<int*>(static_cast<char*>(raw) + code_bytes) : nullptr;
     if (rc == VX_OK) {
+        const int init[2] = {65535, 0};
         cudaError_t e = cudaMemcpyAsync(raw, host, n * 2, cudaMemcpyDefault, g.st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(qrange, init, sizeof(init), cudaMemcpyHostToDevice, g.st);
         if (e != cudaSuccess) rc = fail(VX_E_CUDA, "upload failed: %s", cudaGetErrorString(e));
     }
     if (rc == VX_OK) {
@@ -643,13 +697,25 @@ int32_t vx_upload_scaled(vx_ctx ctx, const void* host, int32_t host_dtype, float
         {
             VX_LAUNCH(g.c, g.s, "convert16_kernel");
             if (host_dtype == VX_I16)
-                convert16_kernel<short><<<grid, 256, 0, g.st>>>((const short*)raw, (float*)im->d, n, slope, inter);
+                convert16_kernel<short><<<grid, 256, 0, g.st>>>((const short*)raw, (float*)im->d, n, slope, inter, qrange);
             else
-                convert16_kernel<unsigned short><<<grid, 256, 0, g.st>>>((const unsigned short*)raw, (float*)im->d, n, slope, inter);
+                convert16_kernel<unsigned short><<<grid, 256, 0, g.st>>>((const unsigned short*)raw, (float*)im->d, n, slope, inter, qrange);
         }
         rc = check_launch("convert16_kernel");
     }
-    if (rc != VX_OK) { drop(im); return rc; }
+    if (rc != VX_OK) {
+        if (raw) dev_free(g.c, im->home, raw);
+        drop(im);
+        return rc;
+    }
+    const int mono = quant_monotone(host_dtype, slope, inter);
+    if (mono != 0) {
+        im->q16 = raw;
+        im->q_dtype = host_dtype;
+        im->q_increasing = mono > 0;
+    } else {
+        dev_free(g.c, im->home, raw);   // stream-ordered: recycled after the conversion kernel
+    }
     return g.finish(im, out);
 }
 
@@ -939,6 +1005,15 @@ int32_t vx_mem_stats(vx_ctx ctx, uint64_t* in_use_bytes, uint64_t* cached_bytes,
     if (peak_bytes) *peak_bytes = c->peak_bytes;
     if (oom_retries) *oom_retries = c->oom_retries.load();
     return VX_OK;
+}
+
+int32_t vx_set_option(vx_ctx ctx, int32_t option, int64_t value) {
+    Ctx* c = get_ctx(ctx);
+    VX_REQUIRE(c != nullptr, VX_E_INVALID_ARG, "invalid context handle");
+    switch (option) {
+        case VX_OPT_QUANTISED_PATHS: c->quantised_paths.store(value != 0); return VX_OK;
+    }
+    return fail(VX_E_INVALID_ARG, "unknown option %d", option);
 }
 
 int32_t vx_mem_trim(vx_ctx ctx, uint64_t keep_bytes) {

@@ -580,6 +580,9 @@ class Context:
     def mem_trim(self, keep_bytes: int = 0) -> None:
         check(self.lib.vx_mem_trim(self.handle, keep_bytes))
 
+    def set_option(self, option: int, value: int) -> None:
+        check(self.lib.vx_set_option(self.handle, int(option), int(value)))
+
     def mem_set_budget(self, nbytes: int) -> None:
         """soft cap on the device memory held by live images, scratch and the free lists (0 = none)"""
         check(self.lib.vx_mem_set_budget(self.handle, int(nbytes)))
