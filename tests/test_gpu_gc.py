@@ -107,18 +107,18 @@ def test_cached_blocks_are_released_before_an_allocation_fails(ctx, volume):
     ctx.mem_set_budget(0)
     ctx.sync()
     ctx.mem_trim(0)                                                          # no cached f32-sized block left
-    masks = [ctx.cmp_scalar(volume, ">", 0.1 * i) for i in range(1, 9)]      # 8 x 8.9 MB
-    del masks
+    imgs = [ctx.arith_scalar(volume, "*", float(i)) for i in range(1, 5)]      # 4 x 35.7 MB
+    del imgs
     ctx.sync()
     st0 = ctx.mem_stats()
-    assert st0["cached_bytes"] >= 8 * 8_900_000
-    ctx.mem_set_budget(st0["in_use_bytes"] + st0["cached_bytes"] + 4 * MB)     # no room for an f32 result
-    f = ctx.arith_scalar(volume, "*", 2.0)                                     # 35.7 MB, another size class
+    assert st0["cached_bytes"] >= 4 * 35_000_000
+    ctx.mem_set_budget(st0["in_use_bytes"] + st0["cached_bytes"] + MB // 2)   # no room for a 1.1 MB bit image
+    f = ctx.cmp_scalar(volume, ">", 0.5)                                       # another size class
     st1 = ctx.mem_stats()
     assert st1["oom_retries"] == st0["oom_retries"] + 1
     assert st1["cached_bytes"] < st0["cached_bytes"]
-    assert st1["in_use_bytes"] + st1["cached_bytes"] <= st0["in_use_bytes"] + st0["cached_bytes"] + 4 * MB
-    assert np.array_equal(f.numpy(), volume.numpy() * np.float32(2.0))
+    assert st1["in_use_bytes"] + st1["cached_bytes"] <= st0["in_use_bytes"] + st0["cached_bytes"] + MB // 2
+    assert np.array_equal(f.numpy(), (volume.numpy() > np.float32(0.5)).astype(np.uint8))
     del f
     ctx.mem_set_budget(0)
     ctx.sync()

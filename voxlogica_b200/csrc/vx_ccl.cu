@@ -4,14 +4,15 @@
 //
 //   through(a, b) = union of the connected components of b that contain a voxel of a.
 //
-// Algorithm (B200-first; not the OpenCL branch's ~29 relabelling sweeps, p.78).
-// Everything after the first pass works on 32-voxel bit words, one THREAD per word:
-//   1. init     pack the foreground into bit words (128-bit loads) and create the "anchors"
-//               of every x-run: the run start (parent = itself) and, where a run crosses a
-//               word boundary, the first voxel of the next word (parent = the anchor of the
-//               run's segment in the previous word; lanes trade their words by shuffle).
-//               Only anchors ever get a parent entry, so the label array is written
-//               sparsely (a few entries per word instead of 32);
+// Algorithm (B200-first; not the OpenCL branch's ~29 relabelling sweeps, p.78).  Everything works
+// on 32-voxel bit words of the rows, one THREAD per word, and on a DENSE numbering of the runs:
+//   0. nodes    a node is a run SEGMENT: a maximal run of set voxels inside one row word.  Nodes
+//               are numbered in raster order by a prefix sum over the words (count per block,
+//               one-block scan of the block totals, block scan), so node ids are dense: the parent
+//               array has one u32 per node -- a few MB that stay in L2 -- instead of one per voxel,
+//               and the first node of a component in raster order has its smallest id;
+//   1. init     parent[id] = id, except for a segment that continues a run of the previous word of
+//               its row: it points at that word's last segment (id - 1);
 //   2. merge    per word, contacts with the backward neighbour rows ((y-1,z), (y-1,z-1),
 //               (y,z-1), (y+1,z-1) for 26-adjacency; (y-1,z), (y,z-1) for 6) are found
 //               with bit operations on the neighbour words; one union per place where a
@@ -19,11 +20,14 @@
 //               larger root under the smaller (atomicMin), finds compress paths with
 //               atomicMin (this can only replace a parent by an ancestor, never lose a
 //               link);
-//   3. flatten  every anchor is pointed straight at its root;
-//   4. select   per word and per run segment: anchor -> root -> test (seed flag /
-//               component size) and write 32 output voxels with two 128-bit stores.
-// Roots are the minimum linear index of their component, so labels are canonical.
-// Labels are u32 linear indices inside their own volume (< 2^31); bit 31 is the flag.
+//   3. flatten  every node is pointed straight at its root (one thread per NODE: coalesced);
+//   4. select   per word and per segment: node -> root -> test (seed flag / component size) and
+//               write the 32 output voxels as one word of the result's bit form.
+// Roots are the smallest node id of their component = its first voxel in raster order, so labels
+// (linear index of that voxel + 1) are canonical.  Bit 31 of a parent entry is the flag.
+// Inputs and boolean results are bit-form images (Image::bits): this operator never touches a
+// byte per voxel.
+#include "vx_bits.h"
 #include "vx_internal.h"
 
 namespace vx {
@@ -33,10 +37,12 @@ constexpr unsigned kIdx = 0x7fffffffu;
 constexpr int kCclThreads = 256;
 
 struct Geo {
+    int align16;                // nx % 16 == 0: row words of a flat bit image are written with plain stores
     int nx, ny, nz, nb, nwx;    // nwx = 32-voxel words per row
     unsigned long long rows;    // nb*nz*ny
     unsigned long long nwords;  // rows*nwx
     unsigned long long nvox;    // voxels per volume
+    unsigned nblocks;           // blocks of kCclThreads words
 };
 
 __device__ __forceinline__ unsigned find_root(const unsigned* L, unsigned x) {
@@ -97,6 +103,12 @@ __device__ __forceinline__ unsigned seg_mask(unsigned m, int p) {
     if (len > 32 - p) len = 32 - p;
     return (len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << p;
 }
+// segments of a word: the bits where a segment starts, and how many there are
+__device__ __forceinline__ unsigned seg_starts(unsigned m) { return m & ~(m << 1); }
+// node id of the segment that contains set bit j of a word whose first segment is node `base`
+__device__ __forceinline__ unsigned node_of(unsigned base, unsigned m, int j) {
+    return base + __popc(seg_starts(m) & (0xffffffffu >> (31 - j))) - 1u;
+}
 
 // the word handled by this thread
 struct WordPos {
@@ -121,36 +133,112 @@ __device__ __forceinline__ WordPos word_pos(const Geo& g) {
     return p;
 }
 
-// ---- 1. init: one thread per word ----------------------------------------------------------
-// 32 voxels are read with two 128-bit loads and packed to a bit word; the anchors of the word
-// get their first parents: a run start points at itself, bit 0 of a run that continues from
-// the previous word points at that word's last segment (a chain of at most nwx links along a
-// row, removed by the first find).  The previous word's bits come from the neighbouring lane.
-__device__ __forceinline__ unsigned load_bits32(const uint8_t* __restrict__ src, int nx, int x0);
+// block-wide exclusive scan of one value per thread (kCclThreads threads); *total = block sum
+__device__ __forceinline__ unsigned block_exscan(unsigned v, unsigned* total) {
+    __shared__ unsigned wsum[kCclThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    unsigned base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kCclThreads / 32; w++) {
+        const unsigned t = wsum[w];
+        if (w < warp) base += t;
+        tot += t;
+    }
+    *total = tot;
+    return base + incl - v;
+}
 
+// ---- 0. nodes ------------------------------------------------------------------------------
+// `img` is the image's flat bit form; `bits` receives the row-aligned words the later passes
+// index; blocksum[b] = segments of block b's words.
 __global__ void __launch_bounds__(kCclThreads)
-ccl_init_kernel(const uint8_t* __restrict__ img, unsigned* __restrict__ Lall,
-                unsigned* __restrict__ bits, Geo g) {
+ccl_bits_kernel(const unsigned* __restrict__ img, unsigned* __restrict__ bits, unsigned* __restrict__ blocksum, Geo g) {
     const WordPos p = word_pos(g);
     unsigned m = 0;
     if (p.ok) {
-        m = load_bits32(img + p.row * g.nx + (size_t)p.w * 32, g.nx, p.w * 32);
+        m = flat_row_word(img, p.row, p.w, g.nx);
         bits[p.wid] = m;
     }
+    unsigned total;
+    block_exscan(__popc(seg_starts(m)), &total);
+    if (threadIdx.x == 0) blocksum[blockIdx.x] = total;
+}
+// exclusive scan of the block totals in place, the grand total behind them (one block; every thread
+// scans 16 consecutive entries per trip, so a batch of BraTS volumes takes two trips)
+constexpr int kScanPer = 16;
+__global__ void __launch_bounds__(1024)
+ccl_scan_kernel(unsigned* __restrict__ blocksum, unsigned n) {
+    __shared__ unsigned wsum[32];
+    __shared__ unsigned carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (unsigned i0 = 0; i0 < n; i0 += 1024 * kScanPer) {
+        const unsigned first = i0 + threadIdx.x * kScanPer;
+        unsigned v[kScanPer], mine = 0;
+#pragma unroll
+        for (int e = 0; e < kScanPer; e++) {
+            v[e] = first + e < n ? blocksum[first + e] : 0u;
+            mine += v[e];
+        }
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned base = 0, tot = 0;
+        for (int w = 0; w < 32; w++) {
+            const unsigned t = wsum[w];
+            if (w < warp) base += t;
+            tot += t;
+        }
+        unsigned run = carry + base + incl - mine;
+#pragma unroll
+        for (int e = 0; e < kScanPer; e++) {
+            if (first + e < n) blocksum[first + e] = run;
+            run += v[e];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) blocksum[n] = carry;
+}
+
+// ---- 1. init: node ids and first parents ------------------------------------------------------
+__global__ void __launch_bounds__(kCclThreads)
+ccl_init_kernel(const unsigned* __restrict__ bits, const unsigned* __restrict__ blocksum, unsigned* __restrict__ wbase,
+                unsigned* __restrict__ P, Geo g) {
+    const WordPos p = word_pos(g);
+    const unsigned m = p.ok ? __ldg(bits + p.wid) : 0u;
     unsigned prev_m = __shfl_up_sync(0xffffffffu, m, 1);
+    if ((threadIdx.x & 31) == 0) prev_m = (p.ok && p.wid > 0) ? __ldg(bits + p.wid - 1) : 0u;
+    unsigned total;
+    const unsigned base = __ldg(blocksum + blockIdx.x) + block_exscan(__popc(seg_starts(m)), &total);
     if (!p.ok) return;
-    if (p.w == 0) prev_m = 0;
-    else if ((threadIdx.x & 31) == 0)
-        prev_m = load_bits32(img + p.row * g.nx + (size_t)(p.w - 1) * 32, g.nx, (p.w - 1) * 32);
-    if (m == 0) return;
-    unsigned* L = Lall + (size_t)p.vol * g.nvox;
-    unsigned starts = m & ~((m << 1) | (prev_m >> 31));
+    wbase[p.wid] = base;
+    unsigned starts = seg_starts(m);
+    // a segment at bit 0 that continues a run of the previous word of the same row hangs under that
+    // word's last segment, which is the node just before this word's first
+    const bool cont = (m & 1u) && p.w > 0 && (prev_m >> 31);
+    unsigned id = base;
     while (starts) {
         const int j = __ffs(starts) - 1;
         starts &= starts - 1;
-        L[p.lin0 + j] = p.lin0 + j;
+        P[id] = (j == 0 && cont) ? id - 1u : id;
+        id++;
     }
-    if ((m & 1u) && (prev_m >> 31)) L[p.lin0] = p.lin0 - 32 + seg_start(prev_m, 31);
 }
 
 // ---- 2. merge: one thread per word finds the contacts, the block unites them together -------
@@ -158,43 +246,38 @@ ccl_init_kernel(const uint8_t* __restrict__ img, unsigned* __restrict__ Lall,
 // pointer chasing through L2.  On noisy masks a word has tens of contacts: if each thread
 // united its own, a warp would crawl through them with 2-3 live lanes (ncu: 2.7 active
 // threads per instruction, long-scoreboard bound).  So contacts are first written as (a, b)
-// pairs into a block queue in shared memory, then all 256 threads drain the queue, one
-// union per lane: every lane of a warp has an independent chain of loads in flight.
+// pairs of node ids into a block queue in shared memory, then all 256 threads drain the queue,
+// one union per lane: every lane of a warp has an independent chain of loads in flight.
 constexpr int kQCap = 4096;   // pairs per block and drain round (32 KB); overflow unites directly
 
 template <bool FULL>
 __global__ void __launch_bounds__(kCclThreads)
-ccl_merge_kernel(unsigned* __restrict__ Lall, const unsigned* __restrict__ bits, Geo g) {
+ccl_merge_kernel(unsigned* __restrict__ P, const unsigned* __restrict__ bits, const unsigned* __restrict__ wbase, Geo g) {
     __shared__ uint2 q[kQCap];
     __shared__ unsigned qn;
     const WordPos p = word_pos(g);
-    // volume of the block's first word; a block spans at most two volumes (bit 31 of a pair's
-    // first index says "the second one"; indices inside a volume are < 2^31)
-    const unsigned long long words_per_vol = (unsigned long long)g.nwx * g.ny * g.nz;
-    const unsigned vol0 = (unsigned)(((unsigned long long)blockIdx.x * kCclThreads) / words_per_vol);
     if (threadIdx.x == 0) qn = 0;
     __syncthreads();
     const unsigned* brow = bits + p.row * g.nwx;
+    const unsigned* wrow = wbase + p.row * g.nwx;
     const unsigned m = p.ok ? __ldg(brow + p.w) : 0u;
     const unsigned prev_m = (p.ok && p.w > 0) ? __ldg(brow + p.w - 1) : 0u;
     const unsigned left = (m << 1) | (prev_m >> 31);  // bit j: voxel j-1 of the same row is set
-    const unsigned vtag = (p.vol != vol0) ? kFlag : 0u;
-    unsigned* L = Lall + (size_t)p.vol * g.nvox;
-    const bool far_vol = p.vol > vol0 + 1;   // cannot happen while a volume has >= 256 words; then unite directly
+    const unsigned mybase = m ? __ldg(wrow + p.w) : 0u;
 
     const int ndir = FULL ? 4 : 2;
     const int dys[4] = {-1, 0, -1, 1};
     const int dzs[4] = {0, -1, -1, -1};
     // bits of the row (y+dy, z+dz) relative to voxel j of this word: r0 = same x, rm = x-1,
     // rp = x+1; all zero when the row is outside the volume
-    auto row_bits = [&](int dy, int dz, unsigned& r0, unsigned& rm, unsigned& rp, unsigned& pw) {
-        r0 = rm = rp = pw = 0u;
+    auto row_bits = [&](int dy, int dz, unsigned& r0, unsigned& rm, unsigned& rp, unsigned& pw, unsigned& nn) {
+        r0 = rm = rp = pw = nn = 0u;
         const int yy = p.y + dy, zz = p.z + dz;
         if (m == 0 || yy < 0 || yy >= g.ny || zz < 0 || zz >= g.nz) return false;
         const unsigned* nrow = brow + ((long long)dz * g.ny + dy) * g.nwx;
         const unsigned nc = __ldg(nrow + p.w);
         pw = p.w > 0 ? __ldg(nrow + p.w - 1) : 0u;
-        const unsigned nn = (FULL && p.w + 1 < g.nwx) ? __ldg(nrow + p.w + 1) : 0u;
+        nn = (FULL && p.w + 1 < g.nwx) ? __ldg(nrow + p.w + 1) : 0u;
         r0 = nc;
         rm = (nc << 1) | (pw >> 31);
         rp = (nc >> 1) | (nn << 31);
@@ -213,11 +296,10 @@ ccl_merge_kernel(unsigned* __restrict__ Lall, const unsigned* __restrict__ bits,
 #pragma unroll
         for (int dd = 0; dd < 2; dd++) {
             const int d = d0 + dd;
-            unsigned N0, Nm, Np, np;
-            if (!row_bits(dys[d], dzs[d], N0, Nm, Np, np)) continue;
+            unsigned N0, Nm, Np, np, nn;
+            if (!row_bits(dys[d], dzs[d], N0, Nm, Np, np, nn)) continue;
             const unsigned nc = N0;
-            const long long drow = (long long)dzs[d] * g.ny + dys[d];
-            const unsigned nlin0 = (unsigned)((long long)p.lin0 + drow * g.nx);  // neighbour word, bit 0
+            const unsigned* nwrow = wrow + ((long long)dzs[d] * g.ny + dys[d]) * g.nwx;   // node bases of the neighbour row
             unsigned first, second;
             if (FULL) {
                 first = m & Np & ~N0;             // a neighbour run begins at x+1 next to voxel x
@@ -227,8 +309,8 @@ ccl_merge_kernel(unsigned* __restrict__ Lall, const unsigned* __restrict__ bits,
                 if (d >= 2) {
                     unsigned c0 = u0 | v0, cm = um | vm, cp = up | vp;
                     if (d == 3) {   // (y+1,z) takes the place of (y-1,z)
-                        unsigned w0, wm, wp, wpw;
-                        row_bits(1, 0, w0, wm, wp, wpw);
+                        unsigned w0, wm, wp, wpw, wnn;
+                        row_bits(1, 0, w0, wm, wp, wpw, wnn);
                         c0 = v0 | w0; cm = vm | wm; cp = vp | wp;
                     }
                     first &= ~(c0 | cp);
@@ -240,33 +322,34 @@ ccl_merge_kernel(unsigned* __restrict__ Lall, const unsigned* __restrict__ bits,
             }
             const unsigned cnt = __popc(first) + __popc(second);
             if (cnt == 0) continue;
-            unsigned slot = far_vol ? kQCap : atomicAdd(&qn, cnt);
+            const unsigned nbase = __ldg(nwrow + p.w);
+            unsigned slot = atomicAdd(&qn, cnt);
             while (first) {
                 const int j = __ffs(first) - 1;
                 first &= first - 1;
-                // the neighbour voxel x+1 starts its run, so it is an anchor itself (bit 0 of the
-                // next word when j == 31)
-                const unsigned a = p.lin0 + seg_start(m, j), b = nlin0 + j + 1;
-                if (slot < kQCap) q[slot++] = make_uint2(a | vtag, b);
-                else unite(L, a, b);
+                // the neighbour voxel x+1 starts its run (bit 0 of the next word when j == 31)
+                const unsigned a = node_of(mybase, m, j);
+                const unsigned b = j < 31 ? node_of(nbase, nc, j + 1) : __ldg(nwrow + p.w + 1);
+                if (slot < kQCap) q[slot++] = make_uint2(a, b);
+                else unite(P, a, b);
             }
             while (second) {
                 const int j = __ffs(second) - 1;
                 second &= second - 1;
                 unsigned b;
-                if ((N0 >> j) & 1u) b = nlin0 + seg_start(nc, j);
-                else if (j > 0) b = nlin0 + seg_start(nc, j - 1);
-                else b = nlin0 - 32 + seg_start(np, 31);
-                const unsigned a = p.lin0 + seg_start(m, j);
-                if (slot < kQCap) q[slot++] = make_uint2(a | vtag, b);
-                else unite(L, a, b);
+                if ((N0 >> j) & 1u) b = node_of(nbase, nc, j);
+                else if (j > 0) b = node_of(nbase, nc, j - 1);
+                else b = nbase - 1u;   // voxel 31 of the previous word: that word's last segment
+                const unsigned a = node_of(mybase, m, j);
+                if (slot < kQCap) q[slot++] = make_uint2(a, b);
+                else unite(P, a, b);
             }
         }
         __syncthreads();
         const unsigned n = qn < (unsigned)kQCap ? qn : (unsigned)kQCap;
         for (unsigned i = threadIdx.x; i < n; i += kCclThreads) {
             const uint2 e = q[i];
-            unite(Lall + (size_t)(vol0 + (e.x >> 31)) * g.nvox, e.x & kIdx, e.y);
+            unite(P, e.x, e.y);
         }
         __syncthreads();
         if (threadIdx.x == 0) qn = 0;
@@ -274,81 +357,48 @@ ccl_merge_kernel(unsigned* __restrict__ Lall, const unsigned* __restrict__ bits,
     }
 }
 
-// anchors of a word: run starts plus bit 0 when the run continues from the previous word
-__device__ __forceinline__ unsigned anchor_mask(unsigned m, unsigned prev_m) {
-    return (m & ~((m << 1) | (prev_m >> 31))) | (m & 1u & (prev_m >> 31));
+// ---- 3. flatten: one thread per node ----------------------------------------------------------
+__global__ void __launch_bounds__(kCclThreads)
+ccl_flatten_kernel(unsigned* __restrict__ P, const unsigned* __restrict__ ntotal) {
+    const unsigned n = __ldg(ntotal);
+    for (unsigned id = blockIdx.x * kCclThreads + threadIdx.x; id < n; id += gridDim.x * kCclThreads) {
+        const unsigned r = find_root(P, id);
+        if (r != id) P[id] = r;
+    }
 }
 
-// ---- 3. flatten ----------------------------------------------------------------------------
+// linear index (inside its volume) of every node's first voxel: what labels are made of
 __global__ void __launch_bounds__(kCclThreads)
-ccl_flatten_kernel(unsigned* __restrict__ Lall, const unsigned* __restrict__ bits, Geo g) {
+ccl_npos_kernel(const unsigned* __restrict__ bits, const unsigned* __restrict__ wbase, unsigned* __restrict__ npos, Geo g) {
     const WordPos p = word_pos(g);
     if (!p.ok) return;
-    const unsigned* brow = bits + p.row * g.nwx;
-    const unsigned m = __ldg(brow + p.w);
+    const unsigned m = __ldg(bits + p.wid);
     if (m == 0) return;
-    const unsigned prev_m = p.w > 0 ? __ldg(brow + p.w - 1) : 0u;
-    unsigned* L = Lall + (size_t)p.vol * g.nvox;
-    unsigned anchors = anchor_mask(m, prev_m);
-    while (anchors) {
-        const int j = __ffs(anchors) - 1;
-        anchors &= anchors - 1;
-        const unsigned a = p.lin0 + j;
-        const unsigned r = find_root(L, a);
-        if (r != a) L[a] = r;
-    }
-}
-
-// 32 boolean voxels of `img` at this word as a bit mask
-__device__ __forceinline__ unsigned nib4(unsigned w) {
-    w = __vcmpne4(w, 0u) & 0x01010101u;
-    return ((w * 0x01020408u) >> 24) & 0xfu;
-}
-__device__ __forceinline__ unsigned load_bits32(const uint8_t* __restrict__ src, int nx, int x0) {
-    unsigned v = 0;
-    if ((nx & 15) == 0) {
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
-        v = nib4(a.x) | (nib4(a.y) << 4) | (nib4(a.z) << 8) | (nib4(a.w) << 12);
-        if (x0 + 16 < nx) {
-            const uint4 b = __ldg(reinterpret_cast<const uint4*>(src + 16));
-            v |= (nib4(b.x) | (nib4(b.y) << 4) | (nib4(b.z) << 8) | (nib4(b.w) << 12)) << 16;
-        }
-    } else {
-        const int lim = min(32, nx - x0);
-        for (int b = 0; b < lim; b++) v |= (unsigned)(src[b] != 0) << b;
-    }
-    return v;
-}
-__device__ __forceinline__ unsigned bytes4(unsigned nib) { return (nib * 0x00204081u) & 0x01010101u; }
-__device__ __forceinline__ void store_bits32(uint8_t* __restrict__ dst, int nx, int x0, unsigned v) {
-    if ((nx & 15) == 0) {
-        *reinterpret_cast<uint4*>(dst) = make_uint4(bytes4(v & 0xfu), bytes4((v >> 4) & 0xfu),
-                                                    bytes4((v >> 8) & 0xfu), bytes4((v >> 12) & 0xfu));
-        if (x0 + 16 < nx)
-            *reinterpret_cast<uint4*>(dst + 16) = make_uint4(bytes4((v >> 16) & 0xfu), bytes4((v >> 20) & 0xfu),
-                                                             bytes4((v >> 24) & 0xfu), bytes4(v >> 28));
-    } else {
-        const int lim = min(32, nx - x0);
-        for (int b = 0; b < lim; b++) dst[b] = (uint8_t)((v >> b) & 1u);
+    unsigned starts = seg_starts(m), id = __ldg(wbase + p.wid);
+    while (starts) {
+        const int j = __ffs(starts) - 1;
+        starts &= starts - 1;
+        npos[id++] = p.lin0 + j;
     }
 }
 
 // ---- seeds: every run segment of b that contains a voxel of a flags its root ----------------
 __global__ void __launch_bounds__(kCclThreads)
-ccl_seed_kernel(const uint8_t* __restrict__ seed, unsigned* __restrict__ Lall,
-                const unsigned* __restrict__ bits, Geo g) {
+ccl_seed_kernel(const unsigned* __restrict__ seed, unsigned* __restrict__ P, const unsigned* __restrict__ bits,
+                const unsigned* __restrict__ wbase, Geo g) {
     const WordPos p = word_pos(g);
     if (!p.ok) return;
     const unsigned m = __ldg(bits + p.wid);
     if (m == 0) return;
-    unsigned s = load_bits32(seed + p.row * g.nx + (size_t)p.w * 32, g.nx, p.w * 32) & m;
-    unsigned* L = Lall + (size_t)p.vol * g.nvox;
+    unsigned s = flat_row_word(seed, p.row, p.w, g.nx) & m;
+    if (s == 0) return;
+    const unsigned base = __ldg(wbase + p.wid);
     while (s) {
         const int j = __ffs(s) - 1;
         const int st = seg_start(m, j);
         s &= ~seg_mask(m, st);
-        const unsigned r = find_root(L, p.lin0 + st);
-        if (!(__ldcg(L + r) & kFlag)) atomicOr(L + r, kFlag);
+        const unsigned r = find_root(P, node_of(base, m, st));
+        if (!(__ldcg(P + r) & kFlag)) atomicOr(P + r, kFlag);
     }
 }
 
@@ -357,17 +407,17 @@ enum SelMode { SEL_THROUGH = 0, SEL_LABELS = 1, SEL_MAXVOL = 2 };
 // ---- 4. select -----------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(kCclThreads)
-ccl_select_kernel(const unsigned* __restrict__ Lall, const unsigned* __restrict__ bits, void* out_,
-                  const unsigned* __restrict__ cnt, const unsigned* __restrict__ vmax, Geo g) {
+ccl_select_kernel(const unsigned* __restrict__ P, const unsigned* __restrict__ bits, const unsigned* __restrict__ wbase,
+                  void* out_, const unsigned* __restrict__ cnt, const unsigned* __restrict__ vmax,
+                  const unsigned* __restrict__ npos, Geo g) {
     const WordPos p = word_pos(g);
     if (!p.ok) return;
     const unsigned m = __ldg(bits + p.wid);
-    const unsigned* L = Lall + (size_t)p.vol * g.nvox;
+    unsigned id = m ? __ldg(wbase + p.wid) : 0u;
     const int x0 = p.w * 32;
-    const size_t goff = p.row * g.nx + (size_t)x0;
     unsigned rest = m, outbits = 0;
     if (MODE == SEL_LABELS) {
-        unsigned* dst = reinterpret_cast<unsigned*>(out_) + goff;
+        unsigned* dst = reinterpret_cast<unsigned*>(out_) + p.row * g.nx + (size_t)x0;
         const int lim = min(32, g.nx - x0);
         unsigned lab[32];
 #pragma unroll
@@ -376,7 +426,7 @@ ccl_select_kernel(const unsigned* __restrict__ Lall, const unsigned* __restrict_
             const int st = __ffs(rest) - 1;
             const unsigned sm = seg_mask(m, st);
             rest &= ~sm;
-            const unsigned r = find_root(L, p.lin0 + st) + 1u;
+            const unsigned r = __ldg(npos + find_root(P, id++)) + 1u;
 #pragma unroll
             for (int b = 0; b < 32; b++)
                 if ((sm >> b) & 1u) lab[b] = r;
@@ -398,88 +448,71 @@ ccl_select_kernel(const unsigned* __restrict__ Lall, const unsigned* __restrict_
         const int st = __ffs(rest) - 1;
         const unsigned sm = seg_mask(m, st);
         rest &= ~sm;
-        const unsigned r = find_root(L, p.lin0 + st);
+        const unsigned r = find_root(P, id++);
         bool keep;
-        if (MODE == SEL_THROUGH) keep = (__ldcg(L + r) & kFlag) != 0;
-        else keep = cnt[(size_t)p.vol * g.nvox + r] == vmax[p.vol];
+        if (MODE == SEL_THROUGH) keep = (__ldcg(P + r) & kFlag) != 0;
+        else keep = cnt[r] == vmax[p.vol];
         if (keep) outbits |= sm;
     }
-    store_bits32(reinterpret_cast<uint8_t*>(out_) + goff, g.nx, x0, outbits);
+    flat_store_row_word(reinterpret_cast<unsigned*>(out_), p.row, p.w, g.nx, outbits, g.align16 != 0);
 }
 
 // ---- maxvol --------------------------------------------------------------------------------
-// step 1: zero the counters of the roots (run starts whose parent is themselves)
+// step 1: zero the counters (one per node)
 __global__ void __launch_bounds__(kCclThreads)
-ccl_zero_roots_kernel(const unsigned* __restrict__ Lall, const unsigned* __restrict__ bits,
-                      unsigned* __restrict__ cnt, Geo g) {
-    const WordPos p = word_pos(g);
-    if (!p.ok) return;
-    const unsigned* brow = bits + p.row * g.nwx;
-    const unsigned m = __ldg(brow + p.w);
-    if (m == 0) return;
-    const unsigned prev_m = p.w > 0 ? __ldg(brow + p.w - 1) : 0u;
-    unsigned starts = m & ~((m << 1) | (prev_m >> 31));
-    const size_t vbase = (size_t)p.vol * g.nvox;
-    while (starts) {
-        const int j = __ffs(starts) - 1;
-        starts &= starts - 1;
-        if ((Lall[vbase + p.lin0 + j] & kIdx) == p.lin0 + j) cnt[vbase + p.lin0 + j] = 0;
-    }
+ccl_zero_counts_kernel(unsigned* __restrict__ cnt, const unsigned* __restrict__ ntotal) {
+    const unsigned n = __ldg(ntotal);
+    for (unsigned id = blockIdx.x * kCclThreads + threadIdx.x; id < n; id += gridDim.x * kCclThreads) cnt[id] = 0u;
 }
 // step 2: every run segment adds its length to its root's counter.  Lanes of a warp whose
 // segments share a root (the normal case inside a large component: one hot counter) first add
 // up among themselves and issue ONE atomicAdd; a per-segment atomic serialised on that counter
 // in L2 and made this the longest kernel of maxvol.
 __global__ void __launch_bounds__(kCclThreads)
-ccl_count_kernel(const unsigned* __restrict__ Lall, const unsigned* __restrict__ bits,
+ccl_count_kernel(const unsigned* __restrict__ P, const unsigned* __restrict__ bits, const unsigned* __restrict__ wbase,
                  unsigned* __restrict__ cnt, Geo g) {
     const WordPos p = word_pos(g);
     const unsigned m = p.ok ? __ldg(bits + p.wid) : 0u;
-    const unsigned* L = Lall + (size_t)p.vol * g.nvox;
+    unsigned id = m ? __ldg(wbase + p.wid) : 0u;
     const int lane = threadIdx.x & 31;
     unsigned rest = m;
     while (__any_sync(0xffffffffu, rest != 0u)) {
         const bool has = rest != 0u;
-        unsigned r = 0, c = 0;
+        unsigned r = 0xffffffffu, c = 0;
         if (has) {
             const int st = __ffs(rest) - 1;
             const unsigned sm = seg_mask(m, st);
             rest &= ~sm;
-            r = find_root(L, p.lin0 + st);
+            r = find_root(P, id++);
             c = (unsigned)__popc(sm);
         }
-        const unsigned long long key = has ? (((unsigned long long)p.vol << 32) | r) : ~0ull;
-        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const unsigned peers = __match_any_sync(0xffffffffu, r);
         const unsigned total = __reduce_add_sync(peers, c);
-        if (has && lane == __ffs(peers) - 1) atomicAdd(cnt + (size_t)p.vol * g.nvox + r, total);
+        if (has && lane == __ffs(peers) - 1) atomicAdd(cnt + r, total);
     }
 }
 // step 3: per-volume maximum over roots
 __global__ void __launch_bounds__(kCclThreads)
-ccl_max_kernel(const unsigned* __restrict__ Lall, const unsigned* __restrict__ bits,
+ccl_max_kernel(const unsigned* __restrict__ P, const unsigned* __restrict__ bits, const unsigned* __restrict__ wbase,
                const unsigned* __restrict__ cnt, unsigned* __restrict__ vmax, Geo g) {
     const WordPos p = word_pos(g);
     if (!p.ok) return;
-    const unsigned* brow = bits + p.row * g.nwx;
-    const unsigned m = __ldg(brow + p.w);
+    const unsigned m = __ldg(bits + p.wid);
     if (m == 0) return;
-    const unsigned prev_m = p.w > 0 ? __ldg(brow + p.w - 1) : 0u;
-    unsigned starts = m & ~((m << 1) | (prev_m >> 31));
-    const size_t vbase = (size_t)p.vol * g.nvox;
+    const unsigned base = __ldg(wbase + p.wid);
+    const int nseg = __popc(seg_starts(m));
     unsigned v = 0;
-    while (starts) {
-        const int j = __ffs(starts) - 1;
-        starts &= starts - 1;
-        if ((Lall[vbase + p.lin0 + j] & kIdx) == p.lin0 + j) v = max(v, cnt[vbase + p.lin0 + j]);
-    }
+    for (int i = 0; i < nseg; i++)
+        if ((P[base + i] & kIdx) == base + i) v = max(v, cnt[base + i]);
     if (v) atomicMax(vmax + p.vol, v);
 }
 
 // ---- slab support: labels / reached flags of one z plane, flagging roots by label -----------
 // one thread per word of plane z of every volume
 __global__ void __launch_bounds__(kCclThreads)
-ccl_plane_kernel(const unsigned* __restrict__ Lall, const unsigned* __restrict__ bits,
-                 unsigned* __restrict__ labels, uint8_t* __restrict__ reached, Geo g, int z) {
+ccl_plane_kernel(const unsigned* __restrict__ P, const unsigned* __restrict__ bits, const unsigned* __restrict__ wbase,
+                 const unsigned* __restrict__ npos, unsigned* __restrict__ labels, uint8_t* __restrict__ reached, Geo g,
+                 int z) {
     const unsigned long long words_per_plane = (unsigned long long)g.nwx * g.ny;
     const unsigned long long t = (unsigned long long)blockIdx.x * kCclThreads + threadIdx.x;
     if (t >= words_per_plane * g.nb) return;
@@ -488,8 +521,7 @@ ccl_plane_kernel(const unsigned* __restrict__ Lall, const unsigned* __restrict__
     const int y = (int)(wp / g.nwx), w = (int)(wp % g.nwx);
     const unsigned long long wid = ((unsigned long long)vol * g.nz + z) * words_per_plane + wp;
     const unsigned m = __ldg(bits + wid);
-    const unsigned* L = Lall + (size_t)vol * g.nvox;
-    const unsigned lin0 = (unsigned)(((unsigned long long)z * g.ny + y) * g.nx + (unsigned)w * 32u);
+    unsigned id = m ? __ldg(wbase + wid) : 0u;
     const int x0 = w * 32, lim = min(32, g.nx - x0);
     const size_t o = ((size_t)vol * g.ny + y) * g.nx + x0;
     unsigned rest = m;
@@ -498,92 +530,178 @@ ccl_plane_kernel(const unsigned* __restrict__ Lall, const unsigned* __restrict__
         const int st = __ffs(rest) - 1;
         const unsigned sm = seg_mask(m, st);
         rest &= ~sm;
-        const unsigned r = find_root(L, lin0 + st);
-        const uint8_t hit = (__ldcg(L + r) & kFlag) ? 1 : 0;
-        for (int b = st; b < lim && ((sm >> b) & 1u); b++) { labels[o + b] = r + 1u; reached[o + b] = hit; }
+        const unsigned r = find_root(P, id++);
+        const uint8_t hit = (__ldcg(P + r) & kFlag) ? 1 : 0;
+        const unsigned lab = __ldg(npos + r) + 1u;
+        for (int b = st; b < lim && ((sm >> b) & 1u); b++) { labels[o + b] = lab; reached[o + b] = hit; }
     }
 }
 
-__global__ void ccl_flag_labels_kernel(unsigned* __restrict__ L, const unsigned* __restrict__ labels, size_t n,
-                                       unsigned nvox) {
+// node of the run that starts at voxel `lin` of a single-volume state (a label - 1); ~0 when no run starts there
+__device__ __forceinline__ unsigned node_at(const unsigned* __restrict__ bits, const unsigned* __restrict__ wbase,
+                                            unsigned lin, const Geo& g) {
+    const unsigned row = lin / (unsigned)g.nx;
+    const unsigned x = lin - row * (unsigned)g.nx;
+    const unsigned long long wid = (unsigned long long)row * g.nwx + (x >> 5);
+    const unsigned m = __ldg(bits + wid);
+    if (!((m >> (x & 31u)) & 1u)) return 0xffffffffu;
+    return node_of(__ldg(wbase + wid), m, (int)(x & 31u));
+}
+
+__global__ void ccl_flag_labels_kernel(unsigned* __restrict__ P, const unsigned* __restrict__ bits,
+                                       const unsigned* __restrict__ wbase, const unsigned* __restrict__ labels, size_t n,
+                                       Geo g) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned lab = labels[i];
-    if (lab == 0 || lab > nvox) return;
-    const unsigned r = find_root(L, lab - 1u);
-    atomicOr(L + r, kFlag);
+    if (lab == 0 || lab > (unsigned)g.nvox) return;
+    const unsigned id = node_at(bits, wbase, lab - 1u, g);
+    if (id == 0xffffffffu) return;
+    atomicOr(P + find_root(P, id), kFlag);
 }
 
 // sizes[i] = voxel count of the component whose label is labels[i] (0 for label 0 / invalid)
-__global__ void ccl_sizes_kernel(const unsigned* __restrict__ L, const unsigned* __restrict__ cnt,
-                                 const unsigned* __restrict__ labels, size_t n, unsigned nvox,
-                                 unsigned* __restrict__ sizes) {
+__global__ void ccl_sizes_kernel(const unsigned* __restrict__ P, const unsigned* __restrict__ bits,
+                                 const unsigned* __restrict__ wbase, const unsigned* __restrict__ cnt,
+                                 const unsigned* __restrict__ labels, size_t n, Geo g, unsigned* __restrict__ sizes) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned lab = labels[i];
-    sizes[i] = (lab == 0 || lab > nvox) ? 0u : cnt[find_root(L, lab - 1u)];
+    unsigned id = 0xffffffffu;
+    if (lab != 0 && lab <= (unsigned)g.nvox) id = node_at(bits, wbase, lab - 1u, g);
+    sizes[i] = id == 0xffffffffu ? 0u : cnt[find_root(P, id)];
 }
 
-// flag every root whose component holds exactly `size` voxels (one thread per word; roots are run starts)
+// flag every root whose component holds exactly `size` voxels (one thread per node)
 __global__ void __launch_bounds__(kCclThreads)
-ccl_flag_size_kernel(unsigned* __restrict__ Lall, const unsigned* __restrict__ bits,
-                     const unsigned* __restrict__ cnt, unsigned size, Geo g) {
-    const WordPos p = word_pos(g);
-    if (!p.ok) return;
-    const unsigned* brow = bits + p.row * g.nwx;
-    const unsigned m = __ldg(brow + p.w);
-    if (m == 0) return;
-    const unsigned prev_m = p.w > 0 ? __ldg(brow + p.w - 1) : 0u;
-    unsigned starts = m & ~((m << 1) | (prev_m >> 31));
-    const size_t vbase = (size_t)p.vol * g.nvox;
-    while (starts) {
-        const int j = __ffs(starts) - 1;
-        starts &= starts - 1;
-        const size_t a = vbase + p.lin0 + j;
-        if ((Lall[a] & kIdx) == p.lin0 + j && cnt[a] == size) atomicOr(Lall + a, kFlag);
-    }
+ccl_flag_size_kernel(unsigned* __restrict__ P, const unsigned* __restrict__ cnt, unsigned size,
+                     const unsigned* __restrict__ ntotal) {
+    const unsigned n = __ldg(ntotal);
+    for (unsigned id = blockIdx.x * kCclThreads + threadIdx.x; id < n; id += gridDim.x * kCclThreads)
+        if ((P[id] & kIdx) == id && cnt[id] == size) atomicOr(P + id, kFlag);
 }
 
 static Geo make_geo(const Image* b) {
     Geo g;
     g.nx = b->nx; g.ny = b->ny; g.nz = b->nz; g.nb = b->nb;
     g.nwx = (b->nx + 31) / 32;
+    g.align16 = (b->nx % 16) == 0;
     g.rows = (unsigned long long)b->nb * b->nz * b->ny;
     g.nwords = g.rows * g.nwx;
     g.nvox = b->nvox();
+    g.nblocks = (unsigned)((g.nwords + kCclThreads - 1) / kCclThreads);
     return g;
 }
 
-// shared front end: parents + bit words of image B on the op's stream
-static int ccl_label(OpGuard& og, const Image* B, bool full, unsigned** L_out, unsigned** bits_out,
-                     Geo* geo, unsigned* grid_out, bool flatten = true) {
-    Geo g = make_geo(B);
-    unsigned long long blocks = (g.nwords + kCclThreads - 1) / kCclThreads;
-    VX_REQUIRE(blocks < 0x7fffffffull, VX_E_UNSUPPORTED, "batch too large for one launch");
-    unsigned grid = (unsigned)blocks;
-    unsigned *L = nullptr, *bits = nullptr;
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * B->count(), (void**)&L));
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * g.nwords, (void**)&bits));
-    {
-        VX_LAUNCH(og.c, og.s, "ccl_init_kernel");
-        ccl_init_kernel<<<grid, kCclThreads, 0, og.st>>>((const uint8_t*)B->d, L, bits, g);
+// a new boolean image in bit form for a kernel that writes row words (flat_store_row_word): rows
+// that do not start on half words are merged with atomicOr into a zeroed stream
+static int new_bits_out(OpGuard& og, int nx, int ny, int nz, int nb, const float* sp, Image** O) {
+    VX_TRY(new_bits_image(og.c, nx, ny, nz, nb, sp, O));
+    if (nx % 16) {
+        cudaError_t e = cudaMemsetAsync((*O)->bits, 0, (*O)->bit_words() * 4, og.st);
+        if (e != cudaSuccess) { drop(*O); return fail(VX_E_CUDA, "memset: %s", cudaGetErrorString(e)); }
     }
-    VX_TRY(check_launch("ccl_init_kernel"));
-    {
-        VX_LAUNCH(og.c, og.s, "ccl_merge_kernel");
-        if (full) ccl_merge_kernel<true><<<grid, kCclThreads, 0, og.st>>>(L, bits, g);
-        else ccl_merge_kernel<false><<<grid, kCclThreads, 0, og.st>>>(L, bits, g);
-    }
-    VX_TRY(check_launch("ccl_merge_kernel"));
-    if (flatten) {
-        {
-            VX_LAUNCH(og.c, og.s, "ccl_flatten_kernel");
-            ccl_flatten_kernel<<<grid, kCclThreads, 0, og.st>>>(L, bits, g);
-        }
-        VX_TRY(check_launch("ccl_flatten_kernel"));
-    }
-    *L_out = L; *bits_out = bits; *geo = g; *grid_out = grid;
     return VX_OK;
+}
+
+// Device state of one labelling: the row-aligned bit words, the id of every word's first node,
+// the parents (one per node; capacity = the most segments the rows can hold) and the scan of the
+// block totals, whose last entry is the number of nodes.
+struct CclBufs {
+    unsigned *bits = nullptr, *wbase = nullptr, *P = nullptr, *blocksum = nullptr;
+    size_t cap = 0;   // nodes P can hold
+    Geo g;
+    unsigned grid = 0;
+    const unsigned* ntotal() const { return blocksum + g.nblocks; }
+};
+constexpr int kNodeGrid = kNumSMs * 8;   // blocks of the one-thread-per-node kernels (grid stride)
+
+static void ccl_free(Ctx* c, int s, CclBufs& b) {
+    if (b.bits) scratch_free(c, s, b.bits);
+    if (b.wbase) scratch_free(c, s, b.wbase);
+    if (b.P) scratch_free(c, s, b.P);
+    if (b.blocksum) scratch_free(c, s, b.blocksum);
+    b = CclBufs();
+}
+
+// shared front end: nodes, parents and bit words of image B (bit form Bbits) on the op's stream.
+// On failure everything allocated here is released.
+static int ccl_label(OpGuard& og, const Image* B, const unsigned* Bbits, bool full, CclBufs* out) {
+    CclBufs b;
+    b.g = make_geo(B);
+    const Geo& g = b.g;
+    VX_REQUIRE(g.nblocks < 0x7fffffffu && g.nwords < 0xffffffffull, VX_E_UNSUPPORTED, "batch too large for one launch");
+    b.grid = g.nblocks;
+    // a row of nx voxels holds at most ceil(nx / 2) runs; a run cut by word boundaries adds one node per cut
+    const unsigned long long cap = g.rows * (unsigned long long)((g.nx + 1) / 2 + g.nwx);
+    VX_REQUIRE(cap < 0x7fffffffull, VX_E_UNSUPPORTED, "too many possible runs (%llu) for 31-bit node ids", cap);
+    b.cap = (size_t)cap;
+    int rc = scratch_alloc(og.c, og.s, sizeof(unsigned) * g.nwords, (void**)&b.bits);
+    if (rc == VX_OK) rc = scratch_alloc(og.c, og.s, sizeof(unsigned) * g.nwords, (void**)&b.wbase);
+    if (rc == VX_OK) rc = scratch_alloc(og.c, og.s, sizeof(unsigned) * ((size_t)g.nblocks + 1), (void**)&b.blocksum);
+    if (rc == VX_OK) rc = scratch_alloc(og.c, og.s, sizeof(unsigned) * b.cap, (void**)&b.P);
+    auto step = [&](const char* name) { if (rc == VX_OK) rc = check_launch(name); };
+    if (rc == VX_OK) {
+        VX_LAUNCH(og.c, og.s, "ccl_bits_kernel");
+        ccl_bits_kernel<<<b.grid, kCclThreads, 0, og.st>>>(Bbits, b.bits, b.blocksum, g);
+    }
+    step("ccl_bits_kernel");
+    if (rc == VX_OK) {
+        VX_LAUNCH(og.c, og.s, "ccl_scan_kernel");
+        ccl_scan_kernel<<<1, 1024, 0, og.st>>>(b.blocksum, g.nblocks);
+    }
+    step("ccl_scan_kernel");
+    if (rc == VX_OK) {
+        VX_LAUNCH(og.c, og.s, "ccl_init_kernel");
+        ccl_init_kernel<<<b.grid, kCclThreads, 0, og.st>>>(b.bits, b.blocksum, b.wbase, b.P, g);
+    }
+    step("ccl_init_kernel");
+    if (rc == VX_OK) {
+        VX_LAUNCH(og.c, og.s, "ccl_merge_kernel");
+        if (full) ccl_merge_kernel<true><<<b.grid, kCclThreads, 0, og.st>>>(b.P, b.bits, b.wbase, g);
+        else ccl_merge_kernel<false><<<b.grid, kCclThreads, 0, og.st>>>(b.P, b.bits, b.wbase, g);
+    }
+    step("ccl_merge_kernel");
+    // (select without the flatten pass was measured: -7 % on blobs and sparse masks, +23 % on one
+    // giant component at 512^3, where every run then walks the whole chain: flatten stays)
+    if (rc == VX_OK) {
+        VX_LAUNCH(og.c, og.s, "ccl_flatten_kernel");
+        ccl_flatten_kernel<<<kNodeGrid, kCclThreads, 0, og.st>>>(b.P, b.ntotal());
+    }
+    step("ccl_flatten_kernel");
+    if (rc != VX_OK) { ccl_free(og.c, og.s, b); return rc; }
+    *out = b;
+    return VX_OK;
+}
+
+// first-voxel positions of the nodes (labels are made of them): scratch of the caller
+static int ccl_npos(OpGuard& og, const CclBufs& b, unsigned** npos) {
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * b.cap, (void**)npos));
+    {
+        VX_LAUNCH(og.c, og.s, "ccl_npos_kernel");
+        ccl_npos_kernel<<<b.grid, kCclThreads, 0, og.st>>>(b.bits, b.wbase, *npos, b.g);
+    }
+    return check_launch("ccl_npos_kernel");
+}
+
+// component sizes: cnt (one counter per node, caller's scratch of b.cap entries) and the per-volume maximum
+static int ccl_sizes_of(OpGuard& og, const CclBufs& b, unsigned* cnt, unsigned* vmax) {
+    VX_CUDA(cudaMemsetAsync(vmax, 0, sizeof(unsigned) * b.g.nb, og.st));
+    {
+        VX_LAUNCH(og.c, og.s, "ccl_zero_counts_kernel");
+        ccl_zero_counts_kernel<<<kNodeGrid, kCclThreads, 0, og.st>>>(cnt, b.ntotal());
+    }
+    VX_TRY(check_launch("ccl_zero_counts_kernel"));
+    {
+        VX_LAUNCH(og.c, og.s, "ccl_count_kernel");
+        ccl_count_kernel<<<b.grid, kCclThreads, 0, og.st>>>(b.P, b.bits, b.wbase, cnt, b.g);
+    }
+    VX_TRY(check_launch("ccl_count_kernel"));
+    {
+        VX_LAUNCH(og.c, og.s, "ccl_max_kernel");
+        ccl_max_kernel<<<b.grid, kCclThreads, 0, og.st>>>(b.P, b.bits, b.wbase, cnt, vmax, b.g);
+    }
+    return check_launch("ccl_max_kernel");
 }
 
 }  // namespace vx
@@ -599,29 +717,30 @@ int32_t vx_through(vx_ctx ctx, vx_img a, vx_img b, int32_t conn, vx_img* out) {
     OpGuard og;
     VX_TRY(og.begin(ctx));
     Image *A = nullptr, *B = nullptr;
-    VX_TRY(og.input(a, &A, VX_U8));
-    VX_TRY(og.input(b, &B, VX_U8));
+    const unsigned *Ab = nullptr, *Bb = nullptr;
+    VX_TRY(og.input_bits(a, &A, &Ab));
+    VX_TRY(og.input_bits(b, &B, &Bb));
     VX_TRY(same_shape(A, B));
-    unsigned *L = nullptr, *bits = nullptr, grid = 0;
-    Geo g;
-    // (select without the flatten pass was measured: -7 % on blobs and sparse masks, +23 % on one
-    // giant component at 512^3, where every run then walks the whole chain: flatten stays)
-    VX_TRY(ccl_label(og, B, conn == VX_CONN_FULL, &L, &bits, &g, &grid));
+    CclBufs cb;
+    VX_TRY(ccl_label(og, B, Bb, conn == VX_CONN_FULL, &cb));
+    Image* O = nullptr;
+    int r = VX_OK;
     {
         VX_LAUNCH(og.c, og.s, "ccl_seed_kernel");
-        ccl_seed_kernel<<<grid, kCclThreads, 0, og.st>>>((const uint8_t*)A->d, L, bits, g);
+        ccl_seed_kernel<<<cb.grid, kCclThreads, 0, og.st>>>(Ab, cb.P, cb.bits, cb.wbase, cb.g);
     }
-    VX_TRY(check_launch("ccl_seed_kernel"));
-    Image* O = nullptr;
-    VX_TRY(new_image(og.c, VX_U8, B->nx, B->ny, B->nz, B->nb, B->sp, &O));
-    {
-        VX_LAUNCH(og.c, og.s, "ccl_select_kernel");
-        ccl_select_kernel<SEL_THROUGH><<<grid, kCclThreads, 0, og.st>>>(L, bits, O->d, nullptr, nullptr, g);
+    r = check_launch("ccl_seed_kernel");
+    if (r == VX_OK) r = new_bits_out(og, B->nx, B->ny, B->nz, B->nb, B->sp, &O);
+    if (r == VX_OK) {
+        {
+            VX_LAUNCH(og.c, og.s, "ccl_select_kernel");
+            ccl_select_kernel<SEL_THROUGH><<<cb.grid, kCclThreads, 0, og.st>>>(cb.P, cb.bits, cb.wbase, O->bits, nullptr,
+                                                                              nullptr, nullptr, cb.g);
+        }
+        r = check_launch("ccl_select_kernel");
     }
-    int r = check_launch("ccl_select_kernel");
-    if (r == VX_OK) r = scratch_free(og.c, og.s, L);
-    if (r == VX_OK) r = scratch_free(og.c, og.s, bits);
-    if (r != VX_OK) { drop(O); return r; }
+    ccl_free(og.c, og.s, cb);
+    if (r != VX_OK) { if (O) drop(O); return r; }
     return og.finish(O, out);
 }
 
@@ -632,20 +751,25 @@ int32_t vx_components(vx_ctx ctx, vx_img a, int32_t conn, vx_img* out) {
     OpGuard og;
     VX_TRY(og.begin(ctx));
     Image* A = nullptr;
-    VX_TRY(og.input(a, &A, VX_U8));
-    unsigned *L = nullptr, *bits = nullptr, grid = 0;
-    Geo g;
-    VX_TRY(ccl_label(og, A, conn == VX_CONN_FULL, &L, &bits, &g, &grid));
+    const unsigned* Ab = nullptr;
+    VX_TRY(og.input_bits(a, &A, &Ab));
+    CclBufs cb;
+    VX_TRY(ccl_label(og, A, Ab, conn == VX_CONN_FULL, &cb));
     Image* O = nullptr;
-    VX_TRY(new_image(og.c, VX_U32, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
-    {
-        VX_LAUNCH(og.c, og.s, "ccl_select_kernel");
-        ccl_select_kernel<SEL_LABELS><<<grid, kCclThreads, 0, og.st>>>(L, bits, O->d, nullptr, nullptr, g);
+    unsigned* npos = nullptr;
+    int r = ccl_npos(og, cb, &npos);
+    if (r == VX_OK) r = new_image(og.c, VX_U32, A->nx, A->ny, A->nz, A->nb, A->sp, &O);
+    if (r == VX_OK) {
+        {
+            VX_LAUNCH(og.c, og.s, "ccl_select_kernel");
+            ccl_select_kernel<SEL_LABELS><<<cb.grid, kCclThreads, 0, og.st>>>(cb.P, cb.bits, cb.wbase, O->d, nullptr, nullptr,
+                                                                             npos, cb.g);
+        }
+        r = check_launch("ccl_select_kernel");
     }
-    int r = check_launch("ccl_select_kernel");
-    if (r == VX_OK) r = scratch_free(og.c, og.s, L);
-    if (r == VX_OK) r = scratch_free(og.c, og.s, bits);
-    if (r != VX_OK) { drop(O); return r; }
+    if (npos) scratch_free(og.c, og.s, npos);
+    ccl_free(og.c, og.s, cb);
+    if (r != VX_OK) { if (O) drop(O); return r; }
     return og.finish(O, out);
 }
 
@@ -656,41 +780,28 @@ int32_t vx_maxvol(vx_ctx ctx, vx_img a, int32_t conn, vx_img* out) {
     OpGuard og;
     VX_TRY(og.begin(ctx));
     Image* A = nullptr;
-    VX_TRY(og.input(a, &A, VX_U8));
-    unsigned *L = nullptr, *bits = nullptr, grid = 0;
-    Geo g;
-    VX_TRY(ccl_label(og, A, conn == VX_CONN_FULL, &L, &bits, &g, &grid));
+    const unsigned* Ab = nullptr;
+    VX_TRY(og.input_bits(a, &A, &Ab));
+    CclBufs cb;
+    VX_TRY(ccl_label(og, A, Ab, conn == VX_CONN_FULL, &cb));
     unsigned *cnt = nullptr, *vmax = nullptr;
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * A->count(), (void**)&cnt));
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * A->nb, (void**)&vmax));
-    VX_CUDA(cudaMemsetAsync(vmax, 0, sizeof(unsigned) * A->nb, og.st));
-    {
-        VX_LAUNCH(og.c, og.s, "ccl_zero_roots_kernel");
-        ccl_zero_roots_kernel<<<grid, kCclThreads, 0, og.st>>>(L, bits, cnt, g);
-    }
-    VX_TRY(check_launch("ccl_zero_roots_kernel"));
-    {
-        VX_LAUNCH(og.c, og.s, "ccl_count_kernel");
-        ccl_count_kernel<<<grid, kCclThreads, 0, og.st>>>(L, bits, cnt, g);
-    }
-    VX_TRY(check_launch("ccl_count_kernel"));
-    {
-        VX_LAUNCH(og.c, og.s, "ccl_max_kernel");
-        ccl_max_kernel<<<grid, kCclThreads, 0, og.st>>>(L, bits, cnt, vmax, g);
-    }
-    VX_TRY(check_launch("ccl_max_kernel"));
     Image* O = nullptr;
-    VX_TRY(new_image(og.c, VX_U8, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
-    {
-        VX_LAUNCH(og.c, og.s, "ccl_select_kernel");
-        ccl_select_kernel<SEL_MAXVOL><<<grid, kCclThreads, 0, og.st>>>(L, bits, O->d, cnt, vmax, g);
+    int r = scratch_alloc(og.c, og.s, sizeof(unsigned) * cb.cap, (void**)&cnt);
+    if (r == VX_OK) r = scratch_alloc(og.c, og.s, sizeof(unsigned) * A->nb, (void**)&vmax);
+    if (r == VX_OK) r = ccl_sizes_of(og, cb, cnt, vmax);
+    if (r == VX_OK) r = new_bits_out(og, A->nx, A->ny, A->nz, A->nb, A->sp, &O);
+    if (r == VX_OK) {
+        {
+            VX_LAUNCH(og.c, og.s, "ccl_select_kernel");
+            ccl_select_kernel<SEL_MAXVOL><<<cb.grid, kCclThreads, 0, og.st>>>(cb.P, cb.bits, cb.wbase, O->bits, cnt, vmax,
+                                                                             nullptr, cb.g);
+        }
+        r = check_launch("ccl_select_kernel");
     }
-    int r = check_launch("ccl_select_kernel");
-    if (r == VX_OK) r = scratch_free(og.c, og.s, L);
-    if (r == VX_OK) r = scratch_free(og.c, og.s, bits);
-    if (r == VX_OK) r = scratch_free(og.c, og.s, cnt);
-    if (r == VX_OK) r = scratch_free(og.c, og.s, vmax);
-    if (r != VX_OK) { drop(O); return r; }
+    if (cnt) scratch_free(og.c, og.s, cnt);
+    if (vmax) scratch_free(og.c, og.s, vmax);
+    ccl_free(og.c, og.s, cb);
+    if (r != VX_OK) { if (O) drop(O); return r; }
     return og.finish(O, out);
 }
 
@@ -700,10 +811,9 @@ int32_t vx_maxvol(vx_ctx ctx, vx_img a, int32_t conn, vx_img* out) {
 namespace vx {
 struct CclState {
     Ctx* c = nullptr;
-    unsigned *L = nullptr, *bits = nullptr;
+    CclBufs b;
+    unsigned* npos = nullptr;   // first-voxel positions of the nodes, made by the first vx_ccl_plane
     unsigned* cnt = nullptr;    // per-root voxel counts, allocated by vx_ccl_count
-    Geo g;
-    unsigned grid = 0;
     int nx = 0, ny = 0, nz = 0, nb = 0;
     float sp[3] = {1.f, 1.f, 1.f};
     cudaEvent_t ev = nullptr;   // last operation enqueued on the state
@@ -740,14 +850,17 @@ int32_t vx_ccl_create(vx_ctx ctx, vx_img b, int32_t conn, vx_ccl* out) {
     OpGuard og;
     VX_TRY(og.begin(ctx));
     Image* B = nullptr;
-    VX_TRY(og.input(b, &B, VX_U8));
+    const unsigned* Bb = nullptr;
+    VX_TRY(og.input_bits(b, &B, &Bb));
     CclState* st = new CclState();
     st->c = og.c; st->home = og.s;
     st->nx = B->nx; st->ny = B->ny; st->nz = B->nz; st->nb = B->nb;
     st->sp[0] = B->sp[0]; st->sp[1] = B->sp[1]; st->sp[2] = B->sp[2];
-    int rc = ccl_label(og, B, conn == VX_CONN_FULL, &st->L, &st->bits, &st->g, &st->grid);
-    if (rc == VX_OK && cudaEventCreateWithFlags(&st->ev, cudaEventDisableTiming) != cudaSuccess)
+    int rc = ccl_label(og, B, Bb, conn == VX_CONN_FULL, &st->b);
+    if (rc == VX_OK && cudaEventCreateWithFlags(&st->ev, cudaEventDisableTiming) != cudaSuccess) {
+        ccl_free(og.c, og.s, st->b);
         rc = fail(VX_E_CUDA, "event creation failed");
+    }
     if (rc != VX_OK) { delete st; return rc; }
     VX_TRY(state_leave(og, st));
     VX_TRY(og.finish_scalar());
@@ -762,12 +875,13 @@ int32_t vx_ccl_seed(vx_ctx ctx, vx_ccl state, vx_img a) {
     CclState* st = nullptr;
     VX_TRY(state_enter(og, ctx, state, &st));
     Image* A = nullptr;
-    VX_TRY(og.input(a, &A, VX_U8));
+    const unsigned* Ab = nullptr;
+    VX_TRY(og.input_bits(a, &A, &Ab));
     VX_REQUIRE(A->nx == st->nx && A->ny == st->ny && A->nz == st->nz && A->nb == st->nb, VX_E_SHAPE_MISMATCH,
                "seed image does not have the shape of the labelled image");
     {
         VX_LAUNCH(og.c, og.s, "ccl_seed_kernel");
-        ccl_seed_kernel<<<st->grid, kCclThreads, 0, og.st>>>((const uint8_t*)A->d, st->L, st->bits, st->g);
+        ccl_seed_kernel<<<st->b.grid, kCclThreads, 0, og.st>>>(Ab, st->b.P, st->b.bits, st->b.wbase, st->b.g);
     }
     VX_TRY(check_launch("ccl_seed_kernel"));
     VX_TRY(state_leave(og, st));
@@ -780,15 +894,16 @@ int32_t vx_ccl_plane(vx_ctx ctx, vx_ccl state, int32_t z, vx_img* labels, vx_img
     CclState* st = nullptr;
     VX_TRY(state_enter(og, ctx, state, &st));
     VX_REQUIRE(z >= 0 && z < st->nz, VX_E_INVALID_ARG, "plane %d outside [0,%d)", z, st->nz);
+    if (st->npos == nullptr) VX_TRY(ccl_npos(og, st->b, &st->npos));
     Image *Lb = nullptr, *Rc = nullptr;
     VX_TRY(new_image(og.c, VX_U32, st->nx, st->ny, 1, st->nb, st->sp, &Lb));
     int rc = new_image(og.c, VX_U8, st->nx, st->ny, 1, st->nb, st->sp, &Rc);
     if (rc != VX_OK) { drop(Lb); return rc; }
-    const unsigned long long words = (unsigned long long)st->g.nwx * st->ny * st->nb;
+    const unsigned long long words = (unsigned long long)st->b.g.nwx * st->ny * st->nb;
     {
         VX_LAUNCH(og.c, og.s, "ccl_plane_kernel");
         ccl_plane_kernel<<<(unsigned)((words + kCclThreads - 1) / kCclThreads), kCclThreads, 0, og.st>>>(
-            st->L, st->bits, (unsigned*)Lb->d, (uint8_t*)Rc->d, st->g, z);
+            st->b.P, st->b.bits, st->b.wbase, st->npos, (unsigned*)Lb->d, (uint8_t*)Rc->d, st->b.g, z);
     }
     rc = check_launch("ccl_plane_kernel");
     if (rc == VX_OK) rc = state_leave(og, st);
@@ -812,7 +927,8 @@ int32_t vx_ccl_flag(vx_ctx ctx, vx_ccl state, const uint32_t* labels, uint64_t n
     VX_CUDA(cudaMemcpyAsync(d, labels, sizeof(unsigned) * n, cudaMemcpyDefault, og.st));
     {
         VX_LAUNCH(og.c, og.s, "ccl_flag_labels_kernel");
-        ccl_flag_labels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, og.st>>>(st->L, d, (size_t)n, (unsigned)st->g.nvox);
+        ccl_flag_labels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, og.st>>>(st->b.P, st->b.bits, st->b.wbase, d, (size_t)n,
+                                                                              st->b.g);
     }
     VX_TRY(check_launch("ccl_flag_labels_kernel"));
     VX_TRY(scratch_free(og.c, og.s, d));
@@ -825,10 +941,11 @@ int32_t vx_ccl_select(vx_ctx ctx, vx_ccl state, vx_img* out) {
     CclState* st = nullptr;
     VX_TRY(state_enter(og, ctx, state, &st));
     Image* O = nullptr;
-    VX_TRY(new_image(og.c, VX_U8, st->nx, st->ny, st->nz, st->nb, st->sp, &O));
+    VX_TRY(new_bits_out(og, st->nx, st->ny, st->nz, st->nb, st->sp, &O));
     {
         VX_LAUNCH(og.c, og.s, "ccl_select_kernel");
-        ccl_select_kernel<SEL_THROUGH><<<st->grid, kCclThreads, 0, og.st>>>(st->L, st->bits, O->d, nullptr, nullptr, st->g);
+        ccl_select_kernel<SEL_THROUGH><<<st->b.grid, kCclThreads, 0, og.st>>>(st->b.P, st->b.bits, st->b.wbase, O->bits, nullptr,
+                                                                             nullptr, nullptr, st->b.g);
     }
     int rc = check_launch("ccl_select_kernel");
     if (rc == VX_OK) rc = state_leave(og, st);
@@ -844,27 +961,14 @@ int32_t vx_ccl_count(vx_ctx ctx, vx_ccl state, uint64_t* local_max) {
     VX_TRY(state_enter(og, ctx, state, &st));
     VX_REQUIRE(st->nb == 1, VX_E_UNSUPPORTED, "vx_ccl_count takes a single-volume state");
     unsigned* vmax = nullptr;
-    if (st->cnt == nullptr) VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * st->g.nvox, (void**)&st->cnt));
+    if (st->cnt == nullptr) VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * st->b.cap, (void**)&st->cnt));
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned), (void**)&vmax));
-    VX_CUDA(cudaMemsetAsync(vmax, 0, sizeof(unsigned), og.st));
-    {
-        VX_LAUNCH(og.c, og.s, "ccl_zero_roots_kernel");
-        ccl_zero_roots_kernel<<<st->grid, kCclThreads, 0, og.st>>>(st->L, st->bits, st->cnt, st->g);
-    }
-    VX_TRY(check_launch("ccl_zero_roots_kernel"));
-    {
-        VX_LAUNCH(og.c, og.s, "ccl_count_kernel");
-        ccl_count_kernel<<<st->grid, kCclThreads, 0, og.st>>>(st->L, st->bits, st->cnt, st->g);
-    }
-    VX_TRY(check_launch("ccl_count_kernel"));
-    {
-        VX_LAUNCH(og.c, og.s, "ccl_max_kernel");
-        ccl_max_kernel<<<st->grid, kCclThreads, 0, og.st>>>(st->L, st->bits, st->cnt, vmax, st->g);
-    }
-    VX_TRY(check_launch("ccl_max_kernel"));
+    int rc = ccl_sizes_of(og, st->b, st->cnt, vmax);
     unsigned h = 0;
-    VX_CUDA(cudaMemcpyAsync(&h, vmax, sizeof(unsigned), cudaMemcpyDeviceToHost, og.st));
-    VX_TRY(scratch_free(og.c, og.s, vmax));
+    if (rc == VX_OK && cudaMemcpyAsync(&h, vmax, sizeof(unsigned), cudaMemcpyDeviceToHost, og.st) != cudaSuccess)
+        rc = fail(VX_E_CUDA, "copy of the maximum failed");
+    scratch_free(og.c, og.s, vmax);
+    VX_TRY(rc);
     VX_TRY(state_leave(og, st));
     VX_CUDA(cudaStreamSynchronize(og.st));
     *local_max = h;
@@ -879,18 +983,18 @@ int32_t vx_ccl_sizes(vx_ctx ctx, vx_ccl state, const uint32_t* labels, uint64_t 
     VX_REQUIRE(st->cnt != nullptr, VX_E_INVALID_ARG, "call vx_ccl_count first");
     if (n == 0) return og.finish_scalar();
     VX_REQUIRE(labels != nullptr && sizes != nullptr, VX_E_INVALID_ARG, "NULL argument");
+    Scratch sc(og.c, og.s);
     unsigned *d = nullptr, *o = nullptr;
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * n, (void**)&d));
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * n, (void**)&o));
+    VX_TRY(sc.alloc(sizeof(unsigned) * n, &d));
+    VX_TRY(sc.alloc(sizeof(unsigned) * n, &o));
     VX_CUDA(cudaMemcpyAsync(d, labels, sizeof(unsigned) * n, cudaMemcpyDefault, og.st));
     {
         VX_LAUNCH(og.c, og.s, "ccl_sizes_kernel");
-        ccl_sizes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, og.st>>>(st->L, st->cnt, d, (size_t)n, (unsigned)st->g.nvox, o);
+        ccl_sizes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, og.st>>>(st->b.P, st->b.bits, st->b.wbase, st->cnt, d, (size_t)n,
+                                                                        st->b.g, o);
     }
     VX_TRY(check_launch("ccl_sizes_kernel"));
     VX_CUDA(cudaMemcpyAsync(sizes, o, sizeof(unsigned) * n, cudaMemcpyDefault, og.st));
-    VX_TRY(scratch_free(og.c, og.s, d));
-    VX_TRY(scratch_free(og.c, og.s, o));
     VX_TRY(state_leave(og, st));
     VX_CUDA(cudaStreamSynchronize(og.st));
     return og.finish_scalar();
@@ -903,7 +1007,7 @@ int32_t vx_ccl_flag_size(vx_ctx ctx, vx_ccl state, uint32_t size) {
     VX_REQUIRE(st->cnt != nullptr, VX_E_INVALID_ARG, "call vx_ccl_count first");
     if (size != 0) {
         VX_LAUNCH(og.c, og.s, "ccl_flag_size_kernel");
-        ccl_flag_size_kernel<<<st->grid, kCclThreads, 0, og.st>>>(st->L, st->bits, st->cnt, size, st->g);
+        ccl_flag_size_kernel<<<kNodeGrid, kCclThreads, 0, og.st>>>(st->b.P, st->cnt, size, st->b.ntotal());
     }
     VX_TRY(check_launch("ccl_flag_size_kernel"));
     VX_TRY(state_leave(og, st));
@@ -920,8 +1024,8 @@ int32_t vx_ccl_destroy(vx_ctx ctx, vx_ccl state) {
     }
     // the scratch goes back to the free list of the calling stream, which is ordered after the
     // last operation on the state
-    scratch_free(og.c, og.s, st->L);
-    scratch_free(og.c, og.s, st->bits);
+    ccl_free(og.c, og.s, st->b);
+    if (st->npos) scratch_free(og.c, og.s, st->npos);
     if (st->cnt) scratch_free(og.c, og.s, st->cnt);
     cudaEventDestroy(st->ev);
     delete st;

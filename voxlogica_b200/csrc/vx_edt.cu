@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <vector>
 
+#include "vx_bits.h"
 #include "vx_internal.h"
 
 namespace vx {
@@ -59,7 +60,7 @@ __device__ __forceinline__ int next_set(const unsigned* __restrict__ fl, int pos
 // ------------------------------------------------------------------ x pass
 // one warp per row.  g1 = (dx*sx)^2 to the nearest feature in the row, +inf if none.
 __global__ void __launch_bounds__(kEdtThreads)
-edt_x_kernel(const uint8_t* __restrict__ img, float* __restrict__ g1, unsigned* __restrict__ rowflag,
+edt_x_kernel(const unsigned* __restrict__ img, float* __restrict__ g1, unsigned* __restrict__ rowflag,
              unsigned* __restrict__ planeflag, int nx, int ny, int nz, unsigned long long rows,
              float sx) {
     __shared__ unsigned sm[kEdtThreads / 32][kMaxRowWords];
@@ -67,14 +68,15 @@ edt_x_kernel(const uint8_t* __restrict__ img, float* __restrict__ g1, unsigned* 
     const unsigned long long row = (unsigned long long)blockIdx.x * (kEdtThreads / 32) + warp;
     if (row >= rows) return;
     const int nwx = (nx + 31) >> 5;
-    const uint8_t* src = img + row * nx;
+    // the row's words straight from the image's bit form, one per lane
     unsigned any = 0;
-    for (int c = 0; c < nwx; c++) {
-        int x = c * 32 + lane;
-        unsigned m = __ballot_sync(0xffffffffu, x < nx && src[x] != 0);
-        if (lane == 0) sm[warp][c] = m;
+    for (int c0 = 0; c0 < nwx; c0 += 32) {
+        const int c = c0 + lane;
+        const unsigned m = c < nwx ? flat_row_word(img, row, c, nx) : 0u;
+        if (c < nwx) sm[warp][c] = m;
         any |= m;
     }
+    any = __reduce_or_sync(0xffffffffu, any);
     __syncwarp();
     if (lane == 0 && any) {
         const int y = (int)(row % ny);
@@ -300,13 +302,13 @@ __device__ __forceinline__ unsigned pack_word(const uint8_t* __restrict__ img, u
 // only the first and last lane of a warp pack theirs again), rowany[row] = 1 when the row
 // holds a set voxel.
 __global__ void __launch_bounds__(kEdtThreads)
-pack_bits_kernel(const uint8_t* __restrict__ img, unsigned* __restrict__ D, int nx, int nwx,
+pack_bits_kernel(const unsigned* __restrict__ img, unsigned* __restrict__ D, int nx, int nwx,
                  unsigned long long nwords, int emax, uint8_t* __restrict__ rowany) {
     const unsigned long long wid = (unsigned long long)blockIdx.x * kEdtThreads + threadIdx.x;
     const bool ok = wid < nwords;
     const unsigned long long row = (ok ? wid : 0) / nwx;
     const int w = (int)((ok ? wid : 0) % nwx);
-    const unsigned cur = ok ? pack_word(img, row, w, nx) : 0u;
+    const unsigned cur = ok ? flat_row_word(img, row, w, nx) : 0u;
     unsigned prev = __shfl_up_sync(0xffffffffu, cur, 1), next = __shfl_down_sync(0xffffffffu, cur, 1);
     if (!ok) return;
     D[wid] = cur;
@@ -314,9 +316,9 @@ pack_bits_kernel(const uint8_t* __restrict__ img, unsigned* __restrict__ D, int 
     if (emax <= 0) return;
     const int lane = threadIdx.x & 31;
     if (w == 0) prev = 0u;
-    else if (lane == 0) prev = pack_word(img, row, w - 1, nx);
+    else if (lane == 0) prev = flat_row_word(img, row, w - 1, nx);
     if (w + 1 >= nwx) next = 0u;
-    else if (lane == 31) next = pack_word(img, row, w + 1, nx);
+    else if (lane == 31) next = flat_row_word(img, row, w + 1, nx);
     unsigned acc = cur;
     for (int e = 1; e <= emax; e++) {
         acc |= (cur << e) | (prev >> (32 - e)) | (cur >> e) | (next << (32 - e));
@@ -338,10 +340,10 @@ __device__ __forceinline__ unsigned bytes_of(unsigned nib) {
 // load-offset / add / load / or: entry offsets (e*nwords + (dz*ny+dy)*nwx) are precomputed on
 // the host, and words whose whole ball lies inside the volume skip the bounds tests.
 __global__ void __launch_bounds__(kEdtThreads)
-ball_or_kernel(const unsigned* __restrict__ D, uint8_t* __restrict__ out, int nx, int ny, int nz,
+ball_or_kernel(const unsigned* __restrict__ D, unsigned* __restrict__ out, int nx, int ny, int nz,
                int nwx, unsigned long long nwords, const long long* __restrict__ boff,
                const int* __restrict__ bdyz, int nball, int wy, int wz, int invert,
-               const uint8_t* __restrict__ rowany) {
+               const uint8_t* __restrict__ rowany, int align16) {
     // Rows of the input that hold no set voxel are flagged by the packing kernel.  When no row
     // that any word of this block can reach is occupied, the block writes its (constant) output
     // without touching the bit rows: the dilation half of `filter` runs on what an erosion left
@@ -395,23 +397,8 @@ ball_or_kernel(const unsigned* __restrict__ D, uint8_t* __restrict__ out, int nx
         }
     }
     acc &= ~pad;
-    if (invert) acc = ~acc;
-    const int x0 = w * 32;
-    uint8_t* dst = out + row * nx + x0;
-    if ((nx & 15) == 0) {
-        uint4 v;
-        v.x = bytes_of(acc & 0xfu); v.y = bytes_of((acc >> 4) & 0xfu);
-        v.z = bytes_of((acc >> 8) & 0xfu); v.w = bytes_of((acc >> 12) & 0xfu);
-        *reinterpret_cast<uint4*>(dst) = v;
-        if (x0 + 16 < nx) {
-            v.x = bytes_of((acc >> 16) & 0xfu); v.y = bytes_of((acc >> 20) & 0xfu);
-            v.z = bytes_of((acc >> 24) & 0xfu); v.w = bytes_of((acc >> 28) & 0xfu);
-            *reinterpret_cast<uint4*>(dst + 16) = v;
-        }
-    } else {
-        const int lim = min(32, nx - x0);
-        for (int b = 0; b < lim; b++) dst[b] = (uint8_t)((acc >> b) & 1u);
-    }
+    if (invert) acc = ~acc & ~pad;
+    flat_store_row_word(out, row, w, nx, acc, align16 != 0);   // the result stays in bit form
 }
 
 // ------------------------------------------------------------------ host: thresholds and the ball
@@ -468,7 +455,7 @@ static bool build_ball(const float sp[3], float T, int nx, int ny, int nz, Ball*
 }
 
 // squared-distance passes shared by vx_edt and the large-radius fallback of vx_dist_*
-static int edt_passes(OpGuard& og, const Image* A, void* out, int final_mode, float T, int invert) {
+static int edt_passes(OpGuard& og, const Image* A, const unsigned* Abits, void* out, int final_mode, float T, int invert) {
     const size_t total = A->count();
     const unsigned long long rows = (unsigned long long)A->nb * A->nz * A->ny;
     VX_REQUIRE(A->nx <= kMaxRowWords * 32, VX_E_UNSUPPORTED, "vx_edt supports nx <= %d",
@@ -486,7 +473,7 @@ static int edt_passes(OpGuard& og, const Image* A, void* out, int final_mode, fl
     {
         VX_LAUNCH(og.c, og.s, "edt_x_kernel");
         unsigned grid = (unsigned)((rows + kEdtThreads / 32 - 1) / (kEdtThreads / 32));
-        edt_x_kernel<<<grid, kEdtThreads, 0, og.st>>>((const uint8_t*)A->d, g1, rowflag, planeflag,
+        edt_x_kernel<<<grid, kEdtThreads, 0, og.st>>>(Abits, g1, rowflag, planeflag,
                                                      A->nx, A->ny, A->nz, rows, A->sp[0]);
     }
     VX_TRY(check_launch("edt_x_kernel"));
@@ -542,7 +529,7 @@ static int edt_passes(OpGuard& og, const Image* A, void* out, int final_mode, fl
 
 // ---- the two halves of the transform, for a caller that owns one z-slab ----
 // x and y passes only: squared distance inside each plane (+inf where the plane has no feature)
-static int edt_xy_only(OpGuard& og, const Image* A, float* out) {
+static int edt_xy_only(OpGuard& og, const Image* A, const unsigned* Abits, float* out) {
     const size_t total = A->count();
     const unsigned long long rows = (unsigned long long)A->nb * A->nz * A->ny;
     VX_REQUIRE(A->nx <= kMaxRowWords * 32, VX_E_UNSUPPORTED, "vx_edt supports nx <= %d", kMaxRowWords * 32);
@@ -556,7 +543,7 @@ static int edt_xy_only(OpGuard& og, const Image* A, float* out) {
     {
         VX_LAUNCH(og.c, og.s, "edt_x_kernel");
         unsigned grid = (unsigned)((rows + kEdtThreads / 32 - 1) / (kEdtThreads / 32));
-        edt_x_kernel<<<grid, kEdtThreads, 0, og.st>>>((const uint8_t*)A->d, g1, flags, flags + n_rowflag, A->nx, A->ny,
+        edt_x_kernel<<<grid, kEdtThreads, 0, og.st>>>(Abits, g1, flags, flags + n_rowflag, A->nx, A->ny,
                                                      A->nz, rows, A->sp[0]);
     }
     VX_TRY(check_launch("edt_x_kernel"));
@@ -618,14 +605,23 @@ static int dist_threshold(vx_ctx ctx, vx_img a, float r, bool strict, int invert
     OpGuard og;
     VX_TRY(og.begin(ctx));
     Image* A = nullptr;
-    VX_TRY(og.input(a, &A, VX_U8));
+    const unsigned* Abits = nullptr;
+    VX_TRY(og.input_bits(a, &A, &Abits));
     const float T = threshold_for(r, strict);
     Image* O = nullptr;
-    VX_TRY(new_image(og.c, VX_U8, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
     Ball ball;
     int emax = 0;
     int rc = VX_OK;
-    if (build_ball(A->sp, T, A->nx, A->ny, A->nz, &ball, &emax)) {
+    const bool by_ball = build_ball(A->sp, T, A->nx, A->ny, A->nz, &ball, &emax);
+    // the ball dilation works on bits and leaves bits; the large-radius fallback writes bytes
+    if (by_ball) VX_TRY(new_bits_image(og.c, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
+    else VX_TRY(new_image(og.c, VX_U8, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
+    const int align16 = (A->nx % 16) == 0;
+    if (by_ball && !align16) {
+        cudaError_t ce = cudaMemsetAsync(O->bits, 0, O->bit_words() * 4, og.st);
+        if (ce != cudaSuccess) { drop(O); return fail(VX_E_CUDA, "memset: %s", cudaGetErrorString(ce)); }
+    }
+    if (by_ball) {
         const int nwx = (A->nx + 31) / 32;
         const unsigned long long nwords = (unsigned long long)A->nb * A->nz * A->ny * nwx;
         unsigned* D = nullptr;
@@ -640,7 +636,7 @@ static int dist_threshold(vx_ctx ctx, vx_img a, float r, bool strict, int invert
         const unsigned grid = (unsigned)((nwords + kEdtThreads - 1) / kEdtThreads);
         if (rc == VX_OK) {
             { VX_LAUNCH(og.c, og.s, "pack_bits_kernel");
-              pack_bits_kernel<<<grid, kEdtThreads, 0, og.st>>>((const uint8_t*)A->d, D, A->nx, nwx, nwords, emax, rowany); }
+              pack_bits_kernel<<<grid, kEdtThreads, 0, og.st>>>(Abits, D, A->nx, nwx, nwords, emax, rowany); }
             rc = check_launch("pack_bits_kernel");
         }
         long long* boff = nullptr;
@@ -668,19 +664,24 @@ static int dist_threshold(vx_ctx ctx, vx_img a, float r, bool strict, int invert
             }
             if (rc == VX_OK) {
                 { VX_LAUNCH(og.c, og.s, "ball_or_kernel");
-                  ball_or_kernel<<<grid, kEdtThreads, 0, og.st>>>(D, (uint8_t*)O->d, A->nx, A->ny, A->nz, nwx, nwords, boff,
-                                                                 reinterpret_cast<const int*>(boff + ball.n), ball.n, wy, wz, invert, rowany); }
+                  ball_or_kernel<<<grid, kEdtThreads, 0, og.st>>>(D, O->bits, A->nx, A->ny, A->nz, nwx, nwords, boff,
+                                                                 reinterpret_cast<const int*>(boff + ball.n), ball.n, wy, wz, invert, rowany, align16); }
                 rc = check_launch("ball_or_kernel");
             }
             if (boff) scratch_free(og.c, og.s, boff);
         } else if (rc == VX_OK) {   // empty ball: nothing is within the radius
-            cudaError_t ce = cudaMemsetAsync(O->d, invert ? 1 : 0, O->bytes, og.st);
+            const size_t n = O->count();
+            cudaError_t ce = cudaMemsetAsync(O->bits, invert ? 0xff : 0, O->bit_words() * 4, og.st);
+            if (ce == cudaSuccess && invert && (n & 31)) {   // bits past the batch stay 0
+                const unsigned last = (1u << (n & 31)) - 1u;
+                ce = cudaMemcpyAsync(O->bits + (n >> 5), &last, 4, cudaMemcpyHostToDevice, og.st);
+            }
             if (ce != cudaSuccess) rc = fail(VX_E_CUDA, "memset: %s", cudaGetErrorString(ce));
         }
         if (rc == VX_OK) rc = scratch_free(og.c, og.s, D);
         if (rc == VX_OK && rowany) rc = scratch_free(og.c, og.s, rowany);
     } else {
-        rc = edt_passes(og, A, O->d, EDT_THRESH, T, invert);
+        rc = edt_passes(og, A, Abits, O->d, EDT_THRESH, T, invert);
     }
     if (rc != VX_OK) { drop(O); return rc; }
     return og.finish(O, out);
@@ -697,10 +698,11 @@ int32_t vx_edt(vx_ctx ctx, vx_img a, vx_img* out) {
     OpGuard og;
     VX_TRY(og.begin(ctx));
     Image* A = nullptr;
-    VX_TRY(og.input(a, &A, VX_U8));
+    const unsigned* Abits = nullptr;
+    VX_TRY(og.input_bits(a, &A, &Abits));
     Image* O = nullptr;
     VX_TRY(new_image(og.c, VX_F32, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
-    int rc = edt_passes(og, A, O->d, EDT_SQRT, 0.f, 0);
+    int rc = edt_passes(og, A, Abits, O->d, EDT_SQRT, 0.f, 0);
     if (rc != VX_OK) { drop(O); return rc; }
     return og.finish(O, out);
 }
@@ -710,10 +712,11 @@ int32_t vx_edt_sq_xy(vx_ctx ctx, vx_img a, vx_img* out) {
     OpGuard og;
     VX_TRY(og.begin(ctx));
     Image* A = nullptr;
-    VX_TRY(og.input(a, &A, VX_U8));
+    const unsigned* Abits = nullptr;
+    VX_TRY(og.input_bits(a, &A, &Abits));
     Image* O = nullptr;
     VX_TRY(new_image(og.c, VX_F32, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
-    int rc = edt_xy_only(og, A, (float*)O->d);
+    int rc = edt_xy_only(og, A, Abits, (float*)O->d);
     if (rc != VX_OK) { drop(O); return rc; }
     return og.finish(O, out);
 }

@@ -23,7 +23,18 @@ struct Ctx;
 
 // T1: a device-resident batch of volumes.
 struct Image {
+    // Boolean images (dtype VX_U8) have two interchangeable device representations: `d`, one byte
+    // per voxel (0/1), and `bits`, one BIT per voxel -- a flat little-endian bit stream over the
+    // whole batch, bit (i & 31) of word (i >> 5) = voxel i, x fastest (the format of
+    // vx_download_bits).  An operator produces whichever suits it and consumers ask for what they
+    // read (OpGuard::input / input_bits); the missing one is made on demand, once, and kept.
+    // Operators that work in bit space (connected components, distance balls, near/interior, the
+    // boolean pointwise programs, volume) therefore never touch the byte form: 1/8 of the traffic.
     void* d = nullptr;
+    unsigned* bits = nullptr;
+    cudaEvent_t alt_ready = nullptr;   // completion of the representation that was added after publication ...
+    int alt_stream = -1;               // ... and the stream index it was made on
+    bool bits_frozen = false;          // the byte form was handed out as a raw pointer (vx_device_ptr): never cache bits
     size_t bytes = 0;
     int dtype = 0;
     int nx = 0, ny = 0, nz = 0, nb = 0;
@@ -47,6 +58,7 @@ struct Image {
     int q_dtype = 0;              // VX_I16 / VX_U16, 0 = no tag
     bool q_increasing = true;
     const int* q_range() const { return reinterpret_cast<const int*>(static_cast<const char*>(q16) + ((count() + 7) / 8 * 8) * 2); }
+    size_t bit_words() const { return (count() + 31) / 32; }
     size_t nvox() const { return (size_t)nx * ny * nz; }       // per volume
     size_t count() const { return (size_t)nx * ny * nz * nb; }  // whole batch
 };
@@ -135,6 +147,12 @@ inline cudaStream_t stream_of(Ctx* c, int idx) { return c->streams[idx]; }
 // Allocate a new image on the calling thread's stream.  On success *out holds a
 // handle with one reference owned by the caller.
 int new_image(Ctx* c, int dtype, int nx, int ny, int nz, int nb, const float* sp, Image** out);
+// A boolean image that starts life as bits only (im->d == nullptr until somebody needs bytes).
+int new_bits_image(Ctx* c, int nx, int ny, int nz, int nb, const float* sp, Image** out);
+// Make the missing representation of a boolean image on stream index s (no-op when present).
+int ensure_u8(Ctx* c, Image* im, int s);
+int ensure_bits(Ctx* c, Image* im, int s);
+inline size_t bits_alloc_bytes(size_t voxels) { return ((voxels + 127) / 128) * 16 + 64; }   // whole uint4 groups + slack
 // Make `img` safe to read on stream index `s` (waits for its producer if needed).
 int use_input(Ctx* c, Image* img, int s);
 // Called after the consuming kernels were enqueued on stream `s`.
@@ -200,12 +218,18 @@ struct OpGuard {
     int s = 0;
     cudaStream_t st = nullptr;
     std::vector<Image*> ins;
+    std::vector<Image*> metas;  // pinned for metadata only
+    std::vector<void*> temps;   // scratch made for this call (bit copies of frozen images), freed with the guard
     OpGuard() = default;
     OpGuard(const OpGuard&) = delete;
     OpGuard& operator=(const OpGuard&) = delete;
     ~OpGuard();
     int begin(vx_ctx ctx);
+    // A boolean input comes with its byte form (`d`) materialised: kernels written for bytes need
+    // nothing else.  input_bits() is for kernels that read the bit form: no bytes are made.
     int input(vx_img h, Image** out, int want_dtype /*0 = any*/);
+    int input_bits(vx_img h, Image** out, const unsigned** bits);
+    int input_meta(vx_img h, Image** out);   // pinned for its metadata only: no stream ordering, no conversion
     int finish(Image* out_img, vx_img* out);  // publish output + mark inputs used
     int finish_scalar();                       // ops without an image result
 };

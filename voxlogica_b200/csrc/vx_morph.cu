@@ -12,6 +12,7 @@
 // 128-bit register, with the one missing byte on each side fetched from the
 // neighbouring lane by a width-16 shuffle.  Erosion is the same kernel on the
 // complemented input.  HBM: 1 byte read + 1 byte written per voxel.
+#include "vx_bits.h"
 #include "vx_internal.h"
 
 namespace vx {
@@ -206,11 +207,150 @@ border16_kernel(uint4* __restrict__ out, int ncx, int nx, int ny, int nz, size_t
     out[i] = v;
 }
 
+// ---- near / interior on the bit form -----------------------------------------------------------
+// One thread per 32-voxel row word and chunk of kBitZL planes, marching along z.  A plane
+// contributes  A = its three rows (y-1, y, y+1) spread by one voxel in x  and  C = what it gives to
+// the planes above and below; for 26-adjacency C = A, for 6 only the centre row is spread,
+// the rows y+-1 enter A unspread and C is the bare centre row.  out(z) = A(z) | C(z-1) | C(z+1):
+// three row loads per output word instead of nine.  Erosion is the dilation of the complement
+// inside the image (voxels outside do not exist), complemented.  Traffic: 1/8 byte in and out per
+// voxel; the rows of a neighbourhood are L1/L2 hits.
+constexpr int kBitZL = 16;
+
+// word w of the row at stream position p: its bits c and the bits spread by one voxel in x
+template <bool ERODE>
+__device__ __forceinline__ void load_row_bits(const unsigned* __restrict__ fb, unsigned long long p, unsigned vmask,
+                                              bool has_l, bool has_r, unsigned& c, unsigned& xs) {
+    const unsigned long long k = p >> 5;
+    const unsigned sh = (unsigned)p & 31u;
+    const unsigned b = __ldg(fb + k);
+    unsigned l = 0, r = 0;
+    if (sh == 0) {
+        c = b;
+        if (has_l) l = __ldg(fb + k - 1) >> 31;
+        if (has_r) r = __ldg(fb + k + 1) & 1u;
+    } else {
+        const unsigned hi = __ldg(fb + k + 1);
+        c = __funnelshift_r(b, hi, sh);
+        if (has_l) l = (b >> (sh - 1)) & 1u;
+        if (has_r) r = (hi >> sh) & 1u;
+    }
+    c &= vmask;
+    if (ERODE) {
+        c = ~c & vmask;
+        l = has_l ? l ^ 1u : 0u;
+        r = has_r ? r ^ 1u : 0u;
+    }
+    xs = c | (c << 1) | (c >> 1) | l | (r << 31);
+}
+
+template <bool FULL, bool ERODE>
+__global__ void __launch_bounds__(256)
+morph_bits_kernel(const unsigned* __restrict__ in, unsigned* __restrict__ out, int nx, int ny, int nz, int nwx,
+                  int nzc, unsigned nthreads, int align16) {
+    unsigned t = blockIdx.x * 256u + threadIdx.x;
+    if (t >= nthreads) return;
+    const int w = (int)(t % (unsigned)nwx); t /= (unsigned)nwx;
+    const int y = (int)(t % (unsigned)ny); t /= (unsigned)ny;
+    const int zc = (int)(t % (unsigned)nzc);
+    const unsigned vol = t / (unsigned)nzc;
+    const int z0 = zc * kBitZL, z1 = min(nz, z0 + kBitZL);
+    const int valid = min(32, nx - w * 32);
+    const unsigned vmask = valid >= 32 ? 0xffffffffu : ((1u << valid) - 1u);
+    const bool has_l = w > 0, has_r = (w + 1) * 32 < nx;
+    const bool up = y > 0, dn = y + 1 < ny;
+    const unsigned long long plane = (unsigned long long)nx * ny;
+    // stream position of word w of row (y, z) of this volume
+    auto pos = [&](int z) { return ((unsigned long long)vol * nz + z) * plane + (unsigned long long)y * nx + (unsigned)w * 32u; };
+    auto load_plane = [&](int z, unsigned& A, unsigned& C) {
+        A = C = 0u;
+        if (z < 0 || z >= nz) return;
+        const unsigned long long p = pos(z);
+        unsigned c, xs;
+        load_row_bits<ERODE>(in, p, vmask, has_l, has_r, c, xs);
+        A = xs;
+        C = FULL ? xs : c;
+        if (up) {
+            load_row_bits<ERODE>(in, p - nx, vmask, has_l, has_r, c, xs);
+            A |= FULL ? xs : c;
+        }
+        if (dn) {
+            load_row_bits<ERODE>(in, p + nx, vmask, has_l, has_r, c, xs);
+            A |= FULL ? xs : c;
+        }
+        if (FULL) C = A;
+    };
+    unsigned Am, Cm, A0, C0, A1, C1;
+    load_plane(z0 - 1, Am, Cm);
+    load_plane(z0, A0, C0);
+    for (int z = z0; z < z1; z++) {
+        load_plane(z + 1, A1, C1);
+        unsigned acc = A0 | Cm | C1;
+        if (ERODE) acc = ~acc;
+        flat_store32(out, pos(z), valid, acc & vmask, align16 != 0);
+        Cm = C0; A0 = A1; C0 = C1;
+    }
+}
+
+// faces of every volume, as bits
+__global__ void __launch_bounds__(256)
+border_bits_kernel(unsigned* __restrict__ out, int nx, int ny, int nz, int nwx, unsigned nwords, int align16) {
+    const unsigned wid = blockIdx.x * 256u + threadIdx.x;
+    if (wid >= nwords) return;
+    const unsigned row = wid / (unsigned)nwx;
+    const int w = (int)(wid - row * (unsigned)nwx);
+    const unsigned pz = row / (unsigned)ny;
+    const int y = (int)(row - pz * (unsigned)ny);
+    const int z = (int)(pz % (unsigned)nz);
+    const int valid = min(32, nx - w * 32);
+    const unsigned vmask = valid >= 32 ? 0xffffffffu : ((1u << valid) - 1u);
+    // an axis of extent 1 has no faces (a 2D image is not all border)
+    const bool face = (ny > 1 && (y == 0 || y == ny - 1)) || (nz > 1 && (z == 0 || z == nz - 1));
+    unsigned v = face ? vmask : 0u;
+    if (nx > 1 && w == 0) v |= 1u;
+    if (nx > 1 && (w + 1) * 32 >= nx) v |= 1u << (valid - 1);
+    flat_store32(out, (unsigned long long)row * nx + (unsigned)w * 32u, valid, v, align16 != 0);
+}
+
+static int morph_bits(vx_ctx ctx, vx_img a, int conn, bool erode, vx_img* out) {
+    OpGuard g;
+    VX_TRY(g.begin(ctx));
+    Image* A = nullptr;
+    const unsigned* Ab = nullptr;
+    VX_TRY(g.input_bits(a, &A, &Ab));
+    Image* O = nullptr;
+    VX_TRY(new_bits_image(g.c, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
+    const int align16 = (A->nx % 16) == 0;
+    if (!align16) {
+        cudaError_t ce = cudaMemsetAsync(O->bits, 0, O->bit_words() * 4, g.st);
+        if (ce != cudaSuccess) { drop(O); return fail(VX_E_CUDA, "memset: %s", cudaGetErrorString(ce)); }
+    }
+    const int nwx = (A->nx + 31) / 32;
+    const int nzc = (A->nz + kBitZL - 1) / kBitZL;
+    const unsigned long long nth = (unsigned long long)A->nb * nzc * A->ny * nwx;
+    if (nth >= 0xffffffffull) { drop(O); return fail(VX_E_UNSUPPORTED, "batch too large for one launch"); }
+    const unsigned grid = (unsigned)((nth + 255) / 256);
+    const bool full = conn == VX_CONN_FULL;
+    {
+        VX_LAUNCH(g.c, g.s, "morph_bits_kernel");
+        if (full && !erode) morph_bits_kernel<true, false><<<grid, 256, 0, g.st>>>(Ab, O->bits, A->nx, A->ny, A->nz, nwx, nzc, (unsigned)nth, align16);
+        else if (full) morph_bits_kernel<true, true><<<grid, 256, 0, g.st>>>(Ab, O->bits, A->nx, A->ny, A->nz, nwx, nzc, (unsigned)nth, align16);
+        else if (!erode) morph_bits_kernel<false, false><<<grid, 256, 0, g.st>>>(Ab, O->bits, A->nx, A->ny, A->nz, nwx, nzc, (unsigned)nth, align16);
+        else morph_bits_kernel<false, true><<<grid, 256, 0, g.st>>>(Ab, O->bits, A->nx, A->ny, A->nz, nwx, nzc, (unsigned)nth, align16);
+    }
+    int r = check_launch("morph_bits_kernel");
+    if (r != VX_OK) { drop(O); return r; }
+    return g.finish(O, out);
+}
+
 static int morph(vx_ctx ctx, vx_img a, int conn, bool erode, const void* lo_plane, const void* hi_plane,
                  vx_img* out) {
     VX_REQUIRE(out != nullptr, VX_E_INVALID_ARG, "out is NULL");
     VX_REQUIRE(conn == VX_CONN_FACE || conn == VX_CONN_FULL, VX_E_INVALID_ARG,
                "adjacency must be 6 or 26, got %d", conn);
+    // without halo planes the operator runs on the bit form; the halo variants read the neighbours'
+    // boundary planes as bytes from peer memory and keep the byte kernel
+    if (lo_plane == nullptr && hi_plane == nullptr) return morph_bits(ctx, a, conn, erode, out);
     OpGuard g;
     VX_TRY(g.begin(ctx));
     Image* A = nullptr;
@@ -274,17 +414,20 @@ int32_t vx_border(vx_ctx ctx, vx_img like, vx_img* out) {
     OpGuard g;
     VX_TRY(g.begin(ctx));
     Image* A = nullptr;
-    VX_TRY(g.input(like, &A, 0));
+    VX_TRY(g.input_meta(like, &A));   // only the shape is used
     Image* O = nullptr;
-    VX_TRY(new_image(g.c, VX_U8, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
-    size_t total = A->count();
-    if ((A->nx & 15) == 0) {
-        size_t nchunks = total / 16;
+    VX_TRY(new_bits_image(g.c, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
+    const int align16 = (A->nx % 16) == 0;
+    if (!align16) {
+        cudaError_t ce = cudaMemsetAsync(O->bits, 0, O->bit_words() * 4, g.st);
+        if (ce != cudaSuccess) { drop(O); return fail(VX_E_CUDA, "memset: %s", cudaGetErrorString(ce)); }
+    }
+    const int nwx = (A->nx + 31) / 32;
+    const unsigned long long nwords = (unsigned long long)A->nb * A->nz * A->ny * nwx;
+    if (nwords >= 0xffffffffull) { drop(O); return fail(VX_E_UNSUPPORTED, "batch too large for one launch"); }
+    {
         VX_LAUNCH(g.c, g.s, "border_kernel");
-        border16_kernel<<<(unsigned)((nchunks + 255) / 256), 256, 0, g.st>>>((uint4*)O->d, A->nx / 16, A->nx, A->ny, A->nz, nchunks);
-    } else {
-        VX_LAUNCH(g.c, g.s, "border_kernel");
-        border_kernel<<<(unsigned)((total + 255) / 256), 256, 0, g.st>>>((uint8_t*)O->d, A->nx, A->ny, A->nz, total);
+        border_bits_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, g.st>>>(O->bits, A->nx, A->ny, A->nz, nwx, (unsigned)nwords, align16);
     }
     int r = check_launch("border_kernel");
     if (r != VX_OK) { drop(O); return r; }

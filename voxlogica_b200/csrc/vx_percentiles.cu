@@ -22,6 +22,7 @@
 #include <mutex>
 #include <type_traits>
 
+#include "vx_bits.h"
 #include "vx_internal.h"
 
 namespace vx {
@@ -520,7 +521,7 @@ __device__ __forceinline__ unsigned pq_ucode(unsigned h) {   // 16 raw bits -> o
 // grid (blocks, nb), dynamic shared memory kPqWin * 4.  hist is [nb][65536], zeroed by the caller.
 template <typename T>
 __global__ void __launch_bounds__(256)
-pq_hist_kernel(const T* __restrict__ q, const uint8_t* __restrict__ mask, size_t nvox, const int* __restrict__ qrange,
+pq_hist_kernel(const T* __restrict__ q, const unsigned* __restrict__ mask, size_t nvox, const int* __restrict__ qrange,
                unsigned* __restrict__ hist) {
     extern __shared__ unsigned pq_sh[];
     const int ulo = qrange[0], uhi = qrange[1];
@@ -532,7 +533,8 @@ pq_hist_kernel(const T* __restrict__ q, const uint8_t* __restrict__ mask, size_t
         for (int i = threadIdx.x; i < span; i += 256) pq_sh[i] = 0u;
     __syncthreads();
     const T* qv = q + vol * nvox;
-    const uint8_t* mv = mask + vol * nvox;
+    // the mask is read in its bit form: the 16 voxels of group g are half word g of the volume
+    const unsigned short* mh = reinterpret_cast<const unsigned short*>(mask) + (vol * nvox) / 16;
     auto add = [&](unsigned h) {
         const int u = (int)pq_ucode<T>(h);
         if (win) atomicAdd(&pq_sh[u - ulo], 1u); else atomicAdd(&hv[u], 1u);
@@ -541,19 +543,18 @@ pq_hist_kernel(const T* __restrict__ q, const uint8_t* __restrict__ mask, size_t
     if ((nvox & 15) == 0) {
         const size_t ng = nvox >> 4;
         for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < ng; g += (size_t)gridDim.x * 256) {
-            const uint4 m = __ldg(reinterpret_cast<const uint4*>(mv) + g);
-            if ((m.x | m.y | m.z | m.w) == 0u) continue;
+            const unsigned m = __ldg(mh + g);
+            if (m == 0u) continue;
             const uint4 a = __ldg(reinterpret_cast<const uint4*>(qv) + 2 * g);
             const uint4 b = __ldg(reinterpret_cast<const uint4*>(qv) + 2 * g + 1);
-            const unsigned mw[4] = {m.x, m.y, m.z, m.w};
             const unsigned qw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int i = 0; i < 16; i++)
-                if ((mw[i >> 2] >> (8 * (i & 3))) & 0xffu) add((qw[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+                if ((m >> i) & 1u) add((qw[i >> 1] >> (16 * (i & 1))) & 0xffffu);
         }
     } else {
         for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvox; i += (size_t)gridDim.x * 256)
-            if (mv[i]) add((unsigned)(unsigned short)qv[i]);
+            if (flat_bit(mask, vol * nvox + i)) add((unsigned)(unsigned short)qv[i]);
     }
     if (win) {
         __syncthreads();
@@ -627,7 +628,7 @@ pq_table_kernel(const unsigned* __restrict__ hist, const int* __restrict__ qrang
 // out = mask ? table[code] : 0.  grid (blocks, nb), dynamic shared memory kPqWin * 4.
 template <typename T>
 __global__ void __launch_bounds__(256)
-pq_apply_kernel(const T* __restrict__ q, const uint8_t* __restrict__ mask, size_t nvox, const int* __restrict__ qrange,
+pq_apply_kernel(const T* __restrict__ q, const unsigned* __restrict__ mask, size_t nvox, const int* __restrict__ qrange,
                 const float* __restrict__ table, float* __restrict__ out) {
     extern __shared__ unsigned pq_sh[];
     float* tab = reinterpret_cast<float*>(pq_sh);
@@ -640,7 +641,7 @@ pq_apply_kernel(const T* __restrict__ q, const uint8_t* __restrict__ mask, size_
         for (int i = threadIdx.x; i < span; i += 256) tab[i] = tv[ulo + i];
     __syncthreads();
     const T* qv = q + vol * nvox;
-    const uint8_t* mv = mask + vol * nvox;
+    const unsigned short* mh = reinterpret_cast<const unsigned short*>(mask) + (vol * nvox) / 16;
     float* ov = out + vol * nvox;
     auto look = [&](unsigned h) {
         const int u = (int)pq_ucode<T>(h);
@@ -649,27 +650,26 @@ pq_apply_kernel(const T* __restrict__ q, const uint8_t* __restrict__ mask, size_
     if ((nvox & 15) == 0) {
         const size_t ng = nvox >> 4;
         for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < ng; g += (size_t)gridDim.x * 256) {
-            const uint4 m = __ldg(reinterpret_cast<const uint4*>(mv) + g);
+            const unsigned m = __ldg(mh + g);
             float4* o = reinterpret_cast<float4*>(ov) + 4 * g;
-            if ((m.x | m.y | m.z | m.w) == 0u) {
+            if (m == 0u) {
                 const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
                 o[0] = z; o[1] = z; o[2] = z; o[3] = z;
                 continue;
             }
             const uint4 a = __ldg(reinterpret_cast<const uint4*>(qv) + 2 * g);
             const uint4 b = __ldg(reinterpret_cast<const uint4*>(qv) + 2 * g + 1);
-            const unsigned mw[4] = {m.x, m.y, m.z, m.w};
             const unsigned qw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
             float r[16];
 #pragma unroll
             for (int i = 0; i < 16; i++)
-                r[i] = ((mw[i >> 2] >> (8 * (i & 3))) & 0xffu) ? look((qw[i >> 1] >> (16 * (i & 1))) & 0xffffu) : 0.f;
+                r[i] = ((m >> i) & 1u) ? look((qw[i >> 1] >> (16 * (i & 1))) & 0xffffu) : 0.f;
 #pragma unroll
             for (int j = 0; j < 4; j++) o[j] = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         }
     } else {
         for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvox; i += (size_t)gridDim.x * 256)
-            ov[i] = mv[i] ? look((unsigned)(unsigned short)qv[i]) : 0.f;
+            ov[i] = flat_bit(mask, vol * nvox + i) ? look((unsigned)(unsigned short)qv[i]) : 0.f;
     }
 }
 
@@ -684,7 +684,7 @@ using namespace vx;
 
 // percentiles of a quantised image (the tag of vx_internal.h) by counting
 template <typename T>
-static int percentiles_quantised(OpGuard& og, Image* A, Image* M, double correction, Image* O) {
+static int percentiles_quantised(OpGuard& og, Image* A, const unsigned* Mbits, double correction, Image* O) {
     const size_t nvox = A->nvox();
     const int nb = A->nb;
     Scratch sc(og.c, og.s);
@@ -703,14 +703,13 @@ static int percentiles_quantised(OpGuard& og, Image* A, Image* M, double correct
     // grid: a few blocks per SM in total, every block owns one volume's histogram window
     const int per_vol = std::max(1, std::min((int)((nvox / 16 + 255) / 256), (kNumSMs * 6 + nb - 1) / nb));
     { VX_LAUNCH(og.c, og.s, "pq_hist_kernel");
-      pq_hist_kernel<T><<<dim3(per_vol, nb), 256, kPqWin * 4, og.st>>>(q, (const uint8_t*)M->d, nvox, qrange, hist); }
+      pq_hist_kernel<T><<<dim3(per_vol, nb), 256, kPqWin * 4, og.st>>>(q, Mbits, nvox, qrange, hist); }
     VX_TRY(check_launch("pq_hist_kernel"));
     { VX_LAUNCH(og.c, og.s, "pq_table_kernel");
       pq_table_kernel<<<nb, 1024, 0, og.st>>>(hist, qrange, table, correction, A->q_increasing ? 1 : 0); }
     VX_TRY(check_launch("pq_table_kernel"));
     { VX_LAUNCH(og.c, og.s, "pq_apply_kernel");
-      pq_apply_kernel<T><<<dim3(per_vol, nb), 256, kPqWin * 4, og.st>>>(q, (const uint8_t*)M->d, nvox, qrange, table,
-                                                                       (float*)O->d); }
+      pq_apply_kernel<T><<<dim3(per_vol, nb), 256, kPqWin * 4, og.st>>>(q, Mbits, nvox, qrange, table, (float*)O->d); }
     VX_TRY(check_launch("pq_apply_kernel"));
     return VX_OK;
 }
@@ -721,18 +720,21 @@ extern "C" int32_t vx_percentiles(vx_ctx ctx, vx_img a, vx_img mask, double corr
     VX_TRY(og.begin(ctx));
     Image *A = nullptr, *M = nullptr;
     VX_TRY(og.input(a, &A, VX_F32));
+    if (A->q16 != nullptr && og.c->quantised_paths.load()) {   // at most 65536 distinct values: count, do not sort
+        const unsigned* Mbits = nullptr;
+        VX_TRY(og.input_bits(mask, &M, &Mbits));
+        VX_TRY(same_shape(A, M));
+        Image* O = nullptr;
+        VX_TRY(new_image(og.c, VX_F32, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
+        const int rc = A->q_dtype == VX_I16 ? percentiles_quantised<short>(og, A, Mbits, correction, O)
+                                            : percentiles_quantised<unsigned short>(og, A, Mbits, correction, O);
+        if (rc != VX_OK) { drop(O); return rc; }
+        return og.finish(O, out);
+    }
     VX_TRY(og.input(mask, &M, VX_U8));
     VX_TRY(same_shape(A, M));
     const size_t nvox = A->nvox(), total = A->count();
     const int nb = A->nb;
-    if (A->q16 != nullptr && og.c->quantised_paths.load()) {   // at most 65536 distinct values: count, do not sort
-        Image* O = nullptr;
-        VX_TRY(new_image(og.c, VX_F32, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
-        const int rc = A->q_dtype == VX_I16 ? percentiles_quantised<short>(og, A, M, correction, O)
-                                            : percentiles_quantised<unsigned short>(og, A, M, correction, O);
-        if (rc != VX_OK) { drop(O); return rc; }
-        return og.finish(O, out);
-    }
     const int ntiles_max = (int)((nvox + kTile - 1) / kTile);
     unsigned long long* buf = nullptr;
     unsigned *count = nullptr, *table = nullptr, *totals = nullptr, *plan = nullptr;

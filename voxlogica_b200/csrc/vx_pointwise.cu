@@ -29,7 +29,8 @@ struct DevProg {
     int n_breg, n_freg;
     int nb;
     unsigned long long nvox;     // voxels per volume
-    unsigned long long ngroups;  // 16-voxel groups over the whole batch
+    unsigned long long count;    // voxels of the whole batch
+    unsigned long long ngroups;  // 16-voxel groups over the whole batch (128-voxel groups in the bit kernel)
     const void* leaf[VXP_MAX_LEAVES];
     void* out;
     const float* bscal;  // [n_scalars][nb]
@@ -40,9 +41,21 @@ struct F16 {
     float4 v[4];
 };
 
+// Boolean leaves and boolean results are BIT streams (Image::bits): the 16 voxels of group g are
+// halfword g.  Inside the program a boolean register is 16 bytes of 0/1 (a uint4), which is what
+// the comparisons produce and the select consumes.
+__device__ __forceinline__ unsigned bytes_of_nib(unsigned nib) { return (nib * 0x00204081u) & 0x01010101u; }
+__device__ __forceinline__ unsigned nib_of_bytes(unsigned w) {
+    w = __vcmpne4(w, 0u) & 0x01010101u;
+    return ((w * 0x01020408u) >> 24) & 0xfu;
+}
 __device__ __forceinline__ uint4 ld_b(const DevProg& P, uint8_t kind, uint8_t idx, size_t g,
                                       const uint4* sb) {
-    if (kind == K_LEAF) return __ldg(reinterpret_cast<const uint4*>(P.leaf[idx]) + g);
+    if (kind == K_LEAF) {
+        const unsigned h = __ldg(reinterpret_cast<const unsigned short*>(P.leaf[idx]) + g);
+        return make_uint4(bytes_of_nib(h & 0xfu), bytes_of_nib((h >> 4) & 0xfu), bytes_of_nib((h >> 8) & 0xfu),
+                          bytes_of_nib(h >> 12));
+    }
     return sb[idx * kPwThreads + threadIdx.x];
 }
 __device__ __forceinline__ F16 ld_f(const DevProg& P, uint8_t kind, uint8_t idx, size_t g,
@@ -59,8 +72,14 @@ __device__ __forceinline__ F16 ld_f(const DevProg& P, uint8_t kind, uint8_t idx,
     return r;
 }
 __device__ __forceinline__ void st_b(const DevProg& P, int8_t dst, size_t g, uint4* sb, uint4 v) {
-    if (dst < 0) reinterpret_cast<uint4*>(P.out)[g] = v;
-    else sb[dst * kPwThreads + threadIdx.x] = v;
+    if (dst < 0) {
+        unsigned h = nib_of_bytes(v.x) | (nib_of_bytes(v.y) << 4) | (nib_of_bytes(v.z) << 8) | (nib_of_bytes(v.w) << 12);
+        // bits past the last voxel of the batch stay 0 (the invariant of the bit form)
+        if ((g + 1) * kGroup > P.count) h &= (1u << (unsigned)(P.count - g * kGroup)) - 1u;
+        reinterpret_cast<unsigned short*>(P.out)[g] = (unsigned short)h;
+    } else {
+        sb[dst * kPwThreads + threadIdx.x] = v;
+    }
 }
 __device__ __forceinline__ void st_f(const DevProg& P, int8_t dst, size_t g, float4* sf,
                                      const F16& v) {
@@ -251,11 +270,12 @@ pointwise_program_kernel(const __grid_constant__ DevProg P) {
     }
 }
 
-// Programs over boolean images only (not / and / or / xor chains).  A 16-byte group per thread
-// keeps too few bytes in flight for HBM (ncu: `not` at 50 % of the copy peak with 2048 resident
-// threads x 16 B per SM), so here every thread runs the program on kWideU independent groups
-// per iteration: all leaf loads of an instruction are issued before the first is used.
+// Programs over boolean images only (not / and / or / xor chains) run on the bit form directly: a
+// "group" is a uint4 = 128 voxels, the operators are the machine's own bitwise instructions, and
+// the traffic is 1/8 of the byte form's.  Every thread runs the program on kWideU independent
+// groups per iteration: all leaf loads of an instruction are issued before the first is used.
 constexpr int kWideU = 4;
+constexpr int kBitGroup = 128;   // voxels per uint4 of bits
 
 __device__ __forceinline__ void ld_bw(const DevProg& P, uint8_t kind, uint8_t idx, const size_t (&g)[kWideU],
                                       const uint4* sb, uint4 (&x)[kWideU]) {
@@ -267,12 +287,23 @@ __device__ __forceinline__ void ld_bw(const DevProg& P, uint8_t kind, uint8_t id
             x[u] = sb[(idx * kWideU + u) * kPwThreads + threadIdx.x];
     }
 }
+__device__ __forceinline__ unsigned tail_word(unsigned w, long long valid) {   // keep the low `valid` bits
+    return valid >= 32 ? w : valid <= 0 ? 0u : (w & ((1u << (unsigned)valid) - 1u));
+}
 __device__ __forceinline__ void st_bw(const DevProg& P, int8_t dst, const size_t (&g)[kWideU], uint4* sb,
                                       const uint4 (&x)[kWideU]) {
 #pragma unroll
     for (int u = 0; u < kWideU; u++) {
         if (dst < 0) {
-            if (g[u] < P.ngroups) reinterpret_cast<uint4*>(P.out)[g[u]] = x[u];
+            if (g[u] < P.ngroups) {
+                uint4 v = x[u];
+                if ((g[u] + 1) * kBitGroup > P.count) {   // the last group: bits past the batch stay 0
+                    const long long left = (long long)(P.count - g[u] * kBitGroup);
+                    v.x = tail_word(v.x, left); v.y = tail_word(v.y, left - 32);
+                    v.z = tail_word(v.z, left - 64); v.w = tail_word(v.w, left - 96);
+                }
+                reinterpret_cast<uint4*>(P.out)[g[u]] = v;
+            }
         } else {
             sb[(dst * kWideU + u) * kPwThreads + threadIdx.x] = x[u];
         }
@@ -292,7 +323,7 @@ boolean_program_kernel(const __grid_constant__ DevProg P) {
             const DevOp op = P.ops[i];
             uint4 x[kWideU], y[kWideU];
             if (op.opcode == VXP_CONSTB) {
-                const unsigned w = op.aux ? 0x01010101u : 0u;
+                const unsigned w = op.aux ? 0xffffffffu : 0u;
 #pragma unroll
                 for (int u = 0; u < kWideU; u++) x[u] = make_uint4(w, w, w, w);
             } else {
@@ -302,9 +333,7 @@ boolean_program_kernel(const __grid_constant__ DevProg P) {
 #pragma unroll
             for (int u = 0; u < kWideU; u++) {
                 switch (op.opcode) {
-                    case VXP_NOT:
-                        x[u].x ^= 0x01010101u; x[u].y ^= 0x01010101u; x[u].z ^= 0x01010101u; x[u].w ^= 0x01010101u;
-                        break;
+                    case VXP_NOT: x[u].x = ~x[u].x; x[u].y = ~x[u].y; x[u].z = ~x[u].z; x[u].w = ~x[u].w; break;
                     case VXP_AND: x[u].x &= y[u].x; x[u].y &= y[u].y; x[u].z &= y[u].z; x[u].w &= y[u].w; break;
                     case VXP_OR: x[u].x |= y[u].x; x[u].y |= y[u].y; x[u].z |= y[u].z; x[u].w |= y[u].w; break;
                     case VXP_XOR: x[u].x ^= y[u].x; x[u].y ^= y[u].y; x[u].z ^= y[u].z; x[u].w ^= y[u].w; break;
@@ -363,16 +392,27 @@ int run_pointwise(vx_ctx ctx, const vx_op* prog, int n_ops, const vx_img* leaves
     OpGuard g;
     VX_TRY(g.begin(ctx));
     Image* L[VXP_MAX_LEAVES] = {};
+    const void* leaf_ptr[VXP_MAX_LEAVES] = {};
     for (int i = 0; i < n_leaves; i++) {
-        VX_TRY(g.input(leaves[i], &L[i], 0));
-        VX_REQUIRE(L[i]->dtype == VX_U8 || L[i]->dtype == VX_F32, VX_E_DTYPE,
-                   "leaf %d has dtype %d; pointwise programs take u8 or f32", i, L[i]->dtype);
+        int dt = 0;
+        VX_REQUIRE(vx_info(leaves[i], &dt, nullptr, nullptr, nullptr, nullptr, nullptr) == VX_OK, VX_E_INVALID_ARG,
+                   "invalid image handle %llu", (unsigned long long)leaves[i]);
+        VX_REQUIRE(dt == VX_U8 || dt == VX_F32, VX_E_DTYPE,
+                   "leaf %d has dtype %d; pointwise programs take u8 or f32", i, dt);
+        if (dt == VX_U8) {   // boolean leaves are read as bits
+            const unsigned* b = nullptr;
+            VX_TRY(g.input_bits(leaves[i], &L[i], &b));
+            leaf_ptr[i] = b;
+        } else {
+            VX_TRY(g.input(leaves[i], &L[i], VX_F32));
+            leaf_ptr[i] = L[i]->d;
+        }
         if (i > 0) VX_TRY(same_shape(L[0], L[i]));
     }
     Image* shape = nullptr;
     if (n_leaves > 0) shape = L[0];
     else {
-        VX_TRY(g.input(like, &shape, 0));
+        VX_TRY(g.input_meta(like, &shape));   // only its shape is used
     }
 
     DevProg P;
@@ -492,15 +532,16 @@ int run_pointwise(vx_ctx ctx, const vx_op* prog, int n_ops, const vx_img* leaves
                n_b, n_f, smem);
 
     Image* o = nullptr;
-    VX_TRY(new_image(g.c, out_type == T_B ? VX_U8 : VX_F32, shape->nx, shape->ny, shape->nz,
-                     shape->nb, shape->sp, &o));
+    if (out_type == T_B) VX_TRY(new_bits_image(g.c, shape->nx, shape->ny, shape->nz, shape->nb, shape->sp, &o));
+    else VX_TRY(new_image(g.c, VX_F32, shape->nx, shape->ny, shape->nz, shape->nb, shape->sp, &o));
     P.n_ops = nd;
     P.n_breg = n_b; P.n_freg = n_f;
     P.nb = shape->nb;
     P.nvox = shape->nvox();
+    P.count = shape->count();
     P.ngroups = (shape->count() + kGroup - 1) / kGroup;
-    for (int i = 0; i < n_leaves; i++) P.leaf[i] = L[i]->d;
-    P.out = o->d;
+    for (int i = 0; i < n_leaves; i++) P.leaf[i] = leaf_ptr[i];
+    P.out = out_type == T_B ? (void*)o->bits : o->d;
     float* d_scal = nullptr;
     if (n_scalars > 0 && batch_scalars) {
         size_t bytes = sizeof(float) * (size_t)n_scalars * shape->nb;
@@ -523,7 +564,10 @@ int run_pointwise(vx_ctx ctx, const vx_op* prog, int n_ops, const vx_img* leaves
         boolean_only = oc == VXP_NOT || oc == VXP_AND || oc == VXP_OR || oc == VXP_XOR || oc == OPC_COPYB ||
                        oc == VXP_CONSTB;
     }
-    if (boolean_only) smem *= kWideU;
+    if (boolean_only) {
+        smem *= kWideU;
+        P.ngroups = (shape->count() + kBitGroup - 1) / kBitGroup;
+    }
     int ctas = smem == 0 ? 8 : (int)((220 * 1024) / smem);
     if (ctas < 1) ctas = 1;
     if (ctas > 8) ctas = 8;

@@ -62,6 +62,22 @@ reduce_volume_kernel(const uint8_t* __restrict__ a, size_t nvox, double* __restr
     if (threadIdx.x == 0) partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = v;
 }
 
+// the same count on the bit form: bits [vol * nvox, (vol + 1) * nvox) of the stream
+__global__ void __launch_bounds__(kRedThreads)
+reduce_volume_bits_kernel(const unsigned* __restrict__ bits, size_t nvox, double* __restrict__ partial) {
+    const size_t lo = (size_t)blockIdx.y * nvox, hi = lo + nvox;
+    const size_t w0 = lo >> 5, w1 = (hi - 1) >> 5;
+    unsigned long long cnt = 0;
+    for (size_t w = w0 + (size_t)blockIdx.x * kRedThreads + threadIdx.x; w <= w1; w += (size_t)gridDim.x * kRedThreads) {
+        unsigned x = __ldg(bits + w);
+        if (w == w0) x &= 0xffffffffu << (lo & 31);
+        if (w == w1 && (hi & 31)) x &= (1u << (hi & 31)) - 1u;
+        cnt += __popc(x);
+    }
+    double v = block_reduce<RED_SUM>((double)cnt);
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = v;
+}
+
 // Accumulators of the f32 reductions.  min / max are exact in binary32 (fminf / fmaxf skip
 // NaNs like their binary64 versions on the converted values would); the sum accumulates in
 // binary64 in a fixed order.  RED_MINMAX produces both extrema from ONE read of the image.
@@ -148,7 +164,7 @@ reduce_final_kernel(const double* __restrict__ partial, int per_volume, double* 
 
 // Runs the reduction and leaves nb doubles (RED_MINMAX: nb minima, then nb maxima) in device
 // memory `d_out` (scratch owned by the caller)
-int reduce_device(OpGuard& g, int kind, const Image* a, const Image* mask, double* d_out) {
+int reduce_device(OpGuard& g, int kind, const Image* a, const Image* mask, double* d_out, const unsigned* a_bits) {
     const size_t nvox = a->nvox();
     int per_volume = (int)((nvox + (size_t)kRedThreads * 16 * 4 - 1) / ((size_t)kRedThreads * 16 * 4));
     int cap = (kNumSMs * 8 + a->nb - 1) / a->nb;
@@ -161,7 +177,8 @@ int reduce_device(OpGuard& g, int kind, const Image* a, const Image* mask, doubl
     int k0 = RED_SUM, k1 = RED_SUM;
     if (kind == RED_VOLUME) {
         { VX_LAUNCH(g.c, g.s, "reduce_volume_kernel");
-          reduce_volume_kernel<<<grid, kRedThreads, 0, g.st>>>((const uint8_t*)a->d, nvox, d_part); }
+          if (a_bits) reduce_volume_bits_kernel<<<grid, kRedThreads, 0, g.st>>>(a_bits, nvox, d_part);
+          else reduce_volume_kernel<<<grid, kRedThreads, 0, g.st>>>((const uint8_t*)a->d, nvox, d_part); }
         VX_TRY(check_launch("reduce_volume_kernel"));
     } else {
         const float* p = (const float*)a->d;
@@ -190,14 +207,16 @@ static int reduce_to_host(vx_ctx ctx, int kind, vx_img a, vx_img mask, double* o
     OpGuard g;
     VX_TRY(g.begin(ctx));
     Image *A = nullptr, *M = nullptr;
-    VX_TRY(g.input(a, &A, kind == RED_VOLUME ? VX_U8 : VX_F32));
+    const unsigned* Ab = nullptr;
+    if (kind == RED_VOLUME) VX_TRY(g.input_bits(a, &A, &Ab));   // a popcount over the bit form
+    else VX_TRY(g.input(a, &A, VX_F32));
     if (mask) {
         VX_TRY(g.input(mask, &M, VX_U8));
         VX_TRY(same_shape(A, M));
     }
     double* d_out = nullptr;
     VX_TRY(scratch_alloc(g.c, g.s, sizeof(double) * A->nb, (void**)&d_out));
-    VX_TRY(reduce_device(g, kind, A, M, d_out));
+    VX_TRY(reduce_device(g, kind, A, M, d_out, Ab));
     VX_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * A->nb, cudaMemcpyDeviceToHost, g.st));
     VX_TRY(scratch_free(g.c, g.s, d_out));
     VX_CUDA(cudaStreamSynchronize(g.st));
@@ -218,7 +237,7 @@ static int minmax_to_host(vx_ctx ctx, vx_img a, vx_img mask, double* out_min, do
     }
     double* d_out = nullptr;
     VX_TRY(scratch_alloc(g.c, g.s, sizeof(double) * A->nb * 2, (void**)&d_out));
-    VX_TRY(reduce_device(g, RED_MINMAX, A, M, d_out));
+    VX_TRY(reduce_device(g, RED_MINMAX, A, M, d_out, nullptr));
     VX_CUDA(cudaMemcpyAsync(out_min, d_out, sizeof(double) * A->nb, cudaMemcpyDeviceToHost, g.st));
     VX_CUDA(cudaMemcpyAsync(out_max, d_out + A->nb, sizeof(double) * A->nb, cudaMemcpyDeviceToHost, g.st));
     VX_TRY(scratch_free(g.c, g.s, d_out));

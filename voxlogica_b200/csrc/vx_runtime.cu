@@ -285,7 +285,7 @@ static size_t dtype_size(int dtype) {
     return 0;
 }
 
-int new_image(Ctx* c, int dtype, int nx, int ny, int nz, int nb, const float* sp, Image** out) {
+static int new_image_impl(Ctx* c, int dtype, int nx, int ny, int nz, int nb, const float* sp, bool as_bits, Image** out) {
     size_t es = dtype_size(dtype);
     VX_REQUIRE(es != 0, VX_E_DTYPE, "unknown dtype %d", dtype);
     VX_REQUIRE(nx > 0 && ny > 0 && nz > 0 && nb > 0, VX_E_INVALID_ARG,
@@ -304,21 +304,31 @@ int new_image(Ctx* c, int dtype, int nx, int ny, int nz, int nb, const float* sp
     // kernels read and write whole 16-element groups: pad the allocation so that the
     // last group of the batch stays inside it (the padding is never data)
     size_t alloc = ((im->count() + 15) / 16 * 16) * es + 64;
-    int arc = dev_alloc(c, s, alloc, &im->d);
+    int arc = as_bits ? dev_alloc(c, s, bits_alloc_bytes(im->count()), (void**)&im->bits) : dev_alloc(c, s, alloc, &im->d);
     if (arc != VX_OK) {
         delete im;
         return arc;
     }
     im->ready = get_event(c);
-    c->live_bytes += im->bytes;
+    c->live_bytes += as_bits ? im->bit_words() * 4 : im->bytes;
     c->live_handles += 1;
     register_image(im);
     *out = im;
     return VX_OK;
 }
+int new_image(Ctx* c, int dtype, int nx, int ny, int nz, int nb, const float* sp, Image** out) {
+    return new_image_impl(c, dtype, nx, ny, nz, nb, sp, false, out);
+}
+int new_bits_image(Ctx* c, int nx, int ny, int nz, int nb, const float* sp, Image** out) {
+    return new_image_impl(c, VX_U8, nx, ny, nz, nb, sp, true, out);
+}
 
 int use_input(Ctx* c, Image* img, int s) {
     if (img->home != s) VX_CUDA(cudaStreamWaitEvent(c->streams[s], img->ready, 0));
+    if (img->dtype == VX_U8) {   // a representation added later by another stream
+        std::lock_guard<std::mutex> lk(img->mu);
+        if (img->alt_ready && img->alt_stream != s) VX_CUDA(cudaStreamWaitEvent(c->streams[s], img->alt_ready, 0));
+    }
     return VX_OK;
 }
 
@@ -355,10 +365,13 @@ void drop(Image* im) {
         cudaStreamWaitEvent(st, p.second, 0);
         put_event(c, p.second);
     }
-    dev_free(c, im->home, im->d);
+    uint64_t held = 0;
+    if (im->d) { dev_free(c, im->home, im->d); held += im->bytes; }
+    if (im->bits) { dev_free(c, im->home, im->bits); held += im->bit_words() * 4; }
     if (im->q16) dev_free(c, im->home, im->q16);
+    if (im->alt_ready) put_event(c, im->alt_ready);
     put_event(c, im->ready);
-    c->live_bytes -= im->bytes;
+    c->live_bytes -= held;
     c->live_handles -= 1;
     if (prev != c->device && prev >= 0) cudaSetDevice(prev);
     delete im;
@@ -468,7 +481,9 @@ int OpGuard::begin(vx_ctx ctx) {
     return VX_OK;
 }
 OpGuard::~OpGuard() {
+    for (void* p : temps) dev_free(c, s, p);
     for (Image* im : ins) drop(im);   // the pins taken by input()
+    for (Image* im : metas) drop(im);
 }
 int OpGuard::input(vx_img h, Image** out, int want_dtype) {
     Image* im = pin_img(h);
@@ -479,6 +494,85 @@ int OpGuard::input(vx_img h, Image** out, int want_dtype) {
     VX_REQUIRE(want_dtype == 0 || im->dtype == want_dtype, VX_E_DTYPE,
                "operand has dtype %d, expected %d", im->dtype, want_dtype);
     VX_TRY(use_input(c, im, s));
+    if (im->dtype == VX_U8) VX_TRY(ensure_u8(c, im, s));
+    *out = im;
+    return VX_OK;
+}
+__global__ void __launch_bounds__(256) pack_stream_kernel(const uint8_t* __restrict__ a, unsigned* __restrict__ bits, size_t n);
+__global__ void __launch_bounds__(256) unpack_stream_kernel(const unsigned* __restrict__ bits, uint8_t* __restrict__ a, size_t n);
+
+// The second representation of a boolean image, made on the calling stream after the image's
+// producer (use_input has already ordered this stream behind it).  Other streams wait for
+// alt_ready; the image's free waits for this stream through done_input like for any reader.
+static int alt_done(Ctx* c, Image* im, int s) {
+    if (!im->alt_ready) im->alt_ready = get_event(c);
+    im->alt_stream = s;
+    VX_CUDA(cudaEventRecord(im->alt_ready, c->streams[s]));
+    return VX_OK;
+}
+int ensure_u8(Ctx* c, Image* im, int s) {
+    if (im->dtype != VX_U8) return VX_OK;
+    std::lock_guard<std::mutex> lk(im->mu);
+    if (im->d) return VX_OK;
+    const size_t n = im->count();
+    void* p = nullptr;
+    VX_TRY(dev_alloc(c, s, ((n + 15) / 16 * 16) + 64, &p));
+    {
+        VX_LAUNCH(c, s, "unpack_stream_kernel");
+        unpack_stream_kernel<<<grid_for((n + 31) / 32, 256, 8), 256, 0, c->streams[s]>>>(im->bits, (uint8_t*)p, n);
+    }
+    int rc = check_launch("unpack_stream_kernel");
+    if (rc != VX_OK) { dev_free(c, s, p); return rc; }
+    im->d = p;
+    c->live_bytes += im->bytes;
+    return alt_done(c, im, s);
+}
+static int pack_bits_of(Ctx* c, int s, const Image* im, unsigned* dst) {
+    const size_t n = im->count();
+    {
+        VX_LAUNCH(c, s, "pack_stream_kernel");
+        pack_stream_kernel<<<grid_for((n + 31) / 32, 256, 8), 256, 0, c->streams[s]>>>((const uint8_t*)im->d, dst, n);
+    }
+    return check_launch("pack_stream_kernel");
+}
+int ensure_bits(Ctx* c, Image* im, int s) {
+    if (im->dtype != VX_U8) return fail(VX_E_DTYPE, "only boolean images have a bit form");
+    std::lock_guard<std::mutex> lk(im->mu);
+    if (im->bits) return VX_OK;
+    void* p = nullptr;
+    VX_TRY(dev_alloc(c, s, bits_alloc_bytes(im->count()), &p));
+    int rc = pack_bits_of(c, s, im, (unsigned*)p);
+    if (rc != VX_OK) { dev_free(c, s, p); return rc; }
+    im->bits = (unsigned*)p;
+    c->live_bytes += im->bit_words() * 4;
+    return alt_done(c, im, s);
+}
+int OpGuard::input_meta(vx_img h, Image** out) {
+    Image* im = pin_img(h);
+    VX_REQUIRE(im != nullptr, VX_E_INVALID_ARG, "invalid image handle %llu", (unsigned long long)h);
+    metas.push_back(im);
+    VX_REQUIRE(im->ctx == c, VX_E_INVALID_ARG, "image belongs to another context");
+    *out = im;
+    return VX_OK;
+}
+int OpGuard::input_bits(vx_img h, Image** out, const unsigned** bits) {
+    Image* im = pin_img(h);
+    VX_REQUIRE(im != nullptr, VX_E_INVALID_ARG, "invalid image handle %llu", (unsigned long long)h);
+    ins.push_back(im);
+    VX_REQUIRE(im->ctx == c, VX_E_INVALID_ARG, "image belongs to another context");
+    VX_REQUIRE(im->dtype == VX_U8, VX_E_DTYPE, "operand has dtype %d, expected %d", im->dtype, VX_U8);
+    VX_TRY(use_input(c, im, s));
+    if (im->bits_frozen) {
+        // the byte form may be rewritten through a raw pointer the caller holds: pack a private copy now
+        void* p = nullptr;
+        VX_TRY(dev_alloc(c, s, bits_alloc_bytes(im->count()), &p));
+        temps.push_back(p);
+        VX_TRY(pack_bits_of(c, s, im, (unsigned*)p));
+        *bits = (const unsigned*)p;
+    } else {
+        VX_TRY(ensure_bits(c, im, s));
+        *bits = im->bits;
+    }
     *out = im;
     return VX_OK;
 }
@@ -563,6 +657,22 @@ static int quant_monotone(int host_dtype, float slope, float inter) {   // +1 in
     if (finite) ans = inc ? 1 : dec ? -1 : 0;
     c_dtype = host_dtype; c_slope = slope; c_inter = inter; c_ans = ans;
     return ans;
+}
+
+// bit stream -> boolean bytes, 32 voxels per thread (one word in, two 16-byte stores; the byte
+// buffer is padded, so the last group is written whole)
+__global__ void __launch_bounds__(256)
+unpack_stream_kernel(const unsigned* __restrict__ bits, uint8_t* __restrict__ a, size_t n) {
+    const size_t nw = (n + 31) >> 5;
+    for (size_t w = (size_t)blockIdx.x * 256 + threadIdx.x; w < nw; w += (size_t)gridDim.x * 256) {
+        const unsigned v = __ldg(bits + w);
+        unsigned o[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) o[i] = (((v >> (4 * i)) & 0xfu) * 0x00204081u) & 0x01010101u;
+        uint4* dst = reinterpret_cast<uint4*>(a) + 2 * w;
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
 }
 
 // boolean image -> bit stream, 32 voxels per thread (two 16-byte loads, one word out)
@@ -724,18 +834,11 @@ int32_t vx_download_bits(vx_ctx ctx, vx_img img, void* host, size_t bytes) {
     OpGuard g;
     VX_TRY(g.begin(ctx));
     Image* im = nullptr;
-    VX_TRY(g.input(img, &im, VX_U8));
+    const unsigned* bits = nullptr;
+    VX_TRY(g.input_bits(img, &im, &bits));   // the image's own bit form: results of the bit-space operators have it already
     const size_t n = im->count();
     VX_REQUIRE(bytes == (n + 7) / 8, VX_E_INVALID_ARG, "download size %zu != ceil(%zu voxels / 8) = %zu", bytes, n,
                (n + 7) / 8);
-    Scratch sc(g.c, g.s);
-    unsigned* bits = nullptr;
-    VX_TRY(sc.alloc(((n + 31) / 32) * 4, &bits));
-    {
-        VX_LAUNCH(g.c, g.s, "pack_stream_kernel");
-        pack_stream_kernel<<<grid_for((n + 31) / 32, 256, 8), 256, 0, g.st>>>((const uint8_t*)im->d, bits, n);
-    }
-    VX_TRY(check_launch("pack_stream_kernel"));
     VX_CUDA(cudaMemcpyAsync(host, bits, bytes, cudaMemcpyDefault, g.st));
     VX_CUDA(cudaStreamSynchronize(g.st));
     return g.finish_scalar();
@@ -865,11 +968,15 @@ int32_t vx_transfer(vx_ctx dst_ctx, vx_img img, vx_img* out) {
     VX_TRY(g.begin(dst_ctx));
     Ctx* src = im->ctx;
     Image* o = nullptr;
-    VX_TRY(new_image(g.c, im->dtype, im->nx, im->ny, im->nz, im->nb, im->sp, &o));
+    const bool as_bits = im->d == nullptr;   // a boolean image that only exists as bits travels as bits
+    if (as_bits) VX_TRY(new_bits_image(g.c, im->nx, im->ny, im->nz, im->nb, im->sp, &o));
+    else VX_TRY(new_image(g.c, im->dtype, im->nx, im->ny, im->nz, im->nb, im->sp, &o));
     // order the copy after the producer of `img` (an event of another device may be waited on)
     cudaError_t e = cudaStreamWaitEvent(g.st, im->ready, 0);
+    if (e == cudaSuccess && im->alt_ready) e = cudaStreamWaitEvent(g.st, im->alt_ready, 0);
     if (e == cudaSuccess)
-        e = cudaMemcpyPeerAsync(o->d, g.c->device, im->d, src->device, im->bytes, g.st);
+        e = as_bits ? cudaMemcpyPeerAsync(o->bits, g.c->device, im->bits, src->device, im->bit_words() * 4, g.st)
+                    : cudaMemcpyPeerAsync(o->d, g.c->device, im->d, src->device, im->bytes, g.st);
     if (e != cudaSuccess) {
         drop(o);
         return fail(VX_E_CUDA, "transfer failed: %s", cudaGetErrorString(e));
@@ -890,6 +997,17 @@ int32_t vx_device_ptr(vx_ctx ctx, vx_img img, void** ptr) {
     VX_TRY(g.begin(ctx));
     Image* im = nullptr;
     VX_TRY(g.input(img, &im, 0));   // makes the producer's work visible to this thread's stream
+    if (im->dtype == VX_U8) {
+        // the caller may write through the pointer (the slab path receives planes into images): the
+        // bytes are the truth from now on, a cached bit form would go stale
+        std::lock_guard<std::mutex> lk(im->mu);
+        im->bits_frozen = true;
+        if (im->bits) {
+            dev_free(g.c, g.s, im->bits);   // stream-ordered behind every reader enqueued so far on this stream
+            g.c->live_bytes -= im->bit_words() * 4;
+            im->bits = nullptr;
+        }
+    }
     *ptr = im->d;
     return g.finish_scalar();
 }

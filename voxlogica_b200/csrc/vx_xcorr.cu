@@ -23,6 +23,7 @@
 #include <utility>
 #include <vector>
 
+#include "vx_bits.h"
 #include "vx_internal.h"
 #include "vx_tma.h"
 
@@ -102,7 +103,7 @@ xc_bin_kernel(const float* __restrict__ a, uint8_t* __restrict__ codes, size_t n
 // CODED: `b` is the code image of the sliding pass (b is the image that was binned for it).
 template <bool CODED>
 __global__ void __launch_bounds__(256)
-xc_region_hist_kernel(const void* __restrict__ b_, const uint8_t* __restrict__ region, size_t nvox, int nx, int pitch,
+xc_region_hist_kernel(const void* __restrict__ b_, const unsigned* __restrict__ region, size_t nvox, int nx, int pitch,
                       const float* __restrict__ edges, int k, unsigned* __restrict__ h2) {
     __shared__ unsigned sh[256];
     __shared__ float e[kEdgeStride];
@@ -111,7 +112,8 @@ xc_region_hist_kernel(const void* __restrict__ b_, const uint8_t* __restrict__ r
     for (int i = threadIdx.x; i <= k; i += 256) e[i] = edges[vol * kEdgeStride + i];
     __syncthreads();
     const float inv_w = (e[k] > e[0]) ? (float)k / (e[k] - e[0]) : 0.0f;
-    const uint8_t* reg = region + vol * nvox;
+    // the region is read in its bit form: the 16 voxels of group g are half word g of the volume
+    const unsigned short* reg = reinterpret_cast<const unsigned short*>(region) + (vol * nvox) / 16;
     auto code_at = [&](size_t i) -> unsigned {
         if (CODED) {
             const uint8_t* cb = reinterpret_cast<const uint8_t*>(b_);
@@ -121,26 +123,40 @@ xc_region_hist_kernel(const void* __restrict__ b_, const uint8_t* __restrict__ r
         }
         return code_from_edges(reinterpret_cast<const float*>(b_)[vol * nvox + i], e, k, inv_w);
     };
-    if ((nvox & 15) == 0) {
-        const size_t ng = nvox >> 4;
-        for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < ng; g += (size_t)gridDim.x * 256) {
-            const uint4 r = __ldg(reinterpret_cast<const uint4*>(reg) + g);
-            if ((r.x | r.y | r.z | r.w) == 0) continue;    // regions are small: most groups are empty
-            const unsigned rw[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                if (rw[q] == 0) continue;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (((rw[q] >> (8 * j)) & 0xffu) == 0) continue;
-                    const unsigned code = code_at((g << 4) + 4 * q + j);
+    if ((nvox & 31) == 0) {
+        // one word (32 voxels) per lane; a word that holds region voxels is handed round the warp and
+        // every lane takes one of its bits, so a compact region does not leave 31 lanes waiting for one
+        const unsigned* regw = region + (vol * nvox) / 32;
+        const size_t nw = nvox >> 5;
+        const int lane = threadIdx.x & 31;
+        for (size_t w0 = ((size_t)blockIdx.x * 256 + (threadIdx.x & ~31u)); w0 < nw; w0 += (size_t)gridDim.x * 256) {
+            const size_t w = w0 + lane;
+            const unsigned r = w < nw ? __ldg(regw + w) : 0u;
+            unsigned busy = __ballot_sync(0xffffffffu, r != 0u);
+            while (busy) {
+                const int src = __ffs(busy) - 1;
+                busy &= busy - 1;
+                const unsigned rr = __shfl_sync(0xffffffffu, r, src);
+                if ((rr >> lane) & 1u) {
+                    const unsigned code = code_at(((w0 + src) << 5) + lane);
                     if (code) atomicAdd(&sh[code - 1], 1u);
                 }
             }
         }
+    } else if ((nvox & 15) == 0) {
+        const size_t ng = nvox >> 4;
+        for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < ng; g += (size_t)gridDim.x * 256) {
+            unsigned r = __ldg(reg + g);
+            while (r) {
+                const int j = __ffs(r) - 1;
+                r &= r - 1;
+                const unsigned code = code_at((g << 4) + j);
+                if (code) atomicAdd(&sh[code - 1], 1u);
+            }
+        }
     } else {
         for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvox; i += (size_t)gridDim.x * 256) {
-            if (reg[i] == 0) continue;
+            if (!flat_bit(region, vol * nvox + i)) continue;
             const unsigned code = code_at(i);
             if (code) atomicAdd(&sh[code - 1], 1u);
         }
@@ -959,8 +975,8 @@ static int xcorr_codes(OpGuard& og, Scratch& sc, Image* A, const float* d_edges,
 }
 
 // h2 of `src` (f32 values, or the u8 code image when coded) over region R into d_h2 ([nb][256] u32)
-static int region_hist(OpGuard& og, const void* src, bool coded, Image* R, const float* d_edges, int32_t k,
-                       unsigned* d_h2) {
+static int region_hist(OpGuard& og, const void* src, bool coded, Image* R, const unsigned* Rbits, const float* d_edges,
+                       int32_t k, unsigned* d_h2) {
     const int nb = R->nb;
     const size_t nvox = R->nvox();
     const int pitch = code_pitch(R->nx);
@@ -968,9 +984,9 @@ static int region_hist(OpGuard& og, const void* src, bool coded, Image* R, const
     {
         VX_LAUNCH(og.c, og.s, "xc_region_hist_kernel");
         if (coded)
-            xc_region_hist_kernel<true><<<stream_grid(nvox, nb), 256, 0, og.st>>>(src, (const uint8_t*)R->d, nvox, R->nx, pitch, d_edges, k, d_h2);
+            xc_region_hist_kernel<true><<<stream_grid(nvox, nb), 256, 0, og.st>>>(src, Rbits, nvox, R->nx, pitch, d_edges, k, d_h2);
         else
-            xc_region_hist_kernel<false><<<stream_grid(nvox, nb), 256, 0, og.st>>>(src, (const uint8_t*)R->d, nvox, R->nx, pitch, d_edges, k, d_h2);
+            xc_region_hist_kernel<false><<<stream_grid(nvox, nb), 256, 0, og.st>>>(src, Rbits, nvox, R->nx, pitch, d_edges, k, d_h2);
     }
     return check_launch("xc_region_hist_kernel");
 }
@@ -1122,7 +1138,8 @@ extern "C" int32_t vx_cross_correlation(vx_ctx ctx, vx_img a, vx_img b, vx_img r
     Image *A = nullptr, *B = nullptr, *R = nullptr;
     VX_TRY(og.input(a, &A, VX_F32));
     VX_TRY(og.input(b, &B, VX_F32));
-    VX_TRY(og.input(region, &R, VX_U8));
+    const unsigned* Rbits = nullptr;
+    VX_TRY(og.input_bits(region, &R, &Rbits));
     VX_TRY(same_shape(A, B));
     VX_TRY(same_shape(A, R));
     Scratch sc(og.c, og.s);
@@ -1133,8 +1150,8 @@ extern "C" int32_t vx_cross_correlation(vx_ctx ctx, vx_img a, vx_img b, vx_img r
     VX_TRY(sc.alloc(sizeof(unsigned) * 256 * A->nb, &d_h2));
     VX_TRY(xcorr_codes(og, sc, A, d_edges, k, &d_codes));
     // similarTo(a) correlates an image with itself: its codes are already there
-    if (A == B) VX_TRY(region_hist(og, d_codes, true, R, d_edges, k, d_h2));
-    else VX_TRY(region_hist(og, B->d, false, R, d_edges, k, d_h2));
+    if (A == B) VX_TRY(region_hist(og, d_codes, true, R, Rbits, d_edges, k, d_h2));
+    else VX_TRY(region_hist(og, B->d, false, R, Rbits, d_edges, k, d_h2));
     return xcorr_run(og, sc, A, d_codes, d_h2, rho, k, out);
 }
 
@@ -1147,7 +1164,8 @@ extern "C" int32_t vx_region_histogram(vx_ctx ctx, vx_img b, vx_img region, cons
     VX_TRY(og.begin(ctx));
     Image *B = nullptr, *R = nullptr;
     VX_TRY(og.input(b, &B, VX_F32));
-    VX_TRY(og.input(region, &R, VX_U8));
+    const unsigned* Rbits = nullptr;
+    VX_TRY(og.input_bits(region, &R, &Rbits));
     VX_TRY(same_shape(B, R));
     const int nb = B->nb;
     Scratch sc(og.c, og.s);
@@ -1155,7 +1173,7 @@ extern "C" int32_t vx_region_histogram(vx_ctx ctx, vx_img b, vx_img region, cons
     unsigned* d_h2 = nullptr;
     VX_TRY(upload_edges(og, sc, nb, m, M, k, &d_edges));
     VX_TRY(sc.alloc(sizeof(unsigned) * 256 * nb, &d_h2));
-    VX_TRY(region_hist(og, B->d, false, R, d_edges, k, d_h2));
+    VX_TRY(region_hist(og, B->d, false, R, Rbits, d_edges, k, d_h2));
     std::vector<unsigned> host((size_t)256 * nb);
     VX_CUDA(cudaMemcpyAsync(host.data(), d_h2, sizeof(unsigned) * 256 * nb, cudaMemcpyDeviceToHost, og.st));
     VX_CUDA(cudaStreamSynchronize(og.st));
