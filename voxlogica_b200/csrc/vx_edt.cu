@@ -62,21 +62,24 @@ __device__ __forceinline__ int next_set(const unsigned* __restrict__ fl, int pos
 __global__ void __launch_bounds__(kEdtThreads)
 edt_x_kernel(const unsigned* __restrict__ img, float* __restrict__ g1, unsigned* __restrict__ rowflag,
              unsigned* __restrict__ planeflag, int nx, int ny, int nz, unsigned long long rows,
-             float sx) {
+             float sx, unsigned long long* __restrict__ nfeat) {
     __shared__ unsigned sm[kEdtThreads / 32][kMaxRowWords];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned long long row = (unsigned long long)blockIdx.x * (kEdtThreads / 32) + warp;
     if (row >= rows) return;
     const int nwx = (nx + 31) >> 5;
     // the row's words straight from the image's bit form, one per lane
-    unsigned any = 0;
+    unsigned any = 0, cnt = 0;
     for (int c0 = 0; c0 < nwx; c0 += 32) {
         const int c = c0 + lane;
         const unsigned m = c < nwx ? flat_row_word(img, row, c, nx) : 0u;
         if (c < nwx) sm[warp][c] = m;
         any |= m;
+        cnt += __popc(m);
     }
     any = __reduce_or_sync(0xffffffffu, any);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0 && cnt && nfeat != nullptr) atomicAdd(nfeat, (unsigned long long)cnt);   // feature voxels of the batch
     __syncwarp();
     if (lane == 0 && any) {
         const int y = (int)(row % ny);
@@ -120,7 +123,7 @@ template <int AXIS, int MODE>
 __global__ void __launch_bounds__(kEdtThreads)
 edt_axis_kernel(const float* __restrict__ gin, void* __restrict__ gout_,
                 const unsigned* __restrict__ flags, int nx, int ny, int nz, size_t total, float s,
-                float T, int invert) {
+                float T, int invert, const uint8_t* __restrict__ only, const int* __restrict__ windowed) {
     const size_t idx = (size_t)blockIdx.x * kEdtThreads + threadIdx.x;
     if (idx >= total) return;
     const int x = (int)(idx % nx);
@@ -129,6 +132,8 @@ edt_axis_kernel(const float* __restrict__ gin, void* __restrict__ gout_,
     t0 /= ny;
     const int z = (int)(t0 % nz);
     const size_t vol = t0 / nz;
+    // `only`: the windowed pass settled every column whose flag is 0 (column numbering as in edt_env_kernel)
+    if (only != nullptr && *windowed && !only[AXIS == 1 ? (vol * nz + z) * nx + x : (vol * ny + y) * (size_t)nx + x]) return;
     int i, n;
     size_t stride;
     const float* col;
@@ -179,9 +184,11 @@ __device__ __forceinline__ uint2 env_pack(int s_, int t_, int g_) { return make_
 template <int AXIS, int MODE>
 __global__ void __launch_bounds__(128)
 edt_env_kernel(const float* __restrict__ gin, void* __restrict__ gout_, uint2* __restrict__ stack,
-               int nx, int ny, int nz, size_t ncols, int s2, float T, int invert) {
+               int nx, int ny, int nz, size_t ncols, int s2, float T, int invert, const uint8_t* __restrict__ only,
+               const int* __restrict__ windowed) {
     const size_t col = (size_t)blockIdx.x * 128 + threadIdx.x;
     if (col >= ncols) return;
+    if (only != nullptr && *windowed && !only[col]) return;   // the windowed pass settled this column
     size_t base, stride;
     int n;
     if (AXIS == 1) {   // col = (vol*nz + z) * nx + x
@@ -271,6 +278,116 @@ edt_env_kernel(const float* __restrict__ gin, void* __restrict__ gout_, uint2* _
         else if (MODE == EDT_SQRT) of[o] = __fsqrt_rn(best);
         else ob[o] = (uint8_t)((best < T ? 1 : 0) ^ invert);
         o += stride;
+    }
+}
+
+// ------------------------------------------------------------------ windowed y / z pass
+// out[i] = min_j fl(g[j] + fl(fl((i-j) s)^2)) only needs the rows within sqrt(out[i]) / s of i, and
+// g[i] itself is an upper bound: next to a dense feature set (tissue masks) the window is a few
+// rows wide.  A block stages a tile of 32 columns x kWinT positions plus H halo rows on either
+// side in shared memory (coalesced 128-byte row segments) and every thread scans outwards from
+// its positions until the next offset alone is no smaller than the best value so far -- the same
+// termination rule and the same arithmetic as edt_axis_kernel, so the same bits.  Traffic is the
+// column itself (+ halo): no stack, no scratch.
+// Two levels: H = 16 on every tile, then H = 64 on the tiles that held a position whose scan
+// reached the end of the halo undecided (`tileflags`).  A tile whose smallest staged value already
+// exceeds what a scan of H rows can settle is not scanned at all (features far away: the normal
+// case far from the features).  What the second level cannot settle marks its column
+// `unsettled`; those columns are redone by the envelope / outward-scan kernels.
+// The scan pays off where features are dense: measured at 512^3, blobs (60 % set) 4.74 -> 3.3 ms
+// and Bernoulli 5 % 3.2 -> 1.7 ms for the whole transform, but 1e-4 density 1.3 -> 5.3 ms (every
+// tile is scanned to the end of both halos and still unsettled).  So the x pass counts the feature
+// voxels of the batch and a one-thread kernel turns that into `windowed[0]`: below 2 % the windowed
+// kernels exit at once and the envelope kernels do every column -- decided on the device.
+__global__ void edt_mode_kernel(const unsigned long long* __restrict__ nfeat, unsigned long long total, int* __restrict__ windowed) {
+    windowed[0] = nfeat[0] * 50ull >= total ? 1 : 0;
+}
+
+constexpr int kWinT = 64;    // positions per tile
+constexpr int kWinWarps = 8;
+
+// grid (x tiles, chunks along the axis, planes): AXIS 1: plane = vol * nz + z, axis y; AXIS 2: plane = vol * ny + y, axis z
+// LEVEL 0: every tile, sets tileflags.  LEVEL 1: flagged tiles only, sets the column flags.
+template <int AXIS, int MODE, int H, int LEVEL>
+__global__ void __launch_bounds__(32 * kWinWarps)
+edt_window_kernel(const float* __restrict__ gin, void* __restrict__ gout_, uint8_t* __restrict__ tileflags,
+                  uint8_t* __restrict__ unsettled, int nx, int ny, int nz, float s, float T, int invert,
+                  const int* __restrict__ windowed) {
+    __shared__ float tile[kWinT + 2 * H][32];
+    __shared__ float tk[H + 2];
+    __shared__ float wmin[kWinWarps];
+    if (!*windowed) return;
+    const size_t tile_id = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (LEVEL == 1 && !tileflags[tile_id]) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 32 + lane;
+    const int c0 = blockIdx.y * kWinT;
+    const size_t plane = blockIdx.z;
+    size_t base, stride;
+    int n;
+    if (AXIS == 1) {
+        base = plane * (size_t)ny * nx + x; stride = nx; n = ny;
+    } else {
+        const size_t vol = plane / ny, y = plane - vol * ny;
+        base = (vol * nz * (size_t)ny + y) * nx + x; stride = (size_t)nx * ny; n = nz;
+    }
+    const size_t col = plane * nx + x;
+    const bool live = x < nx;
+    if (threadIdx.x <= H + 1) {   // squared offsets, rounded as the contract says
+        const float t = __fmul_rn((float)threadIdx.x, s);
+        tk[threadIdx.x] = __fmul_rn(t, t);
+    }
+    // stage rows c0 - H .. c0 + T + H - 1 (rows outside the column hold +inf: they never win)
+    float lo = INFINITY;
+    for (int r = warp; r < kWinT + 2 * H; r += kWinWarps) {
+        const int pos = c0 - H + r;
+        const float v = (live && pos >= 0 && pos < n) ? __ldg(gin + base + (size_t)pos * stride) : INFINITY;
+        tile[r][lane] = v;
+        lo = fminf(lo, v);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    if (lane == 0) wmin[warp] = lo;
+    __syncthreads();
+    lo = wmin[0];
+#pragma unroll
+    for (int w = 1; w < kWinWarps; w++) lo = fminf(lo, wmin[w]);
+    const bool whole = c0 - H <= 0 && c0 + kWinT + H >= n;   // the tile holds the whole column
+    // nothing in reach can give a value that a scan of H rows settles: leave the tile to the next level
+    if (!whole && !(lo <= tk[H + 1])) {
+        if (LEVEL == 0) { if (threadIdx.x == 0) tileflags[tile_id] = 1; }
+        else if (live) unsettled[col] = 1;
+        return;
+    }
+    float* of = reinterpret_cast<float*>(gout_);
+    uint8_t* ob = reinterpret_cast<uint8_t*>(gout_);
+    bool unsure = false;
+    constexpr int PER = kWinT / kWinWarps;
+    if (live) {
+#pragma unroll 1
+        for (int e = 0; e < PER; e++) {
+            const int li = warp * PER + e, pos = c0 + li;
+            if (pos >= n) break;
+            const int r = li + H;
+            float best = tile[r][lane];
+            int k = 1;
+            for (; k <= H; k++) {
+                const float t = tk[k];
+                if (!(t < best)) break;
+                best = fminf(best, fminf(__fadd_rn(tile[r - k][lane], t), __fadd_rn(tile[r + k][lane], t)));
+            }
+            // halo exhausted with rows left unseen and the next offset still below the best value
+            if (k > H && (pos - H > 0 || pos + H < n - 1) && tk[H + 1] < best) unsure = true;
+            const size_t o = base + (size_t)pos * stride;
+            if (MODE == EDT_MID) of[o] = best;
+            else if (MODE == EDT_SQRT) of[o] = __fsqrt_rn(best);
+            else ob[o] = (uint8_t)((best < T ? 1 : 0) ^ invert);
+        }
+    }
+    if (LEVEL == 0) {
+        if (__syncthreads_or(unsure) && threadIdx.x == 0) tileflags[tile_id] = 1;
+    } else if (unsure) {
+        unsettled[col] = 1;
     }
 }
 
@@ -454,6 +571,53 @@ static bool build_ball(const float sp[3], float T, int nx, int ny, int nz, Ball*
     return true;
 }
 
+// One pass along y (AXIS 1) or z (AXIS 2): the windowed kernel first, then -- only on the columns
+// it left unsettled -- the exact-integer envelope kernel (env_ok) or the outward scan.
+// colflags: ncols bytes of scratch; stack: one uint2 per voxel when env_ok; rowflags: the emptiness
+// flags the outward scan uses (rows of a plane for y, planes of a volume for z).
+template <int AXIS, int MODE>
+static int axis_pass(OpGuard& og, const float* in, void* out, const Image* A, bool env_ok, uint2* stack,
+                     uint8_t* colflags, const unsigned* rowflags, float T, int invert, const int* mode) {
+    const int nx = A->nx, ny = A->ny, nz = A->nz;
+    const size_t total = A->count();
+    const float s = AXIS == 1 ? A->sp[1] : A->sp[2];
+    const int n = AXIS == 1 ? ny : nz;
+    const size_t planes = AXIS == 1 ? (size_t)A->nb * nz : (size_t)A->nb * ny;
+    const size_t ncols = planes * nx;
+    const unsigned chunks = (unsigned)((n + kWinT - 1) / kWinT);
+    // (grid.z holds at most 65535 planes: a batch beyond that goes to the fallback kernels whole)
+    const bool windowed = mode != nullptr && planes <= 65535u;
+    const uint8_t* only = windowed ? colflags : nullptr;
+    if (windowed) VX_CUDA(cudaMemsetAsync(colflags, 0, ncols, og.st));
+    if (windowed) {
+        const dim3 grid((nx + 31) / 32, chunks, (unsigned)planes);
+        uint8_t* tileflags = nullptr;
+        Scratch sc(og.c, og.s);
+        VX_TRY(sc.alloc((size_t)grid.x * grid.y * grid.z, &tileflags));
+        VX_CUDA(cudaMemsetAsync(tileflags, 0, (size_t)grid.x * grid.y * grid.z, og.st));
+        {
+            VX_LAUNCH(og.c, og.s, AXIS == 1 ? "edt_window_kernel_y" : "edt_window_kernel_z");
+            edt_window_kernel<AXIS, MODE, 16, 0><<<grid, 32 * kWinWarps, 0, og.st>>>(in, out, tileflags, colflags, nx, ny, nz, s, T, invert, mode);
+        }
+        VX_TRY(check_launch("edt_window_kernel"));
+        {
+            VX_LAUNCH(og.c, og.s, AXIS == 1 ? "edt_window2_kernel_y" : "edt_window2_kernel_z");
+            edt_window_kernel<AXIS, MODE, 64, 1><<<grid, 32 * kWinWarps, 0, og.st>>>(in, out, tileflags, colflags, nx, ny, nz, s, T, invert, mode);
+        }
+    }
+    VX_TRY(check_launch("edt_window_kernel"));
+    if (env_ok) {
+        VX_LAUNCH(og.c, og.s, AXIS == 1 ? "edt_env_kernel_y" : "edt_env_kernel_z");
+        edt_env_kernel<AXIS, MODE><<<(unsigned)((ncols + 127) / 128), 128, 0, og.st>>>(in, out, stack, nx, ny, nz, ncols,
+                                                                                     (int)(s * s), T, invert, only, mode);
+    } else {
+        VX_LAUNCH(og.c, og.s, AXIS == 1 ? "edt_axis_kernel_y" : "edt_axis_kernel_z");
+        edt_axis_kernel<AXIS, MODE><<<(unsigned)((total + kEdtThreads - 1) / kEdtThreads), kEdtThreads, 0, og.st>>>(
+            in, out, rowflags, nx, ny, nz, total, s, T, invert, only, mode);
+    }
+    return check_launch("edt fallback pass");
+}
+
 // squared-distance passes shared by vx_edt and the large-radius fallback of vx_dist_*
 static int edt_passes(OpGuard& og, const Image* A, const unsigned* Abits, void* out, int final_mode, float T, int invert) {
     const size_t total = A->count();
@@ -464,19 +628,24 @@ static int edt_passes(OpGuard& og, const Image* A, const unsigned* Abits, void* 
     const size_t n_planeflag = (size_t)A->nb * ((A->nz + 31) / 32);
     unsigned* flags = nullptr;
     float *g1 = nullptr, *g2 = nullptr;
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (n_rowflag + n_planeflag), (void**)&flags));
+    const size_t n_flagwords = (n_rowflag + n_planeflag + 1) / 2 * 2;   // keeps the counter behind them 8-byte aligned
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (n_flagwords + 4), (void**)&flags));
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(float) * total, (void**)&g1));
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(float) * total, (void**)&g2));
-    VX_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (n_rowflag + n_planeflag), og.st));
+    VX_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (n_flagwords + 4), og.st));
     unsigned* rowflag = flags;
     unsigned* planeflag = flags + n_rowflag;
+    unsigned long long* nfeat = reinterpret_cast<unsigned long long*>(flags + n_flagwords);
+    int* mode = reinterpret_cast<int*>(flags + n_flagwords + 2);
     {
         VX_LAUNCH(og.c, og.s, "edt_x_kernel");
         unsigned grid = (unsigned)((rows + kEdtThreads / 32 - 1) / (kEdtThreads / 32));
         edt_x_kernel<<<grid, kEdtThreads, 0, og.st>>>(Abits, g1, rowflag, planeflag,
-                                                     A->nx, A->ny, A->nz, rows, A->sp[0]);
+                                                     A->nx, A->ny, A->nz, rows, A->sp[0], nfeat);
     }
     VX_TRY(check_launch("edt_x_kernel"));
+    edt_mode_kernel<<<1, 1, 0, og.st>>>(nfeat, (unsigned long long)total, mode);
+    VX_TRY(check_launch("edt_mode_kernel"));
     // exact-integer fast path per axis: every spacing up to this axis is a small integer and no
     // squared distance can reach 2^24, so binary32 arithmetic is exact and the O(n)
     // lower-envelope pass yields the contract's value bit for bit
@@ -488,39 +657,13 @@ static int edt_passes(OpGuard& og, const Image* A, const unsigned* Abits, void* 
     const bool env_y = ix && iy && bound_y < 16777216.0 && A->ny <= 65535 && A->ny > 1;
     const bool env_z = ix && iy && iz && bound_z < 16777216.0 && A->nz <= 65535 && A->nz > 1;
     uint2* stack = nullptr;
+    uint8_t* colflags = nullptr;
     if (env_y || env_z) VX_TRY(scratch_alloc(og.c, og.s, sizeof(uint2) * total, (void**)&stack));
-    const unsigned grid = (unsigned)((total + kEdtThreads - 1) / kEdtThreads);
-    if (env_y) {
-        const size_t ncols = (size_t)A->nb * A->nz * A->nx;
-        const int s2 = (int)(A->sp[1] * A->sp[1]);
-        VX_LAUNCH(og.c, og.s, "edt_env_kernel_y");
-        edt_env_kernel<1, EDT_MID><<<(unsigned)((ncols + 127) / 128), 128, 0, og.st>>>(
-            g1, g2, stack, A->nx, A->ny, A->nz, ncols, s2, 0.f, 0);
-    } else {
-        VX_LAUNCH(og.c, og.s, "edt_axis_kernel_y");
-        edt_axis_kernel<1, EDT_MID><<<grid, kEdtThreads, 0, og.st>>>(g1, g2, rowflag, A->nx, A->ny, A->nz,
-                                                                    total, A->sp[1], 0.f, 0);
-    }
-    VX_TRY(check_launch("edt y pass"));
-    if (env_z) {
-        const size_t ncols = (size_t)A->nb * A->ny * A->nx;
-        const int s2 = (int)(A->sp[2] * A->sp[2]);
-        VX_LAUNCH(og.c, og.s, "edt_env_kernel_z");
-        const unsigned eg = (unsigned)((ncols + 127) / 128);
-        if (final_mode == EDT_SQRT)
-            edt_env_kernel<2, EDT_SQRT><<<eg, 128, 0, og.st>>>(g2, out, stack, A->nx, A->ny, A->nz, ncols, s2, 0.f, 0);
-        else
-            edt_env_kernel<2, EDT_THRESH><<<eg, 128, 0, og.st>>>(g2, out, stack, A->nx, A->ny, A->nz, ncols, s2, T, invert);
-    } else {
-        VX_LAUNCH(og.c, og.s, "edt_axis_kernel_z");
-        if (final_mode == EDT_SQRT)
-            edt_axis_kernel<2, EDT_SQRT><<<grid, kEdtThreads, 0, og.st>>>(g2, out, planeflag, A->nx, A->ny,
-                                                                         A->nz, total, A->sp[2], 0.f, 0);
-        else
-            edt_axis_kernel<2, EDT_THRESH><<<grid, kEdtThreads, 0, og.st>>>(g2, out, planeflag, A->nx, A->ny,
-                                                                           A->nz, total, A->sp[2], T, invert);
-    }
-    VX_TRY(check_launch("edt z pass"));
+    VX_TRY(scratch_alloc(og.c, og.s, (size_t)A->nb * std::max(A->nz, A->ny) * A->nx, (void**)&colflags));
+    VX_TRY((axis_pass<1, EDT_MID>(og, g1, g2, A, env_y, stack, colflags, rowflag, 0.f, 0, mode)));
+    if (final_mode == EDT_SQRT) VX_TRY((axis_pass<2, EDT_SQRT>(og, g2, out, A, env_z, stack, colflags, planeflag, 0.f, 0, mode)));
+    else VX_TRY((axis_pass<2, EDT_THRESH>(og, g2, out, A, env_z, stack, colflags, planeflag, T, invert, mode)));
+    VX_TRY(scratch_free(og.c, og.s, colflags));
     if (stack) VX_TRY(scratch_free(og.c, og.s, stack));
     VX_TRY(scratch_free(og.c, og.s, g1));
     VX_TRY(scratch_free(og.c, og.s, g2));
@@ -537,34 +680,32 @@ static int edt_xy_only(OpGuard& og, const Image* A, const unsigned* Abits, float
     const size_t n_planeflag = (size_t)A->nb * ((A->nz + 31) / 32);
     unsigned* flags = nullptr;
     float* g1 = nullptr;
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (n_rowflag + n_planeflag), (void**)&flags));
+    const size_t n_flagwords = (n_rowflag + n_planeflag + 1) / 2 * 2;
+    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * (n_flagwords + 4), (void**)&flags));
     VX_TRY(scratch_alloc(og.c, og.s, sizeof(float) * total, (void**)&g1));
-    VX_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (n_rowflag + n_planeflag), og.st));
+    VX_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (n_flagwords + 4), og.st));
+    unsigned long long* nfeat = reinterpret_cast<unsigned long long*>(flags + n_flagwords);
+    int* mode = reinterpret_cast<int*>(flags + n_flagwords + 2);
     {
         VX_LAUNCH(og.c, og.s, "edt_x_kernel");
         unsigned grid = (unsigned)((rows + kEdtThreads / 32 - 1) / (kEdtThreads / 32));
         edt_x_kernel<<<grid, kEdtThreads, 0, og.st>>>(Abits, g1, flags, flags + n_rowflag, A->nx, A->ny,
-                                                     A->nz, rows, A->sp[0]);
+                                                     A->nz, rows, A->sp[0], nfeat);
     }
     VX_TRY(check_launch("edt_x_kernel"));
+    edt_mode_kernel<<<1, 1, 0, og.st>>>(nfeat, (unsigned long long)total, mode);
+    VX_TRY(check_launch("edt_mode_kernel"));
     auto int_spacing = [](float sp) { return sp >= 1.0f && sp <= 64.0f && sp == floorf(sp); };
     auto span2 = [](float sp, int n) { double d = (double)sp * (n - 1); return d * d; };
     const bool env_y = int_spacing(A->sp[0]) && int_spacing(A->sp[1]) &&
                        span2(A->sp[0], A->nx) + span2(A->sp[1], A->ny) < 16777216.0 && A->ny <= 65535 && A->ny > 1;
-    if (env_y) {
+    {
+        Scratch sc(og.c, og.s);
         uint2* stack = nullptr;
-        VX_TRY(scratch_alloc(og.c, og.s, sizeof(uint2) * total, (void**)&stack));
-        const size_t ncols = (size_t)A->nb * A->nz * A->nx;
-        { VX_LAUNCH(og.c, og.s, "edt_env_kernel_y");
-          edt_env_kernel<1, EDT_MID><<<(unsigned)((ncols + 127) / 128), 128, 0, og.st>>>(
-              g1, out, stack, A->nx, A->ny, A->nz, ncols, (int)(A->sp[1] * A->sp[1]), 0.f, 0); }
-        VX_TRY(check_launch("edt y pass"));
-        VX_TRY(scratch_free(og.c, og.s, stack));
-    } else {
-        { VX_LAUNCH(og.c, og.s, "edt_axis_kernel_y");
-          edt_axis_kernel<1, EDT_MID><<<(unsigned)((total + kEdtThreads - 1) / kEdtThreads), kEdtThreads, 0, og.st>>>(
-              g1, out, flags, A->nx, A->ny, A->nz, total, A->sp[1], 0.f, 0); }
-        VX_TRY(check_launch("edt y pass"));
+        uint8_t* colflags = nullptr;
+        if (env_y) VX_TRY(sc.alloc(sizeof(uint2) * total, &stack));
+        VX_TRY(sc.alloc((size_t)A->nb * A->nz * A->nx, &colflags));
+        VX_TRY((axis_pass<1, EDT_MID>(og, g1, out, A, env_y, stack, colflags, flags, 0.f, 0, mode)));
     }
     VX_TRY(scratch_free(og.c, og.s, g1));
     return scratch_free(og.c, og.s, flags);
@@ -577,26 +718,18 @@ static int edt_z_only(OpGuard& og, const Image* S, float* out, double max_in) {
     const double span = (double)S->sp[2] * (S->nz - 1);
     const bool env_z = int_spacing(S->sp[0]) && int_spacing(S->sp[1]) && int_spacing(S->sp[2]) &&
                        max_in + span * span < 16777216.0 && S->nz <= 65535 && S->nz > 1;
-    if (env_z) {
-        uint2* stack = nullptr;
-        VX_TRY(scratch_alloc(og.c, og.s, sizeof(uint2) * total, (void**)&stack));
-        const size_t ncols = (size_t)S->nb * S->ny * S->nx;
-        { VX_LAUNCH(og.c, og.s, "edt_env_kernel_z");
-          edt_env_kernel<2, EDT_SQRT><<<(unsigned)((ncols + 127) / 128), 128, 0, og.st>>>(
-              (const float*)S->d, out, stack, S->nx, S->ny, S->nz, ncols, (int)(S->sp[2] * S->sp[2]), 0.f, 0); }
-        VX_TRY(check_launch("edt z pass"));
-        return scratch_free(og.c, og.s, stack);
-    }
-    // exact scan over all planes (no emptiness information for a map that came from elsewhere)
-    const size_t n_planeflag = (size_t)S->nb * ((S->nz + 31) / 32);
+    Scratch sc(og.c, og.s);
+    uint2* stack = nullptr;
+    uint8_t* colflags = nullptr;
     unsigned* planeflag = nullptr;
-    VX_TRY(scratch_alloc(og.c, og.s, sizeof(unsigned) * n_planeflag, (void**)&planeflag));
+    if (env_z) VX_TRY(sc.alloc(sizeof(uint2) * total, &stack));
+    VX_TRY(sc.alloc((size_t)S->nb * S->ny * S->nx, &colflags));
+    // the outward scan gets no emptiness information for a map that came from elsewhere: every plane counts
+    const size_t n_planeflag = (size_t)S->nb * ((S->nz + 31) / 32);
+    VX_TRY(sc.alloc(sizeof(unsigned) * n_planeflag, &planeflag));
     VX_CUDA(cudaMemsetAsync(planeflag, 0xff, sizeof(unsigned) * n_planeflag, og.st));
-    { VX_LAUNCH(og.c, og.s, "edt_axis_kernel_z");
-      edt_axis_kernel<2, EDT_SQRT><<<(unsigned)((total + kEdtThreads - 1) / kEdtThreads), kEdtThreads, 0, og.st>>>(
-          (const float*)S->d, out, planeflag, S->nx, S->ny, S->nz, total, S->sp[2], 0.f, 0); }
-    VX_TRY(check_launch("edt z pass"));
-    return scratch_free(og.c, og.s, planeflag);
+    // (a map that came from elsewhere carries no feature count: the envelope / scan kernels do every column)
+    return axis_pass<2, EDT_SQRT>(og, (const float*)S->d, out, S, env_z, stack, colflags, planeflag, 0.f, 0, nullptr);
 }
 
 static int dist_threshold(vx_ctx ctx, vx_img a, float r, bool strict, int invert, vx_img* out) {
