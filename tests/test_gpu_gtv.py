@@ -28,6 +28,34 @@ def test_gtv_spec_matches_oracle(ctx, oracle, shape, seeds):
     assert got["_tasks"] < 60     # hash-consing: shared sub-terms evaluated once
 
 
+@pytest.mark.parametrize("shape", [(48, 80, 96), (33, 50, 70)])
+def test_gtv_spec_on_16bit_upload_matches_oracle(ctx, oracle, shape):
+    """the bench's input path: int16 voxels + scl_slope uploaded with vx_upload_scaled.  The image keeps its
+    16-bit codes, so min/max come from the recorded code range, percentiles are counted and the
+    crossCorrelation bins are tabulated per code -- every named intermediate must still equal the oracle
+    run on the f32 image, bit for bit, with the quantised paths on and off."""
+    from gtv_ref import gtv_oracle
+    from voxlogica_b200 import _abi as A
+    from voxlogica_b200.imgql import run_gtv
+    from voxlogica_b200.synth import brats_like_int16, int16_to_f32
+    raws, slope = zip(*[brats_like_int16(sd, shape) for sd in (1234, 9)])
+    raw = np.stack(raws)
+    f32 = int16_to_f32(raw, slope[0])
+    wants = [gtv_oracle(oracle, f32[i]) for i in range(len(raws))]
+    for opt in (1, 0):
+        ctx.set_option(A.VX_OPT_QUANTISED_PATHS, opt)
+        try:
+            got = run_gtv(ctx, ctx.upload_scaled(raw, slope[0]))
+        finally:
+            ctx.set_option(A.VX_OPT_QUANTISED_PATHS, 1)
+        for i, want in enumerate(wants):
+            for name in NAMES_BOOL:
+                assert np.array_equal(got[name].numpy()[i], want[name]), (name, i, opt)
+            for name in ("normFlair", "tumSim"):
+                assert np.array_equal(got[name].numpy()[i].view(np.uint32), want[name].view(np.uint32)), (name, i, opt)
+            assert got["_printed"]["gtvVolume"][i] == want["gtv"].sum()
+
+
 def test_texture_spec_matches_oracle(ctx, oracle):
     """BASELINE config 4: crossCorrelation texture similarity on four co-registered modalities,
     batched, against the oracle composition (bit-exact, the f32 coefficient maps included)."""

@@ -349,6 +349,29 @@ def test_percentiles_of_quantised_images(ctx, oracle, dtype, slope, inter, lo, h
                               per_volume(oracle.percentiles, f, np.ones(shape, np.uint8), correction=0.0).view(np.uint32))
 
 
+def test_extrema_of_quantised_images(ctx):
+    """min / max / minmax of an image uploaded as 16-bit codes come from the recorded code range of every
+    volume (no pass over the image) and equal the reductions of the f32 image"""
+    from voxlogica_b200 import _abi as A
+    rng = np.random.default_rng(75)
+    for dtype, slope, inter in [(np.int16, 1.0 / 4095.0, 0.0), (np.uint16, -2.5, 1e3), (np.int16, 0.25, -3.0)]:
+        for shape in [(3, 6, 20, 32), (2, 3, 5, 7), (1, 1, 1, 1)]:
+            info = np.iinfo(dtype)
+            raw = np.stack([rng.integers(max(info.min, -500 * (v + 1)), min(info.max, 700 * (v + 2)), size=shape[1:])
+                            for v in range(shape[0])]).astype(dtype)
+            img = ctx.upload_scaled(raw, slope, inter)
+            f = (raw.astype(np.float32) * np.float32(slope) + np.float32(inter)).reshape(shape[0], -1)
+            for opt in (1, 0):
+                ctx.set_option(A.VX_OPT_QUANTISED_PATHS, opt)
+                try:
+                    lo, hi = ctx.minmax(img)
+                    assert np.array_equal(lo, f.min(1).astype(np.float64)) and np.array_equal(hi, f.max(1).astype(np.float64))
+                    assert np.array_equal(ctx.min(img), f.min(1).astype(np.float64))
+                    assert np.array_equal(ctx.max(img), f.max(1).astype(np.float64))
+                finally:
+                    ctx.set_option(A.VX_OPT_QUANTISED_PATHS, 1)
+
+
 def test_quantisation_tag_needs_a_strictly_monotone_scaling(ctx, oracle):
     """slope 0 or a scaling that collapses neighbouring codes in binary32 gives no tag: the sort decides"""
     rng = np.random.default_rng(73)

@@ -53,10 +53,11 @@ struct Image {
     // voxels have equal codes and the order of the codes is the order of the voxels.  Operators
     // that only need the ORDER of the values (percentiles) may work on the codes: 65536 possible
     // values make ranking a counting problem instead of a sort.  q16 also holds, after the codes,
-    // two ints: the smallest and the largest order-preserving code u (see q_ucode) of the batch.
+    // two ints per volume: its smallest and largest order-preserving code u (q + 32768 for int16).
     void* q16 = nullptr;
     int q_dtype = 0;              // VX_I16 / VX_U16, 0 = no tag
     bool q_increasing = true;
+    float q_slope = 1.f, q_inter = 0.f;
     const int* q_range() const { return reinterpret_cast<const int*>(static_cast<const char*>(q16) + ((count() + 7) / 8 * 8) * 2); }
     size_t bit_words() const { return (count() + 31) / 32; }
     size_t nvox() const { return (size_t)nx * ny * nz; }       // per volume

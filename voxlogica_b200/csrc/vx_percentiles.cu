@@ -524,10 +524,10 @@ __global__ void __launch_bounds__(256)
 pq_hist_kernel(const T* __restrict__ q, const unsigned* __restrict__ mask, size_t nvox, const int* __restrict__ qrange,
                unsigned* __restrict__ hist) {
     extern __shared__ unsigned pq_sh[];
-    const int ulo = qrange[0], uhi = qrange[1];
+    const size_t vol = blockIdx.y;
+    const int ulo = qrange[2 * vol], uhi = qrange[2 * vol + 1];
     const int span = uhi - ulo + 1;
     const bool win = span <= kPqWin;            // the usual case: 12-bit scanner data spans 4096 codes
-    const size_t vol = blockIdx.y;
     unsigned* hv = hist + vol * kPqCodes;
     if (win)
         for (int i = threadIdx.x; i < span; i += 256) pq_sh[i] = 0u;
@@ -573,9 +573,9 @@ pq_table_kernel(const unsigned* __restrict__ hist, const int* __restrict__ qrang
                 double correction, int increasing) {
     __shared__ unsigned long long wsum[32];
     __shared__ unsigned long long carry_s;
-    const int ulo = qrange[0], uhi = qrange[1];
-    const int span = uhi - ulo + 1;
     const size_t vol = blockIdx.x;
+    const int ulo = qrange[2 * vol], uhi = qrange[2 * vol + 1];
+    const int span = uhi - ulo + 1;
     const unsigned* hv = hist + vol * kPqCodes;
     float* tv = table + vol * kPqCodes;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -632,10 +632,10 @@ pq_apply_kernel(const T* __restrict__ q, const unsigned* __restrict__ mask, size
                 const float* __restrict__ table, float* __restrict__ out) {
     extern __shared__ unsigned pq_sh[];
     float* tab = reinterpret_cast<float*>(pq_sh);
-    const int ulo = qrange[0], uhi = qrange[1];
+    const size_t vol = blockIdx.y;
+    const int ulo = qrange[2 * vol], uhi = qrange[2 * vol + 1];
     const int span = uhi - ulo + 1;
     const bool win = span <= kPqWin;
-    const size_t vol = blockIdx.y;
     const float* tv = table + vol * kPqCodes;
     if (win)
         for (int i = threadIdx.x; i < span; i += 256) tab[i] = tv[ulo + i];

@@ -162,10 +162,34 @@ reduce_final_kernel(const double* __restrict__ partial, int per_volume, double* 
     if (threadIdx.x == 0) out[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = v;
 }
 
+// min / max of a quantised image (the tag of vx_internal.h) without reading it: the scaling is
+// monotone, so the extrema are the values of the smallest and the largest code of each volume, which
+// the upload already recorded.  out: nb minima (want & 1), then nb maxima (want & 2), as reduce_device.
+__global__ void quant_extrema_kernel(const int* __restrict__ qrange, int nb, int is_signed, int increasing, float slope,
+                                     float inter, int want, double* __restrict__ out) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nb) return;
+    const int bias = is_signed ? 32768 : 0;
+    const float flo = __fadd_rn(__fmul_rn((float)(qrange[2 * v] - bias), slope), inter);
+    const float fhi = __fadd_rn(__fmul_rn((float)(qrange[2 * v + 1] - bias), slope), inter);
+    const float mn = increasing ? flo : fhi, mx = increasing ? fhi : flo;
+    int k = 0;
+    if (want & 1) out[(k++) * nb + v] = (double)mn;
+    if (want & 2) out[k * nb + v] = (double)mx;
+}
+
 // Runs the reduction and leaves nb doubles (RED_MINMAX: nb minima, then nb maxima) in device
 // memory `d_out` (scratch owned by the caller)
 int reduce_device(OpGuard& g, int kind, const Image* a, const Image* mask, double* d_out, const unsigned* a_bits) {
     const size_t nvox = a->nvox();
+    if (a->q16 != nullptr && mask == nullptr && g.c->quantised_paths.load() &&
+        (kind == RED_MIN || kind == RED_MAX || kind == RED_MINMAX)) {
+        const int want = kind == RED_MIN ? 1 : kind == RED_MAX ? 2 : 3;
+        { VX_LAUNCH(g.c, g.s, "quant_extrema_kernel");
+          quant_extrema_kernel<<<(a->nb + 127) / 128, 128, 0, g.st>>>(a->q_range(), a->nb, a->q_dtype == VX_I16, a->q_increasing ? 1 : 0,
+                                                                   a->q_slope, a->q_inter, want, d_out); }
+        return check_launch("quant_extrema_kernel");
+    }
     int per_volume = (int)((nvox + (size_t)kRedThreads * 16 * 4 - 1) / ((size_t)kRedThreads * 16 * 4));
     int cap = (kNumSMs * 8 + a->nb - 1) / a->nb;
     if (per_volume > cap) per_volume = cap;

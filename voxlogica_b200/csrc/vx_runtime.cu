@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <cmath>
 #include <type_traits>
 
@@ -590,42 +591,48 @@ int OpGuard::finish_scalar() {
 // ---- transfer kernels ---------------------------------------------------------
 // raw 16-bit voxels -> f32 with the file's slope/intercept, one rounding per operation (the host
 // loader computes raw.astype(f32) * slope + inter the same way); 8 voxels per thread
-// qrange[0] / qrange[1] receive the smallest / largest order-preserving code of the batch
-// (u = q + 32768 for int16, q for uint16; initialised to 65535 / 0 by the caller).
+// qrange[2 v] / qrange[2 v + 1] receive the smallest / largest order-preserving code of volume v
+// (u = q + 32768 for int16, q for uint16; initialised to 65535 / 0 by the caller).  grid (blocks, nb).
 template <typename T>
 __global__ void __launch_bounds__(256)
-convert16_kernel(const T* __restrict__ raw, float* __restrict__ out, size_t n, float slope, float inter,
+convert16_kernel(const T* __restrict__ raw_all, float* __restrict__ out_all, size_t nvox, float slope, float inter,
                  int* __restrict__ qrange) {
     constexpr int bias = std::is_signed<T>::value ? 32768 : 0;
+    const size_t vol = blockIdx.y;
+    const T* raw = raw_all + vol * nvox;
+    float* out = out_all + vol * nvox;
     int lo_u = 65535, hi_u = 0;
-    const size_t ng = n >> 3;
-    for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < ng; g += (size_t)gridDim.x * 256) {
-        const uint4 w = __ldg(reinterpret_cast<const uint4*>(raw) + g);
-        const unsigned ww[4] = {w.x, w.y, w.z, w.w};
-        float f[8];
+    if ((nvox & 7) == 0) {   // every volume starts 16-byte aligned: 8 voxels per thread and trip
+        const size_t ng = nvox >> 3;
+        for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < ng; g += (size_t)gridDim.x * 256) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4*>(raw) + g);
+            const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+            float f[8];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const T lo = (T)(ww[i] & 0xffffu), hi = (T)(ww[i] >> 16);
-            f[2 * i] = __fadd_rn(__fmul_rn((float)lo, slope), inter);
-            f[2 * i + 1] = __fadd_rn(__fmul_rn((float)hi, slope), inter);
-            lo_u = min(lo_u, min((int)lo, (int)hi) + bias);
-            hi_u = max(hi_u, max((int)lo, (int)hi) + bias);
+            for (int i = 0; i < 4; i++) {
+                const T lo = (T)(ww[i] & 0xffffu), hi = (T)(ww[i] >> 16);
+                f[2 * i] = __fadd_rn(__fmul_rn((float)lo, slope), inter);
+                f[2 * i + 1] = __fadd_rn(__fmul_rn((float)hi, slope), inter);
+                lo_u = min(lo_u, min((int)lo, (int)hi) + bias);
+                hi_u = max(hi_u, max((int)lo, (int)hi) + bias);
+            }
+            float4* o = reinterpret_cast<float4*>(out) + 2 * g;
+            o[0] = make_float4(f[0], f[1], f[2], f[3]);
+            o[1] = make_float4(f[4], f[5], f[6], f[7]);
         }
-        float4* o = reinterpret_cast<float4*>(out) + 2 * g;
-        o[0] = make_float4(f[0], f[1], f[2], f[3]);
-        o[1] = make_float4(f[4], f[5], f[6], f[7]);
-    }
-    if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {   // tail
-        const size_t i = (ng << 3) + threadIdx.x;
-        out[i] = __fadd_rn(__fmul_rn((float)raw[i], slope), inter);
-        lo_u = min(lo_u, (int)raw[i] + bias);
-        hi_u = max(hi_u, (int)raw[i] + bias);
+    } else {
+        for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvox; i += (size_t)gridDim.x * 256) {
+            const T q = raw[i];
+            out[i] = __fadd_rn(__fmul_rn((float)q, slope), inter);
+            lo_u = min(lo_u, (int)q + bias);
+            hi_u = max(hi_u, (int)q + bias);
+        }
     }
     lo_u = __reduce_min_sync(0xffffffffu, lo_u);
     hi_u = __reduce_max_sync(0xffffffffu, hi_u);
     if ((threadIdx.x & 31) == 0 && lo_u <= hi_u) {
-        atomicMin(qrange, lo_u);
-        atomicMax(qrange + 1, hi_u);
+        atomicMin(qrange + 2 * vol, lo_u);
+        atomicMax(qrange + 2 * vol + 1, hi_u);
     }
 }
 
@@ -794,22 +801,26 @@ int32_t vx_upload_scaled(vx_ctx ctx, const void* host, int32_t host_dtype, float
     // 2 more bytes per voxel buy operators that rank values a counting pass instead of a sort
     void* raw = nullptr;
     const size_t code_bytes = ((n + 7) / 8 * 8) * 2;
-    int rc = dev_alloc(g.c, im->home, code_bytes + 16, &raw);
+    int rc = dev_alloc(g.c, im->home, code_bytes + 8 * (size_t)nb, &raw);
     int* qrange = rc == VX_OK ? reinterpret_cast<int*>(static_cast<char*>(raw) + code_bytes) : nullptr;
     if (rc == VX_OK) {
-        const int init[2] = {65535, 0};
+        std::vector<int> init(2 * (size_t)nb);
+        for (int v = 0; v < nb; v++) { init[2 * v] = 65535; init[2 * v + 1] = 0; }
         cudaError_t e = cudaMemcpyAsync(raw, host, n * 2, cudaMemcpyDefault, g.st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(qrange, init, sizeof(init), cudaMemcpyHostToDevice, g.st);
+        // (pageable source: the runtime stages it before returning)
+        if (e == cudaSuccess) e = cudaMemcpyAsync(qrange, init.data(), 8 * (size_t)nb, cudaMemcpyHostToDevice, g.st);
         if (e != cudaSuccess) rc = fail(VX_E_CUDA, "upload failed: %s", cudaGetErrorString(e));
     }
     if (rc == VX_OK) {
-        const int grid = grid_for(n / 8 + 1, 256, 8);
+        const size_t nvox = im->nvox();
+        const int per_vol = std::max(1, std::min((int)((nvox / 8 + 255) / 256), (kNumSMs * 8 + nb - 1) / nb));
+        const dim3 grid(per_vol, nb);
         {
             VX_LAUNCH(g.c, g.s, "convert16_kernel");
             if (host_dtype == VX_I16)
-                convert16_kernel<short><<<grid, 256, 0, g.st>>>((const short*)raw, (float*)im->d, n, slope, inter, qrange);
+                convert16_kernel<short><<<grid, 256, 0, g.st>>>((const short*)raw, (float*)im->d, nvox, slope, inter, qrange);
             else
-                convert16_kernel<unsigned short><<<grid, 256, 0, g.st>>>((const unsigned short*)raw, (float*)im->d, n, slope, inter, qrange);
+                convert16_kernel<unsigned short><<<grid, 256, 0, g.st>>>((const unsigned short*)raw, (float*)im->d, nvox, slope, inter, qrange);
         }
         rc = check_launch("convert16_kernel");
     }
@@ -823,6 +834,8 @@ int32_t vx_upload_scaled(vx_ctx ctx, const void* host, int32_t host_dtype, float
         im->q16 = raw;
         im->q_dtype = host_dtype;
         im->q_increasing = mono > 0;
+        im->q_slope = slope;
+        im->q_inter = inter;
     } else {
         dev_free(g.c, im->home, raw);   // stream-ordered: recycled after the conversion kernel
     }
