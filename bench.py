@@ -411,16 +411,30 @@ def run_ours(args):
     nres = max(1, args.threads)
     last = [None] * nres
 
-    def resident_worker(t, nsteps, errors):
+    class StepQueue:
+        """the K steps of a run, handed to whichever host thread is free next (a fixed split leaves one
+        thread with an extra step when K is not a multiple of the thread count)"""
+        def __init__(self, n):
+            self.n, self.next, self.mu = n, 0, threading.Lock()
+
+        def take(self):
+            with self.mu:
+                if self.next >= self.n:
+                    return False
+                self.next += 1
+                return True
+
+    def resident_worker(t, queue, errors):
         try:
-            for _ in range(t, nsteps, nres):
+            while queue.take():
                 _, last[t] = step_resident(flair)
         except Exception as e:  # pragma: no cover
             errors.append(e)
 
     def run_resident(nsteps):
         errors = []
-        ths = [threading.Thread(target=resident_worker, args=(t, nsteps, errors)) for t in range(nres)]
+        queue = StepQueue(nsteps)
+        ths = [threading.Thread(target=resident_worker, args=(t, queue, errors)) for t in range(nres)]
         [t.start() for t in ths]
         [t.join() for t in ths]
         if errors:
@@ -464,9 +478,9 @@ def run_ours(args):
     for t in range(nthr):
         C.memmove(pins_in[t], host.ctypes.data, host.nbytes)
 
-    def e2e_worker(t, nsteps, errors):
+    def e2e_worker(t, queue, errors):
         try:
-            for _ in range(t, nsteps, nthr):
+            while queue.take():
                 f = ctx.upload_scaled_ptr(pins_in[t], np.int16, shape4, INT16_SLOPE)
                 out = run_gtv(ctx, f)
                 ctx.download_bits_ptr(out["gtv"], pins_out[t], out_bytes)
@@ -475,7 +489,8 @@ def run_ours(args):
 
     def run_e2e(nsteps):
         errors = []
-        ths = [threading.Thread(target=e2e_worker, args=(t, nsteps, errors)) for t in range(nthr)]
+        queue = StepQueue(nsteps)
+        ths = [threading.Thread(target=e2e_worker, args=(t, queue, errors)) for t in range(nthr)]
         [t.start() for t in ths]
         [t.join() for t in ths]
         if errors:

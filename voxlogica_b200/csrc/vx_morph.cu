@@ -215,7 +215,7 @@ border16_kernel(uint4* __restrict__ out, int ncx, int nx, int ny, int nz, size_t
 // three row loads per output word instead of nine.  Erosion is the dilation of the complement
 // inside the image (voxels outside do not exist), complemented.  Traffic: 1/8 byte in and out per
 // voxel; the rows of a neighbourhood are L1/L2 hits.
-constexpr int kBitZL = 16;
+constexpr int kBitZL = 8;
 
 // word w of the row at stream position p: its bits c and the bits spread by one voxel in x
 template <bool ERODE>
@@ -283,7 +283,10 @@ morph_bits_kernel(const unsigned* __restrict__ in, unsigned* __restrict__ out, i
     unsigned Am, Cm, A0, C0, A1, C1;
     load_plane(z0 - 1, Am, Cm);
     load_plane(z0, A0, C0);
-    for (int z = z0; z < z1; z++) {
+    // (fully unrolled: the row loads of the planes ahead are issued before the stores of the planes behind)
+#pragma unroll
+    for (int z = z0; z < z0 + kBitZL; z++) {
+        if (z >= z1) break;
         load_plane(z + 1, A1, C1);
         unsigned acc = A0 | Cm | C1;
         if (ERODE) acc = ~acc;
