@@ -637,8 +637,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="BraTS volumes per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--threads", type=int, default=3,
-                    help="host threads (= CUDA streams of the library) that take the steps in turn")
+    ap.add_argument("--threads", type=int, default=2,
+                    help="host threads (= CUDA streams of the library) that take the steps in turn.  Two: one step's "
+                         "upload overlaps the other's kernels; with three or more, two uploads share the PCIe link and the "
+                         "one the GPU is waiting for arrives later (measured: e2e 1994 volumes/s with 2, 1716 with 3, "
+                         "1622 with 4 or 6; the resident number is the same 2230-2270 for all)")
     ap.add_argument("--wc", action="store_true", help="write-combined pinned staging buffers for the uploads")
     ap.add_argument("--no-slab", action="store_true", help="skip the slab-decomposed volume record of N > 1 runs")
     ap.add_argument("--prof-timed", action="store_true",

@@ -48,6 +48,8 @@ def main():
     # inputs ---------------------------------------------------------------------------
     flair_h = rep(synth.brats_like(1234, shape))
     flair = ctx.upload(flair_h)
+    # the same volumes as a 16-bit file holds them (the bench's input path): the image keeps its codes
+    flair16 = ctx.upload_scaled(np.rint(flair_h * np.float32(synth.INT16_SCALE)).astype(np.int16), synth.INT16_SLOPE)
     noise = ctx.upload(rng.random((B,) + shape, dtype=np.float32))
     zeros = ctx.upload(np.zeros((B,) + shape, np.float32))
     bg = ctx.cmp_scalar(flair, "<", 0.1)                      # dense mask (~75% set, one giant component)
@@ -58,6 +60,7 @@ def main():
     brain = ctx.not_(ctx.and_(bg, ctx.through(ctx.near(ctx.border(bg)), bg)))
     lesion = ctx.cmp_scalar(flair, ">", 0.75)
     mn, mx = ctx.min(flair), ctx.max(flair)
+    mn16, mx16 = ctx.min(flair16), ctx.max(flair16)
     ctx.sync()
 
     # (name, callable, algorithmic bytes per voxel)
@@ -87,9 +90,13 @@ def main():
         ("distlt r=5 blobs", lambda: ctx.distlt(5.0, blobs), 2),
         ("distgeq r=2 blobs", lambda: ctx.distgeq(2.0, blobs), 2),
         ("distlt r=12 blobs", lambda: ctx.distlt(12.0, blobs), 2),
-        ("percentiles brain", lambda: ctx.percentiles(flair, brain), 9),
-        ("percentiles all", lambda: ctx.percentiles(noise, ctx.tt(bg)), 9),
+        ("percentiles brain f32 (sort)", lambda: ctx.percentiles(flair, brain), 9),
+        ("percentiles brain 16-bit upload (counting)", lambda: ctx.percentiles(flair16, brain), 9),
+        ("percentiles all f32 noise (sort)", lambda: ctx.percentiles(noise, ctx.tt(bg)), 9),
+        ("minmax f32", lambda: ctx.minmax(flair), 4),
+        ("minmax 16-bit upload (code range)", lambda: ctx.minmax(flair16), 4),
         ("xcorr rho5 k100 flair", lambda: ctx.cross_correlation(5.0, flair, flair, lesion, mn, mx, 100), 13),
+        ("xcorr rho5 k100 16-bit upload", lambda: ctx.cross_correlation(5.0, flair16, flair16, lesion, mn16, mx16, 100), 13),
         ("xcorr rho5 k100 noise", lambda: ctx.cross_correlation(5.0, noise, noise, lesion, 0.0, 1.0, 100), 13),
         ("xcorr rho5 k100 zeros", lambda: ctx.cross_correlation(5.0, zeros, zeros, lesion, 0.0, 1.0, 100), 13),
         ("xcorr rho2 k100 flair", lambda: ctx.cross_correlation(2.0, flair, flair, lesion, mn, mx, 100), 13),

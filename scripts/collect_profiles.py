@@ -15,7 +15,7 @@ G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 
 
-def main(pre="r01"):
+def main(pre="r02"):
     py = sys.executable
     copies = {"bench_default.json": f"{pre}_bench_b16.json", "bench_b8.json": f"{pre}_bench_b8.json",
               "bench_reference.json": f"{pre}_bench_reference_arm.json", "ops_brats_b16.json": f"{pre}_ops_brats_b16.json",
@@ -31,7 +31,7 @@ def main(pre="r01"):
         subprocess.check_call([py, os.path.join(ROOT, "scripts", "summarize_ncu.py"), "launches",
                                os.path.join(G, "launches.csv"), os.path.join(P, f"{pre}_launches_bench_b8.json")])
     if os.path.isdir(os.path.join(G, "ncu")):
-        subprocess.check_call([py, os.path.join(ROOT, "scripts", "summarize_ncu_dir.py"), os.path.join(G, "ncu"),
+        subprocess.check_call([py, os.path.join(ROOT, "scripts", "summarize_ncu.py"), "families", os.path.join(G, "ncu"),
                                os.path.join(P, f"{pre}_ncu_kernels.json")])
     xr = os.path.join(G, "ncu", "xcorr.ncu-rep")
     if os.path.exists(xr):
