@@ -1,5 +1,6 @@
 """Per-operator microbenchmark: Gvoxel/s and achieved GB/s (algorithmic bytes) against the
-measured HBM peak, per SURVEY.md section 8(d).  Every operator is timed with CUDA events on
+measured HBM peak, per SURVEY.md section 8(d).  Algorithmic bytes count a boolean voxel as ONE BIT
+(round 2: boolean images live as bits on the device), a number as 4 bytes, a 16-bit code as 2.  Every operator is timed with CUDA events on
 the library's stream, after warm-up, with an L2 flush before each timed call.
 
     python scripts/bench_ops.py [--shape brats|512|256] [--batch B] [--reps R] [--only name,name]
@@ -65,43 +66,43 @@ def main():
 
     # (name, callable, algorithmic bytes per voxel)
     ops = [
-        ("threshold f32->u8", lambda: ctx.cmp_scalar(flair, "<", 0.1), 5),
-        ("not u8", lambda: ctx.not_(bg), 2),
-        ("and u8", lambda: ctx.and_(bg, blobs), 3),
+        ("threshold f32->bool", lambda: ctx.cmp_scalar(flair, "<", 0.1), 4.125),
+        ("not", lambda: ctx.not_(bg), 0.25),
+        ("and", lambda: ctx.and_(bg, blobs), 0.375),
         ("arith f32*s", lambda: ctx.arith_scalar(flair, "*", 2.0), 8),
-        ("volume", lambda: ctx.volume(bg), 1),
+        ("volume", lambda: ctx.volume(bg), 0.125),
         ("max f32", lambda: ctx.max(flair), 4),
-        ("border", lambda: ctx.border(bg), 1),
-        ("near26", lambda: ctx.near(blobs, 26), 2),
-        ("near6", lambda: ctx.near(blobs, 6), 2),
-        ("interior26", lambda: ctx.interior(blobs, 26), 2),
-        ("through26 bg-mask", lambda: ctx.through(seeds, bg, 26), 3),
-        ("through26 blobs", lambda: ctx.through(seeds, blobs, 26), 3),
-        ("through6 blobs", lambda: ctx.through(seeds, blobs, 6), 3),
-        ("ccl26 bernoulli .05", lambda: ctx.components(bern[0.05], 26), 5),
-        ("ccl26 bernoulli .3", lambda: ctx.components(bern[0.3], 26), 5),
-        ("ccl26 bernoulli .6", lambda: ctx.components(bern[0.6], 26), 5),
-        ("ccl26 blobs", lambda: ctx.components(blobs, 26), 5),
-        ("maxvol26 blobs", lambda: ctx.maxvol(blobs, 26), 2),
-        ("edt blobs", lambda: ctx.edt(blobs), 5),
-        ("edt bernoulli .05", lambda: ctx.edt(bern[0.05]), 5),
-        ("edt sparse 1e-4", lambda: ctx.edt(sparse), 5),
-        ("edt lesion", lambda: ctx.edt(lesion), 5),
-        ("distlt r=5 blobs", lambda: ctx.distlt(5.0, blobs), 2),
-        ("distgeq r=2 blobs", lambda: ctx.distgeq(2.0, blobs), 2),
-        ("distlt r=12 blobs", lambda: ctx.distlt(12.0, blobs), 2),
-        ("percentiles brain f32 (sort)", lambda: ctx.percentiles(flair, brain), 9),
-        ("percentiles brain 16-bit upload (counting)", lambda: ctx.percentiles(flair16, brain), 9),
-        ("percentiles all f32 noise (sort)", lambda: ctx.percentiles(noise, ctx.tt(bg)), 9),
+        ("border", lambda: ctx.border(bg), 0.125),
+        ("near26", lambda: ctx.near(blobs, 26), 0.25),
+        ("near6", lambda: ctx.near(blobs, 6), 0.25),
+        ("interior26", lambda: ctx.interior(blobs, 26), 0.25),
+        ("through26 bg-mask", lambda: ctx.through(seeds, bg, 26), 0.375),
+        ("through26 blobs", lambda: ctx.through(seeds, blobs, 26), 0.375),
+        ("through6 blobs", lambda: ctx.through(seeds, blobs, 6), 0.375),
+        ("ccl26 bernoulli .05", lambda: ctx.components(bern[0.05], 26), 4.125),
+        ("ccl26 bernoulli .3", lambda: ctx.components(bern[0.3], 26), 4.125),
+        ("ccl26 bernoulli .6", lambda: ctx.components(bern[0.6], 26), 4.125),
+        ("ccl26 blobs", lambda: ctx.components(blobs, 26), 4.125),
+        ("maxvol26 blobs", lambda: ctx.maxvol(blobs, 26), 0.25),
+        ("edt blobs", lambda: ctx.edt(blobs), 4.125),
+        ("edt bernoulli .05", lambda: ctx.edt(bern[0.05]), 4.125),
+        ("edt sparse 1e-4", lambda: ctx.edt(sparse), 4.125),
+        ("edt lesion", lambda: ctx.edt(lesion), 4.125),
+        ("distlt r=5 blobs", lambda: ctx.distlt(5.0, blobs), 0.25),
+        ("distgeq r=2 blobs", lambda: ctx.distgeq(2.0, blobs), 0.25),
+        ("distlt r=12 blobs", lambda: ctx.distlt(12.0, blobs), 0.25),
+        ("percentiles brain f32 (sort)", lambda: ctx.percentiles(flair, brain), 8.125),
+        ("percentiles brain 16-bit upload (counting)", lambda: ctx.percentiles(flair16, brain), 6.125),
+        ("percentiles all f32 noise (sort)", lambda: ctx.percentiles(noise, ctx.tt(bg)), 8.125),
         ("minmax f32", lambda: ctx.minmax(flair), 4),
-        ("minmax 16-bit upload (code range)", lambda: ctx.minmax(flair16), 4),
+        ("minmax 16-bit upload (code range)", lambda: ctx.minmax(flair16), 0),
         ("xcorr rho5 k100 flair", lambda: ctx.cross_correlation(5.0, flair, flair, lesion, mn, mx, 100), 13),
         ("xcorr rho5 k100 16-bit upload", lambda: ctx.cross_correlation(5.0, flair16, flair16, lesion, mn16, mx16, 100), 13),
         ("xcorr rho5 k100 noise", lambda: ctx.cross_correlation(5.0, noise, noise, lesion, 0.0, 1.0, 100), 13),
         ("xcorr rho5 k100 zeros", lambda: ctx.cross_correlation(5.0, zeros, zeros, lesion, 0.0, 1.0, 100), 13),
         ("xcorr rho2 k100 flair", lambda: ctx.cross_correlation(2.0, flair, flair, lesion, mn, mx, 100), 13),
     ]
-    only = [s for s in args.only.split(",") if s]
+    only = [s.replace("_", " ") for s in args.only.split(",") if s]      # "_" stands for a blank: shell-friendly
     results = []
     for name, fn, bpv in ops:
         if only and not any(o in name for o in only):

@@ -21,22 +21,22 @@ run() {  # name, kernel regex, skip, script args...
   echo "$name rc=$?"
 }
 OPS="scripts/bench_ops.py --reps 1 --shape brats --batch 16"
-run xcorr xcorr_tma 2 $OPS --only "xcorr rho5 k100 flair"
-run ccl_merge ccl_merge 2 $OPS --only "through26 bg"
-run ccl_seed ccl_seed 2 $OPS --only "through26 bg"
-run ccl_select ccl_select 2 $OPS --only "through26 bg"
-run ball_or ball_or 2 $OPS --only "distlt r=5"
-run pack_bits pack_bits 2 $OPS --only "distlt r=5"
+run xcorr xcorr_tma 2 $OPS --only rho5_k100_flair
+run ccl_merge ccl_merge 2 $OPS --only through26_bg
+run ccl_seed ccl_seed 2 $OPS --only through26_bg
+run ccl_select ccl_select 2 $OPS --only through26_bg
+run ball_or ball_or 2 $OPS --only distlt_r=5
+run pack_bits pack_bits 2 $OPS --only distlt_r=5
 run morph_bits morph_bits 2 $OPS --only near26
-run boolean_program boolean_program 2 $OPS --only "and u8"
+run boolean_program boolean_program 2 $OPS --only and_u8
 run pointwise_threshold pointwise_program 2 $OPS --only threshold
-run pq_hist pq_hist 2 $OPS --only "percentiles brain 16-bit"
-run pq_apply pq_apply 2 $OPS --only "percentiles brain 16-bit"
-run xc_bin xc_bin 2 $OPS --only "xcorr rho5 k100 16-bit"
-run rs_scatter rs_scatter 8 $OPS --only "percentiles brain f32"
-run pc_rank pc_rank 2 $OPS --only "percentiles brain f32"
-run edt_window edt_window_kernel 1 scripts/bench_ops.py --reps 1 --shape 512 --batch 1 --only "edt blobs"
-run edt_env edt_env 1 scripts/bench_ops.py --reps 1 --shape 512 --batch 1 --only "edt sparse"
+run pq_hist pq_hist 2 $OPS --only percentiles_brain_16-bit
+run pq_apply pq_apply 2 $OPS --only percentiles_brain_16-bit
+run xc_bin xc_bin 2 $OPS --only rho5_k100_16-bit
+run rs_scatter rs_scatter 8 $OPS --only percentiles_brain_f32
+run pc_rank pc_rank 2 $OPS --only percentiles_brain_f32
+run edt_window edt_window_kernel 1 scripts/bench_ops.py --reps 1 --shape 512 --batch 1 --only edt_blobs
+run edt_env edt_env 1 scripts/bench_ops.py --reps 1 --shape 512 --batch 1 --only edt_sparse
 python scripts/bench_ops.py --shape brats --batch 16 --reps 5 --out gpurun_out/ops_brats_b16.json > /dev/null 2>&1; echo "ops rc=$?"
 python scripts/bench_ops.py --shape 512 --batch 1 --reps 5 --out gpurun_out/ops_512.json > /dev/null 2>&1; echo "ops512 rc=$?"
 python scripts/bench_texture.py --batch 4 --steps 5 --out gpurun_out/texture_b4.json > /dev/null 2>&1; echo "texture rc=$?"

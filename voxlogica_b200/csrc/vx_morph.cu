@@ -260,12 +260,11 @@ morph_bits_kernel(const unsigned* __restrict__ in, unsigned* __restrict__ out, i
     const bool has_l = w > 0, has_r = (w + 1) * 32 < nx;
     const bool up = y > 0, dn = y + 1 < ny;
     const unsigned long long plane = (unsigned long long)nx * ny;
-    // stream position of word w of row (y, z) of this volume
-    auto pos = [&](int z) { return ((unsigned long long)vol * nz + z) * plane + (unsigned long long)y * nx + (unsigned)w * 32u; };
-    auto load_plane = [&](int z, unsigned& A, unsigned& C) {
+    // stream position of word w of row (y, z0) of this volume; a plane further is + nx * ny
+    unsigned long long pz = ((unsigned long long)vol * nz + z0) * plane + (unsigned long long)y * nx + (unsigned)w * 32u;
+    auto load_plane = [&](bool exists, unsigned long long p, unsigned& A, unsigned& C) {
         A = C = 0u;
-        if (z < 0 || z >= nz) return;
-        const unsigned long long p = pos(z);
+        if (!exists) return;
         unsigned c, xs;
         load_row_bits<ERODE>(in, p, vmask, has_l, has_r, c, xs);
         A = xs;
@@ -281,17 +280,19 @@ morph_bits_kernel(const unsigned* __restrict__ in, unsigned* __restrict__ out, i
         if (FULL) C = A;
     };
     unsigned Am, Cm, A0, C0, A1, C1;
-    load_plane(z0 - 1, Am, Cm);
-    load_plane(z0, A0, C0);
+    load_plane(z0 > 0, pz - plane, Am, Cm);
+    load_plane(true, pz, A0, C0);
     // (fully unrolled: the row loads of the planes ahead are issued before the stores of the planes behind)
 #pragma unroll
-    for (int z = z0; z < z0 + kBitZL; z++) {
+    for (int i = 0; i < kBitZL; i++) {
+        const int z = z0 + i;
         if (z >= z1) break;
-        load_plane(z + 1, A1, C1);
+        load_plane(z + 1 < nz, pz + plane, A1, C1);
         unsigned acc = A0 | Cm | C1;
         if (ERODE) acc = ~acc;
-        flat_store32(out, pos(z), valid, acc & vmask, align16 != 0);
+        flat_store32(out, pz, valid, acc & vmask, align16 != 0);
         Cm = C0; A0 = A1; C0 = C1;
+        pz += plane;
     }
 }
 
