@@ -611,8 +611,8 @@ def run_ours(args):
                      "how": "CUDA events around every launch of 4 untimed single-stream steps run right after "
                             "the timed region (kernels_serial); the timed region carries no per-kernel events",
                      "traffic_unit": "bytes per launch (dram read+write, ncu --set full, profiles/traffic.json)",
-                     "note": "xcorr_kernel is bound by the shared-memory LSU pipe (ncu: 72% of peak shared "
-                             "wavefronts, 70% issue active, DRAM 0.9%), not by HBM (SURVEY.md 8d); the fraction "
+                     "note": "xcorr_kernel is bound by the shared-memory LSU pipe (ncu, profiles/r02_xcorr_ncu_full.json: "
+                             "76.9% of peak LSU wavefronts, 51% issue active, DRAM 2%), not by HBM (SURVEY.md 8d); the fraction "
                              "against HBM is reported as the contract requires" if name == "xcorr_kernel" else ""},
         "kernels": kernels,
         "kernels_serial": {"note": "one host thread / one stream, 4 untimed steps after the timed region: "
