@@ -40,21 +40,22 @@ WORKLOAD = ("BraTS-shape 240x240x155 GTV segmentation spec (Greta.pdf p.48: thre
             "filter via distlt/distgeq, percentiles, crossCorrelation rho=5 k=100)")
 # algorithmic HBM bytes per voxel per launch (SURVEY.md section 8d / DESIGN.md kernel table)
 ALG_BYTES = {
+    # a boolean voxel is one BIT on the device (1/8 byte), an f32 4 bytes, a 16-bit code 2
     "xcorr_kernel": 5.0,             # u8 bins in, f32 coefficient out (13 B/voxel for the whole operator)
-    "pointwise_program_kernel": None,  # depends on the program (5 for a threshold, 8/12 for arithmetic)
-    "boolean_program_kernel": None,    # 2 (not) or 3 (and/or) per instruction chain
-    "morph16_kernel": 2.0, "ball_or_kernel": 1.0 + 1.0 / 8,
-    "pack_bits_kernel": 1.0 + 1.0 / 8,   # u8 in, packed rows out (+ emax pre-dilated levels, emax/8 more)
-    # union-find kernels as launched by `through`: bits in/out are 1/8 B per voxel, labels are sparse
-    "ccl_init_kernel": 1.0 + 1.0 / 8, "ccl_merge_kernel": None, "ccl_flatten_kernel": None,
-    "ccl_select_kernel": 1.0 + 1.0 / 8, "ccl_seed_kernel": 1.0 + 1.0 / 8,
-    "xc_bin_kernel": 5.0, "xc_region_hist_kernel": 2.0, "pc_compact_kernel": 5.0,
+    "pointwise_program_kernel": None,  # depends on the program (4.125 for a threshold, 8/12 for arithmetic)
+    "boolean_program_kernel": None,    # (leaves + 1) / 8
+    "morph_bits_kernel": 0.25, "ball_or_kernel": 0.25,
+    "pack_bits_kernel": 0.25,        # bits in, packed rows out (+ emax pre-dilated levels, emax/8 more)
+    # union-find kernels as launched by `through`: bits in/out, node ids are 4 bytes per 32-voxel word
+    "ccl_nodes_kernel": 0.375, "ccl_merge_kernel": None, "ccl_flatten_kernel": None,
+    "ccl_select_kernel": 0.25, "ccl_seed_kernel": 0.25,
+    "xc_bin_kernel": 3.0, "xc_region_hist_kernel": 0.125, "pc_compact_kernel": 4.125,
     # the sort kernels move 8-byte pairs of the MASKED voxels only: no per-voxel figure
     "pc_rank_kernel": None, "rs_hist_kernel": None, "rs_scatter_kernel": None, "rs_rowscan_kernel": None,
-    # percentiles of a quantised (16-bit origin) image by counting: codes 2 + mask 1 in, f32 out
-    "pq_hist_kernel": 3.0, "pq_apply_kernel": 7.0,
-    "reduce_f32_kernel": 4.0, "reduce_volume_kernel": 1.0,
-    "border_kernel": 1.0, "edt_x_kernel": 5.0, "edt_axis_kernel_y": 8.0, "edt_axis_kernel_z": 8.0,
+    # percentiles of a quantised (16-bit origin) image by counting: codes 2 + mask bits in (f32 out when the array is made)
+    "pq_hist_kernel": 2.125, "pq_apply_kernel": 6.125,
+    "reduce_f32_kernel": 4.0, "reduce_volume_kernel": 0.125,
+    "border_kernel": 0.125, "edt_x_kernel": 4.125, "edt_axis_kernel_y": 8.0, "edt_axis_kernel_z": 8.0,
 }
 
 
@@ -384,6 +385,9 @@ def run_ours(args):
 
     numa = bind_to_gpu_numa(local)
     ctx = Context(local)
+    if args.independent_uploads:
+        from voxlogica_b200 import _abi as A
+        ctx.set_option(A.VX_OPT_ORDERED_UPLOADS, 0)
     B = args.batch
     shape4 = (B,) + BRATS
     from voxlogica_b200.synth import INT16_SLOPE
@@ -643,6 +647,8 @@ def main():
                          "one the GPU is waiting for arrives later (measured: e2e 1994 volumes/s with 2, 1716 with 3, "
                          "1622 with 4 or 6; the resident number is the same 2230-2270 for all)")
     ap.add_argument("--wc", action="store_true", help="write-combined pinned staging buffers for the uploads")
+    ap.add_argument("--independent-uploads", action="store_true",
+                    help="diagnosis: turn VX_OPT_ORDERED_UPLOADS off (uploads of different threads share the link)")
     ap.add_argument("--no-slab", action="store_true", help="skip the slab-decomposed volume record of N > 1 runs")
     ap.add_argument("--prof-timed", action="store_true",
                     help="diagnosis: per-kernel CUDA events inside the timed region (default: untimed pass only)")

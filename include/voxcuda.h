@@ -400,6 +400,11 @@ VX_API int32_t vx_prof_report(vx_ctx ctx, char* buf, size_t buf_bytes);
  * with images made by vx_upload_scaled (see there); 0 forces the general algorithms -- the results
  * are identical, the switch exists for tests and measurements. */
 #define VX_OPT_QUANTISED_PATHS 1
+/* VX_OPT_ORDERED_UPLOADS (default 1): uploads of 1 MiB and more issued by different caller threads are
+ * chained on the device (each copy waits for the one issued before it), so the host->device link
+ * serves them one at a time in arrival order at its full rate instead of sharing it between them:
+ * the caller that asked first has its data first.  0 = independent copies. */
+#define VX_OPT_ORDERED_UPLOADS 2
 VX_API int32_t vx_set_option(vx_ctx ctx, int32_t option, int64_t value);
 /* Write a buffer larger than L2 so the next kernel starts cold. */
 VX_API int32_t vx_flush_l2(vx_ctx ctx);

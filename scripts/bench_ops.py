@@ -92,7 +92,11 @@ def main():
         ("distgeq r=2 blobs", lambda: ctx.distgeq(2.0, blobs), 0.25),
         ("distlt r=12 blobs", lambda: ctx.distlt(12.0, blobs), 0.25),
         ("percentiles brain f32 (sort)", lambda: ctx.percentiles(flair, brain), 8.125),
-        ("percentiles brain 16-bit upload (counting)", lambda: ctx.percentiles(flair16, brain), 6.125),
+        # the counting path returns a DEFERRED image (tables only); device_ptr asks for the f32 array
+        ("percentiles brain 16-bit upload (counting)", lambda: ctx.device_ptr(ctx.percentiles(flair16, brain)), 6.125),
+        ("percentiles brain 16-bit upload (tables only)", lambda: ctx.percentiles(flair16, brain), 2.125),
+        ("percentiles then cmp 16-bit upload (deferred)", lambda: ctx.cmp_scalar(ctx.percentiles(flair16, brain), ">", 0.95), 2.125 + 2.25),
+        ("percentiles then cmp f32 (sort)", lambda: ctx.cmp_scalar(ctx.percentiles(flair, brain), ">", 0.95), 8.125 + 4.125),
         ("percentiles all f32 noise (sort)", lambda: ctx.percentiles(noise, ctx.tt(bg)), 8.125),
         ("minmax f32", lambda: ctx.minmax(flair), 4),
         ("minmax 16-bit upload (code range)", lambda: ctx.minmax(flair16), 0),

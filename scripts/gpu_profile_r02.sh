@@ -23,6 +23,7 @@ run() {  # name, kernel regex, skip, script args...
 OPS="scripts/bench_ops.py --reps 1 --shape brats --batch 16"
 run xcorr xcorr_tma 2 $OPS --only rho5_k100_flair
 run ccl_merge ccl_merge 2 $OPS --only through26_bg
+run ccl_nodes ccl_nodes 2 $OPS --only through26_bg
 run ccl_seed ccl_seed 2 $OPS --only through26_bg
 run ccl_select ccl_select 2 $OPS --only through26_bg
 run ball_or ball_or 2 $OPS --only distlt_r=5
@@ -30,6 +31,7 @@ run pack_bits pack_bits 2 $OPS --only distlt_r=5
 run morph_bits morph_bits 2 $OPS --only near26
 run boolean_program boolean_program 2 $OPS --only and_u8
 run pointwise_threshold pointwise_program 2 $OPS --only threshold
+run pointwise_deferred pointwise_program 2 $OPS --only percentiles_then_cmp_16-bit
 run pq_hist pq_hist 2 $OPS --only percentiles_brain_16-bit
 run pq_apply pq_apply 2 $OPS --only percentiles_brain_16-bit
 run xc_bin xc_bin 2 $OPS --only rho5_k100_16-bit

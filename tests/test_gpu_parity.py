@@ -349,6 +349,101 @@ def test_percentiles_of_quantised_images(ctx, oracle, dtype, slope, inter, lo, h
                               per_volume(oracle.percentiles, f, np.ones(shape, np.uint8), correction=0.0).view(np.uint32))
 
 
+@pytest.mark.parametrize("dtype", [np.int16, np.uint16])
+def test_pointwise_programs_read_quantised_leaves_as_codes(ctx, dtype):
+    """a pointwise program takes a 16-bit upload by its codes (2 bytes per voxel) and forms the same f32
+    values as the upload's conversion: comparisons, arithmetic and mixed programs, switch on and off"""
+    from voxlogica_b200 import _abi as A
+    rng = np.random.default_rng(95)
+    info = np.iinfo(dtype)
+    for shape in [(2, 5, 7, 13), (1, 3, 16, 24), (3, 1, 1, 3), (1, 2, 9, 8)]:
+        raw = rng.integers(info.min, info.max + 1, size=shape).astype(dtype)
+        other = rng.standard_normal(shape).astype(np.float32)
+        for slope, inter in [(1.0 / 4095.0, 0.0), (0.0007324442, -3.25), (-2.5, 1e-3)]:
+            f = raw.astype(np.float32) * np.float32(slope) + np.float32(inter)
+            img, Oth = ctx.upload_scaled(raw, slope, inter), ctx.upload(other)
+            for opt in (1, 0):
+                ctx.set_option(A.VX_OPT_QUANTISED_PATHS, opt)
+                try:
+                    thr = np.float32(np.median(f))
+                    assert np.array_equal(ctx.cmp_scalar(img, "<", float(thr)).numpy(), (f < thr).astype(np.uint8))
+                    got = ctx.arith_scalar(img, "*", 1.7).numpy()
+                    assert np.array_equal(got.view(np.uint32), (f * np.float32(1.7)).view(np.uint32))
+                    got = ctx.arith(img, "-", Oth).numpy()
+                    assert np.array_equal(got.view(np.uint32), (f - other).view(np.uint32))
+                    assert np.array_equal(ctx.cmp(Oth, ">=", img).numpy(), (other >= f).astype(np.uint8))
+                finally:
+                    ctx.set_option(A.VX_OPT_QUANTISED_PATHS, 1)
+
+
+def test_deferred_percentile_image(ctx, oracle):
+    """percentiles of a 16-bit upload returns an image whose f32 array is made on demand: pointwise
+    programs read codes + mask + table (before and after the array exists), every other consumer gets
+    the array; the operands may be released first; consumers on several threads at once"""
+    import threading
+    from voxlogica_b200 import _abi as A
+    rng = np.random.default_rng(91)
+    for shape, dtype in [((3, 5, 7, 13), np.int16), ((2, 8, 16, 32), np.uint16), ((1, 1, 1, 1), np.int16)]:
+        lo, hi = (-700, 900) if dtype == np.int16 else (0, 3000)
+        raw = rng.integers(lo, hi, size=shape).astype(dtype)
+        m = rnd_mask(shape, 0.6, 92)
+        f = raw.astype(np.float32) * np.float32(0.37) + np.float32(-1.5)
+        want = per_volume(oracle.percentiles, f, m, correction=0.5)
+        other = rng.random(shape).astype(np.float32)
+        img, M, Oth = ctx.upload_scaled(raw, 0.37, -1.5), ctx.upload(m), ctx.upload(other)
+        p = ctx.percentiles(img, M, 0.5)
+        del img, M                                            # the deferred form keeps what it reads alive
+        thr = ctx.cmp_scalar(p, ">", 0.4).numpy()             # reads the deferred form
+        assert np.array_equal(thr, (want > np.float32(0.4)).astype(np.uint8)), shape
+        s1 = ctx.arith(p, "+", Oth).numpy()                   # two f32 leaves, one deferred
+        assert np.array_equal(s1.view(np.uint32), (want + other).view(np.uint32)), shape
+        vol = ctx.volume(ctx.cmp_scalar(p, "<=", 0.25))
+        assert np.array_equal(vol, (want <= np.float32(0.25)).reshape(shape[0], -1).sum(1).astype(np.float64))
+        results, errors = {}, []
+
+        def work(i):
+            try:
+                if i % 2:
+                    results[i] = ctx.cmp_scalar(p, ">=", 0.1 * i).numpy()
+                else:
+                    results[i] = ctx.max(p)                   # a reduction: makes the array
+            except Exception as e:  # pragma: no cover
+                errors.append(e)
+
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert not errors
+        for i in range(8):
+            if i % 2:
+                assert np.array_equal(results[i], (want >= np.float32(0.1 * i)).astype(np.uint8)), (shape, i)
+            else:
+                assert np.array_equal(results[i], want.reshape(shape[0], -1).max(1).astype(np.float64)), (shape, i)
+        assert np.array_equal(p.numpy().view(np.uint32), want.view(np.uint32)), shape
+        thr2 = ctx.cmp_scalar(p, ">", 0.4).numpy()            # the array exists now
+        assert np.array_equal(thr2, thr)
+    assert ctx.mem_info()["live_handles"] >= 0
+
+
+def test_deferred_image_survives_raw_pointers_to_its_operands(ctx, oracle):
+    """vx_device_ptr freezes an image (the caller may write through the pointer): a deferred percentile
+    image made before keeps the codes and mask bits it reads; one made after takes the general path"""
+    rng = np.random.default_rng(93)
+    shape = (2, 6, 10, 32)
+    raw = rng.integers(0, 500, size=shape).astype(np.int16)
+    m = rnd_mask(shape, 0.5, 94)
+    f = raw.astype(np.float32)
+    want = per_volume(oracle.percentiles, f, m, correction=0.0)
+    img, M = ctx.upload_scaled(raw, 1.0, 0.0), ctx.upload(m)
+    p = ctx.percentiles(img, M)
+    assert ctx.device_ptr(M) != 0 and ctx.device_ptr(img) != 0      # both frozen now
+    assert np.array_equal(ctx.cmp_scalar(p, ">", 0.5).numpy(), (want > np.float32(0.5)).astype(np.uint8))
+    assert np.array_equal(p.numpy().view(np.uint32), want.view(np.uint32))
+    p2 = ctx.percentiles(img, M)                                    # frozen operands: sort path, array at once
+    assert np.array_equal(p2.numpy().view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(ctx.max(img), f.reshape(2, -1).max(1).astype(np.float64))
+
+
 def test_extrema_of_quantised_images(ctx):
     """min / max / minmax of an image uploaded as 16-bit codes come from the recorded code range of every
     volume (no pass over the image) and equal the reductions of the f32 image"""
@@ -500,6 +595,40 @@ def test_concurrent_callers(ctx, oracle):
     [t.join() for t in ts]
     assert not errors
     assert all(np.array_equal(r, want) for r in results.values())
+
+
+@pytest.mark.parametrize("ordered", [1, 0])
+def test_concurrent_large_uploads(ctx, ordered):
+    """Uploads above 1 MiB from several caller threads at once: chained on the device in arrival order
+    (VX_OPT_ORDERED_UPLOADS, the default) or independent -- either way every thread gets its own data."""
+    import threading
+    from voxlogica_b200 import _abi as A
+    shape = (2, 16, 160, 256)          # 1.3 M voxels: 2.6 MB as int16, 5.2 MB as f32
+    rng = np.random.default_rng(77)
+    raws = [rng.integers(-2000, 2000, size=shape).astype(np.int16) for _ in range(6)]
+    got, errors = {}, []
+
+    def work(i):
+        try:
+            for rep in range(3):
+                a = ctx.upload_scaled(raws[i], 0.5, 1.0)
+                b = ctx.upload(raws[i].astype(np.float32))
+                got[i] = (a.numpy(), b.numpy())
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    ctx.set_option(A.VX_OPT_ORDERED_UPLOADS, ordered)
+    try:
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+    finally:
+        ctx.set_option(A.VX_OPT_ORDERED_UPLOADS, 1)
+    assert not errors
+    for i in range(6):
+        f = raws[i].astype(np.float32)
+        assert np.array_equal(got[i][0], f * np.float32(0.5) + np.float32(1.0))
+        assert np.array_equal(got[i][1], f)
 
 
 # ------------------------------------------------------------------ transfers in the file's own width

@@ -57,6 +57,26 @@ def test_fsharp_binding_declares_every_export():
     assert set(decl) == {n for n, _ in protos}
 
 
+def test_abi_constants_match_the_header():
+    """every integer `#define VX_* n` of include/voxcuda.h that voxlogica_b200/_abi.py names has the same value
+    there (status codes, dtypes, options, opcodes of the fusion hook), and the options are all mirrored"""
+    from voxlogica_b200 import _abi
+    hdr = open(os.path.join(ROOT, "include", "voxcuda.h")).read()
+    defines = {k: int(v, 0) for k, v in re.findall(r"#define\s+(VXP?_[A-Z0-9_]+)\s+\(?(-?(?:0x)?[0-9a-fA-F]+)\)?\s*(?:/\*.*)?$", hdr, flags=re.M)}
+    enums = re.findall(r"\b(VXP?_[A-Z0-9_]+)\s*=\s*(-?\d+)", hdr)
+    defines.update({k: int(v) for k, v in enums})
+    assert len(defines) > 20
+    seen = 0
+    for name, value in defines.items():
+        if hasattr(_abi, name):
+            assert getattr(_abi, name) == value, name
+            seen += 1
+    assert seen > 20
+    for name in defines:
+        if name.startswith("VX_OPT_"):
+            assert hasattr(_abi, name), name
+
+
 def test_init_without_gpu_fails_loudly():
     """No CPU fallback: without a CUDA device vx_init reports VX_E_CUDA."""
     import ctypes as C

@@ -12,7 +12,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvoxcuda.so")
+# VOXCUDA_LIB: another build of the library (A/B measurements); the default is the in-tree one
+LIB_PATH = os.environ.get("VOXCUDA_LIB") or os.path.join(_HERE, "libvoxcuda.so")
 
 # status codes / enums (mirror include/voxcuda.h)
 VX_OK = 0
@@ -20,6 +21,7 @@ VX_E_INVALID_ARG, VX_E_SHAPE_MISMATCH, VX_E_DTYPE, VX_E_OOM = -1, -2, -3, -4
 VX_E_CUDA, VX_E_NCCL, VX_E_UNSUPPORTED = -5, -6, -7
 VX_U8, VX_F32, VX_U32 = 1, 2, 3
 VX_OPT_QUANTISED_PATHS = 1
+VX_OPT_ORDERED_UPLOADS = 2
 VX_I16, VX_U16 = 4, 5   # host-side voxel types of vx_upload_scaled
 VX_LT, VX_LE, VX_GT, VX_GE, VX_EQ, VX_NE = range(6)
 VX_ADD, VX_SUB, VX_MUL, VX_DIV, VX_RSUB, VX_RDIV, VX_MIN, VX_MAX = range(8)

@@ -156,82 +156,82 @@ __device__ __forceinline__ unsigned block_exscan(unsigned v, unsigned* total) {
     return base + incl - v;
 }
 
-// ---- 0. nodes ------------------------------------------------------------------------------
-// `img` is the image's flat bit form; `bits` receives the row-aligned words the later passes
-// index; blocksum[b] = segments of block b's words.
-__global__ void __launch_bounds__(kCclThreads)
-ccl_bits_kernel(const unsigned* __restrict__ img, unsigned* __restrict__ bits, unsigned* __restrict__ blocksum, Geo g) {
-    const WordPos p = word_pos(g);
-    unsigned m = 0;
-    if (p.ok) {
-        m = flat_row_word(img, p.row, p.w, g.nx);
-        bits[p.wid] = m;
-    }
-    unsigned total;
-    block_exscan(__popc(seg_starts(m)), &total);
-    if (threadIdx.x == 0) blocksum[blockIdx.x] = total;
+// ---- 0 + 1. nodes: bit words, node ids and first parents in ONE pass ------------------------------
+// `img` is the image's flat bit form; `bits` receives the row-aligned words the later passes index,
+// wbase[word] the id of the word's first node, P[id] the first parents: P[id] = id, except for a
+// segment at bit 0 that continues a run of the previous word of its row -- it hangs under that
+// word's last segment, the node just before this word's first.
+// Node ids are a prefix sum of the segment counts over all words.  Single pass with a decoupled
+// look-back (three launches -- count, scan of the block totals, init -- in round 1): a block takes a
+// ticket, scans its 256 counts, publishes its total, and its first warp walks back over the status
+// words of the blocks before it (32 at a time) until it meets one whose inclusive prefix is known.
+// Tickets, not blockIdx, order the blocks: whoever a block waits for is already running.
+// status word: state << 32 | value;  state 0 = nothing yet, 1 = block total, 2 = inclusive prefix.
+constexpr unsigned long long kStAgg = 1ull << 32, kStIncl = 2ull << 32;
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
-// exclusive scan of the block totals in place, the grand total behind them (one block; every thread
-// scans 16 consecutive entries per trip, so a batch of BraTS volumes takes two trips)
-constexpr int kScanPer = 16;
-__global__ void __launch_bounds__(1024)
-ccl_scan_kernel(unsigned* __restrict__ blocksum, unsigned n) {
-    __shared__ unsigned wsum[32];
-    __shared__ unsigned carry;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (unsigned i0 = 0; i0 < n; i0 += 1024 * kScanPer) {
-        const unsigned first = i0 + threadIdx.x * kScanPer;
-        unsigned v[kScanPer], mine = 0;
-#pragma unroll
-        for (int e = 0; e < kScanPer; e++) {
-            v[e] = first + e < n ? blocksum[first + e] : 0u;
-            mine += v[e];
-        }
-        unsigned incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) wsum[warp] = incl;
-        __syncthreads();
-        unsigned base = 0, tot = 0;
-        for (int w = 0; w < 32; w++) {
-            const unsigned t = wsum[w];
-            if (w < warp) base += t;
-            tot += t;
-        }
-        unsigned run = carry + base + incl - mine;
-#pragma unroll
-        for (int e = 0; e < kScanPer; e++) {
-            if (first + e < n) blocksum[first + e] = run;
-            run += v[e];
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) carry += tot;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) blocksum[n] = carry;
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// ---- 1. init: node ids and first parents ------------------------------------------------------
+// status: [nblocks] status words (zeroed), then the ticket counter (zeroed), then the node total (output)
 __global__ void __launch_bounds__(kCclThreads)
-ccl_init_kernel(const unsigned* __restrict__ bits, const unsigned* __restrict__ blocksum, unsigned* __restrict__ wbase,
-                unsigned* __restrict__ P, Geo g) {
-    const WordPos p = word_pos(g);
-    const unsigned m = p.ok ? __ldg(bits + p.wid) : 0u;
+ccl_nodes_kernel(const unsigned* __restrict__ img, unsigned* __restrict__ bits, unsigned* __restrict__ wbase,
+                 unsigned* __restrict__ P, unsigned long long* __restrict__ status, Geo g) {
+    __shared__ unsigned s_bid, s_prefix;
+    unsigned* ticket = reinterpret_cast<unsigned*>(status + g.nblocks);
+    unsigned* ntotal = reinterpret_cast<unsigned*>(status + g.nblocks + 1);
+    if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned bid = s_bid;
+    const unsigned long long wid = (unsigned long long)bid * kCclThreads + threadIdx.x;
+    const bool ok = wid < g.nwords;
+    const unsigned long long row = (ok ? wid : 0) / g.nwx;
+    const int w = (int)((ok ? wid : 0) % g.nwx);
+    const unsigned m = ok ? flat_row_word(img, row, w, g.nx) : 0u;
     unsigned prev_m = __shfl_up_sync(0xffffffffu, m, 1);
-    if ((threadIdx.x & 31) == 0) prev_m = (p.ok && p.wid > 0) ? __ldg(bits + p.wid - 1) : 0u;
+    if ((threadIdx.x & 31) == 0) prev_m = (ok && w > 0) ? flat_row_word(img, row, w - 1, g.nx) : 0u;
     unsigned total;
-    const unsigned base = __ldg(blocksum + blockIdx.x) + block_exscan(__popc(seg_starts(m)), &total);
-    if (!p.ok) return;
-    wbase[p.wid] = base;
+    const unsigned excl = block_exscan(__popc(seg_starts(m)), &total);
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        unsigned prefix = 0;
+        if (bid > 0) {
+            if (lane == 0) st_status(status + bid, kStAgg | total);
+            long long look = (long long)bid - 1;
+            while (true) {
+                const long long idx = look - lane;
+                unsigned long long v = idx >= 0 ? ld_status(status + idx) : kStIncl;
+                while (__any_sync(0xffffffffu, (v >> 32) == 0ull)) {
+                    if ((v >> 32) == 0ull) v = ld_status(status + idx);
+                }
+                const unsigned incl = __ballot_sync(0xffffffffu, (v >> 32) == 2ull);
+                // lanes up to the first one that knows its inclusive prefix contribute
+                const int last = incl ? __ffs(incl) - 1 : 31;
+                unsigned part = lane <= last ? (unsigned)v : 0u;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                prefix += part;
+                if (incl) break;
+                look -= 32;
+            }
+        }
+        if (lane == 0) {
+            st_status(status + bid, kStIncl | (unsigned long long)(prefix + total));
+            s_prefix = prefix;
+            if (bid == g.nblocks - 1) *ntotal = prefix + total;
+        }
+    }
+    __syncthreads();
+    if (!ok) return;
+    const unsigned base = s_prefix + excl;
+    bits[wid] = m;
+    wbase[wid] = base;
     unsigned starts = seg_starts(m);
-    // a segment at bit 0 that continues a run of the previous word of the same row hangs under that
-    // word's last segment, which is the node just before this word's first
-    const bool cont = (m & 1u) && p.w > 0 && (prev_m >> 31);
+    const bool cont = (m & 1u) && w > 0 && (prev_m >> 31);
     unsigned id = base;
     while (starts) {
         const int j = __ffs(starts) - 1;
@@ -608,11 +608,12 @@ static int new_bits_out(OpGuard& og, int nx, int ny, int nz, int nb, const float
 // the parents (one per node; capacity = the most segments the rows can hold) and the scan of the
 // block totals, whose last entry is the number of nodes.
 struct CclBufs {
-    unsigned *bits = nullptr, *wbase = nullptr, *P = nullptr, *blocksum = nullptr;
+    unsigned *bits = nullptr, *wbase = nullptr, *P = nullptr;
+    unsigned long long* status = nullptr;   // look-back status words, the ticket, the node total
     size_t cap = 0;   // nodes P can hold
     Geo g;
     unsigned grid = 0;
-    const unsigned* ntotal() const { return blocksum + g.nblocks; }
+    const unsigned* ntotal() const { return reinterpret_cast<const unsigned*>(status + g.nblocks + 1); }
 };
 constexpr int kNodeGrid = kNumSMs * 8;   // blocks of the one-thread-per-node kernels (grid stride)
 
@@ -620,7 +621,7 @@ static void ccl_free(Ctx* c, int s, CclBufs& b) {
     if (b.bits) scratch_free(c, s, b.bits);
     if (b.wbase) scratch_free(c, s, b.wbase);
     if (b.P) scratch_free(c, s, b.P);
-    if (b.blocksum) scratch_free(c, s, b.blocksum);
+    if (b.status) scratch_free(c, s, b.status);
     b = CclBufs();
 }
 
@@ -638,24 +639,18 @@ static int ccl_label(OpGuard& og, const Image* B, const unsigned* Bbits, bool fu
     b.cap = (size_t)cap;
     int rc = scratch_alloc(og.c, og.s, sizeof(unsigned) * g.nwords, (void**)&b.bits);
     if (rc == VX_OK) rc = scratch_alloc(og.c, og.s, sizeof(unsigned) * g.nwords, (void**)&b.wbase);
-    if (rc == VX_OK) rc = scratch_alloc(og.c, og.s, sizeof(unsigned) * ((size_t)g.nblocks + 1), (void**)&b.blocksum);
+    if (rc == VX_OK) rc = scratch_alloc(og.c, og.s, sizeof(unsigned long long) * ((size_t)g.nblocks + 2), (void**)&b.status);
     if (rc == VX_OK) rc = scratch_alloc(og.c, og.s, sizeof(unsigned) * b.cap, (void**)&b.P);
     auto step = [&](const char* name) { if (rc == VX_OK) rc = check_launch(name); };
     if (rc == VX_OK) {
-        VX_LAUNCH(og.c, og.s, "ccl_bits_kernel");
-        ccl_bits_kernel<<<b.grid, kCclThreads, 0, og.st>>>(Bbits, b.bits, b.blocksum, g);
+        cudaError_t ce = cudaMemsetAsync(b.status, 0, sizeof(unsigned long long) * ((size_t)g.nblocks + 2), og.st);
+        if (ce != cudaSuccess) rc = fail(VX_E_CUDA, "memset: %s", cudaGetErrorString(ce));
     }
-    step("ccl_bits_kernel");
     if (rc == VX_OK) {
-        VX_LAUNCH(og.c, og.s, "ccl_scan_kernel");
-        ccl_scan_kernel<<<1, 1024, 0, og.st>>>(b.blocksum, g.nblocks);
+        VX_LAUNCH(og.c, og.s, "ccl_nodes_kernel");
+        ccl_nodes_kernel<<<b.grid, kCclThreads, 0, og.st>>>(Bbits, b.bits, b.wbase, b.P, b.status, g);
     }
-    step("ccl_scan_kernel");
-    if (rc == VX_OK) {
-        VX_LAUNCH(og.c, og.s, "ccl_init_kernel");
-        ccl_init_kernel<<<b.grid, kCclThreads, 0, og.st>>>(b.bits, b.blocksum, b.wbase, b.P, g);
-    }
-    step("ccl_init_kernel");
+    step("ccl_nodes_kernel");
     if (rc == VX_OK) {
         VX_LAUNCH(og.c, og.s, "ccl_merge_kernel");
         if (full) ccl_merge_kernel<true><<<b.grid, kCclThreads, 0, og.st>>>(b.P, b.bits, b.wbase, g);

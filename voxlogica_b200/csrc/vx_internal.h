@@ -58,6 +58,22 @@ struct Image {
     int q_dtype = 0;              // VX_I16 / VX_U16, 0 = no tag
     bool q_increasing = true;
     float q_slope = 1.f, q_inter = 0.f;
+    // Deferred f32 form (set by vx_percentiles on a quantised operand): the voxels are
+    //     v = mask ? table[volume][u(q)] : 0
+    // for the 16-bit codes q of `src` (u = the order-preserving code), the bit form of `mask` and a
+    // per-volume table owned by this image.  `d` stays nullptr until somebody needs the f32 array
+    // (ensure_f32, through OpGuard::input); the pointwise programs read the three parts directly,
+    // 2.125 bytes per voxel instead of writing 4 and reading them back.  src and mask are held by a
+    // reference each until this image dies.
+    struct Lazy {
+        Image* src = nullptr;
+        Image* mask = nullptr;
+        float* table = nullptr;   // [nb][65536]
+    };
+    Lazy* lazy = nullptr;
+    std::atomic<int> part_users{0};   // deferred images that read this image's q16 / bits: those stay allocated
+    bool q_frozen = false;            // the f32 array was handed out as a raw pointer: the codes no longer describe it
+    bool has_codes() const { return q16 != nullptr && !q_frozen; }
     const int* q_range() const { return reinterpret_cast<const int*>(static_cast<const char*>(q16) + ((count() + 7) / 8 * 8) * 2); }
     size_t bit_words() const { return (count() + 31) / 32; }
     size_t nvox() const { return (size_t)nx * ny * nz; }       // per volume
@@ -103,7 +119,17 @@ struct Ctx {
     // whatever error the dead context produces next.
     std::atomic<int> fault{0};
     char fault_msg[256] = "";
+    // Host->device link: large uploads issued by different caller threads (streams) are chained, each
+    // copy waiting for the one issued before it, so the PCIe link serves them one at a time in
+    // arrival order instead of time-slicing -- the step whose upload was asked for first gets
+    // its data first (VX_OPT_ORDERED_UPLOADS, on by default).
+    std::mutex h2d_mu;
+    cudaEvent_t h2d_ev[8] = {};
+    int h2d_next = 0, h2d_tail = -1;
+    std::atomic<int> ordered_uploads{1};
 };
+// cudaMemcpyAsync host->device on stream st, chained behind the previous large upload of the context
+cudaError_t h2d_copy(Ctx* c, void* dst, const void* src, size_t bytes, cudaStream_t st);
 // Classify a CUDA error; sticky ones are latched on the context of the calling thread's current call.
 bool sticky_cuda_error(cudaError_t e);
 void latch_fault(cudaError_t e, const char* what);
@@ -152,6 +178,12 @@ int new_image(Ctx* c, int dtype, int nx, int ny, int nz, int nb, const float* sp
 int new_bits_image(Ctx* c, int nx, int ny, int nz, int nb, const float* sp, Image** out);
 // Make the missing representation of a boolean image on stream index s (no-op when present).
 int ensure_u8(Ctx* c, Image* im, int s);
+// Make the f32 array of an image that only has its deferred form (no-op otherwise).
+int ensure_f32(Ctx* c, Image* im, int s);
+// An f32 image without its array (Image::lazy is filled in by the caller).
+int new_deferred_image(Ctx* c, int nx, int ny, int nz, int nb, const float* sp, Image** out);
+// vx_percentiles.cu: out = mask ? table[volume][u(q)] : 0 over the whole batch, on stream index s
+int pq_apply_launch(Ctx* c, int s, const Image* src, const unsigned* maskbits, const float* table, float* out);
 int ensure_bits(Ctx* c, Image* im, int s);
 inline size_t bits_alloc_bytes(size_t voxels) { return ((voxels + 127) / 128) * 16 + 64; }   // whole uint4 groups + slack
 // Make `img` safe to read on stream index `s` (waits for its producer if needed).
@@ -229,6 +261,10 @@ struct OpGuard {
     // A boolean input comes with its byte form (`d`) materialised: kernels written for bytes need
     // nothing else.  input_bits() is for kernels that read the bit form: no bytes are made.
     int input(vx_img h, Image** out, int want_dtype /*0 = any*/);
+    // an f32 operand whose deferred form (Image::lazy) is acceptable: no array is made; the parts
+    // the deferred form refers to are pinned and ordered like operands of their own
+    // (*arr = the f32 array when the image has one, nullptr = read the parts)
+    int input_f32_deferred(vx_img h, Image** out, const void** arr);
     int input_bits(vx_img h, Image** out, const unsigned** bits);
     int input_meta(vx_img h, Image** out);   // pinned for its metadata only: no stream ordering, no conversion
     int finish(Image* out_img, vx_img* out);  // publish output + mark inputs used

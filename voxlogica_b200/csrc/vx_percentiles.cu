@@ -682,36 +682,54 @@ __global__ void pc_set_plan_kernel(unsigned* __restrict__ count, unsigned* __res
 
 using namespace vx;
 
-// percentiles of a quantised image (the tag of vx_internal.h) by counting
+static void pq_smem_attrs() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        cudaFuncSetAttribute(pq_hist_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPqWin * 4);
+        cudaFuncSetAttribute(pq_hist_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPqWin * 4);
+        cudaFuncSetAttribute(pq_apply_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPqWin * 4);
+        cudaFuncSetAttribute(pq_apply_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPqWin * 4);
+    });
+}
+// grid: a few blocks per SM in total, every block owns one volume's histogram window
+static int pq_blocks_per_volume(size_t nvox, int nb) {
+    return std::max(1, std::min((int)((nvox / 16 + 255) / 256), (kNumSMs * 6 + nb - 1) / nb));
+}
+
+// the f32 array of a deferred percentile image (Image::lazy): out = mask ? table[volume][u(q)] : 0
+int vx::pq_apply_launch(Ctx* c, int s, const Image* src, const unsigned* maskbits, const float* table, float* out) {
+    pq_smem_attrs();
+    const size_t nvox = src->nvox();
+    const int nb = src->nb;
+    const dim3 grid(pq_blocks_per_volume(nvox, nb), nb);
+    { VX_LAUNCH(c, s, "pq_apply_kernel");
+      if (src->q_dtype == VX_I16)
+          pq_apply_kernel<short><<<grid, 256, kPqWin * 4, c->streams[s]>>>((const short*)src->q16, maskbits, nvox, src->q_range(), table, out);
+      else
+          pq_apply_kernel<unsigned short><<<grid, 256, kPqWin * 4, c->streams[s]>>>((const unsigned short*)src->q16, maskbits, nvox,
+                                                                                    src->q_range(), table, out); }
+    return check_launch("pq_apply_kernel");
+}
+
+// percentiles of a quantised image (the tag of vx_internal.h) by counting: the table of every volume
 template <typename T>
-static int percentiles_quantised(OpGuard& og, Image* A, const unsigned* Mbits, double correction, Image* O) {
+static int percentiles_table(OpGuard& og, Image* A, const unsigned* Mbits, double correction, float* table) {
     const size_t nvox = A->nvox();
     const int nb = A->nb;
     Scratch sc(og.c, og.s);
     unsigned* hist = nullptr;
-    float* table = nullptr;
     VX_TRY(sc.alloc(sizeof(unsigned) * (size_t)nb * kPqCodes, &hist));
-    VX_TRY(sc.alloc(sizeof(float) * (size_t)nb * kPqCodes, &table));
     VX_CUDA(cudaMemsetAsync(hist, 0, sizeof(unsigned) * (size_t)nb * kPqCodes, og.st));
-    static std::once_flag once;
-    std::call_once(once, [] {
-        cudaFuncSetAttribute(pq_hist_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPqWin * 4);
-        cudaFuncSetAttribute(pq_apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPqWin * 4);
-    });
+    pq_smem_attrs();
     const T* q = static_cast<const T*>(A->q16);
     const int* qrange = A->q_range();
-    // grid: a few blocks per SM in total, every block owns one volume's histogram window
-    const int per_vol = std::max(1, std::min((int)((nvox / 16 + 255) / 256), (kNumSMs * 6 + nb - 1) / nb));
+    const int per_vol = pq_blocks_per_volume(nvox, nb);
     { VX_LAUNCH(og.c, og.s, "pq_hist_kernel");
       pq_hist_kernel<T><<<dim3(per_vol, nb), 256, kPqWin * 4, og.st>>>(q, Mbits, nvox, qrange, hist); }
     VX_TRY(check_launch("pq_hist_kernel"));
     { VX_LAUNCH(og.c, og.s, "pq_table_kernel");
       pq_table_kernel<<<nb, 1024, 0, og.st>>>(hist, qrange, table, correction, A->q_increasing ? 1 : 0); }
-    VX_TRY(check_launch("pq_table_kernel"));
-    { VX_LAUNCH(og.c, og.s, "pq_apply_kernel");
-      pq_apply_kernel<T><<<dim3(per_vol, nb), 256, kPqWin * 4, og.st>>>(q, Mbits, nvox, qrange, table, (float*)O->d); }
-    VX_TRY(check_launch("pq_apply_kernel"));
-    return VX_OK;
+    return check_launch("pq_table_kernel");
 }
 
 extern "C" int32_t vx_percentiles(vx_ctx ctx, vx_img a, vx_img mask, double correction, vx_img* out) {
@@ -720,15 +738,34 @@ extern "C" int32_t vx_percentiles(vx_ctx ctx, vx_img a, vx_img mask, double corr
     VX_TRY(og.begin(ctx));
     Image *A = nullptr, *M = nullptr;
     VX_TRY(og.input(a, &A, VX_F32));
-    if (A->q16 != nullptr && og.c->quantised_paths.load()) {   // at most 65536 distinct values: count, do not sort
+    if (A->has_codes() && og.c->quantised_paths.load()) {   // at most 65536 distinct values: count, do not sort
         const unsigned* Mbits = nullptr;
         VX_TRY(og.input_bits(mask, &M, &Mbits));
         VX_TRY(same_shape(A, M));
+        // The result is DEFERRED (Image::lazy): the tables are made now, the f32 array only if
+        // somebody asks for it.  The pointwise programs (thresholds of the GTV spec) read codes, mask
+        // and table instead.  A mask whose bytes the caller can rewrite (vx_device_ptr) has no
+        // lasting bit form: the array is made at once from this call's private copy of the bits.
+        float* table = nullptr;
+        VX_TRY(dev_alloc(og.c, og.s, sizeof(float) * (size_t)A->nb * kPqCodes, (void**)&table));
+        int rc = A->q_dtype == VX_I16 ? percentiles_table<short>(og, A, Mbits, correction, table)
+                                      : percentiles_table<unsigned short>(og, A, Mbits, correction, table);
         Image* O = nullptr;
-        VX_TRY(new_image(og.c, VX_F32, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
-        const int rc = A->q_dtype == VX_I16 ? percentiles_quantised<short>(og, A, Mbits, correction, O)
-                                            : percentiles_quantised<unsigned short>(og, A, Mbits, correction, O);
-        if (rc != VX_OK) { drop(O); return rc; }
+        const bool defer = Mbits == M->bits;
+        if (rc == VX_OK)
+            rc = defer ? new_deferred_image(og.c, A->nx, A->ny, A->nz, A->nb, A->sp, &O)
+                       : new_image(og.c, VX_F32, A->nx, A->ny, A->nz, A->nb, A->sp, &O);
+        if (rc != VX_OK) { dev_free(og.c, og.s, table); return rc; }
+        if (defer) {
+            O->lazy = new Image::Lazy();
+            O->lazy->src = A; A->rc.fetch_add(1); A->part_users.fetch_add(1);
+            O->lazy->mask = M; M->rc.fetch_add(1); M->part_users.fetch_add(1);
+            O->lazy->table = table;   // freed with the image, on its home stream (= this one)
+        } else {
+            rc = pq_apply_launch(og.c, og.s, A, Mbits, table, (float*)O->d);
+            dev_free(og.c, og.s, table);
+            if (rc != VX_OK) { drop(O); return rc; }
+        }
         return og.finish(O, out);
     }
     VX_TRY(og.input(mask, &M, VX_U8));

@@ -32,6 +32,15 @@ struct DevProg {
     unsigned long long count;    // voxels of the whole batch
     unsigned long long ngroups;  // 16-voxel groups over the whole batch (128-voxel groups in the bit kernel)
     const void* leaf[VXP_MAX_LEAVES];
+    // a DEFERRED f32 leaf (Image::lazy): leaf = the 16-bit codes, leaf_tab = the per-volume tables
+    // (nullptr for an ordinary leaf), leaf_mask = the mask's bit stream, leaf_flip = 0x8000 for int16 codes
+    const float* leaf_tab[VXP_MAX_LEAVES];
+    const void* leaf_mask[VXP_MAX_LEAVES];
+    unsigned leaf_flip[VXP_MAX_LEAVES];
+    // an f32 leaf read as the 16-bit codes of a quantised image (Image::q16): leaf = the codes,
+    // v = fl(fl((float)q * slope) + inter) as vx_upload_scaled formed it; leaf_codes = 1 (int16) / 2 (uint16)
+    int leaf_codes[VXP_MAX_LEAVES];
+    float leaf_slope[VXP_MAX_LEAVES], leaf_inter[VXP_MAX_LEAVES];
     void* out;
     const float* bscal;  // [n_scalars][nb]
     DevOp ops[VXP_MAX_OPS];
@@ -61,7 +70,55 @@ __device__ __forceinline__ uint4 ld_b(const DevProg& P, uint8_t kind, uint8_t id
 __device__ __forceinline__ F16 ld_f(const DevProg& P, uint8_t kind, uint8_t idx, size_t g,
                                     const float4* sf) {
     F16 r;
-    if (kind == K_LEAF) {
+    if (kind == K_LEAF && P.leaf_tab[idx] != nullptr) {
+        // deferred leaf: v = mask ? table[volume][u(code)] : 0 -- 2.125 bytes per voxel from HBM, the
+        // look-ups hit L1 (a volume's codes span a few thousand table entries)
+        const unsigned m = __ldg(reinterpret_cast<const unsigned short*>(P.leaf_mask[idx]) + g);
+        float t[kGroup];
+#pragma unroll
+        for (int e = 0; e < kGroup; e++) t[e] = 0.f;
+        if (m != 0u) {
+            const uint4* qp = reinterpret_cast<const uint4*>(P.leaf[idx]) + g * 2;
+            // (the code array ends with the batch's last 8-voxel group: a half without mask bits is not read)
+            const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+            const uint4 a = (m & 0xffu) ? __ldg(qp) : z4, b = (m >> 8) ? __ldg(qp + 1) : z4;
+            const unsigned qw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            const size_t first = g * kGroup;
+            // volume of the group's first voxel (a 32-bit division whenever the batch allows it)
+            const unsigned v0 = P.count <= 0xffffffffull ? (unsigned)first / (unsigned)P.nvox : (unsigned)(first / P.nvox);
+            const bool one_volume = first - (size_t)v0 * P.nvox + (kGroup - 1) < P.nvox;
+            const unsigned flip = P.leaf_flip[idx];
+            const float* tab = P.leaf_tab[idx];
+#pragma unroll
+            for (int e = 0; e < kGroup; e++) {
+                if (!((m >> e) & 1u)) continue;
+                const unsigned v = one_volume ? v0 : (unsigned)((first + e) / P.nvox);
+                const unsigned u = ((qw[e >> 1] >> (16 * (e & 1))) & 0xffffu) ^ flip;
+                t[e] = __ldg(tab + (size_t)v * 65536u + u);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) r.v[q] = make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]);
+    } else if (kind == K_LEAF && P.leaf_codes[idx] != 0) {
+        // quantised leaf: 2 bytes per voxel instead of 4, the same two roundings as the upload's conversion
+        const uint4* qp = reinterpret_cast<const uint4*>(P.leaf[idx]) + g * 2;
+        const size_t first = g * kGroup;
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        // (the code array ends with the batch's last 8-voxel group)
+        const uint4 a = __ldg(qp), b = first + 8 < P.count ? __ldg(qp + 1) : z4;
+        const unsigned qw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        const bool sgn = P.leaf_codes[idx] == 1;
+        const float slope = P.leaf_slope[idx], inter = P.leaf_inter[idx];
+        float t[kGroup];
+#pragma unroll
+        for (int e = 0; e < kGroup; e++) {
+            const unsigned h = (qw[e >> 1] >> (16 * (e & 1))) & 0xffffu;
+            const float q = sgn ? (float)(short)h : (float)h;
+            t[e] = __fadd_rn(__fmul_rn(q, slope), inter);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) r.v[q] = make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]);
+    } else if (kind == K_LEAF) {
         const float4* p = reinterpret_cast<const float4*>(P.leaf[idx]) + g * 4;
 #pragma unroll
         for (int q = 0; q < 4; q++) r.v[q] = __ldg(p + q);
@@ -393,6 +450,10 @@ int run_pointwise(vx_ctx ctx, const vx_op* prog, int n_ops, const vx_img* leaves
     VX_TRY(g.begin(ctx));
     Image* L[VXP_MAX_LEAVES] = {};
     const void* leaf_ptr[VXP_MAX_LEAVES] = {};
+    const float* leaf_tab[VXP_MAX_LEAVES] = {};
+    const void* leaf_mask[VXP_MAX_LEAVES] = {};
+    unsigned leaf_flip[VXP_MAX_LEAVES] = {};
+    int leaf_codes[VXP_MAX_LEAVES] = {};
     for (int i = 0; i < n_leaves; i++) {
         int dt = 0;
         VX_REQUIRE(vx_info(leaves[i], &dt, nullptr, nullptr, nullptr, nullptr, nullptr) == VX_OK, VX_E_INVALID_ARG,
@@ -404,8 +465,17 @@ int run_pointwise(vx_ctx ctx, const vx_op* prog, int n_ops, const vx_img* leaves
             VX_TRY(g.input_bits(leaves[i], &L[i], &b));
             leaf_ptr[i] = b;
         } else {
-            VX_TRY(g.input(leaves[i], &L[i], VX_F32));
-            leaf_ptr[i] = L[i]->d;
+            VX_TRY(g.input_f32_deferred(leaves[i], &L[i], &leaf_ptr[i]));
+            if (leaf_ptr[i] == nullptr) {   // no f32 array yet: read the deferred form
+                const Image::Lazy* z = L[i]->lazy;
+                leaf_ptr[i] = z->src->q16;
+                leaf_tab[i] = z->table;
+                leaf_mask[i] = z->mask->bits;
+                leaf_flip[i] = z->src->q_dtype == VX_I16 ? 0x8000u : 0u;
+            } else if (L[i]->has_codes() && g.c->quantised_paths.load()) {
+                leaf_ptr[i] = L[i]->q16;   // half the bytes of the f32 array, the same values
+                leaf_codes[i] = L[i]->q_dtype == VX_I16 ? 1 : 2;
+            }
         }
         if (i > 0) VX_TRY(same_shape(L[0], L[i]));
     }
@@ -540,7 +610,14 @@ int run_pointwise(vx_ctx ctx, const vx_op* prog, int n_ops, const vx_img* leaves
     P.nvox = shape->nvox();
     P.count = shape->count();
     P.ngroups = (shape->count() + kGroup - 1) / kGroup;
-    for (int i = 0; i < n_leaves; i++) P.leaf[i] = leaf_ptr[i];
+    for (int i = 0; i < n_leaves; i++) {
+        P.leaf[i] = leaf_ptr[i];
+        P.leaf_tab[i] = leaf_tab[i];
+        P.leaf_mask[i] = leaf_mask[i];
+        P.leaf_flip[i] = leaf_flip[i];
+        P.leaf_codes[i] = leaf_codes[i];
+        if (leaf_codes[i]) { P.leaf_slope[i] = L[i]->q_slope; P.leaf_inter[i] = L[i]->q_inter; }
+    }
     P.out = out_type == T_B ? (void*)o->bits : o->d;
     float* d_scal = nullptr;
     if (n_scalars > 0 && batch_scalars) {

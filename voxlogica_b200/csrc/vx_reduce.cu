@@ -182,7 +182,7 @@ __global__ void quant_extrema_kernel(const int* __restrict__ qrange, int nb, int
 // memory `d_out` (scratch owned by the caller)
 int reduce_device(OpGuard& g, int kind, const Image* a, const Image* mask, double* d_out, const unsigned* a_bits) {
     const size_t nvox = a->nvox();
-    if (a->q16 != nullptr && mask == nullptr && g.c->quantised_paths.load() &&
+    if (a->has_codes() && mask == nullptr && g.c->quantised_paths.load() &&
         (kind == RED_MIN || kind == RED_MAX || kind == RED_MINMAX)) {
         const int want = kind == RED_MIN ? 1 : kind == RED_MAX ? 2 : 3;
         { VX_LAUNCH(g.c, g.s, "quant_extrema_kernel");

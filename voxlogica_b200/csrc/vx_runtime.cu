@@ -286,7 +286,8 @@ static size_t dtype_size(int dtype) {
     return 0;
 }
 
-static int new_image_impl(Ctx* c, int dtype, int nx, int ny, int nz, int nb, const float* sp, bool as_bits, Image** out) {
+static int new_image_impl(Ctx* c, int dtype, int nx, int ny, int nz, int nb, const float* sp, bool as_bits, Image** out,
+                          bool deferred = false) {
     size_t es = dtype_size(dtype);
     VX_REQUIRE(es != 0, VX_E_DTYPE, "unknown dtype %d", dtype);
     VX_REQUIRE(nx > 0 && ny > 0 && nz > 0 && nb > 0, VX_E_INVALID_ARG,
@@ -305,13 +306,14 @@ static int new_image_impl(Ctx* c, int dtype, int nx, int ny, int nz, int nb, con
     // kernels read and write whole 16-element groups: pad the allocation so that the
     // last group of the batch stays inside it (the padding is never data)
     size_t alloc = ((im->count() + 15) / 16 * 16) * es + 64;
-    int arc = as_bits ? dev_alloc(c, s, bits_alloc_bytes(im->count()), (void**)&im->bits) : dev_alloc(c, s, alloc, &im->d);
+    int arc = deferred ? VX_OK
+              : as_bits ? dev_alloc(c, s, bits_alloc_bytes(im->count()), (void**)&im->bits) : dev_alloc(c, s, alloc, &im->d);
     if (arc != VX_OK) {
         delete im;
         return arc;
     }
     im->ready = get_event(c);
-    c->live_bytes += as_bits ? im->bit_words() * 4 : im->bytes;
+    c->live_bytes += deferred ? 0 : as_bits ? im->bit_words() * 4 : im->bytes;
     c->live_handles += 1;
     register_image(im);
     *out = im;
@@ -323,10 +325,13 @@ int new_image(Ctx* c, int dtype, int nx, int ny, int nz, int nb, const float* sp
 int new_bits_image(Ctx* c, int nx, int ny, int nz, int nb, const float* sp, Image** out) {
     return new_image_impl(c, VX_U8, nx, ny, nz, nb, sp, true, out);
 }
+int new_deferred_image(Ctx* c, int nx, int ny, int nz, int nb, const float* sp, Image** out) {
+    return new_image_impl(c, VX_F32, nx, ny, nz, nb, sp, false, out, true);
+}
 
 int use_input(Ctx* c, Image* img, int s) {
     if (img->home != s) VX_CUDA(cudaStreamWaitEvent(c->streams[s], img->ready, 0));
-    if (img->dtype == VX_U8) {   // a representation added later by another stream
+    if (img->dtype == VX_U8 || img->lazy) {   // a representation added later by another stream
         std::lock_guard<std::mutex> lk(img->mu);
         if (img->alt_ready && img->alt_stream != s) VX_CUDA(cudaStreamWaitEvent(c->streams[s], img->alt_ready, 0));
     }
@@ -370,6 +375,12 @@ void drop(Image* im) {
     if (im->d) { dev_free(c, im->home, im->d); held += im->bytes; }
     if (im->bits) { dev_free(c, im->home, im->bits); held += im->bit_words() * 4; }
     if (im->q16) dev_free(c, im->home, im->q16);
+    if (im->lazy) {
+        if (im->lazy->table) dev_free(c, im->home, im->lazy->table);
+        if (im->lazy->src) { im->lazy->src->part_users.fetch_sub(1); drop(im->lazy->src); }
+        if (im->lazy->mask) { im->lazy->mask->part_users.fetch_sub(1); drop(im->lazy->mask); }
+        delete im->lazy;
+    }
     if (im->alt_ready) put_event(c, im->alt_ready);
     put_event(c, im->ready);
     c->live_bytes -= held;
@@ -496,6 +507,7 @@ int OpGuard::input(vx_img h, Image** out, int want_dtype) {
                "operand has dtype %d, expected %d", im->dtype, want_dtype);
     VX_TRY(use_input(c, im, s));
     if (im->dtype == VX_U8) VX_TRY(ensure_u8(c, im, s));
+    if (im->lazy) VX_TRY(ensure_f32(c, im, s));
     *out = im;
     return VX_OK;
 }
@@ -505,16 +517,64 @@ __global__ void __launch_bounds__(256) unpack_stream_kernel(const unsigned* __re
 // The second representation of a boolean image, made on the calling stream after the image's
 // producer (use_input has already ordered this stream behind it).  Other streams wait for
 // alt_ready; the image's free waits for this stream through done_input like for any reader.
+// (called with im->mu held) the representation was there already: if another stream made it, this
+// stream has to be behind that -- use_input's wait may have run before it was recorded
+static int alt_wait(Ctx* c, Image* im, int s) {
+    if (im->alt_ready && im->alt_stream != s) VX_CUDA(cudaStreamWaitEvent(c->streams[s], im->alt_ready, 0));
+    return VX_OK;
+}
 static int alt_done(Ctx* c, Image* im, int s) {
     if (!im->alt_ready) im->alt_ready = get_event(c);
     im->alt_stream = s;
     VX_CUDA(cudaEventRecord(im->alt_ready, c->streams[s]));
     return VX_OK;
 }
+int OpGuard::input_f32_deferred(vx_img h, Image** out, const void** arr) {
+    Image* im = pin_img(h);
+    VX_REQUIRE(im != nullptr, VX_E_INVALID_ARG, "invalid image handle %llu", (unsigned long long)h);
+    ins.push_back(im);
+    VX_REQUIRE(im->ctx == c, VX_E_INVALID_ARG, "image belongs to another context");
+    VX_REQUIRE(im->dtype == VX_F32, VX_E_DTYPE, "operand has dtype %d, expected %d", im->dtype, VX_F32);
+    VX_TRY(use_input(c, im, s));
+    *arr = im->d;
+    if (im->lazy) {
+        // the array may be appearing on another stream right now: look under the image's lock
+        std::lock_guard<std::mutex> lk(im->mu);
+        *arr = im->d;
+        if (im->d) VX_TRY(alt_wait(c, im, s));
+    }
+    if (*arr == nullptr) {
+        // The image's ready event already lies behind the producers of src and mask.  They are read on
+        // this stream now: pin them like operands so that finish() records the read before they can go.
+        Image* parts[2] = {im->lazy->src, im->lazy->mask};
+        for (Image* p : parts) {
+            p->rc.fetch_add(1);
+            ins.push_back(p);
+        }
+    }
+    *out = im;
+    return VX_OK;
+}
+// The f32 array of a deferred image, made on the calling stream (use_input has ordered it behind the
+// image's producer, which ran behind the producers of src and mask).
+int ensure_f32(Ctx* c, Image* im, int s) {
+    if (!im->lazy) return VX_OK;
+    std::lock_guard<std::mutex> lk(im->mu);
+    if (im->d) return alt_wait(c, im, s);
+    void* p = nullptr;
+    VX_TRY(dev_alloc(c, s, ((im->count() + 15) / 16 * 16) * 4 + 64, &p));
+    int rc = pq_apply_launch(c, s, im->lazy->src, im->lazy->mask->bits, im->lazy->table, (float*)p);
+    if (rc == VX_OK) rc = done_input(c, im->lazy->src, s);
+    if (rc == VX_OK) rc = done_input(c, im->lazy->mask, s);
+    if (rc != VX_OK) { dev_free(c, s, p); return rc; }
+    im->d = p;
+    c->live_bytes += im->bytes;
+    return alt_done(c, im, s);
+}
 int ensure_u8(Ctx* c, Image* im, int s) {
     if (im->dtype != VX_U8) return VX_OK;
     std::lock_guard<std::mutex> lk(im->mu);
-    if (im->d) return VX_OK;
+    if (im->d) return alt_wait(c, im, s);
     const size_t n = im->count();
     void* p = nullptr;
     VX_TRY(dev_alloc(c, s, ((n + 15) / 16 * 16) + 64, &p));
@@ -539,7 +599,7 @@ static int pack_bits_of(Ctx* c, int s, const Image* im, unsigned* dst) {
 int ensure_bits(Ctx* c, Image* im, int s) {
     if (im->dtype != VX_U8) return fail(VX_E_DTYPE, "only boolean images have a bit form");
     std::lock_guard<std::mutex> lk(im->mu);
-    if (im->bits) return VX_OK;
+    if (im->bits) return alt_wait(c, im, s);
     void* p = nullptr;
     VX_TRY(dev_alloc(c, s, bits_alloc_bytes(im->count()), &p));
     int rc = pack_bits_of(c, s, im, (unsigned*)p);
@@ -707,6 +767,23 @@ pack_stream_kernel(const uint8_t* __restrict__ a, unsigned* __restrict__ bits, s
     }
 }
 
+cudaError_t h2d_copy(Ctx* c, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    if (bytes < (1u << 20) || !c->ordered_uploads.load(std::memory_order_relaxed))
+        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st);
+    std::lock_guard<std::mutex> lk(c->h2d_mu);
+    cudaError_t e = cudaSuccess;
+    if (c->h2d_tail >= 0) e = cudaStreamWaitEvent(st, c->h2d_ev[c->h2d_tail], 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st);
+    if (e != cudaSuccess) return e;
+    const int i = c->h2d_next;
+    if (!c->h2d_ev[i]) e = cudaEventCreateWithFlags(&c->h2d_ev[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(c->h2d_ev[i], st);
+    if (e != cudaSuccess) return e;
+    c->h2d_tail = i;
+    c->h2d_next = (i + 1) % 8;
+    return cudaSuccess;
+}
+
 }  // namespace vx
 
 using namespace vx;
@@ -774,7 +851,7 @@ int32_t vx_upload_batch(vx_ctx ctx, const void* host, int32_t dtype, int32_t nx,
     VX_TRY(g.begin(ctx));
     Image* im = nullptr;
     VX_TRY(new_image(g.c, dtype, nx, ny, nz, nb, spacing, &im));
-    cudaError_t e = cudaMemcpyAsync(im->d, host, im->bytes, cudaMemcpyDefault, g.st);
+    cudaError_t e = h2d_copy(g.c, im->d, host, im->bytes, g.st);
     if (e != cudaSuccess) {
         drop(im);
         return fail(VX_E_CUDA, "upload failed: %s", cudaGetErrorString(e));
@@ -806,7 +883,7 @@ int32_t vx_upload_scaled(vx_ctx ctx, const void* host, int32_t host_dtype, float
     if (rc == VX_OK) {
         std::vector<int> init(2 * (size_t)nb);
         for (int v = 0; v < nb; v++) { init[2 * v] = 65535; init[2 * v + 1] = 0; }
-        cudaError_t e = cudaMemcpyAsync(raw, host, n * 2, cudaMemcpyDefault, g.st);
+        cudaError_t e = h2d_copy(g.c, raw, host, n * 2, g.st);
         // (pageable source: the runtime stages it before returning)
         if (e == cudaSuccess) e = cudaMemcpyAsync(qrange, init.data(), 8 * (size_t)nb, cudaMemcpyHostToDevice, g.st);
         if (e != cudaSuccess) rc = fail(VX_E_CUDA, "upload failed: %s", cudaGetErrorString(e));
@@ -981,6 +1058,14 @@ int32_t vx_transfer(vx_ctx dst_ctx, vx_img img, vx_img* out) {
     VX_TRY(g.begin(dst_ctx));
     Ctx* src = im->ctx;
     Image* o = nullptr;
+    if (im->lazy && !im->d) {   // a deferred f32 image travels as its array
+        const int ss = my_stream_index(src);
+        VX_REQUIRE(ss >= 0, VX_E_CUDA, "could not create a CUDA stream for the calling thread");
+        VX_CUDA(cudaSetDevice(src->device));
+        VX_TRY(use_input(src, im, ss));
+        VX_TRY(ensure_f32(src, im, ss));
+        VX_CUDA(cudaSetDevice(g.c->device));
+    }
     const bool as_bits = im->d == nullptr;   // a boolean image that only exists as bits travels as bits
     if (as_bits) VX_TRY(new_bits_image(g.c, im->nx, im->ny, im->nz, im->nb, im->sp, &o));
     else VX_TRY(new_image(g.c, im->dtype, im->nx, im->ny, im->nz, im->nb, im->sp, &o));
@@ -1015,11 +1100,16 @@ int32_t vx_device_ptr(vx_ctx ctx, vx_img img, void** ptr) {
         // bytes are the truth from now on, a cached bit form would go stale
         std::lock_guard<std::mutex> lk(im->mu);
         im->bits_frozen = true;
-        if (im->bits) {
+        // (a deferred image that reads these bits keeps them: it holds the mask's value as of its own call)
+        if (im->bits && im->part_users.load() == 0) {
             dev_free(g.c, g.s, im->bits);   // stream-ordered behind every reader enqueued so far on this stream
             g.c->live_bytes -= im->bit_words() * 4;
             im->bits = nullptr;
         }
+    } else if (im->q16) {
+        // same for the 16-bit codes of a quantised image: they stop describing the array
+        std::lock_guard<std::mutex> lk(im->mu);
+        im->q_frozen = true;
     }
     *ptr = im->d;
     return g.finish_scalar();
@@ -1143,6 +1233,7 @@ int32_t vx_set_option(vx_ctx ctx, int32_t option, int64_t value) {
     VX_REQUIRE(c != nullptr, VX_E_INVALID_ARG, "invalid context handle");
     switch (option) {
         case VX_OPT_QUANTISED_PATHS: c->quantised_paths.store(value != 0); return VX_OK;
+        case VX_OPT_ORDERED_UPLOADS: c->ordered_uploads.store(value != 0); return VX_OK;
     }
     return fail(VX_E_INVALID_ARG, "unknown option %d", option);
 }

@@ -1021,7 +1021,7 @@ static int xcorr_codes(OpGuard& og, Scratch& sc, Image* A, const float* d_edges,
     {
         VX_LAUNCH(og.c, og.s, "xc_bin_kernel");
         const dim3 grid = stream_grid(A->nvox(), A->nb);
-        if (A->q16 != nullptr && og.c->quantised_paths.load()) {   // bin the 16-bit codes: half the bytes, a table look-up per voxel
+        if (A->has_codes() && og.c->quantised_paths.load()) {   // bin the 16-bit codes: half the bytes, a table look-up per voxel
             if (A->q_dtype == VX_I16)
                 xc_bin_q16_kernel<short><<<grid, 256, 0, og.st>>>((const short*)A->q16, *d_codes, A->nvox(), A->nx, pitch, d_edges, k,
                                                                   A->q_range(), A->q_slope, A->q_inter);

@@ -95,37 +95,20 @@ class CudaEngine:
     def zeros_u8(self, like):
         return self.ctx.ff(like)
 
-    # operators
-    def not_(self, a): return self.ctx.not_(a)
-    def and_(self, a, b): return self.ctx.and_(a, b)
-    def or_(self, a, b): return self.ctx.or_(a, b)
-    def cmp_scalar(self, a, op, s): return self.ctx.cmp_scalar(a, op, s)
-    def cmp(self, a, op, b): return self.ctx.cmp(a, op, b)
-    def arith_scalar(self, a, op, s): return self.ctx.arith_scalar(a, op, s)
-    def arith(self, a, op, b): return self.ctx.arith(a, op, b)
-    def mask(self, a, m, fill=0.0): return self.ctx.mask(a, m, fill)
-    def to_f32(self, a): return self.ctx.to_f32(a)
-    def near(self, a, conn): return self.ctx.near(a, conn)
-    def interior(self, a, conn): return self.ctx.interior(a, conn)
-    def through(self, a, b, conn): return self.ctx.through(a, b, conn)
-    def components(self, a, conn): return self.ctx.components(a, conn)
+    # Operators whose engine signature is the Context's own are handed through by name: the local
+    # half of a slab operator is the whole-volume operator on the slab.
+    _SAME_AS_CONTEXT = frozenset((
+        "not_", "and_", "or_", "cmp_scalar", "cmp", "arith_scalar", "arith", "mask", "to_f32",
+        "near", "interior", "through", "components", "maxvol", "border", "percentiles",
+        # the stages of `through` on a kept union-find state: one local labelling instead of three
+        "ccl_create", "ccl_seed", "ccl_flag", "ccl_select", "ccl_destroy", "ccl_count", "ccl_sizes", "ccl_flag_size",
+        # building blocks of the distributed sample sort and of the slab EDT / crossCorrelation
+        "pc_pairs", "pc_sort", "pc_rank", "pc_scatter", "edt_sq_xy", "edt_z_from_sq", "cross_correlation_h2"))
 
-    # the stages of `through` on a kept union-find state: one local labelling instead of three
-    def ccl_create(self, b, conn): return self.ctx.ccl_create(b, conn)
-    def ccl_seed(self, st, a): self.ctx.ccl_seed(st, a)
-    def ccl_flag(self, st, labels): self.ctx.ccl_flag(st, labels)
-    def ccl_select(self, st): return self.ctx.ccl_select(st)
-    def ccl_destroy(self, st): self.ctx.ccl_destroy(st)
-    def ccl_count(self, st): return self.ctx.ccl_count(st)
-    def ccl_sizes(self, st, labels): return self.ctx.ccl_sizes(st, labels)
-    def ccl_flag_size(self, st, size): self.ctx.ccl_flag_size(st, size)
-    def maxvol(self, a, conn): return self.ctx.maxvol(a, conn)
-    def border(self, like): return self.ctx.border(like)
-    def percentiles(self, a, mask, correction): return self.ctx.percentiles(a, mask, correction)
-    def pc_pairs(self, a, mask): return self.ctx.pc_pairs(a, mask)
-    def pc_sort(self, pairs): return self.ctx.pc_sort(pairs)
-    def pc_rank(self, pairs, less_before, n_total, correction): return self.ctx.pc_rank(pairs, less_before, n_total, correction)
-    def pc_scatter(self, pairs, values, like): return self.ctx.pc_scatter(pairs, values, like)
+    def __getattr__(self, name):
+        if name in CudaEngine._SAME_AS_CONTEXT:
+            return getattr(self.ctx, name)
+        raise AttributeError(name)
 
     def ccl_plane(self, st, z):
         lab, hit = self.ctx.ccl_plane(st, z)
@@ -133,14 +116,10 @@ class CudaEngine:
         self.ctx.sync()
         return tl[0, 0], th[0, 0]
 
-    def edt_sq_xy(self, a): return self.ctx.edt_sq_xy(a)
-    def edt_z_from_sq(self, sq, max_in): return self.ctx.edt_z_from_sq(sq, max_in)
-
     def dist(self, op, r, a):
         return {"<": self.ctx.distlt, "<=": self.ctx.distleq, ">=": self.ctx.distgeq, ">": self.ctx.distgt}[op](r, a)
 
     def region_histogram(self, b, region, m, M, k): return self.ctx.region_histogram(b, region, m, M, k)[0]
-    def cross_correlation_h2(self, rho, a, h2, m, M, k): return self.ctx.cross_correlation_h2(rho, a, h2, m, M, k)
     def volume(self, a): return float(self.ctx.volume(a)[0])
     def min(self, a): return float(self.ctx.min(a)[0])
     def max(self, a): return float(self.ctx.max(a)[0])
