@@ -562,6 +562,8 @@ def test_limits_are_reported(ctx):
 
 # ------------------------------------------------------------------ runtime
 def test_handles_and_memory(ctx):
+    import gc
+    gc.collect()                 # handles of earlier tests still waiting for the collector would skew the count
     before = ctx.mem_info()
     a = ctx.upload(np.ones((4, 8, 16), np.uint8))
     imgs = [ctx.near(a) for _ in range(50)]
