@@ -35,6 +35,7 @@ print("rc", lib.vx_debug_xt_trace(buf))
 t = np.frombuffer(buf, dtype=np.int64).copy()
 t0 = t[0]
 rel = lambda i: int(t[i] - t0) if t[i] else None
+print("block start (before set-up)", rel(998), "block end (consumer warp 0)", rel(999))
 print("consumer: enter", rel(300), "first chunks ready", rel(301), "init done", rel(302))
 print("copy warp issue times  :", [rel(1 + j) for j in range(34)])
 print("flag warp full times   :", [rel(100 + j) for j in range(34)])

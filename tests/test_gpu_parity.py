@@ -512,6 +512,27 @@ def test_cross_correlation_spacing_and_empty_region(ctx, oracle):
     assert np.all(none == 0)
 
 
+def test_cross_correlation_constant_regions(ctx, oracle):
+    """volumes that are mostly one value (background), where whole warps skip their slides.  Volume 0: zero
+    background; volume 1: a counted constant; volume 2: its very first voxel differs from the background"""
+    shape = (3, 14, 121, 100)
+    rng = np.random.default_rng(41)
+    tex = ndi.gaussian_filter(rng.random(shape).astype(np.float32), (0, 1, 1, 1))
+    a = np.zeros(shape, np.float32)
+    a[1] = 0.37
+    a[2] = 0.6
+    a[:, 3:11, 50:75, 30:58] = tex[:, 3:11, 50:75, 30:58]
+    a[0, 7, 100, 90] = 0.9                      # a lone voxel far inside the background
+    a[2, 0, 0, 0] = 0.1
+    reg = np.zeros(shape, np.uint8)
+    reg[:, 4:9, 55:70, 35:50] = 1
+    Aimg, R = ctx.upload(a), ctx.upload(reg)
+    for rho, k in ((5.0, 100), (2.0, 16)):
+        want = np.stack([oracle.cross_correlation(rho, a[i], a[i], reg[i], 0.0, 1.0, k) for i in range(shape[0])])
+        got = ctx.cross_correlation(rho, Aimg, Aimg, R, 0.0, 1.0, k).numpy()
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (rho, k)
+
+
 def test_cross_correlation_wide_ball_and_out_of_range(ctx, oracle):
     """radius beyond the ring kernel's x halo (the direct sliding kernel), values outside [m, M),
     NaN voxels (never counted), an interval with m == M (nothing counted: all zeros)"""

@@ -591,6 +591,7 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
     int* ge = gs + 17;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    XT_T(tid == 0, 998);
     const int vol = blockIdx.z;
     const int x0 = blockIdx.x * 32;
     const int zb = blockIdx.y / g.nseg, sg = blockIdx.y % g.nseg;
@@ -896,6 +897,7 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
             slot_t = slot_t + 1 == nchunk ? 0 : slot_t + 1;
         }
     }
+    XT_T(tid == 0, 999);
 }
 
 // ball columns (dx, dz, ey): offsets with (dx*sx)^2 + (dy*sy)^2 + (dz*sz)^2 <= rho^2, binary64
@@ -1109,10 +1111,14 @@ static int xcorr_run(OpGuard& og, Scratch& sc, Image* A, const uint8_t* d_codes,
     VX_TRY(new_image(og.c, VX_F32, A->nx, A->ny, A->nz, A->nb, A->sp, &O));
     int rc = VX_OK;
     if (tma_ok) {
-        // y segments: whole columns when the batch already fills the machine many times over (the
-        // initial full-ball build costs about three steps), shorter ones for small batches
+        // y segments: whole columns when the batch already fills the machine many times over, shorter
+        // ones for small batches.  The initial full-ball build is expensive (515 counter adds for rho = 5,
+        // and in the block time line of scripts/ubench/xt_trace.py as long as 6-11 slide steps), so a
+        // segment of 240 rows instead of 120 is worth more than the finer tail: 16 BraTS volumes
+        // 4.47 -> 4.08 ms with 3328 blocks of 240 rows instead of 6656 of 120 (noise, where no block is
+        // short: 9.21 -> 9.40).
         const long long ctas_per_seg = (long long)((A->nx + 31) / 32) * ((A->nz + kXtWarps - 1) / kXtWarps) * nb;
-        const long long want = 20LL * kNumSMs * 2;
+        const long long want = 10LL * kNumSMs * 2;
         int nseg = (int)std::min<long long>((want + ctas_per_seg - 1) / ctas_per_seg, std::max(1, A->ny / 40));
         nseg = std::max(1, nseg);
         const int seg = (A->ny + nseg - 1) / nseg;
