@@ -425,6 +425,42 @@ def test_deferred_percentile_image(ctx, oracle):
     assert ctx.mem_info()["live_handles"] >= 0
 
 
+def test_deferred_percentile_thresholds_on_codes(ctx, oracle):
+    """a deferred percentile image that a program only compares with constants is never looked up: the
+    comparison is decided on the code's position against a per-volume break point.  Every comparison, constants
+    below / at / above the table's values (0, 1, exact table entries, negative, NaN), a decreasing scaling,
+    ties, an empty mask in one volume, several comparisons of one leaf fused in one program -- against the
+    oracle's ranks; and corrections outside [0, 1] (no monotone table) take the look-up"""
+    from voxlogica_b200 import _abi as A
+    rng = np.random.default_rng(97)
+    shape = (3, 6, 10, 32)
+    ops = {"<": np.less, "<=": np.less_equal, ">": np.greater, ">=": np.greater_equal}
+    for dtype, slope, inter, corr in [(np.int16, 0.25, -3.0, 0.5), (np.uint16, -0.5, 100.0, 0.0), (np.int16, 1.0, 0.0, 1.0),
+                                       (np.int16, 0.25, 0.0, 1.5)]:
+        lo, hi = (-40, 60) if dtype == np.int16 else (0, 90)           # few distinct values: many ties
+        raw = rng.integers(lo, hi, size=shape).astype(dtype)
+        m = rnd_mask(shape, 0.5, 98)
+        m[1] = 0                                                       # a volume with an empty mask
+        f = raw.astype(np.float32) * np.float32(slope) + np.float32(inter)
+        want = per_volume(oracle.percentiles, f, m, correction=corr)
+        p = ctx.percentiles(ctx.upload_scaled(raw, slope, inter), ctx.upload(m), corr)
+        vals = np.unique(want)
+        consts = [0.0, 1.0, -0.25, 1.5, 0.5, float("nan"), float(vals[len(vals) // 2]), float(vals[-1]), float(vals[min(1, len(vals) - 1)]),
+                  float(np.nextafter(vals[len(vals) // 3], np.float32(2)))]
+        for c in consts:
+            for name, fn in ops.items():
+                got = ctx.cmp_scalar(p, name, c).numpy()
+                assert np.array_equal(got, fn(want, np.float32(c)).astype(np.uint8)), (dtype, slope, corr, name, c)
+        # two comparisons of the same leaf and a boolean leaf in one fused program: (p > a) & (p <= b) & m
+        a, b = float(vals[len(vals) // 4]), float(vals[(3 * len(vals)) // 4])
+        prog = [(A.VXP_LOAD, 0, 0, 0, 0, 0.0), (A.VXP_LOAD, 1, 1, 0, 0, 0.0), (A.VXP_CMPS, 2, 0, 0, A.VX_GT, a),
+                (A.VXP_CMPS, 3, 0, 0, A.VX_LE, b), (A.VXP_AND, 4, 2, 3, 0, 0.0), (A.VXP_AND, 5, 4, 1, 0, 0.0)]
+        got = ctx.fused(prog, [p, ctx.upload(m)]).numpy()
+        ref = ((want > np.float32(a)) & (want <= np.float32(b)) & (m != 0)).astype(np.uint8)
+        assert np.array_equal(got, ref), (dtype, slope, corr)
+        assert np.array_equal(p.numpy().view(np.uint32), want.view(np.uint32))
+
+
 def test_deferred_image_survives_raw_pointers_to_its_operands(ctx, oracle):
     """vx_device_ptr freezes an image (the caller may write through the pointer): a deferred percentile
     image made before keeps the codes and mask bits it reads; one made after takes the general path"""

@@ -69,6 +69,10 @@ struct Image {
         Image* src = nullptr;
         Image* mask = nullptr;
         float* table = nullptr;   // [nb][65536]
+        // the table is non-decreasing over the codes of every volume's range taken in value order
+        // (0 <= correction <= 1, entries of absent codes filled in): `table[code] OP c` is a comparison
+        // of the code's position with a per-volume break point (pointwise programs, vx_pointwise.cu)
+        bool monotone = false;
     };
     Lazy* lazy = nullptr;
     std::atomic<int> part_users{0};   // deferred images that read this image's q16 / bits: those stay allocated

@@ -543,10 +543,11 @@ pq_hist_kernel(const T* __restrict__ q, const unsigned* __restrict__ mask, size_
     if ((nvox & 15) == 0) {
         const size_t ng = nvox >> 4;
         for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < ng; g += (size_t)gridDim.x * 256) {
+            // codes and mask are asked for together (one memory round trip per group, not two in a row)
             const unsigned m = __ldg(mh + g);
-            if (m == 0u) continue;
             const uint4 a = __ldg(reinterpret_cast<const uint4*>(qv) + 2 * g);
             const uint4 b = __ldg(reinterpret_cast<const uint4*>(qv) + 2 * g + 1);
+            if (m == 0u) continue;
             const unsigned qw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int i = 0; i < 16; i++)
@@ -614,7 +615,9 @@ pq_table_kernel(const unsigned* __restrict__ hist, const int* __restrict__ qrang
             chunk += t;
         }
         const unsigned long long less = carry_s + wbase + incl - c;
-        if (p < span && c) {
+        // (codes that do not occur get their entry too -- nobody looks them up, but with them the table
+        // is non-decreasing in value order, which lets a threshold of the result be decided on codes)
+        if (p < span) {
             double num = (double)less;
             if (correction != 0.0) num = __dadd_rn(num, __dmul_rn(correction, (double)c));
             tv[code_at(p)] = (float)__ddiv_rn(num, nd);
@@ -761,6 +764,7 @@ extern "C" int32_t vx_percentiles(vx_ctx ctx, vx_img a, vx_img mask, double corr
             O->lazy->src = A; A->rc.fetch_add(1); A->part_users.fetch_add(1);
             O->lazy->mask = M; M->rc.fetch_add(1); M->part_users.fetch_add(1);
             O->lazy->table = table;   // freed with the image, on its home stream (= this one)
+            O->lazy->monotone = correction >= 0.0 && correction <= 1.0;
         } else {
             rc = pq_apply_launch(og.c, og.s, A, Mbits, table, (float*)O->d);
             dev_free(og.c, og.s, table);

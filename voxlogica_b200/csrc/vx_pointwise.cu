@@ -37,6 +37,13 @@ struct DevProg {
     const float* leaf_tab[VXP_MAX_LEAVES];
     const void* leaf_mask[VXP_MAX_LEAVES];
     unsigned leaf_flip[VXP_MAX_LEAVES];
+    // a deferred leaf that the program only compares with constants (leaf_rank = 1): the look-up is not
+    // made at all.  The table is monotone, so `table[code] OP c` is `position OP' T` with the code's position
+    // in value order inside the volume's code range (leaf_qrange, leaf_incr) and a break point T per
+    // comparison and volume, found by pw_break_points_kernel; voxels outside the mask sit at -0.5.
+    int leaf_rank[VXP_MAX_LEAVES];
+    const int* leaf_qrange[VXP_MAX_LEAVES];
+    int leaf_incr[VXP_MAX_LEAVES];
     // an f32 leaf read as the 16-bit codes of a quantised image (Image::q16): leaf = the codes,
     // v = fl(fl((float)q * slope) + inter) as vx_upload_scaled formed it; leaf_codes = 1 (int16) / 2 (uint16)
     int leaf_codes[VXP_MAX_LEAVES];
@@ -67,35 +74,59 @@ __device__ __forceinline__ uint4 ld_b(const DevProg& P, uint8_t kind, uint8_t id
     }
     return sb[idx * kPwThreads + threadIdx.x];
 }
+// DEF: what the program's deferred leaves need -- 0: there are none, 1: table look-ups (and possibly rank
+// mode), 2: rank mode only.  The kernel is instantiated per case so that the common programs do not carry
+// the registers of the look-up path (80 -> 90 registers cost the f32 threshold a resident block per SM).
+template <int DEF>
 __device__ __forceinline__ F16 ld_f(const DevProg& P, uint8_t kind, uint8_t idx, size_t g,
                                     const float4* sf) {
     F16 r;
-    if (kind == K_LEAF && P.leaf_tab[idx] != nullptr) {
+    if (DEF != 0 && kind == K_LEAF && P.leaf_tab[idx] != nullptr) {
         // deferred leaf: v = mask ? table[volume][u(code)] : 0 -- 2.125 bytes per voxel from HBM, the
         // look-ups hit L1 (a volume's codes span a few thousand table entries)
         const unsigned m = __ldg(reinterpret_cast<const unsigned short*>(P.leaf_mask[idx]) + g);
         float t[kGroup];
 #pragma unroll
         for (int e = 0; e < kGroup; e++) t[e] = 0.f;
+        // The codes are asked for together with the mask, not after it: skipping the 32 bytes of a group
+        // outside the mask saved traffic nobody was short of and put two memory round trips in a row
+        // (0.19 ms per 16 BraTS volumes for 90 MB).  (The code array ends with the batch's last 8-voxel group.)
+        const uint4* qp = reinterpret_cast<const uint4*>(P.leaf[idx]) + g * 2;
+        const size_t first = g * kGroup;
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        const uint4 a = __ldg(qp), b = first + 8 < P.count ? __ldg(qp + 1) : z4;
         if (m != 0u) {
-            const uint4* qp = reinterpret_cast<const uint4*>(P.leaf[idx]) + g * 2;
-            // (the code array ends with the batch's last 8-voxel group: a half without mask bits is not read)
-            const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-            const uint4 a = (m & 0xffu) ? __ldg(qp) : z4, b = (m >> 8) ? __ldg(qp + 1) : z4;
             const unsigned qw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-            const size_t first = g * kGroup;
             // volume of the group's first voxel (a 32-bit division whenever the batch allows it)
             const unsigned v0 = P.count <= 0xffffffffull ? (unsigned)first / (unsigned)P.nvox : (unsigned)(first / P.nvox);
             const bool one_volume = first - (size_t)v0 * P.nvox + (kGroup - 1) < P.nvox;
             const unsigned flip = P.leaf_flip[idx];
             const float* tab = P.leaf_tab[idx];
+            if (DEF == 2 || P.leaf_rank[idx]) {
+                const int* qr = P.leaf_qrange[idx];
+                const bool incr = P.leaf_incr[idx] != 0;
+                int lo = __ldg(qr + 2 * v0), hi = __ldg(qr + 2 * v0 + 1);
 #pragma unroll
-            for (int e = 0; e < kGroup; e++) {
-                if (!((m >> e) & 1u)) continue;
-                const unsigned v = one_volume ? v0 : (unsigned)((first + e) / P.nvox);
-                const unsigned u = ((qw[e >> 1] >> (16 * (e & 1))) & 0xffffu) ^ flip;
-                t[e] = __ldg(tab + (size_t)v * 65536u + u);
+                for (int e = 0; e < kGroup; e++) {
+                    if (!one_volume) {
+                        const unsigned v = (unsigned)((first + e) / P.nvox);
+                        lo = __ldg(qr + 2 * v); hi = __ldg(qr + 2 * v + 1);
+                    }
+                    const int u = (int)(((qw[e >> 1] >> (16 * (e & 1))) & 0xffffu) ^ flip);
+                    t[e] = ((m >> e) & 1u) ? (float)(incr ? u - lo : hi - u) : -0.5f;
+                }
+            } else if (DEF == 1) {
+#pragma unroll
+                for (int e = 0; e < kGroup; e++) {
+                    if (!((m >> e) & 1u)) continue;
+                    const unsigned v = one_volume ? v0 : (unsigned)((first + e) / P.nvox);
+                    const unsigned u = ((qw[e >> 1] >> (16 * (e & 1))) & 0xffffu) ^ flip;
+                    t[e] = __ldg(tab + (size_t)v * 65536u + u);
+                }
             }
+        } else if (DEF == 2 || P.leaf_rank[idx]) {
+#pragma unroll
+            for (int e = 0; e < kGroup; e++) t[e] = -0.5f;
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) r.v[q] = make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]);
@@ -229,7 +260,12 @@ __device__ __forceinline__ float sel1(unsigned m, int sh, float a, float fill) {
     return ((m >> sh) & 0xffu) ? a : fill;
 }
 
-__global__ void __launch_bounds__(kPwThreads)
+// Four blocks per SM (64 registers, a few bytes of spill in the plain instantiation): these programs wait for
+// memory with one group per thread in flight, so residency is what buys bandwidth -- measured on 16 BraTS
+// volumes: threshold 0.119 -> 0.112 ms, deferred threshold 0.183 -> 0.156 ms; six blocks (40 registers)
+// spill kilobytes and lose (0.148 / 0.189).
+template <int DEF>
+__global__ void __launch_bounds__(kPwThreads, 4)
 pointwise_program_kernel(const __grid_constant__ DevProg P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4* sb = reinterpret_cast<uint4*>(smem_raw);
@@ -263,30 +299,30 @@ pointwise_program_kernel(const __grid_constant__ DevProg P) {
                     st_b(P, op.dst, g, sb, ld_b(P, op.a_kind, op.a_idx, g, sb));
                 } break;
                 case OPC_COPYF: {
-                    st_f(P, op.dst, g, sf, ld_f(P, op.a_kind, op.a_idx, g, sf));
+                    st_f(P, op.dst, g, sf, ld_f<DEF>(P, op.a_kind, op.a_idx, g, sf));
                 } break;
                 case VXP_CMPS: {
-                    F16 x = ld_f(P, op.a_kind, op.a_idx, g, sf);
+                    F16 x = ld_f<DEF>(P, op.a_kind, op.a_idx, g, sf);
                     st_b(P, op.dst, g, sb, cmp16(x, splat(op.imm), op.aux));
                 } break;
                 case VXP_CMPSB: {
-                    F16 x = ld_f(P, op.a_kind, op.a_idx, g, sf);
+                    F16 x = ld_f<DEF>(P, op.a_kind, op.a_idx, g, sf);
                     st_b(P, op.dst, g, sb, cmp16(x, batch_scalar(P, op.b_idx, g), op.aux));
                 } break;
                 case VXP_CMP: {
-                    F16 x = ld_f(P, op.a_kind, op.a_idx, g, sf), y = ld_f(P, op.b_kind, op.b_idx, g, sf);
+                    F16 x = ld_f<DEF>(P, op.a_kind, op.a_idx, g, sf), y = ld_f<DEF>(P, op.b_kind, op.b_idx, g, sf);
                     st_b(P, op.dst, g, sb, cmp16(x, y, op.aux));
                 } break;
                 case VXP_ARITHS: {
-                    F16 x = ld_f(P, op.a_kind, op.a_idx, g, sf);
+                    F16 x = ld_f<DEF>(P, op.a_kind, op.a_idx, g, sf);
                     st_f(P, op.dst, g, sf, arith16(x, splat(op.imm), op.aux));
                 } break;
                 case VXP_ARITHSB: {
-                    F16 x = ld_f(P, op.a_kind, op.a_idx, g, sf);
+                    F16 x = ld_f<DEF>(P, op.a_kind, op.a_idx, g, sf);
                     st_f(P, op.dst, g, sf, arith16(x, batch_scalar(P, op.b_idx, g), op.aux));
                 } break;
                 case VXP_ARITH: {
-                    F16 x = ld_f(P, op.a_kind, op.a_idx, g, sf), y = ld_f(P, op.b_kind, op.b_idx, g, sf);
+                    F16 x = ld_f<DEF>(P, op.a_kind, op.a_idx, g, sf), y = ld_f<DEF>(P, op.b_kind, op.b_idx, g, sf);
                     st_f(P, op.dst, g, sf, arith16(x, y, op.aux));
                 } break;
                 case VXP_TOF32: {
@@ -300,7 +336,7 @@ pointwise_program_kernel(const __grid_constant__ DevProg P) {
                     st_f(P, op.dst, g, sf, r);
                 } break;
                 case VXP_TOBOOL: {
-                    F16 x = ld_f(P, op.a_kind, op.a_idx, g, sf);
+                    F16 x = ld_f<DEF>(P, op.a_kind, op.a_idx, g, sf);
                     st_b(P, op.dst, g, sb, cmp16(x, splat(0.f), VX_NE));
                 } break;
                 case VXP_CONSTB: {
@@ -312,7 +348,7 @@ pointwise_program_kernel(const __grid_constant__ DevProg P) {
                 } break;
                 case VXP_SELECT: {
                     uint4 m = ld_b(P, op.a_kind, op.a_idx, g, sb);
-                    F16 x = ld_f(P, op.b_kind, op.b_idx, g, sf);
+                    F16 x = ld_f<DEF>(P, op.b_kind, op.b_idx, g, sf);
                     unsigned w[4] = {m.x, m.y, m.z, m.w};
                     F16 r;
 #pragma unroll
@@ -402,6 +438,53 @@ boolean_program_kernel(const __grid_constant__ DevProg P) {
     }
 }
 
+// Break points of the comparisons of a rank-mode leaf (DevProg::leaf_rank).  One thread per (comparison,
+// volume): T = first position p of the volume's code range, in value order, whose table entry is > c
+// (GT, LE) or >= c (GE, LT); the comparison becomes  position >= T  (GT, GE)  or  position < T  (LT, LE).
+// A voxel outside the mask has the value 0 and the position -0.5: table entries are >= 0, so it goes
+// with the first position unless 0 itself fails / passes the comparison, in which case T = -1 puts
+// the break below it.  NaN constants come out false everywhere, as they must.
+struct BreakSpec {
+    const float* table;
+    const int* qrange;
+    int incr, cmp;
+    float c;
+    int slot;   // row of the scalar array that receives T
+};
+struct BreakSpecs {
+    int n;
+    BreakSpec s[VXP_MAX_OPS];
+};
+__global__ void pw_break_points_kernel(const __grid_constant__ BreakSpecs B, int nb, float* __restrict__ bscal) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B.n * nb) return;
+    const BreakSpec& b = B.s[t / nb];
+    const int vol = t % nb;
+    const int ulo = b.qrange[2 * vol], uhi = b.qrange[2 * vol + 1];
+    const int span = uhi - ulo + 1;
+    const float* tv = b.table + (size_t)vol * 65536u;
+    const float c = b.c;
+    const bool strict_gt = b.cmp == VX_GT || b.cmp == VX_LE;   // first entry > c; otherwise first entry >= c
+    int lo = 0, hi = span > 0 ? span : 0;   // first p in [0, span] with pred(p), pred monotone
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const float v = tv[b.incr ? ulo + mid : uhi - mid];
+        const bool pr = strict_gt ? v > c : v >= c;
+        if (pr) hi = mid; else lo = mid + 1;
+    }
+    float T = (float)lo;
+    bool zero_passes;
+    switch (b.cmp) {
+        case VX_GT: zero_passes = 0.f > c; break;
+        case VX_GE: zero_passes = 0.f >= c; break;
+        case VX_LT: zero_passes = 0.f < c; break;
+        default: zero_passes = 0.f <= c; break;
+    }
+    if (b.cmp == VX_GT || b.cmp == VX_GE) { if (zero_passes) T = -1.f; }
+    else if (!zero_passes) T = -1.f;
+    bscal[(size_t)b.slot * nb + vol] = T;
+}
+
 // ---- host side: validate, allocate registers, launch ---------------------------
 enum { T_NONE = 0, T_B = 1, T_F = 2 };
 
@@ -454,6 +537,7 @@ int run_pointwise(vx_ctx ctx, const vx_op* prog, int n_ops, const vx_img* leaves
     const void* leaf_mask[VXP_MAX_LEAVES] = {};
     unsigned leaf_flip[VXP_MAX_LEAVES] = {};
     int leaf_codes[VXP_MAX_LEAVES] = {};
+    const Image::Lazy* leaf_lazy[VXP_MAX_LEAVES] = {};
     for (int i = 0; i < n_leaves; i++) {
         int dt = 0;
         VX_REQUIRE(vx_info(leaves[i], &dt, nullptr, nullptr, nullptr, nullptr, nullptr) == VX_OK, VX_E_INVALID_ARG,
@@ -472,6 +556,7 @@ int run_pointwise(vx_ctx ctx, const vx_op* prog, int n_ops, const vx_img* leaves
                 leaf_tab[i] = z->table;
                 leaf_mask[i] = z->mask->bits;
                 leaf_flip[i] = z->src->q_dtype == VX_I16 ? 0x8000u : 0u;
+                leaf_lazy[i] = z;
             } else if (L[i]->has_codes() && g.c->quantised_paths.load()) {
                 leaf_ptr[i] = L[i]->q16;   // half the bytes of the f32 array, the same values
                 leaf_codes[i] = L[i]->q_dtype == VX_I16 ? 1 : 2;
@@ -619,18 +704,76 @@ int run_pointwise(vx_ctx ctx, const vx_op* prog, int n_ops, const vx_img* leaves
         if (leaf_codes[i]) { P.leaf_slope[i] = L[i]->q_slope; P.leaf_inter[i] = L[i]->q_inter; }
     }
     P.out = out_type == T_B ? (void*)o->bits : o->d;
+    // Deferred leaves that are only ever compared with constants are read in rank mode (DevProg::leaf_rank):
+    // every such comparison becomes one against a per-volume break point, appended to the scalar array.
+    BreakSpecs bs;
+    bs.n = 0;
+    if (n_scalars < 0 || !batch_scalars) n_scalars = 0;
+    for (int i = 0; i < n_leaves; i++) {
+        if (leaf_lazy[i] == nullptr || !leaf_lazy[i]->monotone) continue;
+        bool ok = true;
+        int uses = 0;
+        for (int j = 0; j < nd && ok; j++) {
+            const DevOp& D = P.ops[j];
+            int ta, tb;
+            const int nopnd = D.opcode == OPC_COPYF ? 1 : D.opcode == OPC_COPYB ? 0 : operand_types(D.opcode, &ta, &tb);
+            const bool a_is = nopnd >= 1 && D.a_kind == K_LEAF && D.a_idx == i && (D.opcode == OPC_COPYF || ta == T_F);
+            const bool b_is = nopnd >= 2 && D.b_kind == K_LEAF && D.b_idx == i && tb == T_F;
+            if (b_is) ok = false;
+            if (a_is) {
+                if (D.opcode == VXP_CMPS && D.aux >= VX_LT && D.aux <= VX_GE) uses++;
+                else ok = false;
+            }
+        }
+        if (!ok || uses == 0 || n_scalars + bs.n + uses > 255) continue;
+        for (int j = 0; j < nd; j++) {
+            DevOp& D = P.ops[j];
+            if (!(D.opcode == VXP_CMPS && D.a_kind == K_LEAF && D.a_idx == i)) continue;
+            BreakSpec& b = bs.s[bs.n];
+            b.table = leaf_lazy[i]->table;
+            b.qrange = leaf_lazy[i]->src->q_range();
+            b.incr = leaf_lazy[i]->src->q_increasing ? 1 : 0;
+            b.cmp = D.aux;
+            b.c = D.imm;
+            b.slot = n_scalars + bs.n;
+            D.opcode = VXP_CMPSB;
+            D.b_idx = (uint8_t)b.slot;
+            D.aux = (D.aux == VX_GT || D.aux == VX_GE) ? VX_GE : VX_LT;
+            bs.n++;
+        }
+        P.leaf_rank[i] = 1;
+        P.leaf_qrange[i] = leaf_lazy[i]->src->q_range();
+        P.leaf_incr[i] = leaf_lazy[i]->src->q_increasing ? 1 : 0;
+    }
     float* d_scal = nullptr;
-    if (n_scalars > 0 && batch_scalars) {
+    if (bs.n > 0 && n_scalars == 0) {
+        int r = scratch_alloc(g.c, g.s, sizeof(float) * (size_t)bs.n * shape->nb, (void**)&d_scal);
+        if (r != VX_OK) { drop(o); return r; }
+        P.bscal = d_scal;
+    }
+    if (n_scalars > 0) {
         size_t bytes = sizeof(float) * (size_t)n_scalars * shape->nb;
-        int r = scratch_alloc(g.c, g.s, bytes, (void**)&d_scal);
+        int r = scratch_alloc(g.c, g.s, sizeof(float) * (size_t)(n_scalars + bs.n) * shape->nb, (void**)&d_scal);
         if (r != VX_OK) { drop(o); return r; }
         // pageable source: the runtime stages it before returning
         cudaError_t e = cudaMemcpyAsync(d_scal, batch_scalars, bytes, cudaMemcpyHostToDevice, g.st);
         if (e != cudaSuccess) { drop(o); return fail(VX_E_CUDA, "scalar upload: %s", cudaGetErrorString(e)); }
         P.bscal = d_scal;
     }
+    if (bs.n > 0) {
+        {
+            VX_LAUNCH(g.c, g.s, "pw_break_points_kernel");
+            pw_break_points_kernel<<<(bs.n * shape->nb + 127) / 128, 128, 0, g.st>>>(bs, shape->nb, d_scal);
+        }
+        int r = check_launch("pw_break_points_kernel");
+        if (r != VX_OK) { scratch_free(g.c, g.s, d_scal); drop(o); return r; }
+    }
+    int def_mode = 0;   // see ld_f
+    for (int i = 0; i < n_leaves; i++)
+        if (leaf_tab[i] != nullptr) def_mode = (P.leaf_rank[i] && def_mode != 1) ? 2 : 1;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(pointwise_program_kernel,
+        cudaError_t e = cudaFuncSetAttribute(def_mode == 0 ? pointwise_program_kernel<0>
+                                             : def_mode == 2 ? pointwise_program_kernel<2> : pointwise_program_kernel<1>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { drop(o); return fail(VX_E_CUDA, "smem attribute: %s", cudaGetErrorString(e)); }
     }
@@ -652,7 +795,9 @@ int run_pointwise(vx_ctx ctx, const vx_op* prog, int n_ops, const vx_img* leaves
     {
         VX_LAUNCH(g.c, g.s, boolean_only ? "boolean_program_kernel" : "pointwise_program_kernel");
         if (boolean_only) boolean_program_kernel<<<grid, kPwThreads, smem, g.st>>>(P);
-        else pointwise_program_kernel<<<grid, kPwThreads, smem, g.st>>>(P);
+        else if (def_mode == 0) pointwise_program_kernel<0><<<grid, kPwThreads, smem, g.st>>>(P);
+        else if (def_mode == 2) pointwise_program_kernel<2><<<grid, kPwThreads, smem, g.st>>>(P);
+        else pointwise_program_kernel<1><<<grid, kPwThreads, smem, g.st>>>(P);
     }
     int r = check_launch("pointwise_program_kernel");
     if (r == VX_OK && d_scal) r = scratch_free(g.c, g.s, d_scal);
