@@ -477,10 +477,10 @@ def run_ours(args):
     import threading
     del flair
     nthr = max(1, args.threads)
-    pins_in = [ctx.host_alloc(host.nbytes, write_combined=args.wc) for _ in range(nthr)]
+    pins_in = [ctx.host_alloc(host.nbytes, write_combined=args.wc) for _ in range(nthr + max(0, args.prefetch))]
     pins_out = [ctx.host_alloc(out_bytes) for _ in range(nthr)]
-    for t in range(nthr):
-        C.memmove(pins_in[t], host.ctypes.data, host.nbytes)
+    for p_in in pins_in:
+        C.memmove(p_in, host.ctypes.data, host.nbytes)
 
     def e2e_worker(t, queue, errors):
         try:
@@ -491,7 +491,74 @@ def run_ours(args):
         except Exception as e:  # pragma: no cover
             errors.append(e)
 
+    # With --prefetch D (default 2) the uploads come from their own host thread (its own library stream), as a
+    # harness that reads the next file while the current one is being analysed would issue them: it keeps at
+    # most D uploaded batches waiting, the `nthr` analysis threads take them in turn (the library orders a
+    # consumer's stream behind the upload through the event in the handle).  Every step still copies its whole
+    # batch host -> device and its masks device -> host inside the timed region; what changes is that both
+    # analysis streams stay busy while the copy engine works (without it each thread's upload sits between
+    # its own steps, so for 5.4 of every 14 ms only one step's kernels are on the device).
+    import queue as pyqueue
+
+    class Pipeline:
+        """the uploading thread and the analysis threads live for the whole end-to-end leg (warm-up and timed
+        run): a host thread keeps its library stream and the device blocks cached on it, and the blocks an
+        uploader needs (one batch of int16 + one of f32) are not the ones an analysis step recycles"""
+
+        def __init__(self):
+            self.jobs = pyqueue.Queue()                        # one token per step, None = shut down
+            self.ready = pyqueue.Queue(maxsize=args.prefetch)  # uploaded batches waiting for an analysis thread
+            self.done = pyqueue.Queue()                        # one entry per finished step: None or the exception
+            self.threads = [threading.Thread(target=self.uploader, daemon=True)] + \
+                           [threading.Thread(target=self.analyst, args=(t,), daemon=True) for t in range(nthr)]
+            [t.start() for t in self.threads]
+
+        def uploader(self):
+            i = 0
+            while self.jobs.get() is not None:
+                try:
+                    f = ctx.upload_scaled_ptr(pins_in[i % len(pins_in)], np.int16, shape4, INT16_SLOPE)
+                except Exception as e:  # pragma: no cover
+                    self.done.put(e)
+                    continue
+                self.ready.put(f)
+                del f
+                i += 1
+            for _ in range(nthr):
+                self.ready.put(None)
+
+        def analyst(self, t):
+            while True:
+                f = self.ready.get()
+                if f is None:
+                    return
+                try:
+                    out = run_gtv(ctx, f)
+                    del f
+                    ctx.download_bits_ptr(out["gtv"], pins_out[t], out_bytes)
+                    del out
+                    self.done.put(None)
+                except Exception as e:  # pragma: no cover
+                    f = None
+                    self.done.put(e)
+
+        def run(self, nsteps):
+            for _ in range(nsteps):
+                self.jobs.put(1)
+            for _ in range(nsteps):
+                r = self.done.get()
+                if r is not None:
+                    raise r
+
+        def close(self):
+            self.jobs.put(None)
+            [t.join(timeout=30) for t in self.threads]
+
+    pipe = Pipeline() if args.prefetch > 0 else None
+
     def run_e2e(nsteps):
+        if pipe is not None:
+            return pipe.run(nsteps)
         errors = []
         queue = StepQueue(nsteps)
         ths = [threading.Thread(target=e2e_worker, args=(t, queue, errors)) for t in range(nthr)]
@@ -500,7 +567,7 @@ def run_ours(args):
         if errors:
             raise errors[0]
 
-    run_e2e(2 * nthr)
+    run_e2e(2 * nthr + (args.prefetch + 2 if pipe is not None else 0))   # every block the pipeline cycles through exists
     barrier()
     # achieved host->device bandwidth of this rank with every rank copying at once (what bounds e2e
     # when the host fabric is shared): five uploads of the batch from pinned memory, untimed otherwise
@@ -516,6 +583,8 @@ def run_ours(args):
     ctx.sync()
     ms_e2e = (time.perf_counter() - t0) * 1e3      # all streams drained: host clock around device work
     barrier()
+    if pipe is not None:
+        pipe.close()
 
     # ---- per-kernel table from an untimed pass with ONE host thread (one stream): launch
     # durations without other streams' kernels sharing the SMs, which is what a roofline
@@ -603,7 +672,9 @@ def run_ours(args):
                             "the device by vx_upload_scaled, bit-identical to converting on the host",
                    "data_note": "min(batch,4) generated volumes per rank + axis flips"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-                "ms_per_step": ms_e2e / args.steps, "host_threads": nthr, "numa": numa,
+                "ms_per_step": ms_e2e / args.steps, "host_threads": nthr, "prefetch": args.prefetch,
+                "upload_thread": "own host thread, at most `prefetch` uploaded batches ahead" if args.prefetch > 0 else "none",
+                "numa": numa,
                 "h2d_gbs_this_rank_all_ranks_copying": round(h2d_gbs, 2),
                 "timing": "host perf_counter around K steps with all streams synchronised on both sides"},
         "gpu_launches": launches,
@@ -646,6 +717,9 @@ def main():
                          "upload overlaps the other's kernels; with three or more, two uploads share the PCIe link and the "
                          "one the GPU is waiting for arrives later (measured: e2e 1994 volumes/s with 2, 1716 with 3, "
                          "1622 with 4 or 6; the resident number is the same 2230-2270 for all)")
+    ap.add_argument("--prefetch", type=int, default=2,
+                    help="end-to-end leg: uploaded batches the uploading host thread keeps ahead of the analysis threads "
+                         "(0: every analysis thread uploads its own step's batch, the round-1 scheme)")
     ap.add_argument("--wc", action="store_true", help="write-combined pinned staging buffers for the uploads")
     ap.add_argument("--independent-uploads", action="store_true",
                     help="diagnosis: turn VX_OPT_ORDERED_UPLOADS off (uploads of different threads share the link)")

@@ -569,6 +569,47 @@ def test_cross_correlation_constant_regions(ctx, oracle):
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (rho, k)
 
 
+def test_cross_correlation_flat_rows_at_the_top_and_bottom_of_the_image(ctx, oracle):
+    """balls that reach over the first / last rows of the image while everything they see inside it is one
+    value: the kernel builds them from row counts and moves voxels between the not-counted code and the
+    reference code in closed form (warps whose columns all lie inside the image in x and z; nx = 100 has one
+    such chunk, x = 32..63).  Volume 0: counted constant background, texture in the middle rows; volume 1:
+    the same with a background that is NOT counted (below m); volume 2: constant everywhere; volume 3:
+    texture touching the first rows only.  Also an image with fewer rows than the ball is high (top and
+    bottom crossed in the same step)."""
+    rng = np.random.default_rng(43)
+    shape = (4, 13, 40, 100)
+    tex = ndi.gaussian_filter(rng.random(shape).astype(np.float32), (0, 1, 1, 1))
+    a = np.full(shape, 0.37, np.float32)
+    a[1] = -1.0
+    a[0:2, :, 14:26, :] = tex[0:2, :, 14:26, :]
+    a[3, :, 0:9, 20:80] = tex[3, :, 0:9, 20:80]
+    reg = np.zeros(shape, np.uint8)
+    reg[:, 3:10, 16:24, 35:60] = 1
+    reg[3, 3:10, 0:6, 35:60] = 1
+    Aimg, R = ctx.upload(a), ctx.upload(reg)
+    for rho, k in ((5.0, 100), (2.0, 16), (3.0, 33), (4.0, 50)):
+        want = np.stack([oracle.cross_correlation(rho, a[i], a[i], reg[i], 0.0, 1.0, k) for i in range(shape[0])])
+        got = ctx.cross_correlation(rho, Aimg, Aimg, R, 0.0, 1.0, k).numpy()
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (rho, k)
+    # anisotropic spacing: the table-driven kernel (column list not compiled in)
+    sp = (1.0, 1.25, 1.0)
+    As, Rs = ctx.upload(a[:2], spacing=sp), ctx.upload(reg[:2], spacing=sp)
+    want = np.stack([oracle.cross_correlation(5.0, a[i], a[i], reg[i], 0.0, 1.0, 40, spacing=sp) for i in range(2)])
+    got = ctx.cross_correlation(5.0, As, As, Rs, 0.0, 1.0, 40).numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # 7 rows under a ball of 11
+    low = np.full((2, 12, 7, 100), 0.5, np.float32)
+    low[1, :, :, 40:60] = tex[1, :12, :7, 40:60]
+    lreg = np.zeros(low.shape, np.uint8)
+    lreg[:, 2:9, 1:6, 30:70] = 1
+    L, LR = ctx.upload(low), ctx.upload(lreg)
+    for rho, k in ((5.0, 100), (2.0, 16)):
+        want = np.stack([oracle.cross_correlation(rho, low[i], low[i], lreg[i], 0.0, 1.0, k) for i in range(2)])
+        got = ctx.cross_correlation(rho, L, L, LR, 0.0, 1.0, k).numpy()
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), ("low", rho, k)
+
+
 def test_cross_correlation_wide_ball_and_out_of_range(ctx, oracle):
     """radius beyond the ring kernel's x halo (the direct sliding kernel), values outside [m, M),
     NaN voxels (never counted), an interval with m == M (nothing counted: all zeros)"""

@@ -480,12 +480,14 @@ struct BallCols {
     static constexpr int MAXC = (2 * W + 1) * (2 * W + 1);
     int n;
     int dx[MAXC], dz[MAXC], e[MAXC];
-    constexpr BallCols() : n(0), dx{}, dz{}, e{} {
+    int cnt[W + 1];   // columns per y half-extent
+    constexpr BallCols() : n(0), dx{}, dz{}, e{}, cnt{} {
         for (int z = -W; z <= W; z++)
             for (int x = -W; x <= W; x++) {
                 const int rem = R2 - x * x - z * z;
                 if (rem < 0) continue;
                 dx[n] = x; dz[n] = z; e[n] = cisqrt(rem);
+                cnt[e[n]]++;
                 n++;
             }
     }
@@ -497,6 +499,18 @@ struct Ball {
 };
 template <int R2>
 constexpr BallCols<R2> Ball<R2>::c;
+
+// number of columns with y half-extent e (a compare chain over constants: folds when e is known)
+template <int R2, int... E>
+__device__ __forceinline__ int ball_cnt_impl(int e, std::integer_sequence<int, E...>) {
+    int r = 0;
+    ((r = (e == E) ? std::integral_constant<int, Ball<R2>::c.cnt[E]>::value : r), ...);
+    return r;
+}
+template <int R2>
+__device__ __forceinline__ int ball_cnt(int e) {
+    return ball_cnt_impl<R2>(e, std::make_integer_sequence<int, Ball<R2>::W + 1>{});
+}
 
 constexpr int kXtBatch = 14;   // counter pairs whose shared-memory operations are in flight together
 
@@ -540,28 +554,29 @@ __device__ __forceinline__ void xt_slide(unsigned hbase, const unsigned* pin, co
 }
 
 // one row of the initial ball: columns whose half-extent reaches |dy| add their voxel of ring row
-// `prow`; with `flat` every column adds all its 2e+1 voxels at once (they hold one value).
+// `prow`; with `nin` (a flat neighbourhood) every column adds all its voxels that lie inside the image
+// at once -- nin[e] of the 2e+1 rows of a column with half-extent e -- since they hold one value.
 // Batched like the slide: the ring reads of a batch are issued before its atomics.
 template <int R2, int BASE, int... J>
 __device__ __forceinline__ void xt_init_batch(std::integer_sequence<int, J...>, unsigned hbase, unsigned prow, int ady,
-                                              bool flat) {
+                                              const unsigned* nin) {
     unsigned v[sizeof...(J)];
     ((v[J] = (Ball<R2>::c.e[BASE + J] >= ady)
                  ? lds_u8_imm<(Ball<R2>::W + Ball<R2>::c.dz[BASE + J]) * (kXtCH * kXtRowB) + kXtHalo + Ball<R2>::c.dx[BASE + J]>(prow)
                  : 0u),
      ...);
     (((Ball<R2>::c.e[BASE + J] >= ady)
-          ? (void)atoms_add(hbase + v[J] * kXtHS, flat ? (unsigned)(2 * Ball<R2>::c.e[BASE + J] + 1) : 1u)
+          ? (void)atoms_add(hbase + v[J] * kXtHS, nin ? nin[std::integral_constant<int, Ball<R2>::c.e[BASE + J]>::value] : 1u)
           : (void)0),
      ...);
 }
 template <int R2, int BASE>
-__device__ __forceinline__ void xt_init_row(unsigned hbase, unsigned prow, int ady, bool flat) {
+__device__ __forceinline__ void xt_init_row(unsigned hbase, unsigned prow, int ady, const unsigned* nin) {
     constexpr int N = Ball<R2>::c.n;
     if constexpr (BASE < N) {
         constexpr int CNT = (N - BASE) < kXtBatch ? (N - BASE) : kXtBatch;
-        xt_init_batch<R2, BASE>(std::make_integer_sequence<int, CNT>{}, hbase, prow, ady, flat);
-        xt_init_row<R2, BASE + CNT>(hbase, prow, ady, flat);
+        xt_init_batch<R2, BASE>(std::make_integer_sequence<int, CNT>{}, hbase, prow, ady, nin);
+        xt_init_row<R2, BASE + CNT>(hbase, prow, ady, nin);
     }
 }
 
@@ -675,7 +690,8 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
                 for (int u = 0; u < 4; u++) {
                     const int sgm = (q0 + u) * 8 + (lane >> 2);   // plane 2q + (lane >> 4), row (lane >> 2) & 3
                     const int zz = z0 - g.wz + (sgm >> 2);
-                    need[u] = sgm < nsegm && zz >= 0 && zz < g.nz;
+                    const int ry = r0 + j * kXtCH + (sgm & 3);   // rows above / below the image hold no voxels: flat
+                    need[u] = sgm < nsegm && zz >= 0 && zz < g.nz && ry >= 0 && ry < g.ny;
                     v[u] = need[u] ? cbase[(q0 + u) * 32 + lane] : make_uint4(ref4, ref4, ref4, ref4);
                 }
 #pragma unroll
@@ -740,16 +756,37 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
     XT_T(tid == 0, 301);
     for (int rel = 0; rel <= wy2; rel++) examine_next();
     unsigned S = 0;   // sum over ALL codes (the dummy code 0 included) of h^2
+    // columns per y half-extent (compiled in for the known balls)
+    auto ncols_of = [&](int e) -> int {
+        if constexpr (R2 > 0) return ball_cnt<R2>(e);
+        else return ge[e] - gs[e];
+    };
+    // every column of this warp's balls lies inside the image in x and z (warp-uniform)
+    const bool xz_in = x0 - g.wx >= 0 && x0 + 31 + g.wx < g.nx && z - g.wz >= 0 && z + g.wz < g.nz;
     if (wactive) {
         const bool flat0 = run >= wy2 + 1;
+        // flat: the whole neighbourhood of the first voxel is one value per column.  A column with half-extent
+        // e has nin[e] of its 2e+1 voxels in rows of the image: they go to ONE counter (the reference code, or
+        // code 0 where the column lies outside the image in x or z); the voxels in rows above / below the image
+        // are not counted (code 0) whatever the column.
+        unsigned nin[17];
+        unsigned outside = 0;
+        if (flat0) {
+#pragma unroll
+            for (int e = 0; e <= (R2 > 0 ? Ball<R2>::W : 16); e++) {
+                if (e > wy) break;
+                const int lo = max(0, y0 - e), hi = min(g.ny - 1, y0 + e);
+                nin[e] = (unsigned)(hi - lo + 1);
+                outside += (unsigned)ncols_of(e) * (unsigned)(2 * e + 1 - (hi - lo + 1));
+            }
+        }
         if constexpr (R2 == 0) {
             if (flat0) {
-                // the whole neighbourhood of the first voxel is one value per column: every column
-                // adds its 2e+1 voxels to one counter (the reference code, or code 0 outside the image)
                 const unsigned prow = tb + rowoff(wy);
                 for (int e = 0; e <= wy; e++)
                     for (int c = gs[e]; c < ge[e]; c++)
-                        atoms_add(hbase + lds_u8(prow + cols[c]) * kXtHS, (unsigned)(2 * e + 1));
+                        atoms_add(hbase + lds_u8(prow + cols[c]) * kXtHS, nin[e]);
+                hist[tid] += outside;
             } else {
                 for (int e = 0; e <= wy; e++)
                     for (int c = gs[e]; c < ge[e]; c++) {
@@ -760,9 +797,14 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
             }
         } else {
             // row by row: row dy of the ball holds the columns with half-extent >= |dy|.  A flat
-            // neighbourhood needs one row only, every column weighted by its 2e+1 voxels.
-            for (int dy = flat0 ? 0 : -wy; dy <= (flat0 ? 0 : wy); dy++)
-                xt_init_row<R2, 0>(hbase, tb + rowoff(wy + dy), dy < 0 ? -dy : dy, flat0);
+            // neighbourhood needs one row only, every column weighted by its voxels inside the image.
+            if (flat0) {
+                xt_init_row<R2, 0>(hbase, tb + rowoff(wy), 0, nin);
+                hist[tid] += outside;
+            } else {
+                for (int dy = -wy; dy <= wy; dy++)
+                    xt_init_row<R2, 0>(hbase, tb + rowoff(wy + dy), dy < 0 ? -dy : dy, nullptr);
+            }
         }
         for (int c = 0; c < nbin; c++) {
             const unsigned h = hist[c * kXtCons + tid];
@@ -809,7 +851,9 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
         XT_T(tid == 0, 400 + t);
         // ---- four steps at once where nothing changes: the next four rows are flat as well, so
         // the slides t .. t+3 move nothing and rows t .. t+3 all get the current coefficient
-        if (tq == 0 && t + 4 < T && run >= wy2 + 1) {
+        // (rows above / below the image count as flat, but a slide whose window reaches them does move
+        // counters: those steps are taken one at a time below)
+        if (tq == 0 && t + 4 < T && run >= wy2 + 1 && y0 + t >= wy && y0 + t + 4 + wy < g.ny) {
             ensure(t + wy2 + 4);
             XT_T(tid == 0, 600 + t);
             int i1 = x_idx + 1, i2 = x_idx + 2, i3 = x_idx + 3;
@@ -837,7 +881,33 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
         // ---- slide the ball from row y0+t to y0+t+1: ring rows t .. t+2wy+1
         ensure(t + wy2 + 1);
         examine_next();
-        if (wactive && run < wy2 + 2) {
+        // The slide moves nothing when its whole window (ring rows t .. t+2wy+1) is flat AND lies inside the
+        // image in y.  Where the window is flat but reaches over the top or bottom of the image, a column moves
+        // one voxel between code 0 (the row outside) and the reference code (the row inside): for a warp whose
+        // columns all lie inside the image in x and z that is a known number of moves between two counters.
+        const int yv = y0 + t;
+        const bool ycross = yv < wy || yv + 1 + wy >= g.ny;
+        const bool allflat = run >= wy2 + 2;
+        if (wactive && allflat && ycross && xz_in) {
+            int d = 0;   // voxels that move from code 0 to the reference code
+#pragma unroll
+            for (int e = 0; e <= (R2 > 0 ? Ball<R2>::W : 16); e++) {
+                if (e > wy) break;
+                const bool out_gone = yv - e < 0, in_gone = yv + 1 + e >= g.ny;   // leaving / entering row is outside
+                d += ncols_of(e) * ((out_gone && !in_gone ? 1 : 0) - (in_gone && !out_gone ? 1 : 0));
+            }
+            if (d != 0) {
+                const unsigned refc = lds_u8(tb + rowoff(t + wy) + g.wz * (kXtCH * kXtRowB) + kXtHalo);   // own voxel
+                if (refc != 0) {   // (a reference value that is not counted shares code 0 with the rows outside)
+                    unsigned* hr = hist + refc * kXtCons + tid;
+                    const unsigned h0 = hist[tid], h1 = *hr;
+                    hist[tid] = h0 - (unsigned)d;
+                    *hr = h1 + (unsigned)d;
+                    S += 2u * (unsigned)d * (h1 - h0) + 2u * (unsigned)(d * d);
+                }
+                dirty = true;
+            }
+        } else if (wactive && (!allflat || ycross)) {
             unsigned A = 0;            // sum of counters before +1 minus sum of counters before -1
             if constexpr (R2 > 0) {
                 constexpr int W = Ball<R2>::W;
