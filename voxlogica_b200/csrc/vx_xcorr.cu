@@ -436,13 +436,13 @@ constexpr unsigned kXtHS = kXtCons * 4;      // byte stride between two codes of
 
 #ifdef XT_TRACE
 __device__ long long xt_trace[1024];
-#define XT_T(cond, idx) do { if ((cond) && blockIdx.x == 3 && blockIdx.y == 20 && blockIdx.z == 1) xt_trace[(idx)] = clock64(); } while (0)
+#define XT_T(cond, idx) do { if ((cond) && xt_bx == 3 && xt_by == 20 && vol == 1) xt_trace[(idx)] = clock64(); } while (0)
 #else
 #define XT_T(cond, idx) do { } while (0)
 #endif
 
 struct XtGeo {
-    int nx, ny, nz, k, seg, nseg, ball;
+    int nx, ny, nz, nb, k, seg, nseg, ball;
     int ncols, nreal;          // length of the column table (with alignment filler) / real columns
     int wx, wy, wz, P, nchunk, pitch;
     int gstart[17], gend[17];  // columns with y half-extent e are [gstart[e], gend[e]), gstart 4-aligned
@@ -510,6 +510,22 @@ __device__ __forceinline__ int ball_cnt_impl(int e, std::integer_sequence<int, E
 template <int R2>
 __device__ __forceinline__ int ball_cnt(int e) {
     return ball_cnt_impl<R2>(e, std::make_integer_sequence<int, Ball<R2>::W + 1>{});
+}
+
+// sum over the columns that lie inside the image in x and z of sgn[e(column)] (this lane's x, this warp's z)
+template <int R2, int... I>
+__device__ __forceinline__ int ball_signed_cols_impl(int x, int z, int nx, int nz, const int* sgn, std::integer_sequence<int, I...>) {
+    int d = 0;
+    ((d += ((unsigned)(x + std::integral_constant<int, Ball<R2>::c.dx[I]>::value) < (unsigned)nx &&
+            (unsigned)(z + std::integral_constant<int, Ball<R2>::c.dz[I]>::value) < (unsigned)nz)
+               ? sgn[std::integral_constant<int, Ball<R2>::c.e[I]>::value]
+               : 0),
+     ...);
+    return d;
+}
+template <int R2>
+__device__ __forceinline__ int ball_signed_cols(int x, int z, int nx, int nz, const int* sgn) {
+    return ball_signed_cols_impl<R2>(x, z, nx, nz, sgn, std::make_integer_sequence<int, Ball<R2>::c.n>{});
 }
 
 constexpr int kXtBatch = 14;   // counter pairs whose shared-memory operations are in flight together
@@ -580,7 +596,11 @@ __device__ __forceinline__ void xt_init_row(unsigned hbase, unsigned prow, int a
     }
 }
 
-// grid (ceil(nx/32), ceil(nz/6)*nseg, nb), block 256.  Dynamic shared memory:
+// grid: ceil(nx/32) * ceil(nz/6)*nseg * nb blocks in ONE dimension; block i works on volume i % nb and on the
+// (x chunk, plane block and segment) order[i / nb].  The host sorts that table from the centre of the volume
+// outwards: blocks in the middle of a head slide through texture for their whole column (700 k cycles), blocks
+// in the background skip most of theirs (50 k), and with the blocks in raster order the kernel ended on the
+// heavy blocks of the last volume with most SMs idle.  Block 256 threads.  Dynamic shared memory:
 //   ring [nchunk][P][4][64] u8 | hist [k+1][192] u32 | h2s [k+1] u32 | cols [ncols] u32 | rowmask [64] u32 |
 //   mbarriers [48] u64 | gs, ge [17] int
 // cols[c] = byte offset of column c inside a chunk relative to (plane = warp, x = lane):
@@ -588,9 +608,13 @@ __device__ __forceinline__ void xt_init_row(unsigned hbase, unsigned prow, int a
 template <int R2>
 __global__ void __launch_bounds__(kXtThreads, 2)
 xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ codes,
-                 float* __restrict__ out, const unsigned* __restrict__ cols_g, const unsigned* __restrict__ h2,
-                 const XcStat* __restrict__ vstat, const __grid_constant__ XtGeo g) {
+                 float* __restrict__ out, const unsigned* __restrict__ cols_g, const unsigned* __restrict__ order,
+                 const unsigned* __restrict__ h2, const XcStat* __restrict__ vstat, const __grid_constant__ XtGeo g) {
     extern __shared__ unsigned char xt_smem_raw[];
+    const unsigned xt_rank = blockIdx.x / (unsigned)g.nb;
+    const int vol = (int)(blockIdx.x - xt_rank * (unsigned)g.nb);
+    const unsigned xt_place = __ldg(order + xt_rank);
+    const int xt_bx = (int)(xt_place & 0xffffu), xt_by = (int)(xt_place >> 16);
     // TMA destinations must be 128-byte aligned: align the dynamic window by hand (128 spare bytes)
     unsigned char* xt_smem = xt_smem_raw + ((128u - (smem_u32(xt_smem_raw) & 127u)) & 127u);
     const int chunkB = g.P * kXtCH * kXtRowB;   // P is even: a multiple of 128
@@ -607,9 +631,8 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     XT_T(tid == 0, 998);
-    const int vol = blockIdx.z;
-    const int x0 = blockIdx.x * 32;
-    const int zb = blockIdx.y / g.nseg, sg = blockIdx.y % g.nseg;
+    const int x0 = xt_bx * 32;
+    const int zb = xt_by / g.nseg, sg = xt_by % g.nseg;
     const int z0 = zb * kXtWarps;
     const int y0 = sg * g.seg;
     const int T = min(g.ny, y0 + g.seg) - y0;        // rows of this segment (>= 1)
@@ -883,22 +906,38 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
         examine_next();
         // The slide moves nothing when its whole window (ring rows t .. t+2wy+1) is flat AND lies inside the
         // image in y.  Where the window is flat but reaches over the top or bottom of the image, a column moves
-        // one voxel between code 0 (the row outside) and the reference code (the row inside): for a warp whose
-        // columns all lie inside the image in x and z that is a known number of moves between two counters.
+        // one voxel between code 0 (the row outside) and the reference code (the row inside) -- unless it lies
+        // outside the image in x or z, where every row holds code 0: a known number of moves between two counters.
         const int yv = y0 + t;
         const bool ycross = yv < wy || yv + 1 + wy >= g.ny;
         const bool allflat = run >= wy2 + 2;
-        if (wactive && allflat && ycross && xz_in) {
-            int d = 0;   // voxels that move from code 0 to the reference code
+        if (wactive && allflat && ycross) {
+            int sgn[17];   // per half-extent: +1 the column's leaving row is outside the image, -1 its entering row
+            int dall = 0;  // voxels that move from code 0 to the reference code when every column is inside in x, z
 #pragma unroll
             for (int e = 0; e <= (R2 > 0 ? Ball<R2>::W : 16); e++) {
                 if (e > wy) break;
                 const bool out_gone = yv - e < 0, in_gone = yv + 1 + e >= g.ny;   // leaving / entering row is outside
-                d += ncols_of(e) * ((out_gone && !in_gone ? 1 : 0) - (in_gone && !out_gone ? 1 : 0));
+                sgn[e] = (out_gone && !in_gone ? 1 : 0) - (in_gone && !out_gone ? 1 : 0);
+                dall += ncols_of(e) * sgn[e];
             }
-            if (d != 0) {
+            int d = dall;
+            if (!xz_in) {   // columns outside the image in x or z hold code 0 in every row: they move nothing
+                if constexpr (R2 > 0) {
+                    d = ball_signed_cols<R2>(x, z, g.nx, g.nz, sgn);
+                } else {
+                    d = 0;
+                    for (int e = 0; e <= wy; e++)
+                        for (int c = gs[e]; c < ge[e]; c++) {
+                            const int co = (int)cols[c];   // (wz + dz) * 256 + 16 + dx
+                            const int dz = co / (kXtCH * kXtRowB) - g.wz, dx = co % (kXtCH * kXtRowB) - kXtHalo;
+                            if ((unsigned)(x + dx) < (unsigned)g.nx && (unsigned)(z + dz) < (unsigned)g.nz) d += sgn[e];
+                        }
+                }
+            }
+            if (dall != 0 || !xz_in) {
                 const unsigned refc = lds_u8(tb + rowoff(t + wy) + g.wz * (kXtCH * kXtRowB) + kXtHalo);   // own voxel
-                if (refc != 0) {   // (a reference value that is not counted shares code 0 with the rows outside)
+                if (refc != 0 && d != 0) {   // (a reference value that is not counted shares code 0 with the rows outside)
                     unsigned* hr = hist + refc * kXtCons + tid;
                     const unsigned h0 = hist[tid], h1 = *hr;
                     hist[tid] = h0 - (unsigned)d;
@@ -907,7 +946,7 @@ xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
                 }
                 dirty = true;
             }
-        } else if (wactive && (!allflat || ycross)) {
+        } else if (wactive && !allflat) {
             unsigned A = 0;            // sum of counters before +1 minus sum of counters before -1
             if constexpr (R2 > 0) {
                 constexpr int W = Ball<R2>::W;
@@ -1137,7 +1176,8 @@ static int xcorr_run(OpGuard& og, Scratch& sc, Image* A, const uint8_t* d_codes,
     unsigned* d_cols = nullptr;
     XcStat* d_vstat = nullptr;
     VX_TRY(sc.alloc(sizeof(XcStat) * nb, &d_vstat));
-    VX_TRY(sc.alloc(sizeof(unsigned) * (cols.size() + 128), &d_cols));
+    const size_t max_places = (size_t)((A->nx + 31) / 32) * ((A->nz + kXtWarps - 1) / kXtWarps) * (size_t)std::max(1, A->ny / 40 + 1);
+    VX_TRY(sc.alloc(sizeof(unsigned) * (cols.size() + 128 + max_places), &d_cols));
     {
         VX_LAUNCH(og.c, og.s, "xc_stat_kernel");
         xc_stat_kernel<<<(nb + 63) / 64, 64, 0, og.st>>>(d_h2, k, nb, d_vstat);
@@ -1193,9 +1233,26 @@ static int xcorr_run(OpGuard& og, Scratch& sc, Image* A, const uint8_t* d_codes,
         nseg = std::max(1, nseg);
         const int seg = (A->ny + nseg - 1) / nseg;
         nseg = (A->ny + seg - 1) / seg;
-        g.nx = A->nx; g.ny = A->ny; g.nz = A->nz; g.k = k;
+        // places (x chunk, plane block * nseg + segment) from the centre of the volume outwards, appended to the
+        // column table so that one copy carries both
+        const int gx = (A->nx + 31) / 32, nzb = (A->nz + kXtWarps - 1) / kXtWarps, gy = nzb * nseg;
+        const size_t places_at = (tcols.size() + 3) & ~(size_t)3;
+        {
+            std::vector<std::pair<float, unsigned>> keyed;
+            keyed.reserve((size_t)gx * gy);
+            for (int by = 0; by < gy; by++)
+                for (int bx = 0; bx < gx; bx++) {
+                    const float fx = (bx + 0.5f) / gx - 0.5f, fz = (by / nseg + 0.5f) / nzb - 0.5f,
+                                fy = (by % nseg + 0.5f) / nseg - 0.5f;
+                    keyed.emplace_back(fx * fx + fz * fz + fy * fy, (unsigned)bx | ((unsigned)by << 16));
+                }
+            std::stable_sort(keyed.begin(), keyed.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+            tcols.resize(places_at, 0u);
+            for (auto& kv : keyed) tcols.push_back(kv.second);
+        }
+        g.nx = A->nx; g.ny = A->ny; g.nz = A->nz; g.nb = nb; g.k = k;
         g.seg = seg; g.nseg = nseg; g.ball = (int)ball;
-        g.ncols = (int)tcols.size(); g.nreal = (int)cols.size();
+        g.ncols = (int)places_at; g.nreal = (int)cols.size();   // (the places follow the columns in tcols)
         g.wx = wx; g.wy = wy; g.wz = wz; g.P = P; g.nchunk = nchunk; g.pitch = pitch;
         // unit spacing and an integer-valued ball: the kernels with the column list compiled in
         auto kern = xcorr_tma_kernel<0>;
@@ -1219,13 +1276,16 @@ static int xcorr_run(OpGuard& og, Scratch& sc, Image* A, const uint8_t* d_codes,
             cudaError_t e = cudaMemcpyAsync(d_cols, tcols.data(), sizeof(unsigned) * tcols.size(), cudaMemcpyHostToDevice, og.st);
             if (e == cudaSuccess)
                 e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
+            if (e == cudaSuccess && (gx > 0xffff || gy > 0xffff || (unsigned long long)gx * gy * nb > 0x7fffffffull)) {
+                rc = fail(VX_E_UNSUPPORTED, "crossCorrelation: %d x %d x %d blocks exceed the launch grid", gx, gy, nb);
+            }
             if (e != cudaSuccess) rc = fail(VX_E_CUDA, "crossCorrelation set-up: %s", cudaGetErrorString(e));
         }
         if (rc == VX_OK) {
-            dim3 grid((A->nx + 31) / 32, ((A->nz + kXtWarps - 1) / kXtWarps) * nseg, nb);
+            dim3 grid((unsigned)((size_t)gx * gy * nb));
             {
                 VX_LAUNCH(og.c, og.s, "xcorr_kernel");
-                kern<<<grid, kXtThreads, smem_tma, og.st>>>(tmap, d_codes, (float*)O->d, d_cols, d_h2, d_vstat, g);
+                kern<<<grid, kXtThreads, smem_tma, og.st>>>(tmap, d_codes, (float*)O->d, d_cols, d_cols + places_at, d_h2, d_vstat, g);
             }
             rc = check_launch("xcorr_kernel");
         }
