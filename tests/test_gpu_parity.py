@@ -461,6 +461,51 @@ def test_deferred_percentile_thresholds_on_codes(ctx, oracle):
         assert np.array_equal(p.numpy().view(np.uint32), want.view(np.uint32))
 
 
+def test_single_comparison_of_a_coded_image(ctx, oracle):
+    """ONE comparison of an image that is read as 16-bit codes -- a 16-bit upload, or a deferred percentile
+    image -- with a constant or a per-volume scalar, possibly negated (`!(a >. c)`, what `filter` asks for),
+    takes the 32-voxels-per-thread kernel: all six comparisons, NaN and out-of-range constants, voxel counts that
+    are not multiples of 32 (volumes share a word of the result), against numpy on the same f32 values and
+    against the interpreter (quantised paths off)."""
+    from voxlogica_b200 import _abi as A
+    rng = np.random.default_rng(131)
+    ops = {"<": (np.less, A.VX_LT), "<=": (np.less_equal, A.VX_LE), ">": (np.greater, A.VX_GT),
+           ">=": (np.greater_equal, A.VX_GE), "==": (np.equal, A.VX_EQ), "!=": (np.not_equal, A.VX_NE)}
+    for shape in [(3, 5, 7, 9), (2, 4, 6, 32), (5, 1, 3, 11)]:
+        for dtype, slope, inter in [(np.int16, 0.25, -3.0), (np.uint16, -0.5, 40.0)]:
+            lo, hi = (-40, 60) if dtype == np.int16 else (0, 90)
+            raw = rng.integers(lo, hi, size=shape).astype(dtype)
+            f = raw.astype(np.float32) * np.float32(slope) + np.float32(inter)
+            img = ctx.upload_scaled(raw, slope, inter)
+            consts = [float(f.flat[3]), float(np.median(f)), -1e9, 1e9, float("nan")]
+            for c in consts:
+                for name, (fn, code) in ops.items():
+                    want = fn(f, np.float32(c)).astype(np.uint8)
+                    assert np.array_equal(ctx.cmp_scalar(img, name, c).numpy(), want), (shape, dtype, name, c)
+                    prog = [(A.VXP_LOAD, 0, 0, 0, 0, 0.0), (A.VXP_CMPS, 1, 0, 0, code, c), (A.VXP_NOT, 2, 1, 0, 0, 0.0)]
+                    assert np.array_equal(ctx.fused(prog, [img]).numpy(), 1 - want), (shape, dtype, "not", name, c)
+            # per-volume scalars (VXP_CMPSB)
+            bs = np.array([[float(f[v].flat[1]) for v in range(shape[0])]], np.float32)
+            prog = [(A.VXP_LOAD, 0, 0, 0, 0, 0.0), (A.VXP_CMPSB, 1, 0, 0, A.VX_GE, 0.0)]
+            want = (f >= bs[0][:, None, None, None]).astype(np.uint8)
+            assert np.array_equal(ctx.fused(prog, [img], bs).numpy(), want), (shape, dtype, "cmpsb")
+            # a deferred percentile image, negated comparison; the interpreter gives the same
+            m = rnd_mask(shape, 0.6, 132)
+            m[0] = 0
+            pw = per_volume(oracle.percentiles, f, m, correction=0.5)
+            for opt in (1, 0):
+                ctx.set_option(A.VX_OPT_QUANTISED_PATHS, opt)
+                try:
+                    p = ctx.percentiles(img, ctx.upload(m), 0.5)
+                    for c in (0.0, 0.5, float(np.unique(pw)[-1]), 1.0):
+                        for name, (fn, code) in list(ops.items())[:4]:
+                            prog = [(A.VXP_LOAD, 0, 0, 0, 0, 0.0), (A.VXP_CMPS, 1, 0, 0, code, c), (A.VXP_NOT, 2, 1, 0, 0, 0.0)]
+                            want = 1 - fn(pw, np.float32(c)).astype(np.uint8)
+                            assert np.array_equal(ctx.fused(prog, [p]).numpy(), want), (shape, dtype, opt, name, c)
+                finally:
+                    ctx.set_option(A.VX_OPT_QUANTISED_PATHS, 1)
+
+
 def test_deferred_image_survives_raw_pointers_to_its_operands(ctx, oracle):
     """vx_device_ptr freezes an image (the caller may write through the pointer): a deferred percentile
     image made before keeps the codes and mask bits it reads; one made after takes the general path"""

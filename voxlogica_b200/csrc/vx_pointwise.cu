@@ -485,6 +485,84 @@ __global__ void pw_break_points_kernel(const __grid_constant__ BreakSpecs B, int
     bscal[(size_t)b.slot * nb + vol] = T;
 }
 
+// ---- one comparison of a 16-bit-coded image with a constant -----------------------------------------
+// `flair <. 0.1` on a 16-bit upload and `percentiles(..) >. c` on a deferred percentile image are ONE
+// comparison of a leaf that is read as 16-bit codes: 2 (+ 1/8) bytes in and 1/8 byte out per voxel.  In
+// the interpreter a thread has one 16-voxel group (32 bytes) in flight and the block 8 KB: these two
+// programs ran at 2.5 TB/s where the f32 threshold, with twice the bytes per thread, reaches 5.  Here a
+// thread takes 32 voxels -- four 16-byte loads issued together, one word of the result's bit form out.
+// RANK: the leaf is a deferred percentile image in rank mode (value = position of the code in the volume's
+// code range, -0.5 outside the mask, against a per-volume break point); otherwise a quantised f32 leaf
+// (value = fl(fl(q * slope) + inter), against the constant or a per-volume scalar).  Same arithmetic as
+// ld_f / cmp16 of the interpreter, so the result is bit-identical.
+struct CodeCmp {
+    const uint4* codes;
+    const unsigned* mask;      // RANK: bit form of the percentile mask
+    const int* qrange;         // RANK: [nb][2] code range of every volume
+    const float* thr;          // per-volume thresholds [nb], or nullptr: imm
+    float imm, slope, inter;
+    unsigned flip;             // RANK: 0x8000 for int16 codes
+    int sgn, incr, nb;
+    unsigned invert;           // 0xffffffff: the program negates the comparison (`!(a >. c)`, what filter asks for)
+    unsigned long long nvox, count;
+    unsigned* out;
+};
+template <bool RANK, int CMP>
+__global__ void __launch_bounds__(kPwThreads)
+code_compare_kernel(const __grid_constant__ CodeCmp a) {
+    const size_t nw = (a.count + 31) / 32;
+    for (size_t w = (size_t)blockIdx.x * kPwThreads + threadIdx.x; w < nw; w += (size_t)gridDim.x * kPwThreads) {
+        const size_t first = w * 32;
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        uint4 q[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) q[j] = first + 8 * j < a.count ? __ldg(a.codes + w * 4 + j) : z4;
+        const unsigned m = RANK ? __ldg(a.mask + w) : 0xffffffffu;
+        unsigned v0 = a.count <= 0xffffffffull ? (unsigned)first / (unsigned)a.nvox : (unsigned)(first / a.nvox);
+        const bool one_volume = first - (size_t)v0 * a.nvox + 31 < a.nvox;
+        if (v0 >= (unsigned)a.nb) v0 = a.nb - 1;
+        float thr = a.thr ? __ldg(a.thr + v0) : a.imm;
+        int lo = 0, hi = 0;
+        if (RANK) { lo = __ldg(a.qrange + 2 * v0); hi = __ldg(a.qrange + 2 * v0 + 1); }
+        const unsigned qw[16] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y, q[1].z, q[1].w,
+                                 q[2].x, q[2].y, q[2].z, q[2].w, q[3].x, q[3].y, q[3].z, q[3].w};
+        unsigned bits = 0;
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+            if (!one_volume) {
+                unsigned v = (unsigned)((first + e) / a.nvox);
+                if (v >= (unsigned)a.nb) v = a.nb - 1;
+                if (a.thr) thr = __ldg(a.thr + v);
+                if (RANK) { lo = __ldg(a.qrange + 2 * v); hi = __ldg(a.qrange + 2 * v + 1); }
+            }
+            const unsigned h = (qw[e >> 1] >> (16 * (e & 1))) & 0xffffu;
+            float x;
+            if (RANK) {
+                const int u = (int)(h ^ a.flip);
+                x = ((m >> e) & 1u) ? (float)(a.incr ? u - lo : hi - u) : -0.5f;
+            } else {
+                x = __fadd_rn(__fmul_rn(a.sgn ? (float)(short)h : (float)h, a.slope), a.inter);
+            }
+            bits |= cmp1(x, thr, CMP) << e;
+        }
+        bits ^= a.invert;
+        // bits past the last voxel of the batch stay 0 (the invariant of the bit form)
+        if (first + 32 > a.count) bits &= (1u << (unsigned)(a.count - first)) - 1u;
+        a.out[w] = bits;
+    }
+}
+template <bool RANK>
+static void launch_code_compare(int cmp, int grid, cudaStream_t st, const CodeCmp& a) {
+    switch (cmp) {
+        case VX_LT: code_compare_kernel<RANK, VX_LT><<<grid, kPwThreads, 0, st>>>(a); break;
+        case VX_LE: code_compare_kernel<RANK, VX_LE><<<grid, kPwThreads, 0, st>>>(a); break;
+        case VX_GT: code_compare_kernel<RANK, VX_GT><<<grid, kPwThreads, 0, st>>>(a); break;
+        case VX_GE: code_compare_kernel<RANK, VX_GE><<<grid, kPwThreads, 0, st>>>(a); break;
+        case VX_EQ: code_compare_kernel<RANK, VX_EQ><<<grid, kPwThreads, 0, st>>>(a); break;
+        default: code_compare_kernel<RANK, VX_NE><<<grid, kPwThreads, 0, st>>>(a); break;
+    }
+}
+
 // ---- host side: validate, allocate registers, launch ---------------------------
 enum { T_NONE = 0, T_B = 1, T_F = 2 };
 
@@ -792,14 +870,45 @@ int run_pointwise(vx_ctx ctx, const vx_op* prog, int n_ops, const vx_img* leaves
     if (ctas < 1) ctas = 1;
     if (ctas > 8) ctas = 8;
     int grid = grid_for(boolean_only ? (P.ngroups + kWideU - 1) / kWideU : P.ngroups, kPwThreads, ctas);
-    {
+    // one comparison of a coded leaf with a constant (or a per-volume scalar): the 32-voxels-per-thread kernel
+    bool code_cmp = false;
+    const bool negated = nd == 2 && P.ops[1].opcode == VXP_NOT && P.ops[1].a_kind == K_REG && P.ops[0].dst >= 0 &&
+                         P.ops[1].a_idx == (uint8_t)P.ops[0].dst && P.ops[1].dst < 0;
+    if ((nd == 1 || negated) && out_type == T_B && (P.ops[0].opcode == VXP_CMPS || P.ops[0].opcode == VXP_CMPSB) &&
+        P.ops[0].a_kind == K_LEAF && g.c->quantised_paths.load()) {
+        const int li = P.ops[0].a_idx;
+        const bool rank = leaf_tab[li] != nullptr && P.leaf_rank[li] != 0;
+        if (rank || (leaf_tab[li] == nullptr && leaf_codes[li] != 0)) {
+            CodeCmp a;
+            memset(&a, 0, sizeof(a));
+            a.codes = reinterpret_cast<const uint4*>(leaf_ptr[li]);
+            a.mask = reinterpret_cast<const unsigned*>(leaf_mask[li]);
+            a.qrange = P.leaf_qrange[li];
+            a.thr = P.ops[0].opcode == VXP_CMPSB ? P.bscal + (size_t)P.ops[0].b_idx * shape->nb : nullptr;
+            a.imm = P.ops[0].imm;
+            a.slope = P.leaf_slope[li]; a.inter = P.leaf_inter[li];
+            a.flip = leaf_flip[li];
+            a.sgn = leaf_codes[li] == 1; a.incr = P.leaf_incr[li]; a.nb = shape->nb;
+            a.nvox = P.nvox; a.count = P.count;
+            a.invert = negated ? 0xffffffffu : 0u;
+            a.out = reinterpret_cast<unsigned*>(o->bits);
+            const int cgrid = grid_for((P.count + 31) / 32, kPwThreads, 8);
+            {
+                VX_LAUNCH(g.c, g.s, "code_compare_kernel");
+                if (rank) launch_code_compare<true>(P.ops[0].aux, cgrid, g.st, a);
+                else launch_code_compare<false>(P.ops[0].aux, cgrid, g.st, a);
+            }
+            code_cmp = true;
+        }
+    }
+    if (!code_cmp) {
         VX_LAUNCH(g.c, g.s, boolean_only ? "boolean_program_kernel" : "pointwise_program_kernel");
         if (boolean_only) boolean_program_kernel<<<grid, kPwThreads, smem, g.st>>>(P);
         else if (def_mode == 0) pointwise_program_kernel<0><<<grid, kPwThreads, smem, g.st>>>(P);
         else if (def_mode == 2) pointwise_program_kernel<2><<<grid, kPwThreads, smem, g.st>>>(P);
         else pointwise_program_kernel<1><<<grid, kPwThreads, smem, g.st>>>(P);
     }
-    int r = check_launch("pointwise_program_kernel");
+    int r = check_launch(code_cmp ? "code_compare_kernel" : "pointwise_program_kernel");
     if (r == VX_OK && d_scal) r = scratch_free(g.c, g.s, d_scal);
     if (r != VX_OK) { drop(o); return r; }
     return g.finish(o, out);
