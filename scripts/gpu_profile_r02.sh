@@ -31,7 +31,7 @@ run pack_bits pack_bits 2 $OPS --only distlt_r=5
 run morph_bits morph_bits 2 $OPS --only near26
 run boolean_program boolean_program 2 $OPS --only and_u8
 run pointwise_threshold pointwise_program 2 $OPS --only threshold
-run pointwise_deferred pointwise_program 2 $OPS --only percentiles_then_cmp_16-bit
+run code_compare code_compare 2 $OPS --only percentiles_then_cmp_16-bit
 run pq_hist pq_hist 2 $OPS --only percentiles_brain_16-bit
 run pq_apply pq_apply 2 $OPS --only percentiles_brain_16-bit
 run xc_bin xc_bin 2 $OPS --only rho5_k100_16-bit

@@ -527,6 +527,31 @@ code_compare_kernel(const __grid_constant__ CodeCmp a) {
         const unsigned qw[16] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y, q[1].z, q[1].w,
                                  q[2].x, q[2].y, q[2].z, q[2].w, q[3].x, q[3].y, q[3].z, q[3].w};
         unsigned bits = 0;
+        if (RANK && (CMP == VX_GE || CMP == VX_LT) && one_volume) {
+            // position >= T on integers: T is -1 (everything passes, voxels outside the mask included) or a
+            // position, and then `position >= T` is one comparison of the code itself with lo + T (hi - T
+            // for a decreasing scaling) and voxels outside the mask fail.  (The float form below needs a
+            // subtraction, a conversion, a select and a comparison per voxel: the kernel was issue-bound.)
+            const int Ti = (int)thr;
+            unsigned ge = 0;
+            if (a.incr) {
+                const int A = lo + Ti;
+#pragma unroll
+                for (int e = 0; e < 32; e++) {
+                    const int u = (int)(((qw[e >> 1] >> (16 * (e & 1))) & 0xffffu) ^ a.flip);
+                    ge |= (u >= A ? 1u : 0u) << e;
+                }
+            } else {
+                const int A = hi - Ti;
+#pragma unroll
+                for (int e = 0; e < 32; e++) {
+                    const int u = (int)(((qw[e >> 1] >> (16 * (e & 1))) & 0xffffu) ^ a.flip);
+                    ge |= (u <= A ? 1u : 0u) << e;
+                }
+            }
+            ge = Ti < 0 ? 0xffffffffu : (ge & m);
+            bits = CMP == VX_GE ? ge : ~ge;
+        } else
 #pragma unroll
         for (int e = 0; e < 32; e++) {
             if (!one_volume) {

@@ -422,8 +422,18 @@ xcorr_direct_kernel(const uint8_t* __restrict__ codes, float* __restrict__ out,
 //    empty: all 6 consumer warps are done with the chunk).  No __syncthreads in the loop.
 //  * flat-region shortcut per WARP: the producer marks every (row, plane) segment whose
 //    in-image bytes all equal one reference code; when all rows and planes a warp's slide
-//    touches are flat its histograms cannot change and the step is a plain store.
-constexpr int kXtWarps = 6;                  // consumer warps = z planes per block
+//    touches are flat its histograms cannot change and the step is a plain store.  Rows above
+//    and below the image count as flat too (they hold nothing but the not-counted code 0): a
+//    column that starts at the top of the image builds its first ball from row counts (81
+//    counter adds instead of 515 for rho = 5), and a slide whose flat window reaches over the
+//    top or bottom moves a KNOWN number of voxels between code 0 and the reference code -- two
+//    counter updates and a closed-form change of the sum of squares.  (Before, every column
+//    paid a full build and ten full slides at its two ends, background or not: 13 of the ~110
+//    busy-step equivalents of an average BraTS column.)
+constexpr int kXtWarps = 6;                  // consumer warps = z planes per block.  (12 per block, one block per SM, the same
+                                             // 12 warps per SM on one ring: 7 % faster where every step is busy -- noise 9.43 ->
+                                             // 8.80 ms per 16 volumes -- but BraTS volumes 3.63 -> 4.05 ms: a block of 12 planes
+                                             // is busy where any of them is, and background columns cost 0.69 instead of 0.54)
 constexpr int kXtCons = kXtWarps * 32;       // histogram owners
 constexpr int kXtThreads = kXtCons + 64;     // + the copy warp and the flag warp
 constexpr int kXtCH = 4;                     // rows per TMA chunk
@@ -596,24 +606,32 @@ __device__ __forceinline__ void xt_init_row(unsigned hbase, unsigned prow, int a
     }
 }
 
-// grid: ceil(nx/32) * ceil(nz/6)*nseg * nb blocks in ONE dimension; block i works on volume i % nb and on the
-// (x chunk, plane block and segment) order[i / nb].  The host sorts that table from the centre of the volume
-// outwards: blocks in the middle of a head slide through texture for their whole column (700 k cycles), blocks
-// in the background skip most of theirs (50 k), and with the blocks in raster order the kernel ended on the
-// heavy blocks of the last volume with most SMs idle.  Block 256 threads.  Dynamic shared memory:
+// grid: (units * 4 * nb) blocks in ONE dimension.  A unit is 2 x chunks by 2 plane blocks (of one y segment);
+// the host sorts the units from the centre of the volume outwards and the blocks run unit by unit, inside a
+// unit volume by volume, the (up to) four places of the unit together: block i works on volume (i / 4) % nb
+// and place order[(i / (4 nb)) * 4 + i % 4] (0xffffffff: the unit has no such place, the block leaves).
+// Why: blocks in the middle of a head slide through texture for their whole column (700 k cycles), blocks in
+// the background skip most of theirs (50 k), and ONE busy block does not fill the shared-memory pipe of its SM
+// (56 % in the block time line against 77 % with two).  In raster order busy and idle blocks shared SMs all
+// along and the kernel ended on the busy blocks of the last volume; sorted, the SMs hold two busy blocks each
+// until the busy blocks of all volumes are done, and the cheap ones fill the end: 3.74 -> 3.61 ms per 16 BraTS
+// volumes.  The four places of a unit share most of their planes, so those come from L2 (with single places
+// interleaved over the volumes the kernel read 6 x the code image from DRAM; four shells of a volume in raster
+// order kept the traffic but lost the gain: 3.74 ms).  Block 256 threads.  Dynamic shared memory:
 //   ring [nchunk][P][4][64] u8 | hist [k+1][192] u32 | h2s [k+1] u32 | cols [ncols] u32 | rowmask [64] u32 |
 //   mbarriers [48] u64 | gs, ge [17] int
 // cols[c] = byte offset of column c inside a chunk relative to (plane = warp, x = lane):
 // (wz+dz)*256 + 16 + dx.   R2 > 0: the ball is Ball<R2> (unit spacing), cols/gs/ge are not used.
 template <int R2>
-__global__ void __launch_bounds__(kXtThreads, 2)
+__global__ void __launch_bounds__(kXtThreads, kXtWarps <= 6 ? 2 : 1)
 xcorr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ codes,
                  float* __restrict__ out, const unsigned* __restrict__ cols_g, const unsigned* __restrict__ order,
                  const unsigned* __restrict__ h2, const XcStat* __restrict__ vstat, const __grid_constant__ XtGeo g) {
     extern __shared__ unsigned char xt_smem_raw[];
-    const unsigned xt_rank = blockIdx.x / (unsigned)g.nb;
-    const int vol = (int)(blockIdx.x - xt_rank * (unsigned)g.nb);
-    const unsigned xt_place = __ldg(order + xt_rank);
+    const unsigned xt_unit = blockIdx.x / (4u * (unsigned)g.nb), xt_rem = blockIdx.x - xt_unit * 4u * (unsigned)g.nb;
+    const int vol = (int)(xt_rem >> 2);
+    const unsigned xt_place = __ldg(order + xt_unit * 4u + (xt_rem & 3u));
+    if (xt_place == 0xffffffffu) return;   // a unit at the edge of the grid of places
     const int xt_bx = (int)(xt_place & 0xffffu), xt_by = (int)(xt_place >> 16);
     // TMA destinations must be 128-byte aligned: align the dynamic window by hand (128 spare bytes)
     unsigned char* xt_smem = xt_smem_raw + ((128u - (smem_u32(xt_smem_raw) & 127u)) & 127u);
@@ -1176,7 +1194,8 @@ static int xcorr_run(OpGuard& og, Scratch& sc, Image* A, const uint8_t* d_codes,
     unsigned* d_cols = nullptr;
     XcStat* d_vstat = nullptr;
     VX_TRY(sc.alloc(sizeof(XcStat) * nb, &d_vstat));
-    const size_t max_places = (size_t)((A->nx + 31) / 32) * ((A->nz + kXtWarps - 1) / kXtWarps) * (size_t)std::max(1, A->ny / 40 + 1);
+    const size_t max_places = 4 * (size_t)((A->nx + 31) / 32 / 2 + 1) * ((A->nz + kXtWarps - 1) / kXtWarps / 2 + 1) *
+                              (size_t)std::max(1, A->ny / 40 + 1);
     VX_TRY(sc.alloc(sizeof(unsigned) * (cols.size() + 128 + max_places), &d_cols));
     {
         VX_LAUNCH(og.c, og.s, "xc_stat_kernel");
@@ -1233,22 +1252,32 @@ static int xcorr_run(OpGuard& og, Scratch& sc, Image* A, const uint8_t* d_codes,
         nseg = std::max(1, nseg);
         const int seg = (A->ny + nseg - 1) / nseg;
         nseg = (A->ny + seg - 1) / seg;
-        // places (x chunk, plane block * nseg + segment) from the centre of the volume outwards, appended to the
-        // column table so that one copy carries both
-        const int gx = (A->nx + 31) / 32, nzb = (A->nz + kXtWarps - 1) / kXtWarps, gy = nzb * nseg;
+        // units (2 x chunks by 2 plane blocks of one segment) from the centre of the volume outwards, four place
+        // slots each (x chunk | (plane block * nseg + segment) << 16, or 0xffffffff), appended to the column
+        // table so that one copy carries both
+        const int gx = (A->nx + 31) / 32, nzb = (A->nz + kXtWarps - 1) / kXtWarps;
+        const int ux = (gx + 1) / 2, uz = (nzb + 1) / 2;
+        const size_t n_units = (size_t)ux * uz * nseg;
         const size_t places_at = (tcols.size() + 3) & ~(size_t)3;
         {
-            std::vector<std::pair<float, unsigned>> keyed;
-            keyed.reserve((size_t)gx * gy);
-            for (int by = 0; by < gy; by++)
-                for (int bx = 0; bx < gx; bx++) {
-                    const float fx = (bx + 0.5f) / gx - 0.5f, fz = (by / nseg + 0.5f) / nzb - 0.5f,
-                                fy = (by % nseg + 0.5f) / nseg - 0.5f;
-                    keyed.emplace_back(fx * fx + fz * fz + fy * fy, (unsigned)bx | ((unsigned)by << 16));
-                }
+            std::vector<std::pair<float, unsigned>> keyed;   // (distance of the unit's centre from the volume's, unit)
+            keyed.reserve(n_units);
+            for (int sg = 0; sg < nseg; sg++)
+                for (int kz = 0; kz < uz; kz++)
+                    for (int kx = 0; kx < ux; kx++) {
+                        const float cx = 0.5f * (2 * kx + std::min(2 * kx + 2, gx)), cz = 0.5f * (2 * kz + std::min(2 * kz + 2, nzb));
+                        const float fx = cx / gx - 0.5f, fz = cz / nzb - 0.5f, fy = (sg + 0.5f) / nseg - 0.5f;
+                        keyed.emplace_back(fx * fx + fz * fz + fy * fy, (unsigned)((sg * uz + kz) * ux + kx));
+                    }
             std::stable_sort(keyed.begin(), keyed.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
             tcols.resize(places_at, 0u);
-            for (auto& kv : keyed) tcols.push_back(kv.second);
+            for (auto& kv : keyed) {
+                const int kx = (int)(kv.second % ux), kz = (int)(kv.second / ux % uz), sg = (int)(kv.second / ux / uz);
+                for (int j = 0; j < 4; j++) {
+                    const int bx = 2 * kx + (j & 1), zb = 2 * kz + (j >> 1);
+                    tcols.push_back(bx < gx && zb < nzb ? (unsigned)bx | ((unsigned)(zb * nseg + sg) << 16) : 0xffffffffu);
+                }
+            }
         }
         g.nx = A->nx; g.ny = A->ny; g.nz = A->nz; g.nb = nb; g.k = k;
         g.seg = seg; g.nseg = nseg; g.ball = (int)ball;
@@ -1276,13 +1305,13 @@ static int xcorr_run(OpGuard& og, Scratch& sc, Image* A, const uint8_t* d_codes,
             cudaError_t e = cudaMemcpyAsync(d_cols, tcols.data(), sizeof(unsigned) * tcols.size(), cudaMemcpyHostToDevice, og.st);
             if (e == cudaSuccess)
                 e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
-            if (e == cudaSuccess && (gx > 0xffff || gy > 0xffff || (unsigned long long)gx * gy * nb > 0x7fffffffull)) {
-                rc = fail(VX_E_UNSUPPORTED, "crossCorrelation: %d x %d x %d blocks exceed the launch grid", gx, gy, nb);
+            if (e == cudaSuccess && (gx > 0xffff || nzb * nseg > 0xffff || (unsigned long long)n_units * 4 * nb > 0x7fffffffull)) {
+                rc = fail(VX_E_UNSUPPORTED, "crossCorrelation: %d x %d x %d blocks exceed the launch grid", gx, nzb * nseg, nb);
             }
             if (e != cudaSuccess) rc = fail(VX_E_CUDA, "crossCorrelation set-up: %s", cudaGetErrorString(e));
         }
         if (rc == VX_OK) {
-            dim3 grid((unsigned)((size_t)gx * gy * nb));
+            dim3 grid((unsigned)(n_units * 4 * nb));
             {
                 VX_LAUNCH(og.c, og.s, "xcorr_kernel");
                 kern<<<grid, kXtThreads, smem_tma, og.st>>>(tmap, d_codes, (float*)O->d, d_cols, d_cols + places_at, d_h2, d_vstat, g);
