@@ -258,6 +258,22 @@ def bind_to_gpu_numa(local: int):
         return f"unavailable ({type(e).__name__}: {e})"
 
 
+def xcorr_note():
+    """what binds the dominant kernel, with the figures of the committed ncu capture"""
+    txt = "xcorr_kernel is bound by the shared-memory LSU pipe, not by HBM (SURVEY.md 8d); the fraction against HBM is " \
+          "reported as the contract requires"
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r02_xcorr_ncu_full.json")))["captures"][0]
+        f = lambda k: float(cap[k]["value"])
+        txt += (" (ncu, profiles/r02_xcorr_ncu_full.json: %.1f%% of peak shared-memory wavefronts, %.0f%% issue active, "
+                "DRAM %.1f%%)" % (f("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+                                  f("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                                  f("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")))
+    except Exception:
+        pass
+    return txt
+
+
 # --------------------------------------------------------------------------------- slab leg (N > 1)
 def slab_leg(ctx, dist, rank, world, local):
     """BASELINE config 5b: ONE oversized volume slab-decomposed along z over the N ranks, after the
@@ -686,9 +702,7 @@ def run_ours(args):
                      "how": "CUDA events around every launch of 4 untimed single-stream steps run right after "
                             "the timed region (kernels_serial); the timed region carries no per-kernel events",
                      "traffic_unit": "bytes per launch (dram read+write, ncu --set full, profiles/traffic.json)",
-                     "note": "xcorr_kernel is bound by the shared-memory LSU pipe (ncu, profiles/r02_xcorr_ncu_full.json: "
-                             "76.9% of peak LSU wavefronts, 51% issue active, DRAM 2%), not by HBM (SURVEY.md 8d); the fraction "
-                             "against HBM is reported as the contract requires" if name == "xcorr_kernel" else ""},
+                     "note": xcorr_note() if name == "xcorr_kernel" else ""},
         "kernels": kernels,
         "kernels_serial": {"note": "one host thread / one stream, 4 untimed steps after the timed region: "
                                    "per-launch durations without cross-stream sharing of the SMs; "
