@@ -621,6 +621,7 @@ def run_ours(args):
         del flair
 
     slab = None
+    by_rank = None
     if dist is not None and not args.no_slab:
         del pins_in, pins_out
         try:
@@ -629,6 +630,9 @@ def run_ours(args):
             slab = {"error": f"{type(e).__name__}: {e}"}
     if dist is not None:
         t = torch.tensor([ms, ms_e2e], device=f"cuda:{local}", dtype=torch.float64)
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        by_rank = [[round(float(x[0]) / args.steps, 3), round(float(x[1]) / args.steps, 3)] for x in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
         n = torch.tensor([launches], device=f"cuda:{local}", dtype=torch.int64)
@@ -711,6 +715,7 @@ def run_ours(args):
         "clocks": clocks,
         "cpu_baseline": cb,
         "slab": slab,
+        "ms_per_step_by_rank": by_rank,   # [resident, end to end] of every rank; value and e2e use the slowest
         "gtv_voxels_last_step": [float(v) for v in (vols if vols is not None else [])][:4],
     }
     print(json.dumps(line), flush=True)
