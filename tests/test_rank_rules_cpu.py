@@ -61,3 +61,29 @@ def test_fallback_only_for_runs_crossing_a_warp():
     assert ranks_by_warp_rules(keys)[2] == 0
     keys = np.zeros(100, np.uint32)                         # one run over four warps: inner warps search both ways
     assert ranks_by_warp_rules(keys)[2] > 0
+
+
+def test_rank_mode_comparison_on_integers():
+    """code_compare_kernel's rank mode, restated.  The interpreter decides `table[code] OP c` of a deferred
+    percentile image on float positions: x = inside the mask ? float(position of the code in the volume's code
+    range, in value order) : -0.5, result = x >= T (GT, GE) or x < T (LT, LE) with the break point T = -1 or a
+    position.  The fast kernel compares the code itself: for T >= 0  `position >= T`  is  `code >= lo + T`
+    (increasing scaling) or `code <= hi - T` (decreasing), voxels outside the mask fail; for T = -1 everything
+    passes.  Both forms must agree for every code, mask bit, direction, flip and break point."""
+    rng = np.random.default_rng(17)
+    for incr in (True, False):
+        for flip in (0, 0x8000):
+            raw = rng.integers(0, 65536, size=4000).astype(np.int64)         # the 16 bits as stored
+            u = raw ^ flip                                                    # position order of the codes
+            lo, hi = int(u.min()), int(u.max())
+            m = rng.random(raw.size) < 0.6
+            for T in (-1, 0, 1, 17, (hi - lo) // 2, hi - lo, hi - lo + 1, 65535):
+                pos = (u - lo) if incr else (hi - u)
+                x = np.where(m, pos.astype(np.float32), np.float32(-0.5))
+                ge_float = x >= np.float32(T)
+                if T < 0:
+                    ge_int = np.ones(raw.size, bool)
+                else:
+                    ge_int = ((u >= lo + T) if incr else (u <= hi - T)) & m
+                assert np.array_equal(ge_float, ge_int), (incr, flip, T)
+                assert np.array_equal(x < np.float32(T), ~ge_int), (incr, flip, T)
