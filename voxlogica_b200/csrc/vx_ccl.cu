@@ -469,56 +469,40 @@ ccl_seed_kernel(const unsigned* __restrict__ seed, unsigned* __restrict__ P, con
 enum SelMode { SEL_THROUGH = 0, SEL_LABELS = 1, SEL_MAXVOL = 2 };
 
 // ---- 4. select -----------------------------------------------------------------------------
-template <int MODE>
+// u32 labels (first voxel of the root + 1): one word of the mask per thread, 128 bytes out
 __global__ void __launch_bounds__(kCclThreads)
-ccl_select_kernel(const unsigned* __restrict__ P, const unsigned* __restrict__ bits, const unsigned* __restrict__ wbase,
-                  void* out_, const unsigned* __restrict__ cnt, const unsigned* __restrict__ vmax,
-                  const unsigned* __restrict__ npos, Geo g) {
+ccl_labels_kernel(const unsigned* __restrict__ P, const unsigned* __restrict__ bits, const unsigned* __restrict__ wbase,
+                  unsigned* __restrict__ out, const unsigned* __restrict__ npos, Geo g) {
     const WordPos p = word_pos(g);
     if (!p.ok) return;
     const unsigned m = __ldg(bits + p.wid);
     unsigned id = m ? __ldg(wbase + p.wid) : 0u;
     const int x0 = p.w * 32;
-    unsigned rest = m, outbits = 0;
-    if (MODE == SEL_LABELS) {
-        unsigned* dst = reinterpret_cast<unsigned*>(out_) + p.row * g.nx + (size_t)x0;
-        const int lim = min(32, g.nx - x0);
-        unsigned lab[32];
+    unsigned rest = m;
+    unsigned* dst = out + p.row * g.nx + (size_t)x0;
+    const int lim = min(32, g.nx - x0);
+    unsigned lab[32];
 #pragma unroll
-        for (int b = 0; b < 32; b++) lab[b] = 0;
-        while (rest) {
-            const int st = __ffs(rest) - 1;
-            const unsigned sm = seg_mask(m, st);
-            rest &= ~sm;
-            const unsigned r = __ldg(npos + find_root(P, id++)) + 1u;
-#pragma unroll
-            for (int b = 0; b < 32; b++)
-                if ((sm >> b) & 1u) lab[b] = r;
-        }
-        if ((g.nx & 3) == 0) {
-#pragma unroll
-            for (int q = 0; q < 8; q++)
-                if (4 * q < lim)
-                    reinterpret_cast<uint4*>(dst)[q] =
-                        make_uint4(lab[4 * q], lab[4 * q + 1], lab[4 * q + 2], lab[4 * q + 3]);
-        } else {
-#pragma unroll
-            for (int b = 0; b < 32; b++)
-                if (b < lim) dst[b] = lab[b];
-        }
-        return;
-    }
+    for (int b = 0; b < 32; b++) lab[b] = 0;
     while (rest) {
         const int st = __ffs(rest) - 1;
         const unsigned sm = seg_mask(m, st);
         rest &= ~sm;
-        const unsigned r = find_root(P, id++);
-        bool keep;
-        if (MODE == SEL_THROUGH) keep = (__ldcg(P + r) & kFlag) != 0;
-        else keep = cnt[r] == vmax[p.vol];
-        if (keep) outbits |= sm;
+        const unsigned r = __ldg(npos + find_root(P, id++)) + 1u;
+#pragma unroll
+        for (int b = 0; b < 32; b++)
+            if ((sm >> b) & 1u) lab[b] = r;
     }
-    flat_store_row_word(reinterpret_cast<unsigned*>(out_), p.row, p.w, g.nx, outbits, g.align16 != 0);
+    if ((g.nx & 3) == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            if (4 * q < lim)
+                reinterpret_cast<uint4*>(dst)[q] = make_uint4(lab[4 * q], lab[4 * q + 1], lab[4 * q + 2], lab[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int b = 0; b < 32; b++)
+            if (b < lim) dst[b] = lab[b];
+    }
 }
 
 // boolean results (through, maxvol): four words per thread
@@ -859,8 +843,7 @@ int32_t vx_components(vx_ctx ctx, vx_img a, int32_t conn, vx_img* out) {
     if (r == VX_OK) {
         {
             VX_LAUNCH(og.c, og.s, "ccl_select_kernel");
-            ccl_select_kernel<SEL_LABELS><<<cb.grid, kCclThreads, 0, og.st>>>(cb.P, cb.bits, cb.wbase, O->d, nullptr, nullptr,
-                                                                             npos, cb.g);
+            ccl_labels_kernel<<<cb.grid, kCclThreads, 0, og.st>>>(cb.P, cb.bits, cb.wbase, reinterpret_cast<unsigned*>(O->d), npos, cb.g);
         }
         r = check_launch("ccl_select_kernel");
     }
