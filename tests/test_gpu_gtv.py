@@ -130,3 +130,13 @@ def test_specs_from_files(ctx, oracle, tmp_path):
     ref = gtv_oracle(oracle, vol)
     got, sp = vio.read_nifti(str(tmp_path / "gtv.nii.gz"))
     assert np.array_equal(got.astype(np.uint8), ref["gtv"]) and it.printed["gtvVolume"][0] == ref["gtv"].sum()
+    # the same spec from a 16-bit file with scl_slope, as a scanner stores it: run_file sends the int16 voxels
+    # (vx_upload_scaled), the operators take their code paths, the result is that of the f32 values
+    from voxlogica_b200.synth import brats_like_int16, int16_to_f32
+    raw, slope = brats_like_int16(seed=12, shape=(40, 64, 72))
+    vio.write_nifti(str(tmp_path / "flair.nii.gz"), raw, slope=float(slope))
+    it = run_file(ctx, str(tmp_path / "gtv.imgql"))
+    ref = gtv_oracle(oracle, int16_to_f32(raw, slope))
+    got, sp = vio.read_nifti(str(tmp_path / "gtv.nii.gz"))
+    assert np.array_equal(got.astype(np.uint8), ref["gtv"]) and it.printed["gtvVolume"][0] == ref["gtv"].sum()
+    assert ref["gtv"].sum() > 0

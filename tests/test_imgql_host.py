@@ -331,6 +331,50 @@ def test_nifti_raw_reader_keeps_file_dtype_and_scaling(tmp_path):
     assert np.array_equal(arr, a.astype(np.float32))
 
 
+def test_run_file_sends_16_bit_files_as_16_bits(tmp_path):
+    """run_file loads a 16-bit NIfTI file (int16 / uint16 + scl_slope / scl_inter, what scanners and BraTS
+    store) with upload_scaled -- the file's own voxels and the header's scaling -- and everything else with
+    upload; write_nifti stores the scaling it is given.  (A recording stand-in for the device.)"""
+    from voxlogica_b200 import imgql, io
+    from voxlogica_b200.ops import Image
+
+    calls = []
+
+    class FakeImage(Image):
+        __slots__ = ()
+
+        def __init__(self):
+            self.ctx, self.handle = None, 1
+
+        def __del__(self):
+            pass
+
+    class FakeCtx:
+        def upload_scaled(self, raw, slope, inter=0.0, spacing=None):
+            calls.append(("scaled", raw.dtype, raw.shape, slope, inter, tuple(spacing)))
+            return FakeImage()
+
+        def upload(self, arr, spacing=None, batched=None):
+            calls.append(("f32", arr.dtype, arr.shape, tuple(spacing)))
+            return FakeImage()
+
+    rng = np.random.default_rng(5)
+    spec = 'load a = "a.nii.gz"\nlet x = intensity(a)\n'
+    (tmp_path / "s.imgql").write_text(spec)
+    for dtype, slope, inter, want in ((np.int16, 1.0 / 4095.0, 0.0, "scaled"), (np.uint16, 0.5, -3.0, "scaled"),
+                                      (np.float32, 1.0, 0.0, "f32"), (np.uint8, 1.0, 0.0, "f32")):
+        vol = rng.integers(0, 200, size=(3, 4, 5)).astype(dtype)
+        io.write_nifti(str(tmp_path / "a.nii.gz"), vol, (1.0, 2.0, 0.5), slope=slope, inter=inter)
+        raw, s2, i2, sp = io.read_nifti_raw(str(tmp_path / "a.nii.gz"))
+        assert np.array_equal(raw, vol) and s2 == np.float32(slope) and i2 == np.float32(inter) and sp == (1.0, 2.0, 0.5)
+        calls.clear()
+        imgql.run_file(FakeCtx(), str(tmp_path / "s.imgql"))
+        assert len(calls) == 1 and calls[0][0] == want, calls
+        if want == "scaled":
+            assert calls[0][1] == dtype and calls[0][2] == (3, 4, 5) and calls[0][3] == np.float32(slope) \
+                   and calls[0][4] == np.float32(inter) and calls[0][5] == (1.0, 2.0, 0.5)
+
+
 # ------------------------------------------------------------------ GC policy of the driver (no GPU)
 class _CountedImage:
     """numpy-backed stand-in for an HBM image that counts how many are alive"""

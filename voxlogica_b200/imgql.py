@@ -797,7 +797,15 @@ def run_file(ctx: Context, path: str, conn: int = 26) -> Interpreter:
     spacing = {}
 
     def loader(name):
-        chans = vio.load_image(os.path.join(base, name))
+        full = os.path.join(base, name)
+        if full.lower().endswith((".nii", ".nii.gz")):
+            # a 16-bit file travels as 16 bits: half the PCIe bytes, the same f32 image, and the operators
+            # that rank or bin its values take their counting paths (vx_upload_scaled keeps the codes)
+            raw, slope, inter, sp = vio.read_nifti_raw(full)
+            if raw.dtype in (np.int16, np.uint16):
+                spacing["sp"] = sp
+                return Loaded({"intensity": ctx.upload_scaled(raw, slope, inter, spacing=sp)})
+        chans = vio.load_image(full)
         out = {}
         for k, (arr, sp) in chans.items():
             out[k] = ctx.upload(arr, spacing=sp)

@@ -81,8 +81,9 @@ def read_nifti_raw(path: str):
     return data, float(slope), float(inter), sp
 
 
-def write_nifti(path: str, arr: np.ndarray, spacing=(1.0, 1.0, 1.0)) -> None:
-    """arr: [nz][ny][nx] (or [ny][nx]); uint8 / int16 / int32 / float32 / float64."""
+def write_nifti(path: str, arr: np.ndarray, spacing=(1.0, 1.0, 1.0), slope: float = 1.0, inter: float = 0.0) -> None:
+    """arr: [nz][ny][nx] (or [ny][nx]); uint8 / int16 / int32 / float32 / float64.  ``slope`` / ``inter`` go to the
+    header's scl_slope / scl_inter (value = voxel * slope + inter), as scanners store 12-bit data in int16 files."""
     a = np.ascontiguousarray(arr)
     if a.ndim == 2:
         a = a[None]
@@ -99,7 +100,7 @@ def write_nifti(path: str, arr: np.ndarray, spacing=(1.0, 1.0, 1.0)) -> None:
     struct.pack_into("<hh", hdr, 70, _NIFTI_CODES[a.dtype], a.dtype.itemsize * 8)
     struct.pack_into("<8f", hdr, 76, 1.0, float(spacing[0]), float(spacing[1]), float(spacing[2]), 1.0, 1.0, 1.0, 1.0)
     struct.pack_into("<f", hdr, 108, 352.0)
-    struct.pack_into("<ff", hdr, 112, 1.0, 0.0)
+    struct.pack_into("<ff", hdr, 112, float(slope), float(inter))
     hdr[123] = 2  # xyzt_units: millimetres
     struct.pack_into("<hh", hdr, 252, 0, 2)  # qform_code 0, sform_code 2 (aligned)
     struct.pack_into("<4f", hdr, 280, float(spacing[0]), 0.0, 0.0, 0.0)
