@@ -9,12 +9,13 @@ of synthetic BraTS-shaped volumes (240x240x155 f32, SURVEY.md section 8d config 
 GPU, driven through the ImgQL driver -> ctypes -> libvoxcuda.so (the C ABI).
   value : volumes/s with the batch already resident in HBM (weak scaling: every rank
           owns its own batch; the path shards by volume, no data-path collective).
-  e2e   : the same with the batch in pinned HOST memory: H2D of the f32 volumes and D2H
-          of the u8 GTV masks inside the timed region.
+  e2e   : the same with the batch in pinned HOST memory: every step's int16 voxels (what a
+          NIfTI file holds) go host -> device and its GTV masks come back as bits, inside the
+          timed region; one host thread uploads ahead of the analysis threads (--prefetch).
   roofline     : dominant kernel by device time, algorithmic bytes / CUDA-event time
                  against the measured HBM copy peak (MEASURED_PEAKS.json).
   cpu_baseline : the CPU oracle (a port: the reference implementation is not mounted)
-                 timed on this box's host cores on a bounded sample.
+                 timed on this box's host cores on one full-size volume.
 One JSON line on stdout (rank 0).
 """
 from __future__ import annotations
@@ -49,6 +50,7 @@ ALG_BYTES = {
     # union-find kernels as launched by `through`: bits in/out, node ids are 4 bytes per 32-voxel word
     "ccl_nodes_kernel": 0.375, "ccl_merge_kernel": None, "ccl_flatten_kernel": None,
     "ccl_select_kernel": 0.25, "ccl_seed_kernel": 0.25,
+    "code_compare_kernel": 2.25,     # 16-bit codes (+ mask bits) in, result bits out
     "xc_bin_kernel": 3.0, "xc_region_hist_kernel": 0.125, "pc_compact_kernel": 4.125,
     # the sort kernels move 8-byte pairs of the MASKED voxels only: no per-voxel figure
     "pc_rank_kernel": None, "rs_hist_kernel": None, "rs_scatter_kernel": None, "rs_rowscan_kernel": None,
@@ -732,10 +734,9 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="BraTS volumes per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--threads", type=int, default=2,
-                    help="host threads (= CUDA streams of the library) that take the steps in turn.  Two: one step's "
-                         "upload overlaps the other's kernels; with three or more, two uploads share the PCIe link and the "
-                         "one the GPU is waiting for arrives later (measured: e2e 1994 volumes/s with 2, 1716 with 3, "
-                         "1622 with 4 or 6; the resident number is the same 2230-2270 for all)")
+                    help="host threads (= CUDA streams of the library) that take the steps in turn: the kernels of one "
+                         "step fill the gaps and tails of the other's (three or four change nothing: the device is "
+                         "busy).  In the end-to-end leg these are the analysis threads; see --prefetch")
     ap.add_argument("--prefetch", type=int, default=2,
                     help="end-to-end leg: uploaded batches the uploading host thread keeps ahead of the analysis threads "
                          "(0: every analysis thread uploads its own step's batch, the round-1 scheme)")
